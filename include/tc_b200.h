@@ -1,0 +1,173 @@
+/* tc_b200.h - C ABI of the B200 correction engine (libtc_b200.so).
+ *
+ * The reference (mortazavilab/TranscriptClean v2.1) has no FFI: its seam is the Python call
+ *   batch_correct(sam_transcripts, options, refs, outfiles, buffer_size)   TranscriptClean.py:350-403
+ * which loops correct_transcript(line, options, refs)                       TranscriptClean.py:406-460.
+ * This library replaces everything between "N parsed SAM records in" and "corrected
+ * records / log counters / TE records out" of that call.  Plain pointers and sizes only.
+ *
+ * Conventions: every function returns 0 on success, a negative TC_E_* code otherwise;
+ * tc_last_error() gives the text.  One context per GPU, one host thread per context.
+ * All `const T*` inputs are HOST pointers unless the function name ends in `_device`.
+ * Output buffers are owned by the context (pinned host memory) and stay valid until the next
+ * tc_correct_batch / tc_dryrun_batch / tc_ctx_destroy on that context.
+ */
+#ifndef TC_B200_H
+#define TC_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tc_ctx tc_ctx;
+
+enum {
+    TC_OK = 0,
+    TC_E_CUDA = -1,       /* CUDA runtime error (no device, OOM, launch failure) */
+    TC_E_ARG = -2,        /* bad argument */
+    TC_E_STATE = -3,      /* call order (e.g. batch before genome) */
+    TC_E_INPUT = -4       /* a read the engine flags as unsupported (see TC_ST_ERR_*) */
+};
+
+/* options.maxLenIndel / maxSJOffset / correct* of the reference (TranscriptClean.py:100-126),
+ * plus the two pyranges.nearest() semantics the reference's tests leave unpinned. */
+typedef struct {
+    int32_t max_len_indel;       /* --maxLenIndel, default 5 */
+    int32_t max_sj_offset;       /* --maxSJOffset, default 5 */
+    int32_t correct_mismatches;  /* --correctMismatches true/false */
+    int32_t correct_indels;      /* --correctIndels */
+    int32_t correct_sjs;         /* --correctSJs (only effective when junctions are loaded) */
+    int32_t sj_ignore_strand;    /* 0: nearest site on the read's strand (default); 1: any strand */
+    int32_t sj_tie_right;        /* 0: equidistant -> lower coordinate (default); 1: higher */
+    int32_t reserved;
+} tc_options;
+
+/* per-read status word */
+enum {
+    TC_ST_CLASS_MASK = 3u,        /* 0 primary, 1 unmapped, 2 non-primary   (TC.py:1570-1575) */
+    TC_ST_FALLBACK = 1u << 2,     /* exception path: original read is output (TC.py:450-456) */
+    TC_ST_CIGAR_REWRITTEN = 1u << 3, /* a corrector re-serialised the CIGAR; else verbatim input */
+    TC_ST_NMMD_DEVICE = 1u << 4,  /* NM/MD come from the engine (nm[], md[]); else input tags */
+    TC_ST_NMMD_NONE = 1u << 5,    /* NM/MD are None (alignment ran past the contig end) */
+    TC_ST_JM_DEVICE = 1u << 6,    /* jM must be rendered from jm[]; else input tag */
+    TC_ST_JI_DEVICE = 1u << 7,    /* jI must be rendered from ji[]; else input tag */
+    TC_ST_CANONICAL = 1u << 8,    /* transcript.isCanonical */
+    TC_ST_ALL_ANNOT = 1u << 9,    /* transcript.allJnsAnnotated */
+    TC_ST_ERR_INTRON = 1u << 10,  /* junction rescue drove an intron length <= 0 (unsupported) */
+    TC_ST_ERR_MERGE = 1u << 11    /* dry run only: MD/CIGAR merge ran off a list (reference crashes) */
+};
+
+/* indices into counters[10*i + k]; -1 encodes the reference's "NA" (TC.py:1577-1586) */
+enum { TC_C_COR_DEL, TC_C_UNC_DEL, TC_C_VAR_DEL, TC_C_COR_INS, TC_C_UNC_INS, TC_C_VAR_INS,
+       TC_C_COR_MM, TC_C_UNC_MM, TC_C_COR_SJ, TC_C_UNC_SJ };
+
+/* one row of the .TE.log (TC.py:911-936, 1017-1046, 1119-1134, 1227-1228, 1650-1668) */
+typedef struct {
+    int32_t a;        /* Mismatch: position; Insertion/Deletion: g-1; NC_SJ: intron start */
+    int32_t b;        /* Insertion/Deletion: g+size-1; NC_SJ: intron end; Mismatch: unused */
+    int32_t size;
+    uint8_t type;     /* 0 Mismatch 1 Insertion 2 Deletion 3 NC_SJ_boundary */
+    uint8_t status;   /* 0 Corrected 1 Uncorrected */
+    uint8_t reason;   /* 0 NA 1 VariantMatch 2 TooLarge 3 TooFarFromAnnotJn 4 Other 5 DryRun */
+    uint8_t pad;
+} tc_te;
+
+/* Columnar batch of SAM records (what Transcript.__init__ parses, transcript.py:10-72). */
+typedef struct {
+    int64_t n_reads;
+    const int32_t* flag;      /* FLAG */
+    const int32_t* chrom;     /* index of RNAME in the loaded genome, -1 for '*' */
+    const int32_t* pos;       /* POS, 1-based */
+    const uint8_t* tags;      /* bit0 NM present, bit1 MD present, bit2 jM present, bit3 jI present */
+    const int64_t* seq_off;   /* n+1 */
+    const uint8_t* seq;       /* SEQ bytes (ASCII) */
+    const int64_t* cig_off;   /* n+1 */
+    const uint8_t* cig_op;    /* CIGAR op letters */
+    const int32_t* cig_len;   /* CIGAR op lengths */
+    const int64_t* md_off;    /* n+1 */
+    const uint8_t* md;        /* value of the MD tag (third ':' piece), when present */
+    const int64_t* ji_off;    /* n+1 */
+    const int32_t* ji;        /* integers of the input jI tag, when present */
+} tc_batch_in;
+
+typedef struct {
+    int64_t n_reads;
+    const uint32_t* status;   /* n */
+    const int32_t* counters;  /* 10 n */
+    const int32_t* nm;        /* n; valid with TC_ST_NMMD_DEVICE */
+    const int64_t* seq_off;   /* n+1 */
+    const uint8_t* seq;
+    const int64_t* cig_off;   /* n+1 */
+    const uint8_t* cig_op;
+    const int32_t* cig_len;
+    const int64_t* md_off;    /* n; start of the read's MD value in md[] (arbitrary order) */
+    const int32_t* md_len;    /* n */
+    const uint8_t* md;
+    const int64_t* jn_off;    /* n+1; junction objects of the read */
+    const int8_t* jm;         /* motif codes */
+    const int32_t* ji;        /* 2 per junction */
+    const int64_t* te_off;    /* n+1 */
+    const tc_te* te;          /* in reference order (stage order, positional inside a stage) */
+} tc_batch_out;
+
+/* device timing of the last batch call, milliseconds (CUDA events on the context's stream) */
+typedef struct {
+    float h2d_ms, kernels_ms, d2h_ms;
+    float k_nmmd_init_ms, k_measure_ms, k_plan_ms, k_junction_ms, k_emit_ms;
+    int32_t launches;         /* kernels of this library launched by the call */
+    int32_t md_pool_retries;
+    int64_t h2d_bytes, d2h_bytes;
+} tc_timing;
+
+tc_ctx* tc_ctx_create(int device);
+void tc_ctx_destroy(tc_ctx* ctx);
+const char* tc_last_error(tc_ctx* ctx);     /* ctx may be NULL: error of the failed create */
+int tc_ctx_set_options(tc_ctx* ctx, const tc_options* opts);
+void* tc_ctx_stream(tc_ctx* ctx);           /* cudaStream_t the context launches on */
+
+/* refs.genome (pyfaidx.Fasta in the reference, TC.py:221): 2-bit base plane (16 bases per
+ * word, base i in bits 2*(i%16), A=0 C=1 G=2 T=3), lower-case plane (32 bases per word), and
+ * literal runs for every base outside ACGTacgt.  chrom_off[c] is the contig's first base in
+ * the planes (a multiple of 64). */
+int tc_ctx_load_genome(tc_ctx* ctx, int32_t n_chrom, const int64_t* chrom_len,
+                       const int64_t* chrom_off, int64_t n_bases_padded,
+                       const uint32_t* bases2, const uint32_t* lower1,
+                       int64_t n_exc, const int64_t* exc_start, const int64_t* exc_end,
+                       const uint8_t* exc_byte);
+
+/* refs.donors / refs.acceptors / refs.sjAnnot (processSpliceAnnotation, TC.py:666-766).
+ * *_s: sorted keys (chrom<<33 | strand<<32 | pos0), strand 0 '+', 1 '-';
+ * *_u: sorted, de-duplicated keys (chrom<<32 | pos0);
+ * annotated junctions: sorted pairs (k1 = chrom<<32 | start, k2 = end<<1 | strand). */
+int tc_ctx_load_junctions(tc_ctx* ctx, int64_t n_don_s, const uint64_t* don_s,
+                          int64_t n_acc_s, const uint64_t* acc_s,
+                          int64_t n_don_u, const uint64_t* don_u,
+                          int64_t n_acc_u, const uint64_t* acc_u,
+                          int64_t n_annot, const uint64_t* ann_k1, const uint64_t* ann_k2);
+
+/* refs.snps / refs.insertions / refs.deletions (processVCF, TC.py:769-856).
+ * snp: sorted keys (chrom<<32 | POS), one row per ALT base.
+ * ins: rows sorted by (key = chrom<<32 | POS, size), allele bytes in CSR form.
+ * del: rows sorted by (key, size). */
+int tc_ctx_load_variants(tc_ctx* ctx, int64_t n_snp, const uint64_t* snp_key, const uint8_t* snp_alt,
+                         int64_t n_ins, const uint64_t* ins_key, const int32_t* ins_size,
+                         const int64_t* ins_aoff, const uint8_t* ins_bytes,
+                         int64_t n_del, const uint64_t* del_key, const int32_t* del_size);
+
+/* batch_correct() minus text rendering: host columns in, host columns out (H2D, kernels, D2H). */
+int tc_correct_batch(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out);
+/* dryRun() (TC.py:1615-1678): only status, counters, te_off, te are filled. */
+int tc_dryrun_batch(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out);
+
+/* The same work split for device-resident measurement: upload once, run many, download. */
+int tc_batch_upload(tc_ctx* ctx, const tc_batch_in* in);
+int tc_batch_run(tc_ctx* ctx, int dry_run);
+int tc_batch_download(tc_ctx* ctx, tc_batch_out* out);
+
+int tc_get_timing(tc_ctx* ctx, tc_timing* t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

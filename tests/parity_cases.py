@@ -1,0 +1,67 @@
+"""Parity checks shared by the CPU (hostsim) and GPU test modules: every check takes an engine
+and compares the product pipeline with (a) outputs of the unmodified reference stored under
+tests/golden and (b) the oracle on freshly generated seeded cases."""
+import goldens
+import pipeline
+import synth
+from transcriptclean_b200.genome import GenomeImage
+
+
+def check_fixture(engine, rec):
+    gi = GenomeImage.from_windows(rec["chrom_len"], rec["windows"])
+    have_sj = len(rec["sj_rows"]) > 0
+    sjf, vcf = pipeline.write_tables(rec["sj_rows"] if have_sj else None, rec["vcf_rows"])
+    got = pipeline.product_texts(engine, gi, rec["lines"], sjf, vcf, rec["opts"])
+    d = pipeline.first_diff(got, rec["expected"])
+    assert d is None, d
+    got = pipeline.product_texts(engine, gi, rec["lines"], None, None, {}, dry=True)
+    d = pipeline.first_diff(got, rec["expected_dry"])
+    assert d is None, d
+    if rec["answer_matches"]:
+        assert got is not None and pipeline.product_texts(engine, gi, rec["lines"], sjf, vcf, rec["opts"])["sam"].split() \
+            == rec["ref_answer_line"].split()
+
+
+def check_synth_golden(engine, seed):
+    rec = goldens.load_synth(seed)
+    gi = GenomeImage.from_dict(rec["genome"])
+    sjf, vcf = pipeline.write_tables(rec["sj_rows"], rec["vcf_rows"])
+    for run in rec["runs"]:
+        got = pipeline.product_texts(engine, gi, rec["lines"], sjf if run["use_sj"] else None,
+                                     vcf if run["use_vcf"] else None, run["opts"])
+        d = pipeline.first_diff(got, run["expected"])
+        assert d is None, (run["opts"], d)
+    got = pipeline.product_texts(engine, GenomeImage.from_dict(rec["dry_genome"]), rec["dry_lines"], None, None, {}, dry=True)
+    d = pipeline.first_diff(got, rec["expected_dry"])
+    assert d is None, d
+
+
+MODES = (
+    (dict(), True, False),
+    (dict(), True, True),
+    (dict(primaryOnly=True, correctMismatches=False), False, False),
+    (dict(canonOnly=True, maxSJOffset=8, maxLenIndel=3), True, True),
+    (dict(correctIndels=False), True, True),
+    (dict(correctSJs=False), True, True),
+)
+UNPINNED_MODES = (
+    (dict(sjIgnoreStrand=True, sjTieRight=True), True, True),
+    (dict(sjIgnoreStrand=False, sjTieRight=True), True, False),
+    (dict(sjIgnoreStrand=True, sjTieRight=False), True, False),
+)
+
+
+def check_generated(engine, seed, n_reads=150, unpinned=False, **kw):
+    case = synth.make_case(seed, n_reads=n_reads, unpinned=unpinned, **kw)
+    sjf, vcf = pipeline.write_tables(case.sj_rows, case.vcf_rows)
+    gi = GenomeImage.from_dict(case.genome)
+    for opts, us, uv in (MODES + UNPINNED_MODES if unpinned else MODES):
+        got = pipeline.product_texts(engine, gi, case.lines, sjf if us else None, vcf if uv else None, opts)
+        want = pipeline.oracle_texts(case.genome, case.lines, sjf if us else None, vcf if uv else None, opts)
+        d = pipeline.first_diff(got, want)
+        assert d is None, (seed, opts, d)
+    clean = synth.make_case(seed, n_reads=n_reads, quirks=False, **kw)
+    got = pipeline.product_texts(engine, GenomeImage.from_dict(clean.genome), clean.lines, None, None, {}, dry=True)
+    want = pipeline.oracle_texts(clean.genome, clean.lines, None, None, {}, dry=True)
+    d = pipeline.first_diff(got, want)
+    assert d is None, (seed, "dry", d)

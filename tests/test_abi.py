@@ -1,0 +1,44 @@
+"""The C-ABI library loads without a GPU and exports every function include/tc_b200.h declares."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "tc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tc_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_declared_symbols():
+    import __graft_entry__ as g
+    g.build()
+    from transcriptclean_b200 import engine
+    lib = ctypes.CDLL(engine.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(engine.EXPORTS) == names
+
+
+def test_no_gpu_is_a_loud_error():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from transcriptclean_b200 import engine
+    with pytest.raises(engine.EngineError):
+        engine.Engine(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "transcriptclean_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no CPU fallback", ""), f
+                assert "hostsim" not in src.lower() or f in ("tc_b200.cu", "tc_plan.cuh"), f

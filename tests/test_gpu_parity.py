@@ -1,0 +1,45 @@
+"""GPU parity: the CUDA path (through the C ABI) against outputs of the unmodified reference
+(tests/golden) and against the oracle on seeded cases.  Bit-exact on all four output texts."""
+import pytest
+
+import goldens
+import parity_cases as pc
+
+pytestmark = pytest.mark.gpu
+FIX = goldens.load_fixtures()
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from transcriptclean_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("rec", FIX, ids=[r["name"] for r in FIX])
+def test_reference_fixture(engine, rec):
+    pc.check_fixture(engine, rec)
+
+
+@pytest.mark.parametrize("seed", goldens.SYNTH_SEEDS)
+def test_reference_synthetic(engine, seed):
+    pc.check_synth_golden(engine, seed)
+
+
+@pytest.mark.parametrize("seed", range(300, 330))
+def test_generated_vs_oracle(engine, seed):
+    pc.check_generated(engine, seed, unpinned=(seed % 3 == 0))
+
+
+def test_long_reads_and_many(engine):
+    pc.check_generated(engine, 999, n_reads=1500, err=0.08, shift_frac=0.4)
+
+
+def test_empty_batch(engine):
+    import numpy as np
+    from transcriptclean_b200.genome import GenomeImage
+    from transcriptclean_b200 import api
+    refs = api.make_refs(GenomeImage.from_dict({"chr1": "ACGT" * 100}), engine=engine)
+    out = api.correct_batch_text([], api.Struct(), refs)
+    assert out == {"sam": "", "fa": "", "log": "", "te": ""}

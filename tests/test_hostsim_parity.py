@@ -1,0 +1,32 @@
+"""CPU-only checks of the planning code (csrc/tc_plan.cuh, shared verbatim with the kernels)
+and of the host-side parser / table builders / renderer, through the hostsim build of the ABI.
+The GPU parity tests proper are in test_gpu_parity.py."""
+import pytest
+
+import goldens
+import parity_cases as pc
+from hostsim_engine import HostSimEngine
+
+FIX = goldens.load_fixtures()
+
+
+@pytest.fixture(scope="module")
+def engine():
+    e = HostSimEngine()
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("rec", FIX, ids=[r["name"] for r in FIX])
+def test_reference_fixture(engine, rec):
+    pc.check_fixture(engine, rec)
+
+
+@pytest.mark.parametrize("seed", goldens.SYNTH_SEEDS)
+def test_reference_synthetic(engine, seed):
+    pc.check_synth_golden(engine, seed)
+
+
+@pytest.mark.parametrize("seed", range(200, 212))
+def test_generated_vs_oracle(engine, seed):
+    pc.check_generated(engine, seed, unpinned=(seed % 3 == 0))

@@ -1,0 +1,143 @@
+"""Host-side mirror of the reference's interface for the correction path.
+
+Same names and argument meaning as /root/reference/TranscriptClean/TranscriptClean.py:
+  prep_refs(options, transcripts, sam_header)            TC.py:203-255
+  batch_correct(sam_transcripts, options, refs, outfiles, buffer_size)   TC.py:350-403
+  correct_transcript(transcript_line, options, refs)     TC.py:406-460
+  dryRun(sam, options, outfiles)                         TC.py:1615-1678
+`options` is any object with the reference's option attributes (correct* are the strings
+"true"/"false" as in the reference, booleans are accepted too); `refs` carries the device
+context instead of pyfaidx / pyranges / dict objects.
+"""
+import warnings
+
+from . import engine as E
+from . import render, sam
+from .genome import GenomeImage
+from .tables import SjTables, VariantTables, build_sj_tables, build_variant_tables
+
+
+class Struct(dict):
+    """dstruct.Struct of the reference (dstruct.py:1-11)."""
+
+    def __init__(self, **kw):
+        dict.__init__(self, kw)
+        self.__dict__ = self
+
+
+def _truthy(v):
+    return v is True or (isinstance(v, str) and v.lower() == "true")
+
+
+def _opt(options, name, default=None):
+    return getattr(options, name, default) if not isinstance(options, dict) else options.get(name, default)
+
+
+def make_refs(genome, sj_tables=None, var_tables=None, device=0, engine=None):
+    """Builds the `refs` Struct around an Engine.  `genome` is a GenomeImage."""
+    refs = Struct()
+    refs.genome = genome
+    refs.engine = engine if engine is not None else E.Engine(device)
+    refs.engine.load_genome(genome)
+    refs.sj = sj_tables if sj_tables is not None else SjTables()
+    refs.var = var_tables if var_tables is not None else VariantTables()
+    refs.engine.load_junctions(refs.sj)
+    refs.engine.load_variants(refs.var)
+    refs.sjAnnot = refs.sj          # len(refs.sjAnnot) > 0 keeps its meaning (TC.py:443)
+    return refs
+
+
+def prep_refs(options, transcripts, sam_header=None, device=0, engine=None, genome=None):
+    """TC.py:203-255: genome, splice annotation restricted to the chromosomes of `transcripts`,
+    variant catalogues.  No temp files are written."""
+    if genome is None:
+        print("Reading genome ..............................")
+        genome = GenomeImage.from_fasta(_opt(options, "refGenome"))
+    chroms = set(t.split("\t")[2] for t in transcripts)
+    sj = var = None
+    sj_file, vcf = _opt(options, "sjAnnotFile"), _opt(options, "variantFile")
+    if not _truthy(_opt(options, "correctSJs", "true")):
+        print("SJ correction turned off in options. Skipping reference SJ parsing.")
+    elif sj_file is not None:
+        print("Processing annotated splice junctions ...")
+        sj = build_sj_tables(sj_file, chroms, genome.index)
+    else:
+        print("No splice annotation provided. Will skip splice junction correction.")
+    if vcf is not None:
+        print("Processing variant file .................")
+        var = build_variant_tables(vcf, int(_opt(options, "maxLenIndel", 5)), genome.index)
+    else:
+        print("No variant file provided. Transcript correction will not be variant-aware.")
+    return make_refs(genome, sj, var, device=device, engine=engine)
+
+
+def _set_engine_options(options, refs):
+    refs.engine.set_options(
+        maxLenIndel=int(_opt(options, "maxLenIndel", 5)), maxSJOffset=int(_opt(options, "maxSJOffset", 5)),
+        correctMismatches=_truthy(_opt(options, "correctMismatches", "true")),
+        correctIndels=_truthy(_opt(options, "correctIndels", "true")),
+        correctSJs=_truthy(_opt(options, "correctSJs", "true")),
+        sj_ignore_strand=bool(_opt(options, "sjIgnoreStrand", False)),
+        sj_tie_right=bool(_opt(options, "sjTieRight", False)))
+
+
+def correct_batch_text(sam_transcripts, options, refs):
+    """Corrects a list of SAM lines on the GPU and returns the four output texts."""
+    _set_engine_options(options, refs)
+    pb = sam.parse_lines(sam_transcripts, refs.genome)
+    res = refs.engine.correct(pb.cols)
+    return render.render_batch(pb, res, bool(_opt(options, "primaryOnly", False)), bool(_opt(options, "canonOnly", False)),
+                               warn=print)
+
+
+def batch_correct(sam_transcripts, options, refs, outfiles, buffer_size=100):
+    """TC.py:350-403.  `buffer_size` only staggers disk writes in the reference; the whole list
+    is one device batch here."""
+    print("Correcting transcripts...")
+    out = correct_batch_text(sam_transcripts, options, refs)
+    outfiles.sam.write(out["sam"])
+    outfiles.fasta.write(out["fa"])
+    outfiles.log.write(out["log"])
+    outfiles.TElog.write(out["te"])
+
+
+def correct_transcript(transcript_line, options, refs):
+    """TC.py:406-460: (Transcript-like or None, logInfo, TE_entries) for one SAM line."""
+    _set_engine_options(options, refs)
+    pb = sam.parse_lines([transcript_line], refs.genome)
+    res = refs.engine.correct(pb.cols)
+    render.check_errors(pb, res)
+    st = int(res.status[0])
+    cls = st & E.ST_CLASS_MASK
+    log = Struct()
+    log.TranscriptID = transcript_line.split("\t", 1)[0]
+    log.Mapping = render.CLASS_NAME[cls]
+    for k, name in enumerate(("corrected_deletions", "uncorrected_deletions", "variant_deletions",
+                              "corrected_insertions", "uncorrected_insertions", "variant_insertions",
+                              "corrected_mismatches", "uncorrected_mismatches", "corrected_NC_SJs",
+                              "uncorrected_NC_SJs")):
+        c = int(res.counters[0][k])
+        log[name] = "NA" if c < 0 else c
+    if cls != 0:
+        return None, log, ""
+    if st & E.ST_FALLBACK:
+        warnings.warn("Problem encountered while correcting transcript with ID %s. Will output original version."
+                      % log.TranscriptID)
+    view = render.ReadView(pb, res, 0)
+    return view, log, render.te_rows(view.QNAME, view.CHROM, res.te[res.te_off[0]:res.te_off[1]])
+
+
+def dry_run_text(sam_transcripts, refs):
+    pb = sam.parse_lines(sam_transcripts, refs.genome)
+    res = refs.engine.dryrun(pb.cols)
+    return render.render_dry(pb, res)
+
+
+def dryRun(sam_lines, options, outfiles, refs=None, device=0):
+    """TC.py:1615-1678."""
+    print("Dry run mode: Identifying indels and mismatches.........")
+    if refs is None:
+        refs = make_refs(GenomeImage.from_fasta(_opt(options, "refGenome")), device=device)
+    out = dry_run_text(sam_lines, refs)
+    outfiles.log.write(out["log"])
+    outfiles.TElog.write(out["te"])

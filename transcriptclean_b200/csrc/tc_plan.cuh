@@ -1,0 +1,777 @@
+// tc_plan.cuh - per-read planning logic of the correction path (one thread per read).
+//
+// These functions decide *what* happens to a read - which mismatches / indels are rewritten,
+// which junctions move, the new CIGAR, the TE.log records, the counters - and describe the new
+// SEQ as a short list of segments (slices of the input SEQ or of the genome).  No bulk bytes
+// move here; tc_emit (warp per read) materialises SEQ and regenerates NM/MD afterwards.
+//
+// Semantics follow the reference line by line (citations: TC = TranscriptClean.py,
+// tr = transcript.py, sj = spliceJunction.py, ib = intronBound.py; Qn = SURVEY.md 3.4).
+#pragma once
+#include <stdint.h>
+#include "../../include/tc_b200.h"
+
+#ifdef TC_HOSTSIM
+#define TC_HD inline
+#else
+#define TC_HD __device__ inline
+#endif
+
+typedef unsigned long long u64;
+
+// ---------------------------------------------------------------------------------- tables
+
+struct GenomeDev {
+    const uint32_t* g2;        // 2-bit bases, 16 per word
+    const uint32_t* lo1;       // lower-case plane, 32 per word
+    const uint32_t* excblk;    // 1 bit per 256-base block that holds a non-ACGT base
+    const int64_t* chrom_off;
+    const int64_t* chrom_len;
+    const int64_t* exc_start;  // literal runs: [start, end) in plane coordinates
+    const int64_t* exc_end;
+    const uint8_t* exc_byte;
+    int64_t n_exc;
+    int32_t n_chrom;
+};
+
+struct SjDev {
+    const u64 *don_s, *acc_s, *don_u, *acc_u, *ann_k1, *ann_k2;
+    int64_t n_don_s, n_acc_s, n_don_u, n_acc_u, n_ann;
+};
+
+struct VarDev {
+    const u64* snp_key; const uint8_t* snp_alt; int64_t n_snp;
+    const u64* ins_key; const int32_t* ins_size; const int64_t* ins_aoff; const uint8_t* ins_bytes; int64_t n_ins;
+    const u64* del_key; const int32_t* del_size; int64_t n_del;
+};
+
+struct BatchDev {
+    int64_t n;
+    const int32_t *flag, *chrom, *pos;
+    const uint8_t* tags;
+    const int64_t* seq_off; const uint8_t* seq;
+    const int64_t* cig_off; const uint8_t* cig_op; const int32_t* cig_len;
+    const int64_t* md_off; const uint8_t* md;
+    const int64_t* ji_off; const int32_t* ji;
+};
+
+// per-read state (structure of arrays) + workspace
+struct WorkDev {
+    uint32_t* status;
+    int32_t* counters;       // 10 per read
+    // NM/MD computed at init for reads that lack either tag (tr.py:47-48)
+    const uint8_t* md_init_pool; int64_t* md_init_off; int32_t* md_init_len; int32_t* nm_init;
+    // measure
+    int32_t* n_mdtok; int32_t* n_jn; uint8_t* mflags;
+    int32_t *cig_cap, *seg_cap, *te_cap;
+    int64_t* ws_off;         // n+1 (exclusive scan of the need)
+    u64* ws;
+    // current planned state
+    int8_t* cig_buf; int32_t* n_cig_cur;    // -1 = the input CIGAR
+    int8_t* seg_buf; int32_t* n_seg_cur;    // -1 = the input SEQ
+    int32_t* n_te; int32_t* te_cnt;         // te_cnt: 3 per read (mismatch, insertion, deletion rows)
+    int32_t* nm_extra; uint8_t* refresh;
+    // exact output sizes, turned into offsets (n+1) by exclusive scans
+    int64_t *o_seq, *o_cig, *o_te, *o_jn;
+};
+
+enum { MF_HAS_I = 1, MF_HAS_D = 2, MF_HAS_N = 4, MF_MD_ACGTN = 8 };
+enum { TAG_NM = 1, TAG_MD = 2, TAG_JM = 4, TAG_JI = 8 };
+
+struct Params {
+    GenomeDev G; SjDev S; VarDev V; BatchDev B; WorkDev W; tc_options O;
+    int32_t sj_enabled;      // len(refs.sjAnnot) > 0 (TC.py:443)
+};
+
+// ---------------------------------------------------------------------------------- packing
+
+#define SEG_LEN_BITS 24
+#define SEG_LEN_MASK ((1ull << SEG_LEN_BITS) - 1)
+TC_HD u64 seg_make(int kind, int64_t src, int64_t len) { return ((u64)kind << 63) | ((u64)src << SEG_LEN_BITS) | (u64)len; }
+TC_HD int seg_kind(u64 s) { return (int)(s >> 63); }
+TC_HD int64_t seg_src(u64 s) { return (int64_t)((s & ~(1ull << 63)) >> SEG_LEN_BITS); }
+TC_HD int64_t seg_len(u64 s) { return (int64_t)(s & SEG_LEN_MASK); }
+TC_HD u64 cg_make(int op, int32_t len) { return ((u64)(uint32_t)op << 32) | (uint32_t)len; }
+TC_HD int cg_op(u64 c) { return (int)(c >> 32); }
+TC_HD int32_t cg_len(u64 c) { return (int32_t)(uint32_t)c; }
+
+struct WsView { u64* cig[3]; u64* seg[3]; tc_te* te; int32_t* jn; };
+// junction record, 8 int32: b0 b1 start end code snap_ji0 snap_ji1 snap_jm
+#define JN_STRIDE 8
+
+TC_HD int64_t ws_need_units(int cig_cap, int seg_cap, int te_cap, int n_jn) {
+    return 3ll * cig_cap + 3ll * seg_cap + 2ll * te_cap + 4ll * n_jn;
+}
+TC_HD WsView ws_view(const WorkDev& W, int64_t i) {
+    WsView v; u64* p = W.ws + W.ws_off[i];
+    int cc = W.cig_cap[i], sc = W.seg_cap[i], tc = W.te_cap[i];
+    for (int k = 0; k < 3; k++) { v.cig[k] = p; p += cc; }
+    for (int k = 0; k < 3; k++) { v.seg[k] = p; p += sc; }
+    v.te = (tc_te*)p; p += 2ll * tc;
+    v.jn = (int32_t*)p;
+    return v;
+}
+
+// ---------------------------------------------------------------------------------- genome
+
+TC_HD uint8_t genome_byte_fast(const GenomeDev& G, int64_t g) {
+    uint32_t code = (G.g2[g >> 4] >> ((g & 15) * 2)) & 3u;
+    uint32_t low = (G.lo1[g >> 5] >> (g & 31)) & 1u;
+    return (uint8_t)((0x54474341u >> (code * 8)) & 0xff) | (uint8_t)(low << 5);   // "ACGT"
+}
+TC_HD bool genome_blk_has_exc(const GenomeDev& G, int64_t g) {
+    int64_t b = g >> 8;
+    return (G.excblk[b >> 5] >> (b & 31)) & 1u;
+}
+TC_HD uint8_t genome_byte_exc(const GenomeDev& G, int64_t g) {   // g lies in a flagged block
+    int64_t lo = 0, hi = G.n_exc;
+    while (lo < hi) { int64_t m = (lo + hi) >> 1; if (G.exc_start[m] <= g) lo = m + 1; else hi = m; }
+    if (lo > 0 && g < G.exc_end[lo - 1]) return G.exc_byte[lo - 1];
+    return genome_byte_fast(G, g);
+}
+TC_HD uint8_t genome_byte(const GenomeDev& G, int64_t g) {
+    return genome_blk_has_exc(G, g) ? genome_byte_exc(G, g) : genome_byte_fast(G, g);
+}
+TC_HD uint8_t up8(uint8_t c) { return (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c; }
+
+// pyfaidx get_seq(chrom, s, e): number of bases actually returned (truncated at the contig end)
+TC_HD int fetch_len(const GenomeDev& G, int chrom, int64_t s, int64_t e) {
+    int64_t L = G.chrom_len[chrom];
+    if (e > L) e = L;
+    return e >= s ? (int)(e - s + 1) : 0;
+}
+
+// ---------------------------------------------------------------------------------- searches
+
+TC_HD int64_t lower_bound_u64(const u64* a, int64_t lo, int64_t hi, u64 key) {
+    while (lo < hi) { int64_t m = (lo + hi) >> 1; if (a[m] < key) lo = m + 1; else hi = m; }
+    return lo;
+}
+
+// nearest annotated site (pyranges.nearest as used at TC.py:1241-1259).  false = nothing on this
+// chromosome/strand -> the reference's .iloc[0] raises (Q23).
+TC_HD bool sj_nearest(const u64* tab, int64_t n, u64 prefix, int64_t q, bool tie_right, int& dist) {
+    int64_t lo = lower_bound_u64(tab, 0, n, prefix << 32);
+    int64_t hi = lower_bound_u64(tab, lo, n, (prefix + 1) << 32);
+    if (lo == hi) return false;
+    int64_t i = lower_bound_u64(tab, lo, hi, (prefix << 32) | (u64)(uint32_t)q);
+    int64_t best;
+    if (i < hi) {
+        best = (int64_t)(tab[i] & 0xffffffffull);
+        if (i > lo) {
+            int64_t left = (int64_t)(tab[i - 1] & 0xffffffffull);
+            int64_t dl = q - left, dr = best - q;
+            if (dl < dr || (dl == dr && !tie_right)) best = left;
+        }
+    } else {
+        best = (int64_t)(tab[i - 1] & 0xffffffffull);
+    }
+    dist = (int)(best - q);
+    return true;
+}
+
+TC_HD bool sj_annotated(const SjDev& S, int chrom, int32_t start, int32_t end, int strand) {
+    u64 k1 = ((u64)chrom << 32) | (uint32_t)start, k2 = ((u64)(uint32_t)end << 1) | (u64)strand;
+    int64_t lo = lower_bound_u64(S.ann_k1, 0, S.n_ann, k1);
+    int64_t hi = lower_bound_u64(S.ann_k1, lo, S.n_ann, k1 + 1);
+    int64_t j = lower_bound_u64(S.ann_k2, lo, hi, k2);
+    return j < hi && S.ann_k2[j] == k2;
+}
+
+TC_HD bool snp_match(const VarDev& V, int chrom, int64_t pos, uint8_t base) {   // TC.py:1114-1118
+    u64 key = ((u64)chrom << 32) | (uint32_t)pos;
+    for (int64_t j = lower_bound_u64(V.snp_key, 0, V.n_snp, key); j < V.n_snp && V.snp_key[j] == key; j++)
+        if (V.snp_alt[j] == base) return true;
+    return false;
+}
+TC_HD int64_t indel_lower(const u64* key, const int32_t* size, int64_t n, u64 k, int32_t sz) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t m = (lo + hi) >> 1;
+        if (key[m] < k || (key[m] == k && size[m] < sz)) lo = m + 1; else hi = m;
+    }
+    return lo;
+}
+TC_HD bool ins_match(const VarDev& V, int chrom, int64_t pos, int32_t ct, const uint8_t* s) {   // TC.py:905-909
+    u64 key = ((u64)chrom << 32) | (uint32_t)pos;
+    for (int64_t j = indel_lower(V.ins_key, V.ins_size, V.n_ins, key, ct);
+         j < V.n_ins && V.ins_key[j] == key && V.ins_size[j] == ct; j++) {
+        int64_t a = V.ins_aoff[j], b = V.ins_aoff[j + 1];
+        if (b - a != ct) continue;
+        bool eq = true;
+        for (int t = 0; t < ct; t++) if (V.ins_bytes[a + t] != s[t]) { eq = false; break; }
+        if (eq) return true;
+    }
+    return false;
+}
+TC_HD bool del_match(const VarDev& V, int chrom, int64_t pos, int32_t ct) {   // TC.py:1012
+    u64 key = ((u64)chrom << 32) | (uint32_t)pos;
+    int64_t j = indel_lower(V.del_key, V.del_size, V.n_del, key, ct);
+    return j < V.n_del && V.del_key[j] == key && V.del_size[j] == ct;
+}
+
+// ---------------------------------------------------------------------------------- MD tokens
+
+struct MdCur { const uint8_t* p; int len; int i; };
+TC_HD bool is_dig(uint8_t c) { return c >= '0' && c <= '9'; }
+// splitMD (tr.py:128-157): runs of digits -> ('M', value); other runs -> '^...' = ('D', len-1),
+// else ('X', len).
+TC_HD bool md_next(MdCur& t, int& op, int32_t& cnt) {
+    if (t.i >= t.len) return false;
+    uint8_t c = t.p[t.i];
+    if (is_dig(c)) {
+        int64_t v = 0;
+        while (t.i < t.len && is_dig(t.p[t.i])) { v = v * 10 + (t.p[t.i] - '0'); t.i++; }
+        op = 'M'; cnt = (int32_t)v;
+    } else {
+        int s = t.i;
+        while (t.i < t.len && !is_dig(t.p[t.i])) t.i++;
+        int L = t.i - s;
+        if (c == '^') { op = 'D'; cnt = L - 1; } else { op = 'X'; cnt = L; }
+    }
+    return true;
+}
+
+TC_HD void md_effective(const Params& P, int64_t i, const uint8_t*& p, int& len) {
+    if (P.W.status[i] & TC_ST_NMMD_DEVICE) { p = P.W.md_init_pool + P.W.md_init_off[i]; len = P.W.md_init_len[i]; }
+    else { p = P.B.md + P.B.md_off[i]; len = (int)(P.B.md_off[i + 1] - P.B.md_off[i]); }
+}
+
+TC_HD int read_class(int32_t flag, int32_t chrom) {           // TC.py:1570-1575 (Q1)
+    if (chrom < 0 || flag == 4) return 1;
+    if (flag > 16) return 2;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- K0 measure
+
+// Sizes the per-read workspace.  Runs after the init NM/MD pass so that reads without tags are
+// measured on their generated MD.
+TC_HD void measure_read(const Params& P, int64_t i) {
+    const BatchDev& B = P.B; const WorkDev& W = P.W;
+    uint32_t st = W.status[i];
+    for (int k = 0; k < 10; k++) W.counters[10 * i + k] = -1;
+    W.cig_buf[i] = -1; W.seg_buf[i] = -1; W.n_cig_cur[i] = 0; W.n_seg_cur[i] = 0;
+    W.n_te[i] = 0; W.te_cnt[3 * i] = W.te_cnt[3 * i + 1] = W.te_cnt[3 * i + 2] = 0;
+    W.nm_extra[i] = 0; W.refresh[i] = 0;
+    W.n_mdtok[i] = 0; W.n_jn[i] = 0; W.mflags[i] = 0;
+    W.cig_cap[i] = W.seg_cap[i] = W.te_cap[i] = 0;
+    if ((st & TC_ST_CLASS_MASK) != 0) { W.ws_off[i] = 0; return; }
+    int64_t c0 = B.cig_off[i], c1 = B.cig_off[i + 1];
+    int nc = (int)(c1 - c0), nN = 0; uint8_t mf = 0;
+    for (int64_t c = c0; c < c1; c++) {
+        uint8_t op = B.cig_op[c];
+        if (op == 'I') mf |= MF_HAS_I; else if (op == 'D') mf |= MF_HAS_D; else if (op == 'N') { mf |= MF_HAS_N; nN++; }
+    }
+    int ntok = 0;
+    if (!(st & TC_ST_NMMD_NONE)) {
+        MdCur t; md_effective(P, i, t.p, t.len); t.i = 0;
+        for (int k = 0; k < t.len; k++) {
+            uint8_t u = up8(t.p[k]);
+            if (u == 'A' || u == 'C' || u == 'T' || u == 'G' || u == 'N') { mf |= MF_MD_ACGTN; break; }
+        }
+        int op; int32_t cnt;
+        while (md_next(t, op, cnt)) ntok++;
+    }
+    int nj = 0;
+    if (mf & MF_HAS_N) nj = (B.tags[i] & TAG_JI) ? (int)((B.ji_off[i + 1] - B.ji_off[i]) / 2) : nN;   // tr.py:56-62
+    W.n_mdtok[i] = ntok; W.n_jn[i] = nj; W.mflags[i] = mf;
+    int cc = nc + ntok + 2 * nj + 2, sc = nc + ntok + 4 * nj + 4, tc = nc + ntok + nj + 1;
+    W.cig_cap[i] = cc; W.seg_cap[i] = sc; W.te_cap[i] = tc;
+    W.ws_off[i] = ws_need_units(cc, sc, tc, nj);      // need; scanned into offsets afterwards
+}
+
+// ---------------------------------------------------------------------------------- K1 plan
+
+struct Emit {                 // newCIGAR / newSeq / MVal bookkeeping (endMatch, TC.py:1171-1183)
+    u64* cig; int nc; u64* seg; int ns; int32_t run; int64_t seqlen;
+    TC_HD void match(int32_t n) { run += n; }
+    TC_HD void flush() { if (run > 0) { cig[nc++] = cg_make('M', run); run = 0; } }
+    TC_HD void op(int o, int32_t n) { flush(); cig[nc++] = cg_make(o, n); }
+    TC_HD void push(int kind, int64_t src, int64_t len) {
+        if (len <= 0) return;
+        seqlen += len;
+        if (ns > 0) {
+            u64 last = seg[ns - 1];
+            if (seg_kind(last) == kind && seg_src(last) + seg_len(last) == src &&
+                seg_len(last) + len <= (int64_t)SEG_LEN_MASK) { seg[ns - 1] = seg_make(kind, seg_src(last), seg_len(last) + len); return; }
+        }
+        seg[ns++] = seg_make(kind, src, len);
+    }
+};
+
+TC_HD void te_put(tc_te* te, int& n, int type, int32_t a, int32_t b, int32_t size, int status, int reason) {
+    tc_te r; r.a = a; r.b = b; r.size = size; r.type = (uint8_t)type; r.status = (uint8_t)status;
+    r.reason = (uint8_t)reason; r.pad = 0; te[n++] = r;
+}
+
+// Stages 1-3 in one left-to-right pass.  The reference runs correctMismatches (TC.py:1077-1168),
+// correctInsertions (859-964) and correctDeletions (967-1074) as three passes; because each only
+// rewrites its own kind of op, keeps the genome cursor of every op, and joins M runs the same
+// way, one pass over the MD x CIGAR merge (tr.py:159-213) yields the same CIGAR, SEQ, counters
+// and TE rows (rows are re-ordered by stage in tc_emit).
+TC_HD void plan_read(const Params& P, int64_t i) {
+    const BatchDev& B = P.B; const WorkDev& W = P.W; const tc_options& O = P.O;
+    uint32_t st = W.status[i];
+    if ((st & TC_ST_CLASS_MASK) != 0) return;
+    int32_t* C = W.counters + 10 * i;
+    const uint8_t mf = W.mflags[i];
+    if (O.correct_mismatches) {
+        C[TC_C_COR_MM] = 0; C[TC_C_UNC_MM] = 0;                      // TC.py:1081-1082
+        if (st & TC_ST_NMMD_NONE) { W.status[i] = st | TC_ST_FALLBACK; return; }   // None.upper() (TC.py:1090)
+    }
+    bool stage1 = O.correct_mismatches && (mf & MF_MD_ACGTN);
+    bool indel = O.correct_indels != 0;
+    bool rewritten = stage1 || (indel && (mf & (MF_HAS_I | MF_HAS_D)));
+    if (!rewritten) {
+        if (indel) for (int k = TC_C_COR_DEL; k <= TC_C_VAR_INS; k++) C[k] = 0;
+        return;
+    }
+    WsView v = ws_view(W, i);
+    Emit E; E.cig = v.cig[0]; E.nc = 0; E.seg = v.seg[0]; E.ns = 0; E.run = 0; E.seqlen = 0;
+    const int chrom = B.chrom[i];
+    const int64_t goff = P.G.chrom_off[chrom] - 1;       // plane index of 1-based position p is goff + p
+    const uint8_t* seq = B.seq + B.seq_off[i];
+    int64_t q = 0, g = B.pos[i];
+    int nte = 0; int cM = 0, uM = 0, cI = 0, uI = 0, vI = 0, cD = 0, uD = 0, vD = 0;
+    int nteM = 0, nteI = 0, nteD = 0; int32_t ins_removed = 0; bool sawD = false;
+    // merge state (tr.py:171-211)
+    int64_t ci = B.cig_off[i]; const int64_t cend = B.cig_off[i + 1];
+    int32_t crem = ci < cend ? B.cig_len[ci] : 0;
+    MdCur md; md.i = 0; md.len = 0; md.p = 0;
+    int mop = 0; int32_t mrem = 0; bool have_md = false;
+    if (stage1) { md_effective(P, i, md.p, md.len); have_md = md_next(md, mop, mrem); }
+    bool fail = false;
+    while (true) {
+        int op; int32_t ct;
+        if (stage1) {
+            if (!have_md && ci >= cend) break;
+            if (ci >= cend) { fail = true; break; }                   // cigarOperation[cigarIndex] IndexError (Q14)
+            int cop = B.cig_op[ci];
+            if (cop == 'H' || cop == 'S' || cop == 'I' || cop == 'N') { op = cop; ct = crem; ci++; if (ci < cend) crem = B.cig_len[ci]; }
+            else {
+                if (!have_md) { fail = true; break; }                 // mdCount[mdIndex] IndexError
+                if (crem < mrem) { mrem -= crem; op = cop; ct = crem; ci++; if (ci < cend) crem = B.cig_len[ci]; }
+                else if (crem > mrem) { crem -= mrem; op = mop; ct = mrem; have_md = md_next(md, mop, mrem); }
+                else { op = mop; ct = mrem; have_md = md_next(md, mop, mrem); ci++; if (ci < cend) crem = B.cig_len[ci]; }
+            }
+        } else {
+            if (ci >= cend) break;
+            op = B.cig_op[ci]; ct = B.cig_len[ci]; ci++;
+        }
+        switch (op) {
+        case 'M':
+            E.push(0, q, ct); E.match(ct); q += ct; g += ct; break;
+        case 'X':                                                     // only produced by the MD side
+            if (snp_match(P.V, chrom, g, seq[q])) {                   // TC.py:1115-1130 (Q11)
+                te_put(v.te, nte, 0, (int32_t)g, 0, ct, 1, 1); uM++; nteM++;
+                E.push(0, q, ct);
+            } else {
+                te_put(v.te, nte, 0, (int32_t)g, 0, ct, 0, 0); cM++; nteM++;
+                E.push(1, goff + g, ct);                              // genome bases verbatim (Q6)
+            }
+            E.match(ct); q += ct; g += ct; break;
+        case 'S':
+            E.op('S', ct); E.push(0, q, ct); q += ct; break;
+        case 'I': {
+            bool keep = true;
+            if (indel) {                                              // TC.py:898-940
+                nteI++;
+                if (ct > O.max_len_indel) { te_put(v.te, nte, 1, (int32_t)(g - 1), (int32_t)(g + ct - 1), ct, 1, 2); uI++; }
+                else if (ins_match(P.V, chrom, g - 1, ct, seq + q)) { te_put(v.te, nte, 1, (int32_t)(g - 1), (int32_t)(g + ct - 1), ct, 1, 1); vI++; }
+                else { te_put(v.te, nte, 1, (int32_t)(g - 1), (int32_t)(g + ct - 1), ct, 0, 0); cI++; keep = false; ins_removed += ct; }
+            }
+            if (keep) { E.op('I', ct); E.push(0, q, ct); }
+            q += ct; break; }
+        case 'D': {
+            bool keep = true; sawD = true;
+            if (indel) {                                              // TC.py:1007-1051
+                nteD++;
+                if (ct > O.max_len_indel) { te_put(v.te, nte, 2, (int32_t)(g - 1), (int32_t)(g + ct - 1), ct, 1, 2); uD++; }
+                else if (del_match(P.V, chrom, g - 1, ct)) { te_put(v.te, nte, 2, (int32_t)(g - 1), (int32_t)(g + ct - 1), ct, 1, 1); vD++; }
+                else { te_put(v.te, nte, 2, (int32_t)(g - 1), (int32_t)(g + ct - 1), ct, 0, 0); cD++; keep = false; }
+            }
+            if (keep) E.op('D', ct); else { E.push(1, goff + g, ct); E.match(ct); }
+            g += ct; break; }
+        case 'N': case 'H':
+            E.op(op, ct); g += ct; break;
+        default: break;                                               // other ops vanish (Q10)
+        }
+    }
+    if (fail) {                                                       // whole-read fallback (Q13): stage 1 raised
+        W.status[i] = st | TC_ST_FALLBACK;                            // before stages 2-3 zeroed their counters
+        return;
+    }
+    E.flush();
+    C[TC_C_COR_MM] = O.correct_mismatches ? cM : -1; C[TC_C_UNC_MM] = O.correct_mismatches ? uM : -1;
+    if (indel) { C[TC_C_COR_INS] = cI; C[TC_C_UNC_INS] = uI; C[TC_C_VAR_INS] = vI;
+                 C[TC_C_COR_DEL] = cD; C[TC_C_UNC_DEL] = uD; C[TC_C_VAR_DEL] = vD; }
+    W.cig_buf[i] = 0; W.n_cig_cur[i] = E.nc; W.seg_buf[i] = 0; W.n_seg_cur[i] = E.ns;
+    W.n_te[i] = nte; W.te_cnt[3 * i] = nteM; W.te_cnt[3 * i + 1] = nteI; W.te_cnt[3 * i + 2] = nteD;
+    // NM/MD refresh points (Q7): end of correctDeletions when the CIGAR holds a D, else end of
+    // correctMismatches; insertion removal never refreshes, so NM keeps counting removed bases.
+    if (indel && sawD) { W.refresh[i] = 1; W.nm_extra[i] = 0; }
+    else if (stage1) { W.refresh[i] = 1; W.nm_extra[i] = ins_removed; }
+    W.status[i] = st | TC_ST_CIGAR_REWRITTEN;
+}
+
+// ---------------------------------------------------------------------------------- K2 junctions
+
+TC_HD int motif_code(uint8_t a0, uint8_t a1, uint8_t b0, uint8_t b1) {   // sj.py:71-89
+    uint32_t m = ((uint32_t)up8(a0) << 24) | ((uint32_t)up8(a1) << 16) | ((uint32_t)up8(b0) << 8) | up8(b1);
+    switch (m) {
+    case 0x47544147u: return 1;   // GTAG
+    case 0x43544143u: return 2;   // CTAC
+    case 0x47434147u: return 3;   // GCAG
+    case 0x43544743u: return 4;   // CTGC
+    case 0x41544143u: return 5;   // ATAC
+    case 0x47544154u: return 6;   // GTAT
+    }
+    return 0;
+}
+
+// checkSpliceMotif (sj.py:48-68).  false = pyfaidx would raise (start < 1).
+TC_HD bool junction_code(const Params& P, int chrom, int strand, int32_t b0, int32_t b1, int32_t start,
+                         int32_t end, int& code) {
+    if (b0 < 1 || b1 - 1 < 1) return false;
+    const GenomeDev& G = P.G; int64_t goff = G.chrom_off[chrom] - 1;
+    int n0 = fetch_len(G, chrom, b0, (int64_t)b0 + 1), n1 = fetch_len(G, chrom, (int64_t)b1 - 1, b1);
+    int mc = 0;
+    if (n0 == 2 && n1 == 2)
+        mc = motif_code(genome_byte(G, goff + b0), genome_byte(G, goff + b0 + 1),
+                        genome_byte(G, goff + b1 - 1), genome_byte(G, goff + b1));
+    code = mc + (sj_annotated(P.S, chrom, start, end, strand) ? 20 : 0);
+    return true;
+}
+
+struct ExonLoc { int lo, hi; int64_t q0, q1; int nidx; };
+// group_CIGAR_by_exon_and_intron (TC.py:1379-1412): exon t = ops between the t-th and (t+1)-th N;
+// its sequence = the M/S/I bases in that range.
+TC_HD bool locate_exon(const u64* cig, int n, int t, ExonLoc& e, int& nN) {
+    int exon = 0, lo = 0; int64_t q = 0, q0 = 0; bool found = false;
+    for (int k = 0; k < n; k++) {
+        int op = cg_op(cig[k]);
+        if (op == 'N') {
+            if (exon == t) { e.lo = lo; e.hi = k; e.q0 = q0; e.q1 = q; e.nidx = k; found = true; }
+            exon++; lo = k + 1; q0 = q;
+        } else if (op == 'M' || op == 'S' || op == 'I') q += cg_len(cig[k]);
+    }
+    if (exon == t) { e.lo = lo; e.hi = n; e.q0 = q0; e.q1 = q; e.nidx = -1; found = true; }
+    nN = exon;
+    return found;
+}
+TC_HD int64_t cig_query_len(const u64* cig, int n) {             // tr.py:591-605
+    int64_t q = 0;
+    for (int k = 0; k < n; k++) { int op = cg_op(cig[k]); if (op == 'M' || op == 'S' || op == 'I') q += cg_len(cig[k]); }
+    return q;
+}
+
+// editExonCIGAR (TC.py:1515-1555) applied to ops [lo,hi) of src, plus the intron length change.
+// Returns the new op count, or -1 for the IndexError on an empty exon (TC.py:1526).
+TC_HD int cig_edit(const u64* src, int n, u64* dst, int lo, int hi, bool at_end, int nb,
+                   int intron_idx, int intron_delta, bool& degenerate) {
+    int m = 0;
+    for (int k = 0; k < lo; k++) {
+        u64 c = src[k];
+        if (k == intron_idx) { int32_t L = cg_len(c) + intron_delta; if (L <= 0) degenerate = true; c = cg_make('N', L); }
+        dst[m++] = c;
+    }
+    int ne = hi - lo;
+    if (nb >= 0) {
+        if (ne == 0) return -1;
+        if (at_end) {
+            for (int k = lo; k < hi - 1; k++) dst[m++] = src[k];
+            u64 last = src[hi - 1];
+            if (cg_op(last) == 'M') dst[m++] = cg_make('M', cg_len(last) + nb);
+            else { dst[m++] = last; dst[m++] = cg_make('M', nb); }
+        } else {
+            u64 first = src[lo];
+            if (cg_op(first) == 'M') dst[m++] = cg_make('M', cg_len(first) + nb);
+            else { dst[m++] = cg_make('M', nb); dst[m++] = first; }
+            for (int k = lo + 1; k < hi; k++) dst[m++] = src[k];
+        }
+    } else {
+        int64_t need = -(int64_t)nb;
+        if (at_end) {
+            int k = hi - 1; int32_t keep_len = -1;
+            for (; k >= lo; k--) {
+                int64_t rem = (int64_t)cg_len(src[k]) - need;
+                if (rem > 0) { keep_len = (int32_t)rem; break; }
+                if (rem == 0) { k--; break; }
+                need = -rem;
+            }
+            // ops lo..k survive; op k shortened when keep_len >= 0
+            for (int j = lo; j <= k; j++) dst[m++] = (j == k && keep_len >= 0) ? cg_make(cg_op(src[j]), keep_len) : src[j];
+        } else {
+            int k = lo; int32_t keep_len = -1;
+            for (; k < hi; k++) {
+                int64_t rem = (int64_t)cg_len(src[k]) - need;
+                if (rem > 0) { keep_len = (int32_t)rem; break; }
+                if (rem == 0) { k++; break; }
+                need = -rem;
+            }
+            for (int j = k; j < hi; j++) dst[m++] = (j == k && keep_len >= 0) ? cg_make(cg_op(src[j]), keep_len) : src[j];
+        }
+    }
+    for (int k = hi; k < n; k++) {
+        u64 c = src[k];
+        if (k == intron_idx) { int32_t L = cg_len(c) + intron_delta; if (L <= 0) degenerate = true; c = cg_make('N', L); }
+        dst[m++] = c;
+    }
+    return m;
+}
+
+TC_HD int seg_insert(const u64* s, int n, u64* d, int64_t qpos, u64 ns) {
+    int m = 0; int64_t q = 0; bool done = seg_len(ns) == 0;
+    for (int j = 0; j < n; j++) {
+        int64_t len = seg_len(s[j]);
+        if (!done && qpos <= q) { d[m++] = ns; done = true; }
+        if (!done && qpos < q + len) {
+            int64_t l1 = qpos - q;
+            d[m++] = seg_make(seg_kind(s[j]), seg_src(s[j]), l1);
+            d[m++] = ns;
+            d[m++] = seg_make(seg_kind(s[j]), seg_src(s[j]) + l1, len - l1);
+            done = true; q += len; continue;
+        }
+        d[m++] = s[j]; q += len;
+    }
+    if (!done) d[m++] = ns;
+    return m;
+}
+TC_HD int seg_delete(const u64* s, int n, u64* d, int64_t qa, int64_t qb) {
+    int m = 0; int64_t q = 0;
+    for (int j = 0; j < n; j++) {
+        int64_t len = seg_len(s[j]), a = q, b = q + len;
+        q = b;
+        if (b <= qa || a >= qb || qa >= qb) { d[m++] = s[j]; continue; }
+        if (a < qa) d[m++] = seg_make(seg_kind(s[j]), seg_src(s[j]), qa - a);
+        if (b > qb) d[m++] = seg_make(seg_kind(s[j]), seg_src(s[j]) + (qb - a), b - qb);
+    }
+    return m;
+}
+
+struct JnState {              // the transcript copy being edited by attempt_jn_correction
+    const u64* cig; int nc; const u64* seg; int ns; int64_t seqlen;
+};
+
+// fix_one_side_of_junction (TC.py:1415-1479).  `bound` is mutated before the checks that can
+// still fail, exactly like intronBound.pos (Q18).  Returns false for every path on which the
+// reference raises inside the try at TC.py:1323-1342.
+TC_HD bool fix_side(const Params& P, int chrom, int k, int side, int d, int32_t* bound, JnState& S,
+                    u64* cig_dst, u64* seg_dst, bool& degenerate) {
+    if (d == 0) return true;
+    ExonLoc e; int nN; int t = side == 0 ? k : k + 1;
+    if (!locate_exon(S.cig, S.nc, t, e, nN)) return false;            // exonSeqs[targetExon] IndexError
+    const GenomeDev& G = P.G; int64_t goff = G.chrom_off[chrom] - 1;
+    int ns2; int64_t newlen = S.seqlen;
+    if (side == 0) {
+        if (d > 0) {                                                  // case 1: extend exon end from the genome
+            int32_t b = *bound;
+            if (b < 1) return false;
+            int gl = fetch_len(G, chrom, b, (int64_t)b + d - 1);
+            ns2 = seg_insert(S.seg, S.ns, seg_dst, e.q1, seg_make(1, goff + b, gl)); newlen += gl;
+        } else {                                                      // case 3: exon[0:d]
+            int64_t m = e.q1 - e.q0; if (m > -d) m = -d;
+            ns2 = seg_delete(S.seg, S.ns, seg_dst, e.q1 - m, e.q1); newlen -= m;
+        }
+        *bound += d;
+        if (k >= nN) return false;                                    // intronCIGARs[jn_number] IndexError
+        int ncn = cig_edit(S.cig, S.nc, cig_dst, e.lo, e.hi, true, d, e.nidx, -d, degenerate);
+        if (ncn < 0) return false;
+        S.nc = ncn;
+    } else {
+        if (d < 0) {                                                  // case 2: prepend to the next exon
+            int64_t start = (int64_t)*bound + 1 + d;
+            if (start < 1) return false;
+            int gl = fetch_len(G, chrom, start, (int64_t)*bound);
+            ns2 = seg_insert(S.seg, S.ns, seg_dst, e.q0, seg_make(1, goff + start, gl)); newlen += gl;
+        } else {                                                      // case 4: exon[d:]
+            int64_t m = e.q1 - e.q0; if (m > d) m = d;
+            ns2 = seg_delete(S.seg, S.ns, seg_dst, e.q0, e.q0 + m); newlen -= m;
+        }
+        *bound += d;
+        // the intron before exon k+1 is the k-th N op
+        ExonLoc ek; ek.nidx = -1; int nn2; locate_exon(S.cig, S.nc, k, ek, nn2);
+        int ncn = cig_edit(S.cig, S.nc, cig_dst, e.lo, e.hi, false, -d, ek.nidx, d, degenerate);
+        if (ncn < 0) return false;
+        S.nc = ncn;
+    }
+    S.cig = cig_dst; S.seg = seg_dst; S.ns = ns2; S.seqlen = newlen;
+    return newlen == cig_query_len(S.cig, S.nc);                      // TC.py:1476-1477
+}
+
+TC_HD void junction_read(const Params& P, int64_t i) {
+    const BatchDev& B = P.B; const WorkDev& W = P.W; const tc_options& O = P.O;
+    uint32_t st = W.status[i];
+    if ((st & TC_ST_CLASS_MASK) != 0) return;
+    const int chrom = B.chrom[i]; const int strand = (B.flag[i] == 16) ? 1 : 0;     // tr.py:51-53
+    const int nj = W.n_jn[i]; const uint8_t tags = B.tags[i];
+    WsView v = ws_view(W, i); int32_t* J = v.jn;
+    // ---- Transcript.__init__: junction objects from jI (input tag, else from the CIGAR)
+    if (nj > 0) {
+        if (tags & TAG_JI) {
+            const int32_t* ji = B.ji + B.ji_off[i];
+            for (int k = 0; k < nj; k++) { J[k * JN_STRIDE] = ji[2 * k]; J[k * JN_STRIDE + 1] = ji[2 * k + 1]; }
+        } else {                                                      // compute_jI (tr.py:368-393)
+            int64_t g = B.pos[i]; int k = 0;
+            for (int64_t c = B.cig_off[i]; c < B.cig_off[i + 1]; c++) {
+                int op = B.cig_op[c]; int32_t ct = B.cig_len[c];
+                if (op == 'N') { J[k * JN_STRIDE] = (int32_t)g; J[k * JN_STRIDE + 1] = (int32_t)(g + ct - 1); k++; }
+                if (op != 'S' && op != 'I') g += ct;
+            }
+        }
+    }
+    bool canon = true, annot = true;
+    for (int k = 0; k < nj; k++) {
+        int32_t* r = J + k * JN_STRIDE; r[2] = r[0]; r[3] = r[1];
+        int code = 0; junction_code(P, chrom, strand, r[0], r[1], r[2], r[3], code);
+        r[4] = code; r[5] = r[0]; r[6] = r[1]; r[7] = code;
+        if (code == 0 || code == 20) canon = false;
+        if (code < 20) annot = false;
+    }
+    if (!(tags & TAG_JM)) st |= TC_ST_JM_DEVICE | TC_ST_JI_DEVICE;     // tr.py:69-70
+    else if (!(tags & TAG_JI)) st |= TC_ST_JI_DEVICE;                  // tr.py:56-57
+    // ---- cleanNoncanonical (TC.py:1186-1231)
+    int32_t* C = W.counters + 10 * i;
+    const bool run = !(st & TC_ST_FALLBACK) && O.correct_sjs && P.sj_enabled;
+    if (run) {
+        C[TC_C_COR_SJ] = 0; C[TC_C_UNC_SJ] = 0;
+        if (!canon) {
+            int nte = W.n_te[i]; int cJ = 0, uJ = 0;
+            const int64_t Lq = B.seq_off[i + 1] - B.seq_off[i];
+            // committed transcript state
+            int cb = W.cig_buf[i], sb = W.seg_buf[i]; int nc = W.n_cig_cur[i], ns = W.n_seg_cur[i];
+            if (cb < 0) {                                             // still the input: bring it into the workspace
+                nc = 0; for (int64_t c = B.cig_off[i]; c < B.cig_off[i + 1]; c++) v.cig[0][nc++] = cg_make(B.cig_op[c], B.cig_len[c]);
+                ns = 0; if (Lq > 0) v.seg[0][ns++] = seg_make(0, 0, Lq);
+                cb = 0; sb = 0;
+            }
+            int64_t seqlen = 0; for (int s = 0; s < ns; s++) seqlen += seg_len(v.seg[sb][s]);
+            bool whole_fail = false, degenerate = false, any_ok = false;
+            const bool tie_right = O.sj_tie_right != 0;
+            for (int k = 0; k < nj && !whole_fail; k++) {
+                int32_t* r = J + k * JN_STRIDE;
+                if (!(r[4] == 0 || r[4] == 20)) continue;
+                const int32_t id_a = r[2], id_b = r[3];
+                const int ds = strand == 0 ? 0 : 1, as = 1 - ds;       // sj.py:29-41
+                int d_don, d_acc; bool ok_t;
+                if (O.sj_ignore_strand) {
+                    ok_t = sj_nearest(P.S.don_u, P.S.n_don_u, (u64)chrom, (int64_t)r[ds] - 1, tie_right, d_don) &&
+                           sj_nearest(P.S.acc_u, P.S.n_acc_u, (u64)chrom, (int64_t)r[as] - 1, tie_right, d_acc);
+                } else {
+                    u64 pre = ((u64)chrom << 1) | (u64)strand;
+                    ok_t = sj_nearest(P.S.don_s, P.S.n_don_s, pre, (int64_t)r[ds] - 1, tie_right, d_don) &&
+                           sj_nearest(P.S.acc_s, P.S.n_acc_s, pre, (int64_t)r[as] - 1, tie_right, d_acc);
+                }
+                if (!ok_t) { whole_fail = true; break; }              // Q23: raises outside the inner try
+                int ad = d_don < 0 ? -d_don : d_don, aa = d_acc < 0 ? -d_acc : d_acc;
+                int dist = ((d_don < 0) != (d_acc < 0)) ? ad + aa : (ad > aa ? ad - aa : aa - ad);   // TC.py:1371-1375
+                if (dist > O.max_sj_offset || ad > 2 * O.max_sj_offset || aa > 2 * O.max_sj_offset) {
+                    uJ++; te_put(v.te, nte, 3, id_a, id_b, dist, 1, 3); continue;
+                }
+                // the two scratch buffers that are not the committed one
+                int t1 = (cb + 1) % 3, t2 = (cb + 2) % 3, u1 = (sb + 1) % 3, u2 = (sb + 2) % 3;
+                JnState S; S.cig = v.cig[cb]; S.nc = nc; S.seg = v.seg[sb]; S.ns = ns; S.seqlen = seqlen;
+                int used_c = cb, used_s = sb;
+                bool ok = true;
+                if (d_don != 0) { ok = fix_side(P, chrom, k, ds, d_don, &r[ds], S, v.cig[t1], v.seg[u1], degenerate); used_c = t1; used_s = u1; }
+                if (ok && d_acc != 0) {
+                    int tc = used_c == cb ? t1 : t2, ts = used_s == sb ? u1 : u2;
+                    ok = fix_side(P, chrom, k, as, d_acc, &r[as], S, v.cig[tc], v.seg[ts], degenerate); used_c = tc; used_s = ts;
+                }
+                if (ok) {                                             // update_post_ncsj_correction (TC.py:1279-1294)
+                    r[2] = r[0]; r[3] = r[1];
+                    int code;
+                    if (!junction_code(P, chrom, strand, r[0], r[1], r[2], r[3], code)) ok = false;
+                    else r[4] = code;
+                }
+                if (ok) {
+                    cb = used_c; sb = used_s; nc = S.nc; ns = S.ns; seqlen = S.seqlen; any_ok = true;
+                    canon = true; annot = true;
+                    for (int m = 0; m < nj; m++) {                     // tags + flags from the shared junction objects
+                        int32_t* rr = J + m * JN_STRIDE;
+                        rr[5] = rr[0]; rr[6] = rr[1]; rr[7] = rr[4];
+                        if (rr[4] == 0 || rr[4] == 20) canon = false;
+                        if (rr[4] < 20) annot = false;
+                    }
+                    cJ++; te_put(v.te, nte, 3, id_a, id_b, dist, 0, 0);
+                } else {
+                    uJ++; te_put(v.te, nte, 3, id_a, id_b, dist, 1, 4);
+                }
+            }
+            if (whole_fail) {                                         // Q13/Q23: original read, TE dropped
+                st |= TC_ST_FALLBACK; st &= ~(uint32_t)TC_ST_CIGAR_REWRITTEN;
+                W.cig_buf[i] = -1; W.seg_buf[i] = -1; W.n_te[i] = 0;
+                W.te_cnt[3 * i] = W.te_cnt[3 * i + 1] = W.te_cnt[3 * i + 2] = 0;
+                W.refresh[i] = 0; W.nm_extra[i] = 0;
+                // junction flags go back to the init values (no fix was committed before the raise)
+                canon = true; annot = true;
+                for (int m = 0; m < nj; m++) { int c = J[m * JN_STRIDE + 4]; if (c == 0 || c == 20) canon = false; if (c < 20) annot = false; }
+            } else {
+                C[TC_C_COR_SJ] = cJ; C[TC_C_UNC_SJ] = uJ;
+                W.n_te[i] = nte;
+                if (any_ok) {
+                    W.cig_buf[i] = (int8_t)cb; W.seg_buf[i] = (int8_t)sb; W.n_cig_cur[i] = nc; W.n_seg_cur[i] = ns;
+                    W.refresh[i] = 1; W.nm_extra[i] = 0;
+                    st |= TC_ST_CIGAR_REWRITTEN | TC_ST_JM_DEVICE | TC_ST_JI_DEVICE;
+                    if (degenerate) st |= TC_ST_ERR_INTRON;
+                }
+            }
+        }
+    }
+    if (canon) st |= TC_ST_CANONICAL;
+    if (annot) st |= TC_ST_ALL_ANNOT;
+    W.status[i] = st;
+}
+
+// exact output sizes of a read (input to the four exclusive scans that place tc_emit's output)
+TC_HD void sizes_read(const Params& P, int64_t i) {
+    const BatchDev& B = P.B; const WorkDev& W = P.W;
+    uint32_t st = W.status[i];
+    if ((st & TC_ST_CLASS_MASK) != 0) { W.o_seq[i] = W.o_cig[i] = W.o_te[i] = W.o_jn[i] = 0; return; }
+    int64_t sl;
+    if (W.seg_buf[i] < 0) sl = B.seq_off[i + 1] - B.seq_off[i];
+    else { WsView v = ws_view(W, i); sl = 0; const u64* s = v.seg[W.seg_buf[i]]; for (int k = 0; k < W.n_seg_cur[i]; k++) sl += seg_len(s[k]); }
+    W.o_seq[i] = sl;
+    W.o_cig[i] = W.cig_buf[i] < 0 ? (B.cig_off[i + 1] - B.cig_off[i]) : W.n_cig_cur[i];
+    W.o_te[i] = W.n_te[i];
+    W.o_jn[i] = W.n_jn[i];
+}
+
+// ---------------------------------------------------------------------------------- dry run
+
+// dryRun (TC.py:1615-1678): positional inventory of X / D / I from the MD x CIGAR merge.
+TC_HD void dry_read(const Params& P, int64_t i) {
+    const BatchDev& B = P.B; const WorkDev& W = P.W;
+    uint32_t st = W.status[i];
+    if ((st & TC_ST_CLASS_MASK) != 0) return;
+    int32_t* C = W.counters + 10 * i;
+    C[TC_C_UNC_DEL] = C[TC_C_UNC_INS] = C[TC_C_UNC_MM] = 0;
+    if (st & TC_ST_NMMD_NONE) { W.status[i] = st | TC_ST_ERR_MERGE; return; }
+    WsView v = ws_view(W, i);
+    int64_t g = B.pos[i]; int nte = 0, uM = 0, uI = 0, uD = 0;
+    int64_t ci = B.cig_off[i]; const int64_t cend = B.cig_off[i + 1];
+    int32_t crem = ci < cend ? B.cig_len[ci] : 0;
+    MdCur md; md.i = 0; md_effective(P, i, md.p, md.len);
+    int mop = 0; int32_t mrem = 0; bool have_md = md_next(md, mop, mrem);
+    while (true) {
+        int op; int32_t ct;
+        if (!have_md && ci >= cend) break;
+        if (ci >= cend) { W.status[i] = st | TC_ST_ERR_MERGE; return; }
+        int cop = B.cig_op[ci];
+        if (cop == 'H' || cop == 'S' || cop == 'I' || cop == 'N') { op = cop; ct = crem; ci++; if (ci < cend) crem = B.cig_len[ci]; }
+        else {
+            if (!have_md) { W.status[i] = st | TC_ST_ERR_MERGE; return; }
+            if (crem < mrem) { mrem -= crem; op = cop; ct = crem; ci++; if (ci < cend) crem = B.cig_len[ci]; }
+            else if (crem > mrem) { crem -= mrem; op = mop; ct = mrem; have_md = md_next(md, mop, mrem); }
+            else { op = mop; ct = mrem; have_md = md_next(md, mop, mrem); ci++; if (ci < cend) crem = B.cig_len[ci]; }
+        }
+        if (op == 'M') g += ct;
+        else if (op == 'X') { te_put(v.te, nte, 0, (int32_t)g, 0, ct, 1, 5); uM++; g += ct; }
+        else if (op == 'D') { te_put(v.te, nte, 2, (int32_t)(g - 1), (int32_t)(g + ct - 1), ct, 1, 5); uD++; g += ct; }
+        else if (op == 'I') { te_put(v.te, nte, 1, (int32_t)(g - 1), (int32_t)(g + ct - 1), ct, 1, 5); uI++; }
+        else if (op == 'N' || op == 'H') g += ct;
+    }
+    C[TC_C_UNC_DEL] = uD; C[TC_C_UNC_INS] = uI; C[TC_C_UNC_MM] = uM;
+    W.n_te[i] = nte;
+}

@@ -1,0 +1,227 @@
+"""ctypes binding of libtc_b200.so (C ABI: include/tc_b200.h).  No CPU fallback: if the CUDA
+library is missing or no GPU is usable, constructing an Engine raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libtc_b200.so")
+
+EXPORTS = ["tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_set_options", "tc_ctx_stream",
+           "tc_ctx_load_genome", "tc_ctx_load_junctions", "tc_ctx_load_variants", "tc_correct_batch",
+           "tc_dryrun_batch", "tc_batch_upload", "tc_batch_run", "tc_batch_download", "tc_get_timing"]
+
+# status bits (include/tc_b200.h)
+ST_CLASS_MASK, ST_FALLBACK, ST_CIGAR_REWRITTEN = 3, 1 << 2, 1 << 3
+ST_NMMD_DEVICE, ST_NMMD_NONE, ST_JM_DEVICE, ST_JI_DEVICE = 1 << 4, 1 << 5, 1 << 6, 1 << 7
+ST_CANONICAL, ST_ALL_ANNOT, ST_ERR_INTRON, ST_ERR_MERGE = 1 << 8, 1 << 9, 1 << 10, 1 << 11
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class _Options(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("max_len_indel", "max_sj_offset", "correct_mismatches", "correct_indels",
+                                          "correct_sjs", "sj_ignore_strand", "sj_tie_right", "reserved")]
+
+
+class _BatchIn(C.Structure):
+    _fields_ = [("n_reads", C.c_int64)] + [(n, C.c_void_p) for n in (
+        "flag", "chrom", "pos", "tags", "seq_off", "seq", "cig_off", "cig_op", "cig_len", "md_off", "md", "ji_off", "ji")]
+
+
+class _BatchOut(C.Structure):
+    _fields_ = [("n_reads", C.c_int64)] + [(n, C.c_void_p) for n in (
+        "status", "counters", "nm", "seq_off", "seq", "cig_off", "cig_op", "cig_len", "md_off", "md_len", "md",
+        "jn_off", "jm", "ji", "te_off", "te")]
+
+
+class Timing(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("h2d_ms", "kernels_ms", "d2h_ms", "k_nmmd_init_ms", "k_measure_ms",
+                                         "k_plan_ms", "k_junction_ms", "k_emit_ms")] + \
+               [("launches", C.c_int32), ("md_pool_retries", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+TE_DTYPE = np.dtype([("a", "<i4"), ("b", "<i4"), ("size", "<i4"), ("type", "u1"), ("status", "u1"),
+                     ("reason", "u1"), ("pad", "u1")])
+
+
+def load_library(path=LIB_PATH):
+    if not os.path.exists(path):
+        raise EngineError("CUDA library %s is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a).  There is no CPU fallback." % path)
+    lib = C.CDLL(path)
+    _declare(lib)
+    return lib
+
+
+def _declare(lib):
+    lib.tc_ctx_create.restype = C.c_void_p
+    lib.tc_ctx_create.argtypes = [C.c_int]
+    lib.tc_ctx_destroy.argtypes = [C.c_void_p]
+    lib.tc_ctx_destroy.restype = None
+    lib.tc_last_error.restype = C.c_char_p
+    lib.tc_last_error.argtypes = [C.c_void_p]
+    lib.tc_ctx_stream.restype = C.c_void_p
+    lib.tc_ctx_stream.argtypes = [C.c_void_p]
+    lib.tc_ctx_set_options.argtypes = [C.c_void_p, C.POINTER(_Options)]
+    lib.tc_ctx_load_genome.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.tc_ctx_load_junctions.argtypes = [C.c_void_p] + [C.c_int64, C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p]
+    lib.tc_ctx_load_variants.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    for f in ("tc_correct_batch", "tc_dryrun_batch"):
+        getattr(lib, f).argtypes = [C.c_void_p, C.POINTER(_BatchIn), C.POINTER(_BatchOut)]
+    lib.tc_batch_upload.argtypes = [C.c_void_p, C.POINTER(_BatchIn)]
+    lib.tc_batch_run.argtypes = [C.c_void_p, C.c_int]
+    lib.tc_batch_download.argtypes = [C.c_void_p, C.POINTER(_BatchOut)]
+    lib.tc_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
+    for f in EXPORTS:
+        if f not in ("tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_stream"):
+            getattr(lib, f).restype = C.c_int
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+class BatchResult:
+    """numpy copies of a tc_batch_out."""
+
+    def __init__(self, out, dry):
+        n = out.n_reads
+        self.n = n
+        self.dry = dry
+
+        def arr(p, dtype, count):
+            if not p or count == 0:
+                return np.zeros(0, dtype=dtype)
+            buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(p)
+            return np.frombuffer(buf, dtype=dtype, count=count).copy()
+
+        self.status = arr(out.status, np.uint32, n)
+        self.counters = arr(out.counters, np.int32, 10 * n).reshape(n, 10)
+        self.te_off = arr(out.te_off, np.int64, n + 1) if n else np.zeros(1, np.int64)
+        self.te = arr(out.te, TE_DTYPE, int(self.te_off[-1]))
+        if dry:
+            return
+        self.nm = arr(out.nm, np.int32, n)
+        self.seq_off = arr(out.seq_off, np.int64, n + 1) if n else np.zeros(1, np.int64)
+        self.seq = arr(out.seq, np.uint8, int(self.seq_off[-1]))
+        self.cig_off = arr(out.cig_off, np.int64, n + 1) if n else np.zeros(1, np.int64)
+        self.cig_op = arr(out.cig_op, np.uint8, int(self.cig_off[-1]))
+        self.cig_len = arr(out.cig_len, np.int32, int(self.cig_off[-1]))
+        self.md_off = arr(out.md_off, np.int64, n)
+        self.md_len = arr(out.md_len, np.int32, n)
+        md_total = int((self.md_off + self.md_len).max()) if n else 0
+        self.md = arr(out.md, np.uint8, md_total)
+        self.jn_off = arr(out.jn_off, np.int64, n + 1) if n else np.zeros(1, np.int64)
+        self.jm = arr(out.jm, np.int8, int(self.jn_off[-1]))
+        self.ji = arr(out.ji, np.int32, 2 * int(self.jn_off[-1]))
+
+
+class Engine:
+    """One correction context on one GPU."""
+
+    def __init__(self, device=0):
+        self._setup(load_library(), device)
+
+    def _setup(self, lib, device):
+        self._lib = lib
+        self._ctx = lib.tc_ctx_create(int(device))
+        if not self._ctx:
+            raise EngineError("cannot create a CUDA context on device %d: %s (no CPU fallback)"
+                              % (device, lib.tc_last_error(None).decode()))
+        self.device = device
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.tc_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EngineError("%s failed (%d): %s" % (what, rc, self._lib.tc_last_error(self._ctx).decode()))
+
+    def stream(self):
+        return self._lib.tc_ctx_stream(self._ctx)
+
+    def set_options(self, maxLenIndel=5, maxSJOffset=5, correctMismatches=True, correctIndels=True,
+                    correctSJs=True, sj_ignore_strand=False, sj_tie_right=False):
+        o = _Options(int(maxLenIndel), int(maxSJOffset), int(bool(correctMismatches)), int(bool(correctIndels)),
+                     int(bool(correctSJs)), int(bool(sj_ignore_strand)), int(bool(sj_tie_right)), 0)
+        self._check(self._lib.tc_ctx_set_options(self._ctx, C.byref(o)), "tc_ctx_set_options")
+
+    def load_genome(self, g):
+        st, en, by = g.exceptions()
+        self._check(self._lib.tc_ctx_load_genome(
+            self._ctx, len(g.names), _ptr(g.chrom_len), _ptr(g.chrom_off), int(g.n_pad), _ptr(g.bases2), _ptr(g.lower1),
+            len(st), _ptr(st), _ptr(en), _ptr(by)), "tc_ctx_load_genome")
+
+    def load_junctions(self, t):
+        self._check(self._lib.tc_ctx_load_junctions(
+            self._ctx, len(t.don_s), _ptr(t.don_s), len(t.acc_s), _ptr(t.acc_s), len(t.don_u), _ptr(t.don_u),
+            len(t.acc_u), _ptr(t.acc_u), len(t.ann_k1), _ptr(t.ann_k1), _ptr(t.ann_k2)), "tc_ctx_load_junctions")
+
+    def load_variants(self, v):
+        self._check(self._lib.tc_ctx_load_variants(
+            self._ctx, len(v.snp_key), _ptr(v.snp_key), _ptr(v.snp_alt), len(v.ins_key), _ptr(v.ins_key), _ptr(v.ins_size),
+            _ptr(v.ins_aoff), _ptr(v.ins_bytes), len(v.del_key), _ptr(v.del_key), _ptr(v.del_size)), "tc_ctx_load_variants")
+
+    @staticmethod
+    def _batch_in(cols):
+        b = _BatchIn()
+        b.n_reads = len(cols["flag"])
+        for k in ("flag", "chrom", "pos", "tags", "seq_off", "seq", "cig_off", "cig_op", "cig_len", "md_off", "md",
+                  "ji_off", "ji"):
+            a = cols[k]
+            assert a.flags["C_CONTIGUOUS"]
+            setattr(b, k, a.ctypes.data if a.size else None)
+        return b
+
+    def correct(self, cols):
+        """tc_correct_batch: host columns in -> BatchResult (host copies)."""
+        b, out = self._batch_in(cols), _BatchOut()
+        self._check(self._lib.tc_correct_batch(self._ctx, C.byref(b), C.byref(out)), "tc_correct_batch")
+        return BatchResult(out, False)
+
+    def dryrun(self, cols):
+        b, out = self._batch_in(cols), _BatchOut()
+        self._check(self._lib.tc_dryrun_batch(self._ctx, C.byref(b), C.byref(out)), "tc_dryrun_batch")
+        return BatchResult(out, True)
+
+    # split calls for device-resident measurement
+    def upload(self, cols):
+        b = self._batch_in(cols)
+        self._check(self._lib.tc_batch_upload(self._ctx, C.byref(b)), "tc_batch_upload")
+
+    def run(self, dry=False):
+        self._check(self._lib.tc_batch_run(self._ctx, int(dry)), "tc_batch_run")
+
+    def download(self, dry=False, copy=True):
+        out = _BatchOut()
+        self._check(self._lib.tc_batch_download(self._ctx, C.byref(out)), "tc_batch_download")
+        return BatchResult(out, dry) if copy else out
+
+    def raw_correct(self, b):
+        """tc_correct_batch on a prepared _BatchIn; returns the raw _BatchOut (no numpy copies)."""
+        out = _BatchOut()
+        self._check(self._lib.tc_correct_batch(self._ctx, C.byref(b), C.byref(out)), "tc_correct_batch")
+        return out
+
+    def timing(self):
+        t = Timing()
+        self._check(self._lib.tc_get_timing(self._ctx, C.byref(t)), "tc_get_timing")
+        return t.as_dict()

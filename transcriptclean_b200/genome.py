@@ -1,0 +1,161 @@
+"""Genome image for the device: 2-bit base plane + lower-case plane + literal runs.
+
+Replaces `pyfaidx.Fasta` as used by the reference (TranscriptClean.py:221; fetches at
+transcript.py:300,323, intronBound.py:36-44, TC.py:1016,1036,1142,1441,1457).  The image keeps
+every byte of the FASTA recoverable - case and N / IUPAC codes leak into SEQ and MD in the
+reference - in 0.375 byte per base:
+  bases2  uint32, 16 bases per word, base i in bits 2*(i%16); A=0 C=1 G=2 T=3
+  lower1  uint32, 32 bases per word, bit set = lower case
+  exc_*   sorted runs [start,end) of one literal byte for everything outside ACGTacgt
+Contigs are laid out back to back, each starting at a multiple of 64 bases.
+"""
+import numpy as np
+
+_CODE = np.zeros(256, dtype=np.uint8)
+for _i, _c in enumerate("ACGT"):
+    _CODE[ord(_c)] = _i
+    _CODE[ord(_c.lower())] = _i
+_IS_ACGT = np.zeros(256, dtype=bool)
+for _c in "ACGTacgt":
+    _IS_ACGT[ord(_c)] = True
+_IS_LOWER_ACGT = np.zeros(256, dtype=bool)
+for _c in "acgt":
+    _IS_LOWER_ACGT[ord(_c)] = True
+
+
+def _pad64(n):
+    return (n + 63) // 64 * 64
+
+
+class GenomeImage:
+    def __init__(self, names, lens):
+        self.names = list(names)
+        self.index = {n: i for i, n in enumerate(self.names)}
+        self.chrom_len = np.asarray(lens, dtype=np.int64)
+        offs, o = [], 0
+        for L in lens:
+            offs.append(o)
+            o += _pad64(int(L)) + 64
+        self.chrom_off = np.asarray(offs, dtype=np.int64)
+        self.n_pad = max(64, o)
+        self.bases2 = np.zeros(self.n_pad // 16, dtype=np.uint32)
+        self.lower1 = np.zeros(self.n_pad // 32, dtype=np.uint32)
+        self._exc = []          # (start, end, byte) in plane coordinates
+
+    # ------------------------------------------------------------------ builders
+    def _put(self, off, a):
+        """Write ASCII bytes `a` (uint8 array) at plane offset `off` (any alignment)."""
+        n = len(a)
+        if n == 0:
+            return
+        if off % 32 == 0:
+            self._put_aligned(off, a)
+        else:
+            head = min(n, 32 - off % 32)
+            self._put_slow(off, a[:head])
+            if n > head:
+                self._put_aligned(off + head, a[head:])
+
+    def _put_slow(self, off, a):
+        pos = off + np.arange(len(a), dtype=np.int64)
+        codes = _CODE[a].astype(np.uint32)
+        w, s = pos >> 4, ((pos & 15) * 2).astype(np.uint32)
+        np.bitwise_and.at(self.bases2, w, ~(np.uint32(3) << s))
+        np.bitwise_or.at(self.bases2, w, codes << s)
+        lw, ls = pos >> 5, (pos & 31).astype(np.uint32)
+        np.bitwise_and.at(self.lower1, lw, ~(np.uint32(1) << ls))
+        np.bitwise_or.at(self.lower1, lw, _IS_LOWER_ACGT[a].astype(np.uint32) << ls)
+        self._scan_exc(off, a)
+
+    def _put_aligned(self, off, a):
+        n = len(a)
+        full = n // 32 * 32
+        if full:
+            body = a[:full]
+            c = _CODE[body].reshape(-1, 4)
+            b = (c[:, 0] | (c[:, 1] << 2) | (c[:, 2] << 4) | (c[:, 3] << 6)).astype(np.uint8)
+            self.bases2[off // 16: off // 16 + full // 16] = b.view("<u4")
+            lo = np.packbits(_IS_LOWER_ACGT[body], bitorder="little")
+            self.lower1[off // 32: off // 32 + full // 32] = lo.view("<u4")
+            self._scan_exc(off, body)
+        if n > full:
+            self._put_slow(off + full, a[full:])
+
+    def _scan_exc(self, off, a):
+        bad = ~_IS_ACGT[a]
+        if not bad.any():
+            return
+        idx = np.flatnonzero(bad)
+        vals = a[idx]
+        brk = np.flatnonzero((np.diff(idx) != 1) | (np.diff(vals) != 0)) + 1
+        starts = np.concatenate(([0], brk))
+        ends = np.concatenate((brk, [len(idx)]))
+        for s, e in zip(starts, ends):
+            self._exc.append((off + int(idx[s]), off + int(idx[e - 1]) + 1, int(vals[s])))
+
+    @classmethod
+    def from_dict(cls, seqs):
+        names = list(seqs.keys())
+        g = cls(names, [len(seqs[n]) for n in names])
+        for i, n in enumerate(names):
+            s = seqs[n]
+            a = np.frombuffer(s.encode("ascii") if isinstance(s, str) else bytes(s), dtype=np.uint8)
+            g._put(int(g.chrom_off[i]), a)
+        return g
+
+    @classmethod
+    def from_fasta(cls, path):
+        """Contig name = first word of the header (pyfaidx key semantics, TC.py:469-470)."""
+        with open(path, "rb") as f:
+            data = f.read()
+        recs = []
+        pos = 0
+        while True:
+            h = data.find(b">", pos)
+            if h < 0:
+                break
+            nl = data.find(b"\n", h)
+            nxt = data.find(b"\n>", nl)
+            end = len(data) if nxt < 0 else nxt + 1
+            name = data[h + 1:nl].split()[0].decode()
+            body = np.frombuffer(data, dtype=np.uint8, count=end - nl - 1, offset=nl + 1)
+            body = body[(body != 10) & (body != 13)]
+            recs.append((name, body))
+            pos = end
+        g = cls([r[0] for r in recs], [len(r[1]) for r in recs])
+        for i, (_, body) in enumerate(recs):
+            g._put(int(g.chrom_off[i]), body)
+        return g
+
+    @classmethod
+    def from_windows(cls, chrom_len, windows, fill="N"):
+        """Contigs that are `fill` everywhere except the given {name: [[start(1-based), bases]]}."""
+        names = list(chrom_len.keys())
+        g = cls(names, [chrom_len[n] for n in names])
+        fb = ord(fill)
+        for i, n in enumerate(names):
+            off, L = int(g.chrom_off[i]), int(chrom_len[n])
+            cur = 1
+            for s, b in sorted((int(s), b) for s, b in windows.get(n, [])):
+                if s > cur:
+                    g._exc.append((off + cur - 1, off + s - 1, fb))
+                a = np.frombuffer(b.encode("ascii"), dtype=np.uint8)
+                g._put_slow(off + s - 1, a)
+                cur = s + len(b)
+            if cur <= L:
+                g._exc.append((off + cur - 1, off + L, fb))
+        return g
+
+    # ------------------------------------------------------------------ accessors
+    def exceptions(self):
+        ex = sorted(self._exc)
+        st = np.asarray([e[0] for e in ex], dtype=np.int64)
+        en = np.asarray([e[1] for e in ex], dtype=np.int64)
+        by = np.asarray([e[2] for e in ex], dtype=np.uint8)
+        return st, en, by
+
+    def keys(self):
+        return list(self.names)
+
+    def nbytes(self):
+        return self.bases2.nbytes + self.lower1.nbytes
