@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py - reads corrected per second on the BASELINE.json workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the correction path (TranscriptClean.py:406-460 and callees) over one
+batch of synthetic reads.  N=1 workload = BASELINE.json configs[1]: synthetic PacBio Iso-seq
+reads (~2 kb, ~1 % error, 6 exons) against a synthetic 248,956,422-bp "chr1" with a STAR-format
+SJ table (tools/synth_gen.c; the real hg38 / GM12878 inputs are not shipped).  With N>1 every
+rank corrects its own shard of the same shape (weak scaling, no data-path collective).
+
+  value  device-resident throughput: inputs already in HBM, tc_batch_run() only
+  e2e    through the C ABI with host buffers: tc_correct_batch() = H2D + kernels + D2H
+  roofline  the dominant kernel's algorithmic bytes / its CUDA-event time vs measured HBM peak
+  cpu_baseline  the oracle port of the reference (oracle/tc_oracle.py) on a bounded sample
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = "configs[1]: synthetic PacBio Iso-seq reads (~2 kb, ~1% error, 6 exons) vs synthetic 248,956,422-bp chr1 + STAR SJ table"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    def __init__(self, device):
+        self.path = tempfile.mktemp(prefix="tc_clocks_", suffix=".csv")
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def oracle_setup(w, sj_path):
+    from oracle import tc_oracle as oc
+    genome = oc.Genome({w.chrom: w.genome.tobytes().decode("ascii")})
+    sj = oc.SjTables.from_file(sj_path, {w.chrom})
+    return oc, genome, sj
+
+
+_ORACLE = {}
+
+
+def _oracle_chunk(lines):
+    oc, genome, sj = _ORACLE["ctx"]
+    out = oc.correct_lines(lines, oc.Options(), genome, sj, None)
+    return len(out["log"])
+
+
+def oracle_rate(w, sj_path, lines, threads, steps=1, warmup=0):
+    """Reads/s of the oracle port on `lines` with `threads` forked workers."""
+    import multiprocessing as mp
+    _ORACLE["ctx"] = oracle_setup(w, sj_path)
+    _ORACLE["ctx"][0].FAITHFUL_PER_BASE = True     # per-base genome walk like transcript.py:296-318
+    chunks = [lines[i::threads] for i in range(threads)]
+    times = []
+    if threads == 1:
+        for s in range(warmup + steps):
+            t0 = time.perf_counter(); _oracle_chunk(lines); t1 = time.perf_counter()
+            if s >= warmup:
+                times.append(t1 - t0)
+    else:
+        ctx = mp.get_context("fork")
+        with ctx.Pool(threads) as pool:
+            for s in range(warmup + steps):
+                t0 = time.perf_counter(); pool.map(_oracle_chunk, chunks); t1 = time.perf_counter()
+                if s >= warmup:
+                    times.append(t1 - t0)
+    return len(lines) / (sum(times) / len(times)), sum(times) / len(times)
+
+
+def write_sj(w):
+    path = tempfile.mktemp(prefix="tc_sj_", suffix=".tab")
+    with open(path, "w") as f:
+        for r in w.sj_rows():
+            f.write("\t".join(str(x) for x in r) + "\n")
+    return path
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation (oracle port; the reference is pure
+    Python and is not shipped to the GPU box) with all host threads, on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tools.workload import Workload
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    w = Workload(seed=args.seed, chrom_len=args.chrom_len, n_genes=args.genes)
+    sj_path = write_sj(w)
+    n_sample = args.ref_reads if args.ref_reads else threads * 600
+    cols, nm = w.reads(args.shape, n_sample)
+    lines = w.sam_lines(cols, nm, 0, n_sample)
+    rate, sec = oracle_rate(w, sj_path, lines, threads, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": "reads corrected/sec", "value": rate, "unit": "reads/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "shape": args.shape, "reads_per_step": n_sample},
+            "cpu_baseline": {"value": rate, "unit": "reads/s", "cores": threads, "kind": "port",
+                             "sample": "first %d reads of the workload per step, %d forked workers, oracle/tc_oracle.py "
+                                       "with the reference's per-base genome walk" % (n_sample, threads)},
+            "e2e": {"value": rate, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--reads", type=int, default=1000000, help="reads per GPU per step")
+    ap.add_argument("--shape", default="pacbio")
+    ap.add_argument("--chrom-len", type=int, default=248956422)
+    ap.add_argument("--genes", type=int, default=3000)
+    ap.add_argument("--seed", type=int, default=20261019)
+    ap.add_argument("--cpu-sample", type=int, default=3000)
+    ap.add_argument("--ref-reads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from tools.workload import Workload
+    from transcriptclean_b200 import engine as E
+    from transcriptclean_b200.tables import build_sj_tables
+
+    steps, warmup = args.steps, max(args.warmup, 3)
+    w = Workload(seed=args.seed, chrom_len=args.chrom_len, n_genes=args.genes)
+    sj_path = write_sj(w)
+    cols, nm = w.reads(args.shape, args.reads, seed_offset=rank)
+    gi = w.genome_image()
+    eng = E.Engine(local)
+    eng.set_options()
+    eng.load_genome(gi)
+    eng.load_junctions(build_sj_tables(sj_path, {w.chrom}, gi.index))
+
+    # inputs in pinned host memory
+    pinned = {}
+    for k, a in cols.items():
+        t = torch.empty(max(a.nbytes, 8), dtype=torch.uint8, pin_memory=True)
+        if a.nbytes:
+            t[:a.nbytes].copy_(torch.from_numpy(a.view(np.uint8).reshape(-1)))
+        pinned[k] = t
+    b = E._BatchIn()
+    b.n_reads = args.reads
+    for k in cols:
+        setattr(b, k, pinned[k].data_ptr())
+    h2d_bytes = int(sum(a.nbytes for a in cols.values()))
+
+    stream = torch.cuda.ExternalStream(eng.stream())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        eng.raw_correct(b)
+    t_last = eng.timing()
+    d2h_bytes = int(t_last["d2h_bytes"])
+
+    # ---- device-resident: upload once, time K runs
+    eng._check(eng._lib.tc_batch_upload(eng._ctx, C.byref(b)), "upload")
+    eng.run()
+    sampler = ClockSampler(local)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern = {k: 0.0 for k in ("k_nmmd_init_ms", "k_measure_ms", "k_plan_ms", "k_junction_ms", "k_emit_ms", "kernels_ms")}
+    launches = 0
+    e0.record(stream)
+    for _ in range(steps):
+        eng.run()
+        t = eng.timing()
+        for k in kern:
+            kern[k] += t[k]
+        launches += t["launches"]
+    e1.record(stream)
+    barrier()
+    ms_run = e0.elapsed_time(e1)
+    # ---- end to end through the ABI with host buffers
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(steps):
+        out = eng.raw_correct(b)
+    f1.record(stream)
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop()
+
+    tm = torch.tensor([ms_run, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_run, ms_e2e = float(tm[0]), float(tm[1])
+
+    # ---- algorithmic bytes of the dominant kernel (DESIGN.md "Kernels and rooflines")
+    res = E.BatchResult(out, False)
+    st = res.status
+    primary = (st & E.ST_CLASS_MASK) == 0
+    refreshed = primary & ((st & E.ST_NMMD_DEVICE) != 0)
+    seq_len_out = np.diff(res.seq_off)
+    cig_m = np.where(res.cig_op == ord("M"), res.cig_len, 0).astype(np.int64)
+    m_per_read = np.add.reduceat(np.concatenate((cig_m, [0])), np.minimum(res.cig_off[:-1], len(cig_m)))
+    m_per_read = np.where(np.diff(res.cig_off) > 0, m_per_read, 0)
+    bytes_emit = (int(cols["seq"].nbytes) + int(res.seq.nbytes) + 0.375 * float(m_per_read[refreshed].sum())
+                  + float(seq_len_out[refreshed].sum())        # the compare re-reads the new SEQ
+                  + 13.0 * len(res.cig_op) + 32.0 * len(res.te) + 9.0 * len(res.jm) + float(res.md_len.sum())
+                  + 64.0 * int(primary.sum()))
+    bytes_plan = (5.0 * len(cols["cig_op"]) + float(cols["md"].nbytes) + 8.0 * len(res.cig_op) + 16.0 * len(res.te)
+                  + 96.0 * int(primary.sum()))
+    per = {k: v / steps for k, v in kern.items()}
+    dom = max(("k_emit_ms", "k_plan_ms", "k_junction_ms", "k_nmmd_init_ms", "k_measure_ms"), key=lambda k: per[k])
+    dom_bytes = bytes_emit if dom == "k_emit_ms" else bytes_plan
+    peak, peak_src = peaks()
+    achieved = dom_bytes / (per[dom] * 1e-3) / 1e9
+
+    reads_total = args.reads * world
+    line = {
+        "metric": "reads corrected/sec", "value": reads_total * steps / (ms_run * 1e-3), "unit": "reads/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_run / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "shape": args.shape, "reads_per_gpu_per_step": args.reads,
+                   "mean_read_len": float(cols["seq"].nbytes) / args.reads,
+                   "l2": "inputs (%.2f GB per step) are larger than L2; no flush needed" % (h2d_bytes / 1e9),
+                   "parallelism": "reads sharded by input-order chunk, tables replicated, no collective"},
+        "e2e": {"value": reads_total * steps / (ms_e2e * 1e-3), "unit": "reads/s", "ms_per_step": ms_e2e / steps,
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+        "gpu_launches": int(launches),
+        "kernel_ms_per_step": per,
+        "roofline": {"bound": "hbm", "kernel": dom.replace("_ms", ""), "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": dom_bytes},
+        "clocks": clocks,
+    }
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        ns = min(args.cpu_sample, args.reads)
+        lines = w.sam_lines(cols, nm, 0, ns)
+        rate, sec = oracle_rate(w, sj_path, lines, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": "reads/s", "cores": 1, "kind": "port",
+                                "sample": "first %d reads of the same batch, 1 thread, oracle/tc_oracle.py with the "
+                                          "reference's per-base genome walk (%.1f s)" % (ns, sec)}
+    if rank == 0:
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
