@@ -96,7 +96,8 @@ typedef struct {
     const uint32_t* status;   /* n */
     const int32_t* counters;  /* 10 n */
     const int32_t* nm;        /* n; valid with TC_ST_NMMD_DEVICE */
-    const int64_t* seq_off;   /* n+1 */
+    const int64_t* seq_off;   /* n+1; rows start at multiples of 16 bytes */
+    const int32_t* seq_len;   /* n; length of the read's new SEQ */
     const uint8_t* seq;
     const int64_t* cig_off;   /* n+1 */
     const uint8_t* cig_op;

@@ -54,6 +54,16 @@ TC_HD void cig_get(const CigSrc& c, int k, int& op, int32_t& len) {
 
 #define FULL 0xffffffffu
 #define WARPS_PER_BLOCK 8
+#define EMIT_CAP 4096            // reads whose new SEQ fits are staged in shared memory
+#define EMIT_MAXBP 256
+#define EMIT_MAXGI 256
+
+struct __align__(16) EmitSmem {  // per warp
+    uint8_t seq[EMIT_CAP + 32];
+    uint16_t bp_pos[EMIT_MAXBP]; int16_t bp_shift[EMIT_MAXBP];     // starts of input-SEQ slices: output offset, src-dst shift
+    uint16_t gi_out[EMIT_MAXGI]; uint16_t gi_len[EMIT_MAXGI]; int32_t gi_src[EMIT_MAXGI];   // genome slices
+};
+#define EMIT_SMEM_BYTES (1024 + WARPS_PER_BLOCK * sizeof(EmitSmem))
 
 __device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
     int x = v;
@@ -64,44 +74,92 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
 }
 
 __device__ __forceinline__ bool warp_range_has_exc(const GenomeDev& G, int64_t g0, int64_t g1, int lane) {
+    const int64_t b0 = g0 >> 8; const int nblk = (int)(((g1 - 1) >> 8) - b0) + 1;
     bool hit = false;
-    for (int64_t b = (g0 >> 8) + lane; b <= ((g1 - 1) >> 8); b += 32) hit |= (G.excblk[b >> 5] >> (b & 31)) & 1u;
+    for (int t = lane; t < nblk; t += 32) { const int64_t b = b0 + t; hit |= (G.excblk[b >> 5] >> (b & 31)) & 1u; }
     return __any_sync(FULL, hit);
 }
 
-// getNMandMDFlags (tr.py:280-342, Q8/Q9): one warp walks the CIGAR; lanes take consecutive
-// bases of an M run, gather the genome byte (2-bit plane + case plane, literal runs when the
-// run touches a flagged block), compare case-insensitively, and compact the mismatch tokens
-// with ballot / popc / prefix sums.  WRITE=false measures NM and the MD length; WRITE=true
-// writes the MD bytes.
-template <bool WRITE>
-__device__ void warp_nmmd(const GenomeDev& G, const uint8_t* __restrict__ seq, const CigSrc& cs, int chrom,
-                          int64_t pos, int lane, int& nm_out, int& len_out, bool& none_out, uint8_t* dst) {
+struct NmMd { int nm, len, ntok, carry; bool none; };
+
+// getNMandMDFlags (tr.py:280-342, Q8/Q9).  One warp walks the CIGAR.
+//  FAST (SEQ staged in shared memory, 16-byte aligned): every lane takes 16 bases of an M run -
+//    five LDS.32 + funnel shifts for the read bytes, two coalesced words of the 2-bit plane,
+//    a 256-entry code->ASCII table, one XOR per 4 bases; a 512-base chunk without difference
+//    costs ~50 instructions.  A chunk with any difference (or an M run that touches a literal
+//    run of the genome) is redone by the exact path below.
+//  exact path: lanes take consecutive bases, gather the genome byte (2-bit + case plane,
+//    literal runs), compare case-insensitively, and compact the mismatch tokens with
+//    ballot / popc / prefix sums.
+// WRITE=false measures NM and the MD length; WRITE=true writes the MD bytes.
+template <bool WRITE, bool FAST>
+__device__ NmMd warp_nmmd(const GenomeDev& G, const uint8_t* seq, const uint32_t* lut, const CigSrc& cs, int chrom,
+                          int64_t pos, int lane, uint8_t* dst) {
     const int64_t goff = G.chrom_off[chrom] - 1, clen = G.chrom_len[chrom];
-    int nm = 0, len = 0, carry = 0; int64_t q = 0, g = pos; bool none = false;
+    NmMd R; R.nm = 0; R.len = 0; R.ntok = 0; R.carry = 0; R.none = false;
+    int nm = 0, len = 0, carry = 0, ntok = 0; int64_t q = 0, g = pos; bool none = false;
+    // one literal-run check for the whole reference span; per-op checks only when it hits
+    bool span_exc;
+    {
+        int64_t span = 0;
+        for (int k = lane; k < cs.n; k += 32) { int op; int32_t ct; cig_get(cs, k, op, ct); if (op == 'M' || op == 'D' || op == 'N' || op == 'H') span += ct; }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) span += __shfl_xor_sync(FULL, span, d);
+        int64_t e = pos + span; if (e > clen + 1) e = clen + 1;
+        span_exc = (pos >= 1 && e > pos) ? warp_range_has_exc(G, goff + pos, goff + e, lane) : true;
+    }
     for (int k = 0; k < cs.n && !none; k++) {
         int op; int32_t ct; cig_get(cs, k, op, ct);
         if (op == 'M') {
             if (ct <= 0) continue;
             if (g < 1 || g + ct - 1 > clen) { none = true; break; }   // empty fetch (tr.py:303-304)
             const int64_t g0 = goff + g;
-            const bool exc = warp_range_has_exc(G, g0, g0 + ct, lane);
-            for (int32_t c = 0; c < ct; c += 32) {
-                const int32_t idx = c + lane; const bool valid = idx < ct;
-                uint8_t rb = 0, gb = 0;
-                if (valid) { rb = seq[q + idx]; gb = exc ? genome_byte(G, g0 + idx) : genome_byte_fast(G, g0 + idx); }
-                const bool mism = valid && up8(rb) != up8(gb);
-                const unsigned mask = __ballot_sync(FULL, mism);
-                const int nvalid = min(32, ct - c);
-                if (mask == 0) { carry += nvalid; continue; }
-                nm += __popc(mask);
-                const unsigned below = mask & ((1u << lane) - 1u);
-                const int run_before = below ? (lane - (31 - __clz(below)) - 1) : carry + lane;
-                const int nd = ndigits((uint32_t)run_before);
-                int total; const int off = warp_excl_scan(mism ? nd + 1 : 0, lane, total);
-                if (WRITE && mism) { write_dec(dst + len + off, (uint32_t)run_before, nd); dst[len + off + nd] = gb; }
-                len += total;
-                carry = nvalid - 1 - (31 - __clz(mask));
+            const bool exc = span_exc && warp_range_has_exc(G, g0, g0 + ct, lane);
+            for (int32_t c0 = 0; c0 < ct; c0 += (FAST ? 512 : 32)) {
+                const int span = min(FAST ? 512 : 32, ct - c0);
+                if (FAST) {
+                    bool bad = exc;
+                    if (!exc) {
+                        const int32_t lo = c0 + 16 * lane; int nb = ct - lo; nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+                        if (nb > 0) {
+                            const int a = (int)q + lo;
+                            const uint32_t* sp = reinterpret_cast<const uint32_t*>(seq) + (a >> 2); const int sh = (a & 3) * 8;
+                            const uint32_t x0 = sp[0], x1 = sp[1], x2 = sp[2], x3 = sp[3], x4 = sp[4];
+                            const int64_t gb = g0 + lo; const uint32_t* gp = G.g2 + (gb >> 4);
+                            const uint32_t gw = __funnelshift_r(gp[0], gp[1], (int)(gb & 15) * 2);
+                            uint32_t d0 = (__funnelshift_r(x0, x1, sh) & 0xDFDFDFDFu) ^ lut[gw & 255u];
+                            uint32_t d1 = (__funnelshift_r(x1, x2, sh) & 0xDFDFDFDFu) ^ lut[(gw >> 8) & 255u];
+                            uint32_t d2 = (__funnelshift_r(x2, x3, sh) & 0xDFDFDFDFu) ^ lut[(gw >> 16) & 255u];
+                            uint32_t d3 = (__funnelshift_r(x3, x4, sh) & 0xDFDFDFDFu) ^ lut[gw >> 24];
+                            if (nb < 16) {                              // the lane that holds the end of the run
+                                const uint32_t m0 = nb >= 4 ? ~0u : ((1u << (8 * nb)) - 1u);
+                                const uint32_t m1 = nb >= 8 ? ~0u : (nb <= 4 ? 0u : ((1u << (8 * (nb - 4))) - 1u));
+                                const uint32_t m2 = nb >= 12 ? ~0u : (nb <= 8 ? 0u : ((1u << (8 * (nb - 8))) - 1u));
+                                const uint32_t m3 = nb <= 12 ? 0u : ((1u << (8 * (nb - 12))) - 1u);
+                                d0 &= m0; d1 &= m1; d2 &= m2; d3 &= m3;
+                            }
+                            bad = (d0 | d1 | d2 | d3) != 0u;
+                        }
+                    }
+                    if (!__any_sync(FULL, bad)) { carry += span; continue; }
+                }
+                for (int32_t c = c0; c < c0 + span; c += 32) {           // exact path
+                    const int32_t idx = c + lane; const bool valid = idx < c0 + span;
+                    uint8_t rb = 0, gb = 0;
+                    if (valid) { rb = seq[q + idx]; gb = exc ? genome_byte(G, g0 + idx) : genome_byte_fast(G, g0 + idx); }
+                    const bool mism = valid && up8(rb) != up8(gb);
+                    const unsigned mask = __ballot_sync(FULL, mism);
+                    const int nvalid = min(32, c0 + span - c);
+                    if (mask == 0) { carry += nvalid; continue; }
+                    nm += __popc(mask); ntok += __popc(mask);
+                    const unsigned below = mask & ((1u << lane) - 1u);
+                    const int run_before = below ? (lane - (31 - __clz(below)) - 1) : carry + lane;
+                    const int nd = ndigits((uint32_t)run_before);
+                    int total; const int off = warp_excl_scan(mism ? nd + 1 : 0, lane, total);
+                    if (WRITE && mism) { write_dec(dst + len + off, (uint32_t)run_before, nd); dst[len + off + nd] = gb; }
+                    len += total;
+                    carry = nvalid - 1 - (31 - __clz(mask));
+                }
             }
             q += ct; g += ct;
         } else if (op == 'D') {
@@ -113,17 +171,19 @@ __device__ void warp_nmmd(const GenomeDev& G, const uint8_t* __restrict__ seq, c
                 if (lane == 0) { write_dec(dst + len, (uint32_t)carry, nd); dst[len + nd] = '^'; }
                 for (int j = lane; j < gl; j += 32) dst[len + nd + 1 + j] = genome_byte(G, goff + g + j);
             }
-            len += nd + 1 + gl; carry = 0; nm += ct; g += ct;
+            len += nd + 1 + gl; carry = 0; nm += ct; g += ct; ntok++;
         } else if (op == 'I') { q += ct; nm += ct; }
         else if (op == 'S') q += ct;
         else if (op == 'N' || op == 'H') g += ct;
     }
+    R.carry = carry;
     if (!none && carry > 0) {
         const int nd = ndigits((uint32_t)carry);
         if (WRITE && lane == 0) write_dec(dst + len, (uint32_t)carry, nd);
         len += nd;
     }
-    nm_out = nm; len_out = len; none_out = none;
+    R.nm = nm; R.len = len; R.none = none; R.ntok = ntok;
+    return R;
 }
 
 // grabs `len` bytes of an MD pool for the warp; returns the offset or -1 when the pool is full
@@ -133,6 +193,21 @@ __device__ __forceinline__ int64_t pool_grab(unsigned long long* cursor, int64_t
     if (lane == 0) off = atomicAdd(cursor, (unsigned long long)len);
     off = __shfl_sync(FULL, off, 0);
     return ((int64_t)off + len <= cap) ? (int64_t)off : -1;
+}
+
+// measure, allocate, write: MD of one read into a pool.  Reads without any token (the usual
+// case after correction) only need the final run length.
+template <bool FAST>
+__device__ __forceinline__ void nmmd_to_pool(const GenomeDev& G, const uint8_t* seq, const uint32_t* lut, const CigSrc& cs,
+                                             int chrom, int64_t pos, int lane, unsigned long long* cursor, int64_t cap,
+                                             uint8_t* pool, int& nm, int& len, int64_t& off, bool& none) {
+    NmMd r = warp_nmmd<false, FAST>(G, seq, lut, cs, chrom, pos, lane, 0);
+    none = r.none; nm = r.nm; len = r.none ? 0 : r.len;
+    off = pool_grab(cursor, cap, len, lane);
+    if (off >= 0 && len > 0) {
+        if (r.ntok == 0) { if (lane == 0) write_dec(pool + off, (uint32_t)r.carry, len); }
+        else warp_nmmd<true, FAST>(G, seq, lut, cs, chrom, pos, lane, pool + off);
+    }
 }
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_init(Params P, InitDev I, int32_t* nm_init) {
@@ -145,13 +220,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_init(Params P, InitDev
         if (cls == 0 && (!(tags & TAG_NM) || !(tags & TAG_MD))) {
             CigSrc cs; cs.packed = 0; cs.op = P.B.cig_op + P.B.cig_off[i]; cs.len = P.B.cig_len + P.B.cig_off[i];
             cs.n = (int)(P.B.cig_off[i + 1] - P.B.cig_off[i]);
-            const uint8_t* seq = P.B.seq + P.B.seq_off[i];
-            int nm, len; bool none;
-            warp_nmmd<false>(P.G, seq, cs, P.B.chrom[i], P.B.pos[i], lane, nm, len, none, 0);
+            int nm, len; int64_t off; bool none;
+            nmmd_to_pool<false>(P.G, P.B.seq + P.B.seq_off[i], 0, cs, P.B.chrom[i], P.B.pos[i], lane, I.cursor, I.cap, I.pool, nm, len, off, none);
             st |= TC_ST_NMMD_DEVICE;
-            if (none) { st |= TC_ST_NMMD_NONE; len = 0; nm = 0; }
-            int64_t off = pool_grab(I.cursor, I.cap, len, lane);
-            if (off >= 0 && len > 0) warp_nmmd<true>(P.G, seq, cs, P.B.chrom[i], P.B.pos[i], lane, nm, len, none, I.pool + off);
+            if (none) { st |= TC_ST_NMMD_NONE; nm = 0; }
             if (lane == 0) { P.W.md_init_off[i] = off < 0 ? 0 : off; P.W.md_init_len[i] = off < 0 ? 0 : len; nm_init[i] = nm; }
         }
         if (lane == 0) P.W.status[i] = st;
@@ -164,14 +236,26 @@ __global__ void k_junction(Params P) { int64_t i = (int64_t)blockIdx.x * blockDi
 __global__ void k_sizes(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) sizes_read(P, i); }
 __global__ void k_dry(Params P) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P.B.n) { dry_read(P, i); P.W.o_seq[i] = P.W.o_cig[i] = P.W.o_jn[i] = 0; P.W.o_te[i] = P.W.n_te[i]; }
+    if (i < P.B.n) { dry_read(P, i); P.W.o_seq[i] = P.W.o_cig[i] = P.W.o_jn[i] = 0; P.W.o_te[i] = P.W.n_te[i]; P.W.seq_len_out[i] = 0; }
 }
 
-// Output stage: one warp per read.
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit(Params P, OutDev O, int dry) {
+// Output stage: one warp per read.  `seq_words` = number of 32-bit words that may be read from
+// the input SEQ array (the buffer is padded).
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit(Params P, OutDev O, int dry, int64_t seq_words) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw);             // 4 bases (8 bits of the 2-bit plane) -> 4 ASCII bytes
+    EmitSmem& SM = reinterpret_cast<EmitSmem*>(smem_raw + 1024)[threadIdx.x >> 5];
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) {
+        const uint32_t acgt = 0x54474341u;
+        lut[t] = ((acgt >> (8 * (t & 3))) & 255u) | (((acgt >> (8 * ((t >> 2) & 3))) & 255u) << 8) |
+                 (((acgt >> (8 * ((t >> 4) & 3))) & 255u) << 16) | (((acgt >> (8 * ((t >> 6) & 3))) & 255u) << 24);
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     const int64_t nw = (int64_t)gridDim.x * WARPS_PER_BLOCK;
     const BatchDev& B = P.B; const WorkDev& W = P.W;
+    const uint32_t* S32 = reinterpret_cast<const uint32_t*>(B.seq);
     for (int64_t i = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); i < B.n; i += nw) {
         uint32_t st = W.status[i];
         if ((st & TC_ST_CLASS_MASK) != 0) { if (lane == 0) { O.md_off[i] = 0; O.md_len[i] = 0; O.nm[i] = 0; } continue; }
@@ -180,7 +264,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit(Params P, OutDev 
         {
             const int nte = W.n_te[i]; tc_te* dst = O.te + W.o_te[i];
             if (dry) { for (int k = lane; k < nte; k += 32) dst[k] = v.te[k]; }
-            else {
+            else if (nte > 0) {
                 int base[4]; base[0] = 0; base[1] = W.te_cnt[3 * i]; base[2] = base[1] + W.te_cnt[3 * i + 1];
                 base[3] = base[2] + W.te_cnt[3 * i + 2];
                 for (int c = 0; c < nte; c += 32) {
@@ -190,7 +274,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit(Params P, OutDev 
 #pragma unroll
                     for (int ty = 0; ty < 4; ty++) {
                         const unsigned m = __ballot_sync(FULL, t == ty);
-                        if (t == ty) dst[base[ty] + __popc(m & ((1u << lane) - 1u))] = r;
+                        if (t == ty) dst[base[ty] + __popc(m & lt)] = r;
                         base[ty] += __popc(m);
                     }
                 }
@@ -213,33 +297,102 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit(Params P, OutDev 
                 djm[k] = (int8_t)r[7]; dji[2 * k] = r[5]; dji[2 * k + 1] = r[6];
             }
         }
-        // ---- SEQ: slices of the input read and genome gathers
-        const uint8_t* in_seq = B.seq + B.seq_off[i];
+        // ---- SEQ
+        const int64_t in_base = B.seq_off[i];
+        const uint8_t* in_seq = B.seq + in_base;
+        const int64_t Lq = B.seq_off[i + 1] - in_base;
+        const int out_len = W.seq_len_out[i];
         uint8_t* out_seq = O.seq + W.o_seq[i];
-        if (W.seg_buf[i] < 0) {
-            const int64_t L = B.seq_off[i + 1] - B.seq_off[i];
-            for (int64_t j = lane; j < L; j += 32) out_seq[j] = in_seq[j];
+        const int chrom = B.chrom[i]; const int64_t pos = B.pos[i];
+        const int64_t gbase = P.G.chrom_off[chrom] - 1 + pos;            // plane index of the read's first reference base
+        const int sb = W.seg_buf[i];
+        bool fast = out_len <= EMIT_CAP;
+        int nbp = 0, ngi = 0;
+        if (fast) {
+            // (A) segment list -> starts of input slices (output offset, shift) + genome slices
+            if (sb < 0) { if (lane == 0) { SM.bp_pos[0] = 0; SM.bp_shift[0] = 0; } nbp = 1; }
+            else {
+                const u64* segs = v.seg[sb]; const int ns = W.n_seg_cur[i]; int obase = 0; bool bad = false;
+                for (int s0 = 0; s0 < ns; s0 += 32) {
+                    const int s = s0 + lane; const bool valid = s < ns;
+                    const u64 sg = valid ? segs[s] : 0ull;
+                    const int len = valid ? (int)seg_len(sg) : 0; const int64_t src = seg_src(sg); const int kind = seg_kind(sg);
+                    int total; const int ostart = obase + warp_excl_scan(len, lane, total);
+                    const bool isR = valid && kind == 0, isG = valid && kind == 1;
+                    const unsigned mR = __ballot_sync(FULL, isR), mG = __ballot_sync(FULL, isG);
+                    if (isR) {
+                        const int idx = nbp + __popc(mR & lt); const int64_t shift = src - ostart;
+                        if (idx < EMIT_MAXBP && shift >= -32768 && shift <= 32767) { SM.bp_pos[idx] = (uint16_t)ostart; SM.bp_shift[idx] = (int16_t)shift; }
+                        else bad = true;
+                    }
+                    if (isG) {
+                        const int idx = ngi + __popc(mG & lt); const int64_t rel = src - gbase;
+                        if (idx < EMIT_MAXGI && len <= 65535 && rel >= -2147483647ll && rel <= 2147483647ll) {
+                            SM.gi_out[idx] = (uint16_t)ostart; SM.gi_len[idx] = (uint16_t)len; SM.gi_src[idx] = (int32_t)rel;
+                        } else bad = true;
+                    }
+                    nbp += __popc(mR); ngi += __popc(mG); obase += total;
+                }
+                if (__any_sync(FULL, bad)) fast = false;
+            }
+        }
+        if (fast) {
+            __syncwarp();
+            const int nchunk = (out_len + 15) >> 4;
+            // (B) bulk copy, 16 output bytes per lane, with the shift in force at the chunk start
+            for (int c = lane; c < nchunk; c += 32) {
+                const int p = c << 4; int k = 0;
+                if (nbp > 1) {
+#pragma unroll
+                    for (int step = EMIT_MAXBP / 2; step; step >>= 1) { const int t = k + step; if (t < nbp && (int)SM.bp_pos[t] <= p) k = t; }
+                }
+                int64_t a = in_base + p + (nbp ? (int)SM.bp_shift[k] : 0);
+                if (a < 0) a = 0;
+                int64_t wi = a >> 2; const int sh = (int)(a & 3) * 8;
+                if (wi + 4 >= seq_words) wi = seq_words - 5;
+                const uint32_t x0 = S32[wi], x1 = S32[wi + 1], x2 = S32[wi + 2], x3 = S32[wi + 3], x4 = S32[wi + 4];
+                uint4 o; o.x = __funnelshift_r(x0, x1, sh); o.y = __funnelshift_r(x1, x2, sh); o.z = __funnelshift_r(x2, x3, sh); o.w = __funnelshift_r(x3, x4, sh);
+                *reinterpret_cast<uint4*>(SM.seq + p) = o;
+            }
+            __syncwarp();
+            // (C) the part of a chunk that follows a slice start inside it
+            for (int k = lane; k < nbp; k += 32) {
+                const int b = SM.bp_pos[k];
+                if (b & 15) {
+                    int end = (b | 15) + 1; if (end > out_len) end = out_len;
+                    if (k + 1 < nbp && (int)SM.bp_pos[k + 1] < end) end = SM.bp_pos[k + 1];
+                    const int sh = SM.bp_shift[k];
+                    for (int p = b; p < end; p++) SM.seq[p] = in_seq[p + sh];
+                }
+            }
+            __syncwarp();
+            // (D) genome slices (corrected mismatches, deletion fills, junction extensions): byte exact (Q6)
+            for (int k = lane; k < ngi; k += 32) {
+                const int o = SM.gi_out[k], len = SM.gi_len[k]; const int64_t src = gbase + SM.gi_src[k];
+                for (int j = 0; j < len; j++) SM.seq[o + j] = genome_byte(P.G, src + j);
+            }
+            __syncwarp();
+            // (E) one coalesced store of the row (rows are padded to 16 bytes)
+            for (int c = lane; c < nchunk; c += 32) reinterpret_cast<uint4*>(out_seq)[c] = *reinterpret_cast<const uint4*>(SM.seq + (c << 4));
+        } else if (sb < 0) {
+            for (int64_t j = lane; j < Lq; j += 32) out_seq[j] = in_seq[j];
         } else {
-            const u64* segs = v.seg[W.seg_buf[i]]; const int ns = W.n_seg_cur[i]; int64_t o = 0;
+            const u64* segs = v.seg[sb]; const int ns = W.n_seg_cur[i]; int64_t o = 0;
             for (int s = 0; s < ns; s++) {
                 const u64 sg = segs[s]; const int64_t src = seg_src(sg), len = seg_len(sg);
                 if (seg_kind(sg) == 0) { for (int64_t j = lane; j < len; j += 32) out_seq[o + j] = in_seq[src + j]; }
-                else {
-                    const bool exc = warp_range_has_exc(P.G, src, src + len, lane);
-                    for (int64_t j = lane; j < len; j += 32) out_seq[o + j] = exc ? genome_byte(P.G, src + j) : genome_byte_fast(P.G, src + j);
-                }
+                else { for (int64_t j = lane; j < len; j += 32) out_seq[o + j] = genome_byte(P.G, src + j); }
                 o += len;
             }
         }
         // ---- NM / MD
         if (W.refresh[i]) {
             __syncwarp();
-            int nm, len; bool none;
-            warp_nmmd<false>(P.G, out_seq, cs, B.chrom[i], B.pos[i], lane, nm, len, none, 0);
+            int nm, len; int64_t off; bool none;
+            if (fast) nmmd_to_pool<true>(P.G, SM.seq, lut, cs, chrom, pos, lane, O.md_cursor, O.md_cap, O.md_pool, nm, len, off, none);
+            else nmmd_to_pool<false>(P.G, out_seq, lut, cs, chrom, pos, lane, O.md_cursor, O.md_cap, O.md_pool, nm, len, off, none);
             st = (st & ~(uint32_t)TC_ST_NMMD_NONE) | TC_ST_NMMD_DEVICE;
-            if (none) { st |= TC_ST_NMMD_NONE; len = 0; }
-            const int64_t off = pool_grab(O.md_cursor, O.md_cap, len, lane);
-            if (off >= 0 && len > 0) warp_nmmd<true>(P.G, out_seq, cs, B.chrom[i], B.pos[i], lane, nm, len, none, O.md_pool + off);
+            if (none) st |= TC_ST_NMMD_NONE;
             if (lane == 0) { O.nm[i] = nm + W.nm_extra[i]; O.md_off[i] = off < 0 ? 0 : off; O.md_len[i] = off < 0 ? 0 : len; W.status[i] = st; }
         } else if (st & TC_ST_NMMD_DEVICE) {                           // generated at init and never refreshed
             const int len = W.md_init_len[i];
@@ -247,6 +400,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit(Params P, OutDev 
             if (off >= 0) { const uint8_t* s = W.md_init_pool + W.md_init_off[i]; for (int j = lane; j < len; j += 32) O.md_pool[off + j] = s[j]; }
             if (lane == 0) { O.nm[i] = W.nm_init[i]; O.md_off[i] = off < 0 ? 0 : off; O.md_len[i] = off < 0 ? 0 : len; }
         } else if (lane == 0) { O.nm[i] = 0; O.md_off[i] = 0; O.md_len[i] = 0; }
+        __syncwarp();
     }
 }
 
@@ -340,7 +494,7 @@ struct tc_ctx {
     // work
     DevBuf w_status, w_counters, w_md_init_off, w_md_init_len, w_nm_init, w_n_mdtok, w_n_jn, w_mflags,
         w_cig_cap, w_seg_cap, w_te_cap, w_ws_off, w_ws, w_cig_buf, w_n_cig_cur, w_seg_buf, w_n_seg_cur, w_n_te,
-        w_te_cnt, w_nm_extra, w_refresh, w_o_seq, w_o_cig, w_o_te, w_o_jn, init_pool, cursors, scan_tmp;
+        w_te_cnt, w_nm_extra, w_refresh, w_o_seq, w_o_cig, w_o_te, w_o_jn, w_seq_len, init_pool, cursors, scan_tmp;
     WorkDev W;
     // dense outputs on the device
     DevBuf o_nm, o_md_off, o_md_len, o_md_pool, o_seq, o_cig_op, o_cig_len, o_te, o_jm, o_ji;
@@ -348,7 +502,7 @@ struct tc_ctx {
     bool ran = false, ran_dry = false;
     // pinned host outputs
     HostBuf h_status, h_counters, h_nm, h_seq_off, h_seq, h_cig_off, h_cig_op, h_cig_len, h_md_off, h_md_len, h_md,
-        h_jn_off, h_jm, h_ji, h_te_off, h_te, h_tot;
+        h_jn_off, h_jm, h_ji, h_te_off, h_te, h_tot, h_seq_len;
     tc_timing tm;
 };
 
@@ -428,11 +582,11 @@ void tc_ctx_destroy(tc_ctx* ctx) {
                    &ctx->w_status, &ctx->w_counters, &ctx->w_md_init_off, &ctx->w_md_init_len, &ctx->w_nm_init, &ctx->w_n_mdtok, &ctx->w_n_jn,
                    &ctx->w_mflags, &ctx->w_cig_cap, &ctx->w_seg_cap, &ctx->w_te_cap, &ctx->w_ws_off, &ctx->w_ws, &ctx->w_cig_buf, &ctx->w_n_cig_cur,
                    &ctx->w_seg_buf, &ctx->w_n_seg_cur, &ctx->w_n_te, &ctx->w_te_cnt, &ctx->w_nm_extra, &ctx->w_refresh, &ctx->w_o_seq, &ctx->w_o_cig,
-                   &ctx->w_o_te, &ctx->w_o_jn, &ctx->init_pool, &ctx->cursors, &ctx->scan_tmp,
+                   &ctx->w_o_te, &ctx->w_o_jn, &ctx->w_seq_len, &ctx->init_pool, &ctx->cursors, &ctx->scan_tmp,
                    &ctx->o_nm, &ctx->o_md_off, &ctx->o_md_len, &ctx->o_md_pool, &ctx->o_seq, &ctx->o_cig_op, &ctx->o_cig_len, &ctx->o_te, &ctx->o_jm, &ctx->o_ji};
     for (DevBuf* b : d) b->release();
     HostBuf* h[] = {&ctx->h_status, &ctx->h_counters, &ctx->h_nm, &ctx->h_seq_off, &ctx->h_seq, &ctx->h_cig_off, &ctx->h_cig_op, &ctx->h_cig_len,
-                    &ctx->h_md_off, &ctx->h_md_len, &ctx->h_md, &ctx->h_jn_off, &ctx->h_jm, &ctx->h_ji, &ctx->h_te_off, &ctx->h_te, &ctx->h_tot};
+                    &ctx->h_md_off, &ctx->h_md_len, &ctx->h_md, &ctx->h_jn_off, &ctx->h_jm, &ctx->h_ji, &ctx->h_te_off, &ctx->h_te, &ctx->h_tot, &ctx->h_seq_len};
     for (HostBuf* b : h) b->release();
 #ifndef TC_HOSTSIM
     for (int k = 0; k < 12; k++) cudaEventDestroy(ctx->ev[k]);
@@ -569,7 +723,7 @@ static int alloc_work(tc_ctx* ctx) {
     CK(ctx->w_te_cap.ensure(n1 * 4)); CK(ctx->w_ws_off.ensure(n1 * 8)); CK(ctx->w_cig_buf.ensure(n1)); CK(ctx->w_n_cig_cur.ensure(n1 * 4));
     CK(ctx->w_seg_buf.ensure(n1)); CK(ctx->w_n_seg_cur.ensure(n1 * 4)); CK(ctx->w_n_te.ensure(n1 * 4)); CK(ctx->w_te_cnt.ensure(n1 * 12));
     CK(ctx->w_nm_extra.ensure(n1 * 4)); CK(ctx->w_refresh.ensure(n1)); CK(ctx->w_o_seq.ensure(n1 * 8)); CK(ctx->w_o_cig.ensure(n1 * 8));
-    CK(ctx->w_o_te.ensure(n1 * 8)); CK(ctx->w_o_jn.ensure(n1 * 8)); CK(ctx->cursors.ensure(64));
+    CK(ctx->w_o_te.ensure(n1 * 8)); CK(ctx->w_o_jn.ensure(n1 * 8)); CK(ctx->w_seq_len.ensure(n1 * 4)); CK(ctx->cursors.ensure(64));
     CK(ctx->o_nm.ensure(n1 * 4)); CK(ctx->o_md_off.ensure(n1 * 8)); CK(ctx->o_md_len.ensure(n1 * 4));
     WorkDev& W = ctx->W;
     W.status = (uint32_t*)ctx->w_status.p; W.counters = (int32_t*)ctx->w_counters.p;
@@ -579,7 +733,7 @@ static int alloc_work(tc_ctx* ctx) {
     W.ws_off = (int64_t*)ctx->w_ws_off.p; W.cig_buf = (int8_t*)ctx->w_cig_buf.p; W.n_cig_cur = (int32_t*)ctx->w_n_cig_cur.p;
     W.seg_buf = (int8_t*)ctx->w_seg_buf.p; W.n_seg_cur = (int32_t*)ctx->w_n_seg_cur.p; W.n_te = (int32_t*)ctx->w_n_te.p;
     W.te_cnt = (int32_t*)ctx->w_te_cnt.p; W.nm_extra = (int32_t*)ctx->w_nm_extra.p; W.refresh = (uint8_t*)ctx->w_refresh.p;
-    W.o_seq = (int64_t*)ctx->w_o_seq.p; W.o_cig = (int64_t*)ctx->w_o_cig.p; W.o_te = (int64_t*)ctx->w_o_te.p; W.o_jn = (int64_t*)ctx->w_o_jn.p;
+    W.o_seq = (int64_t*)ctx->w_o_seq.p; W.o_cig = (int64_t*)ctx->w_o_cig.p; W.o_te = (int64_t*)ctx->w_o_te.p; W.o_jn = (int64_t*)ctx->w_o_jn.p; W.seq_len_out = (int32_t*)ctx->w_seq_len.p;
     return 0;
 }
 
@@ -689,6 +843,10 @@ int tc_batch_run(tc_ctx* ctx, int dry) {
     ctx->tot_seq = tot[1]; ctx->tot_cig = tot[2]; ctx->tot_te = tot[3]; ctx->tot_jn = tot[4];
     CK(ctx->o_seq.ensure((size_t)ctx->tot_seq + 64)); CK(ctx->o_cig_op.ensure((size_t)ctx->tot_cig + 64)); CK(ctx->o_cig_len.ensure((size_t)ctx->tot_cig * 4 + 64));
     CK(ctx->o_te.ensure((size_t)ctx->tot_te * 16 + 64)); CK(ctx->o_jm.ensure((size_t)ctx->tot_jn + 64)); CK(ctx->o_ji.ensure((size_t)ctx->tot_jn * 8 + 64));
+    CK(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMIT_SMEM_BYTES));
+    int occ = 1; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_emit, WARPS_PER_BLOCK * 32, EMIT_SMEM_BYTES));
+    int ge = (int)(wb < (int64_t)nsm * occ ? wb : (int64_t)nsm * occ);
+    const int64_t seq_words = (int64_t)(ctx->b_seq.cap / 4);
     int64_t md_cap = ctx->o_md_pool.cap > 0 ? (int64_t)ctx->o_md_pool.cap : (64 * n + 8 * ctx->n_cig + (1 << 20));
     CK(cudaEventRecord(ctx->ev[7], ctx->stream));
     for (int attempt = 0;; attempt++) {
@@ -697,7 +855,7 @@ int tc_batch_run(tc_ctx* ctx, int dry) {
         OutDev O; O.nm = (int32_t*)ctx->o_nm.p; O.md_off = (int64_t*)ctx->o_md_off.p; O.md_len = (int32_t*)ctx->o_md_len.p;
         O.md_pool = (uint8_t*)ctx->o_md_pool.p; O.md_cursor = cur; O.md_cap = md_cap; O.seq = (uint8_t*)ctx->o_seq.p;
         O.cig_op = (uint8_t*)ctx->o_cig_op.p; O.cig_len = (int32_t*)ctx->o_cig_len.p; O.te = (tc_te*)ctx->o_te.p; O.jm = (int8_t*)ctx->o_jm.p; O.ji = (int32_t*)ctx->o_ji.p;
-        k_emit<<<gw, WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(P, O, dry); ctx->tm.launches++;
+        k_emit<<<ge, WARPS_PER_BLOCK * 32, EMIT_SMEM_BYTES, ctx->stream>>>(P, O, dry, seq_words); ctx->tm.launches++;
         CK(cudaGetLastError());
         if (attempt == 0) CK(cudaEventRecord(ctx->ev[8], ctx->stream));
         if (be_read_i64(ctx, (const int64_t*)cur, tot) || be_sync(ctx)) return TC_E_CUDA;
@@ -724,7 +882,7 @@ int tc_batch_run(tc_ctx* ctx, int dry) {
     ctx->W.ws_off[n] = 0; be_scan(ctx, ctx->W.ws_off, n + 1);
     CK(ctx->w_ws.ensure((size_t)(ctx->W.ws_off[n] + 8) * 8)); ctx->W.ws = (u64*)ctx->w_ws.p; P.W.ws = ctx->W.ws;
     for (int64_t i = 0; i < n; i++) {
-        if (dry) { dry_read(P, i); P.W.o_seq[i] = P.W.o_cig[i] = P.W.o_jn[i] = 0; P.W.o_te[i] = P.W.n_te[i]; }
+        if (dry) { dry_read(P, i); P.W.o_seq[i] = P.W.o_cig[i] = P.W.o_jn[i] = 0; P.W.o_te[i] = P.W.n_te[i]; P.W.seq_len_out[i] = 0; }
         else { plan_read(P, i); junction_read(P, i); sizes_read(P, i); }
     }
     int64_t* sc[4] = {ctx->W.o_seq, ctx->W.o_cig, ctx->W.o_te, ctx->W.o_jn};
@@ -757,7 +915,7 @@ int tc_batch_download(tc_ctx* ctx, tc_batch_out* out) {
         if (be_d2h(ctx, ctx->h_status, ctx->W.status, (size_t)n * 4) || be_d2h(ctx, ctx->h_counters, ctx->W.counters, (size_t)n * 40) ||
             be_d2h(ctx, ctx->h_te_off, ctx->W.o_te, n1 * 8) || be_d2h(ctx, ctx->h_te, ctx->o_te.p, (size_t)ctx->tot_te * 16)) return TC_E_CUDA;
         if (!ctx->ran_dry) {
-            if (be_d2h(ctx, ctx->h_nm, ctx->o_nm.p, (size_t)n * 4) || be_d2h(ctx, ctx->h_seq_off, ctx->W.o_seq, n1 * 8) ||
+            if (be_d2h(ctx, ctx->h_nm, ctx->o_nm.p, (size_t)n * 4) || be_d2h(ctx, ctx->h_seq_off, ctx->W.o_seq, n1 * 8) || be_d2h(ctx, ctx->h_seq_len, ctx->W.seq_len_out, (size_t)n * 4) ||
                 be_d2h(ctx, ctx->h_seq, ctx->o_seq.p, (size_t)ctx->tot_seq) || be_d2h(ctx, ctx->h_cig_off, ctx->W.o_cig, n1 * 8) ||
                 be_d2h(ctx, ctx->h_cig_op, ctx->o_cig_op.p, (size_t)ctx->tot_cig) || be_d2h(ctx, ctx->h_cig_len, ctx->o_cig_len.p, (size_t)ctx->tot_cig * 4) ||
                 be_d2h(ctx, ctx->h_md_off, ctx->o_md_off.p, (size_t)n * 8) || be_d2h(ctx, ctx->h_md_len, ctx->o_md_len.p, (size_t)n * 4) ||
@@ -774,7 +932,7 @@ int tc_batch_download(tc_ctx* ctx, tc_batch_out* out) {
 #endif
     }
     out->status = (const uint32_t*)ctx->h_status.p; out->counters = (const int32_t*)ctx->h_counters.p; out->nm = (const int32_t*)ctx->h_nm.p;
-    out->seq_off = (const int64_t*)ctx->h_seq_off.p; out->seq = (const uint8_t*)ctx->h_seq.p;
+    out->seq_off = (const int64_t*)ctx->h_seq_off.p; out->seq_len = (const int32_t*)ctx->h_seq_len.p; out->seq = (const uint8_t*)ctx->h_seq.p;
     out->cig_off = (const int64_t*)ctx->h_cig_off.p; out->cig_op = (const uint8_t*)ctx->h_cig_op.p; out->cig_len = (const int32_t*)ctx->h_cig_len.p;
     out->md_off = (const int64_t*)ctx->h_md_off.p; out->md_len = (const int32_t*)ctx->h_md_len.p; out->md = (const uint8_t*)ctx->h_md.p;
     out->jn_off = (const int64_t*)ctx->h_jn_off.p; out->jm = (const int8_t*)ctx->h_jm.p; out->ji = (const int32_t*)ctx->h_ji.p;

@@ -73,6 +73,7 @@ struct WorkDev {
     int32_t* nm_extra; uint8_t* refresh;
     // exact output sizes, turned into offsets (n+1) by exclusive scans
     int64_t *o_seq, *o_cig, *o_te, *o_jn;
+    int32_t* seq_len_out;    // exact length of the new SEQ (o_seq offsets are padded to 16 bytes)
 };
 
 enum { MF_HAS_I = 1, MF_HAS_D = 2, MF_HAS_N = 4, MF_MD_ACGTN = 8 };
@@ -728,11 +729,12 @@ TC_HD void junction_read(const Params& P, int64_t i) {
 TC_HD void sizes_read(const Params& P, int64_t i) {
     const BatchDev& B = P.B; const WorkDev& W = P.W;
     uint32_t st = W.status[i];
-    if ((st & TC_ST_CLASS_MASK) != 0) { W.o_seq[i] = W.o_cig[i] = W.o_te[i] = W.o_jn[i] = 0; return; }
+    if ((st & TC_ST_CLASS_MASK) != 0) { W.o_seq[i] = W.o_cig[i] = W.o_te[i] = W.o_jn[i] = 0; W.seq_len_out[i] = 0; return; }
     int64_t sl;
     if (W.seg_buf[i] < 0) sl = B.seq_off[i + 1] - B.seq_off[i];
     else { WsView v = ws_view(W, i); sl = 0; const u64* s = v.seg[W.seg_buf[i]]; for (int k = 0; k < W.n_seg_cur[i]; k++) sl += seg_len(s[k]); }
-    W.o_seq[i] = sl;
+    W.o_seq[i] = (sl + 15) & ~15ll;                 // 16-byte aligned rows: tc_emit stores whole uint4
+    W.seq_len_out[i] = (int32_t)sl;
     W.o_cig[i] = W.cig_buf[i] < 0 ? (B.cig_off[i + 1] - B.cig_off[i]) : W.n_cig_cur[i];
     W.o_te[i] = W.n_te[i];
     W.o_jn[i] = W.n_jn[i];

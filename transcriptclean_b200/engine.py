@@ -34,7 +34,7 @@ class _BatchIn(C.Structure):
 
 class _BatchOut(C.Structure):
     _fields_ = [("n_reads", C.c_int64)] + [(n, C.c_void_p) for n in (
-        "status", "counters", "nm", "seq_off", "seq", "cig_off", "cig_op", "cig_len", "md_off", "md_len", "md",
+        "status", "counters", "nm", "seq_off", "seq_len", "seq", "cig_off", "cig_op", "cig_len", "md_off", "md_len", "md",
         "jn_off", "jm", "ji", "te_off", "te")]
 
 
@@ -112,6 +112,7 @@ class BatchResult:
             return
         self.nm = arr(out.nm, np.int32, n)
         self.seq_off = arr(out.seq_off, np.int64, n + 1) if n else np.zeros(1, np.int64)
+        self.seq_len = arr(out.seq_len, np.int32, n)
         self.seq = arr(out.seq, np.uint8, int(self.seq_off[-1]))
         self.cig_off = arr(out.cig_off, np.int64, n + 1) if n else np.zeros(1, np.int64)
         self.cig_op = arr(out.cig_op, np.uint8, int(self.cig_off[-1]))
