@@ -82,7 +82,8 @@ __device__ __forceinline__ bool warp_range_has_exc(const GenomeDev& G, int64_t g
 
 struct NmMd { int nm, len, ntok, carry; bool none; };
 
-// getNMandMDFlags (tr.py:280-342, Q8/Q9).  One warp walks the CIGAR.
+// getNMandMDFlags (tr.py:280-342, Q8/Q9).  One warp walks the CIGAR (ops are fetched 32 at a
+// time, one per lane, and broadcast with shuffles; cursors are 32-bit offsets from POS).
 //  FAST (SEQ staged in shared memory, 16-byte aligned): every lane takes 16 bases of an M run -
 //    five LDS.32 + funnel shifts for the read bytes, two coalesced words of the 2-bit plane,
 //    a 256-entry code->ASCII table, one XOR per 4 bases; a 512-base chunk without difference
@@ -96,85 +97,95 @@ template <bool WRITE, bool FAST>
 __device__ NmMd warp_nmmd(const GenomeDev& G, const uint8_t* seq, const uint32_t* lut, const CigSrc& cs, int chrom,
                           int64_t pos, int lane, uint8_t* dst) {
     const int64_t goff = G.chrom_off[chrom] - 1, clen = G.chrom_len[chrom];
-    NmMd R; R.nm = 0; R.len = 0; R.ntok = 0; R.carry = 0; R.none = false;
-    int nm = 0, len = 0, carry = 0, ntok = 0; int64_t q = 0, g = pos; bool none = false;
-    // one literal-run check for the whole reference span; per-op checks only when it hits
-    bool span_exc;
+    const int64_t gbase = goff + pos;                   // plane index of reference offset 0
+    NmMd R;
+    int nm = 0, len = 0, carry = 0, ntok = 0, q = 0, gr = 0; bool none = false;
+    // reference span: one literal-run check and one contig-end check for the whole read
+    bool span_exc, careful;
     {
         int64_t span = 0;
         for (int k = lane; k < cs.n; k += 32) { int op; int32_t ct; cig_get(cs, k, op, ct); if (op == 'M' || op == 'D' || op == 'N' || op == 'H') span += ct; }
 #pragma unroll
         for (int d = 16; d; d >>= 1) span += __shfl_xor_sync(FULL, span, d);
-        int64_t e = pos + span; if (e > clen + 1) e = clen + 1;
-        span_exc = (pos >= 1 && e > pos) ? warp_range_has_exc(G, goff + pos, goff + e, lane) : true;
+        careful = pos < 1 || pos + span - 1 > clen || span > 0x7fffffffll;
+        span_exc = careful || (span > 0 && warp_range_has_exc(G, gbase, gbase + span, lane));
     }
-    for (int k = 0; k < cs.n && !none; k++) {
-        int op; int32_t ct; cig_get(cs, k, op, ct);
-        if (op == 'M') {
-            if (ct <= 0) continue;
-            if (g < 1 || g + ct - 1 > clen) { none = true; break; }   // empty fetch (tr.py:303-304)
-            const int64_t g0 = goff + g;
-            const bool exc = span_exc && warp_range_has_exc(G, g0, g0 + ct, lane);
-            for (int32_t c0 = 0; c0 < ct; c0 += (FAST ? 512 : 32)) {
-                const int span = min(FAST ? 512 : 32, ct - c0);
-                if (FAST) {
-                    bool bad = exc;
-                    if (!exc) {
-                        const int32_t lo = c0 + 16 * lane; int nb = ct - lo; nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-                        if (nb > 0) {
-                            const int a = (int)q + lo;
-                            const uint32_t* sp = reinterpret_cast<const uint32_t*>(seq) + (a >> 2); const int sh = (a & 3) * 8;
-                            const uint32_t x0 = sp[0], x1 = sp[1], x2 = sp[2], x3 = sp[3], x4 = sp[4];
-                            const int64_t gb = g0 + lo; const uint32_t* gp = G.g2 + (gb >> 4);
-                            const uint32_t gw = __funnelshift_r(gp[0], gp[1], (int)(gb & 15) * 2);
-                            uint32_t d0 = (__funnelshift_r(x0, x1, sh) & 0xDFDFDFDFu) ^ lut[gw & 255u];
-                            uint32_t d1 = (__funnelshift_r(x1, x2, sh) & 0xDFDFDFDFu) ^ lut[(gw >> 8) & 255u];
-                            uint32_t d2 = (__funnelshift_r(x2, x3, sh) & 0xDFDFDFDFu) ^ lut[(gw >> 16) & 255u];
-                            uint32_t d3 = (__funnelshift_r(x3, x4, sh) & 0xDFDFDFDFu) ^ lut[gw >> 24];
-                            if (nb < 16) {                              // the lane that holds the end of the run
-                                const uint32_t m0 = nb >= 4 ? ~0u : ((1u << (8 * nb)) - 1u);
-                                const uint32_t m1 = nb >= 8 ? ~0u : (nb <= 4 ? 0u : ((1u << (8 * (nb - 4))) - 1u));
-                                const uint32_t m2 = nb >= 12 ? ~0u : (nb <= 8 ? 0u : ((1u << (8 * (nb - 8))) - 1u));
-                                const uint32_t m3 = nb <= 12 ? 0u : ((1u << (8 * (nb - 12))) - 1u);
-                                d0 &= m0; d1 &= m1; d2 &= m2; d3 &= m3;
+    for (int k0 = 0; k0 < cs.n && !none; k0 += 32) {
+        int op_l = 0; int32_t ct_l = 0;
+        if (k0 + lane < cs.n) cig_get(cs, k0 + lane, op_l, ct_l);
+        const int nround = min(32, cs.n - k0);
+        for (int j = 0; j < nround; j++) {
+            const int op = __shfl_sync(FULL, op_l, j); const int32_t ct = __shfl_sync(FULL, ct_l, j);
+            if (op == 'M') {
+                if (ct <= 0) continue;
+                if (careful) { const int64_t g = pos + gr; if (g < 1 || g + ct - 1 > clen) { none = true; break; } }   // tr.py:303-304
+                const int64_t g0 = gbase + gr;
+                const bool exc = span_exc && warp_range_has_exc(G, g0, g0 + ct, lane);
+                for (int32_t c0 = 0; c0 < ct; c0 += (FAST ? 512 : 32)) {
+                    const int span = min(FAST ? 512 : 32, ct - c0);
+                    if (FAST) {
+                        bool bad = exc;
+                        if (!exc) {
+                            const int32_t lo = c0 + 16 * lane; int nb = ct - lo; nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+                            if (nb > 0) {
+                                const int a = q + lo;
+                                const uint32_t* sp = reinterpret_cast<const uint32_t*>(seq) + (a >> 2); const int sh = (a & 3) * 8;
+                                const uint32_t x0 = sp[0], x1 = sp[1], x2 = sp[2], x3 = sp[3], x4 = sp[4];
+                                const int64_t gb = g0 + lo; const uint32_t* gp = G.g2 + (gb >> 4);
+                                const uint32_t gw = __funnelshift_r(gp[0], gp[1], (int)(gb & 15) * 2);
+                                uint32_t d0 = (__funnelshift_r(x0, x1, sh) & 0xDFDFDFDFu) ^ lut[gw & 255u];
+                                uint32_t d1 = (__funnelshift_r(x1, x2, sh) & 0xDFDFDFDFu) ^ lut[(gw >> 8) & 255u];
+                                uint32_t d2 = (__funnelshift_r(x2, x3, sh) & 0xDFDFDFDFu) ^ lut[(gw >> 16) & 255u];
+                                uint32_t d3 = (__funnelshift_r(x3, x4, sh) & 0xDFDFDFDFu) ^ lut[gw >> 24];
+                                if (nb < 16) {                          // the lane that holds the end of the run
+                                    const uint32_t m0 = nb >= 4 ? ~0u : ((1u << (8 * nb)) - 1u);
+                                    const uint32_t m1 = nb >= 8 ? ~0u : (nb <= 4 ? 0u : ((1u << (8 * (nb - 4))) - 1u));
+                                    const uint32_t m2 = nb >= 12 ? ~0u : (nb <= 8 ? 0u : ((1u << (8 * (nb - 8))) - 1u));
+                                    const uint32_t m3 = nb <= 12 ? 0u : ((1u << (8 * (nb - 12))) - 1u);
+                                    d0 &= m0; d1 &= m1; d2 &= m2; d3 &= m3;
+                                }
+                                bad = (d0 | d1 | d2 | d3) != 0u;
                             }
-                            bad = (d0 | d1 | d2 | d3) != 0u;
                         }
+                        if (!__any_sync(FULL, bad)) { carry += span; continue; }
                     }
-                    if (!__any_sync(FULL, bad)) { carry += span; continue; }
+                    for (int32_t c = c0; c < c0 + span; c += 32) {       // exact path
+                        const int32_t idx = c + lane; const bool valid = idx < c0 + span;
+                        uint8_t rb = 0, gb = 0;
+                        if (valid) { rb = seq[q + idx]; gb = exc ? genome_byte(G, g0 + idx) : genome_byte_fast(G, g0 + idx); }
+                        const bool mism = valid && up8(rb) != up8(gb);
+                        const unsigned mask = __ballot_sync(FULL, mism);
+                        const int nvalid = min(32, c0 + span - c);
+                        if (mask == 0) { carry += nvalid; continue; }
+                        nm += __popc(mask); ntok += __popc(mask);
+                        const unsigned below = mask & ((1u << lane) - 1u);
+                        const int run_before = below ? (lane - (31 - __clz(below)) - 1) : carry + lane;
+                        const int nd = ndigits((uint32_t)run_before);
+                        int total; const int off = warp_excl_scan(mism ? nd + 1 : 0, lane, total);
+                        if (WRITE && mism) { write_dec(dst + len + off, (uint32_t)run_before, nd); dst[len + off + nd] = gb; }
+                        len += total;
+                        carry = nvalid - 1 - (31 - __clz(mask));
+                    }
                 }
-                for (int32_t c = c0; c < c0 + span; c += 32) {           // exact path
-                    const int32_t idx = c + lane; const bool valid = idx < c0 + span;
-                    uint8_t rb = 0, gb = 0;
-                    if (valid) { rb = seq[q + idx]; gb = exc ? genome_byte(G, g0 + idx) : genome_byte_fast(G, g0 + idx); }
-                    const bool mism = valid && up8(rb) != up8(gb);
-                    const unsigned mask = __ballot_sync(FULL, mism);
-                    const int nvalid = min(32, c0 + span - c);
-                    if (mask == 0) { carry += nvalid; continue; }
-                    nm += __popc(mask); ntok += __popc(mask);
-                    const unsigned below = mask & ((1u << lane) - 1u);
-                    const int run_before = below ? (lane - (31 - __clz(below)) - 1) : carry + lane;
-                    const int nd = ndigits((uint32_t)run_before);
-                    int total; const int off = warp_excl_scan(mism ? nd + 1 : 0, lane, total);
-                    if (WRITE && mism) { write_dec(dst + len + off, (uint32_t)run_before, nd); dst[len + off + nd] = gb; }
-                    len += total;
-                    carry = nvalid - 1 - (31 - __clz(mask));
+                q += ct; gr += ct;
+            } else if (op == 'D') {
+                int gl = ct;
+                if (careful) {
+                    const int64_t g = pos + gr;
+                    if (g < 1) { none = true; break; }
+                    gl = fetch_len(G, chrom, g, g + ct - 1);
+                    if (gl == 0) { none = true; break; }                // tr.py:327-328
                 }
-            }
-            q += ct; g += ct;
-        } else if (op == 'D') {
-            if (g < 1) { none = true; break; }
-            const int gl = fetch_len(G, chrom, g, g + ct - 1);
-            if (gl == 0) { none = true; break; }                       // tr.py:327-328
-            const int nd = ndigits((uint32_t)carry);
-            if (WRITE) {
-                if (lane == 0) { write_dec(dst + len, (uint32_t)carry, nd); dst[len + nd] = '^'; }
-                for (int j = lane; j < gl; j += 32) dst[len + nd + 1 + j] = genome_byte(G, goff + g + j);
-            }
-            len += nd + 1 + gl; carry = 0; nm += ct; g += ct; ntok++;
-        } else if (op == 'I') { q += ct; nm += ct; }
-        else if (op == 'S') q += ct;
-        else if (op == 'N' || op == 'H') g += ct;
+                const int nd = ndigits((uint32_t)carry);
+                if (WRITE) {
+                    if (lane == 0) { write_dec(dst + len, (uint32_t)carry, nd); dst[len + nd] = '^'; }
+                    for (int t = lane; t < gl; t += 32) dst[len + nd + 1 + t] = genome_byte(G, gbase + gr + t);
+                }
+                len += nd + 1 + gl; carry = 0; nm += ct; gr += ct; ntok++;
+            } else if (op == 'I') { q += ct; nm += ct; }
+            else if (op == 'S') q += ct;
+            else if (op == 'N' || op == 'H') gr += ct;
+        }
     }
     R.carry = carry;
     if (!none && carry > 0) {
@@ -236,7 +247,7 @@ __global__ void k_junction(Params P) { int64_t i = (int64_t)blockIdx.x * blockDi
 __global__ void k_sizes(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) sizes_read(P, i); }
 __global__ void k_dry(Params P) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P.B.n) { dry_read(P, i); P.W.o_seq[i] = P.W.o_cig[i] = P.W.o_jn[i] = 0; P.W.o_te[i] = P.W.n_te[i]; P.W.seq_len_out[i] = 0; }
+    if (i < P.B.n) { dry_read(P, i); dry_sizes(P, i); }
 }
 
 // Output stage: one warp per read.  `seq_words` = number of 32-bit words that may be read from
@@ -259,18 +270,24 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit(Params P, OutDev 
     for (int64_t i = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); i < B.n; i += nw) {
         uint32_t st = W.status[i];
         if ((st & TC_ST_CLASS_MASK) != 0) { if (lane == 0) { O.md_off[i] = 0; O.md_len[i] = 0; O.nm[i] = 0; } continue; }
-        WsView v = ws_view(W, i);
+        // the read's plan row: one word per lane, fields broadcast by shuffle
+        const int pw = lane < 16 ? W.plan[i].w[lane] : 0;
+#define PF(k) __shfl_sync(FULL, pw, (k))
+        const int pflags = PF(EP_FLAGS), cig_cap = PF(EP_CIGCAP), seg_cap = PF(EP_SEGCAP), nm_extra = PF(EP_NMEXTRA);
+        const int cb = ((pflags >> 2) & 3) - 1, sb = ((pflags >> 4) & 3) - 1;
+        u64* const ws = W.ws + W.ws_off[i];
+        const tc_te* const ws_te = reinterpret_cast<const tc_te*>(ws + 3ll * cig_cap + 3ll * seg_cap);
         // ---- TE rows: stage order (mismatch, insertion, deletion, junction), positional inside
-        {
-            const int nte = W.n_te[i]; tc_te* dst = O.te + W.o_te[i];
-            if (dry) { for (int k = lane; k < nte; k += 32) dst[k] = v.te[k]; }
-            else if (nte > 0) {
-                int base[4]; base[0] = 0; base[1] = W.te_cnt[3 * i]; base[2] = base[1] + W.te_cnt[3 * i + 1];
-                base[3] = base[2] + W.te_cnt[3 * i + 2];
+        const int nte = PF(EP_NTE);
+        if (nte > 0) {
+            tc_te* dst = O.te + W.o_te[i];
+            if (dry) { for (int k = lane; k < nte; k += 32) dst[k] = ws_te[k]; }
+            else {
+                int base[4]; base[0] = 0; base[1] = PF(EP_TEMM); base[2] = base[1] + PF(EP_TEINS); base[3] = base[2] + PF(EP_TEDEL);
                 for (int c = 0; c < nte; c += 32) {
                     const int k = c + lane; const bool valid = k < nte;
                     tc_te r; int t = -1;
-                    if (valid) { r = v.te[k]; t = r.type; }
+                    if (valid) { r = ws_te[k]; t = r.type; }
 #pragma unroll
                     for (int ty = 0; ty < 4; ty++) {
                         const unsigned m = __ballot_sync(FULL, t == ty);
@@ -282,18 +299,20 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit(Params P, OutDev 
         }
         if (dry) { if (lane == 0) { O.md_off[i] = 0; O.md_len[i] = 0; O.nm[i] = 0; } continue; }
         // ---- CIGAR
-        CigSrc cs;
-        if (W.cig_buf[i] < 0) { cs.packed = 0; cs.op = B.cig_op + B.cig_off[i]; cs.len = B.cig_len + B.cig_off[i]; cs.n = (int)(B.cig_off[i + 1] - B.cig_off[i]); }
-        else { cs.packed = v.cig[W.cig_buf[i]]; cs.op = 0; cs.len = 0; cs.n = W.n_cig_cur[i]; }
+        CigSrc cs; cs.n = PF(EP_NCIG);
+        if (cb < 0) { cs.packed = 0; cs.op = B.cig_op + B.cig_off[i]; cs.len = B.cig_len + B.cig_off[i]; }
+        else { cs.packed = ws + (int64_t)cb * cig_cap; cs.op = 0; cs.len = 0; }
         {
-            uint8_t* dop = O.cig_op + W.o_cig[i]; int32_t* dl = O.cig_len + W.o_cig[i];
+            const int64_t oc = W.o_cig[i]; uint8_t* dop = O.cig_op + oc; int32_t* dl = O.cig_len + oc;
             for (int k = lane; k < cs.n; k += 32) { int op; int32_t l; cig_get(cs, k, op, l); dop[k] = (uint8_t)op; dl[k] = l; }
         }
         // ---- jM / jI snapshot
-        {
-            const int nj = W.n_jn[i]; int8_t* djm = O.jm + W.o_jn[i]; int32_t* dji = O.ji + 2 * W.o_jn[i];
+        const int nj = PF(EP_NJN);
+        if (nj > 0) {
+            const int64_t oj = W.o_jn[i]; int8_t* djm = O.jm + oj; int32_t* dji = O.ji + 2 * oj;
+            const int32_t* jn = reinterpret_cast<const int32_t*>(ws + 3ll * cig_cap + 3ll * seg_cap + 2ll * PF(EP_TECAP));
             for (int k = lane; k < nj; k += 32) {
-                const int32_t* r = v.jn + k * JN_STRIDE;
+                const int32_t* r = jn + k * JN_STRIDE;
                 djm[k] = (int8_t)r[7]; dji[2 * k] = r[5]; dji[2 * k + 1] = r[6];
             }
         }
@@ -301,18 +320,19 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit(Params P, OutDev 
         const int64_t in_base = B.seq_off[i];
         const uint8_t* in_seq = B.seq + in_base;
         const int64_t Lq = B.seq_off[i + 1] - in_base;
-        const int out_len = W.seq_len_out[i];
+        const int out_len = PF(EP_OUTLEN);
         uint8_t* out_seq = O.seq + W.o_seq[i];
         const int chrom = B.chrom[i]; const int64_t pos = B.pos[i];
         const int64_t gbase = P.G.chrom_off[chrom] - 1 + pos;            // plane index of the read's first reference base
-        const int sb = W.seg_buf[i];
+        const u64* const ws_seg = ws + 3ll * cig_cap + (int64_t)(sb < 0 ? 0 : sb) * seg_cap;
+        const int ns = PF(EP_NSEG);
         bool fast = out_len <= EMIT_CAP;
         int nbp = 0, ngi = 0;
         if (fast) {
             // (A) segment list -> starts of input slices (output offset, shift) + genome slices
             if (sb < 0) { if (lane == 0) { SM.bp_pos[0] = 0; SM.bp_shift[0] = 0; } nbp = 1; }
             else {
-                const u64* segs = v.seg[sb]; const int ns = W.n_seg_cur[i]; int obase = 0; bool bad = false;
+                const u64* segs = ws_seg; int obase = 0; bool bad = false;
                 for (int s0 = 0; s0 < ns; s0 += 32) {
                     const int s = s0 + lane; const bool valid = s < ns;
                     const u64 sg = valid ? segs[s] : 0ull;
@@ -339,13 +359,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit(Params P, OutDev 
         if (fast) {
             __syncwarp();
             const int nchunk = (out_len + 15) >> 4;
+            int top = 1; while (top * 2 < nbp) top <<= 1; if (nbp <= 1) top = 0;
             // (B) bulk copy, 16 output bytes per lane, with the shift in force at the chunk start
             for (int c = lane; c < nchunk; c += 32) {
                 const int p = c << 4; int k = 0;
-                if (nbp > 1) {
-#pragma unroll
-                    for (int step = EMIT_MAXBP / 2; step; step >>= 1) { const int t = k + step; if (t < nbp && (int)SM.bp_pos[t] <= p) k = t; }
-                }
+                for (int step = top; step; step >>= 1) { const int t = k + step; if (t < nbp && (int)SM.bp_pos[t] <= p) k = t; }
                 int64_t a = in_base + p + (nbp ? (int)SM.bp_shift[k] : 0);
                 if (a < 0) a = 0;
                 int64_t wi = a >> 2; const int sh = (int)(a & 3) * 8;
@@ -377,7 +395,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit(Params P, OutDev 
         } else if (sb < 0) {
             for (int64_t j = lane; j < Lq; j += 32) out_seq[j] = in_seq[j];
         } else {
-            const u64* segs = v.seg[sb]; const int ns = W.n_seg_cur[i]; int64_t o = 0;
+            const u64* segs = ws_seg; int64_t o = 0;
             for (int s = 0; s < ns; s++) {
                 const u64 sg = segs[s]; const int64_t src = seg_src(sg), len = seg_len(sg);
                 if (seg_kind(sg) == 0) { for (int64_t j = lane; j < len; j += 32) out_seq[o + j] = in_seq[src + j]; }
@@ -386,14 +404,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit(Params P, OutDev 
             }
         }
         // ---- NM / MD
-        if (W.refresh[i]) {
+        if (pflags & 1) {
             __syncwarp();
             int nm, len; int64_t off; bool none;
             if (fast) nmmd_to_pool<true>(P.G, SM.seq, lut, cs, chrom, pos, lane, O.md_cursor, O.md_cap, O.md_pool, nm, len, off, none);
             else nmmd_to_pool<false>(P.G, out_seq, lut, cs, chrom, pos, lane, O.md_cursor, O.md_cap, O.md_pool, nm, len, off, none);
             st = (st & ~(uint32_t)TC_ST_NMMD_NONE) | TC_ST_NMMD_DEVICE;
             if (none) st |= TC_ST_NMMD_NONE;
-            if (lane == 0) { O.nm[i] = nm + W.nm_extra[i]; O.md_off[i] = off < 0 ? 0 : off; O.md_len[i] = off < 0 ? 0 : len; W.status[i] = st; }
+            if (lane == 0) { O.nm[i] = nm + nm_extra; O.md_off[i] = off < 0 ? 0 : off; O.md_len[i] = off < 0 ? 0 : len; W.status[i] = st; }
         } else if (st & TC_ST_NMMD_DEVICE) {                           // generated at init and never refreshed
             const int len = W.md_init_len[i];
             const int64_t off = pool_grab(O.md_cursor, O.md_cap, len, lane);
@@ -494,7 +512,7 @@ struct tc_ctx {
     // work
     DevBuf w_status, w_counters, w_md_init_off, w_md_init_len, w_nm_init, w_n_mdtok, w_n_jn, w_mflags,
         w_cig_cap, w_seg_cap, w_te_cap, w_ws_off, w_ws, w_cig_buf, w_n_cig_cur, w_seg_buf, w_n_seg_cur, w_n_te,
-        w_te_cnt, w_nm_extra, w_refresh, w_o_seq, w_o_cig, w_o_te, w_o_jn, w_seq_len, init_pool, cursors, scan_tmp;
+        w_te_cnt, w_nm_extra, w_refresh, w_o_seq, w_o_cig, w_o_te, w_o_jn, w_seq_len, w_plan, init_pool, cursors, scan_tmp;
     WorkDev W;
     // dense outputs on the device
     DevBuf o_nm, o_md_off, o_md_len, o_md_pool, o_seq, o_cig_op, o_cig_len, o_te, o_jm, o_ji;
@@ -582,7 +600,7 @@ void tc_ctx_destroy(tc_ctx* ctx) {
                    &ctx->w_status, &ctx->w_counters, &ctx->w_md_init_off, &ctx->w_md_init_len, &ctx->w_nm_init, &ctx->w_n_mdtok, &ctx->w_n_jn,
                    &ctx->w_mflags, &ctx->w_cig_cap, &ctx->w_seg_cap, &ctx->w_te_cap, &ctx->w_ws_off, &ctx->w_ws, &ctx->w_cig_buf, &ctx->w_n_cig_cur,
                    &ctx->w_seg_buf, &ctx->w_n_seg_cur, &ctx->w_n_te, &ctx->w_te_cnt, &ctx->w_nm_extra, &ctx->w_refresh, &ctx->w_o_seq, &ctx->w_o_cig,
-                   &ctx->w_o_te, &ctx->w_o_jn, &ctx->w_seq_len, &ctx->init_pool, &ctx->cursors, &ctx->scan_tmp,
+                   &ctx->w_o_te, &ctx->w_o_jn, &ctx->w_seq_len, &ctx->w_plan, &ctx->init_pool, &ctx->cursors, &ctx->scan_tmp,
                    &ctx->o_nm, &ctx->o_md_off, &ctx->o_md_len, &ctx->o_md_pool, &ctx->o_seq, &ctx->o_cig_op, &ctx->o_cig_len, &ctx->o_te, &ctx->o_jm, &ctx->o_ji};
     for (DevBuf* b : d) b->release();
     HostBuf* h[] = {&ctx->h_status, &ctx->h_counters, &ctx->h_nm, &ctx->h_seq_off, &ctx->h_seq, &ctx->h_cig_off, &ctx->h_cig_op, &ctx->h_cig_len,
@@ -723,7 +741,7 @@ static int alloc_work(tc_ctx* ctx) {
     CK(ctx->w_te_cap.ensure(n1 * 4)); CK(ctx->w_ws_off.ensure(n1 * 8)); CK(ctx->w_cig_buf.ensure(n1)); CK(ctx->w_n_cig_cur.ensure(n1 * 4));
     CK(ctx->w_seg_buf.ensure(n1)); CK(ctx->w_n_seg_cur.ensure(n1 * 4)); CK(ctx->w_n_te.ensure(n1 * 4)); CK(ctx->w_te_cnt.ensure(n1 * 12));
     CK(ctx->w_nm_extra.ensure(n1 * 4)); CK(ctx->w_refresh.ensure(n1)); CK(ctx->w_o_seq.ensure(n1 * 8)); CK(ctx->w_o_cig.ensure(n1 * 8));
-    CK(ctx->w_o_te.ensure(n1 * 8)); CK(ctx->w_o_jn.ensure(n1 * 8)); CK(ctx->w_seq_len.ensure(n1 * 4)); CK(ctx->cursors.ensure(64));
+    CK(ctx->w_o_te.ensure(n1 * 8)); CK(ctx->w_o_jn.ensure(n1 * 8)); CK(ctx->w_seq_len.ensure(n1 * 4)); CK(ctx->w_plan.ensure(n1 * sizeof(EmitPlan))); CK(ctx->cursors.ensure(64));
     CK(ctx->o_nm.ensure(n1 * 4)); CK(ctx->o_md_off.ensure(n1 * 8)); CK(ctx->o_md_len.ensure(n1 * 4));
     WorkDev& W = ctx->W;
     W.status = (uint32_t*)ctx->w_status.p; W.counters = (int32_t*)ctx->w_counters.p;
@@ -733,7 +751,7 @@ static int alloc_work(tc_ctx* ctx) {
     W.ws_off = (int64_t*)ctx->w_ws_off.p; W.cig_buf = (int8_t*)ctx->w_cig_buf.p; W.n_cig_cur = (int32_t*)ctx->w_n_cig_cur.p;
     W.seg_buf = (int8_t*)ctx->w_seg_buf.p; W.n_seg_cur = (int32_t*)ctx->w_n_seg_cur.p; W.n_te = (int32_t*)ctx->w_n_te.p;
     W.te_cnt = (int32_t*)ctx->w_te_cnt.p; W.nm_extra = (int32_t*)ctx->w_nm_extra.p; W.refresh = (uint8_t*)ctx->w_refresh.p;
-    W.o_seq = (int64_t*)ctx->w_o_seq.p; W.o_cig = (int64_t*)ctx->w_o_cig.p; W.o_te = (int64_t*)ctx->w_o_te.p; W.o_jn = (int64_t*)ctx->w_o_jn.p; W.seq_len_out = (int32_t*)ctx->w_seq_len.p;
+    W.o_seq = (int64_t*)ctx->w_o_seq.p; W.o_cig = (int64_t*)ctx->w_o_cig.p; W.o_te = (int64_t*)ctx->w_o_te.p; W.o_jn = (int64_t*)ctx->w_o_jn.p; W.seq_len_out = (int32_t*)ctx->w_seq_len.p; W.plan = (EmitPlan*)ctx->w_plan.p;
     return 0;
 }
 
@@ -882,7 +900,7 @@ int tc_batch_run(tc_ctx* ctx, int dry) {
     ctx->W.ws_off[n] = 0; be_scan(ctx, ctx->W.ws_off, n + 1);
     CK(ctx->w_ws.ensure((size_t)(ctx->W.ws_off[n] + 8) * 8)); ctx->W.ws = (u64*)ctx->w_ws.p; P.W.ws = ctx->W.ws;
     for (int64_t i = 0; i < n; i++) {
-        if (dry) { dry_read(P, i); P.W.o_seq[i] = P.W.o_cig[i] = P.W.o_jn[i] = 0; P.W.o_te[i] = P.W.n_te[i]; P.W.seq_len_out[i] = 0; }
+        if (dry) { dry_read(P, i); dry_sizes(P, i); }
         else { plan_read(P, i); junction_read(P, i); sizes_read(P, i); }
     }
     int64_t* sc[4] = {ctx->W.o_seq, ctx->W.o_cig, ctx->W.o_te, ctx->W.o_jn};

@@ -55,6 +55,11 @@ struct BatchDev {
     const int64_t* ji_off; const int32_t* ji;
 };
 
+// everything tc_emit needs to know about a read, packed by sizes_read (one 64-byte row)
+struct EmitPlan { int32_t w[16]; };
+enum { EP_FLAGS, EP_NCIG, EP_NSEG, EP_NTE, EP_TEMM, EP_TEINS, EP_TEDEL, EP_NJN, EP_OUTLEN, EP_NMEXTRA, EP_CIGCAP, EP_SEGCAP, EP_TECAP };
+// EP_FLAGS: bit0 refresh, bits 2-3 cig_buf+1, bits 4-5 seg_buf+1
+
 // per-read state (structure of arrays) + workspace
 struct WorkDev {
     uint32_t* status;
@@ -73,6 +78,7 @@ struct WorkDev {
     int32_t* nm_extra; uint8_t* refresh;
     // exact output sizes, turned into offsets (n+1) by exclusive scans
     int64_t *o_seq, *o_cig, *o_te, *o_jn;
+    EmitPlan* plan;
     int32_t* seq_len_out;    // exact length of the new SEQ (o_seq offsets are padded to 16 bytes)
 };
 
@@ -735,12 +741,30 @@ TC_HD void sizes_read(const Params& P, int64_t i) {
     else { WsView v = ws_view(W, i); sl = 0; const u64* s = v.seg[W.seg_buf[i]]; for (int k = 0; k < W.n_seg_cur[i]; k++) sl += seg_len(s[k]); }
     W.o_seq[i] = (sl + 15) & ~15ll;                 // 16-byte aligned rows: tc_emit stores whole uint4
     W.seq_len_out[i] = (int32_t)sl;
-    W.o_cig[i] = W.cig_buf[i] < 0 ? (B.cig_off[i + 1] - B.cig_off[i]) : W.n_cig_cur[i];
+    const int ncig = W.cig_buf[i] < 0 ? (int)(B.cig_off[i + 1] - B.cig_off[i]) : W.n_cig_cur[i];
+    W.o_cig[i] = ncig;
     W.o_te[i] = W.n_te[i];
     W.o_jn[i] = W.n_jn[i];
+    EmitPlan ep;
+    ep.w[EP_FLAGS] = (W.refresh[i] ? 1 : 0) | ((W.cig_buf[i] + 1) << 2) | ((W.seg_buf[i] + 1) << 4);
+    ep.w[EP_NCIG] = ncig; ep.w[EP_NSEG] = W.n_seg_cur[i]; ep.w[EP_NTE] = W.n_te[i];
+    ep.w[EP_TEMM] = W.te_cnt[3 * i]; ep.w[EP_TEINS] = W.te_cnt[3 * i + 1]; ep.w[EP_TEDEL] = W.te_cnt[3 * i + 2];
+    ep.w[EP_NJN] = W.n_jn[i]; ep.w[EP_OUTLEN] = (int32_t)sl; ep.w[EP_NMEXTRA] = W.nm_extra[i];
+    ep.w[EP_CIGCAP] = W.cig_cap[i]; ep.w[EP_SEGCAP] = W.seg_cap[i]; ep.w[EP_TECAP] = W.te_cap[i];
+    ep.w[13] = ep.w[14] = ep.w[15] = 0;
+    W.plan[i] = ep;
 }
 
 // ---------------------------------------------------------------------------------- dry run
+
+TC_HD void dry_sizes(const Params& P, int64_t i) {
+    const WorkDev& W = P.W;
+    W.o_seq[i] = W.o_cig[i] = W.o_jn[i] = 0; W.o_te[i] = W.n_te[i]; W.seq_len_out[i] = 0;
+    EmitPlan ep;
+    for (int k = 0; k < 16; k++) ep.w[k] = 0;
+    ep.w[EP_NTE] = W.n_te[i]; ep.w[EP_CIGCAP] = W.cig_cap[i]; ep.w[EP_SEGCAP] = W.seg_cap[i]; ep.w[EP_TECAP] = W.te_cap[i];
+    W.plan[i] = ep;
+}
 
 // dryRun (TC.py:1615-1678): positional inventory of X / D / I from the MD x CIGAR merge.
 TC_HD void dry_read(const Params& P, int64_t i) {
