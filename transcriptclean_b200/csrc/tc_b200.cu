@@ -55,8 +55,8 @@ TC_HD void cig_get(const CigSrc& c, int k, int& op, int32_t& len) {
 #define FULL 0xffffffffu
 #define WARPS_PER_BLOCK 8
 #define EMIT_CAP 4096            // reads whose new SEQ fits are staged in shared memory
-#define EMIT_MAXBP 256
-#define EMIT_MAXGI 256
+#define EMIT_MAXBP 192
+#define EMIT_MAXGI 192
 
 struct __align__(16) EmitSmem {  // per warp
     uint8_t seq[EMIT_CAP + 32];
@@ -242,8 +242,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_init(Params P, InitDev
 }
 
 __global__ void k_measure(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) measure_read(P, i); }
-__global__ void k_plan(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) plan_read(P, i); }
-__global__ void k_junction(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) junction_read(P, i); }
+__global__ void __launch_bounds__(128, 8) k_plan(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) plan_read(P, i); }
+__global__ void __launch_bounds__(128, 8) k_junction(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) junction_read(P, i); }
 __global__ void k_sizes(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) sizes_read(P, i); }
 __global__ void k_dry(Params P) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -252,7 +252,7 @@ __global__ void k_dry(Params P) {
 
 // Output stage: one warp per read.  `seq_words` = number of 32-bit words that may be read from
 // the input SEQ array (the buffer is padded).
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit(Params P, OutDev O, int dry, int64_t seq_words) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutDev O, int dry, int64_t seq_words) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw);             // 4 bases (8 bits of the 2-bit plane) -> 4 ASCII bytes
     EmitSmem& SM = reinterpret_cast<EmitSmem*>(smem_raw + 1024)[threadIdx.x >> 5];
@@ -358,6 +358,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit(Params P, OutDev 
         }
         if (fast) {
             __syncwarp();
+            bool read_exc = false;
+            for (int k = lane; k < ngi; k += 32) { const int64_t src = gbase + SM.gi_src[k]; read_exc |= genome_blk_has_exc(P.G, src) | genome_blk_has_exc(P.G, src + SM.gi_len[k] - 1) | (SM.gi_len[k] > 256); }
+            read_exc = __any_sync(FULL, read_exc);
             const int nchunk = (out_len + 15) >> 4;
             int top = 1; while (top * 2 < nbp) top <<= 1; if (nbp <= 1) top = 0;
             // (B) bulk copy, 16 output bytes per lane, with the shift in force at the chunk start
@@ -373,21 +376,28 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit(Params P, OutDev 
                 *reinterpret_cast<uint4*>(SM.seq + p) = o;
             }
             __syncwarp();
-            // (C) the part of a chunk that follows a slice start inside it
+            // (C) the part of a chunk that follows a slice start inside it: same 5-word gather, byte stores
             for (int k = lane; k < nbp; k += 32) {
                 const int b = SM.bp_pos[k];
                 if (b & 15) {
                     int end = (b | 15) + 1; if (end > out_len) end = out_len;
                     if (k + 1 < nbp && (int)SM.bp_pos[k + 1] < end) end = SM.bp_pos[k + 1];
-                    const int sh = SM.bp_shift[k];
-                    for (int p = b; p < end; p++) SM.seq[p] = in_seq[p + sh];
+                    int64_t a = in_base + b + (int)SM.bp_shift[k];
+                    int64_t wi = a >> 2; const int sh = (int)(a & 3) * 8;
+                    if (wi + 4 >= seq_words) wi = seq_words - 5;
+                    const uint32_t x0 = S32[wi], x1 = S32[wi + 1], x2 = S32[wi + 2], x3 = S32[wi + 3], x4 = S32[wi + 4];
+                    uint32_t w[4]; w[0] = __funnelshift_r(x0, x1, sh); w[1] = __funnelshift_r(x1, x2, sh); w[2] = __funnelshift_r(x2, x3, sh); w[3] = __funnelshift_r(x3, x4, sh);
+                    const int n = end - b;
+#pragma unroll
+                    for (int j = 0; j < 15; j++) if (j < n) SM.seq[b + j] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
                 }
             }
             __syncwarp();
             // (D) genome slices (corrected mismatches, deletion fills, junction extensions): byte exact (Q6)
             for (int k = lane; k < ngi; k += 32) {
                 const int o = SM.gi_out[k], len = SM.gi_len[k]; const int64_t src = gbase + SM.gi_src[k];
-                for (int j = 0; j < len; j++) SM.seq[o + j] = genome_byte(P.G, src + j);
+                if (read_exc) { for (int j = 0; j < len; j++) SM.seq[o + j] = genome_byte(P.G, src + j); }
+                else { for (int j = 0; j < len; j++) SM.seq[o + j] = genome_byte_fast(P.G, src + j); }
             }
             __syncwarp();
             // (E) one coalesced store of the row (rows are padded to 16 bytes)

@@ -178,11 +178,13 @@ TC_HD bool sj_nearest(const u64* tab, int64_t n, u64 prefix, int64_t q, bool tie
 }
 
 TC_HD bool sj_annotated(const SjDev& S, int chrom, int32_t start, int32_t end, int strand) {
-    u64 k1 = ((u64)chrom << 32) | (uint32_t)start, k2 = ((u64)(uint32_t)end << 1) | (u64)strand;
-    int64_t lo = lower_bound_u64(S.ann_k1, 0, S.n_ann, k1);
-    int64_t hi = lower_bound_u64(S.ann_k1, lo, S.n_ann, k1 + 1);
-    int64_t j = lower_bound_u64(S.ann_k2, lo, hi, k2);
-    return j < hi && S.ann_k2[j] == k2;
+    const u64 k1 = ((u64)chrom << 32) | (uint32_t)start, k2 = ((u64)(uint32_t)end << 1) | (u64)strand;
+    int64_t lo = 0, hi = S.n_ann;                        // one lexicographic search over (k1, k2)
+    while (lo < hi) {
+        const int64_t m = (lo + hi) >> 1; const u64 a = S.ann_k1[m];
+        if (a < k1 || (a == k1 && S.ann_k2[m] < k2)) lo = m + 1; else hi = m;
+    }
+    return lo < S.n_ann && S.ann_k1[lo] == k1 && S.ann_k2[lo] == k2;
 }
 
 TC_HD bool snp_match(const VarDev& V, int chrom, int64_t pos, uint8_t base) {   // TC.py:1114-1118
@@ -308,8 +310,10 @@ struct Emit {                 // newCIGAR / newSeq / MVal bookkeeping (endMatch,
 };
 
 TC_HD void te_put(tc_te* te, int& n, int type, int32_t a, int32_t b, int32_t size, int status, int reason) {
-    tc_te r; r.a = a; r.b = b; r.size = size; r.type = (uint8_t)type; r.status = (uint8_t)status;
-    r.reason = (uint8_t)reason; r.pad = 0; te[n++] = r;
+    u64* p = reinterpret_cast<u64*>(te + n);             // the TE area of the workspace is 8-byte aligned
+    p[0] = (u64)(uint32_t)a | ((u64)(uint32_t)b << 32);
+    p[1] = (u64)(uint32_t)size | ((u64)(uint32_t)(type & 255) << 32) | ((u64)(uint32_t)(status & 255) << 40) | ((u64)(uint32_t)(reason & 255) << 48);
+    n++;
 }
 
 // Stages 1-3 in one left-to-right pass.  The reference runs correctMismatches (TC.py:1077-1168),
@@ -444,9 +448,16 @@ TC_HD bool junction_code(const Params& P, int chrom, int strand, int32_t b0, int
     const GenomeDev& G = P.G; int64_t goff = G.chrom_off[chrom] - 1;
     int n0 = fetch_len(G, chrom, b0, (int64_t)b0 + 1), n1 = fetch_len(G, chrom, (int64_t)b1 - 1, b1);
     int mc = 0;
-    if (n0 == 2 && n1 == 2)
-        mc = motif_code(genome_byte(G, goff + b0), genome_byte(G, goff + b0 + 1),
-                        genome_byte(G, goff + b1 - 1), genome_byte(G, goff + b1));
+    if (n0 == 2 && n1 == 2) {
+        const int64_t ga = goff + b0, gb = goff + b1 - 1;
+        if (genome_blk_has_exc(G, ga) | genome_blk_has_exc(G, ga + 1) | genome_blk_has_exc(G, gb) | genome_blk_has_exc(G, gb + 1)) {
+            mc = motif_code(genome_byte(G, ga), genome_byte(G, ga + 1), genome_byte(G, gb), genome_byte(G, gb + 1));
+        } else {                                        // case does not matter for the motif: 2-bit plane only
+            const uint32_t c = ((G.g2[ga >> 4] >> ((ga & 15) * 2)) & 3u) | (((G.g2[(ga + 1) >> 4] >> (((ga + 1) & 15) * 2)) & 3u) << 2) |
+                               (((G.g2[gb >> 4] >> ((gb & 15) * 2)) & 3u) << 4) | (((G.g2[(gb + 1) >> 4] >> (((gb + 1) & 15) * 2)) & 3u) << 6);
+            mc = c == 142u ? 1 : c == 77u ? 2 : c == 134u ? 3 : c == 109u ? 4 : c == 76u ? 5 : c == 206u ? 6 : 0;   // GTAG CTAC GCAG CTGC ATAC GTAT
+        }
+    }
     code = mc + (sj_annotated(P.S, chrom, start, end, strand) ? 20 : 0);
     return true;
 }
