@@ -161,6 +161,10 @@ int tc_correct_batch(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out);
 /* dryRun() (TC.py:1615-1678): only status, counters, te_off, te are filled. */
 int tc_dryrun_batch(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out);
 
+/* tc_correct_batch / tc_dryrun_batch cut batches larger than 1.5 x chunk_reads into chunks and
+ * overlap upload, kernels and download on three streams (default 131072; 0 = one piece). */
+int tc_ctx_set_pipeline(tc_ctx* ctx, int64_t chunk_reads);
+
 /* The same work split for device-resident measurement: upload once, run many, download. */
 int tc_batch_upload(tc_ctx* ctx, const tc_batch_in* in);
 int tc_batch_run(tc_ctx* ctx, int dry_run);

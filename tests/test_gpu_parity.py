@@ -36,6 +36,16 @@ def test_long_reads_and_many(engine):
     pc.check_generated(engine, 999, n_reads=1500, err=0.08, shift_frac=0.4)
 
 
+def test_pipelined_chunks(engine):
+    """tc_correct_batch cut into small chunks (3-stream pipeline, rebased offsets) gives the same texts."""
+    for chunk in (16, 37, 100):
+        engine.set_pipeline(chunk)
+        try:
+            pc.check_generated(engine, 777 + chunk, n_reads=260, unpinned=False)
+        finally:
+            engine.set_pipeline(131072)
+
+
 def test_empty_batch(engine):
     import numpy as np
     from transcriptclean_b200.genome import GenomeImage

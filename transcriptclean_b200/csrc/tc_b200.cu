@@ -250,9 +250,9 @@ __global__ void k_dry(Params P) {
     if (i < P.B.n) { dry_read(P, i); dry_sizes(P, i); }
 }
 
-// Output stage: one warp per read.  `seq_words` = number of 32-bit words that may be read from
-// the input SEQ array (the buffer is padded).
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutDev O, int dry, int64_t seq_words) {
+// Output stage: one warp per read.  [seq_lo, seq_hi) = 32-bit words of B.seq that may be read
+// (the batch's SEQ buffer on the device, padded).
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutDev O, int dry, int64_t seq_lo, int64_t seq_hi) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw);             // 4 bases (8 bits of the 2-bit plane) -> 4 ASCII bytes
     EmitSmem& SM = reinterpret_cast<EmitSmem*>(smem_raw + 1024)[threadIdx.x >> 5];
@@ -368,9 +368,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
                 const int p = c << 4; int k = 0;
                 for (int step = top; step; step >>= 1) { const int t = k + step; if (t < nbp && (int)SM.bp_pos[t] <= p) k = t; }
                 int64_t a = in_base + p + (nbp ? (int)SM.bp_shift[k] : 0);
-                if (a < 0) a = 0;
                 int64_t wi = a >> 2; const int sh = (int)(a & 3) * 8;
-                if (wi + 4 >= seq_words) wi = seq_words - 5;
+                if (wi < seq_lo) wi = seq_lo;
+                if (wi + 4 >= seq_hi) wi = seq_hi - 5;
                 const uint32_t x0 = S32[wi], x1 = S32[wi + 1], x2 = S32[wi + 2], x3 = S32[wi + 3], x4 = S32[wi + 4];
                 uint4 o; o.x = __funnelshift_r(x0, x1, sh); o.y = __funnelshift_r(x1, x2, sh); o.z = __funnelshift_r(x2, x3, sh); o.w = __funnelshift_r(x3, x4, sh);
                 *reinterpret_cast<uint4*>(SM.seq + p) = o;
@@ -384,7 +384,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
                     if (k + 1 < nbp && (int)SM.bp_pos[k + 1] < end) end = SM.bp_pos[k + 1];
                     int64_t a = in_base + b + (int)SM.bp_shift[k];
                     int64_t wi = a >> 2; const int sh = (int)(a & 3) * 8;
-                    if (wi + 4 >= seq_words) wi = seq_words - 5;
+                    if (wi < seq_lo) wi = seq_lo;
+                    if (wi + 4 >= seq_hi) wi = seq_hi - 5;
                     const uint32_t x0 = S32[wi], x1 = S32[wi + 1], x2 = S32[wi + 2], x3 = S32[wi + 3], x4 = S32[wi + 4];
                     uint32_t w[4]; w[0] = __funnelshift_r(x0, x1, sh); w[1] = __funnelshift_r(x1, x2, sh); w[2] = __funnelshift_r(x2, x3, sh); w[3] = __funnelshift_r(x3, x4, sh);
                     const int n = end - b;
@@ -501,80 +502,119 @@ static void host_nmmd(const GenomeDev& G, const uint8_t* seq, const CigSrc& cs, 
 
 // ---------------------------------------------------------------------------------- context
 
+// Everything that belongs to one batch (or one chunk of a pipelined batch) on the device.
+struct Slot {
+    DevBuf b_flag, b_chrom, b_pos, b_tags, b_seq_off, b_seq, b_cig_off, b_cig_op, b_cig_len, b_md_off, b_md, b_ji_off, b_ji;
+    BatchDev B; int64_t n = 0, n_seq = 0, n_cig = 0, n_md = 0, n_ji = 0;
+    int64_t seq_lo_word = 0, seq_hi_word = 0;       // words of B.seq (as uint32) that may be dereferenced
+    DevBuf w_status, w_counters, w_md_init_off, w_md_init_len, w_nm_init, w_n_mdtok, w_n_jn, w_mflags,
+        w_cig_cap, w_seg_cap, w_te_cap, w_ws_off, w_ws, w_cig_buf, w_n_cig_cur, w_seg_buf, w_n_seg_cur, w_n_te,
+        w_te_cnt, w_nm_extra, w_refresh, w_o_seq, w_o_cig, w_o_te, w_o_jn, w_seq_len, w_plan, init_pool, cursors, scan_tmp;
+    WorkDev W;
+    DevBuf o_nm, o_md_off, o_md_len, o_md_pool, o_seq, o_cig_op, o_cig_len, o_te, o_jm, o_ji;
+    int64_t tot_seq = 0, tot_cig = 0, tot_te = 0, tot_jn = 0, md_used = 0;
+    int64_t base_seq = 0, base_cig = 0, base_te = 0, base_jn = 0, base_md = 0;   // position of this chunk in the batch output
+    HostBuf h_tot;
+    bool ran = false, ran_dry = false;
+#ifndef TC_HOSTSIM
+    cudaEvent_t ev_in = nullptr, ev_cmp = nullptr, ev_out = nullptr;
+#endif
+    void release() {
+        DevBuf* d[] = {&b_flag, &b_chrom, &b_pos, &b_tags, &b_seq_off, &b_seq, &b_cig_off, &b_cig_op, &b_cig_len, &b_md_off, &b_md, &b_ji_off, &b_ji,
+                       &w_status, &w_counters, &w_md_init_off, &w_md_init_len, &w_nm_init, &w_n_mdtok, &w_n_jn, &w_mflags, &w_cig_cap, &w_seg_cap,
+                       &w_te_cap, &w_ws_off, &w_ws, &w_cig_buf, &w_n_cig_cur, &w_seg_buf, &w_n_seg_cur, &w_n_te, &w_te_cnt, &w_nm_extra, &w_refresh,
+                       &w_o_seq, &w_o_cig, &w_o_te, &w_o_jn, &w_seq_len, &w_plan, &init_pool, &cursors, &scan_tmp,
+                       &o_nm, &o_md_off, &o_md_len, &o_md_pool, &o_seq, &o_cig_op, &o_cig_len, &o_te, &o_jm, &o_ji};
+        for (DevBuf* b : d) b->release();
+        h_tot.release();
+    }
+};
+
+
 struct tc_ctx {
     int device = 0;
     std::string err;
     tc_options opt;
 #ifndef TC_HOSTSIM
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev[12];
 #endif
     bool have_genome = false;
-    // tables
     DevBuf g2, lo1, excblk, chrom_off, chrom_len, exc_start, exc_end, exc_byte;
     DevBuf don_s, acc_s, don_u, acc_u, ann_k1, ann_k2;
     DevBuf snp_key, snp_alt, ins_key, ins_size, ins_aoff, ins_bytes, del_key, del_size;
     GenomeDev G; SjDev S; VarDev V;
-    std::vector<int64_t> h_chrom_len;
-    // batch input on the device
-    DevBuf b_flag, b_chrom, b_pos, b_tags, b_seq_off, b_seq, b_cig_off, b_cig_op, b_cig_len, b_md_off, b_md, b_ji_off, b_ji;
-    BatchDev B; int64_t n = 0; int64_t n_seq = 0, n_cig = 0, n_md = 0, n_ji = 0;
-    // work
-    DevBuf w_status, w_counters, w_md_init_off, w_md_init_len, w_nm_init, w_n_mdtok, w_n_jn, w_mflags,
-        w_cig_cap, w_seg_cap, w_te_cap, w_ws_off, w_ws, w_cig_buf, w_n_cig_cur, w_seg_buf, w_n_seg_cur, w_n_te,
-        w_te_cnt, w_nm_extra, w_refresh, w_o_seq, w_o_cig, w_o_te, w_o_jn, w_seq_len, w_plan, init_pool, cursors, scan_tmp;
-    WorkDev W;
-    // dense outputs on the device
-    DevBuf o_nm, o_md_off, o_md_len, o_md_pool, o_seq, o_cig_op, o_cig_len, o_te, o_jm, o_ji;
-    int64_t tot_seq = 0, tot_cig = 0, tot_te = 0, tot_jn = 0, md_used = 0;
-    bool ran = false, ran_dry = false;
-    // pinned host outputs
+    Slot slot[2];
+    int64_t n = 0; bool ran = false, ran_dry = false; bool piped = false;
+    int64_t chunk_reads = 131072;   // reads per chunk of the pipelined tc_correct_batch (0 = never pipeline)
+    // pinned host outputs (whole batch)
     HostBuf h_status, h_counters, h_nm, h_seq_off, h_seq, h_cig_off, h_cig_op, h_cig_len, h_md_off, h_md_len, h_md,
-        h_jn_off, h_jm, h_ji, h_te_off, h_te, h_tot, h_seq_len;
+        h_jn_off, h_jm, h_ji, h_te_off, h_te, h_seq_len;
     tc_timing tm;
 };
 
 static std::string g_create_err;
 
 #ifndef TC_HOSTSIM
-static int be_h2d(tc_ctx* ctx, DevBuf& d, const void* src, size_t bytes) {
-    CK(d.ensure(bytes ? bytes : 8));
-    if (bytes) CK(cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+__global__ void k_set_u64(unsigned long long* p, unsigned long long v) { *p = v; }
+
+static int be_h2d(tc_ctx* ctx, cudaStream_t st, DevBuf& d, size_t dst_off, const void* src, size_t bytes, size_t slack = 0) {
+    CK(d.ensure(dst_off + bytes + slack + 8));
+    if (bytes) CK(cudaMemcpyAsync((char*)d.p + dst_off, src, bytes, cudaMemcpyHostToDevice, st));
     ctx->tm.h2d_bytes += (int64_t)bytes;
     return 0;
 }
-static int be_d2h(tc_ctx* ctx, HostBuf& h, const void* src, size_t bytes) {
-    CK(h.ensure(bytes ? bytes : 8));
-    if (bytes) CK(cudaMemcpyAsync(h.p, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+// grows a pinned host buffer, keeping its content; `busy` = a stream that may still be writing into it
+static int host_reserve(tc_ctx* ctx, HostBuf& h, size_t need, size_t keep, cudaStream_t busy) {
+    if (need <= h.cap) return 0;
+    if (busy) CK(cudaStreamSynchronize(busy));
+    void* old = h.p; h.p = nullptr; h.cap = 0;
+    size_t want = need + need / 4 + 4096;
+    CK(cudaHostAlloc(&h.p, want, cudaHostAllocDefault)); h.cap = want;
+    if (old) { if (keep) memcpy(h.p, old, keep); cudaFreeHost(old); }
+    return 0;
+}
+static int be_d2h(tc_ctx* ctx, cudaStream_t st, HostBuf& h, size_t dst_off, const void* src, size_t bytes) {
+    if (bytes) CK(cudaMemcpyAsync((char*)h.p + dst_off, src, bytes, cudaMemcpyDeviceToHost, st));
     ctx->tm.d2h_bytes += (int64_t)bytes;
     return 0;
 }
-static int be_sync(tc_ctx* ctx) { CK(cudaStreamSynchronize(ctx->stream)); return 0; }
-static int be_zero(tc_ctx* ctx, void* p, size_t bytes) { CK(cudaMemsetAsync(p, 0, bytes, ctx->stream)); return 0; }
-// in-place exclusive prefix sum over n1 int64 values
-static int be_scan(tc_ctx* ctx, int64_t* a, int64_t n1) {
+static int be_sync(tc_ctx* ctx, cudaStream_t st) { CK(cudaStreamSynchronize(st)); return 0; }
+static int be_zero(tc_ctx* ctx, cudaStream_t st, void* p, size_t bytes) { CK(cudaMemsetAsync(p, 0, bytes, st)); return 0; }
+// in-place exclusive prefix sum over n1 int64 values, starting at `init`
+static int be_scan(tc_ctx* ctx, cudaStream_t st, DevBuf& tmpbuf, int64_t* a, int64_t n1, int64_t init) {
     size_t tmp = 0;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, a, a, (int)n1, ctx->stream));
-    CK(ctx->scan_tmp.ensure(tmp));
-    CK(cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, tmp, a, a, (int)n1, ctx->stream));
+    CK(cub::DeviceScan::ExclusiveScan(nullptr, tmp, a, a, ::cuda::std::plus<>{}, init, (int)n1, st));
+    CK(tmpbuf.ensure(tmp));
+    CK(cub::DeviceScan::ExclusiveScan(tmpbuf.p, tmp, a, a, ::cuda::std::plus<>{}, init, (int)n1, st));
     ctx->tm.launches += 2;
     return 0;
 }
-static int be_read_i64(tc_ctx* ctx, const int64_t* dev, int64_t* host) {
-    CK(cudaMemcpyAsync(host, dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
+static int be_read_i64(tc_ctx* ctx, cudaStream_t st, const int64_t* dev, int64_t* host) {
+    CK(cudaMemcpyAsync(host, dev, 8, cudaMemcpyDeviceToHost, st));
     return 0;
 }
+typedef cudaStream_t stream_t;
 #else
-static int be_h2d(tc_ctx* ctx, DevBuf& d, const void* src, size_t bytes) {
-    CK(d.ensure(bytes ? bytes : 8)); if (bytes) memcpy(d.p, src, bytes); ctx->tm.h2d_bytes += (int64_t)bytes; return 0;
+typedef int stream_t;
+static int be_h2d(tc_ctx* ctx, stream_t, DevBuf& d, size_t dst_off, const void* src, size_t bytes, size_t slack = 0) {
+    CK(d.ensure(dst_off + bytes + slack + 8)); if (bytes) memcpy((char*)d.p + dst_off, src, bytes); ctx->tm.h2d_bytes += (int64_t)bytes; return 0;
 }
-static int be_d2h(tc_ctx* ctx, HostBuf& h, const void* src, size_t bytes) {
-    CK(h.ensure(bytes ? bytes : 8)); if (bytes) memcpy(h.p, src, bytes); ctx->tm.d2h_bytes += (int64_t)bytes; return 0;
+static int host_reserve(tc_ctx* ctx, HostBuf& h, size_t need, size_t keep, stream_t) {
+    if (need <= h.cap) return 0;
+    void* old = h.p; size_t want = need + need / 4 + 4096;
+    h.p = calloc(want, 1); h.cap = want;
+    if (!h.p) { ctx->err = "out of host memory"; return 1; }
+    if (old) { if (keep) memcpy(h.p, old, keep); free(old); }
+    return 0;
 }
-static int be_sync(tc_ctx*) { return 0; }
-static int be_zero(tc_ctx*, void* p, size_t bytes) { memset(p, 0, bytes); return 0; }
-static int be_scan(tc_ctx*, int64_t* a, int64_t n1) { int64_t s = 0; for (int64_t k = 0; k < n1; k++) { int64_t v = a[k]; a[k] = s; s += v; } return 0; }
-static int be_read_i64(tc_ctx*, const int64_t* dev, int64_t* host) { *host = *dev; return 0; }
+static int be_d2h(tc_ctx* ctx, stream_t, HostBuf& h, size_t dst_off, const void* src, size_t bytes) {
+    if (bytes) memcpy((char*)h.p + dst_off, src, bytes); ctx->tm.d2h_bytes += (int64_t)bytes; return 0;
+}
+static int be_sync(tc_ctx*, stream_t) { return 0; }
+static int be_zero(tc_ctx*, stream_t, void* p, size_t bytes) { memset(p, 0, bytes); return 0; }
+static int be_scan(tc_ctx*, stream_t, DevBuf&, int64_t* a, int64_t n1, int64_t init) { int64_t s = init; for (int64_t k = 0; k < n1; k++) { int64_t v = a[k]; a[k] = s; s += v; } return 0; }
+static int be_read_i64(tc_ctx*, stream_t, const int64_t* dev, int64_t* host) { *host = *dev; return 0; }
 #endif
 
 extern "C" {
@@ -590,7 +630,14 @@ tc_ctx* tc_ctx_create(int device) {
 #ifndef TC_HOSTSIM
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
     for (int k = 0; k < 12 && e == cudaSuccess; k++) e = cudaEventCreate(&ctx->ev[k]);
+    for (int k = 0; k < 2 && e == cudaSuccess; k++) {
+        e = cudaEventCreateWithFlags(&ctx->slot[k].ev_in, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->slot[k].ev_cmp, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->slot[k].ev_out, cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) { g_create_err = std::string("tc_ctx_create: ") + cudaGetErrorString(e); delete ctx; return nullptr; }
 #endif
     return ctx;
@@ -600,25 +647,20 @@ void tc_ctx_destroy(tc_ctx* ctx) {
     if (!ctx) return;
 #ifndef TC_HOSTSIM
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(ctx->s_out);
 #endif
     DevBuf* d[] = {&ctx->g2, &ctx->lo1, &ctx->excblk, &ctx->chrom_off, &ctx->chrom_len, &ctx->exc_start, &ctx->exc_end, &ctx->exc_byte,
                    &ctx->don_s, &ctx->acc_s, &ctx->don_u, &ctx->acc_u, &ctx->ann_k1, &ctx->ann_k2, &ctx->snp_key, &ctx->snp_alt,
-                   &ctx->ins_key, &ctx->ins_size, &ctx->ins_aoff, &ctx->ins_bytes, &ctx->del_key, &ctx->del_size,
-                   &ctx->b_flag, &ctx->b_chrom, &ctx->b_pos, &ctx->b_tags, &ctx->b_seq_off, &ctx->b_seq, &ctx->b_cig_off, &ctx->b_cig_op,
-                   &ctx->b_cig_len, &ctx->b_md_off, &ctx->b_md, &ctx->b_ji_off, &ctx->b_ji,
-                   &ctx->w_status, &ctx->w_counters, &ctx->w_md_init_off, &ctx->w_md_init_len, &ctx->w_nm_init, &ctx->w_n_mdtok, &ctx->w_n_jn,
-                   &ctx->w_mflags, &ctx->w_cig_cap, &ctx->w_seg_cap, &ctx->w_te_cap, &ctx->w_ws_off, &ctx->w_ws, &ctx->w_cig_buf, &ctx->w_n_cig_cur,
-                   &ctx->w_seg_buf, &ctx->w_n_seg_cur, &ctx->w_n_te, &ctx->w_te_cnt, &ctx->w_nm_extra, &ctx->w_refresh, &ctx->w_o_seq, &ctx->w_o_cig,
-                   &ctx->w_o_te, &ctx->w_o_jn, &ctx->w_seq_len, &ctx->w_plan, &ctx->init_pool, &ctx->cursors, &ctx->scan_tmp,
-                   &ctx->o_nm, &ctx->o_md_off, &ctx->o_md_len, &ctx->o_md_pool, &ctx->o_seq, &ctx->o_cig_op, &ctx->o_cig_len, &ctx->o_te, &ctx->o_jm, &ctx->o_ji};
+                   &ctx->ins_key, &ctx->ins_size, &ctx->ins_aoff, &ctx->ins_bytes, &ctx->del_key, &ctx->del_size};
     for (DevBuf* b : d) b->release();
+    for (int k = 0; k < 2; k++) ctx->slot[k].release();
     HostBuf* h[] = {&ctx->h_status, &ctx->h_counters, &ctx->h_nm, &ctx->h_seq_off, &ctx->h_seq, &ctx->h_cig_off, &ctx->h_cig_op, &ctx->h_cig_len,
-                    &ctx->h_md_off, &ctx->h_md_len, &ctx->h_md, &ctx->h_jn_off, &ctx->h_jm, &ctx->h_ji, &ctx->h_te_off, &ctx->h_te, &ctx->h_tot, &ctx->h_seq_len};
+                    &ctx->h_md_off, &ctx->h_md_len, &ctx->h_md, &ctx->h_jn_off, &ctx->h_jm, &ctx->h_ji, &ctx->h_te_off, &ctx->h_te, &ctx->h_seq_len};
     for (HostBuf* b : h) b->release();
 #ifndef TC_HOSTSIM
     for (int k = 0; k < 12; k++) cudaEventDestroy(ctx->ev[k]);
-    cudaStreamDestroy(ctx->stream);
+    for (int k = 0; k < 2; k++) { cudaEventDestroy(ctx->slot[k].ev_in); cudaEventDestroy(ctx->slot[k].ev_cmp); cudaEventDestroy(ctx->slot[k].ev_out); }
+    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out);
 #endif
     delete ctx;
 }
@@ -640,6 +682,14 @@ void* tc_ctx_stream(tc_ctx* ctx) {
 #endif
 }
 
+static stream_t main_stream(tc_ctx* ctx) {
+#ifndef TC_HOSTSIM
+    return ctx->stream;
+#else
+    (void)ctx; return 0;
+#endif
+}
+
 int tc_ctx_load_genome(tc_ctx* ctx, int32_t n_chrom, const int64_t* chrom_len, const int64_t* chrom_off,
                        int64_t n_pad, const uint32_t* bases2, const uint32_t* lower1, int64_t n_exc,
                        const int64_t* exc_start, const int64_t* exc_end, const uint8_t* exc_byte) {
@@ -647,6 +697,7 @@ int tc_ctx_load_genome(tc_ctx* ctx, int32_t n_chrom, const int64_t* chrom_len, c
 #ifndef TC_HOSTSIM
     CK(cudaSetDevice(ctx->device));
 #endif
+    stream_t st = main_stream(ctx);
     // block bitmap of literal runs (1 bit per 256 bases)
     int64_t nblk = (n_pad >> 8) + 2, nwords = (nblk + 31) / 32 + 1;
     std::vector<uint32_t> blk((size_t)nwords, 0u);
@@ -654,21 +705,15 @@ int tc_ctx_load_genome(tc_ctx* ctx, int32_t n_chrom, const int64_t* chrom_len, c
         if (exc_end[k] <= exc_start[k] || exc_start[k] < 0 || exc_end[k] > n_pad) { ctx->err = "tc_ctx_load_genome: bad literal run"; return TC_E_ARG; }
         for (int64_t b = exc_start[k] >> 8; b <= (exc_end[k] - 1) >> 8; b++) blk[(size_t)(b >> 5)] |= 1u << (b & 31);
     }
-    if (be_h2d(ctx, ctx->g2, bases2, (size_t)(n_pad / 16) * 4)) return TC_E_CUDA;
-    if (be_h2d(ctx, ctx->lo1, lower1, (size_t)(n_pad / 32) * 4)) return TC_E_CUDA;
-    if (be_h2d(ctx, ctx->excblk, blk.data(), (size_t)nwords * 4)) return TC_E_CUDA;
-    if (be_h2d(ctx, ctx->chrom_off, chrom_off, (size_t)n_chrom * 8)) return TC_E_CUDA;
-    if (be_h2d(ctx, ctx->chrom_len, chrom_len, (size_t)n_chrom * 8)) return TC_E_CUDA;
-    if (be_h2d(ctx, ctx->exc_start, exc_start, (size_t)n_exc * 8)) return TC_E_CUDA;
-    if (be_h2d(ctx, ctx->exc_end, exc_end, (size_t)n_exc * 8)) return TC_E_CUDA;
-    if (be_h2d(ctx, ctx->exc_byte, exc_byte, (size_t)n_exc)) return TC_E_CUDA;
-    if (be_sync(ctx)) return TC_E_CUDA;
+    if (be_h2d(ctx, st, ctx->g2, 0, bases2, (size_t)(n_pad / 16) * 4, 256) || be_h2d(ctx, st, ctx->lo1, 0, lower1, (size_t)(n_pad / 32) * 4, 256) ||
+        be_h2d(ctx, st, ctx->excblk, 0, blk.data(), (size_t)nwords * 4) || be_h2d(ctx, st, ctx->chrom_off, 0, chrom_off, (size_t)n_chrom * 8) ||
+        be_h2d(ctx, st, ctx->chrom_len, 0, chrom_len, (size_t)n_chrom * 8) || be_h2d(ctx, st, ctx->exc_start, 0, exc_start, (size_t)n_exc * 8) ||
+        be_h2d(ctx, st, ctx->exc_end, 0, exc_end, (size_t)n_exc * 8) || be_h2d(ctx, st, ctx->exc_byte, 0, exc_byte, (size_t)n_exc) || be_sync(ctx, st)) return TC_E_CUDA;
     GenomeDev& G = ctx->G;
     G.g2 = (const uint32_t*)ctx->g2.p; G.lo1 = (const uint32_t*)ctx->lo1.p; G.excblk = (const uint32_t*)ctx->excblk.p;
     G.chrom_off = (const int64_t*)ctx->chrom_off.p; G.chrom_len = (const int64_t*)ctx->chrom_len.p;
     G.exc_start = (const int64_t*)ctx->exc_start.p; G.exc_end = (const int64_t*)ctx->exc_end.p;
     G.exc_byte = (const uint8_t*)ctx->exc_byte.p; G.n_exc = n_exc; G.n_chrom = n_chrom;
-    ctx->h_chrom_len.assign(chrom_len, chrom_len + n_chrom);
     ctx->have_genome = true;
     return TC_OK;
 }
@@ -680,9 +725,10 @@ int tc_ctx_load_junctions(tc_ctx* ctx, int64_t n_don_s, const uint64_t* don_s, i
 #ifndef TC_HOSTSIM
     CK(cudaSetDevice(ctx->device));
 #endif
-    if (be_h2d(ctx, ctx->don_s, don_s, (size_t)n_don_s * 8) || be_h2d(ctx, ctx->acc_s, acc_s, (size_t)n_acc_s * 8) ||
-        be_h2d(ctx, ctx->don_u, don_u, (size_t)n_don_u * 8) || be_h2d(ctx, ctx->acc_u, acc_u, (size_t)n_acc_u * 8) ||
-        be_h2d(ctx, ctx->ann_k1, k1, (size_t)n_annot * 8) || be_h2d(ctx, ctx->ann_k2, k2, (size_t)n_annot * 8) || be_sync(ctx)) return TC_E_CUDA;
+    stream_t st = main_stream(ctx);
+    if (be_h2d(ctx, st, ctx->don_s, 0, don_s, (size_t)n_don_s * 8) || be_h2d(ctx, st, ctx->acc_s, 0, acc_s, (size_t)n_acc_s * 8) ||
+        be_h2d(ctx, st, ctx->don_u, 0, don_u, (size_t)n_don_u * 8) || be_h2d(ctx, st, ctx->acc_u, 0, acc_u, (size_t)n_acc_u * 8) ||
+        be_h2d(ctx, st, ctx->ann_k1, 0, k1, (size_t)n_annot * 8) || be_h2d(ctx, st, ctx->ann_k2, 0, k2, (size_t)n_annot * 8) || be_sync(ctx, st)) return TC_E_CUDA;
     SjDev& S = ctx->S;
     S.don_s = (const u64*)ctx->don_s.p; S.acc_s = (const u64*)ctx->acc_s.p; S.don_u = (const u64*)ctx->don_u.p; S.acc_u = (const u64*)ctx->acc_u.p;
     S.ann_k1 = (const u64*)ctx->ann_k1.p; S.ann_k2 = (const u64*)ctx->ann_k2.p;
@@ -697,11 +743,12 @@ int tc_ctx_load_variants(tc_ctx* ctx, int64_t n_snp, const uint64_t* snp_key, co
 #ifndef TC_HOSTSIM
     CK(cudaSetDevice(ctx->device));
 #endif
+    stream_t st = main_stream(ctx);
     int64_t nab = n_ins ? ins_aoff[n_ins] : 0;
-    if (be_h2d(ctx, ctx->snp_key, snp_key, (size_t)n_snp * 8) || be_h2d(ctx, ctx->snp_alt, snp_alt, (size_t)n_snp) ||
-        be_h2d(ctx, ctx->ins_key, ins_key, (size_t)n_ins * 8) || be_h2d(ctx, ctx->ins_size, ins_size, (size_t)n_ins * 4) ||
-        be_h2d(ctx, ctx->ins_aoff, ins_aoff, (size_t)(n_ins ? n_ins + 1 : 0) * 8) || be_h2d(ctx, ctx->ins_bytes, ins_bytes, (size_t)nab) ||
-        be_h2d(ctx, ctx->del_key, del_key, (size_t)n_del * 8) || be_h2d(ctx, ctx->del_size, del_size, (size_t)n_del * 4) || be_sync(ctx)) return TC_E_CUDA;
+    if (be_h2d(ctx, st, ctx->snp_key, 0, snp_key, (size_t)n_snp * 8) || be_h2d(ctx, st, ctx->snp_alt, 0, snp_alt, (size_t)n_snp) ||
+        be_h2d(ctx, st, ctx->ins_key, 0, ins_key, (size_t)n_ins * 8) || be_h2d(ctx, st, ctx->ins_size, 0, ins_size, (size_t)n_ins * 4) ||
+        be_h2d(ctx, st, ctx->ins_aoff, 0, ins_aoff, (size_t)(n_ins ? n_ins + 1 : 0) * 8) || be_h2d(ctx, st, ctx->ins_bytes, 0, ins_bytes, (size_t)nab) ||
+        be_h2d(ctx, st, ctx->del_key, 0, del_key, (size_t)n_del * 8) || be_h2d(ctx, st, ctx->del_size, 0, del_size, (size_t)n_del * 4) || be_sync(ctx, st)) return TC_E_CUDA;
     VarDev& V = ctx->V;
     V.snp_key = (const u64*)ctx->snp_key.p; V.snp_alt = (const uint8_t*)ctx->snp_alt.p; V.n_snp = n_snp;
     V.ins_key = (const u64*)ctx->ins_key.p; V.ins_size = (const int32_t*)ctx->ins_size.p; V.ins_aoff = (const int64_t*)ctx->ins_aoff.p;
@@ -710,65 +757,73 @@ int tc_ctx_load_variants(tc_ctx* ctx, int64_t n_snp, const uint64_t* snp_key, co
     return TC_OK;
 }
 
-int tc_batch_upload(tc_ctx* ctx, const tc_batch_in* in) {
-    if (!ctx || !in || in->n_reads < 0) return TC_E_ARG;
-    if (!ctx->have_genome) { ctx->err = "tc_batch_upload: load a genome first"; return TC_E_STATE; }
-    if (in->n_reads >= (1ll << 31) - 2) { ctx->err = "tc_batch_upload: batch too large"; return TC_E_ARG; }
-#ifndef TC_HOSTSIM
-    CK(cudaSetDevice(ctx->device));
-    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-#endif
-    const int64_t n = in->n_reads;
-    ctx->tm.h2d_bytes = 0;
-    ctx->n = n;
-    ctx->n_seq = n ? in->seq_off[n] : 0; ctx->n_cig = n ? in->cig_off[n] : 0;
-    ctx->n_md = n ? in->md_off[n] : 0; ctx->n_ji = n ? in->ji_off[n] : 0;
+}  // extern "C"
+
+// uploads reads [r0, r1) of `in` into slot S.  CSR offsets stay the batch's absolute offsets; the
+// data pointers are shifted so that they can be applied unchanged.
+static int slot_upload(tc_ctx* ctx, Slot& S, const tc_batch_in* in, int64_t r0, int64_t r1, stream_t st) {
+    const int64_t n = r1 - r0;
+    S.n = n; S.ran = false;
     static const int64_t zero_off[1] = {0};
-    if (be_h2d(ctx, ctx->b_flag, in->flag, (size_t)n * 4) || be_h2d(ctx, ctx->b_chrom, in->chrom, (size_t)n * 4) ||
-        be_h2d(ctx, ctx->b_pos, in->pos, (size_t)n * 4) || be_h2d(ctx, ctx->b_tags, in->tags, (size_t)n) ||
-        be_h2d(ctx, ctx->b_seq_off, n ? in->seq_off : zero_off, (size_t)(n + 1) * 8) || be_h2d(ctx, ctx->b_seq, in->seq, (size_t)ctx->n_seq) ||
-        be_h2d(ctx, ctx->b_cig_off, n ? in->cig_off : zero_off, (size_t)(n + 1) * 8) || be_h2d(ctx, ctx->b_cig_op, in->cig_op, (size_t)ctx->n_cig) ||
-        be_h2d(ctx, ctx->b_cig_len, in->cig_len, (size_t)ctx->n_cig * 4) ||
-        be_h2d(ctx, ctx->b_md_off, n ? in->md_off : zero_off, (size_t)(n + 1) * 8) || be_h2d(ctx, ctx->b_md, in->md, (size_t)ctx->n_md) ||
-        be_h2d(ctx, ctx->b_ji_off, n ? in->ji_off : zero_off, (size_t)(n + 1) * 8) || be_h2d(ctx, ctx->b_ji, in->ji, (size_t)ctx->n_ji * 4)) return TC_E_CUDA;
-#ifndef TC_HOSTSIM
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-#endif
-    BatchDev& B = ctx->B;
-    B.n = n; B.flag = (const int32_t*)ctx->b_flag.p; B.chrom = (const int32_t*)ctx->b_chrom.p; B.pos = (const int32_t*)ctx->b_pos.p;
-    B.tags = (const uint8_t*)ctx->b_tags.p; B.seq_off = (const int64_t*)ctx->b_seq_off.p; B.seq = (const uint8_t*)ctx->b_seq.p;
-    B.cig_off = (const int64_t*)ctx->b_cig_off.p; B.cig_op = (const uint8_t*)ctx->b_cig_op.p; B.cig_len = (const int32_t*)ctx->b_cig_len.p;
-    B.md_off = (const int64_t*)ctx->b_md_off.p; B.md = (const uint8_t*)ctx->b_md.p; B.ji_off = (const int64_t*)ctx->b_ji_off.p; B.ji = (const int32_t*)ctx->b_ji.p;
-    ctx->ran = false;
+    const int64_t s0 = n ? in->seq_off[r0] : 0, c0 = n ? in->cig_off[r0] : 0, m0 = n ? in->md_off[r0] : 0, j0 = n ? in->ji_off[r0] : 0;
+    S.n_seq = n ? in->seq_off[r1] - s0 : 0; S.n_cig = n ? in->cig_off[r1] - c0 : 0;
+    S.n_md = n ? in->md_off[r1] - m0 : 0; S.n_ji = n ? in->ji_off[r1] - j0 : 0;
+    const size_t d0 = (size_t)(s0 & 15);            // keeps (device pointer - s0) 16-byte aligned
+    if (be_h2d(ctx, st, S.b_flag, 0, in->flag + r0, (size_t)n * 4) || be_h2d(ctx, st, S.b_chrom, 0, in->chrom + r0, (size_t)n * 4) ||
+        be_h2d(ctx, st, S.b_pos, 0, in->pos + r0, (size_t)n * 4) || be_h2d(ctx, st, S.b_tags, 0, in->tags + r0, (size_t)n) ||
+        be_h2d(ctx, st, S.b_seq_off, 0, n ? in->seq_off + r0 : zero_off, (size_t)(n + 1) * 8) ||
+        be_h2d(ctx, st, S.b_seq, d0, n ? in->seq + s0 : nullptr, (size_t)S.n_seq, 256) ||
+        be_h2d(ctx, st, S.b_cig_off, 0, n ? in->cig_off + r0 : zero_off, (size_t)(n + 1) * 8) ||
+        be_h2d(ctx, st, S.b_cig_op, 0, n ? in->cig_op + c0 : nullptr, (size_t)S.n_cig) ||
+        be_h2d(ctx, st, S.b_cig_len, 0, n ? in->cig_len + c0 : nullptr, (size_t)S.n_cig * 4) ||
+        be_h2d(ctx, st, S.b_md_off, 0, n ? in->md_off + r0 : zero_off, (size_t)(n + 1) * 8) ||
+        be_h2d(ctx, st, S.b_md, 0, n ? in->md + m0 : nullptr, (size_t)S.n_md) ||
+        be_h2d(ctx, st, S.b_ji_off, 0, n ? in->ji_off + r0 : zero_off, (size_t)(n + 1) * 8) ||
+        be_h2d(ctx, st, S.b_ji, 0, n ? in->ji + j0 : nullptr, (size_t)S.n_ji * 4)) return TC_E_CUDA;
+    BatchDev& B = S.B;
+    B.n = n; B.flag = (const int32_t*)S.b_flag.p; B.chrom = (const int32_t*)S.b_chrom.p; B.pos = (const int32_t*)S.b_pos.p;
+    B.tags = (const uint8_t*)S.b_tags.p; B.seq_off = (const int64_t*)S.b_seq_off.p; B.seq = (const uint8_t*)S.b_seq.p + d0 - s0;
+    B.cig_off = (const int64_t*)S.b_cig_off.p; B.cig_op = (const uint8_t*)S.b_cig_op.p - c0; B.cig_len = (const int32_t*)S.b_cig_len.p - c0;
+    B.md_off = (const int64_t*)S.b_md_off.p; B.md = (const uint8_t*)S.b_md.p - m0; B.ji_off = (const int64_t*)S.b_ji_off.p; B.ji = (const int32_t*)S.b_ji.p - j0;
+    S.seq_lo_word = (s0 - (int64_t)d0) / 4; S.seq_hi_word = S.seq_lo_word + (int64_t)(S.b_seq.cap / 4);
     return TC_OK;
 }
 
-static int alloc_work(tc_ctx* ctx) {
-    const size_t n = (size_t)ctx->n, n1 = n + 1;
-    CK(ctx->w_status.ensure(n1 * 4)); CK(ctx->w_counters.ensure(n1 * 40)); CK(ctx->w_md_init_off.ensure(n1 * 8));
-    CK(ctx->w_md_init_len.ensure(n1 * 4)); CK(ctx->w_nm_init.ensure(n1 * 4)); CK(ctx->w_n_mdtok.ensure(n1 * 4));
-    CK(ctx->w_n_jn.ensure(n1 * 4)); CK(ctx->w_mflags.ensure(n1)); CK(ctx->w_cig_cap.ensure(n1 * 4)); CK(ctx->w_seg_cap.ensure(n1 * 4));
-    CK(ctx->w_te_cap.ensure(n1 * 4)); CK(ctx->w_ws_off.ensure(n1 * 8)); CK(ctx->w_cig_buf.ensure(n1)); CK(ctx->w_n_cig_cur.ensure(n1 * 4));
-    CK(ctx->w_seg_buf.ensure(n1)); CK(ctx->w_n_seg_cur.ensure(n1 * 4)); CK(ctx->w_n_te.ensure(n1 * 4)); CK(ctx->w_te_cnt.ensure(n1 * 12));
-    CK(ctx->w_nm_extra.ensure(n1 * 4)); CK(ctx->w_refresh.ensure(n1)); CK(ctx->w_o_seq.ensure(n1 * 8)); CK(ctx->w_o_cig.ensure(n1 * 8));
-    CK(ctx->w_o_te.ensure(n1 * 8)); CK(ctx->w_o_jn.ensure(n1 * 8)); CK(ctx->w_seq_len.ensure(n1 * 4)); CK(ctx->w_plan.ensure(n1 * sizeof(EmitPlan))); CK(ctx->cursors.ensure(64));
-    CK(ctx->o_nm.ensure(n1 * 4)); CK(ctx->o_md_off.ensure(n1 * 8)); CK(ctx->o_md_len.ensure(n1 * 4));
-    WorkDev& W = ctx->W;
-    W.status = (uint32_t*)ctx->w_status.p; W.counters = (int32_t*)ctx->w_counters.p;
-    W.md_init_off = (int64_t*)ctx->w_md_init_off.p; W.md_init_len = (int32_t*)ctx->w_md_init_len.p; W.nm_init = (int32_t*)ctx->w_nm_init.p;
-    W.n_mdtok = (int32_t*)ctx->w_n_mdtok.p; W.n_jn = (int32_t*)ctx->w_n_jn.p; W.mflags = (uint8_t*)ctx->w_mflags.p;
-    W.cig_cap = (int32_t*)ctx->w_cig_cap.p; W.seg_cap = (int32_t*)ctx->w_seg_cap.p; W.te_cap = (int32_t*)ctx->w_te_cap.p;
-    W.ws_off = (int64_t*)ctx->w_ws_off.p; W.cig_buf = (int8_t*)ctx->w_cig_buf.p; W.n_cig_cur = (int32_t*)ctx->w_n_cig_cur.p;
-    W.seg_buf = (int8_t*)ctx->w_seg_buf.p; W.n_seg_cur = (int32_t*)ctx->w_n_seg_cur.p; W.n_te = (int32_t*)ctx->w_n_te.p;
-    W.te_cnt = (int32_t*)ctx->w_te_cnt.p; W.nm_extra = (int32_t*)ctx->w_nm_extra.p; W.refresh = (uint8_t*)ctx->w_refresh.p;
-    W.o_seq = (int64_t*)ctx->w_o_seq.p; W.o_cig = (int64_t*)ctx->w_o_cig.p; W.o_te = (int64_t*)ctx->w_o_te.p; W.o_jn = (int64_t*)ctx->w_o_jn.p; W.seq_len_out = (int32_t*)ctx->w_seq_len.p; W.plan = (EmitPlan*)ctx->w_plan.p;
+static int alloc_work(tc_ctx* ctx, Slot& S) {
+    const size_t n = (size_t)S.n, n1 = n + 1;
+    CK(S.w_status.ensure(n1 * 4)); CK(S.w_counters.ensure(n1 * 40)); CK(S.w_md_init_off.ensure(n1 * 8));
+    CK(S.w_md_init_len.ensure(n1 * 4)); CK(S.w_nm_init.ensure(n1 * 4)); CK(S.w_n_mdtok.ensure(n1 * 4));
+    CK(S.w_n_jn.ensure(n1 * 4)); CK(S.w_mflags.ensure(n1)); CK(S.w_cig_cap.ensure(n1 * 4)); CK(S.w_seg_cap.ensure(n1 * 4));
+    CK(S.w_te_cap.ensure(n1 * 4)); CK(S.w_ws_off.ensure(n1 * 8)); CK(S.w_cig_buf.ensure(n1)); CK(S.w_n_cig_cur.ensure(n1 * 4));
+    CK(S.w_seg_buf.ensure(n1)); CK(S.w_n_seg_cur.ensure(n1 * 4)); CK(S.w_n_te.ensure(n1 * 4)); CK(S.w_te_cnt.ensure(n1 * 12));
+    CK(S.w_nm_extra.ensure(n1 * 4)); CK(S.w_refresh.ensure(n1)); CK(S.w_o_seq.ensure(n1 * 8)); CK(S.w_o_cig.ensure(n1 * 8));
+    CK(S.w_o_te.ensure(n1 * 8)); CK(S.w_o_jn.ensure(n1 * 8)); CK(S.w_seq_len.ensure(n1 * 4)); CK(S.w_plan.ensure(n1 * sizeof(EmitPlan))); CK(S.cursors.ensure(64));
+    CK(S.o_nm.ensure(n1 * 4)); CK(S.o_md_off.ensure(n1 * 8)); CK(S.o_md_len.ensure(n1 * 4));
+    WorkDev& W = S.W;
+    W.status = (uint32_t*)S.w_status.p; W.counters = (int32_t*)S.w_counters.p;
+    W.md_init_off = (int64_t*)S.w_md_init_off.p; W.md_init_len = (int32_t*)S.w_md_init_len.p; W.nm_init = (int32_t*)S.w_nm_init.p;
+    W.n_mdtok = (int32_t*)S.w_n_mdtok.p; W.n_jn = (int32_t*)S.w_n_jn.p; W.mflags = (uint8_t*)S.w_mflags.p;
+    W.cig_cap = (int32_t*)S.w_cig_cap.p; W.seg_cap = (int32_t*)S.w_seg_cap.p; W.te_cap = (int32_t*)S.w_te_cap.p;
+    W.ws_off = (int64_t*)S.w_ws_off.p; W.cig_buf = (int8_t*)S.w_cig_buf.p; W.n_cig_cur = (int32_t*)S.w_n_cig_cur.p;
+    W.seg_buf = (int8_t*)S.w_seg_buf.p; W.n_seg_cur = (int32_t*)S.w_n_seg_cur.p; W.n_te = (int32_t*)S.w_n_te.p;
+    W.te_cnt = (int32_t*)S.w_te_cnt.p; W.nm_extra = (int32_t*)S.w_nm_extra.p; W.refresh = (uint8_t*)S.w_refresh.p;
+    W.o_seq = (int64_t*)S.w_o_seq.p; W.o_cig = (int64_t*)S.w_o_cig.p; W.o_te = (int64_t*)S.w_o_te.p; W.o_jn = (int64_t*)S.w_o_jn.p;
+    W.seq_len_out = (int32_t*)S.w_seq_len.p; W.plan = (EmitPlan*)S.w_plan.p;
     return 0;
 }
 
-static Params make_params(tc_ctx* ctx) {
-    Params P; P.G = ctx->G; P.S = ctx->S; P.V = ctx->V; P.B = ctx->B; P.W = ctx->W; P.O = ctx->opt;
+static Params make_params(tc_ctx* ctx, Slot& S) {
+    Params P; P.G = ctx->G; P.S = ctx->S; P.V = ctx->V; P.B = S.B; P.W = S.W; P.O = ctx->opt;
     P.sj_enabled = ctx->S.n_ann > 0 ? 1 : 0;
     return P;
+}
+
+static OutDev make_out(Slot& S, unsigned long long* cur, int64_t md_cap) {
+    OutDev O; O.nm = (int32_t*)S.o_nm.p; O.md_off = (int64_t*)S.o_md_off.p; O.md_len = (int32_t*)S.o_md_len.p;
+    O.md_pool = (uint8_t*)S.o_md_pool.p - S.base_md; O.md_cursor = cur; O.md_cap = S.base_md + md_cap;
+    O.seq = (uint8_t*)S.o_seq.p - S.base_seq; O.cig_op = (uint8_t*)S.o_cig_op.p - S.base_cig; O.cig_len = (int32_t*)S.o_cig_len.p - S.base_cig;
+    O.te = (tc_te*)S.o_te.p - S.base_te; O.jm = (int8_t*)S.o_jm.p - S.base_jn; O.ji = (int32_t*)S.o_ji.p - 2 * S.base_jn;
+    return O;
 }
 
 #ifdef TC_HOSTSIM
@@ -816,159 +871,270 @@ static void host_emit_read(Params& P, OutDev& O, int64_t i, int dry, std::vector
 }
 #endif
 
-int tc_batch_run(tc_ctx* ctx, int dry) {
-    if (!ctx) return TC_E_ARG;
-    if (!ctx->have_genome) { ctx->err = "tc_batch_run: load a genome first"; return TC_E_STATE; }
-    const int64_t n = ctx->n;
-#ifndef TC_HOSTSIM
-    CK(cudaSetDevice(ctx->device));
-#endif
-    if (alloc_work(ctx)) return TC_E_CUDA;
-    ctx->tm.launches = 0; ctx->tm.md_pool_retries = 0;
-    HostBuf& ht = ctx->h_tot; CK(ht.ensure(128)); int64_t* tot = (int64_t*)ht.p;
-    unsigned long long* cur = (unsigned long long*)ctx->cursors.p;
-    Params P = make_params(ctx);
-    ctx->tot_seq = ctx->tot_cig = ctx->tot_te = ctx->tot_jn = 0; ctx->md_used = 0;
-    if (n == 0) { ctx->ran = true; ctx->ran_dry = dry != 0; return TC_OK; }
+
+// runs the kernel pipeline of one slot on stream `st`.  Output offsets start at the slot's
+// base_* (its position in the whole batch).
+static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
+    const int64_t n = S.n;
+    if (alloc_work(ctx, S)) return TC_E_CUDA;
+    CK(S.h_tot.ensure(128)); int64_t* tot = (int64_t*)S.h_tot.p;
+    unsigned long long* cur = (unsigned long long*)S.cursors.p;
+    Params P = make_params(ctx, S);
+    S.tot_seq = S.tot_cig = S.tot_te = S.tot_jn = 0; S.md_used = 0;
+    if (n == 0) { S.ran = true; S.ran_dry = dry != 0; return TC_OK; }
 #ifndef TC_HOSTSIM
     const int TPB = 128; const int gb = (int)((n + TPB - 1) / TPB);
     int nsm = 148; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
     int64_t wb = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; int gw = (int)(wb < (int64_t)nsm * 8 ? wb : (int64_t)nsm * 8);
-    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-    // ---- init NM/MD (pool sized from the reads that lack a tag; exact retry on overflow)
-    int64_t init_cap = ctx->init_pool.cap > (1 << 20) ? (int64_t)ctx->init_pool.cap : (1 << 20);
+    if (timed) CK(cudaEventRecord(ctx->ev[2], st));
+    // ---- init NM/MD (exact retry on overflow)
+    int64_t init_cap = S.init_pool.cap > (1 << 20) ? (int64_t)S.init_pool.cap : (1 << 20);
     for (int attempt = 0;; attempt++) {
-        CK(ctx->init_pool.ensure((size_t)init_cap)); init_cap = (int64_t)ctx->init_pool.cap;
-        if (be_zero(ctx, cur, 64)) return TC_E_CUDA;
-        InitDev I; I.pool = (uint8_t*)ctx->init_pool.p; I.cursor = cur; I.cap = init_cap;
-        P.W.md_init_pool = I.pool; ctx->W.md_init_pool = I.pool;
-        k_init<<<gw, WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(P, I, ctx->W.nm_init); ctx->tm.launches++;
+        CK(S.init_pool.ensure((size_t)init_cap)); init_cap = (int64_t)S.init_pool.cap;
+        if (be_zero(ctx, st, cur, 64)) return TC_E_CUDA;
+        InitDev I; I.pool = (uint8_t*)S.init_pool.p; I.cursor = cur; I.cap = init_cap;
+        P.W.md_init_pool = I.pool; S.W.md_init_pool = I.pool;
+        k_init<<<gw, WARPS_PER_BLOCK * 32, 0, st>>>(P, I, S.W.nm_init); ctx->tm.launches++;
         CK(cudaGetLastError());
-        if (be_read_i64(ctx, (const int64_t*)cur, tot) || be_sync(ctx)) return TC_E_CUDA;
+        k_measure<<<gb, TPB, 0, st>>>(P); ctx->tm.launches++;        // measure only needs lengths: safe before the overflow check
+        CK(cudaGetLastError());
+        if (be_zero(ctx, st, S.W.ws_off + n, 8) || be_scan(ctx, st, S.scan_tmp, S.W.ws_off, n + 1, 0) ||
+            be_read_i64(ctx, st, (const int64_t*)cur, tot) || be_read_i64(ctx, st, S.W.ws_off + n, tot + 1) || be_sync(ctx, st)) return TC_E_CUDA;
         if (tot[0] <= init_cap) break;
         if (attempt >= 2) { ctx->err = "init MD pool overflow"; return TC_E_CUDA; }
         init_cap = tot[0] + 1024; ctx->tm.md_pool_retries++;
     }
-    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-    // ---- measure + workspace
-    k_measure<<<gb, TPB, 0, ctx->stream>>>(P); ctx->tm.launches++;
-    CK(cudaGetLastError());
-    if (be_zero(ctx, ctx->W.ws_off + n, 8) || be_scan(ctx, ctx->W.ws_off, n + 1) || be_read_i64(ctx, ctx->W.ws_off + n, tot) || be_sync(ctx)) return TC_E_CUDA;
-    CK(ctx->w_ws.ensure((size_t)(tot[0] + 8) * 8));
-    ctx->W.ws = (u64*)ctx->w_ws.p; P.W.ws = ctx->W.ws;
-    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
-    if (dry) { k_dry<<<gb, TPB, 0, ctx->stream>>>(P); ctx->tm.launches++; CK(cudaGetLastError()); CK(cudaEventRecord(ctx->ev[5], ctx->stream)); CK(cudaEventRecord(ctx->ev[6], ctx->stream)); }
+    if (timed) CK(cudaEventRecord(ctx->ev[4], st));
+    CK(S.w_ws.ensure((size_t)(tot[1] + 8) * 8));
+    S.W.ws = (u64*)S.w_ws.p; P.W.ws = S.W.ws;
+    if (dry) { k_dry<<<gb, TPB, 0, st>>>(P); ctx->tm.launches++; CK(cudaGetLastError()); if (timed) { CK(cudaEventRecord(ctx->ev[5], st)); CK(cudaEventRecord(ctx->ev[6], st)); } }
     else {
-        k_plan<<<gb, TPB, 0, ctx->stream>>>(P); ctx->tm.launches++; CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->ev[5], ctx->stream));
-        k_junction<<<gb, TPB, 0, ctx->stream>>>(P); ctx->tm.launches++; CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->ev[6], ctx->stream));
-        k_sizes<<<gb, TPB, 0, ctx->stream>>>(P); ctx->tm.launches++; CK(cudaGetLastError());
+        k_plan<<<gb, TPB, 0, st>>>(P); ctx->tm.launches++; CK(cudaGetLastError());
+        if (timed) CK(cudaEventRecord(ctx->ev[5], st));
+        k_junction<<<gb, TPB, 0, st>>>(P); ctx->tm.launches++; CK(cudaGetLastError());
+        if (timed) CK(cudaEventRecord(ctx->ev[6], st));
+        k_sizes<<<gb, TPB, 0, st>>>(P); ctx->tm.launches++; CK(cudaGetLastError());
     }
-    int64_t* sc[4] = {ctx->W.o_seq, ctx->W.o_cig, ctx->W.o_te, ctx->W.o_jn};
-    for (int k = 0; k < 4; k++) { if (be_zero(ctx, sc[k] + n, 8) || be_scan(ctx, sc[k], n + 1) || be_read_i64(ctx, sc[k] + n, tot + 1 + k)) return TC_E_CUDA; }
-    if (be_sync(ctx)) return TC_E_CUDA;
-    ctx->tot_seq = tot[1]; ctx->tot_cig = tot[2]; ctx->tot_te = tot[3]; ctx->tot_jn = tot[4];
-    CK(ctx->o_seq.ensure((size_t)ctx->tot_seq + 64)); CK(ctx->o_cig_op.ensure((size_t)ctx->tot_cig + 64)); CK(ctx->o_cig_len.ensure((size_t)ctx->tot_cig * 4 + 64));
-    CK(ctx->o_te.ensure((size_t)ctx->tot_te * 16 + 64)); CK(ctx->o_jm.ensure((size_t)ctx->tot_jn + 64)); CK(ctx->o_ji.ensure((size_t)ctx->tot_jn * 8 + 64));
+    int64_t* sc[4] = {S.W.o_seq, S.W.o_cig, S.W.o_te, S.W.o_jn};
+    const int64_t bases[4] = {S.base_seq, S.base_cig, S.base_te, S.base_jn};
+    for (int k = 0; k < 4; k++) { if (be_zero(ctx, st, sc[k] + n, 8) || be_scan(ctx, st, S.scan_tmp, sc[k], n + 1, bases[k]) || be_read_i64(ctx, st, sc[k] + n, tot + 1 + k)) return TC_E_CUDA; }
+    if (be_sync(ctx, st)) return TC_E_CUDA;
+    S.tot_seq = tot[1] - bases[0]; S.tot_cig = tot[2] - bases[1]; S.tot_te = tot[3] - bases[2]; S.tot_jn = tot[4] - bases[3];
+    CK(S.o_seq.ensure((size_t)S.tot_seq + 64)); CK(S.o_cig_op.ensure((size_t)S.tot_cig + 64)); CK(S.o_cig_len.ensure((size_t)S.tot_cig * 4 + 64));
+    CK(S.o_te.ensure((size_t)S.tot_te * 16 + 64)); CK(S.o_jm.ensure((size_t)S.tot_jn + 64)); CK(S.o_ji.ensure((size_t)S.tot_jn * 8 + 64));
     CK(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMIT_SMEM_BYTES));
     int occ = 1; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_emit, WARPS_PER_BLOCK * 32, EMIT_SMEM_BYTES));
     int ge = (int)(wb < (int64_t)nsm * occ ? wb : (int64_t)nsm * occ);
-    const int64_t seq_words = (int64_t)(ctx->b_seq.cap / 4);
-    int64_t md_cap = ctx->o_md_pool.cap > 0 ? (int64_t)ctx->o_md_pool.cap : (64 * n + 8 * ctx->n_cig + (1 << 20));
-    CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+    int64_t md_cap = S.o_md_pool.cap > 0 ? (int64_t)S.o_md_pool.cap : (64 * n + 8 * S.n_cig + (1 << 20));
+    if (timed) CK(cudaEventRecord(ctx->ev[7], st));
     for (int attempt = 0;; attempt++) {
-        CK(ctx->o_md_pool.ensure((size_t)md_cap)); md_cap = (int64_t)ctx->o_md_pool.cap;
-        if (be_zero(ctx, cur, 64)) return TC_E_CUDA;
-        OutDev O; O.nm = (int32_t*)ctx->o_nm.p; O.md_off = (int64_t*)ctx->o_md_off.p; O.md_len = (int32_t*)ctx->o_md_len.p;
-        O.md_pool = (uint8_t*)ctx->o_md_pool.p; O.md_cursor = cur; O.md_cap = md_cap; O.seq = (uint8_t*)ctx->o_seq.p;
-        O.cig_op = (uint8_t*)ctx->o_cig_op.p; O.cig_len = (int32_t*)ctx->o_cig_len.p; O.te = (tc_te*)ctx->o_te.p; O.jm = (int8_t*)ctx->o_jm.p; O.ji = (int32_t*)ctx->o_ji.p;
-        k_emit<<<ge, WARPS_PER_BLOCK * 32, EMIT_SMEM_BYTES, ctx->stream>>>(P, O, dry, seq_words); ctx->tm.launches++;
+        CK(S.o_md_pool.ensure((size_t)md_cap)); md_cap = (int64_t)S.o_md_pool.cap;
+        k_set_u64<<<1, 1, 0, st>>>(cur, (unsigned long long)S.base_md);
+        OutDev O = make_out(S, cur, md_cap);
+        k_emit<<<ge, WARPS_PER_BLOCK * 32, EMIT_SMEM_BYTES, st>>>(P, O, dry, S.seq_lo_word, S.seq_hi_word); ctx->tm.launches += 2;
         CK(cudaGetLastError());
-        if (attempt == 0) CK(cudaEventRecord(ctx->ev[8], ctx->stream));
-        if (be_read_i64(ctx, (const int64_t*)cur, tot) || be_sync(ctx)) return TC_E_CUDA;
-        if (tot[0] <= md_cap) { ctx->md_used = tot[0]; break; }
+        if (timed && attempt == 0) CK(cudaEventRecord(ctx->ev[8], st));
+        if (be_read_i64(ctx, st, (const int64_t*)cur, tot) || be_sync(ctx, st)) return TC_E_CUDA;
+        if (tot[0] - S.base_md <= md_cap) { S.md_used = tot[0] - S.base_md; break; }
         if (attempt >= 2) { ctx->err = "MD pool overflow"; return TC_E_CUDA; }
-        md_cap = tot[0] + 1024; ctx->tm.md_pool_retries++;
+        md_cap = tot[0] - S.base_md + 1024; ctx->tm.md_pool_retries++;
     }
-    CK(cudaEventRecord(ctx->ev[9], ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    cudaEventElapsedTime(&ctx->tm.kernels_ms, ctx->ev[2], ctx->ev[9]);
-    cudaEventElapsedTime(&ctx->tm.k_nmmd_init_ms, ctx->ev[2], ctx->ev[3]);
-    cudaEventElapsedTime(&ctx->tm.k_measure_ms, ctx->ev[3], ctx->ev[4]);
-    cudaEventElapsedTime(&ctx->tm.k_plan_ms, ctx->ev[4], ctx->ev[5]);
-    cudaEventElapsedTime(&ctx->tm.k_junction_ms, ctx->ev[5], ctx->ev[6]);
-    cudaEventElapsedTime(&ctx->tm.k_emit_ms, ctx->ev[7], ctx->ev[8]);
+    if (timed) {
+        CK(cudaEventRecord(ctx->ev[9], st));
+        CK(cudaStreamSynchronize(st));
+        float t;
+        cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[9]); ctx->tm.kernels_ms += t;
+        cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[4]); ctx->tm.k_nmmd_init_ms += t;     // k_init + k_measure + scan
+        ctx->tm.k_measure_ms += 0.f;
+        cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]); ctx->tm.k_plan_ms += t;
+        cudaEventElapsedTime(&t, ctx->ev[5], ctx->ev[6]); ctx->tm.k_junction_ms += t;
+        cudaEventElapsedTime(&t, ctx->ev[7], ctx->ev[8]); ctx->tm.k_emit_ms += t;
+    }
 #else
+    (void)timed; (void)st;
     std::vector<uint8_t> ipool, opool;
-    {   // init needs the pool pointer before measure; build it first
-        for (int64_t i = 0; i < n; i++) host_init_read(P, i, ipool);
-        CK(ctx->init_pool.ensure(ipool.size() + 8)); memcpy(ctx->init_pool.p, ipool.data(), ipool.size());
-        P.W.md_init_pool = (const uint8_t*)ctx->init_pool.p; ctx->W.md_init_pool = P.W.md_init_pool;
-    }
+    for (int64_t i = 0; i < n; i++) host_init_read(P, i, ipool);
+    CK(S.init_pool.ensure(ipool.size() + 8)); memcpy(S.init_pool.p, ipool.data(), ipool.size());
+    P.W.md_init_pool = (const uint8_t*)S.init_pool.p; S.W.md_init_pool = P.W.md_init_pool;
     for (int64_t i = 0; i < n; i++) measure_read(P, i);
-    ctx->W.ws_off[n] = 0; be_scan(ctx, ctx->W.ws_off, n + 1);
-    CK(ctx->w_ws.ensure((size_t)(ctx->W.ws_off[n] + 8) * 8)); ctx->W.ws = (u64*)ctx->w_ws.p; P.W.ws = ctx->W.ws;
+    S.W.ws_off[n] = 0; be_scan(ctx, st, S.scan_tmp, S.W.ws_off, n + 1, 0);
+    CK(S.w_ws.ensure((size_t)(S.W.ws_off[n] + 8) * 8)); S.W.ws = (u64*)S.w_ws.p; P.W.ws = S.W.ws;
     for (int64_t i = 0; i < n; i++) {
         if (dry) { dry_read(P, i); dry_sizes(P, i); }
         else { plan_read(P, i); junction_read(P, i); sizes_read(P, i); }
     }
-    int64_t* sc[4] = {ctx->W.o_seq, ctx->W.o_cig, ctx->W.o_te, ctx->W.o_jn};
-    for (int k = 0; k < 4; k++) { sc[k][n] = 0; be_scan(ctx, sc[k], n + 1); tot[1 + k] = sc[k][n]; }
-    ctx->tot_seq = tot[1]; ctx->tot_cig = tot[2]; ctx->tot_te = tot[3]; ctx->tot_jn = tot[4];
-    CK(ctx->o_seq.ensure((size_t)ctx->tot_seq + 64)); CK(ctx->o_cig_op.ensure((size_t)ctx->tot_cig + 64)); CK(ctx->o_cig_len.ensure((size_t)ctx->tot_cig * 4 + 64));
-    CK(ctx->o_te.ensure((size_t)ctx->tot_te * 16 + 64)); CK(ctx->o_jm.ensure((size_t)ctx->tot_jn + 64)); CK(ctx->o_ji.ensure((size_t)ctx->tot_jn * 8 + 64));
-    OutDev O; O.nm = (int32_t*)ctx->o_nm.p; O.md_off = (int64_t*)ctx->o_md_off.p; O.md_len = (int32_t*)ctx->o_md_len.p; O.md_pool = 0; O.md_cursor = 0; O.md_cap = 0;
-    O.seq = (uint8_t*)ctx->o_seq.p; O.cig_op = (uint8_t*)ctx->o_cig_op.p; O.cig_len = (int32_t*)ctx->o_cig_len.p; O.te = (tc_te*)ctx->o_te.p; O.jm = (int8_t*)ctx->o_jm.p; O.ji = (int32_t*)ctx->o_ji.p;
+    int64_t* sc[4] = {S.W.o_seq, S.W.o_cig, S.W.o_te, S.W.o_jn};
+    const int64_t bases[4] = {S.base_seq, S.base_cig, S.base_te, S.base_jn};
+    for (int k = 0; k < 4; k++) { sc[k][n] = 0; be_scan(ctx, st, S.scan_tmp, sc[k], n + 1, bases[k]); tot[1 + k] = sc[k][n] - bases[k]; }
+    S.tot_seq = tot[1]; S.tot_cig = tot[2]; S.tot_te = tot[3]; S.tot_jn = tot[4];
+    CK(S.o_seq.ensure((size_t)S.tot_seq + 64)); CK(S.o_cig_op.ensure((size_t)S.tot_cig + 64)); CK(S.o_cig_len.ensure((size_t)S.tot_cig * 4 + 64));
+    CK(S.o_te.ensure((size_t)S.tot_te * 16 + 64)); CK(S.o_jm.ensure((size_t)S.tot_jn + 64)); CK(S.o_ji.ensure((size_t)S.tot_jn * 8 + 64));
+    OutDev O = make_out(S, nullptr, 0);
     for (int64_t i = 0; i < n; i++) host_emit_read(P, O, i, dry, opool);
-    CK(ctx->o_md_pool.ensure(opool.size() + 8)); memcpy(ctx->o_md_pool.p, opool.data(), opool.size()); ctx->md_used = (int64_t)opool.size();
+    for (int64_t i = 0; i < n; i++) O.md_off[i] += S.base_md;
+    CK(S.o_md_pool.ensure(opool.size() + 8)); memcpy(S.o_md_pool.p, opool.data(), opool.size()); S.md_used = (int64_t)opool.size();
     (void)cur;
 #endif
-    ctx->ran = true; ctx->ran_dry = dry != 0;
+    S.ran = true; S.ran_dry = dry != 0;
     return TC_OK;
 }
 
-int tc_batch_download(tc_ctx* ctx, tc_batch_out* out) {
-    if (!ctx || !out) return TC_E_ARG;
-    if (!ctx->ran) { ctx->err = "tc_batch_download: nothing has run"; return TC_E_STATE; }
-    const int64_t n = ctx->n; const size_t n1 = (size_t)n + 1;
-#ifndef TC_HOSTSIM
-    CK(cudaSetDevice(ctx->device));
-    CK(cudaEventRecord(ctx->ev[10], ctx->stream));
-#endif
-    ctx->tm.d2h_bytes = 0;
+// reserves the pinned host arrays for the batch rows [0, r1) and output positions up to the slot's end
+static int host_reserve_all(tc_ctx* ctx, Slot& S, int64_t r0, int64_t n_total, bool dry, stream_t busy) {
+    const size_t n1 = (size_t)n_total + 1; (void)r0;
+    if (host_reserve(ctx, ctx->h_status, n1 * 4, 0, busy) || host_reserve(ctx, ctx->h_counters, n1 * 40, 0, busy) ||
+        host_reserve(ctx, ctx->h_te_off, n1 * 8, 0, busy) ||
+        host_reserve(ctx, ctx->h_te, (size_t)(S.base_te + S.tot_te) * 16 + 64, (size_t)S.base_te * 16, busy)) return TC_E_CUDA;
+    if (dry) return 0;
+    if (host_reserve(ctx, ctx->h_nm, n1 * 4, 0, busy) || host_reserve(ctx, ctx->h_seq_off, n1 * 8, 0, busy) || host_reserve(ctx, ctx->h_seq_len, n1 * 4, 0, busy) ||
+        host_reserve(ctx, ctx->h_cig_off, n1 * 8, 0, busy) || host_reserve(ctx, ctx->h_md_off, n1 * 8, 0, busy) || host_reserve(ctx, ctx->h_md_len, n1 * 4, 0, busy) ||
+        host_reserve(ctx, ctx->h_jn_off, n1 * 8, 0, busy) ||
+        host_reserve(ctx, ctx->h_seq, (size_t)(S.base_seq + S.tot_seq) + 64, (size_t)S.base_seq, busy) ||
+        host_reserve(ctx, ctx->h_cig_op, (size_t)(S.base_cig + S.tot_cig) + 64, (size_t)S.base_cig, busy) ||
+        host_reserve(ctx, ctx->h_cig_len, (size_t)(S.base_cig + S.tot_cig) * 4 + 64, (size_t)S.base_cig * 4, busy) ||
+        host_reserve(ctx, ctx->h_md, (size_t)(S.base_md + S.md_used) + 64, (size_t)S.base_md, busy) ||
+        host_reserve(ctx, ctx->h_jm, (size_t)(S.base_jn + S.tot_jn) + 64, (size_t)S.base_jn, busy) ||
+        host_reserve(ctx, ctx->h_ji, (size_t)(S.base_jn + S.tot_jn) * 8 + 64, (size_t)S.base_jn * 8, busy)) return TC_E_CUDA;
+    return 0;
+}
+
+// enqueues the device-to-host copies of a slot's results into the batch-wide pinned arrays
+static int slot_download(tc_ctx* ctx, Slot& S, int64_t r0, stream_t st) {
+    const int64_t n = S.n; const size_t n1 = (size_t)n + 1;
+    if (n == 0) return 0;
+    if (be_d2h(ctx, st, ctx->h_status, (size_t)r0 * 4, S.W.status, (size_t)n * 4) || be_d2h(ctx, st, ctx->h_counters, (size_t)r0 * 40, S.W.counters, (size_t)n * 40) ||
+        be_d2h(ctx, st, ctx->h_te_off, (size_t)r0 * 8, S.W.o_te, n1 * 8) || be_d2h(ctx, st, ctx->h_te, (size_t)S.base_te * 16, S.o_te.p, (size_t)S.tot_te * 16)) return TC_E_CUDA;
+    if (S.ran_dry) return 0;
+    if (be_d2h(ctx, st, ctx->h_nm, (size_t)r0 * 4, S.o_nm.p, (size_t)n * 4) || be_d2h(ctx, st, ctx->h_seq_off, (size_t)r0 * 8, S.W.o_seq, n1 * 8) ||
+        be_d2h(ctx, st, ctx->h_seq_len, (size_t)r0 * 4, S.W.seq_len_out, (size_t)n * 4) || be_d2h(ctx, st, ctx->h_seq, (size_t)S.base_seq, S.o_seq.p, (size_t)S.tot_seq) ||
+        be_d2h(ctx, st, ctx->h_cig_off, (size_t)r0 * 8, S.W.o_cig, n1 * 8) || be_d2h(ctx, st, ctx->h_cig_op, (size_t)S.base_cig, S.o_cig_op.p, (size_t)S.tot_cig) ||
+        be_d2h(ctx, st, ctx->h_cig_len, (size_t)S.base_cig * 4, S.o_cig_len.p, (size_t)S.tot_cig * 4) ||
+        be_d2h(ctx, st, ctx->h_md_off, (size_t)r0 * 8, S.o_md_off.p, (size_t)n * 8) || be_d2h(ctx, st, ctx->h_md_len, (size_t)r0 * 4, S.o_md_len.p, (size_t)n * 4) ||
+        be_d2h(ctx, st, ctx->h_md, (size_t)S.base_md, S.o_md_pool.p, (size_t)S.md_used) || be_d2h(ctx, st, ctx->h_jn_off, (size_t)r0 * 8, S.W.o_jn, n1 * 8) ||
+        be_d2h(ctx, st, ctx->h_jm, (size_t)S.base_jn, S.o_jm.p, (size_t)S.tot_jn) || be_d2h(ctx, st, ctx->h_ji, (size_t)S.base_jn * 8, S.o_ji.p, (size_t)S.tot_jn * 8)) return TC_E_CUDA;
+    return 0;
+}
+
+static void fill_out(tc_ctx* ctx, tc_batch_out* out, int64_t n) {
     memset(out, 0, sizeof(*out));
     out->n_reads = n;
-    if (n > 0) {
-        if (be_d2h(ctx, ctx->h_status, ctx->W.status, (size_t)n * 4) || be_d2h(ctx, ctx->h_counters, ctx->W.counters, (size_t)n * 40) ||
-            be_d2h(ctx, ctx->h_te_off, ctx->W.o_te, n1 * 8) || be_d2h(ctx, ctx->h_te, ctx->o_te.p, (size_t)ctx->tot_te * 16)) return TC_E_CUDA;
-        if (!ctx->ran_dry) {
-            if (be_d2h(ctx, ctx->h_nm, ctx->o_nm.p, (size_t)n * 4) || be_d2h(ctx, ctx->h_seq_off, ctx->W.o_seq, n1 * 8) || be_d2h(ctx, ctx->h_seq_len, ctx->W.seq_len_out, (size_t)n * 4) ||
-                be_d2h(ctx, ctx->h_seq, ctx->o_seq.p, (size_t)ctx->tot_seq) || be_d2h(ctx, ctx->h_cig_off, ctx->W.o_cig, n1 * 8) ||
-                be_d2h(ctx, ctx->h_cig_op, ctx->o_cig_op.p, (size_t)ctx->tot_cig) || be_d2h(ctx, ctx->h_cig_len, ctx->o_cig_len.p, (size_t)ctx->tot_cig * 4) ||
-                be_d2h(ctx, ctx->h_md_off, ctx->o_md_off.p, (size_t)n * 8) || be_d2h(ctx, ctx->h_md_len, ctx->o_md_len.p, (size_t)n * 4) ||
-                be_d2h(ctx, ctx->h_md, ctx->o_md_pool.p, (size_t)ctx->md_used) || be_d2h(ctx, ctx->h_jn_off, ctx->W.o_jn, n1 * 8) ||
-                be_d2h(ctx, ctx->h_jm, ctx->o_jm.p, (size_t)ctx->tot_jn) || be_d2h(ctx, ctx->h_ji, ctx->o_ji.p, (size_t)ctx->tot_jn * 8)) return TC_E_CUDA;
-        }
-#ifndef TC_HOSTSIM
-        CK(cudaEventRecord(ctx->ev[11], ctx->stream));
-#endif
-        if (be_sync(ctx)) return TC_E_CUDA;
-#ifndef TC_HOSTSIM
-        cudaEventElapsedTime(&ctx->tm.d2h_ms, ctx->ev[10], ctx->ev[11]);
-        cudaEventElapsedTime(&ctx->tm.h2d_ms, ctx->ev[0], ctx->ev[1]);
-#endif
-    }
     out->status = (const uint32_t*)ctx->h_status.p; out->counters = (const int32_t*)ctx->h_counters.p; out->nm = (const int32_t*)ctx->h_nm.p;
     out->seq_off = (const int64_t*)ctx->h_seq_off.p; out->seq_len = (const int32_t*)ctx->h_seq_len.p; out->seq = (const uint8_t*)ctx->h_seq.p;
     out->cig_off = (const int64_t*)ctx->h_cig_off.p; out->cig_op = (const uint8_t*)ctx->h_cig_op.p; out->cig_len = (const int32_t*)ctx->h_cig_len.p;
     out->md_off = (const int64_t*)ctx->h_md_off.p; out->md_len = (const int32_t*)ctx->h_md_len.p; out->md = (const uint8_t*)ctx->h_md.p;
     out->jn_off = (const int64_t*)ctx->h_jn_off.p; out->jm = (const int8_t*)ctx->h_jm.p; out->ji = (const int32_t*)ctx->h_ji.p;
     out->te_off = (const int64_t*)ctx->h_te_off.p; out->te = (const tc_te*)ctx->h_te.p;
+}
+
+static void reset_bases(Slot& S) { S.base_seq = S.base_cig = S.base_te = S.base_jn = S.base_md = 0; }
+
+extern "C" {
+
+int tc_batch_upload(tc_ctx* ctx, const tc_batch_in* in) {
+    if (!ctx || !in || in->n_reads < 0) return TC_E_ARG;
+    if (!ctx->have_genome) { ctx->err = "tc_batch_upload: load a genome first"; return TC_E_STATE; }
+    if (in->n_reads >= (1ll << 31) - 2) { ctx->err = "tc_batch_upload: batch too large"; return TC_E_ARG; }
+#ifndef TC_HOSTSIM
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+#endif
+    ctx->tm.h2d_bytes = 0;
+    ctx->n = in->n_reads; ctx->ran = false;
+    int rc = slot_upload(ctx, ctx->slot[0], in, 0, in->n_reads, main_stream(ctx));
+#ifndef TC_HOSTSIM
+    if (!rc) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+#endif
+    return rc;
+}
+
+int tc_batch_run(tc_ctx* ctx, int dry) {
+    if (!ctx) return TC_E_ARG;
+    if (!ctx->have_genome) { ctx->err = "tc_batch_run: load a genome first"; return TC_E_STATE; }
+#ifndef TC_HOSTSIM
+    CK(cudaSetDevice(ctx->device));
+#endif
+    ctx->tm.launches = 0; ctx->tm.md_pool_retries = 0;
+    ctx->tm.kernels_ms = ctx->tm.k_nmmd_init_ms = ctx->tm.k_measure_ms = ctx->tm.k_plan_ms = ctx->tm.k_junction_ms = ctx->tm.k_emit_ms = 0.f;
+    reset_bases(ctx->slot[0]);
+    int rc = slot_run(ctx, ctx->slot[0], dry, main_stream(ctx), true);
+    if (!rc) { ctx->ran = true; ctx->ran_dry = dry != 0; ctx->piped = false; }
+    return rc;
+}
+
+int tc_batch_download(tc_ctx* ctx, tc_batch_out* out) {
+    if (!ctx || !out) return TC_E_ARG;
+    if (!ctx->ran) { ctx->err = "tc_batch_download: nothing has run"; return TC_E_STATE; }
+    const int64_t n = ctx->n;
+    if (!ctx->piped) {
+#ifndef TC_HOSTSIM
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaEventRecord(ctx->ev[10], ctx->stream));
+#endif
+        ctx->tm.d2h_bytes = 0;
+        Slot& S = ctx->slot[0];
+        if (host_reserve_all(ctx, S, 0, n, ctx->ran_dry, main_stream(ctx)) || slot_download(ctx, S, 0, main_stream(ctx))) return TC_E_CUDA;
+#ifndef TC_HOSTSIM
+        CK(cudaEventRecord(ctx->ev[11], ctx->stream));
+#endif
+        if (be_sync(ctx, main_stream(ctx))) return TC_E_CUDA;
+#ifndef TC_HOSTSIM
+        cudaEventElapsedTime(&ctx->tm.d2h_ms, ctx->ev[10], ctx->ev[11]);
+        cudaEventElapsedTime(&ctx->tm.h2d_ms, ctx->ev[0], ctx->ev[1]);
+#endif
+    }
+    fill_out(ctx, out, n);
     return TC_OK;
 }
 
+// host columns in -> host columns out.  Large batches are cut into chunks of chunk_reads
+// reads and pipelined over three streams: upload of chunk c+1, kernels of chunk c and download
+// of chunk c-1 overlap (PCIe is full duplex); two slots alternate.
 static int run_all(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out, int dry) {
+    if (!ctx || !in || !out || in->n_reads < 0) return TC_E_ARG;
+    if (!ctx->have_genome) { ctx->err = "load a genome first"; return TC_E_STATE; }
+    const int64_t n = in->n_reads;
+#ifndef TC_HOSTSIM
+    const int64_t CH = ctx->chunk_reads;
+    if (CH > 0 && n > CH + CH / 2) {
+        CK(cudaSetDevice(ctx->device));
+        ctx->tm.h2d_bytes = ctx->tm.d2h_bytes = 0; ctx->tm.launches = 0; ctx->tm.md_pool_retries = 0;
+        ctx->tm.kernels_ms = ctx->tm.k_nmmd_init_ms = ctx->tm.k_measure_ms = ctx->tm.k_plan_ms = ctx->tm.k_junction_ms = ctx->tm.k_emit_ms = 0.f;
+        ctx->n = n; ctx->ran = false;
+        const int64_t nchunk = (n + CH - 1) / CH;
+        int64_t bs = 0, bc = 0, bt = 0, bj = 0, bm = 0;
+        CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+        if (slot_upload(ctx, ctx->slot[0], in, 0, CH < n ? CH : n, ctx->s_in)) return TC_E_CUDA;
+        CK(cudaEventRecord(ctx->slot[0].ev_in, ctx->s_in));
+        for (int64_t c = 0; c < nchunk; c++) {
+            Slot& S = ctx->slot[c & 1];
+            const int64_t r0 = c * CH;
+            if (c + 1 < nchunk) {                                   // next upload: its slot's kernels (chunk c-1) are done
+                Slot& N = ctx->slot[(c + 1) & 1];
+                const int64_t a = (c + 1) * CH, b = a + CH < n ? a + CH : n;
+                if (slot_upload(ctx, N, in, a, b, ctx->s_in)) return TC_E_CUDA;
+                CK(cudaEventRecord(N.ev_in, ctx->s_in));
+            }
+            CK(cudaStreamWaitEvent(ctx->stream, S.ev_in, 0));
+            if (c >= 2) CK(cudaStreamWaitEvent(ctx->stream, S.ev_out, 0));   // the slot's previous results have left the device
+            S.base_seq = bs; S.base_cig = bc; S.base_te = bt; S.base_jn = bj; S.base_md = bm;
+            int rc = slot_run(ctx, S, dry, ctx->stream, false);
+            if (rc) return rc;
+            CK(cudaEventRecord(S.ev_cmp, ctx->stream));
+            if (host_reserve_all(ctx, S, r0, n, dry != 0, ctx->s_out)) return TC_E_CUDA;
+            CK(cudaStreamWaitEvent(ctx->s_out, S.ev_cmp, 0));
+            if (slot_download(ctx, S, r0, ctx->s_out)) return TC_E_CUDA;
+            CK(cudaEventRecord(S.ev_out, ctx->s_out));
+            bs += S.tot_seq; bc += S.tot_cig; bt += S.tot_te; bj += S.tot_jn; bm += S.md_used;
+        }
+        CK(cudaStreamSynchronize(ctx->s_out));
+        CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaEventElapsedTime(&ctx->tm.kernels_ms, ctx->ev[0], ctx->ev[1]);
+        ctx->ran = true; ctx->ran_dry = dry != 0; ctx->piped = true;
+        fill_out(ctx, out, n);
+        return TC_OK;
+    }
+#endif
     int rc = tc_batch_upload(ctx, in);
     if (rc) return rc;
     rc = tc_batch_run(ctx, dry);
@@ -977,6 +1143,12 @@ static int run_all(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out, int dr
 }
 int tc_correct_batch(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out) { return run_all(ctx, in, out, 0); }
 int tc_dryrun_batch(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out) { return run_all(ctx, in, out, 1); }
+
+int tc_ctx_set_pipeline(tc_ctx* ctx, int64_t chunk_reads) {
+    if (!ctx || chunk_reads < 0) return TC_E_ARG;
+    ctx->chunk_reads = chunk_reads;
+    return TC_OK;
+}
 
 int tc_get_timing(tc_ctx* ctx, tc_timing* t) { if (!ctx || !t) return TC_E_ARG; *t = ctx->tm; return TC_OK; }
 

@@ -10,7 +10,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libtc_b200.so")
 
 EXPORTS = ["tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_set_options", "tc_ctx_stream",
            "tc_ctx_load_genome", "tc_ctx_load_junctions", "tc_ctx_load_variants", "tc_correct_batch",
-           "tc_dryrun_batch", "tc_batch_upload", "tc_batch_run", "tc_batch_download", "tc_get_timing"]
+           "tc_dryrun_batch", "tc_batch_upload", "tc_batch_run", "tc_batch_download", "tc_get_timing",
+           "tc_ctx_set_pipeline"]
 
 # status bits (include/tc_b200.h)
 ST_CLASS_MASK, ST_FALLBACK, ST_CIGAR_REWRITTEN = 3, 1 << 2, 1 << 3
@@ -81,6 +82,7 @@ def _declare(lib):
     lib.tc_batch_run.argtypes = [C.c_void_p, C.c_int]
     lib.tc_batch_download.argtypes = [C.c_void_p, C.POINTER(_BatchOut)]
     lib.tc_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
+    lib.tc_ctx_set_pipeline.argtypes = [C.c_void_p, C.c_int64]
     for f in EXPORTS:
         if f not in ("tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_stream"):
             getattr(lib, f).restype = C.c_int
@@ -164,6 +166,9 @@ class Engine:
         o = _Options(int(maxLenIndel), int(maxSJOffset), int(bool(correctMismatches)), int(bool(correctIndels)),
                      int(bool(correctSJs)), int(bool(sj_ignore_strand)), int(bool(sj_tie_right)), 0)
         self._check(self._lib.tc_ctx_set_options(self._ctx, C.byref(o)), "tc_ctx_set_options")
+
+    def set_pipeline(self, chunk_reads):
+        self._check(self._lib.tc_ctx_set_pipeline(self._ctx, int(chunk_reads)), "tc_ctx_set_pipeline")
 
     def load_genome(self, g):
         st, en, by = g.exceptions()
