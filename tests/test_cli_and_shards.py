@@ -1,0 +1,115 @@
+"""Host-side logic on CPU: the `transcriptclean` option surface, file outputs, and the sharded
+(N>1) paths - threads and a world_size-2 gloo group - through the hostsim engine."""
+import os
+import sys
+import tempfile
+
+import pytest
+
+import pipeline
+import synth
+from hostsim_engine import HostSimEngine
+from transcriptclean_b200 import cli, shard
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _case_files(seed, n_reads=120):
+    case = synth.make_case(seed, n_reads=n_reads)
+    d = tempfile.mkdtemp(prefix="tc_cli_")
+    case.write_fasta(d + "/g.fa"); case.write_sam(d + "/in.sam"); case.write_sj(d + "/sj.tab"); case.write_vcf(d + "/v.vcf")
+    return case, d
+
+
+def test_shard_bounds_match_split_input():
+    assert shard.shard_bounds(10, 3) == [(0, 4), (4, 8), (8, 10)]
+    assert shard.shard_bounds(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    assert shard.shard_bounds(0, 2) == [(0, 0), (0, 0)]
+
+
+def test_option_surface_and_prefix_abbreviations():
+    d = tempfile.mkdtemp()
+    o = cli.get_options(["--sam", "x.sam", "--g", "g.fa", "-j", "sj", "--maxLenIndel", "3", "--correctSJs", "False",
+                         "--primaryOnly", "--canonOnly", "--o", d + "/out/TC"])
+    assert (o.refGenome, o.sjAnnotFile, o.maxLenIndel, o.correctSJs, o.primaryOnly, o.canonOnly) == \
+        ("g.fa", "sj", 3, "false", True, True)
+    assert o.tmp_dir == d + "/out/TC_tmp/"
+    with pytest.raises(RuntimeError):
+        cli.get_options(["--correctIndels", "maybe"])
+    assert cli.get_options(["--o", d]).outprefix == d + "/TC"          # a directory gets the default prefix
+
+
+@pytest.mark.parametrize("n_engines", [1, 3])
+def test_cli_end_to_end_files(n_engines):
+    case, d = _case_files(31)
+    o = cli.get_options(["-s", d + "/in.sam", "-g", d + "/g.fa", "-j", d + "/sj.tab", "-v", d + "/v.vcf",
+                         "-o", d + "/TC", "--deleteTmp"])
+    engines = [HostSimEngine() for _ in range(n_engines)]
+    cli.run(o, engines=engines)
+    want = pipeline.oracle_texts(case.genome, case.lines, d + "/sj.tab", d + "/v.vcf", {})
+    sam = open(d + "/TC_clean.sam").read()
+    assert sam.startswith("@HD") and sam.split("\n", 1)[0] == "@HD\tVN:1.0\tSO:unsorted"
+    body = "".join(l + "\n" for l in sam.splitlines() if not l.startswith("@"))
+    assert body == want["sam"]
+    assert open(d + "/TC_clean.fa").read() == want["fa"]
+    assert open(d + "/TC_clean.log").read() == cli.LOG_HEADER + want["log"]
+    assert open(d + "/TC_clean.TE.log").read() == cli.TE_HEADER + want["te"]
+    assert not os.path.exists(d + "/TC_tmp")
+
+
+def test_cli_dry_run_writes_only_logs():
+    case = synth.make_case(32, n_reads=80, quirks=False)
+    d = tempfile.mkdtemp(prefix="tc_cli_")
+    case.write_fasta(d + "/g.fa"); case.write_sam(d + "/in.sam")
+    o = cli.get_options(["-s", d + "/in.sam", "-g", d + "/g.fa", "--dryRun", "-o", d + "/TC"])
+    cli.run(o, engines=[HostSimEngine()])
+    want = pipeline.oracle_texts(case.genome, case.lines, None, None, {}, dry=True)
+    assert open(d + "/TC_clean.log").read() == cli.LOG_HEADER + want["log"]
+    assert open(d + "/TC_clean.TE.log").read() == cli.TE_HEADER + want["te"]
+    assert not os.path.exists(d + "/TC_clean.sam") and not os.path.exists(d + "/TC_clean.fa")
+
+
+def test_unknown_chromosome_is_reported():
+    case, d = _case_files(33, 20)
+    with open(d + "/in.sam", "a") as f:
+        f.write("x\t0\tchrNope\t1\t60\t4M\t*\t0\t0\tACGT\t*\n")
+    o = cli.get_options(["-s", d + "/in.sam", "-g", d + "/g.fa", "-o", d + "/TC"])
+    with pytest.raises(RuntimeError, match="not found in the fasta reference"):
+        cli.run(o, engines=[HostSimEngine()])
+
+
+_WORKER = r"""
+import os, sys, json
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import torch.distributed as dist
+import synth, pipeline
+from hostsim_engine import HostSimEngine
+from transcriptclean_b200 import api, shard
+from transcriptclean_b200.genome import GenomeImage
+from transcriptclean_b200.tables import build_sj_tables
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+case = synth.make_case(55, n_reads=90)
+sjf, _ = pipeline.write_tables(case.sj_rows, None)
+gi = GenomeImage.from_dict(case.genome)
+chroms = set(l.split("\t")[2] for l in case.lines)
+refs = api.make_refs(gi, build_sj_tables(sjf, chroms, gi.index), None, engine=HostSimEngine())
+out = shard.correct_sharded_dist(case.lines, api.Struct(), refs, api.correct_batch_text, dist)
+if dist.get_rank() == 0:
+    want = pipeline.oracle_texts(case.genome, case.lines, sjf, None, {})
+    assert out == want, pipeline.first_diff(out, want)
+    print("RANK0_OK")
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_world_size_2_gloo_shards_concatenate_in_order():
+    import socket
+    import subprocess
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    code = _WORKER % {"root": ROOT, "port": port}
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=300)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "RANK0_OK" in outs[0]

@@ -1,0 +1,164 @@
+"""`transcriptclean` command line on top of the B200 engine.
+
+Option surface, defaults, prefix abbreviations (optparse) and output files are those of the
+reference (getOptions / cleanup_options / combine_outputs, TranscriptClean.py:72-200, 604-663).
+`--threads` keeps its place in the interface; here it is the number of GPUs to shard over
+(capped by the GPUs present), the analogue of the reference's worker processes.
+"""
+import os
+import sys
+from optparse import OptionParser
+
+from . import api
+from .genome import GenomeImage
+from .shard import correct_sharded_threads
+
+LOG_HEADER = "\t".join(["TranscriptID", "Mapping", "corrected_deletions", "uncorrected_deletions", "variant_deletions",
+                        "corrected_insertions", "uncorrected_insertions", "variant_insertions", "corrected_mismatches",
+                        "uncorrected_mismatches", "corrected_NC_SJs", "uncorrected_NC_SJs"]) + "\n"
+TE_HEADER = "\t".join(["TranscriptID", "Position", "ErrorType", "Size", "Corrected", "ReasonNotCorrected"]) + "\n"
+
+
+def get_options(argv=None):
+    p = OptionParser()
+    p.add_option("--sam", "-s", dest="sam", metavar="FILE", type="string", default="",
+                 help="Input SAM file containing transcripts to correct. Must contain a header.")
+    p.add_option("--genome", "-g", dest="refGenome", metavar="FILE", type="string", default="",
+                 help="Reference genome fasta file.")
+    p.add_option("--threads", "-t", dest="n_threads", type="int", default=1,
+                 help="Number of GPUs to shard the reads over (the reference's worker count).")
+    p.add_option("--spliceJns", "-j", dest="sjAnnotFile", metavar="FILE", type="string", default=None,
+                 help="STAR-format splice junction file.")
+    p.add_option("--variants", "-v", dest="variantFile", metavar="FILE", type="string", default=None,
+                 help="VCF of variants to avoid correcting away (optional).")
+    p.add_option("--maxLenIndel", dest="maxLenIndel", type="int", default=5, help="Maximum size indel to correct (Default: 5 bp)")
+    p.add_option("--maxSJOffset", dest="maxSJOffset", type="int", default=5,
+                 help="Maximum distance from annotated splice junction to correct (Default: 5 bp)")
+    p.add_option("--outprefix", "-o", dest="outprefix", metavar="FILE", type="string", default="TC",
+                 help="Output file prefix. '_clean' plus a file extension will be added to the end.")
+    p.add_option("--correctMismatches", "-m", dest="correctMismatches", type="string", default="true")
+    p.add_option("--correctIndels", "-i", dest="correctIndels", type="string", default="true")
+    p.add_option("--correctSJs", dest="correctSJs", type="string", default="true")
+    p.add_option("--dryRun", dest="dryRun", action="store_true", default=False)
+    p.add_option("--primaryOnly", dest="primaryOnly", action="store_true", default=False)
+    p.add_option("--canonOnly", dest="canonOnly", action="store_true", default=False)
+    p.add_option("--tmpDir", dest="tmp_path", default=None)
+    p.add_option("--bufferSize", dest="buffer_size", type="int", default=100)
+    p.add_option("--deleteTmp", dest="delete_tmp", action="store_true", default=False)
+    options, _ = p.parse_args(argv)
+    return cleanup_options(options)
+
+
+def cleanup_options(options):
+    """TC.py:158-200: case-fold and validate the true/false strings, derive TC_tmp and the prefix."""
+    for name, flag in (("correctMismatches", "--correctMismatches/-m"), ("correctIndels", "--correctIndels/-i"),
+                       ("correctSJs", "--correctSJs")):
+        v = getattr(options, name).lower()
+        if v not in ("true", "false"):
+            raise RuntimeError("Invalid choice for %s option. Valid choices are 'true' and 'false'" % flag)
+        setattr(options, name, v)
+    if options.tmp_path is not None:
+        parts = options.tmp_path.split("/")
+        options.tmp_dir = "/".join((parts if os.path.isdir(options.tmp_path) else parts[0:-1]) + ["TC_tmp/"])
+    else:
+        options.tmp_dir = "/".join(options.outprefix.split("/")[0:-1] + ["TC_tmp/"])
+    if os.path.isdir(options.outprefix):
+        options.outprefix = "/".join(options.outprefix.split("/") + ["TC"])
+    return options
+
+
+def split_sam(path):
+    """TC.py:519-541: header lines, chromosome set, alignment lines (stripped)."""
+    header, chroms, lines = [], set(), []
+    with open(path) as f:
+        for line in f:
+            line = line.strip()
+            if line.startswith("@"):
+                header.append(line)
+            elif line:
+                lines.append(line)
+                chroms.add(line.split("\t")[2])
+    return header, chroms, lines
+
+
+def validate_chroms(genome, vcf_file, sam_chroms):
+    """TC.py:463-516, same messages."""
+    fasta_chroms = set(genome.keys())
+    sam_chroms = set(sam_chroms)
+    sam_chroms.discard("*")
+    if not sam_chroms.issubset(fasta_chroms):
+        fmt = lambda s: "{" + ", ".join('"' + str(x) + '"' for x in s) + "}"
+        raise RuntimeError("One or more SAM chromosomes were not found in the fasta reference.\nSAM chromosomes:\n"
+                           + fmt(sam_chroms) + "\nFASTA chromosomes:\n" + fmt(fasta_chroms) + "\n"
+                           "One common cause of this problem is when the fasta headers contain more than one word. "
+                           "If this is the case, try trimming the headers to include only the chromosome name (i.e. '>chr1').")
+    if vcf_file is not None:
+        import gzip
+        opener = gzip.open if str(vcf_file).endswith(".gz") else open
+        try:
+            with opener(vcf_file, "rt") as f:
+                vcf_chroms = set(l.split("\t", 1)[0] for l in f if l.strip() and not l.startswith("#"))
+        except Exception as e:
+            print(e)
+            raise RuntimeError("Problem reading the provided VCF file. Please make sure that the filename is correct and "
+                               "that your VCF file is properly formatted, including a header.")
+        if len(sam_chroms & vcf_chroms) == 0:
+            fmt = lambda s: "{" + ", ".join('"' + str(x) + '"' for x in s) + "}"
+            raise RuntimeError("None of the chromosomes included in the VCF file matched the chromosomes in the provided "
+                               "SAM file.\nSAM chromosomes:\n" + fmt(sam_chroms) + "\nVCF chromosomes:\n" + fmt(vcf_chroms) + "\n")
+
+
+def write_outputs(options, header, texts):
+    """combine_outputs (TC.py:604-663): headers + bodies; no SAM / FASTA in --dryRun."""
+    pre = options.outprefix
+    with open(pre + "_clean.log", "w") as f:
+        f.write(LOG_HEADER + texts["log"])
+    with open(pre + "_clean.TE.log", "w") as f:
+        f.write(TE_HEADER + texts["te"])
+    if not options.dryRun:
+        with open(pre + "_clean.sam", "w") as f:
+            for line in header:
+                f.write(line + "\n")
+            f.write(texts["sam"])
+        with open(pre + "_clean.fa", "w") as f:
+            f.write(texts["fa"])
+
+
+def n_gpus_available():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 1
+
+
+def run(options, engines=None):
+    """engines: optional list of pre-built Engine objects (tests inject CPU stand-ins here)."""
+    header, chroms, lines = split_sam(options.sam)
+    print("Reading genome ..............................")
+    genome = GenomeImage.from_fasta(options.refGenome)
+    validate_chroms(genome, options.variantFile, chroms)
+    os.makedirs(options.tmp_dir, exist_ok=True)          # kept for interface compatibility (--tmpDir / --deleteTmp)
+    if engines is None:
+        from .engine import Engine
+        n = max(1, min(int(options.n_threads), max(1, n_gpus_available())))
+        engines = [Engine(d) for d in range(n)]
+    refs_list = [api.prep_refs(options, lines, header, engine=e, genome=genome) for e in engines]
+    if options.dryRun:
+        worker = lambda part, opts, refs: api.dry_run_text(part, refs)
+    else:
+        worker = lambda part, opts, refs: api.correct_batch_text(part, opts, refs)
+    texts = correct_sharded_threads(lines, options, refs_list, worker)
+    write_outputs(options, header, texts)
+    if options.delete_tmp:
+        import shutil
+        shutil.rmtree(options.tmp_dir, ignore_errors=True)
+    return texts
+
+
+def main(argv=None):
+    run(get_options(argv))
+
+
+if __name__ == "__main__":
+    main()
