@@ -1,0 +1,100 @@
+"""GPU parity on the BASELINE.json workload shapes (tools/synth_gen.c) at sizes the oracle
+finishes in seconds, and size-independent properties at a large size."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import goldens
+import pipeline
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from tools.workload import Workload
+    from transcriptclean_b200.engine import Engine
+    w = Workload(seed=77, chrom_len=24_000_000, n_genes=300)
+    gi = w.genome_image()
+    d = tempfile.mkdtemp(prefix="tc_wl_")
+    sjf = goldens.write_rows(w.sj_rows(), d + "/sj.tab")
+    eng = Engine(0)
+    yield w, gi, sjf, eng, d
+    eng.close()
+    w.close()
+
+
+def _compare(setup, shape, n, opts, vcf_rows=None, dry=False):
+    w, gi, sjf, eng, d = setup
+    cols, nm = w.reads(shape, n, seed_offset=3)
+    lines = w.sam_lines(cols, nm, 0, n)
+    vcf = goldens.write_rows(vcf_rows, d + "/v_%s.vcf" % shape) if vcf_rows else None
+    got = pipeline.product_texts(eng, gi, lines, sjf, vcf, opts, dry=dry)
+    want = pipeline.oracle_texts({w.chrom: w.genome.tobytes().decode()}, lines, sjf, vcf, opts, dry=dry)
+    diff = pipeline.first_diff(got, want)
+    assert diff is None, diff
+    return want
+
+
+def test_config1_pacbio_shape(setup):
+    want = _compare(setup, "pacbio", 5000, {})
+    assert want["te"].count("NC_SJ_boundary\t") > 50 and want["te"].count("Corrected") > 10000
+
+
+def test_config2_variant_aware(setup):
+    from tools.workload import variants_from_reads
+    w = setup[0]
+    cols, nm = w.reads("pacbio", 4000, seed_offset=3)
+    rows = variants_from_reads(w, cols, 0, 4000, frac=0.3)
+    want = _compare(setup, "pacbio", 4000, {}, vcf_rows=rows)
+    assert want["te"].count("VariantMatch") > 3000
+
+
+def test_config3_ont_shape_canon_only(setup):
+    want = _compare(setup, "ont", 3000, {"canonOnly": True})
+    assert want["te"].count("TooLarge") > 500 and want["sam"].count("\n") < 3000
+
+
+def test_config4_dry_run_then_full(setup):
+    _compare(setup, "ont", 2000, {}, dry=True)
+    _compare(setup, "ont", 2000, {"primaryOnly": True})
+
+
+def test_large_batch_properties(setup):
+    """300k reads: the pipelined host-buffer path and the device-resident path agree byte for
+    byte; counters account for every TE row; every new SEQ has the length its CIGAR implies."""
+    from transcriptclean_b200 import engine as E
+    from transcriptclean_b200.tables import build_sj_tables
+    w, gi, sjf, eng, d = setup
+    eng.set_options()
+    eng.load_genome(gi)
+    eng.load_junctions(build_sj_tables(sjf, {w.chrom}, gi.index))
+    from transcriptclean_b200.tables import VariantTables
+    eng.load_variants(VariantTables())
+    n = 300000
+    cols, nm = w.reads("pacbio", n, seed_offset=9)
+    eng.set_pipeline(50000)
+    a = eng.correct(cols)                  # pipelined, 6 chunks
+    eng.set_pipeline(0)
+    b = eng.correct(cols)                  # one piece
+    eng.set_pipeline(131072)
+    for name in ("status", "counters", "nm", "seq_len", "cig_op", "cig_len", "jm", "ji", "te_off", "cig_off", "jn_off", "seq_off"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    assert np.array_equal(a.te, b.te)
+    assert np.array_equal(a.md_len, b.md_len)
+    # SEQ rows (padding bytes excluded) and MD values compared through their offsets
+    idx = np.flatnonzero(a.seq_len > 0)[::97]
+    for i in idx:
+        assert a.seq[a.seq_off[i]:a.seq_off[i] + a.seq_len[i]].tobytes() == b.seq[b.seq_off[i]:b.seq_off[i] + b.seq_len[i]].tobytes()
+        assert a.md[a.md_off[i]:a.md_off[i] + a.md_len[i]].tobytes() == b.md[b.md_off[i]:b.md_off[i] + b.md_len[i]].tobytes()
+    primary = (a.status & E.ST_CLASS_MASK) == 0
+    ok = primary & ((a.status & E.ST_FALLBACK) == 0)
+    c = np.where(a.counters < 0, 0, a.counters)
+    assert np.array_equal(c[ok].sum(axis=1), np.diff(a.te_off)[ok])
+    qlen = np.where(np.isin(a.cig_op, np.frombuffer(b"MIS", dtype=np.uint8)), a.cig_len, 0).astype(np.int64)
+    per = np.add.reduceat(np.concatenate((qlen, [0])), np.minimum(a.cig_off[:-1], len(qlen)))
+    per = np.where(np.diff(a.cig_off) > 0, per, 0)
+    assert np.array_equal(per[primary], a.seq_len[primary].astype(np.int64))
+    assert int((a.status & (E.ST_ERR_INTRON | E.ST_ERR_MERGE)).sum()) == 0

@@ -136,3 +136,54 @@ class Workload:
 
     def close(self):
         self.lib.tcsynth_free_genes(C.byref(self.genes))
+
+
+def variants_from_reads(w, cols, lo, hi, frac=0.3, seed=1):
+    """VCF rows (CHROM POS ID REF ALT) that whitelist a fraction of the errors planted in reads
+    [lo, hi): the variant-aware configuration of BASELINE.json (configs[2]) at test scale."""
+    import re
+    rng = np.random.default_rng(seed)
+    g = w.genome
+    rows = []
+    for i in range(lo, hi):
+        if cols["chrom"][i] < 0 or cols["flag"][i] > 16 or not (cols["tags"][i] & 2):
+            continue
+        a, b = cols["cig_off"][i], cols["cig_off"][i + 1]
+        md = cols["md"][cols["md_off"][i]:cols["md_off"][i + 1]].tobytes().decode()
+        seq = cols["seq"][cols["seq_off"][i]:cols["seq_off"][i + 1]].tobytes().decode()
+        toks = re.findall(r"[0-9]+|\^[A-Za-z]+|[A-Za-z]", md)
+        # walk CIGAR; mismatch positions from MD
+        mm = []
+        ref_i = 0
+        for t in toks:
+            if t[0].isdigit():
+                ref_i += int(t)
+            elif t[0] == "^":
+                ref_i += len(t) - 1
+            else:
+                mm.append(ref_i); ref_i += 1
+        gp, q, ref_i, k = int(cols["pos"][i]), 0, 0, 0
+        for op, ct in zip(cols["cig_op"][a:b], cols["cig_len"][a:b]):
+            op, ct = chr(op), int(ct)
+            if op == "M":
+                while k < len(mm) and mm[k] < ref_i + ct:
+                    off = mm[k] - ref_i
+                    if rng.random() < frac:
+                        rows.append([w.chrom, gp + off, ".", chr(g[gp + off - 1]).upper(), seq[q + off]])
+                    k += 1
+                gp += ct; q += ct; ref_i += ct
+            elif op == "D":
+                if rng.random() < frac:
+                    rows.append([w.chrom, gp - 1, ".", g[gp - 2:gp - 1 + ct].tobytes().decode().upper(), chr(g[gp - 2]).upper()])
+                gp += ct; ref_i += ct
+            elif op == "I":
+                if rng.random() < frac:
+                    anchor = chr(g[gp - 2]).upper()
+                    rows.append([w.chrom, gp - 1, ".", anchor, anchor + seq[q:q + ct]])
+                q += ct
+            elif op == "S":
+                q += ct
+            elif op in "NH":
+                gp += ct
+    rows.sort(key=lambda r: r[1])
+    return rows
