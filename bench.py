@@ -150,10 +150,14 @@ def run_reference_arm(args):
                              "sample": "first %d reads of the workload per step, %d forked workers, oracle/tc_oracle.py "
                                        "with the reference's per-base genome walk" % (n_sample, threads)},
             "e2e": {"value": rate, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def main():
+    # stdout carries exactly one JSON line: everything else (NCCL banner, library chatter) goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -167,6 +171,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=3000)
     ap.add_argument("--ref-reads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--debug-mask", type=int, default=0, help="profiling aid: skip phases of k_emit (results invalid)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -192,7 +197,7 @@ def main():
     cols, nm = w.reads(args.shape, args.reads, seed_offset=rank)
     gi = w.genome_image()
     eng = E.Engine(local)
-    eng.set_options()
+    eng.set_options(debug=args.debug_mask)
     eng.load_genome(gi)
     eng.load_junctions(build_sj_tables(sj_path, {w.chrom}, gi.index))
 
@@ -302,7 +307,7 @@ def main():
                                 "sample": "first %d reads of the same batch, 1 thread, oracle/tc_oracle.py with the "
                                           "reference's per-base genome walk (%.1f s)" % (ns, sec)}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -278,8 +278,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
         u64* const ws = W.ws + W.ws_off[i];
         const tc_te* const ws_te = reinterpret_cast<const tc_te*>(ws + 3ll * cig_cap + 3ll * seg_cap);
         // ---- TE rows: stage order (mismatch, insertion, deletion, junction), positional inside
+        const int dbg = P.O.reserved;     // profiling aid: bit0 skip small copies, bit1 skip SEQ, bit2 skip NM/MD (results invalid)
         const int nte = PF(EP_NTE);
-        if (nte > 0) {
+        if (nte > 0 && !(dbg & 1)) {
             tc_te* dst = O.te + W.o_te[i];
             if (dry) { for (int k = lane; k < nte; k += 32) dst[k] = ws_te[k]; }
             else {
@@ -304,11 +305,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
         else { cs.packed = ws + (int64_t)cb * cig_cap; cs.op = 0; cs.len = 0; }
         {
             const int64_t oc = W.o_cig[i]; uint8_t* dop = O.cig_op + oc; int32_t* dl = O.cig_len + oc;
-            for (int k = lane; k < cs.n; k += 32) { int op; int32_t l; cig_get(cs, k, op, l); dop[k] = (uint8_t)op; dl[k] = l; }
+            if (!(dbg & 1)) for (int k = lane; k < cs.n; k += 32) { int op; int32_t l; cig_get(cs, k, op, l); dop[k] = (uint8_t)op; dl[k] = l; }
         }
         // ---- jM / jI snapshot
         const int nj = PF(EP_NJN);
-        if (nj > 0) {
+        if (nj > 0 && !(dbg & 1)) {
             const int64_t oj = W.o_jn[i]; int8_t* djm = O.jm + oj; int32_t* dji = O.ji + 2 * oj;
             const int32_t* jn = reinterpret_cast<const int32_t*>(ws + 3ll * cig_cap + 3ll * seg_cap + 2ll * PF(EP_TECAP));
             for (int k = lane; k < nj; k += 32) {
@@ -328,6 +329,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
         const int ns = PF(EP_NSEG);
         bool fast = out_len <= EMIT_CAP;
         int nbp = 0, ngi = 0;
+        if (dbg & 2) { if (pflags & 1) { } continue; }
         if (fast) {
             // (A) segment list -> starts of input slices (output offset, shift) + genome slices
             if (sb < 0) { if (lane == 0) { SM.bp_pos[0] = 0; SM.bp_shift[0] = 0; } nbp = 1; }
@@ -415,7 +417,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
             }
         }
         // ---- NM / MD
-        if (pflags & 1) {
+        if ((pflags & 1) && !(dbg & 4)) {
             __syncwarp();
             int nm, len; int64_t off; bool none;
             if (fast) nmmd_to_pool<true>(P.G, SM.seq, lut, cs, chrom, pos, lane, O.md_cursor, O.md_cap, O.md_pool, nm, len, off, none);

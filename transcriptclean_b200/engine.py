@@ -162,9 +162,9 @@ class Engine:
         return self._lib.tc_ctx_stream(self._ctx)
 
     def set_options(self, maxLenIndel=5, maxSJOffset=5, correctMismatches=True, correctIndels=True,
-                    correctSJs=True, sj_ignore_strand=False, sj_tie_right=False):
+                    correctSJs=True, sj_ignore_strand=False, sj_tie_right=False, debug=0):
         o = _Options(int(maxLenIndel), int(maxSJOffset), int(bool(correctMismatches)), int(bool(correctIndels)),
-                     int(bool(correctSJs)), int(bool(sj_ignore_strand)), int(bool(sj_tie_right)), 0)
+                     int(bool(correctSJs)), int(bool(sj_ignore_strand)), int(bool(sj_tie_right)), int(debug))
         self._check(self._lib.tc_ctx_set_options(self._ctx, C.byref(o)), "tc_ctx_set_options")
 
     def set_pipeline(self, chunk_reads):
