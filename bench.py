@@ -241,6 +241,7 @@ def main():
         for k in kern:
             kern[k] += t[k]
         launches += t["launches"]
+        exact_reads = t["exact_nmmd_reads"]
     e1.record(stream)
     barrier()
     ms_run = e0.elapsed_time(e1)
@@ -293,7 +294,7 @@ def main():
         "e2e": {"value": reads_total * steps / (ms_e2e * 1e-3), "unit": "reads/s", "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": int(launches),
-        "kernel_ms_per_step": per,
+        "kernel_ms_per_step": per, "exact_nmmd_reads_per_step": int(exact_reads),
         "roofline": {"bound": "hbm", "kernel": dom.replace("_ms", ""), "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom_bytes},

@@ -119,6 +119,7 @@ typedef struct {
     int32_t launches;         /* kernels of this library launched by the call */
     int32_t md_pool_retries;
     int64_t h2d_bytes, d2h_bytes;
+    int64_t exact_nmmd_reads; /* reads whose NM/MD needed the exact path (a difference to the genome, a D op, ...) */
 } tc_timing;
 
 tc_ctx* tc_ctx_create(int device);

@@ -30,14 +30,20 @@
 struct OutDev {
     int32_t* nm; int64_t* md_off; int32_t* md_len;
     uint8_t* md_pool; unsigned long long* md_cursor; int64_t md_cap;
+    int64_t md_inline;       // MD values of <= 8 bytes live at md_inline + 8*i (no allocation); longer ones in the pool behind
     uint8_t* seq; uint8_t* cig_op; int32_t* cig_len; tc_te* te; int8_t* jm; int32_t* ji;
 };
 struct InitDev { uint8_t* pool; unsigned long long* cursor; int64_t cap; };
 
 TC_HD int ndigits(uint32_t v) {
-    int n = 1;
-    while (v >= 10) { v /= 10; n++; }
-    return n;
+    return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 : v < 10000000u ? 7 :
+           v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
+}
+// decimal digits of v (nd of them, nd <= 8) packed little-endian into one 64-bit word
+TC_HD unsigned long long dec_word(uint32_t v, int nd) {
+    unsigned long long w = 0;
+    for (int k = nd - 1; k >= 0; k--) { w |= (unsigned long long)('0' + v % 10) << (8 * k); v /= 10; }
+    return w;
 }
 TC_HD void write_dec(uint8_t* dst, uint32_t v, int nd) {
     for (int k = nd - 1; k >= 0; k--) { dst[k] = (uint8_t)('0' + v % 10); v /= 10; }
@@ -57,11 +63,22 @@ TC_HD void cig_get(const CigSrc& c, int k, int& op, int32_t& len) {
 #define EMIT_CAP 4096            // reads whose new SEQ fits are staged in shared memory
 #define EMIT_MAXBP 192
 #define EMIT_MAXGI 192
+#define EMIT_GBUF_WORDS 400
 
+#define EMIT_MAXRUN 64
 struct __align__(16) EmitSmem {  // per warp
     uint8_t seq[EMIT_CAP + 32];
-    uint16_t bp_pos[EMIT_MAXBP]; int16_t bp_shift[EMIT_MAXBP];     // starts of input-SEQ slices: output offset, src-dst shift
-    uint16_t gi_out[EMIT_MAXGI]; uint16_t gi_len[EMIT_MAXGI]; int32_t gi_src[EMIT_MAXGI];   // genome slices
+    uint8_t chunk_bp[(EMIT_CAP >> 4) + 16];                             // slice in force at the start of each 16-byte chunk
+    union {
+        struct {                                                        // while SEQ is built
+            uint16_t bp_pos[EMIT_MAXBP]; int16_t bp_shift[EMIT_MAXBP]; // starts of input-SEQ slices: output offset, src-dst shift
+            uint16_t gi_out[EMIT_MAXGI]; uint16_t gi_len[EMIT_MAXGI]; int32_t gi_src[EMIT_MAXGI];   // genome slices
+        };
+        struct {                                                        // while NM/MD is verified (tier 1)
+            uint16_t run_q[EMIT_MAXRUN], run_ct[EMIT_MAXRUN], run_w[EMIT_MAXRUN]; int32_t run_g[EMIT_MAXRUN];   // M runs
+            uint32_t gbuf[EMIT_GBUF_WORDS + 4];                         // their 2-bit genome words
+        };
+    };
 };
 #define EMIT_SMEM_BYTES (1024 + WARPS_PER_BLOCK * sizeof(EmitSmem))
 
@@ -211,10 +228,10 @@ __device__ __forceinline__ int64_t pool_grab(unsigned long long* cursor, int64_t
 template <bool FAST>
 __device__ __forceinline__ void nmmd_to_pool(const GenomeDev& G, const uint8_t* seq, const uint32_t* lut, const CigSrc& cs,
                                              int chrom, int64_t pos, int lane, unsigned long long* cursor, int64_t cap,
-                                             uint8_t* pool, int& nm, int& len, int64_t& off, bool& none) {
+                                             uint8_t* pool, int64_t inline_off, int& nm, int& len, int64_t& off, bool& none) {
     NmMd r = warp_nmmd<false, FAST>(G, seq, lut, cs, chrom, pos, lane, 0);
     none = r.none; nm = r.nm; len = r.none ? 0 : r.len;
-    off = pool_grab(cursor, cap, len, lane);
+    off = (inline_off >= 0 && len <= 8) ? inline_off : pool_grab(cursor, cap, len, lane);
     if (off >= 0 && len > 0) {
         if (r.ntok == 0) { if (lane == 0) write_dec(pool + off, (uint32_t)r.carry, len); }
         else warp_nmmd<true, FAST>(G, seq, lut, cs, chrom, pos, lane, pool + off);
@@ -232,7 +249,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_init(Params P, InitDev
             CigSrc cs; cs.packed = 0; cs.op = P.B.cig_op + P.B.cig_off[i]; cs.len = P.B.cig_len + P.B.cig_off[i];
             cs.n = (int)(P.B.cig_off[i + 1] - P.B.cig_off[i]);
             int nm, len; int64_t off; bool none;
-            nmmd_to_pool<false>(P.G, P.B.seq + P.B.seq_off[i], 0, cs, P.B.chrom[i], P.B.pos[i], lane, I.cursor, I.cap, I.pool, nm, len, off, none);
+            nmmd_to_pool<false>(P.G, P.B.seq + P.B.seq_off[i], 0, cs, P.B.chrom[i], P.B.pos[i], lane, I.cursor, I.cap, I.pool, -1, nm, len, off, none);
             st |= TC_ST_NMMD_DEVICE;
             if (none) { st |= TC_ST_NMMD_NONE; nm = 0; }
             if (lane == 0) { P.W.md_init_off[i] = off < 0 ? 0 : off; P.W.md_init_len[i] = off < 0 ? 0 : len; nm_init[i] = nm; }
@@ -243,15 +260,42 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_init(Params P, InitDev
 
 __global__ void k_measure(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) measure_read(P, i); }
 __global__ void __launch_bounds__(128, 8) k_plan(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) plan_read(P, i); }
-__global__ void __launch_bounds__(128, 8) k_junction(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) junction_read(P, i); }
+// junction objects for every read; reads that need cleanNoncanonical are appended to `list`
+__global__ void __launch_bounds__(128, 8) k_jn_init(Params P, int32_t* list, unsigned* count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.B.n && junction_init_read(P, i)) list[atomicAdd(count, 1u)] = (int32_t)i;
+}
+// noncanonical junction rescue, one thread per listed read (dense: no idle lanes next to a busy one)
+__global__ void __launch_bounds__(128, 8) k_jn_fix(Params P, const int32_t* list, const unsigned* count) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (int64_t)*count) junction_fix_read(P, list[t]);
+}
 __global__ void k_sizes(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) sizes_read(P, i); }
 __global__ void k_dry(Params P) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P.B.n) { dry_read(P, i); dry_sizes(P, i); }
 }
 
+__global__ void k_pack(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) pack_read(P, i); }
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // Output stage: one warp per read.  [seq_lo, seq_hi) = 32-bit words of B.seq that may be read
 // (the batch's SEQ buffer on the device, padded).
+//   1. plan row (128 B, one word per lane) -> everything about the read; the next read's row,
+//      segment list and SEQ lines are prefetched into L2 meanwhile
+//   2. TE rows back into stage order (ballot partition), CIGAR and jM/jI copies
+//   3. SEQ: built in shared memory - (A) segment list -> slice table, (B) 16-byte chunks gathered
+//      from the input SEQ with the shift in force, (C) fix-ups after slice starts, (D) genome
+//      slices byte-exact, (E) one coalesced 16-byte-vector store
+//   4. NM/MD (getNMandMDFlags): tier 1 stages the 2-bit genome words of every M run in shared
+//      memory with cp.async (all loads in flight at once) and verifies 16 bases per lane against
+//      the staged SEQ; a read that verifies clean needs no token (MD = total match length).
+//      Anything else (a difference, a D op, a literal run, the contig end) takes warp_nmmd.
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutDev O, int dry, int64_t seq_lo, int64_t seq_hi) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw);             // 4 bases (8 bits of the 2-bit plane) -> 4 ASCII bytes
@@ -267,69 +311,73 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
     const int64_t nw = (int64_t)gridDim.x * WARPS_PER_BLOCK;
     const BatchDev& B = P.B; const WorkDev& W = P.W;
     const uint32_t* S32 = reinterpret_cast<const uint32_t*>(B.seq);
-    for (int64_t i = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); i < B.n; i += nw) {
-        uint32_t st = W.status[i];
-        if ((st & TC_ST_CLASS_MASK) != 0) { if (lane == 0) { O.md_off[i] = 0; O.md_len[i] = 0; O.nm[i] = 0; } continue; }
-        // the read's plan row: one word per lane, fields broadcast by shuffle
-        const int pw = lane < 16 ? W.plan[i].w[lane] : 0;
+    const int dbg = P.O.reserved;     // profiling aid: bit0 skip small copies, bit1 skip SEQ, bit2 skip NM/MD (results invalid)
+    int64_t i = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int pw = i < B.n ? W.plan[i].w[lane] : 0;
+    for (; i < B.n; i += nw) {
 #define PF(k) __shfl_sync(FULL, pw, (k))
+#define PF64(k) ((int64_t)(((u64)(uint32_t)PF((k) + 1) << 32) | (u64)(uint32_t)PF(k)))
+        uint32_t st = (uint32_t)PF(EP_STATUS);
         const int pflags = PF(EP_FLAGS), cig_cap = PF(EP_CIGCAP), seg_cap = PF(EP_SEGCAP), nm_extra = PF(EP_NMEXTRA);
+        const int ncig = PF(EP_NCIG), nte = PF(EP_NTE), nj = PF(EP_NJN), out_len = PF(EP_OUTLEN), ns = PF(EP_NSEG), te_cap = PF(EP_TECAP);
+        const int te_mm = PF(EP_TEMM), te_ins = PF(EP_TEINS), te_del = PF(EP_TEDEL);
+        const int chrom = PF(EP_CHROM); const int64_t pos = PF(EP_POS);
+        const int64_t ws_off = PF64(EP_WS_LO), o_seq = PF64(EP_OSEQ_LO), o_cig = PF64(EP_OCIG_LO), o_te = PF64(EP_OTE_LO), o_jn = PF64(EP_OJN_LO);
+        const int64_t in_base = PF64(EP_INB_LO), cig0 = PF64(EP_CIG0_LO); const int Lq = PF(EP_LQ);
+        // next read: fetch its row now (consumed at the end of this iteration), and pull its segment
+        // list and SEQ lines towards L2
+        const int64_t inext = i + nw;
+        const int pw_next = inext < B.n ? W.plan[inext].w[lane] : 0;
+        if ((st & TC_ST_CLASS_MASK) != 0) { if (lane == 0) { O.md_off[i] = 0; O.md_len[i] = 0; O.nm[i] = 0; } pw = pw_next; continue; }
+        u64* const ws = W.ws + ws_off;
+        const tc_te* const ws_te = reinterpret_cast<const tc_te*>(ws + 3ll * seg_cap + 3ll * cig_cap);
         const int cb = ((pflags >> 2) & 3) - 1, sb = ((pflags >> 4) & 3) - 1;
-        u64* const ws = W.ws + W.ws_off[i];
-        const tc_te* const ws_te = reinterpret_cast<const tc_te*>(ws + 3ll * cig_cap + 3ll * seg_cap);
         // ---- TE rows: stage order (mismatch, insertion, deletion, junction), positional inside
-        const int dbg = P.O.reserved;     // profiling aid: bit0 skip small copies, bit1 skip SEQ, bit2 skip NM/MD (results invalid)
-        const int nte = PF(EP_NTE);
         if (nte > 0 && !(dbg & 1)) {
-            tc_te* dst = O.te + W.o_te[i];
+            tc_te* dst = O.te + o_te;
             if (dry) { for (int k = lane; k < nte; k += 32) dst[k] = ws_te[k]; }
             else {
-                int base[4]; base[0] = 0; base[1] = PF(EP_TEMM); base[2] = base[1] + PF(EP_TEINS); base[3] = base[2] + PF(EP_TEDEL);
+                int base0 = 0, base1 = te_mm, base2 = te_mm + te_ins, base3 = te_mm + te_ins + te_del;
                 for (int c = 0; c < nte; c += 32) {
                     const int k = c + lane; const bool valid = k < nte;
                     tc_te r; int t = -1;
                     if (valid) { r = ws_te[k]; t = r.type; }
-#pragma unroll
-                    for (int ty = 0; ty < 4; ty++) {
-                        const unsigned m = __ballot_sync(FULL, t == ty);
-                        if (t == ty) dst[base[ty] + __popc(m & lt)] = r;
-                        base[ty] += __popc(m);
+                    const unsigned m0 = __ballot_sync(FULL, t == 0), m1 = __ballot_sync(FULL, t == 1), m2 = __ballot_sync(FULL, t == 2), m3 = __ballot_sync(FULL, t == 3);
+                    if (valid) {
+                        const int slot = t == 0 ? base0 + __popc(m0 & lt) : t == 1 ? base1 + __popc(m1 & lt) : t == 2 ? base2 + __popc(m2 & lt) : base3 + __popc(m3 & lt);
+                        dst[slot] = r;
                     }
+                    base0 += __popc(m0); base1 += __popc(m1); base2 += __popc(m2); base3 += __popc(m3);
                 }
             }
         }
-        if (dry) { if (lane == 0) { O.md_off[i] = 0; O.md_len[i] = 0; O.nm[i] = 0; } continue; }
+        if (dry) { if (lane == 0) { O.md_off[i] = 0; O.md_len[i] = 0; O.nm[i] = 0; } pw = pw_next; continue; }
         // ---- CIGAR
-        CigSrc cs; cs.n = PF(EP_NCIG);
-        if (cb < 0) { cs.packed = 0; cs.op = B.cig_op + B.cig_off[i]; cs.len = B.cig_len + B.cig_off[i]; }
-        else { cs.packed = ws + (int64_t)cb * cig_cap; cs.op = 0; cs.len = 0; }
-        {
-            const int64_t oc = W.o_cig[i]; uint8_t* dop = O.cig_op + oc; int32_t* dl = O.cig_len + oc;
-            if (!(dbg & 1)) for (int k = lane; k < cs.n; k += 32) { int op; int32_t l; cig_get(cs, k, op, l); dop[k] = (uint8_t)op; dl[k] = l; }
+        CigSrc cs; cs.n = ncig;
+        if (cb < 0) { cs.packed = 0; cs.op = B.cig_op + cig0; cs.len = B.cig_len + cig0; }
+        else { cs.packed = ws + 3ll * seg_cap + (int64_t)cb * cig_cap; cs.op = 0; cs.len = 0; }
+        if (!(dbg & 1)) {
+            uint8_t* dop = O.cig_op + o_cig; int32_t* dl = O.cig_len + o_cig;
+            for (int k = lane; k < ncig; k += 32) { int op; int32_t l; cig_get(cs, k, op, l); dop[k] = (uint8_t)op; dl[k] = l; }
         }
         // ---- jM / jI snapshot
-        const int nj = PF(EP_NJN);
         if (nj > 0 && !(dbg & 1)) {
-            const int64_t oj = W.o_jn[i]; int8_t* djm = O.jm + oj; int32_t* dji = O.ji + 2 * oj;
-            const int32_t* jn = reinterpret_cast<const int32_t*>(ws + 3ll * cig_cap + 3ll * seg_cap + 2ll * PF(EP_TECAP));
+            int8_t* djm = O.jm + o_jn; int32_t* dji = O.ji + 2 * o_jn;
+            const int32_t* jn = reinterpret_cast<const int32_t*>(ws + 3ll * seg_cap + 3ll * cig_cap + 2ll * te_cap);
             for (int k = lane; k < nj; k += 32) {
                 const int32_t* r = jn + k * JN_STRIDE;
                 djm[k] = (int8_t)r[7]; dji[2 * k] = r[5]; dji[2 * k + 1] = r[6];
             }
         }
+        if (dbg & 2) { pw = pw_next; continue; }
         // ---- SEQ
-        const int64_t in_base = B.seq_off[i];
         const uint8_t* in_seq = B.seq + in_base;
-        const int64_t Lq = B.seq_off[i + 1] - in_base;
-        const int out_len = PF(EP_OUTLEN);
-        uint8_t* out_seq = O.seq + W.o_seq[i];
-        const int chrom = B.chrom[i]; const int64_t pos = B.pos[i];
-        const int64_t gbase = P.G.chrom_off[chrom] - 1 + pos;            // plane index of the read's first reference base
-        const u64* const ws_seg = ws + 3ll * cig_cap + (int64_t)(sb < 0 ? 0 : sb) * seg_cap;
-        const int ns = PF(EP_NSEG);
+        uint8_t* out_seq = O.seq + o_seq;
+        const int64_t goff = P.G.chrom_off[chrom] - 1, clen = P.G.chrom_len[chrom];
+        const int64_t gbase = goff + pos;                                // plane index of the read's first reference base
+        const u64* const ws_seg = ws + (int64_t)(sb < 0 ? 0 : sb) * seg_cap;
         bool fast = out_len <= EMIT_CAP;
         int nbp = 0, ngi = 0;
-        if (dbg & 2) { if (pflags & 1) { } continue; }
         if (fast) {
             // (A) segment list -> starts of input slices (output offset, shift) + genome slices
             if (sb < 0) { if (lane == 0) { SM.bp_pos[0] = 0; SM.bp_shift[0] = 0; } nbp = 1; }
@@ -358,18 +406,32 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
                 if (__any_sync(FULL, bad)) fast = false;
             }
         }
+        // the next read's segment list and SEQ lines -> L2 while this read is being built
+        if (inext < B.n) {
+            const int64_t nws = ((int64_t)__shfl_sync(FULL, pw_next, EP_WS_HI) << 32) | (uint32_t)__shfl_sync(FULL, pw_next, EP_WS_LO);
+            const int64_t nin = ((int64_t)__shfl_sync(FULL, pw_next, EP_INB_HI) << 32) | (uint32_t)__shfl_sync(FULL, pw_next, EP_INB_LO);
+            const int nlq = __shfl_sync(FULL, pw_next, EP_LQ);
+            if (lane < 2) prefetch_l2(W.ws + nws + lane * 16);
+            else if ((lane - 2) * 128 < nlq) prefetch_l2(B.seq + nin + (lane - 2) * 128);
+        }
         if (fast) {
             __syncwarp();
             bool read_exc = false;
             for (int k = lane; k < ngi; k += 32) { const int64_t src = gbase + SM.gi_src[k]; read_exc |= genome_blk_has_exc(P.G, src) | genome_blk_has_exc(P.G, src + SM.gi_len[k] - 1) | (SM.gi_len[k] > 256); }
             read_exc = __any_sync(FULL, read_exc);
             const int nchunk = (out_len + 15) >> 4;
-            int top = 1; while (top * 2 < nbp) top <<= 1; if (nbp <= 1) top = 0;
+            // each slice writes its index into the chunks that start inside it (slice k is in force from the
+            // first chunk boundary at or after its start up to the next slice's first chunk)
+            for (int k = lane; k < nbp; k += 32) {
+                const int c0 = k == 0 ? 0 : ((int)SM.bp_pos[k] + 15) >> 4;
+                const int c1 = k + 1 < nbp ? ((int)SM.bp_pos[k + 1] + 15) >> 4 : nchunk;
+                for (int c = c0; c < c1; c++) SM.chunk_bp[c] = (uint8_t)k;
+            }
+            __syncwarp();
             // (B) bulk copy, 16 output bytes per lane, with the shift in force at the chunk start
             for (int c = lane; c < nchunk; c += 32) {
-                const int p = c << 4; int k = 0;
-                for (int step = top; step; step >>= 1) { const int t = k + step; if (t < nbp && (int)SM.bp_pos[t] <= p) k = t; }
-                int64_t a = in_base + p + (nbp ? (int)SM.bp_shift[k] : 0);
+                const int p = c << 4; const int k = SM.chunk_bp[c];
+                const int64_t a = in_base + p + (nbp ? (int)SM.bp_shift[k] : 0);
                 int64_t wi = a >> 2; const int sh = (int)(a & 3) * 8;
                 if (wi < seq_lo) wi = seq_lo;
                 if (wi + 4 >= seq_hi) wi = seq_hi - 5;
@@ -384,7 +446,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
                 if (b & 15) {
                     int end = (b | 15) + 1; if (end > out_len) end = out_len;
                     if (k + 1 < nbp && (int)SM.bp_pos[k + 1] < end) end = SM.bp_pos[k + 1];
-                    int64_t a = in_base + b + (int)SM.bp_shift[k];
+                    const int64_t a = in_base + b + (int)SM.bp_shift[k];
                     int64_t wi = a >> 2; const int sh = (int)(a & 3) * 8;
                     if (wi < seq_lo) wi = seq_lo;
                     if (wi + 4 >= seq_hi) wi = seq_hi - 5;
@@ -418,10 +480,99 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
         }
         // ---- NM / MD
         if ((pflags & 1) && !(dbg & 4)) {
-            __syncwarp();
-            int nm, len; int64_t off; bool none;
-            if (fast) nmmd_to_pool<true>(P.G, SM.seq, lut, cs, chrom, pos, lane, O.md_cursor, O.md_cap, O.md_pool, nm, len, off, none);
-            else nmmd_to_pool<false>(P.G, out_seq, lut, cs, chrom, pos, lane, O.md_cursor, O.md_cap, O.md_pool, nm, len, off, none);
+            __syncwarp();                                              // SM tables are dead from here on: their space holds the run list
+            int nm = 0, len = 0; int64_t off = 0; bool none = false; bool done = false;
+            if (fast && ncig <= 32 * 4) {
+                // tier 1: run list (query offset, reference offset, length) of the M ops, lane-parallel
+                uint16_t* run_q = SM.run_q; uint16_t* run_ct = SM.run_ct; uint16_t* run_w = SM.run_w; int32_t* run_g = SM.run_g;
+                int nrun = 0, qcur = 0, nD = 0, ibases = 0; int64_t gcur = 0; bool ovf = false;
+                for (int k0 = 0; k0 < ncig; k0 += 32) {
+                    int op = 0; int32_t ct = 0;
+                    if (k0 + lane < ncig) cig_get(cs, k0 + lane, op, ct);
+                    const int qadv = (op == 'M' || op == 'I' || op == 'S') ? ct : 0;
+                    const int gadv = (op == 'M' || op == 'D' || op == 'N' || op == 'H') ? ct : 0;
+                    int qtot, gtot; const int qs = warp_excl_scan(qadv, lane, qtot); const int gs = warp_excl_scan(gadv, lane, gtot);
+                    const bool isM = op == 'M' && ct > 0;
+                    const unsigned mM = __ballot_sync(FULL, isM);
+                    nD += __popc(__ballot_sync(FULL, op == 'D'));
+                    ibases += op == 'I' ? ct : 0;
+                    if (isM) {
+                        const int idx = nrun + __popc(mM & lt);
+                        if (idx < EMIT_MAXRUN && gcur + gs < 0x7fffffffll) { run_q[idx] = (uint16_t)(qcur + qs); run_g[idx] = (int32_t)(gcur + gs); run_ct[idx] = (uint16_t)ct; }
+                        else ovf = true;
+                        // literal runs (N, IUPAC) under this M run?  (blocks of 256 bases; a run spans at most 17)
+                        const int64_t ga = gbase + gcur + gs;
+                        for (int64_t b = ga >> 8; b <= (ga + ct - 1) >> 8; b++) ovf |= (P.G.excblk[b >> 5] >> (b & 31)) & 1u;
+                    }
+                    nrun += __popc(mM); qcur += qtot; gcur += gtot;
+                }
+#pragma unroll
+                for (int d = 16; d; d >>= 1) ibases += __shfl_xor_sync(FULL, ibases, d);
+                const bool careful = pos < 1 || pos + gcur - 1 > clen;
+                bool tier1 = !careful && nD == 0 && nrun <= EMIT_MAXRUN && !__any_sync(FULL, ovf);
+                int wtot = 0;
+                if (tier1) {                                           // word offsets of the staged genome runs
+                    __syncwarp();
+                    for (int r0 = 0; r0 < nrun; r0 += 32) {
+                        const int r = r0 + lane; int nwd = 0;
+                        if (r < nrun) { const int64_t g0 = gbase + run_g[r]; nwd = (int)(((g0 + run_ct[r] - 1) >> 4) - (g0 >> 4)) + 2; }
+                        int tot; const int wo = wtot + warp_excl_scan(nwd, lane, tot);
+                        if (r < nrun) run_w[r] = (uint16_t)wo;
+                        wtot += tot;
+                    }
+                    if (wtot > EMIT_GBUF_WORDS) tier1 = false;
+                }
+                if (tier1) {
+                    __syncwarp();
+                    uint32_t* gb = SM.gbuf;
+                    for (int r = 0; r < nrun; r++) {                   // all genome words of the read in flight at once
+                        const int64_t g0 = gbase + run_g[r]; const int nwd = (int)(((g0 + run_ct[r] - 1) >> 4) - (g0 >> 4)) + 2;
+                        const uint32_t* gsrc = P.G.g2 + (g0 >> 4); uint32_t* gdst = gb + run_w[r];
+                        for (int t = lane; t < nwd; t += 32) cp_async4(gdst + t, gsrc + t);
+                    }
+                    cp_async_wait_all();
+                    __syncwarp();
+                    bool bad = false; int total_m = 0;
+                    for (int r = 0; r < nrun; r++) {
+                        const int q = run_q[r], ct = run_ct[r]; const int64_t g0 = gbase + run_g[r]; const uint32_t* gr = gb + run_w[r];
+                        const int gsub = (int)(g0 & 15);
+                        for (int c0 = 0; c0 < ct; c0 += 512) {
+                            const int lo = c0 + 16 * lane; int nb = ct - lo; nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+                            if (nb > 0) {
+                                const int a = q + lo;
+                                const uint32_t* sp = reinterpret_cast<const uint32_t*>(SM.seq) + (a >> 2); const int sh = (a & 3) * 8;
+                                const uint32_t x0 = sp[0], x1 = sp[1], x2 = sp[2], x3 = sp[3], x4 = sp[4];
+                                const int gi = (gsub + lo) >> 4;
+                                const uint32_t gw = __funnelshift_r(gr[gi], gr[gi + 1], ((gsub + lo) & 15) * 2);
+                                uint32_t d0 = (__funnelshift_r(x0, x1, sh) & 0xDFDFDFDFu) ^ lut[gw & 255u];
+                                uint32_t d1 = (__funnelshift_r(x1, x2, sh) & 0xDFDFDFDFu) ^ lut[(gw >> 8) & 255u];
+                                uint32_t d2 = (__funnelshift_r(x2, x3, sh) & 0xDFDFDFDFu) ^ lut[(gw >> 16) & 255u];
+                                uint32_t d3 = (__funnelshift_r(x3, x4, sh) & 0xDFDFDFDFu) ^ lut[gw >> 24];
+                                if (nb < 16) {
+                                    const uint32_t m0 = nb >= 4 ? ~0u : ((1u << (8 * nb)) - 1u);
+                                    const uint32_t m1 = nb >= 8 ? ~0u : (nb <= 4 ? 0u : ((1u << (8 * (nb - 4))) - 1u));
+                                    const uint32_t m2 = nb >= 12 ? ~0u : (nb <= 8 ? 0u : ((1u << (8 * (nb - 8))) - 1u));
+                                    const uint32_t m3 = nb <= 12 ? 0u : ((1u << (8 * (nb - 12))) - 1u);
+                                    d0 &= m0; d1 &= m1; d2 &= m2; d3 &= m3;
+                                }
+                                bad |= (d0 | d1 | d2 | d3) != 0u;
+                            }
+                        }
+                        total_m += ct;
+                    }
+                    if (!__any_sync(FULL, bad)) {                      // every aligned base equals the genome: MD is one number
+                        nm = ibases; len = total_m > 0 ? ndigits((uint32_t)total_m) : 0;
+                        off = O.md_inline + 8 * i;                      // at most 5 digits: the read's inline slot
+                        if (lane == 0) *reinterpret_cast<unsigned long long*>(O.md_pool + off) = dec_word((uint32_t)total_m, len);   // slot is 8-byte aligned
+                        done = true;
+                    }
+                }
+            }
+            if (!done) {
+                if (lane == 0) atomicAdd(O.md_cursor + 1, 1ull);             // statistics: reads that needed the exact NM/MD path
+                if (fast) nmmd_to_pool<true>(P.G, SM.seq, lut, cs, chrom, pos, lane, O.md_cursor, O.md_cap, O.md_pool, O.md_inline + 8 * i, nm, len, off, none);
+                else nmmd_to_pool<false>(P.G, out_seq, lut, cs, chrom, pos, lane, O.md_cursor, O.md_cap, O.md_pool, O.md_inline + 8 * i, nm, len, off, none);
+            }
             st = (st & ~(uint32_t)TC_ST_NMMD_NONE) | TC_ST_NMMD_DEVICE;
             if (none) st |= TC_ST_NMMD_NONE;
             if (lane == 0) { O.nm[i] = nm + nm_extra; O.md_off[i] = off < 0 ? 0 : off; O.md_len[i] = off < 0 ? 0 : len; W.status[i] = st; }
@@ -432,6 +583,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
             if (lane == 0) { O.nm[i] = W.nm_init[i]; O.md_off[i] = off < 0 ? 0 : off; O.md_len[i] = off < 0 ? 0 : len; }
         } else if (lane == 0) { O.nm[i] = 0; O.md_off[i] = 0; O.md_len[i] = 0; }
         __syncwarp();
+        pw = pw_next;
     }
 }
 
@@ -511,7 +663,7 @@ struct Slot {
     int64_t seq_lo_word = 0, seq_hi_word = 0;       // words of B.seq (as uint32) that may be dereferenced
     DevBuf w_status, w_counters, w_md_init_off, w_md_init_len, w_nm_init, w_n_mdtok, w_n_jn, w_mflags,
         w_cig_cap, w_seg_cap, w_te_cap, w_ws_off, w_ws, w_cig_buf, w_n_cig_cur, w_seg_buf, w_n_seg_cur, w_n_te,
-        w_te_cnt, w_nm_extra, w_refresh, w_o_seq, w_o_cig, w_o_te, w_o_jn, w_seq_len, w_plan, init_pool, cursors, scan_tmp;
+        w_te_cnt, w_nm_extra, w_refresh, w_o_seq, w_o_cig, w_o_te, w_o_jn, w_seq_len, w_plan, w_fix_list, init_pool, cursors, scan_tmp;
     WorkDev W;
     DevBuf o_nm, o_md_off, o_md_len, o_md_pool, o_seq, o_cig_op, o_cig_len, o_te, o_jm, o_ji;
     int64_t tot_seq = 0, tot_cig = 0, tot_te = 0, tot_jn = 0, md_used = 0;
@@ -525,7 +677,7 @@ struct Slot {
         DevBuf* d[] = {&b_flag, &b_chrom, &b_pos, &b_tags, &b_seq_off, &b_seq, &b_cig_off, &b_cig_op, &b_cig_len, &b_md_off, &b_md, &b_ji_off, &b_ji,
                        &w_status, &w_counters, &w_md_init_off, &w_md_init_len, &w_nm_init, &w_n_mdtok, &w_n_jn, &w_mflags, &w_cig_cap, &w_seg_cap,
                        &w_te_cap, &w_ws_off, &w_ws, &w_cig_buf, &w_n_cig_cur, &w_seg_buf, &w_n_seg_cur, &w_n_te, &w_te_cnt, &w_nm_extra, &w_refresh,
-                       &w_o_seq, &w_o_cig, &w_o_te, &w_o_jn, &w_seq_len, &w_plan, &init_pool, &cursors, &scan_tmp,
+                       &w_o_seq, &w_o_cig, &w_o_te, &w_o_jn, &w_seq_len, &w_plan, &w_fix_list, &init_pool, &cursors, &scan_tmp,
                        &o_nm, &o_md_off, &o_md_len, &o_md_pool, &o_seq, &o_cig_op, &o_cig_len, &o_te, &o_jm, &o_ji};
         for (DevBuf* b : d) b->release();
         h_tot.release();
@@ -822,7 +974,7 @@ static Params make_params(tc_ctx* ctx, Slot& S) {
 
 static OutDev make_out(Slot& S, unsigned long long* cur, int64_t md_cap) {
     OutDev O; O.nm = (int32_t*)S.o_nm.p; O.md_off = (int64_t*)S.o_md_off.p; O.md_len = (int32_t*)S.o_md_len.p;
-    O.md_pool = (uint8_t*)S.o_md_pool.p - S.base_md; O.md_cursor = cur; O.md_cap = S.base_md + md_cap;
+    O.md_pool = (uint8_t*)S.o_md_pool.p - S.base_md; O.md_cursor = cur; O.md_cap = S.base_md + md_cap; O.md_inline = S.base_md;
     O.seq = (uint8_t*)S.o_seq.p - S.base_seq; O.cig_op = (uint8_t*)S.o_cig_op.p - S.base_cig; O.cig_len = (int32_t*)S.o_cig_len.p - S.base_cig;
     O.te = (tc_te*)S.o_te.p - S.base_te; O.jm = (int8_t*)S.o_jm.p - S.base_jn; O.ji = (int32_t*)S.o_ji.p - 2 * S.base_jn;
     return O;
@@ -913,13 +1065,17 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
     else {
         k_plan<<<gb, TPB, 0, st>>>(P); ctx->tm.launches++; CK(cudaGetLastError());
         if (timed) CK(cudaEventRecord(ctx->ev[5], st));
-        k_junction<<<gb, TPB, 0, st>>>(P); ctx->tm.launches++; CK(cudaGetLastError());
+        CK(S.w_fix_list.ensure((size_t)(n + 1) * 4));
+        if (be_zero(ctx, st, cur + 2, 8)) return TC_E_CUDA;
+        k_jn_init<<<gb, TPB, 0, st>>>(P, (int32_t*)S.w_fix_list.p, (unsigned*)(cur + 2)); ctx->tm.launches++; CK(cudaGetLastError());
+        k_jn_fix<<<gb, TPB, 0, st>>>(P, (const int32_t*)S.w_fix_list.p, (const unsigned*)(cur + 2)); ctx->tm.launches++; CK(cudaGetLastError());
         if (timed) CK(cudaEventRecord(ctx->ev[6], st));
         k_sizes<<<gb, TPB, 0, st>>>(P); ctx->tm.launches++; CK(cudaGetLastError());
     }
     int64_t* sc[4] = {S.W.o_seq, S.W.o_cig, S.W.o_te, S.W.o_jn};
     const int64_t bases[4] = {S.base_seq, S.base_cig, S.base_te, S.base_jn};
     for (int k = 0; k < 4; k++) { if (be_zero(ctx, st, sc[k] + n, 8) || be_scan(ctx, st, S.scan_tmp, sc[k], n + 1, bases[k]) || be_read_i64(ctx, st, sc[k] + n, tot + 1 + k)) return TC_E_CUDA; }
+    k_pack<<<gb, TPB, 0, st>>>(P); ctx->tm.launches++; CK(cudaGetLastError());
     if (be_sync(ctx, st)) return TC_E_CUDA;
     S.tot_seq = tot[1] - bases[0]; S.tot_cig = tot[2] - bases[1]; S.tot_te = tot[3] - bases[2]; S.tot_jn = tot[4] - bases[3];
     CK(S.o_seq.ensure((size_t)S.tot_seq + 64)); CK(S.o_cig_op.ensure((size_t)S.tot_cig + 64)); CK(S.o_cig_len.ensure((size_t)S.tot_cig * 4 + 64));
@@ -927,17 +1083,18 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
     CK(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMIT_SMEM_BYTES));
     int occ = 1; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_emit, WARPS_PER_BLOCK * 32, EMIT_SMEM_BYTES));
     int ge = (int)(wb < (int64_t)nsm * occ ? wb : (int64_t)nsm * occ);
-    int64_t md_cap = S.o_md_pool.cap > 0 ? (int64_t)S.o_md_pool.cap : (64 * n + 8 * S.n_cig + (1 << 20));
+    int64_t md_cap = S.o_md_pool.cap > (size_t)(8 * n + (1 << 20)) ? (int64_t)S.o_md_pool.cap : (72 * n + 8 * S.n_cig + (1 << 20));
     if (timed) CK(cudaEventRecord(ctx->ev[7], st));
     for (int attempt = 0;; attempt++) {
         CK(S.o_md_pool.ensure((size_t)md_cap)); md_cap = (int64_t)S.o_md_pool.cap;
-        k_set_u64<<<1, 1, 0, st>>>(cur, (unsigned long long)S.base_md);
+        k_set_u64<<<1, 1, 0, st>>>(cur + 1, 0ull);
+        k_set_u64<<<1, 1, 0, st>>>(cur, (unsigned long long)(S.base_md + 8 * n));      // the pool starts behind the inline slots
         OutDev O = make_out(S, cur, md_cap);
         k_emit<<<ge, WARPS_PER_BLOCK * 32, EMIT_SMEM_BYTES, st>>>(P, O, dry, S.seq_lo_word, S.seq_hi_word); ctx->tm.launches += 2;
         CK(cudaGetLastError());
         if (timed && attempt == 0) CK(cudaEventRecord(ctx->ev[8], st));
-        if (be_read_i64(ctx, st, (const int64_t*)cur, tot) || be_sync(ctx, st)) return TC_E_CUDA;
-        if (tot[0] - S.base_md <= md_cap) { S.md_used = tot[0] - S.base_md; break; }
+        if (be_read_i64(ctx, st, (const int64_t*)cur, tot) || be_read_i64(ctx, st, (const int64_t*)cur + 1, tot + 6) || be_sync(ctx, st)) return TC_E_CUDA;
+        if (tot[0] - S.base_md <= md_cap) { S.md_used = tot[0] - S.base_md; ctx->tm.exact_nmmd_reads += tot[6]; break; }
         if (attempt >= 2) { ctx->err = "MD pool overflow"; return TC_E_CUDA; }
         md_cap = tot[0] - S.base_md + 1024; ctx->tm.md_pool_retries++;
     }
@@ -1055,7 +1212,7 @@ int tc_batch_run(tc_ctx* ctx, int dry) {
 #ifndef TC_HOSTSIM
     CK(cudaSetDevice(ctx->device));
 #endif
-    ctx->tm.launches = 0; ctx->tm.md_pool_retries = 0;
+    ctx->tm.launches = 0; ctx->tm.md_pool_retries = 0; ctx->tm.exact_nmmd_reads = 0;
     ctx->tm.kernels_ms = ctx->tm.k_nmmd_init_ms = ctx->tm.k_measure_ms = ctx->tm.k_plan_ms = ctx->tm.k_junction_ms = ctx->tm.k_emit_ms = 0.f;
     reset_bases(ctx->slot[0]);
     int rc = slot_run(ctx, ctx->slot[0], dry, main_stream(ctx), true);
@@ -1099,7 +1256,7 @@ static int run_all(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out, int dr
     const int64_t CH = ctx->chunk_reads;
     if (CH > 0 && n > CH + CH / 2) {
         CK(cudaSetDevice(ctx->device));
-        ctx->tm.h2d_bytes = ctx->tm.d2h_bytes = 0; ctx->tm.launches = 0; ctx->tm.md_pool_retries = 0;
+        ctx->tm.h2d_bytes = ctx->tm.d2h_bytes = 0; ctx->tm.launches = 0; ctx->tm.md_pool_retries = 0; ctx->tm.exact_nmmd_reads = 0;
         ctx->tm.kernels_ms = ctx->tm.k_nmmd_init_ms = ctx->tm.k_measure_ms = ctx->tm.k_plan_ms = ctx->tm.k_junction_ms = ctx->tm.k_emit_ms = 0.f;
         ctx->n = n; ctx->ran = false;
         const int64_t nchunk = (n + CH - 1) / CH;

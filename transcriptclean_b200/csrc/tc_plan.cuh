@@ -55,9 +55,13 @@ struct BatchDev {
     const int64_t* ji_off; const int32_t* ji;
 };
 
-// everything tc_emit needs to know about a read, packed by sizes_read (one 64-byte row)
-struct EmitPlan { int32_t w[16]; };
-enum { EP_FLAGS, EP_NCIG, EP_NSEG, EP_NTE, EP_TEMM, EP_TEINS, EP_TEDEL, EP_NJN, EP_OUTLEN, EP_NMEXTRA, EP_CIGCAP, EP_SEGCAP, EP_TECAP };
+// everything tc_emit needs to know about a read: one 128-byte row, one word per lane.
+// Words 0-15 are written by sizes_read, 16-31 by pack_read once the output offsets are scanned.
+struct alignas(16) EmitPlan { int32_t w[32]; };
+enum { EP_FLAGS, EP_NCIG, EP_NSEG, EP_NTE, EP_TEMM, EP_TEINS, EP_TEDEL, EP_NJN, EP_OUTLEN, EP_NMEXTRA, EP_CIGCAP, EP_SEGCAP, EP_TECAP,
+       EP_STATUS, EP_CHROM, EP_POS,
+       EP_WS_LO = 16, EP_WS_HI, EP_OSEQ_LO, EP_OSEQ_HI, EP_OCIG_LO, EP_OCIG_HI, EP_OTE_LO, EP_OTE_HI, EP_OJN_LO, EP_OJN_HI,
+       EP_INB_LO, EP_INB_HI, EP_LQ, EP_CIG0_LO, EP_CIG0_HI };
 // EP_FLAGS: bit0 refresh, bits 2-3 cig_buf+1, bits 4-5 seg_buf+1
 
 // per-read state (structure of arrays) + workspace
@@ -112,8 +116,8 @@ TC_HD int64_t ws_need_units(int cig_cap, int seg_cap, int te_cap, int n_jn) {
 TC_HD WsView ws_view(const WorkDev& W, int64_t i) {
     WsView v; u64* p = W.ws + W.ws_off[i];
     int cc = W.cig_cap[i], sc = W.seg_cap[i], tc = W.te_cap[i];
+    for (int k = 0; k < 3; k++) { v.seg[k] = p; p += sc; }      // segment lists first: tc_emit prefetches them
     for (int k = 0; k < 3; k++) { v.cig[k] = p; p += cc; }
-    for (int k = 0; k < 3; k++) { v.seg[k] = p; p += sc; }
     v.te = (tc_te*)p; p += 2ll * tc;
     v.jn = (int32_t*)p;
     return v;
@@ -618,10 +622,12 @@ TC_HD bool fix_side(const Params& P, int chrom, int k, int side, int d, int32_t*
     return newlen == cig_query_len(S.cig, S.nc);                      // TC.py:1476-1477
 }
 
-TC_HD void junction_read(const Params& P, int64_t i) {
+// Transcript.__init__: junction objects, motif codes, canonical / annotated flags (tr.py:56-70, sj.py:8-68).
+// Returns true when cleanNoncanonical has work to do for this read.
+TC_HD bool junction_init_read(const Params& P, int64_t i) {
     const BatchDev& B = P.B; const WorkDev& W = P.W; const tc_options& O = P.O;
     uint32_t st = W.status[i];
-    if ((st & TC_ST_CLASS_MASK) != 0) return;
+    if ((st & TC_ST_CLASS_MASK) != 0) return false;
     const int chrom = B.chrom[i]; const int strand = (B.flag[i] == 16) ? 1 : 0;     // tr.py:51-53
     const int nj = W.n_jn[i]; const uint8_t tags = B.tags[i];
     WsView v = ws_view(W, i); int32_t* J = v.jn;
@@ -649,12 +655,27 @@ TC_HD void junction_read(const Params& P, int64_t i) {
     }
     if (!(tags & TAG_JM)) st |= TC_ST_JM_DEVICE | TC_ST_JI_DEVICE;     // tr.py:69-70
     else if (!(tags & TAG_JI)) st |= TC_ST_JI_DEVICE;                  // tr.py:56-57
-    // ---- cleanNoncanonical (TC.py:1186-1231)
     int32_t* C = W.counters + 10 * i;
     const bool run = !(st & TC_ST_FALLBACK) && O.correct_sjs && P.sj_enabled;
-    if (run) {
-        C[TC_C_COR_SJ] = 0; C[TC_C_UNC_SJ] = 0;
-        if (!canon) {
+    if (run) { C[TC_C_COR_SJ] = 0; C[TC_C_UNC_SJ] = 0; }                // TC.py:1192-1193
+    if (canon) st |= TC_ST_CANONICAL;
+    if (annot) st |= TC_ST_ALL_ANNOT;
+    W.status[i] = st;
+    return run && !canon;
+}
+
+// cleanNoncanonical (TC.py:1186-1231) for a read whose junction objects exist and that is not canonical.
+TC_HD void junction_fix_read(const Params& P, int64_t i) {
+    const BatchDev& B = P.B; const WorkDev& W = P.W; const tc_options& O = P.O;
+    uint32_t st = W.status[i];
+    const int chrom = B.chrom[i]; const int strand = (B.flag[i] == 16) ? 1 : 0;
+    const int nj = W.n_jn[i];
+    WsView v = ws_view(W, i); int32_t* J = v.jn;
+    int32_t* C = W.counters + 10 * i;
+    bool canon = false, annot = (st & TC_ST_ALL_ANNOT) != 0;
+    st &= ~(uint32_t)(TC_ST_CANONICAL | TC_ST_ALL_ANNOT);
+    {
+        {
             int nte = W.n_te[i]; int cJ = 0, uJ = 0;
             const int64_t Lq = B.seq_off[i + 1] - B.seq_off[i];
             // committed transcript state
@@ -742,11 +763,13 @@ TC_HD void junction_read(const Params& P, int64_t i) {
     W.status[i] = st;
 }
 
+TC_HD void junction_read(const Params& P, int64_t i) { if (junction_init_read(P, i)) junction_fix_read(P, i); }
+
 // exact output sizes of a read (input to the four exclusive scans that place tc_emit's output)
 TC_HD void sizes_read(const Params& P, int64_t i) {
     const BatchDev& B = P.B; const WorkDev& W = P.W;
     uint32_t st = W.status[i];
-    if ((st & TC_ST_CLASS_MASK) != 0) { W.o_seq[i] = W.o_cig[i] = W.o_te[i] = W.o_jn[i] = 0; W.seq_len_out[i] = 0; return; }
+    if ((st & TC_ST_CLASS_MASK) != 0) { W.o_seq[i] = W.o_cig[i] = W.o_te[i] = W.o_jn[i] = 0; W.seq_len_out[i] = 0; W.plan[i].w[EP_STATUS] = (int32_t)st; return; }
     int64_t sl;
     if (W.seg_buf[i] < 0) sl = B.seq_off[i + 1] - B.seq_off[i];
     else { WsView v = ws_view(W, i); sl = 0; const u64* s = v.seg[W.seg_buf[i]]; for (int k = 0; k < W.n_seg_cur[i]; k++) sl += seg_len(s[k]); }
@@ -757,13 +780,20 @@ TC_HD void sizes_read(const Params& P, int64_t i) {
     W.o_te[i] = W.n_te[i];
     W.o_jn[i] = W.n_jn[i];
     EmitPlan ep;
+    for (int k = 0; k < 16; k++) ep.w[k] = 0;
     ep.w[EP_FLAGS] = (W.refresh[i] ? 1 : 0) | ((W.cig_buf[i] + 1) << 2) | ((W.seg_buf[i] + 1) << 4);
     ep.w[EP_NCIG] = ncig; ep.w[EP_NSEG] = W.n_seg_cur[i]; ep.w[EP_NTE] = W.n_te[i];
     ep.w[EP_TEMM] = W.te_cnt[3 * i]; ep.w[EP_TEINS] = W.te_cnt[3 * i + 1]; ep.w[EP_TEDEL] = W.te_cnt[3 * i + 2];
     ep.w[EP_NJN] = W.n_jn[i]; ep.w[EP_OUTLEN] = (int32_t)sl; ep.w[EP_NMEXTRA] = W.nm_extra[i];
     ep.w[EP_CIGCAP] = W.cig_cap[i]; ep.w[EP_SEGCAP] = W.seg_cap[i]; ep.w[EP_TECAP] = W.te_cap[i];
-    ep.w[13] = ep.w[14] = ep.w[15] = 0;
-    W.plan[i] = ep;
+    ep.w[EP_STATUS] = (int32_t)st; ep.w[EP_CHROM] = B.chrom[i]; ep.w[EP_POS] = B.pos[i];
+#ifndef TC_HOSTSIM
+    int4* dst = reinterpret_cast<int4*>(W.plan[i].w);
+    const int4* src = reinterpret_cast<const int4*>(ep.w);
+    for (int k = 0; k < 4; k++) dst[k] = src[k];
+#else
+    for (int k = 0; k < 16; k++) W.plan[i].w[k] = ep.w[k];
+#endif
 }
 
 // ---------------------------------------------------------------------------------- dry run
@@ -774,7 +804,24 @@ TC_HD void dry_sizes(const Params& P, int64_t i) {
     EmitPlan ep;
     for (int k = 0; k < 16; k++) ep.w[k] = 0;
     ep.w[EP_NTE] = W.n_te[i]; ep.w[EP_CIGCAP] = W.cig_cap[i]; ep.w[EP_SEGCAP] = W.seg_cap[i]; ep.w[EP_TECAP] = W.te_cap[i];
-    W.plan[i] = ep;
+    ep.w[EP_STATUS] = (int32_t)W.status[i];
+    for (int k = 0; k < 16; k++) W.plan[i].w[k] = ep.w[k];
+}
+
+// second half of the plan row: offsets that exist only after the exclusive scans
+TC_HD void pack_read(const Params& P, int64_t i) {
+    const BatchDev& B = P.B; const WorkDev& W = P.W;
+    int32_t* w = W.plan[i].w;
+    const int64_t ws = W.ws_off[i], os = W.o_seq[i], oc = W.o_cig[i], ot = W.o_te[i], oj = W.o_jn[i], ib = B.seq_off[i], c0 = B.cig_off[i];
+    w[EP_WS_LO] = (int32_t)(uint32_t)ws; w[EP_WS_HI] = (int32_t)(ws >> 32);
+    w[EP_OSEQ_LO] = (int32_t)(uint32_t)os; w[EP_OSEQ_HI] = (int32_t)(os >> 32);
+    w[EP_OCIG_LO] = (int32_t)(uint32_t)oc; w[EP_OCIG_HI] = (int32_t)(oc >> 32);
+    w[EP_OTE_LO] = (int32_t)(uint32_t)ot; w[EP_OTE_HI] = (int32_t)(ot >> 32);
+    w[EP_OJN_LO] = (int32_t)(uint32_t)oj; w[EP_OJN_HI] = (int32_t)(oj >> 32);
+    w[EP_INB_LO] = (int32_t)(uint32_t)ib; w[EP_INB_HI] = (int32_t)(ib >> 32);
+    w[EP_LQ] = (int32_t)(B.seq_off[i + 1] - ib);
+    w[EP_CIG0_LO] = (int32_t)(uint32_t)c0; w[EP_CIG0_HI] = (int32_t)(c0 >> 32);
+    w[31] = 0;
 }
 
 // dryRun (TC.py:1615-1678): positional inventory of X / D / I from the MD x CIGAR merge.
