@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=3000)
     ap.add_argument("--ref-reads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--text-sample", type=int, default=100000, help="reads for the SAM-text path measurement (0 = skip)")
     ap.add_argument("--debug-mask", type=int, default=0, help="profiling aid: skip phases of k_emit (results invalid)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -300,6 +301,19 @@ def main():
                      "algorithmic_bytes_per_launch": dom_bytes},
         "clocks": clocks,
     }
+    if world == 1 and rank == 0 and args.text_sample > 0:
+        # SAM text in -> four output texts (C++ host parse / render + GPU), in memory
+        from transcriptclean_b200 import api
+        ns = min(args.text_sample, args.reads)
+        text = ("\n".join(w.sam_lines(cols, nm, 0, ns)) + "\n").encode()
+        refs = api.Struct(); refs.genome = gi; refs.engine = eng
+        api.correct_sam_text(text, api.Struct(), refs)
+        t0 = time.perf_counter()
+        _, txt = api.correct_sam_text(text, api.Struct(), refs)
+        t1 = time.perf_counter()
+        line["sam_text_path"] = {"value": ns / (t1 - t0), "unit": "reads/s", "in_bytes": len(text),
+                                 "out_bytes": sum(len(v) for v in txt.values()),
+                                 "sample": "%d reads as SAM text -> clean SAM + FASTA + log + TE.log texts, host threads=%d" % (ns, min(32, os.cpu_count() or 1))}
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         ns = min(args.cpu_sample, args.reads)
         lines = w.sam_lines(cols, nm, 0, ns)

@@ -173,6 +173,27 @@ int tc_batch_download(tc_ctx* ctx, tc_batch_out* out);
 
 int tc_get_timing(tc_ctx* ctx, tc_timing* t);
 
+/* ---- host side: SAM text <-> columns (csrc/tc_host.cpp, multi-threaded C++; no GPU involved) ----
+ * tc_sam_parse replaces split_SAM (TranscriptClean.py:519-541) + the field / tag handling of
+ * Transcript.__init__ (transcript.py:10-72): header lines are set aside, alignment lines become a
+ * tc_batch_in.  `text` must stay alive as long as the tc_sam (fields are referenced, not copied).
+ * Returns NULL and fills `err` for records the reference would crash on (see sam.py). */
+typedef struct tc_sam tc_sam;
+tc_sam* tc_sam_parse(const char* text, int64_t len, int32_t n_chrom, const char* const* chrom_names,
+                     const int64_t* chrom_len, int32_t n_threads, char* err, int64_t err_cap);
+void tc_sam_free(tc_sam* s);
+/* distinct RNAMEs of the alignment lines, newline-joined (split_SAM's chromosome set, TC.py:535); free with tc_free */
+char* tc_sam_rnames(const char* text, int64_t len, int64_t* out_len);
+void tc_free(void* p);
+int64_t tc_sam_n_reads(const tc_sam* s);
+int64_t tc_sam_header(const tc_sam* s, const char** text);      /* '@' lines, newline-terminated */
+void tc_sam_batch(const tc_sam* s, tc_batch_in* out);            /* view of the parsed columns */
+/* printableSAM / printableFa (transcript.py:244-268), create_log_string (TC.py:1591-1604), the TE
+ * rows and the emission rules of batch_correct (TC.py:373-385).  The four texts are owned by `s`. */
+int tc_sam_render(tc_sam* s, const tc_batch_out* res, int32_t primary_only, int32_t canon_only, int32_t dry,
+                  int32_t n_threads, const char** sam, int64_t* sam_len, const char** fa, int64_t* fa_len,
+                  const char** log, int64_t* log_len, const char** te, int64_t* te_len, char* err, int64_t err_cap);
+
 #ifdef __cplusplus
 }
 #endif

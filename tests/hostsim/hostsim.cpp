@@ -5,3 +5,4 @@
 // the oracle on machines without a GPU.  GPU parity is established separately (-m gpu tests).
 #define TC_HOSTSIM 1
 #include "../../transcriptclean_b200/csrc/tc_b200.cu"
+#include "../../transcriptclean_b200/csrc/tc_host.cpp"

@@ -98,3 +98,18 @@ def test_large_batch_properties(setup):
     per = np.where(np.diff(a.cig_off) > 0, per, 0)
     assert np.array_equal(per[primary], a.seq_len[primary].astype(np.int64))
     assert int((a.status & (E.ST_ERR_INTRON | E.ST_ERR_MERGE)).sum()) == 0
+
+
+def test_sam_text_fast_path_on_gpu(setup):
+    """SAM text in, four texts out: C++ host parse/render around the CUDA path equals the oracle."""
+    from transcriptclean_b200 import api
+    from transcriptclean_b200.tables import build_sj_tables
+    w, gi, sjf, eng, d = setup
+    cols, nm = w.reads("ont", 2500, seed_offset=5)
+    lines = w.sam_lines(cols, nm, 0, 2500)
+    refs = api.make_refs(gi, build_sj_tables(sjf, {w.chrom}, gi.index), None, engine=eng)
+    header, got = api.correct_sam_text(("@HD\tVN:1.0\n" + "\n".join(lines) + "\n").encode(), api.Struct(canonOnly=True), refs)
+    want = pipeline.oracle_texts({w.chrom: w.genome.tobytes().decode()}, lines, sjf, None, {"canonOnly": True})
+    assert header == "@HD\tVN:1.0\n"
+    diff = pipeline.first_diff({k: v.decode() for k, v in got.items()}, want)
+    assert diff is None, diff

@@ -90,6 +90,19 @@ def correct_batch_text(sam_transcripts, options, refs):
                                warn=print)
 
 
+def correct_sam_text(text, options, refs, dry=False):
+    """Fast path for whole SAM texts (bytes): parsing and rendering in the library's C++ host code,
+    correction on the GPU.  Returns (header str, {"sam","fa","log","te"} as bytes)."""
+    _set_engine_options(options, refs)
+    st = refs.engine.parse_sam(text, refs.genome)
+    try:
+        raw = refs.engine.raw_dryrun(st.batch) if dry else refs.engine.raw_correct(st.batch)
+        out = st.render(raw, bool(_opt(options, "primaryOnly", False)), bool(_opt(options, "canonOnly", False)), dry)
+        return st.header, out
+    finally:
+        st.close()
+
+
 def batch_correct(sam_transcripts, options, refs, outfiles, buffer_size=100):
     """TC.py:350-403.  `buffer_size` only staggers disk writes in the reference; the whole list
     is one device batch here."""

@@ -11,7 +11,6 @@ from optparse import OptionParser
 
 from . import api
 from .genome import GenomeImage
-from .shard import correct_sharded_threads
 
 LOG_HEADER = "\t".join(["TranscriptID", "Mapping", "corrected_deletions", "uncorrected_deletions", "variant_deletions",
                         "corrected_insertions", "uncorrected_insertions", "variant_insertions", "corrected_mismatches",
@@ -109,18 +108,17 @@ def validate_chroms(genome, vcf_file, sam_chroms):
 
 
 def write_outputs(options, header, texts):
-    """combine_outputs (TC.py:604-663): headers + bodies; no SAM / FASTA in --dryRun."""
+    """combine_outputs (TC.py:604-663): headers + bodies; no SAM / FASTA in --dryRun.
+    header: the '@' lines, newline-terminated; texts: bytes."""
     pre = options.outprefix
-    with open(pre + "_clean.log", "w") as f:
-        f.write(LOG_HEADER + texts["log"])
-    with open(pre + "_clean.TE.log", "w") as f:
-        f.write(TE_HEADER + texts["te"])
+    with open(pre + "_clean.log", "wb") as f:
+        f.write(LOG_HEADER.encode() + texts["log"])
+    with open(pre + "_clean.TE.log", "wb") as f:
+        f.write(TE_HEADER.encode() + texts["te"])
     if not options.dryRun:
-        with open(pre + "_clean.sam", "w") as f:
-            for line in header:
-                f.write(line + "\n")
-            f.write(texts["sam"])
-        with open(pre + "_clean.fa", "w") as f:
+        with open(pre + "_clean.sam", "wb") as f:
+            f.write(header.encode() + texts["sam"])
+        with open(pre + "_clean.fa", "wb") as f:
             f.write(texts["fa"])
 
 
@@ -132,23 +130,59 @@ def n_gpus_available():
         return 1
 
 
+def split_text(text, n):
+    """Cuts a SAM text (bytes) into n pieces at line boundaries, balanced by bytes.  Any
+    contiguous cut reproduces the single-worker output order when the pieces are concatenated."""
+    cuts = [0]
+    for k in range(1, n):
+        p = text.find(b"\n", len(text) * k // n)
+        cuts.append(len(text) if p < 0 else p + 1)
+    cuts.append(len(text))
+    for k in range(1, len(cuts)):
+        cuts[k] = max(cuts[k], cuts[k - 1])
+    return [text[cuts[k]:cuts[k + 1]] for k in range(n)]
+
+
 def run(options, engines=None):
-    """engines: optional list of pre-built Engine objects (tests inject CPU stand-ins here)."""
-    header, chroms, lines = split_sam(options.sam)
+    """engines: optional list of pre-built Engine objects (tests inject CPU stand-ins here).
+    SAM parsing and text rendering run in the library's multi-threaded C++ host code
+    (csrc/tc_host.cpp); correction runs on the GPU(s); one host thread per GPU."""
+    import threading
+    from . import engine as E
+    with open(options.sam, "rb") as f:
+        text = f.read()
     print("Reading genome ..............................")
     genome = GenomeImage.from_fasta(options.refGenome)
+    if engines is None:
+        n = max(1, min(int(options.n_threads), max(1, n_gpus_available())))
+        engines = [E.Engine(d) for d in range(n)]
+    chroms = E.sam_rnames(engines[0]._lib, text)
     validate_chroms(genome, options.variantFile, chroms)
     os.makedirs(options.tmp_dir, exist_ok=True)          # kept for interface compatibility (--tmpDir / --deleteTmp)
-    if engines is None:
-        from .engine import Engine
-        n = max(1, min(int(options.n_threads), max(1, n_gpus_available())))
-        engines = [Engine(d) for d in range(n)]
-    refs_list = [api.prep_refs(options, lines, header, engine=e, genome=genome) for e in engines]
-    if options.dryRun:
-        worker = lambda part, opts, refs: api.dry_run_text(part, refs)
-    else:
-        worker = lambda part, opts, refs: api.correct_batch_text(part, opts, refs)
-    texts = correct_sharded_threads(lines, options, refs_list, worker)
+
+    class _ChromLines:                                    # prep_refs only needs the chromosome of each line
+        def __iter__(self):
+            return iter("x\tx\t" + c for c in chroms)
+
+    refs_list = [api.prep_refs(options, _ChromLines(), None, engine=e, genome=genome) for e in engines]
+    parts = split_text(text, len(engines))
+    results, errs = [None] * len(parts), []
+
+    def work(k):
+        try:
+            results[k] = api.correct_sam_text(parts[k], options, refs_list[k], dry=bool(options.dryRun))
+        except Exception as e:
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(len(parts))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errs:
+        raise errs[0]
+    header = "".join(r[0] for r in results)
+    texts = {k: b"".join(r[1][k] for r in results) for k in ("sam", "fa", "log", "te")}
     write_outputs(options, header, texts)
     if options.delete_tmp:
         import shutil

@@ -1,0 +1,382 @@
+// tc_host.cpp - host-side SAM ingest and text rendering (C++, multi-threaded).
+//
+// the callers either side of the correction path.  Replaces, with identical
+// results, the Python-level work of the reference around correct_transcript():
+//   split_SAM                      TranscriptClean.py:519-541   header / alignment lines
+//   init_log_info                  TranscriptClean.py:1558-1588 mapping class
+//   Transcript.__init__            transcript.py:10-72          field and tag handling
+//   printableSAM / printableFa     transcript.py:244-268, reverseComplement 541-576
+//   create_log_string              TranscriptClean.py:1591-1604
+//   TE rows                        TC.py:911-936, 1017-1046, 1119-1134, 1227-1228, 1650-1668
+//   batch_correct emission rules   TC.py:373-385 (Q19)
+// transcriptclean_b200/sam.py and render.py are the same logic in Python; tests compare the two.
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/tc_b200.h"
+
+namespace {
+
+struct Span { int64_t s; int32_t n; };
+
+struct Part {                       // what one parser thread produces
+    std::vector<int32_t> flag, chrom, pos; std::vector<uint8_t> tags, cls;
+    std::vector<int64_t> seq_len, cig_n, md_n, ji_n;
+    std::vector<uint8_t> seq, cig_op, md; std::vector<int32_t> cig_len, ji;
+    std::vector<Span> line, f[9], cigar, tg[4];
+    std::vector<int64_t> other_off; std::vector<Span> other;
+    std::vector<Span> header;
+    std::string err;
+};
+
+inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
+
+// Python int(): optional surrounding whitespace, optional sign, digits (underscores not supported)
+bool py_int(const char* p, int n, int64_t& out) {
+    int a = 0, b = n;
+    while (a < b && is_ws(p[a])) a++;
+    while (b > a && is_ws(p[b - 1])) b--;
+    if (a >= b) return false;
+    bool neg = false;
+    if (p[a] == '+' || p[a] == '-') { neg = p[a] == '-'; a++; }
+    if (a >= b) return false;
+    int64_t v = 0;
+    for (int k = a; k < b; k++) { if (p[k] < '0' || p[k] > '9') return false; v = v * 10 + (p[k] - '0'); if (v > (1ll << 40)) return false; }
+    out = neg ? -v : v;
+    return true;
+}
+
+}  // namespace
+
+struct tc_sam {
+    const char* text = nullptr; int64_t len = 0;
+    int64_t n = 0;
+    std::vector<int32_t> flag, chrom, pos; std::vector<uint8_t> tags, cls;
+    std::vector<int64_t> seq_off, cig_off, md_off, ji_off;
+    std::vector<uint8_t> seq, cig_op, md; std::vector<int32_t> cig_len, ji;
+    std::vector<Span> line, f[9], cigar, tg[4];
+    std::vector<int64_t> other_off; std::vector<Span> other;
+    std::string header;
+    std::string out_sam, out_fa, out_log, out_te;
+};
+
+namespace {
+
+void set_err(char* err, int64_t cap, const std::string& m) {
+    if (err && cap > 0) { snprintf(err, (size_t)cap, "%s", m.c_str()); }
+}
+
+void parse_range(const char* T, int64_t a, int64_t b, const std::unordered_map<std::string, int>& cmap, const int64_t* clen, Part& P) {
+    int64_t p = a;
+    std::vector<Span> fld;
+    while (p < b && P.err.empty()) {
+        int64_t e = p;
+        while (e < b && T[e] != '\n') e++;
+        int64_t s = p, t = e;
+        p = e + 1;
+        while (s < t && is_ws(T[s])) s++;
+        while (t > s && is_ws(T[t - 1])) t--;
+        if (s >= t) continue;
+        if (T[s] == '@') { P.header.push_back({s, (int32_t)(t - s)}); continue; }
+        fld.clear();
+        int64_t q = s;
+        for (int64_t k = s; k <= t; k++) if (k == t || T[k] == '\t') { fld.push_back({q, (int32_t)(k - q)}); q = k + 1; }
+        if (fld.size() < 11) { P.err = "SAM record with fewer than 11 fields: " + std::string(T + s, (size_t)std::min<int64_t>(80, t - s)); break; }
+        std::string qname(T + fld[0].s, (size_t)fld[0].n);
+        int64_t fl;
+        if (!py_int(T + fld[1].s, fld[1].n, fl)) { P.err = "read " + qname + ": FLAG is not an integer"; break; }
+        const bool star = fld[2].n == 1 && T[fld[2].s] == '*';
+        const int cls = (star || fl == 4) ? 1 : (fl > 16 ? 2 : 0);
+        P.flag.push_back((int32_t)fl); P.cls.push_back((uint8_t)cls); P.line.push_back({s, (int32_t)(t - s)});
+        for (int k = 0; k < 9; k++) P.f[k].push_back(fld[k]);
+        if (cls != 0) {
+            P.chrom.push_back(cls == 1 ? -1 : 0); P.pos.push_back(0); P.tags.push_back(0);
+            P.seq_len.push_back(0); P.cig_n.push_back(0); P.md_n.push_back(0); P.ji_n.push_back(0);
+            P.cigar.push_back({0, 0}); for (int k = 0; k < 4; k++) P.tg[k].push_back({0, 0});
+            P.other_off.push_back((int64_t)P.other.size());
+            continue;
+        }
+        auto it = cmap.find(std::string(T + fld[2].s, (size_t)fld[2].n));
+        if (it == cmap.end()) { P.err = "read " + qname + ": chromosome " + std::string(T + fld[2].s, (size_t)fld[2].n) + " is not in the reference genome"; break; }
+        const int c = it->second;
+        int64_t posv;
+        if (!py_int(T + fld[3].s, fld[3].n, posv)) { P.err = "read " + qname + ": POS is not an integer"; break; }
+        // CIGAR: ^(?:[0-9]+[A-Z])+$
+        const char* cg = T + fld[5].s; const int cn = fld[5].n;
+        int64_t qlen = 0, gend = posv; bool okc = cn > 0, hasN = false; int nops = 0;
+        for (int k = 0; k < cn && okc;) {
+            int64_t v = 0; int d = 0;
+            while (k < cn && cg[k] >= '0' && cg[k] <= '9') { v = v * 10 + (cg[k] - '0'); k++; d++; if (v > (1ll << 40)) okc = false; }
+            if (d == 0 || k >= cn || cg[k] < 'A' || cg[k] > 'Z') { okc = false; break; }
+            const char op = cg[k++];
+            if (v < 1) { P.err = "read " + qname + ": zero-length CIGAR operation"; break; }
+            P.cig_op.push_back((uint8_t)op); P.cig_len.push_back((int32_t)v); nops++;
+            if (op == 'M' || op == 'I' || op == 'S') qlen += v;
+            if (op == 'M' || op == 'D' || op == 'N' || op == 'H') gend += v;
+            if (op == 'N') hasN = true;
+        }
+        if (!P.err.empty()) break;
+        if (!okc) { P.err = "read " + qname + ": unsupported CIGAR '" + std::string(cg, (size_t)std::min(cn, 40)) + "'"; break; }
+        if (qlen != fld[9].n) { P.err = "read " + qname + ": SEQ length " + std::to_string(fld[9].n) + " does not match CIGAR (" + std::to_string(qlen) + ")"; break; }
+        if (posv < 1 || gend - 1 > clen[c]) { P.err = "read " + qname + ": alignment runs off contig " + std::string(T + fld[2].s, (size_t)fld[2].n); break; }
+        Span tg[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+        P.other_off.push_back((int64_t)P.other.size());
+        for (size_t k = 11; k < fld.size(); k++) {
+            const char* x = T + fld[k].s; const int n = fld[k].n;
+            int which = -1;
+            if (n >= 2) {
+                if (x[0] == 'N' && x[1] == 'M') which = 0; else if (x[0] == 'M' && x[1] == 'D') which = 1;
+                else if (x[0] == 'j' && x[1] == 'M') which = 2; else if (x[0] == 'j' && x[1] == 'I') which = 3;
+            }
+            if (which >= 0) tg[which] = fld[k]; else P.other.push_back(fld[k]);
+        }
+        uint8_t tb = 0; int64_t mdn = 0, jin = 0;
+        if (tg[0].n) tb |= 1;
+        if (tg[1].n) {
+            tb |= 2;
+            const char* x = T + tg[1].s; const int n = tg[1].n;
+            int c1 = -1, c2 = -1, c3 = n;
+            for (int k = 0; k < n; k++) if (x[k] == ':') { if (c1 < 0) c1 = k; else if (c2 < 0) c2 = k; else { c3 = k; break; } }
+            if (c2 < 0) { P.err = "read " + qname + ": malformed MD tag"; break; }
+            if (tg[0].n) { P.md.insert(P.md.end(), x + c2 + 1, x + c3); mdn = c3 - c2 - 1; }
+        }
+        if (tg[2].n) tb |= 4;
+        if (tg[3].n) {
+            tb |= 8;
+            if (hasN) {
+                const char* x = T + tg[3].s; const int n = tg[3].n;
+                int lc = -1; for (int k = 0; k < n; k++) if (x[k] == ':') lc = k;
+                int k = lc + 1; int idx = 0; bool bad = false;
+                while (k <= n) {
+                    int e2 = k; while (e2 < n && x[e2] != ',') e2++;
+                    if (idx > 0) {
+                        int64_t v;
+                        if (!py_int(x + k, e2 - k, v)) { P.err = "read " + qname + ": malformed jI tag"; bad = true; break; }
+                        if (v < 2 || v > clen[c]) { P.err = "read " + qname + ": jI tag does not describe intron pairs on the contig"; bad = true; break; }
+                        P.ji.push_back((int32_t)v); jin++;
+                    }
+                    idx++; k = e2 + 1;
+                }
+                if (bad) break;
+                if (jin % 2) { P.err = "read " + qname + ": jI tag does not describe intron pairs on the contig"; break; }
+            }
+        }
+        P.chrom.push_back(c); P.pos.push_back((int32_t)posv); P.tags.push_back(tb);
+        P.seq.insert(P.seq.end(), T + fld[9].s, T + fld[9].s + fld[9].n);
+        P.seq_len.push_back(fld[9].n); P.cig_n.push_back(nops); P.md_n.push_back(mdn); P.ji_n.push_back(jin);
+        P.cigar.push_back(fld[5]); for (int k = 0; k < 4; k++) P.tg[k].push_back(tg[k]);
+    }
+}
+
+template <class T> void append(std::vector<T>& d, const std::vector<T>& s) { d.insert(d.end(), s.begin(), s.end()); }
+
+const char* const CLASS_NAME[3] = {"primary", "unmapped", "non-primary"};
+const char* const TE_TYPE[4] = {"Mismatch", "Insertion", "Deletion", "NC_SJ_boundary"};
+const char* const TE_STATUS[2] = {"Corrected", "Uncorrected"};
+const char* const TE_REASON[6] = {"NA", "VariantMatch", "TooLarge", "TooFarFromAnnotJn", "Other", "DryRun"};
+
+inline void put_int(std::string& o, int64_t v) { char b[24]; int n = snprintf(b, sizeof b, "%lld", (long long)v); o.append(b, (size_t)n); }
+
+struct Comp { uint8_t t[256]; Comp() { for (int k = 0; k < 256; k++) t[k] = (uint8_t)k; const char* a = "ACGTNacgtn*"; const char* b = "TGCANtgcan*"; for (int k = 0; a[k]; k++) t[(uint8_t)a[k]] = (uint8_t)b[k]; } };
+const Comp COMP;
+
+void render_range(const tc_sam* S, const tc_batch_out* R, int64_t a, int64_t b, bool primary_only, bool canon_only, bool dry,
+                  std::string& sam, std::string& fa, std::string& lg, std::string& te) {
+    const char* T = S->text;
+    std::string row, seq;
+    for (int64_t i = a; i < b; i++) {
+        const uint32_t st = R->status[i]; const int cls = (int)(st & TC_ST_CLASS_MASK);
+        // log row: TranscriptID, Mapping, ten counters ("NA" = -1)
+        lg.append(T + S->f[0][i].s, (size_t)S->f[0][i].n); lg.push_back('\t'); lg.append(CLASS_NAME[cls]);
+        for (int k = 0; k < 10; k++) { lg.push_back('\t'); const int32_t c = R->counters[10 * i + k]; if (c < 0) lg.append("NA"); else put_int(lg, c); }
+        lg.push_back('\n');
+        if (cls != 0) {
+            if (!dry && !primary_only && !canon_only) { sam.append(T + S->line[i].s, (size_t)S->line[i].n); sam.push_back('\n'); }
+            continue;
+        }
+        for (int64_t k = R->te_off[i]; k < R->te_off[i + 1]; k++) {
+            const tc_te& r = R->te[k];
+            te.append(T + S->f[0][i].s, (size_t)S->f[0][i].n); te.push_back('\t');
+            te.append(T + S->f[2][i].s, (size_t)S->f[2][i].n); te.push_back('_'); put_int(te, r.a);
+            if (r.type != 0) { te.push_back('_'); put_int(te, r.b); }
+            te.push_back('\t'); te.append(TE_TYPE[r.type]); te.push_back('\t'); put_int(te, r.size); te.push_back('\t');
+            te.append(TE_STATUS[r.status]); te.push_back('\t'); te.append(TE_REASON[r.reason]); te.push_back('\n');
+        }
+        if (dry) continue;
+        if (canon_only && !(st & (TC_ST_CANONICAL | TC_ST_ALL_ANNOT))) continue;
+        // ---- SAM line (printableSAM): empty fields are dropped, the line is stripped
+        row.clear();
+        auto add = [&](const char* p, int64_t n) { if (n > 0) { if (!row.empty()) row.push_back('\t'); row.append(p, (size_t)n); } };
+        auto add_span = [&](const Span& s) { add(T + s.s, s.n); };
+        auto add_num = [&](int64_t v) { if (!row.empty()) row.push_back('\t'); put_int(row, v); };
+        add_span(S->f[0][i]); add_num(S->flag[i]); add_span(S->f[2][i]); add_num(S->pos[i]); add_span(S->f[4][i]);
+        if (st & TC_ST_CIGAR_REWRITTEN) {
+            if (R->cig_off[i + 1] > R->cig_off[i]) {
+                if (!row.empty()) row.push_back('\t');
+                for (int64_t k = R->cig_off[i]; k < R->cig_off[i + 1]; k++) { put_int(row, R->cig_len[k]); row.push_back((char)R->cig_op[k]); }
+            }
+        } else add_span(S->cigar[i]);
+        add_span(S->f[6][i]); add_span(S->f[7][i]); add_span(S->f[8][i]);
+        const uint8_t* sq = R->seq + R->seq_off[i]; const int32_t sl = R->seq_len[i];
+        add((const char*)sq, sl);
+        add("*", 1);
+        for (int64_t k = S->other_off[i]; k < S->other_off[i + 1]; k++) {
+            // otherFields is one tab-joined field: dropped only when the whole join is empty
+            if (k == S->other_off[i]) { bool any = false; for (int64_t m = k; m < S->other_off[i + 1]; m++) any |= S->other[m].n > 0 || m > k; if (!any) break; if (!row.empty()) row.push_back('\t'); }
+            else row.push_back('\t');
+            row.append(T + S->other[k].s, (size_t)S->other[k].n);
+        }
+        if (st & TC_ST_NMMD_DEVICE) {
+            if (!(st & TC_ST_NMMD_NONE)) {
+                if (!row.empty()) row.push_back('\t');
+                row.append("NM:i:"); put_int(row, R->nm[i]); row.append("\tMD:Z:");
+                row.append((const char*)R->md + R->md_off[i], (size_t)R->md_len[i]);
+            }
+        } else { add_span(S->tg[0][i]); add_span(S->tg[1][i]); }
+        const int64_t j0 = R->jn_off[i], j1 = R->jn_off[i + 1];
+        if (st & TC_ST_JM_DEVICE) {
+            if (!row.empty()) row.push_back('\t');
+            row.append("jM:B:c");
+            if (j1 > j0) for (int64_t k = j0; k < j1; k++) { row.push_back(','); put_int(row, R->jm[k]); } else row.append(",-1");
+        } else add_span(S->tg[2][i]);
+        if (st & TC_ST_JI_DEVICE) {
+            if (!row.empty()) row.push_back('\t');
+            row.append("jI:B:i");
+            if (j1 > j0) for (int64_t k = 2 * j0; k < 2 * j1; k++) { row.push_back(','); put_int(row, R->ji[k]); } else row.append(",-1");
+        } else add_span(S->tg[3][i]);
+        size_t x = 0, y = row.size();
+        while (x < y && is_ws(row[x])) x++;
+        while (y > x && is_ws(row[y - 1])) y--;
+        sam.append(row, x, y - x); sam.push_back('\n');
+        // ---- FASTA record (printableFa): reverse complement on the minus strand, 80 columns
+        fa.push_back('>'); fa.append(T + S->f[0][i].s, (size_t)S->f[0][i].n); fa.push_back('\n');
+        if (S->flag[i] == 16) { seq.resize((size_t)sl); for (int32_t k = 0; k < sl; k++) seq[(size_t)k] = (char)COMP.t[sq[sl - 1 - k]]; }
+        const char* sp = S->flag[i] == 16 ? seq.data() : (const char*)sq;
+        for (int32_t k = 0; k < sl; k += 80) { if (k) fa.push_back('\n'); fa.append(sp + k, (size_t)std::min(80, sl - k)); }
+        fa.push_back('\n');
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+tc_sam* tc_sam_parse(const char* text, int64_t len, int32_t n_chrom, const char* const* chrom_names, const int64_t* chrom_len,
+                     int32_t n_threads, char* err, int64_t err_cap) {
+    if (!text || len < 0) { set_err(err, err_cap, "tc_sam_parse: no text"); return nullptr; }
+    std::unordered_map<std::string, int> cmap;
+    for (int k = 0; k < n_chrom; k++) cmap.emplace(chrom_names[k], k);
+    int T = n_threads < 1 ? 1 : n_threads;
+    if (len < (1 << 20)) T = 1;
+    std::vector<int64_t> cut(T + 1, len);
+    cut[0] = 0;
+    for (int k = 1; k < T; k++) { int64_t p = len / T * k; while (p < len && text[p] != '\n') p++; cut[k] = p < len ? p + 1 : len; }
+    for (int k = 1; k <= T; k++) if (cut[k] < cut[k - 1]) cut[k] = cut[k - 1];
+    std::vector<Part> parts((size_t)T);
+    std::vector<std::thread> th;
+    for (int k = 0; k < T; k++) th.emplace_back(parse_range, text, cut[k], cut[k + 1], std::cref(cmap), chrom_len, std::ref(parts[(size_t)k]));
+    for (auto& t : th) t.join();
+    for (auto& p : parts) if (!p.err.empty()) { set_err(err, err_cap, p.err); return nullptr; }
+    tc_sam* S = new tc_sam();
+    S->text = text; S->len = len;
+    S->seq_off.push_back(0); S->cig_off.push_back(0); S->md_off.push_back(0); S->ji_off.push_back(0);
+    for (auto& p : parts) {
+        for (auto& h : p.header) { S->header.append(text + h.s, (size_t)h.n); S->header.push_back('\n'); }
+        const int64_t obase = (int64_t)S->other.size();
+        for (size_t i = 0; i < p.flag.size(); i++) {
+            S->seq_off.push_back(S->seq_off.back() + p.seq_len[i]); S->cig_off.push_back(S->cig_off.back() + p.cig_n[i]);
+            S->md_off.push_back(S->md_off.back() + p.md_n[i]); S->ji_off.push_back(S->ji_off.back() + p.ji_n[i]);
+            S->other_off.push_back(obase + p.other_off[i]);
+        }
+        append(S->flag, p.flag); append(S->chrom, p.chrom); append(S->pos, p.pos); append(S->tags, p.tags); append(S->cls, p.cls);
+        append(S->seq, p.seq); append(S->cig_op, p.cig_op); append(S->cig_len, p.cig_len); append(S->md, p.md); append(S->ji, p.ji);
+        append(S->line, p.line); for (int k = 0; k < 9; k++) append(S->f[k], p.f[k]); append(S->cigar, p.cigar);
+        for (int k = 0; k < 4; k++) append(S->tg[k], p.tg[k]);
+        append(S->other, p.other);
+        p = Part();
+    }
+    S->other_off.push_back((int64_t)S->other.size());
+    S->n = (int64_t)S->flag.size();
+    // keep the data arrays addressable even when empty, and padded for the device's vector loads
+    S->seq.reserve(S->seq.size() + 64); S->cig_op.reserve(S->cig_op.size() + 8); S->cig_len.reserve(S->cig_len.size() + 8);
+    S->md.reserve(S->md.size() + 8); S->ji.reserve(S->ji.size() + 8);
+    return S;
+}
+
+// distinct RNAME values of the alignment lines, newline-joined (what split_SAM collects for
+// validate_chroms, TC.py:535-536).  The caller releases the string with tc_free.
+char* tc_sam_rnames(const char* text, int64_t len, int64_t* out_len) {
+    std::unordered_map<std::string, int> seen; std::string out;
+    int64_t p = 0;
+    while (p < len) {
+        const char* nl = (const char*)memchr(text + p, '\n', (size_t)(len - p));
+        int64_t e = nl ? nl - text : len, s = p;
+        p = e + 1;
+        while (s < e && is_ws(text[s])) s++;
+        if (s >= e || text[s] == '@') continue;
+        int tabs = 0; int64_t a = -1, b = -1;
+        for (int64_t k = s; k < e; k++) if (text[k] == '\t') { tabs++; if (tabs == 2) a = k + 1; else if (tabs == 3) { b = k; break; } }
+        if (a < 0) continue;
+        if (b < 0) { b = e; while (b > a && is_ws(text[b - 1])) b--; }
+        if (seen.emplace(std::string(text + a, (size_t)(b - a)), 1).second) { out.append(text + a, (size_t)(b - a)); out.push_back('\n'); }
+    }
+    char* r = (char*)malloc(out.size() + 1);
+    memcpy(r, out.data(), out.size()); r[out.size()] = 0;
+    if (out_len) *out_len = (int64_t)out.size();
+    return r;
+}
+void tc_free(void* p) { free(p); }
+
+void tc_sam_free(tc_sam* S) { delete S; }
+int64_t tc_sam_n_reads(const tc_sam* S) { return S ? S->n : 0; }
+int64_t tc_sam_header(const tc_sam* S, const char** text) { if (!S) return 0; if (text) *text = S->header.data(); return (int64_t)S->header.size(); }
+
+void tc_sam_batch(const tc_sam* S, tc_batch_in* b) {
+    memset(b, 0, sizeof(*b));
+    b->n_reads = S->n; b->flag = S->flag.data(); b->chrom = S->chrom.data(); b->pos = S->pos.data(); b->tags = S->tags.data();
+    b->seq_off = S->seq_off.data(); b->seq = S->seq.data(); b->cig_off = S->cig_off.data(); b->cig_op = S->cig_op.data();
+    b->cig_len = S->cig_len.data(); b->md_off = S->md_off.data(); b->md = S->md.data(); b->ji_off = S->ji_off.data(); b->ji = S->ji.data();
+}
+
+int tc_sam_render(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_t canon_only, int32_t dry, int32_t n_threads,
+                  const char** sam, int64_t* sam_len, const char** fa, int64_t* fa_len, const char** lg, int64_t* lg_len,
+                  const char** te, int64_t* te_len, char* err, int64_t err_cap) {
+    if (!S || !R || R->n_reads != S->n) { set_err(err, err_cap, "tc_sam_render: result does not belong to this batch"); return TC_E_ARG; }
+    for (int64_t i = 0; i < S->n; i++) {
+        const uint32_t st = R->status[i];
+        if (st & (TC_ST_ERR_INTRON | TC_ST_ERR_MERGE)) {
+            std::string q(S->text + S->f[0][i].s, (size_t)S->f[0][i].n);
+            set_err(err, err_cap, (st & TC_ST_ERR_INTRON)
+                        ? "read " + q + ": junction rescue would leave an intron of length <= 0 (unsupported input)"
+                        : "read " + q + ": MD tag and CIGAR disagree (the reference's --dryRun crashes on this read)");
+            return TC_E_INPUT;
+        }
+    }
+    int T = n_threads < 1 ? 1 : n_threads;
+    if (S->n < 4096) T = 1;
+    std::vector<std::string> ps((size_t)T), pf((size_t)T), pl((size_t)T), pt((size_t)T);
+    std::vector<std::thread> th;
+    for (int k = 0; k < T; k++) {
+        const int64_t a = S->n * k / T, b = S->n * (k + 1) / T;
+        th.emplace_back(render_range, S, R, a, b, primary_only != 0, canon_only != 0, dry != 0, std::ref(ps[(size_t)k]), std::ref(pf[(size_t)k]),
+                        std::ref(pl[(size_t)k]), std::ref(pt[(size_t)k]));
+    }
+    for (auto& t : th) t.join();
+    auto join = [](std::string& dst, std::vector<std::string>& src) {
+        size_t tot = 0; for (auto& s : src) tot += s.size();
+        dst.clear(); dst.reserve(tot);
+        for (auto& s : src) { dst.append(s); std::string().swap(s); }
+    };
+    join(S->out_sam, ps); join(S->out_fa, pf); join(S->out_log, pl); join(S->out_te, pt);
+    *sam = S->out_sam.data(); *sam_len = (int64_t)S->out_sam.size(); *fa = S->out_fa.data(); *fa_len = (int64_t)S->out_fa.size();
+    *lg = S->out_log.data(); *lg_len = (int64_t)S->out_log.size(); *te = S->out_te.data(); *te_len = (int64_t)S->out_te.size();
+    return TC_OK;
+}
+
+}  // extern "C"

@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libtc_b200.so")
 EXPORTS = ["tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_set_options", "tc_ctx_stream",
            "tc_ctx_load_genome", "tc_ctx_load_junctions", "tc_ctx_load_variants", "tc_correct_batch",
            "tc_dryrun_batch", "tc_batch_upload", "tc_batch_run", "tc_batch_download", "tc_get_timing",
-           "tc_ctx_set_pipeline"]
+           "tc_ctx_set_pipeline", "tc_sam_parse", "tc_sam_free", "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_render",
+           "tc_sam_rnames", "tc_free"]
 
 # status bits (include/tc_b200.h)
 ST_CLASS_MASK, ST_FALLBACK, ST_CIGAR_REWRITTEN = 3, 1 << 2, 1 << 3
@@ -84,8 +85,24 @@ def _declare(lib):
     lib.tc_batch_download.argtypes = [C.c_void_p, C.POINTER(_BatchOut)]
     lib.tc_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
     lib.tc_ctx_set_pipeline.argtypes = [C.c_void_p, C.c_int64]
+    lib.tc_sam_parse.restype = C.c_void_p
+    lib.tc_sam_parse.argtypes = [C.c_char_p, C.c_int64, C.c_int32, C.POINTER(C.c_char_p), C.c_void_p, C.c_int32, C.c_char_p, C.c_int64]
+    lib.tc_sam_free.argtypes = [C.c_void_p]
+    lib.tc_sam_free.restype = None
+    lib.tc_sam_rnames.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]
+    lib.tc_sam_rnames.restype = C.c_void_p
+    lib.tc_free.argtypes = [C.c_void_p]
+    lib.tc_free.restype = None
+    lib.tc_sam_n_reads.argtypes = [C.c_void_p]
+    lib.tc_sam_n_reads.restype = C.c_int64
+    lib.tc_sam_header.argtypes = [C.c_void_p, C.POINTER(C.c_char_p)]
+    lib.tc_sam_header.restype = C.c_int64
+    lib.tc_sam_batch.argtypes = [C.c_void_p, C.POINTER(_BatchIn)]
+    lib.tc_sam_batch.restype = None
+    lib.tc_sam_render.argtypes = [C.c_void_p, C.POINTER(_BatchOut)] + [C.c_int32] * 4 + [C.POINTER(C.c_void_p), C.POINTER(C.c_int64)] * 4 + [C.c_char_p, C.c_int64]
     for f in EXPORTS:
-        if f not in ("tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_stream"):
+        if f not in ("tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_stream", "tc_sam_parse", "tc_sam_free",
+                     "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_rnames", "tc_free"):
             getattr(lib, f).restype = C.c_int
 
 
@@ -127,6 +144,81 @@ class BatchResult:
         self.jn_off = arr(out.jn_off, np.int64, n + 1) if n else np.zeros(1, np.int64)
         self.jm = arr(out.jm, np.int8, int(self.jn_off[-1]))
         self.ji = arr(out.ji, np.int32, 2 * int(self.jn_off[-1]))
+
+
+def sam_rnames(lib, text):
+    """Set of RNAME strings of the alignment lines of a SAM text (bytes)."""
+    n = C.c_int64()
+    p = lib.tc_sam_rnames(text, len(text), C.byref(n))
+    try:
+        return set(C.string_at(p, n.value).decode().split("\n")) - {""}
+    finally:
+        lib.tc_free(p)
+
+
+class SamText:
+    """SAM text parsed by the library (tc_sam_parse): header, columnar batch, and the renderer of the
+    four output texts.  Host-side only; the same logic as sam.py / render.py, in multi-threaded C++."""
+
+    def __init__(self, lib, text, genome, n_threads=None):
+        self._lib = lib
+        self._text = text if isinstance(text, bytes) else bytes(text)      # kept alive: fields are referenced
+        names = (C.c_char_p * len(genome.names))(*[n.encode() for n in genome.names])
+        err = C.create_string_buffer(1024)
+        nt = int(n_threads or min(32, os.cpu_count() or 1))
+        self._nt = nt
+        self._h = lib.tc_sam_parse(self._text, len(self._text), len(genome.names), names, genome.chrom_len.ctypes.data, nt, err, 1024)
+        if not self._h:
+            from .sam import SamFormatError
+            raise SamFormatError(err.value.decode())
+        self.n = lib.tc_sam_n_reads(self._h)
+        p = C.c_char_p()
+        n = lib.tc_sam_header(self._h, C.byref(p))
+        self.header = C.string_at(p, n).decode() if n else ""
+        self.batch = _BatchIn()
+        lib.tc_sam_batch(self._h, C.byref(self.batch))
+
+    def cols(self):
+        """numpy views of the parsed columns (valid while this object lives)."""
+        b, n = self.batch, self.n
+
+        def view(ptr, dtype, count):
+            if not ptr or count == 0:
+                return np.zeros(0, dtype=dtype)
+            return np.frombuffer((C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr), dtype=dtype, count=count)
+
+        so, co = view(b.seq_off, np.int64, n + 1), view(b.cig_off, np.int64, n + 1)
+        mo, jo = view(b.md_off, np.int64, n + 1), view(b.ji_off, np.int64, n + 1)
+        if n == 0:
+            so = co = mo = jo = np.zeros(1, dtype=np.int64)
+        return {"flag": view(b.flag, np.int32, n), "chrom": view(b.chrom, np.int32, n), "pos": view(b.pos, np.int32, n),
+                "tags": view(b.tags, np.uint8, n), "seq_off": so, "seq": view(b.seq, np.uint8, int(so[-1])), "cig_off": co,
+                "cig_op": view(b.cig_op, np.uint8, int(co[-1])), "cig_len": view(b.cig_len, np.int32, int(co[-1])), "md_off": mo,
+                "md": view(b.md, np.uint8, int(mo[-1])), "ji_off": jo, "ji": view(b.ji, np.int32, int(jo[-1]))}
+
+    def render(self, raw_out, primary_only=False, canon_only=False, dry=False):
+        """raw_out: the _BatchOut of Engine.raw_correct / raw_dryrun for this batch -> four bytes objects."""
+        ptr = [C.c_void_p() for _ in range(4)]
+        ln = [C.c_int64() for _ in range(4)]
+        err = C.create_string_buffer(1024)
+        args = []
+        for a, b in zip(ptr, ln):
+            args += [C.byref(a), C.byref(b)]
+        rc = self._lib.tc_sam_render(self._h, C.byref(raw_out), int(primary_only), int(canon_only), int(dry), self._nt, *args, err, 1024)
+        if rc != 0:
+            raise EngineError(err.value.decode())
+        return {k: C.string_at(p, l.value) if l.value else b"" for k, p, l in zip(("sam", "fa", "log", "te"), ptr, ln)}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.tc_sam_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Engine:
@@ -227,6 +319,14 @@ class Engine:
         out = _BatchOut()
         self._check(self._lib.tc_correct_batch(self._ctx, C.byref(b), C.byref(out)), "tc_correct_batch")
         return out
+
+    def raw_dryrun(self, b):
+        out = _BatchOut()
+        self._check(self._lib.tc_dryrun_batch(self._ctx, C.byref(b), C.byref(out)), "tc_dryrun_batch")
+        return out
+
+    def parse_sam(self, text, genome, n_threads=None):
+        return SamText(self._lib, text, genome, n_threads)
 
     def timing(self):
         t = Timing()
