@@ -35,6 +35,9 @@ struct Part {                       // what one parser thread produces
     std::string err;
 };
 
+template <class V> inline void put_bytes(V& v, const char* p, int64_t n) {
+    const size_t o = v.size(); v.resize(o + (size_t)n); if (n) memcpy(v.data() + o, p, (size_t)n);
+}
 inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
 
 // Python int(): optional surrounding whitespace, optional sign, digits (underscores not supported)
@@ -75,9 +78,19 @@ void set_err(char* err, int64_t cap, const std::string& m) {
 void parse_range(const char* T, int64_t a, int64_t b, const std::unordered_map<std::string, int>& cmap, const int64_t* clen, Part& P) {
     int64_t p = a;
     std::vector<Span> fld;
+    {   // sized from the byte range: a long-read SAM line is mostly SEQ (and QUAL when present)
+        const size_t bytes = (size_t)(b - a), est = bytes / 1500 + 16;
+        P.seq.reserve(bytes - bytes / 8); P.cig_op.reserve(est * 40); P.cig_len.reserve(est * 40); P.md.reserve(est * 80);
+        P.flag.reserve(est); P.chrom.reserve(est); P.pos.reserve(est); P.tags.reserve(est); P.cls.reserve(est); P.line.reserve(est);
+        for (int k = 0; k < 9; k++) P.f[k].reserve(est);
+        for (int k = 0; k < 4; k++) P.tg[k].reserve(est);
+        P.cigar.reserve(est); P.other.reserve(est * 3); P.other_off.reserve(est);
+        P.seq_len.reserve(est); P.cig_n.reserve(est); P.md_n.reserve(est); P.ji_n.reserve(est);
+    }
+    Span last_chrom = {0, 0}; int last_cid = -1;
     while (p < b && P.err.empty()) {
-        int64_t e = p;
-        while (e < b && T[e] != '\n') e++;
+        const char* nlp = (const char*)memchr(T + p, '\n', (size_t)(b - p));
+        int64_t e = nlp ? nlp - T : b;
         int64_t s = p, t = e;
         p = e + 1;
         while (s < t && is_ws(T[s])) s++;
@@ -85,10 +98,15 @@ void parse_range(const char* T, int64_t a, int64_t b, const std::unordered_map<s
         if (s >= t) continue;
         if (T[s] == '@') { P.header.push_back({s, (int32_t)(t - s)}); continue; }
         fld.clear();
-        int64_t q = s;
-        for (int64_t k = s; k <= t; k++) if (k == t || T[k] == '\t') { fld.push_back({q, (int32_t)(k - q)}); q = k + 1; }
+        for (int64_t q = s;;) {
+            const char* tp = (const char*)memchr(T + q, '\t', (size_t)(t - q));
+            const int64_t k = tp ? tp - T : t;
+            fld.push_back({q, (int32_t)(k - q)});
+            if (!tp) break;
+            q = k + 1;
+        }
         if (fld.size() < 11) { P.err = "SAM record with fewer than 11 fields: " + std::string(T + s, (size_t)std::min<int64_t>(80, t - s)); break; }
-        std::string qname(T + fld[0].s, (size_t)fld[0].n);
+#define qname std::string(T + fld[0].s, (size_t)fld[0].n)
         int64_t fl;
         if (!py_int(T + fld[1].s, fld[1].n, fl)) { P.err = "read " + qname + ": FLAG is not an integer"; break; }
         const bool star = fld[2].n == 1 && T[fld[2].s] == '*';
@@ -102,9 +120,13 @@ void parse_range(const char* T, int64_t a, int64_t b, const std::unordered_map<s
             P.other_off.push_back((int64_t)P.other.size());
             continue;
         }
-        auto it = cmap.find(std::string(T + fld[2].s, (size_t)fld[2].n));
-        if (it == cmap.end()) { P.err = "read " + qname + ": chromosome " + std::string(T + fld[2].s, (size_t)fld[2].n) + " is not in the reference genome"; break; }
-        const int c = it->second;
+        int c;
+        if (last_cid >= 0 && last_chrom.n == fld[2].n && memcmp(T + last_chrom.s, T + fld[2].s, (size_t)fld[2].n) == 0) c = last_cid;
+        else {
+            auto it = cmap.find(std::string(T + fld[2].s, (size_t)fld[2].n));
+            if (it == cmap.end()) { P.err = "read " + qname + ": chromosome " + std::string(T + fld[2].s, (size_t)fld[2].n) + " is not in the reference genome"; break; }
+            c = it->second; last_cid = c; last_chrom = fld[2];
+        }
         int64_t posv;
         if (!py_int(T + fld[3].s, fld[3].n, posv)) { P.err = "read " + qname + ": POS is not an integer"; break; }
         // CIGAR: ^(?:[0-9]+[A-Z])+$
@@ -144,7 +166,7 @@ void parse_range(const char* T, int64_t a, int64_t b, const std::unordered_map<s
             int c1 = -1, c2 = -1, c3 = n;
             for (int k = 0; k < n; k++) if (x[k] == ':') { if (c1 < 0) c1 = k; else if (c2 < 0) c2 = k; else { c3 = k; break; } }
             if (c2 < 0) { P.err = "read " + qname + ": malformed MD tag"; break; }
-            if (tg[0].n) { P.md.insert(P.md.end(), x + c2 + 1, x + c3); mdn = c3 - c2 - 1; }
+            if (tg[0].n) { put_bytes(P.md, x + c2 + 1, c3 - c2 - 1); mdn = c3 - c2 - 1; }
         }
         if (tg[2].n) tb |= 4;
         if (tg[3].n) {
@@ -168,10 +190,11 @@ void parse_range(const char* T, int64_t a, int64_t b, const std::unordered_map<s
             }
         }
         P.chrom.push_back(c); P.pos.push_back((int32_t)posv); P.tags.push_back(tb);
-        P.seq.insert(P.seq.end(), T + fld[9].s, T + fld[9].s + fld[9].n);
+        put_bytes(P.seq, T + fld[9].s, fld[9].n);
         P.seq_len.push_back(fld[9].n); P.cig_n.push_back(nops); P.md_n.push_back(mdn); P.ji_n.push_back(jin);
         P.cigar.push_back(fld[5]); for (int k = 0; k < 4; k++) P.tg[k].push_back(tg[k]);
     }
+#undef qname
 }
 
 template <class T> void append(std::vector<T>& d, const std::vector<T>& s) { d.insert(d.end(), s.begin(), s.end()); }
@@ -181,7 +204,12 @@ const char* const TE_TYPE[4] = {"Mismatch", "Insertion", "Deletion", "NC_SJ_boun
 const char* const TE_STATUS[2] = {"Corrected", "Uncorrected"};
 const char* const TE_REASON[6] = {"NA", "VariantMatch", "TooLarge", "TooFarFromAnnotJn", "Other", "DryRun"};
 
-inline void put_int(std::string& o, int64_t v) { char b[24]; int n = snprintf(b, sizeof b, "%lld", (long long)v); o.append(b, (size_t)n); }
+inline void put_int(std::string& o, int64_t v) {
+    char b[24]; int n = 24; const bool neg = v < 0; uint64_t u = neg ? (uint64_t)(-v) : (uint64_t)v;
+    do { b[--n] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (neg) b[--n] = '-';
+    o.append(b + n, (size_t)(24 - n));
+}
 
 struct Comp { uint8_t t[256]; Comp() { for (int k = 0; k < 256; k++) t[k] = (uint8_t)k; const char* a = "ACGTNacgtn*"; const char* b = "TGCANtgcan*"; for (int k = 0; a[k]; k++) t[(uint8_t)a[k]] = (uint8_t)b[k]; } };
 const Comp COMP;
@@ -190,6 +218,11 @@ void render_range(const tc_sam* S, const tc_batch_out* R, int64_t a, int64_t b, 
                   std::string& sam, std::string& fa, std::string& lg, std::string& te) {
     const char* T = S->text;
     std::string row, seq;
+    if (b > a && !dry) {
+        const size_t sb = (size_t)((R->seq_off[b] - R->seq_off[a]) + (b - a) * 400 + (R->cig_off[b] - R->cig_off[a]) * 6);
+        sam.reserve(sb); fa.reserve((size_t)(R->seq_off[b] - R->seq_off[a]) + (size_t)(b - a) * 64);
+    }
+    if (b > a) { lg.reserve((size_t)(b - a) * 80); te.reserve((size_t)(R->te_off[b] - R->te_off[a]) * 64 + 64); }
     for (int64_t i = a; i < b; i++) {
         const uint32_t st = R->status[i]; const int cls = (int)(st & TC_ST_CLASS_MASK);
         // log row: TranscriptID, Mapping, ten counters ("NA" = -1)
@@ -285,27 +318,42 @@ tc_sam* tc_sam_parse(const char* text, int64_t len, int32_t n_chrom, const char*
     for (auto& p : parts) if (!p.err.empty()) { set_err(err, err_cap, p.err); return nullptr; }
     tc_sam* S = new tc_sam();
     S->text = text; S->len = len;
-    S->seq_off.push_back(0); S->cig_off.push_back(0); S->md_off.push_back(0); S->ji_off.push_back(0);
-    for (auto& p : parts) {
+    // totals, then every part is copied to its place by its own thread
+    std::vector<size_t> r0((size_t)T + 1, 0), s0((size_t)T + 1, 0), c0((size_t)T + 1, 0), m0((size_t)T + 1, 0), j0((size_t)T + 1, 0), o0((size_t)T + 1, 0);
+    for (int k = 0; k < T; k++) {
+        const Part& p = parts[(size_t)k];
+        r0[k + 1] = r0[k] + p.flag.size(); s0[k + 1] = s0[k] + p.seq.size(); c0[k + 1] = c0[k] + p.cig_op.size();
+        m0[k + 1] = m0[k] + p.md.size(); j0[k + 1] = j0[k] + p.ji.size(); o0[k + 1] = o0[k] + p.other.size();
         for (auto& h : p.header) { S->header.append(text + h.s, (size_t)h.n); S->header.push_back('\n'); }
-        const int64_t obase = (int64_t)S->other.size();
-        for (size_t i = 0; i < p.flag.size(); i++) {
-            S->seq_off.push_back(S->seq_off.back() + p.seq_len[i]); S->cig_off.push_back(S->cig_off.back() + p.cig_n[i]);
-            S->md_off.push_back(S->md_off.back() + p.md_n[i]); S->ji_off.push_back(S->ji_off.back() + p.ji_n[i]);
-            S->other_off.push_back(obase + p.other_off[i]);
-        }
-        append(S->flag, p.flag); append(S->chrom, p.chrom); append(S->pos, p.pos); append(S->tags, p.tags); append(S->cls, p.cls);
-        append(S->seq, p.seq); append(S->cig_op, p.cig_op); append(S->cig_len, p.cig_len); append(S->md, p.md); append(S->ji, p.ji);
-        append(S->line, p.line); for (int k = 0; k < 9; k++) append(S->f[k], p.f[k]); append(S->cigar, p.cigar);
-        for (int k = 0; k < 4; k++) append(S->tg[k], p.tg[k]);
-        append(S->other, p.other);
-        p = Part();
     }
+    const size_t n = r0[T];
+    S->flag.resize(n); S->chrom.resize(n); S->pos.resize(n); S->tags.resize(n); S->cls.resize(n);
+    S->seq_off.resize(n + 1); S->cig_off.resize(n + 1); S->md_off.resize(n + 1); S->ji_off.resize(n + 1); S->other_off.resize(n);
+    S->seq.resize(s0[T] + 64); S->cig_op.resize(c0[T] + 8); S->cig_len.resize(c0[T] + 8); S->md.resize(m0[T] + 8); S->ji.resize(j0[T] + 8);
+    S->line.resize(n); for (int k = 0; k < 9; k++) S->f[k].resize(n); S->cigar.resize(n); for (int k = 0; k < 4; k++) S->tg[k].resize(n);
+    S->other.resize(o0[T]);
+    auto place = [&](int k) {
+        Part& p = parts[(size_t)k]; const size_t r = r0[k], m = p.flag.size();
+        auto cp = [](auto& dst, size_t at, const auto& src) { if (!src.empty()) memcpy(dst.data() + at, src.data(), src.size() * sizeof(src[0])); };
+        cp(S->flag, r, p.flag); cp(S->chrom, r, p.chrom); cp(S->pos, r, p.pos); cp(S->tags, r, p.tags); cp(S->cls, r, p.cls);
+        cp(S->seq, s0[k], p.seq); cp(S->cig_op, c0[k], p.cig_op); cp(S->cig_len, c0[k], p.cig_len); cp(S->md, m0[k], p.md); cp(S->ji, j0[k], p.ji);
+        cp(S->line, r, p.line); for (int q = 0; q < 9; q++) cp(S->f[q], r, p.f[q]); cp(S->cigar, r, p.cigar); for (int q = 0; q < 4; q++) cp(S->tg[q], r, p.tg[q]);
+        cp(S->other, o0[k], p.other);
+        int64_t so = (int64_t)s0[k], co = (int64_t)c0[k], mo = (int64_t)m0[k], jo = (int64_t)j0[k];
+        for (size_t i = 0; i < m; i++) {
+            S->seq_off[r + i] = so; S->cig_off[r + i] = co; S->md_off[r + i] = mo; S->ji_off[r + i] = jo; S->other_off[r + i] = (int64_t)o0[k] + p.other_off[i];
+            so += p.seq_len[i]; co += p.cig_n[i]; mo += p.md_n[i]; jo += p.ji_n[i];
+        }
+        p = Part();
+    };
+    {
+        std::vector<std::thread> tp;
+        for (int k = 0; k < T; k++) tp.emplace_back(place, k);
+        for (auto& t : tp) t.join();
+    }
+    S->seq_off[n] = (int64_t)s0[T]; S->cig_off[n] = (int64_t)c0[T]; S->md_off[n] = (int64_t)m0[T]; S->ji_off[n] = (int64_t)j0[T];
     S->other_off.push_back((int64_t)S->other.size());
     S->n = (int64_t)S->flag.size();
-    // keep the data arrays addressable even when empty, and padded for the device's vector loads
-    S->seq.reserve(S->seq.size() + 64); S->cig_op.reserve(S->cig_op.size() + 8); S->cig_len.reserve(S->cig_len.size() + 8);
-    S->md.reserve(S->md.size() + 8); S->ji.reserve(S->ji.size() + 8);
     return S;
 }
 
