@@ -74,7 +74,7 @@ def _genome(rng, n_chrom, length):
     return g
 
 
-def _genes(rng, g, per_chrom, sj_rows, strand0_frac=0.05):
+def _genes(rng, g, per_chrom, sj_rows, strand0_frac=0.05, exon_len=(30, 400)):
     """Lay out genes (exon blocks) and plant splice motifs; returns list of gene dicts."""
     genes = []
     for chrom, s in g.items():
@@ -85,7 +85,7 @@ def _genes(rng, g, per_chrom, sj_rows, strand0_frac=0.05):
             n_ex = rng.randrange(2, 9)
             exons, p = [], pos
             for e in range(n_ex):
-                el = rng.randrange(30, 400)
+                el = rng.randrange(exon_len[0], exon_len[1])
                 exons.append((p, p + el - 1))           # 1-based inclusive
                 p += el + rng.randrange(60, 3000)
             if p + 3000 >= L:
@@ -132,11 +132,11 @@ def _std_md(read_seq_aligned):
 
 def make_case(seed, n_reads=200, n_chrom=2, chrom_len=120000, genes_per_chrom=12, err=0.02,
               shift_frac=0.25, unpinned=False, variant_frac=0.3, tagless_frac=0.2,
-              quirks=True):
+              quirks=True, exon_len=(30, 400)):
     rng = random.Random(seed)
     case = Case()
     g = _genome(rng, n_chrom, chrom_len)
-    genes = _genes(rng, g, genes_per_chrom, case.sj_rows)
+    genes = _genes(rng, g, genes_per_chrom, case.sj_rows, exon_len=exon_len)
     case.genome = {k: "".join(v) for k, v in g.items()}
     annotated = {}
     for r in case.sj_rows:

@@ -36,6 +36,18 @@ def test_long_reads_and_many(engine):
     pc.check_generated(engine, 999, n_reads=1500, err=0.08, shift_frac=0.4)
 
 
+def test_reads_longer_than_the_shared_memory_stage(engine):
+    """Reads of 5-20 kb (new SEQ > EMIT_CAP) and reads with hundreds of slices take the generic
+    paths of the output kernel."""
+    pc.check_generated(engine, 1201, n_reads=120, chrom_len=400000, genes_per_chrom=10, exon_len=(900, 3000), err=0.03)
+    pc.check_generated(engine, 1202, n_reads=150, err=0.12, shift_frac=0.5)
+
+
+def test_tagless_input_at_scale(engine):
+    """No NM/MD/jM/jI tags at all: NM/MD are bootstrapped on the device for every read (tr.py:47-48)."""
+    pc.check_generated(engine, 1203, n_reads=400, tagless_frac=1.0)
+
+
 def test_pipelined_chunks(engine):
     """tc_correct_batch cut into small chunks (3-stream pipeline, rebased offsets) gives the same texts."""
     for chunk in (16, 37, 100):
