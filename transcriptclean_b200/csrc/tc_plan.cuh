@@ -245,9 +245,10 @@ TC_HD bool md_next(MdCur& t, int& op, int32_t& cnt) {
     return true;
 }
 
-TC_HD void md_effective(const Params& P, int64_t i, const uint8_t*& p, int& len) {
+// `B` may be a copy of P.B whose cig_op / cig_len / md pointers address a staged (shared-memory) copy
+TC_HD void md_effective(const Params& P, const BatchDev& B, int64_t i, const uint8_t*& p, int& len) {
     if (P.W.status[i] & TC_ST_NMMD_DEVICE) { p = P.W.md_init_pool + P.W.md_init_off[i]; len = P.W.md_init_len[i]; }
-    else { p = P.B.md + P.B.md_off[i]; len = (int)(P.B.md_off[i + 1] - P.B.md_off[i]); }
+    else { p = B.md + B.md_off[i]; len = (int)(B.md_off[i + 1] - B.md_off[i]); }
 }
 
 TC_HD int read_class(int32_t flag, int32_t chrom) {           // TC.py:1570-1575 (Q1)
@@ -278,7 +279,7 @@ TC_HD void measure_read(const Params& P, int64_t i) {
     }
     int ntok = 0;
     if (!(st & TC_ST_NMMD_NONE)) {
-        MdCur t; md_effective(P, i, t.p, t.len); t.i = 0;
+        MdCur t; md_effective(P, B, i, t.p, t.len); t.i = 0;
         for (int k = 0; k < t.len; k++) {
             uint8_t u = up8(t.p[k]);
             if (u == 'A' || u == 'C' || u == 'T' || u == 'G' || u == 'N') { mf |= MF_MD_ACGTN; break; }
@@ -325,8 +326,8 @@ TC_HD void te_put(tc_te* te, int& n, int type, int32_t a, int32_t b, int32_t siz
 // rewrites its own kind of op, keeps the genome cursor of every op, and joins M runs the same
 // way, one pass over the MD x CIGAR merge (tr.py:159-213) yields the same CIGAR, SEQ, counters
 // and TE rows (rows are re-ordered by stage in tc_emit).
-TC_HD void plan_read(const Params& P, int64_t i) {
-    const BatchDev& B = P.B; const WorkDev& W = P.W; const tc_options& O = P.O;
+TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
+    const WorkDev& W = P.W; const tc_options& O = P.O;
     uint32_t st = W.status[i];
     if ((st & TC_ST_CLASS_MASK) != 0) return;
     int32_t* C = W.counters + 10 * i;
@@ -355,7 +356,7 @@ TC_HD void plan_read(const Params& P, int64_t i) {
     int32_t crem = ci < cend ? B.cig_len[ci] : 0;
     MdCur md; md.i = 0; md.len = 0; md.p = 0;
     int mop = 0; int32_t mrem = 0; bool have_md = false;
-    if (stage1) { md_effective(P, i, md.p, md.len); have_md = md_next(md, mop, mrem); }
+    if (stage1) { md_effective(P, B, i, md.p, md.len); have_md = md_next(md, mop, mrem); }
     bool fail = false;
     while (true) {
         int op; int32_t ct;
@@ -378,7 +379,7 @@ TC_HD void plan_read(const Params& P, int64_t i) {
         case 'M':
             E.push(0, q, ct); E.match(ct); q += ct; g += ct; break;
         case 'X':                                                     // only produced by the MD side
-            if (snp_match(P.V, chrom, g, seq[q])) {                   // TC.py:1115-1130 (Q11)
+            if (P.V.n_snp > 0 && snp_match(P.V, chrom, g, seq[q])) {   // TC.py:1115-1130 (Q11); SEQ is only touched when a catalogue exists
                 te_put(v.te, nte, 0, (int32_t)g, 0, ct, 1, 1); uM++; nteM++;
                 E.push(0, q, ct);
             } else {
@@ -429,6 +430,8 @@ TC_HD void plan_read(const Params& P, int64_t i) {
     else if (stage1) { W.refresh[i] = 1; W.nm_extra[i] = ins_removed; }
     W.status[i] = st | TC_ST_CIGAR_REWRITTEN;
 }
+
+TC_HD void plan_read(const Params& P, int64_t i) { plan_read(P, i, P.B); }
 
 // ---------------------------------------------------------------------------------- K2 junctions
 
@@ -836,7 +839,7 @@ TC_HD void dry_read(const Params& P, int64_t i) {
     int64_t g = B.pos[i]; int nte = 0, uM = 0, uI = 0, uD = 0;
     int64_t ci = B.cig_off[i]; const int64_t cend = B.cig_off[i + 1];
     int32_t crem = ci < cend ? B.cig_len[ci] : 0;
-    MdCur md; md.i = 0; md_effective(P, i, md.p, md.len);
+    MdCur md; md.i = 0; md_effective(P, B, i, md.p, md.len);
     int mop = 0; int32_t mrem = 0; bool have_md = md_next(md, mop, mrem);
     while (true) {
         int op; int32_t ct;
