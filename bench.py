@@ -271,10 +271,11 @@ def main():
     cig_m = np.where(res.cig_op == ord("M"), res.cig_len, 0).astype(np.int64)
     m_per_read = np.add.reduceat(np.concatenate((cig_m, [0])), np.minimum(res.cig_off[:-1], len(cig_m)))
     m_per_read = np.where(np.diff(res.cig_off) > 0, m_per_read, 0)
-    bytes_emit = (int(cols["seq"].nbytes) + int(res.seq.nbytes) + 0.375 * float(m_per_read[refreshed].sum())
-                  + float(seq_len_out[refreshed].sum())        # the compare re-reads the new SEQ
+    # k_emit: SEQ in + SEQ out (16-byte padded rows) + 2-bit genome words under the verified M bases
+    # + CIGAR (8 B packed in, 5 B out) + TE rows (16 B in, 16 B out) + jM/jI (9 B) + MD + the 128-byte plan row
+    bytes_emit = (int(cols["seq"].nbytes) + int(res.seq.nbytes) + 0.25 * float(m_per_read[refreshed].sum())
                   + 13.0 * len(res.cig_op) + 32.0 * len(res.te) + 9.0 * len(res.jm) + float(res.md_len.sum())
-                  + 64.0 * int(primary.sum()))
+                  + 128.0 * int(primary.sum()))
     bytes_plan = (5.0 * len(cols["cig_op"]) + float(cols["md"].nbytes) + 8.0 * len(res.cig_op) + 16.0 * len(res.te)
                   + 96.0 * int(primary.sum()))
     per = {k: v / steps for k, v in kern.items()}
@@ -282,6 +283,10 @@ def main():
     dom_bytes = bytes_emit if dom == "k_emit_ms" else bytes_plan
     peak, peak_src = peaks()
     achieved = dom_bytes / (per[dom] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_k_emit_traffic.json")
+    if dom == "k_emit_ms" and os.path.exists(tpath):      # DRAM bytes per read from the committed ncu --set full capture
+        traffic = json.load(open(tpath))["dram_bytes_per_read"] * args.reads
 
     reads_total = args.reads * world
     line = {
@@ -297,7 +302,7 @@ def main():
         "gpu_launches": int(launches),
         "kernel_ms_per_step": per, "exact_nmmd_reads_per_step": int(exact_reads),
         "roofline": {"bound": "hbm", "kernel": dom.replace("_ms", ""), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom_bytes},
         "clocks": clocks,
     }
