@@ -63,7 +63,8 @@ TC_HD void cig_get(const CigSrc& c, int k, int& op, int32_t& len) {
 #define EMIT_CAP 4096            // reads whose new SEQ fits are staged in shared memory
 #define EMIT_MAXBP 192
 #define EMIT_MAXGI 192
-#define EMIT_GBUF_WORDS 400
+#define EMIT_GBUF_WORDS 280
+#define EMIT_MAXD 44
 
 #define EMIT_MAXRUN 64
 struct __align__(16) EmitSmem {  // per warp
@@ -77,6 +78,7 @@ struct __align__(16) EmitSmem {  // per warp
         struct {                                                        // while NM/MD is verified (tier 1)
             uint16_t run_q[EMIT_MAXRUN], run_ct[EMIT_MAXRUN], run_w[EMIT_MAXRUN]; int32_t run_g[EMIT_MAXRUN];   // M runs
             uint32_t gbuf[EMIT_GBUF_WORDS + 4];                         // their 2-bit genome words
+            int32_t d_g[EMIT_MAXD], d_ct[EMIT_MAXD], d_run[EMIT_MAXD];    // D ops: reference offset, length, match run before
         };
     };
 };
@@ -485,17 +487,29 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
             if (fast && ncig <= 32 * 4) {
                 // tier 1: run list (query offset, reference offset, length) of the M ops, lane-parallel
                 uint16_t* run_q = SM.run_q; uint16_t* run_ct = SM.run_ct; uint16_t* run_w = SM.run_w; int32_t* run_g = SM.run_g;
-                int nrun = 0, qcur = 0, nD = 0, ibases = 0; int64_t gcur = 0; bool ovf = false;
+                int nrun = 0, qcur = 0, nD = 0, ibases = 0, dbases = 0, mcur = 0, m_at_last_d = 0; int64_t gcur = 0; bool ovf = false;
                 for (int k0 = 0; k0 < ncig; k0 += 32) {
                     int op = 0; int32_t ct = 0;
                     if (k0 + lane < ncig) cig_get(cs, k0 + lane, op, ct);
                     const int qadv = (op == 'M' || op == 'I' || op == 'S') ? ct : 0;
                     const int gadv = (op == 'M' || op == 'D' || op == 'N' || op == 'H') ? ct : 0;
                     int qtot, gtot; const int qs = warp_excl_scan(qadv, lane, qtot); const int gs = warp_excl_scan(gadv, lane, gtot);
-                    const bool isM = op == 'M' && ct > 0;
-                    const unsigned mM = __ballot_sync(FULL, isM);
-                    nD += __popc(__ballot_sync(FULL, op == 'D'));
-                    ibases += op == 'I' ? ct : 0;
+                    const bool isM = op == 'M' && ct > 0, isD = op == 'D';
+                    const unsigned mM = __ballot_sync(FULL, isM), mD = __ballot_sync(FULL, isD);
+                    int mtot; const int ms = warp_excl_scan(op == 'M' ? ct : 0, lane, mtot);   // matched bases before this op
+                    {   // MD token of a D op: <matches since the previous token>^<bases>
+                        const unsigned prev = mD & lt;                  // nearest earlier D in this round, else the carried one
+                        const int cand = __shfl_sync(FULL, mcur + ms, prev ? 31 - __clz(prev) : lane);
+                        if (isD) {
+                            const int idx = nD + __popc(prev);
+                            if (idx < EMIT_MAXD) { SM.d_g[idx] = (int32_t)(gcur + gs); SM.d_ct[idx] = ct; SM.d_run[idx] = mcur + ms - (prev ? cand : m_at_last_d); }
+                            else ovf = true;
+                        }
+                        const int lastd = __shfl_sync(FULL, mcur + ms, mD ? 31 - __clz(mD) : 0);
+                        if (mD) m_at_last_d = lastd;
+                    }
+                    nD += __popc(mD);
+                    ibases += op == 'I' ? ct : 0; dbases += isD ? ct : 0;
                     if (isM) {
                         const int idx = nrun + __popc(mM & lt);
                         if (idx < EMIT_MAXRUN && gcur + gs < 0x7fffffffll) { run_q[idx] = (uint16_t)(qcur + qs); run_g[idx] = (int32_t)(gcur + gs); run_ct[idx] = (uint16_t)ct; }
@@ -504,12 +518,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
                         const int64_t ga = gbase + gcur + gs;
                         for (int64_t b = ga >> 8; b <= (ga + ct - 1) >> 8; b++) ovf |= (P.G.excblk[b >> 5] >> (b & 31)) & 1u;
                     }
-                    nrun += __popc(mM); qcur += qtot; gcur += gtot;
+                    nrun += __popc(mM); qcur += qtot; gcur += gtot; mcur += mtot;
                 }
 #pragma unroll
-                for (int d = 16; d; d >>= 1) ibases += __shfl_xor_sync(FULL, ibases, d);
+                for (int d = 16; d; d >>= 1) { ibases += __shfl_xor_sync(FULL, ibases, d); dbases += __shfl_xor_sync(FULL, dbases, d); }
                 const bool careful = pos < 1 || pos + gcur - 1 > clen;
-                bool tier1 = !careful && nD == 0 && nrun <= EMIT_MAXRUN && !__any_sync(FULL, ovf);
+                bool tier1 = !careful && nD <= EMIT_MAXD && nrun <= EMIT_MAXRUN && !__any_sync(FULL, ovf);
                 int wtot = 0;
                 if (tier1) {                                           // word offsets of the staged genome runs
                     __syncwarp();
@@ -560,10 +574,37 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
                         }
                         total_m += ct;
                     }
-                    if (!__any_sync(FULL, bad)) {                      // every aligned base equals the genome: MD is one number
-                        nm = ibases; len = total_m > 0 ? ndigits((uint32_t)total_m) : 0;
-                        off = O.md_inline + 8 * i;                      // at most 5 digits: the read's inline slot
-                        if (lane == 0) *reinterpret_cast<unsigned long long*>(O.md_pool + off) = dec_word((uint32_t)total_m, len);   // slot is 8-byte aligned
+                    if (!__any_sync(FULL, bad)) {                      // every aligned base equals the genome
+                        nm = ibases + dbases;
+                        if (nD == 0) {                                 // MD is one number, at most 5 digits: the read's inline slot
+                            len = total_m > 0 ? ndigits((uint32_t)total_m) : 0;
+                            off = O.md_inline + 8 * i;
+                            if (lane == 0) *reinterpret_cast<unsigned long long*>(O.md_pool + off) = dec_word((uint32_t)total_m, len);   // slot is 8-byte aligned
+                        } else {                                       // one token per D op, then the trailing run
+                            __syncwarp();
+                            int32_t* d_off = SM.run_g;                 // the run list is no longer needed
+                            int tlen = 0;
+                            for (int k0 = 0; k0 < nD; k0 += 32) {
+                                const int k = k0 + lane;
+                                const int t = k < nD ? ndigits((uint32_t)SM.d_run[k]) + 1 + SM.d_ct[k] : 0;
+                                int tot; const int to = tlen + warp_excl_scan(t, lane, tot);
+                                if (k < nD) d_off[k] = to;
+                                tlen += tot;
+                            }
+                            const int final_run = total_m - m_at_last_d, ndf = final_run > 0 ? ndigits((uint32_t)final_run) : 0;
+                            len = tlen + ndf;
+                            off = len <= 8 ? O.md_inline + 8 * i : pool_grab(O.md_cursor, O.md_cap, len, lane);
+                            __syncwarp();
+                            if (off >= 0) {
+                                uint8_t* out = O.md_pool + off;
+                                for (int k = lane; k < nD; k += 32) { const int nd = ndigits((uint32_t)SM.d_run[k]); write_dec(out + d_off[k], (uint32_t)SM.d_run[k], nd); out[d_off[k] + nd] = '^'; }
+                                for (int k = 0; k < nD; k++) {
+                                    uint8_t* bp = out + d_off[k] + ndigits((uint32_t)SM.d_run[k]) + 1; const int64_t g = gbase + SM.d_g[k]; const int ct = SM.d_ct[k];
+                                    for (int j = lane; j < ct; j += 32) bp[j] = genome_byte(P.G, g + j);
+                                }
+                                if (ndf > 0 && lane == 0) write_dec(out + tlen, (uint32_t)final_run, ndf);
+                            }
+                        }
                         done = true;
                     }
                 }
