@@ -524,55 +524,50 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
                 for (int d = 16; d; d >>= 1) { ibases += __shfl_xor_sync(FULL, ibases, d); dbases += __shfl_xor_sync(FULL, dbases, d); }
                 const bool careful = pos < 1 || pos + gcur - 1 > clen;
                 bool tier1 = !careful && nD <= EMIT_MAXD && nrun <= EMIT_MAXRUN && !__any_sync(FULL, ovf);
-                int wtot = 0;
-                if (tier1) {                                           // word offsets of the staged genome runs
-                    __syncwarp();
-                    for (int r0 = 0; r0 < nrun; r0 += 32) {
-                        const int r = r0 + lane; int nwd = 0;
-                        if (r < nrun) { const int64_t g0 = gbase + run_g[r]; nwd = (int)(((g0 + run_ct[r] - 1) >> 4) - (g0 >> 4)) + 2; }
-                        int tot; const int wo = wtot + warp_excl_scan(nwd, lane, tot);
-                        if (r < nrun) run_w[r] = (uint16_t)wo;
-                        wtot += tot;
-                    }
-                    if (wtot > EMIT_GBUF_WORDS) tier1 = false;
-                }
                 if (tier1) {
+                    // flat item space: item = 16 bases of one M run; run_w[r] = first item of run r
                     __syncwarp();
-                    uint32_t* gb = SM.gbuf;
-                    for (int r = 0; r < nrun; r++) {                   // all genome words of the read in flight at once
-                        const int64_t g0 = gbase + run_g[r]; const int nwd = (int)(((g0 + run_ct[r] - 1) >> 4) - (g0 >> 4)) + 2;
-                        const uint32_t* gsrc = P.G.g2 + (g0 >> 4); uint32_t* gdst = gb + run_w[r];
-                        for (int t = lane; t < nwd; t += 32) cp_async4(gdst + t, gsrc + t);
+                    int nit = 0;
+                    for (int r0 = 0; r0 < nrun; r0 += 32) {
+                        const int r = r0 + lane;
+                        int tot; const int io = nit + warp_excl_scan(r < nrun ? ((int)run_ct[r] + 15) >> 4 : 0, lane, tot);
+                        if (r < nrun) run_w[r] = (uint16_t)io;
+                        nit += tot;
                     }
-                    cp_async_wait_all();
                     __syncwarp();
-                    bool bad = false; int total_m = 0;
-                    for (int r = 0; r < nrun; r++) {
-                        const int q = run_q[r], ct = run_ct[r]; const int64_t g0 = gbase + run_g[r]; const uint32_t* gr = gb + run_w[r];
-                        const int gsub = (int)(g0 & 15);
-                        for (int c0 = 0; c0 < ct; c0 += 512) {
-                            const int lo = c0 + 16 * lane; int nb = ct - lo; nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-                            if (nb > 0) {
-                                const int a = q + lo;
-                                const uint32_t* sp = reinterpret_cast<const uint32_t*>(SM.seq) + (a >> 2); const int sh = (a & 3) * 8;
-                                const uint32_t x0 = sp[0], x1 = sp[1], x2 = sp[2], x3 = sp[3], x4 = sp[4];
-                                const int gi = (gsub + lo) >> 4;
-                                const uint32_t gw = __funnelshift_r(gr[gi], gr[gi + 1], ((gsub + lo) & 15) * 2);
-                                uint32_t d0 = (__funnelshift_r(x0, x1, sh) & 0xDFDFDFDFu) ^ lut[gw & 255u];
-                                uint32_t d1 = (__funnelshift_r(x1, x2, sh) & 0xDFDFDFDFu) ^ lut[(gw >> 8) & 255u];
-                                uint32_t d2 = (__funnelshift_r(x2, x3, sh) & 0xDFDFDFDFu) ^ lut[(gw >> 16) & 255u];
-                                uint32_t d3 = (__funnelshift_r(x3, x4, sh) & 0xDFDFDFDFu) ^ lut[gw >> 24];
-                                if (nb < 16) {
-                                    const uint32_t m0 = nb >= 4 ? ~0u : ((1u << (8 * nb)) - 1u);
-                                    const uint32_t m1 = nb >= 8 ? ~0u : (nb <= 4 ? 0u : ((1u << (8 * (nb - 4))) - 1u));
-                                    const uint32_t m2 = nb >= 12 ? ~0u : (nb <= 8 ? 0u : ((1u << (8 * (nb - 8))) - 1u));
-                                    const uint32_t m3 = nb <= 12 ? 0u : ((1u << (8 * (nb - 12))) - 1u);
-                                    d0 &= m0; d1 &= m1; d2 &= m2; d3 &= m3;
-                                }
-                                bad |= (d0 | d1 | d2 | d3) != 0u;
-                            }
+                    bool bad = false; const int total_m = mcur;
+                    // every lane verifies 16 bases per step; the genome words of the next step are
+                    // requested before the current step is compared (two loads in flight per lane)
+                    int r = 0, t = lane;
+                    uint32_t gw0 = 0, gw1 = 0; int a = 0, nb = 0, gsh = 0;
+                    auto locate = [&](int item) {
+                        while (r + 1 < nrun && (int)run_w[r + 1] <= item) r++;
+                        const int lo = (item - (int)run_w[r]) << 4; const int ct = run_ct[r];
+                        nb = ct - lo; nb = nb > 16 ? 16 : nb;
+                        a = (int)run_q[r] + lo;
+                        const int64_t gb = gbase + run_g[r] + lo; const uint32_t* gp = P.G.g2 + (gb >> 4);
+                        gw0 = gp[0]; gw1 = gp[1]; gsh = (int)(gb & 15) * 2;
+                    };
+                    if (t < nit) locate(t);
+                    while (t < nit) {
+                        const uint32_t c0 = gw0, c1 = gw1; const int ca = a, cnb = nb, csh = gsh;
+                        t += 32;
+                        if (t < nit) locate(t);
+                        const uint32_t* sp = reinterpret_cast<const uint32_t*>(SM.seq) + (ca >> 2); const int sh = (ca & 3) * 8;
+                        const uint32_t x0 = sp[0], x1 = sp[1], x2 = sp[2], x3 = sp[3], x4 = sp[4];
+                        const uint32_t gw = __funnelshift_r(c0, c1, csh);
+                        uint32_t d0 = (__funnelshift_r(x0, x1, sh) & 0xDFDFDFDFu) ^ lut[gw & 255u];
+                        uint32_t d1 = (__funnelshift_r(x1, x2, sh) & 0xDFDFDFDFu) ^ lut[(gw >> 8) & 255u];
+                        uint32_t d2 = (__funnelshift_r(x2, x3, sh) & 0xDFDFDFDFu) ^ lut[(gw >> 16) & 255u];
+                        uint32_t d3 = (__funnelshift_r(x3, x4, sh) & 0xDFDFDFDFu) ^ lut[gw >> 24];
+                        if (cnb < 16) {                                // the item that holds the end of a run
+                            const int bits = 8 * cnb;                  // valid bits of the 128-bit difference
+                            d0 &= bits >= 32 ? ~0u : ((1u << bits) - 1u);
+                            d1 &= bits >= 64 ? ~0u : (bits <= 32 ? 0u : ((1u << (bits - 32)) - 1u));
+                            d2 &= bits >= 96 ? ~0u : (bits <= 64 ? 0u : ((1u << (bits - 64)) - 1u));
+                            d3 &= bits <= 96 ? 0u : ((1u << (bits - 96)) - 1u);
                         }
-                        total_m += ct;
+                        bad |= (d0 | d1 | d2 | d3) != 0u;
                     }
                     if (!__any_sync(FULL, bad)) {                      // every aligned base equals the genome
                         nm = ibases + dbases;
