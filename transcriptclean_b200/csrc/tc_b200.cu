@@ -45,6 +45,12 @@ TC_HD unsigned long long dec_word(uint32_t v, int nd) {
     for (int k = nd - 1; k >= 0; k--) { w |= (unsigned long long)('0' + v % 10) << (8 * k); v /= 10; }
     return w;
 }
+// same for v < 10000 (nd <= 4), without a loop
+TC_HD unsigned long long dec_word4(uint32_t v, int nd) {
+    const uint32_t d3 = v / 1000u, r3 = v - d3 * 1000u, d2 = r3 / 100u, r2 = r3 - d2 * 100u, d1 = r2 / 10u, d0 = r2 - d1 * 10u;
+    const uint32_t w = (d3 | (d2 << 8) | (d1 << 16) | (d0 << 24)) + 0x30303030u;
+    return nd > 0 ? (unsigned long long)(w >> (8 * (4 - nd))) : 0ull;
+}
 TC_HD void write_dec(uint8_t* dst, uint32_t v, int nd) {
     for (int k = nd - 1; k >= 0; k--) { dst[k] = (uint8_t)('0' + v % 10); v /= 10; }
 }
@@ -63,10 +69,9 @@ TC_HD void cig_get(const CigSrc& c, int k, int& op, int32_t& len) {
 #define EMIT_CAP 4096            // reads whose new SEQ fits are staged in shared memory
 #define EMIT_MAXBP 192
 #define EMIT_MAXGI 192
-#define EMIT_GBUF_WORDS 280
 #define EMIT_MAXD 44
 
-#define EMIT_MAXRUN 64
+#define EMIT_MAXRUN 32          // M runs of a read that tier 1 handles (one lane per run)
 struct __align__(16) EmitSmem {  // per warp
     uint8_t seq[EMIT_CAP + 32];
     uint8_t chunk_bp[(EMIT_CAP >> 4) + 16];                             // slice in force at the start of each 16-byte chunk
@@ -76,8 +81,8 @@ struct __align__(16) EmitSmem {  // per warp
             uint16_t gi_out[EMIT_MAXGI]; uint16_t gi_len[EMIT_MAXGI]; int32_t gi_src[EMIT_MAXGI];   // genome slices
         };
         struct {                                                        // while NM/MD is verified (tier 1)
-            uint16_t run_q[EMIT_MAXRUN], run_ct[EMIT_MAXRUN], run_w[EMIT_MAXRUN]; int32_t run_g[EMIT_MAXRUN];   // M runs
-            uint32_t gbuf[EMIT_GBUF_WORDS + 4];                         // their 2-bit genome words
+            uint16_t run_q[EMIT_MAXRUN], run_ct[EMIT_MAXRUN]; int32_t run_g[EMIT_MAXRUN];   // M runs: query offset, length, reference offset
+            int32_t rb_w[EMIT_MAXRUN], rb_coff[EMIT_MAXRUN], rb_goff[EMIT_MAXRUN];         // runs that own whole chunks: first item, chunk and genome offsets
             int32_t d_g[EMIT_MAXD], d_ct[EMIT_MAXD], d_run[EMIT_MAXD];    // D ops: reference offset, length, match run before
         };
     };
@@ -385,16 +390,27 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
             if (sb < 0) { if (lane == 0) { SM.bp_pos[0] = 0; SM.bp_shift[0] = 0; } nbp = 1; }
             else {
                 const u64* segs = ws_seg; int obase = 0; bool bad = false;
+                int last_shift = 0x7fffffff;                           // shift of the latest input slice (none yet)
                 for (int s0 = 0; s0 < ns; s0 += 32) {
                     const int s = s0 + lane; const bool valid = s < ns;
                     const u64 sg = valid ? segs[s] : 0ull;
                     const int len = valid ? (int)seg_len(sg) : 0; const int64_t src = seg_src(sg); const int kind = seg_kind(sg);
                     int total; const int ostart = obase + warp_excl_scan(len, lane, total);
                     const bool isR = valid && kind == 0, isG = valid && kind == 1;
-                    const unsigned mR = __ballot_sync(FULL, isR), mG = __ballot_sync(FULL, isG);
-                    if (isR) {
-                        const int idx = nbp + __popc(mR & lt); const int64_t shift = src - ostart;
-                        if (idx < EMIT_MAXBP && shift >= -32768 && shift <= 32767) { SM.bp_pos[idx] = (uint16_t)ostart; SM.bp_shift[idx] = (int16_t)shift; }
+                    const unsigned mR0 = __ballot_sync(FULL, isR), mG = __ballot_sync(FULL, isG);
+                    // an input slice that continues the previous one's shift (only genome slices lie between them:
+                    // corrected mismatches) is not a new slice - the genome bytes are patched in afterwards
+                    const int64_t shift = src - ostart;
+                    const bool shift_ok = shift >= -32768 && shift <= 32767;
+                    const int sh32 = shift_ok ? (int)shift : 0x7ffffffe;
+                    const unsigned prevR = mR0 & lt;
+                    const int prev_shift = __shfl_sync(FULL, sh32, prevR ? 31 - __clz(prevR) : lane);
+                    const bool isBP = isR && (!shift_ok || sh32 != (prevR ? prev_shift : last_shift));
+                    const unsigned mR = __ballot_sync(FULL, isBP);
+                    if (mR0) last_shift = __shfl_sync(FULL, sh32, 31 - __clz(mR0));
+                    if (isBP) {
+                        const int idx = nbp + __popc(mR & lt);
+                        if (idx < EMIT_MAXBP && shift_ok) { SM.bp_pos[idx] = (uint16_t)ostart; SM.bp_shift[idx] = (int16_t)shift; }
                         else bad = true;
                     }
                     if (isG) {
@@ -486,17 +502,22 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
             int nm = 0, len = 0; int64_t off = 0; bool none = false; bool done = false;
             if (fast && ncig <= 32 * 4) {
                 // tier 1: run list (query offset, reference offset, length) of the M ops, lane-parallel
-                uint16_t* run_q = SM.run_q; uint16_t* run_ct = SM.run_ct; uint16_t* run_w = SM.run_w; int32_t* run_g = SM.run_g;
-                int nrun = 0, qcur = 0, nD = 0, ibases = 0, dbases = 0, mcur = 0, m_at_last_d = 0; int64_t gcur = 0; bool ovf = false;
+                uint16_t* run_q = SM.run_q; uint16_t* run_ct = SM.run_ct; int32_t* run_g = SM.run_g;
+                int nrun = 0, qcur = 0, nD = 0, ibases = 0, dbases = 0, mcur = 0, m_at_last_d = 0, qsum = 0; int64_t gcur = 0; bool ovf = false;
                 for (int k0 = 0; k0 < ncig; k0 += 32) {
                     int op = 0; int32_t ct = 0;
                     if (k0 + lane < ncig) cig_get(cs, k0 + lane, op, ct);
                     const int qadv = (op == 'M' || op == 'I' || op == 'S') ? ct : 0;
                     const int gadv = (op == 'M' || op == 'D' || op == 'N' || op == 'H') ? ct : 0;
-                    int qtot, gtot; const int qs = warp_excl_scan(qadv, lane, qtot); const int gs = warp_excl_scan(gadv, lane, gtot);
+                    // query offsets and matched-base counts share one scan (16 bits each: both are bounded by
+                    // the query length, which the REDUX total below checks against out_len <= EMIT_CAP)
+                    qsum += __reduce_add_sync(FULL, qadv);
+                    int qmtot, gtot; const int qm = warp_excl_scan((qadv << 16) | (op == 'M' ? (ct & 0xffff) : 0), lane, qmtot);
+                    const int gs = warp_excl_scan(gadv, lane, gtot);
+                    const int qs = (int)((unsigned)qm >> 16), ms = qm & 0xffff;              // ms: matched bases before this op
+                    const int qtot = (int)((unsigned)qmtot >> 16), mtot = qmtot & 0xffff;
                     const bool isM = op == 'M' && ct > 0, isD = op == 'D';
                     const unsigned mM = __ballot_sync(FULL, isM), mD = __ballot_sync(FULL, isD);
-                    int mtot; const int ms = warp_excl_scan(op == 'M' ? ct : 0, lane, mtot);   // matched bases before this op
                     {   // MD token of a D op: <matches since the previous token>^<bases>
                         const unsigned prev = mD & lt;                  // nearest earlier D in this round, else the carried one
                         const int cand = __shfl_sync(FULL, mcur + ms, prev ? 31 - __clz(prev) : lane);
@@ -516,65 +537,79 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
                         else ovf = true;
                         // literal runs (N, IUPAC) under this M run?  (blocks of 256 bases; a run spans at most 17)
                         const int64_t ga = gbase + gcur + gs;
-                        for (int64_t b = ga >> 8; b <= (ga + ct - 1) >> 8; b++) ovf |= (P.G.excblk[b >> 5] >> (b & 31)) & 1u;
+                        const uint32_t b1 = (uint32_t)((ga + ct - 1) >> 8);
+                        for (uint32_t b = (uint32_t)(ga >> 8); b <= b1; b++) ovf |= (P.G.excblk[b >> 5] >> (b & 31)) & 1u;
                     }
                     nrun += __popc(mM); qcur += qtot; gcur += gtot; mcur += mtot;
                 }
-#pragma unroll
-                for (int d = 16; d; d >>= 1) { ibases += __shfl_xor_sync(FULL, ibases, d); dbases += __shfl_xor_sync(FULL, dbases, d); }
-                const bool careful = pos < 1 || pos + gcur - 1 > clen;
-                bool tier1 = !careful && nD <= EMIT_MAXD && nrun <= EMIT_MAXRUN && !__any_sync(FULL, ovf);
+                ibases = __reduce_add_sync(FULL, ibases); dbases = __reduce_add_sync(FULL, dbases);
+                const bool careful = pos < 1 || pos + gcur - 1 > clen || gbase < 16;   // (chunks may start up to 15 bases before a run)
+                bool tier1 = !careful && qsum == out_len && nD <= EMIT_MAXD && nrun <= EMIT_MAXRUN && !__any_sync(FULL, ovf);
                 if (tier1) {
-                    // flat item space: item = 16 bases of one M run; run_w[r] = first item of run r
-                    __syncwarp();
-                    int nit = 0;
-                    for (int r0 = 0; r0 < nrun; r0 += 32) {
-                        const int r = r0 + lane;
-                        int tot; const int io = nit + warp_excl_scan(r < nrun ? ((int)run_ct[r] + 15) >> 4 : 0, lane, tot);
-                        if (r < nrun) run_w[r] = (uint16_t)io;
-                        nit += tot;
-                    }
+                    // The staged SEQ is verified in aligned 16-byte chunks (one LDS.128 per item; the 2-bit genome
+                    // words carry the shift).  Pass 1: chunks that lie wholly inside an M run, as one flat item
+                    // space over the runs that have any (lane r keeps run r's item offset / chunk offset / genome
+                    // offset; an item finds its run with REDUX.OR + POPC and fetches the two offsets by shuffle).
+                    // Pass 2: the partial chunk at the head and at the tail of every run, one lane each, masked.
                     __syncwarp();
                     bool bad = false; const int total_m = mcur;
-                    // every lane verifies 16 bases per step; the genome words of the next step are
-                    // requested before the current step is compared (two loads in flight per lane)
-                    int r = 0, t = lane;
-                    uint32_t gw0 = 0, gw1 = 0; int a = 0, nb = 0, gsh = 0;
-                    auto locate = [&](int item) {
-                        while (r + 1 < nrun && (int)run_w[r + 1] <= item) r++;
-                        const int lo = (item - (int)run_w[r]) << 4; const int ct = run_ct[r];
-                        nb = ct - lo; nb = nb > 16 ? 16 : nb;
-                        a = (int)run_q[r] + lo;
-                        const int64_t gb = gbase + run_g[r] + lo; const uint32_t* gp = P.G.g2 + (gb >> 4);
-                        gw0 = gp[0]; gw1 = gp[1]; gsh = (int)(gb & 15) * 2;
-                    };
-                    if (t < nit) locate(t);
-                    while (t < nit) {
-                        const uint32_t c0 = gw0, c1 = gw1; const int ca = a, cnb = nb, csh = gsh;
-                        t += 32;
-                        if (t < nit) locate(t);
-                        const uint32_t* sp = reinterpret_cast<const uint32_t*>(SM.seq) + (ca >> 2); const int sh = (ca & 3) * 8;
-                        const uint32_t x0 = sp[0], x1 = sp[1], x2 = sp[2], x3 = sp[3], x4 = sp[4];
-                        const uint32_t gw = __funnelshift_r(c0, c1, csh);
-                        uint32_t d0 = (__funnelshift_r(x0, x1, sh) & 0xDFDFDFDFu) ^ lut[gw & 255u];
-                        uint32_t d1 = (__funnelshift_r(x1, x2, sh) & 0xDFDFDFDFu) ^ lut[(gw >> 8) & 255u];
-                        uint32_t d2 = (__funnelshift_r(x2, x3, sh) & 0xDFDFDFDFu) ^ lut[(gw >> 16) & 255u];
-                        uint32_t d3 = (__funnelshift_r(x3, x4, sh) & 0xDFDFDFDFu) ^ lut[gw >> 24];
-                        if (cnb < 16) {                                // the item that holds the end of a run
-                            const int bits = 8 * cnb;                  // valid bits of the 128-bit difference
-                            d0 &= bits >= 32 ? ~0u : ((1u << bits) - 1u);
-                            d1 &= bits >= 64 ? ~0u : (bits <= 32 ? 0u : ((1u << (bits - 32)) - 1u));
-                            d2 &= bits >= 96 ? ~0u : (bits <= 64 ? 0u : ((1u << (bits - 64)) - 1u));
-                            d3 &= bits <= 96 ? 0u : ((1u << (bits - 96)) - 1u);
+                    int my_w = 0x7fffffff, my_coff = 0, my_goff = 0, nit = 0;
+                    {
+                        int cnt = 0, c0 = 0, q0 = 0, g0 = 0;
+                        if (lane < nrun) { q0 = run_q[lane]; g0 = run_g[lane]; c0 = (q0 + 15) >> 4; cnt = ((q0 + (int)run_ct[lane]) >> 4) - c0; cnt = cnt < 0 ? 0 : cnt; }
+                        const int w = warp_excl_scan(cnt, lane, nit);
+                        const unsigned has = __ballot_sync(FULL, cnt > 0);
+                        if (cnt > 0) { const int k = __popc(has & lt); SM.rb_w[k] = w; SM.rb_coff[k] = c0 - w; SM.rb_goff[k] = g0 - q0; }
+                        __syncwarp();
+                        if (lane < __popc(has)) { my_w = SM.rb_w[lane]; my_coff = SM.rb_coff[lane]; my_goff = SM.rb_goff[lane]; }
+                    }
+                    int rbase = 0;
+                    for (int t0 = 0; t0 < nit; t0 += 32) {
+                        const int t = t0 + lane;
+                        const unsigned word = __reduce_or_sync(FULL, (my_w >= t0 && my_w < t0 + 32) ? 1u << (my_w - t0) : 0u);
+                        int r = rbase + __popc(word & (0xffffffffu >> (31 - lane))) - 1;
+                        rbase += __popc(word);
+                        const int coff = __shfl_sync(FULL, my_coff, r & 31), goff = __shfl_sync(FULL, my_goff, r & 31);
+                        if (t < nit) {
+                            const int p = (t + coff) << 4;                       // chunk start (query offset)
+                            const int64_t gb = gbase + p + goff;                 // plane index under chunk byte 0
+                            const uint32_t* gp = P.G.g2 + (gb >> 4);
+                            const uint32_t gw = __funnelshift_r(gp[0], gp[1], (int)(gb & 15) * 2);
+                            const uint4 x = *reinterpret_cast<const uint4*>(SM.seq + p);
+                            const uint32_t d0 = (x.x & 0xDFDFDFDFu) ^ lut[gw & 255u], d1 = (x.y & 0xDFDFDFDFu) ^ lut[(gw >> 8) & 255u];
+                            const uint32_t d2 = (x.z & 0xDFDFDFDFu) ^ lut[(gw >> 16) & 255u], d3 = (x.w & 0xDFDFDFDFu) ^ lut[gw >> 24];
+                            bad |= (d0 | d1 | d2 | d3) != 0u;
                         }
-                        bad |= (d0 | d1 | d2 | d3) != 0u;
+                    }
+                    for (int j = lane; j < 2 * nrun; j += 32) {
+                        const int r = j >> 1, a = run_q[r], b = a + (int)run_ct[r];
+                        const bool head = (a & 15) != 0;
+                        int s, e;
+                        if (!(j & 1)) { s = a; e = (a | 15) + 1; e = e < b ? e : b; if (!head) e = s; }
+                        else { s = b & ~15; e = b; if (!(b & 15) || (head && (b >> 4) == (a >> 4))) e = s; }
+                        if (e > s) {
+                            const int p = s & ~15, l8 = 8 * (s - p), h8 = 8 * (e - p);   // chunk bytes [lo, hi) count
+                            const int64_t gb = gbase + run_g[r] + (p - a);
+                            const uint32_t* gp = P.G.g2 + (gb >> 4);
+                            const uint32_t gw = __funnelshift_r(gp[0], gp[1], (int)(gb & 15) * 2);
+                            const uint4 x = *reinterpret_cast<const uint4*>(SM.seq + p);
+                            uint32_t d0 = (x.x & 0xDFDFDFDFu) ^ lut[gw & 255u], d1 = (x.y & 0xDFDFDFDFu) ^ lut[(gw >> 8) & 255u];
+                            uint32_t d2 = (x.z & 0xDFDFDFDFu) ^ lut[(gw >> 16) & 255u], d3 = (x.w & 0xDFDFDFDFu) ^ lut[gw >> 24];
+#define TC_BITS_BELOW(b, w) ((b) >= 32 * (w) + 32 ? ~0u : ((b) <= 32 * (w) ? 0u : ((1u << ((b) - 32 * (w))) - 1u)))
+                            d0 &= TC_BITS_BELOW(h8, 0) & ~TC_BITS_BELOW(l8, 0);
+                            d1 &= TC_BITS_BELOW(h8, 1) & ~TC_BITS_BELOW(l8, 1);
+                            d2 &= TC_BITS_BELOW(h8, 2) & ~TC_BITS_BELOW(l8, 2);
+                            d3 &= TC_BITS_BELOW(h8, 3) & ~TC_BITS_BELOW(l8, 3);
+#undef TC_BITS_BELOW
+                            bad |= (d0 | d1 | d2 | d3) != 0u;
+                        }
                     }
                     if (!__any_sync(FULL, bad)) {                      // every aligned base equals the genome
                         nm = ibases + dbases;
                         if (nD == 0) {                                 // MD is one number, at most 5 digits: the read's inline slot
                             len = total_m > 0 ? ndigits((uint32_t)total_m) : 0;
                             off = O.md_inline + 8 * i;
-                            if (lane == 0) *reinterpret_cast<unsigned long long*>(O.md_pool + off) = dec_word((uint32_t)total_m, len);   // slot is 8-byte aligned
+                            if (lane == 0) *reinterpret_cast<unsigned long long*>(O.md_pool + off) = dec_word4((uint32_t)total_m, len);   // slot is 8-byte aligned; total_m <= EMIT_CAP
                         } else {                                       // one token per D op, then the trailing run
                             __syncwarp();
                             int32_t* d_off = SM.run_g;                 // the run list is no longer needed
