@@ -245,23 +245,28 @@ __device__ __forceinline__ void nmmd_to_pool(const GenomeDev& G, const uint8_t* 
     }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_init(Params P, InitDev I, int32_t* nm_init) {
+// status word of every read (thread per read); reads that lack NM or MD (tr.py:47-48) are listed for k_init_nmmd
+__global__ void k_init(Params P, int32_t* list, unsigned* count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.B.n) return;
+    const int cls = read_class(P.B.flag[i], P.B.chrom[i]);
+    const uint8_t tags = P.B.tags[i];
+    P.W.status[i] = (uint32_t)cls;
+    if (cls == 0 && (!(tags & TAG_NM) || !(tags & TAG_MD))) list[atomicAdd(count, 1u)] = (int32_t)i;
+}
+// NM/MD bootstrap of the listed reads, one warp per read
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_init_nmmd(Params P, InitDev I, int32_t* nm_init, const int32_t* list, const unsigned* count) {
     const int lane = threadIdx.x & 31;
-    const int64_t nw = (int64_t)gridDim.x * WARPS_PER_BLOCK;
-    for (int64_t i = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); i < P.B.n; i += nw) {
-        const int cls = read_class(P.B.flag[i], P.B.chrom[i]);
-        uint32_t st = (uint32_t)cls;
-        const uint8_t tags = P.B.tags[i];
-        if (cls == 0 && (!(tags & TAG_NM) || !(tags & TAG_MD))) {
-            CigSrc cs; cs.packed = 0; cs.op = P.B.cig_op + P.B.cig_off[i]; cs.len = P.B.cig_len + P.B.cig_off[i];
-            cs.n = (int)(P.B.cig_off[i + 1] - P.B.cig_off[i]);
-            int nm, len; int64_t off; bool none;
-            nmmd_to_pool<false>(P.G, P.B.seq + P.B.seq_off[i], 0, cs, P.B.chrom[i], P.B.pos[i], lane, I.cursor, I.cap, I.pool, -1, nm, len, off, none);
-            st |= TC_ST_NMMD_DEVICE;
-            if (none) { st |= TC_ST_NMMD_NONE; nm = 0; }
-            if (lane == 0) { P.W.md_init_off[i] = off < 0 ? 0 : off; P.W.md_init_len[i] = off < 0 ? 0 : len; nm_init[i] = nm; }
-        }
-        if (lane == 0) P.W.status[i] = st;
+    const int64_t nw = (int64_t)gridDim.x * WARPS_PER_BLOCK, nl = (int64_t)*count;
+    for (int64_t t = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); t < nl; t += nw) {
+        const int64_t i = list[t];
+        CigSrc cs; cs.packed = 0; cs.op = P.B.cig_op + P.B.cig_off[i]; cs.len = P.B.cig_len + P.B.cig_off[i];
+        cs.n = (int)(P.B.cig_off[i + 1] - P.B.cig_off[i]);
+        int nm, len; int64_t off; bool none;
+        nmmd_to_pool<false>(P.G, P.B.seq + P.B.seq_off[i], 0, cs, P.B.chrom[i], P.B.pos[i], lane, I.cursor, I.cap, I.pool, -1, nm, len, off, none);
+        uint32_t st = P.W.status[i] | TC_ST_NMMD_DEVICE;
+        if (none) { st |= TC_ST_NMMD_NONE; nm = 0; }
+        if (lane == 0) { P.W.md_init_off[i] = off < 0 ? 0 : off; P.W.md_init_len[i] = off < 0 ? 0 : len; nm_init[i] = nm; P.W.status[i] = st; }
     }
 }
 
@@ -766,7 +771,7 @@ struct tc_ctx {
 #endif
     bool have_genome = false;
     DevBuf g2, lo1, excblk, chrom_off, chrom_len, exc_start, exc_end, exc_byte;
-    DevBuf don_s, acc_s, don_u, acc_u, ann_k1, ann_k2;
+    DevBuf don_s, acc_s, don_u, acc_u, ann_k1, ann_k2, sj_rng;
     DevBuf snp_key, snp_alt, ins_key, ins_size, ins_aoff, ins_bytes, del_key, del_size;
     GenomeDev G; SjDev S; VarDev V;
     Slot slot[2];
@@ -954,7 +959,20 @@ int tc_ctx_load_junctions(tc_ctx* ctx, int64_t n_don_s, const uint64_t* don_s, i
     if (be_h2d(ctx, st, ctx->don_s, 0, don_s, (size_t)n_don_s * 8) || be_h2d(ctx, st, ctx->acc_s, 0, acc_s, (size_t)n_acc_s * 8) ||
         be_h2d(ctx, st, ctx->don_u, 0, don_u, (size_t)n_don_u * 8) || be_h2d(ctx, st, ctx->acc_u, 0, acc_u, (size_t)n_acc_u * 8) ||
         be_h2d(ctx, st, ctx->ann_k1, 0, k1, (size_t)n_annot * 8) || be_h2d(ctx, st, ctx->ann_k2, 0, k2, (size_t)n_annot * 8) || be_sync(ctx, st)) return TC_E_CUDA;
+    // first row of every chromosome(/strand) prefix in the four site tables, so that the kernels
+    // search only inside the prefix's rows: rng[t] has np+1 entries, prefix p owns [rng[t][p], rng[t][p+1])
+    const uint64_t* tabs[4] = {don_s, acc_s, don_u, acc_u}; const int64_t ns[4] = {n_don_s, n_acc_s, n_don_u, n_acc_u};
+    int64_t np = 0;
+    for (int t = 0; t < 4; t++) if (ns[t] > 0) { int64_t top = (int64_t)(tabs[t][ns[t] - 1] >> 32) + 1; if (top > np) np = top; }
+    std::vector<int32_t> rng((size_t)(4 * (np + 1)), 0);
+    for (int t = 0; t < 4; t++) {
+        int32_t* r = rng.data() + (size_t)t * (np + 1); int64_t k = 0;
+        for (int64_t pfx = 0; pfx <= np; pfx++) { while (k < ns[t] && (int64_t)(tabs[t][k] >> 32) < pfx) k++; r[pfx] = (int32_t)k; }
+    }
+    if (be_h2d(ctx, st, ctx->sj_rng, 0, rng.data(), rng.size() * 4) || be_sync(ctx, st)) return TC_E_CUDA;
     SjDev& S = ctx->S;
+    S.n_prefix = (int32_t)np;
+    S.rng_don_s = (const int32_t*)ctx->sj_rng.p; S.rng_acc_s = S.rng_don_s + (np + 1); S.rng_don_u = S.rng_acc_s + (np + 1); S.rng_acc_u = S.rng_don_u + (np + 1);
     S.don_s = (const u64*)ctx->don_s.p; S.acc_s = (const u64*)ctx->acc_s.p; S.don_u = (const u64*)ctx->don_u.p; S.acc_u = (const u64*)ctx->acc_u.p;
     S.ann_k1 = (const u64*)ctx->ann_k1.p; S.ann_k2 = (const u64*)ctx->ann_k2.p;
     S.n_don_s = n_don_s; S.n_acc_s = n_acc_s; S.n_don_u = n_don_u; S.n_acc_u = n_acc_u; S.n_ann = n_annot;
@@ -1119,7 +1137,10 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
         if (be_zero(ctx, st, cur, 64)) return TC_E_CUDA;
         InitDev I; I.pool = (uint8_t*)S.init_pool.p; I.cursor = cur; I.cap = init_cap;
         P.W.md_init_pool = I.pool; S.W.md_init_pool = I.pool;
-        k_init<<<gw, WARPS_PER_BLOCK * 32, 0, st>>>(P, I, S.W.nm_init); ctx->tm.launches++;
+        CK(S.w_fix_list.ensure((size_t)(n + 1) * 4));                // (the junction stage reuses this list later)
+        k_init<<<gb, TPB, 0, st>>>(P, (int32_t*)S.w_fix_list.p, (unsigned*)(cur + 2)); ctx->tm.launches++;
+        CK(cudaGetLastError());
+        k_init_nmmd<<<gw, WARPS_PER_BLOCK * 32, 0, st>>>(P, I, S.W.nm_init, (const int32_t*)S.w_fix_list.p, (const unsigned*)(cur + 2)); ctx->tm.launches++;
         CK(cudaGetLastError());
         k_measure<<<gb, TPB, 0, st>>>(P); ctx->tm.launches++;        // measure only needs lengths: safe before the overflow check
         CK(cudaGetLastError());

@@ -37,6 +37,8 @@ struct GenomeDev {
 struct SjDev {
     const u64 *don_s, *acc_s, *don_u, *acc_u, *ann_k1, *ann_k2;
     int64_t n_don_s, n_acc_s, n_don_u, n_acc_u, n_ann;
+    const int32_t *rng_don_s, *rng_acc_s, *rng_don_u, *rng_acc_u;   // first row of each key prefix (n_prefix + 1 entries)
+    int32_t n_prefix;
 };
 
 struct VarDev {
@@ -161,9 +163,9 @@ TC_HD int64_t lower_bound_u64(const u64* a, int64_t lo, int64_t hi, u64 key) {
 
 // nearest annotated site (pyranges.nearest as used at TC.py:1241-1259).  false = nothing on this
 // chromosome/strand -> the reference's .iloc[0] raises (Q23).
-TC_HD bool sj_nearest(const u64* tab, int64_t n, u64 prefix, int64_t q, bool tie_right, int& dist) {
-    int64_t lo = lower_bound_u64(tab, 0, n, prefix << 32);
-    int64_t hi = lower_bound_u64(tab, lo, n, (prefix + 1) << 32);
+TC_HD bool sj_nearest(const u64* tab, const int32_t* rng, int32_t n_prefix, u64 prefix, int64_t q, bool tie_right, int& dist) {
+    if (prefix >= (u64)n_prefix) return false;
+    const int64_t lo = rng[prefix], hi = rng[prefix + 1];
     if (lo == hi) return false;
     int64_t i = lower_bound_u64(tab, lo, hi, (prefix << 32) | (u64)(uint32_t)q);
     int64_t best;
@@ -349,8 +351,8 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
     const int64_t goff = P.G.chrom_off[chrom] - 1;       // plane index of 1-based position p is goff + p
     const uint8_t* seq = B.seq + B.seq_off[i];
     int64_t q = 0, g = B.pos[i];
-    int nte = 0; int cM = 0, uM = 0, cI = 0, uI = 0, vI = 0, cD = 0, uD = 0, vD = 0;
-    int nteM = 0, nteI = 0, nteD = 0; int32_t ins_removed = 0; bool sawD = false;
+    int nte = 0; u64 cnt_cor = 0, cnt_var = 0, cnt_big = 0;   // 21-bit fields: mismatches, insertions, deletions
+    int32_t ins_removed = 0; bool sawD = false;
     // merge state (tr.py:171-211)
     int64_t ci = B.cig_off[i]; const int64_t cend = B.cig_off[i + 1];
     int32_t crem = ci < cend ? B.cig_len[ci] : 0;
@@ -375,50 +377,47 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
             if (ci >= cend) break;
             op = B.cig_op[ci]; ct = B.cig_len[ci]; ci++;
         }
-        switch (op) {
-        case 'M':
-            E.push(0, q, ct); E.match(ct); q += ct; g += ct; break;
-        case 'X':                                                     // only produced by the MD side
-            if (P.V.n_snp > 0 && snp_match(P.V, chrom, g, seq[q])) {   // TC.py:1115-1130 (Q11); SEQ is only touched when a catalogue exists
-                te_put(v.te, nte, 0, (int32_t)g, 0, ct, 1, 1); uM++; nteM++;
-                E.push(0, q, ct);
-            } else {
-                te_put(v.te, nte, 0, (int32_t)g, 0, ct, 0, 0); cM++; nteM++;
-                E.push(1, goff + g, ct);                              // genome bases verbatim (Q6)
+        // One straight-line body for every op kind (lanes of a warp sit on different kinds, so a
+        // switch with six private copies of push / te_put / op would be executed six times over):
+        //   M            SEQ slice, joins the match run
+        //   X            TE row; SNP catalogue hit -> kept as is (TC.py:1115-1130, Q11), else genome bases verbatim (Q6)
+        //   S            CIGAR op + SEQ slice
+        //   I (indels)   TE row; too long / catalogue hit -> kept, else dropped (TC.py:898-940)
+        //   D (indels)   TE row; too long / catalogue hit -> kept, else filled from the genome (TC.py:1007-1051)
+        //   N, H         CIGAR op;   anything else vanishes (Q10)
+        const bool isM = op == 'M', isX = op == 'X', isS = op == 'S', isI = op == 'I', isD = op == 'D', isNH = op == 'N' || op == 'H';
+        const bool edit = isX || ((isI || isD) && indel);                  // gets a TE row
+        bool variant = false, toolarge = false;
+        if (edit) {
+            if (isX) { if (P.V.n_snp > 0) variant = snp_match(P.V, chrom, g, seq[q]); }   // SEQ is only touched when a catalogue exists
+            else {
+                toolarge = ct > O.max_len_indel;
+                if (!toolarge) variant = isI ? (P.V.n_ins > 0 && ins_match(P.V, chrom, g - 1, ct, seq + q)) : (P.V.n_del > 0 && del_match(P.V, chrom, g - 1, ct));
             }
-            E.match(ct); q += ct; g += ct; break;
-        case 'S':
-            E.op('S', ct); E.push(0, q, ct); q += ct; break;
-        case 'I': {
-            bool keep = true;
-            if (indel) {                                              // TC.py:898-940
-                nteI++;
-                if (ct > O.max_len_indel) { te_put(v.te, nte, 1, (int32_t)(g - 1), (int32_t)(g + ct - 1), ct, 1, 2); uI++; }
-                else if (ins_match(P.V, chrom, g - 1, ct, seq + q)) { te_put(v.te, nte, 1, (int32_t)(g - 1), (int32_t)(g + ct - 1), ct, 1, 1); vI++; }
-                else { te_put(v.te, nte, 1, (int32_t)(g - 1), (int32_t)(g + ct - 1), ct, 0, 0); cI++; keep = false; ins_removed += ct; }
-            }
-            if (keep) { E.op('I', ct); E.push(0, q, ct); }
-            q += ct; break; }
-        case 'D': {
-            bool keep = true; sawD = true;
-            if (indel) {                                              // TC.py:1007-1051
-                nteD++;
-                if (ct > O.max_len_indel) { te_put(v.te, nte, 2, (int32_t)(g - 1), (int32_t)(g + ct - 1), ct, 1, 2); uD++; }
-                else if (del_match(P.V, chrom, g - 1, ct)) { te_put(v.te, nte, 2, (int32_t)(g - 1), (int32_t)(g + ct - 1), ct, 1, 1); vD++; }
-                else { te_put(v.te, nte, 2, (int32_t)(g - 1), (int32_t)(g + ct - 1), ct, 0, 0); cD++; keep = false; }
-            }
-            if (keep) E.op('D', ct); else { E.push(1, goff + g, ct); E.match(ct); }
-            g += ct; break; }
-        case 'N': case 'H':
-            E.op(op, ct); g += ct; break;
-        default: break;                                               // other ops vanish (Q10)
+            const bool kept = variant || toolarge;
+            te_put(v.te, nte, isX ? 0 : isI ? 1 : 2, (int32_t)(isX ? g : g - 1), isX ? 0 : (int32_t)(g + ct - 1), ct, kept ? 1 : 0, toolarge ? 2 : variant ? 1 : 0);
+            const u64 inc = 1ull << (isX ? 0 : isI ? 21 : 42);
+            if (toolarge) cnt_big += inc; else if (variant) cnt_var += inc; else cnt_cor += inc;
         }
+        const bool corrected = edit && !variant && !toolarge;
+        sawD |= isD;
+        if (isI && corrected) ins_removed += ct;
+        const bool from_genome = (isX || isD) && corrected;
+        if (isM || isS || (isX && !corrected) || (isI && !corrected) || from_genome) E.push(from_genome ? 1 : 0, from_genome ? goff + g : q, ct);
+        if (isM || isX || (isD && corrected)) E.match(ct);
+        else if (isS || isNH || ((isI || isD) && !corrected)) E.op(op, ct);
+        if (isM || isX || isS || isI) q += ct;
+        if (isM || isX || isD || isNH) g += ct;
     }
     if (fail) {                                                       // whole-read fallback (Q13): stage 1 raised
         W.status[i] = st | TC_ST_FALLBACK;                            // before stages 2-3 zeroed their counters
         return;
     }
     E.flush();
+    const int cM = (int)(cnt_cor & 0x1fffff), cI = (int)((cnt_cor >> 21) & 0x1fffff), cD = (int)((cnt_cor >> 42) & 0x1fffff);
+    const int uM = (int)(cnt_var & 0x1fffff), vI = (int)((cnt_var >> 21) & 0x1fffff), vD = (int)((cnt_var >> 42) & 0x1fffff);
+    const int uI = (int)((cnt_big >> 21) & 0x1fffff), uD = (int)((cnt_big >> 42) & 0x1fffff);
+    const int nteM = cM + uM, nteI = cI + uI + vI, nteD = cD + uD + vD;
     C[TC_C_COR_MM] = O.correct_mismatches ? cM : -1; C[TC_C_UNC_MM] = O.correct_mismatches ? uM : -1;
     if (indel) { C[TC_C_COR_INS] = cI; C[TC_C_UNC_INS] = uI; C[TC_C_VAR_INS] = vI;
                  C[TC_C_COR_DEL] = cD; C[TC_C_UNC_DEL] = uD; C[TC_C_VAR_DEL] = vD; }
@@ -698,12 +697,12 @@ TC_HD void junction_fix_read(const Params& P, int64_t i) {
                 const int ds = strand == 0 ? 0 : 1, as = 1 - ds;       // sj.py:29-41
                 int d_don, d_acc; bool ok_t;
                 if (O.sj_ignore_strand) {
-                    ok_t = sj_nearest(P.S.don_u, P.S.n_don_u, (u64)chrom, (int64_t)r[ds] - 1, tie_right, d_don) &&
-                           sj_nearest(P.S.acc_u, P.S.n_acc_u, (u64)chrom, (int64_t)r[as] - 1, tie_right, d_acc);
+                    ok_t = sj_nearest(P.S.don_u, P.S.rng_don_u, P.S.n_prefix, (u64)chrom, (int64_t)r[ds] - 1, tie_right, d_don) &&
+                           sj_nearest(P.S.acc_u, P.S.rng_acc_u, P.S.n_prefix, (u64)chrom, (int64_t)r[as] - 1, tie_right, d_acc);
                 } else {
                     u64 pre = ((u64)chrom << 1) | (u64)strand;
-                    ok_t = sj_nearest(P.S.don_s, P.S.n_don_s, pre, (int64_t)r[ds] - 1, tie_right, d_don) &&
-                           sj_nearest(P.S.acc_s, P.S.n_acc_s, pre, (int64_t)r[as] - 1, tie_right, d_acc);
+                    ok_t = sj_nearest(P.S.don_s, P.S.rng_don_s, P.S.n_prefix, pre, (int64_t)r[ds] - 1, tie_right, d_don) &&
+                           sj_nearest(P.S.acc_s, P.S.rng_acc_s, P.S.n_prefix, pre, (int64_t)r[as] - 1, tie_right, d_acc);
                 }
                 if (!ok_t) { whole_fail = true; break; }              // Q23: raises outside the inner try
                 int ad = d_don < 0 ? -d_don : d_don, aa = d_acc < 0 ? -d_acc : d_acc;
