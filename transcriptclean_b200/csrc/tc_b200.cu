@@ -735,9 +735,9 @@ static void host_nmmd(const GenomeDev& G, const uint8_t* seq, const CigSrc& cs, 
 // Everything that belongs to one batch (or one chunk of a pipelined batch) on the device.
 struct Slot {
     DevBuf b_flag, b_chrom, b_pos, b_tags, b_seq_off, b_seq, b_cig_off, b_cig_op, b_cig_len, b_md_off, b_md, b_ji_off, b_ji;
-    BatchDev B; int64_t n = 0, n_seq = 0, n_cig = 0, n_md = 0, n_ji = 0;
+    BatchDev B; int64_t n = 0, n_seq = 0, n_cig = 0, n_md = 0, n_ji = 0, md_base = 0;
     int64_t seq_lo_word = 0, seq_hi_word = 0;       // words of B.seq (as uint32) that may be dereferenced
-    DevBuf w_status, w_counters, w_md_init_off, w_md_init_len, w_nm_init, w_n_mdtok, w_n_jn, w_mflags,
+    DevBuf w_status, w_counters, w_md_init_off, w_md_init_len, w_nm_init, w_n_mdtok, w_md_tok, w_n_jn, w_mflags,
         w_cig_cap, w_seg_cap, w_te_cap, w_ws_off, w_ws, w_cig_buf, w_n_cig_cur, w_seg_buf, w_n_seg_cur, w_n_te,
         w_te_cnt, w_nm_extra, w_refresh, w_o_seq, w_o_cig, w_o_te, w_o_jn, w_seq_len, w_plan, w_fix_list, init_pool, cursors, scan_tmp;
     WorkDev W;
@@ -751,7 +751,7 @@ struct Slot {
 #endif
     void release() {
         DevBuf* d[] = {&b_flag, &b_chrom, &b_pos, &b_tags, &b_seq_off, &b_seq, &b_cig_off, &b_cig_op, &b_cig_len, &b_md_off, &b_md, &b_ji_off, &b_ji,
-                       &w_status, &w_counters, &w_md_init_off, &w_md_init_len, &w_nm_init, &w_n_mdtok, &w_n_jn, &w_mflags, &w_cig_cap, &w_seg_cap,
+                       &w_status, &w_counters, &w_md_init_off, &w_md_init_len, &w_nm_init, &w_n_mdtok, &w_md_tok, &w_n_jn, &w_mflags, &w_cig_cap, &w_seg_cap,
                        &w_te_cap, &w_ws_off, &w_ws, &w_cig_buf, &w_n_cig_cur, &w_seg_buf, &w_n_seg_cur, &w_n_te, &w_te_cnt, &w_nm_extra, &w_refresh,
                        &w_o_seq, &w_o_cig, &w_o_te, &w_o_jn, &w_seq_len, &w_plan, &w_fix_list, &init_pool, &cursors, &scan_tmp,
                        &o_nm, &o_md_off, &o_md_len, &o_md_pool, &o_seq, &o_cig_op, &o_cig_len, &o_te, &o_jm, &o_ji};
@@ -771,7 +771,7 @@ struct tc_ctx {
 #endif
     bool have_genome = false;
     DevBuf g2, lo1, excblk, chrom_off, chrom_len, exc_start, exc_end, exc_byte;
-    DevBuf don_s, acc_s, don_u, acc_u, ann_k1, ann_k2, sj_rng;
+    DevBuf don_s, acc_s, don_u, acc_u, ann_k1, ann_k2, sj_rng, ann_hash;
     DevBuf snp_key, snp_alt, ins_key, ins_size, ins_aoff, ins_bytes, del_key, del_size;
     GenomeDev G; SjDev S; VarDev V;
     Slot slot[2];
@@ -970,7 +970,17 @@ int tc_ctx_load_junctions(tc_ctx* ctx, int64_t n_don_s, const uint64_t* don_s, i
         for (int64_t pfx = 0; pfx <= np; pfx++) { while (k < ns[t] && (int64_t)(tabs[t][k] >> 32) < pfx) k++; r[pfx] = (int32_t)k; }
     }
     if (be_h2d(ctx, st, ctx->sj_rng, 0, rng.data(), rng.size() * 4) || be_sync(ctx, st)) return TC_E_CUDA;
+    // annotated set as an open-addressing table (load factor <= 1/2, linear probing)
+    uint32_t slots = 16; while ((int64_t)slots < 2 * n_annot) slots <<= 1;
+    std::vector<AnnSlot> tab(slots); for (auto& e : tab) { e.k1 = ~0ull; e.k2 = 0; }
+    for (int64_t k = 0; k < n_annot; k++) {
+        uint32_t h = ann_hash_of(k1[k], k2[k]) & (slots - 1);
+        while (tab[h].k1 != ~0ull && !(tab[h].k1 == k1[k] && tab[h].k2 == k2[k])) h = (h + 1) & (slots - 1);
+        tab[h].k1 = k1[k]; tab[h].k2 = k2[k];
+    }
+    if (be_h2d(ctx, st, ctx->ann_hash, 0, tab.data(), tab.size() * sizeof(AnnSlot)) || be_sync(ctx, st)) return TC_E_CUDA;
     SjDev& S = ctx->S;
+    S.ann_hash = n_annot > 0 ? (const AnnSlot*)ctx->ann_hash.p : nullptr; S.ann_mask = slots - 1;
     S.n_prefix = (int32_t)np;
     S.rng_don_s = (const int32_t*)ctx->sj_rng.p; S.rng_acc_s = S.rng_don_s + (np + 1); S.rng_don_u = S.rng_acc_s + (np + 1); S.rng_acc_u = S.rng_don_u + (np + 1);
     S.don_s = (const u64*)ctx->don_s.p; S.acc_s = (const u64*)ctx->acc_s.p; S.don_u = (const u64*)ctx->don_u.p; S.acc_u = (const u64*)ctx->acc_u.p;
@@ -1010,7 +1020,7 @@ static int slot_upload(tc_ctx* ctx, Slot& S, const tc_batch_in* in, int64_t r0, 
     static const int64_t zero_off[1] = {0};
     const int64_t s0 = n ? in->seq_off[r0] : 0, c0 = n ? in->cig_off[r0] : 0, m0 = n ? in->md_off[r0] : 0, j0 = n ? in->ji_off[r0] : 0;
     S.n_seq = n ? in->seq_off[r1] - s0 : 0; S.n_cig = n ? in->cig_off[r1] - c0 : 0;
-    S.n_md = n ? in->md_off[r1] - m0 : 0; S.n_ji = n ? in->ji_off[r1] - j0 : 0;
+    S.n_md = n ? in->md_off[r1] - m0 : 0; S.n_ji = n ? in->ji_off[r1] - j0 : 0; S.md_base = m0;
     const size_t d0 = (size_t)(s0 & 15);            // keeps (device pointer - s0) 16-byte aligned
     if (be_h2d(ctx, st, S.b_flag, 0, in->flag + r0, (size_t)n * 4) || be_h2d(ctx, st, S.b_chrom, 0, in->chrom + r0, (size_t)n * 4) ||
         be_h2d(ctx, st, S.b_pos, 0, in->pos + r0, (size_t)n * 4) || be_h2d(ctx, st, S.b_tags, 0, in->tags + r0, (size_t)n) ||
@@ -1046,6 +1056,7 @@ static int alloc_work(tc_ctx* ctx, Slot& S) {
     W.status = (uint32_t*)S.w_status.p; W.counters = (int32_t*)S.w_counters.p;
     W.md_init_off = (int64_t*)S.w_md_init_off.p; W.md_init_len = (int32_t*)S.w_md_init_len.p; W.nm_init = (int32_t*)S.w_nm_init.p;
     W.n_mdtok = (int32_t*)S.w_n_mdtok.p; W.n_jn = (int32_t*)S.w_n_jn.p; W.mflags = (uint8_t*)S.w_mflags.p;
+    CK(S.w_md_tok.ensure((size_t)(S.n_md + 1) * 4)); W.md_tok = (uint32_t*)S.w_md_tok.p - S.md_base;   // indexed by the batch's absolute md offsets
     W.cig_cap = (int32_t*)S.w_cig_cap.p; W.seg_cap = (int32_t*)S.w_seg_cap.p; W.te_cap = (int32_t*)S.w_te_cap.p;
     W.ws_off = (int64_t*)S.w_ws_off.p; W.cig_buf = (int8_t*)S.w_cig_buf.p; W.n_cig_cur = (int32_t*)S.w_n_cig_cur.p;
     W.seg_buf = (int8_t*)S.w_seg_buf.p; W.n_seg_cur = (int32_t*)S.w_n_seg_cur.p; W.n_te = (int32_t*)S.w_n_te.p;
@@ -1142,6 +1153,7 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
         CK(cudaGetLastError());
         k_init_nmmd<<<gw, WARPS_PER_BLOCK * 32, 0, st>>>(P, I, S.W.nm_init, (const int32_t*)S.w_fix_list.p, (const unsigned*)(cur + 2)); ctx->tm.launches++;
         CK(cudaGetLastError());
+        CK(cudaMemsetAsync(S.W.counters, 0xff, (size_t)n * 40, st));
         k_measure<<<gb, TPB, 0, st>>>(P); ctx->tm.launches++;        // measure only needs lengths: safe before the overflow check
         CK(cudaGetLastError());
         if (be_zero(ctx, st, S.W.ws_off + n, 8) || be_scan(ctx, st, S.scan_tmp, S.W.ws_off, n + 1, 0) ||
@@ -1207,6 +1219,7 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
     for (int64_t i = 0; i < n; i++) host_init_read(P, i, ipool);
     CK(S.init_pool.ensure(ipool.size() + 8)); memcpy(S.init_pool.p, ipool.data(), ipool.size());
     P.W.md_init_pool = (const uint8_t*)S.init_pool.p; S.W.md_init_pool = P.W.md_init_pool;
+    memset(S.W.counters, 0xff, (size_t)n * 40);
     for (int64_t i = 0; i < n; i++) measure_read(P, i);
     S.W.ws_off[n] = 0; be_scan(ctx, st, S.scan_tmp, S.W.ws_off, n + 1, 0);
     CK(S.w_ws.ensure((size_t)(S.W.ws_off[n] + 8) * 8)); S.W.ws = (u64*)S.w_ws.p; P.W.ws = S.W.ws;

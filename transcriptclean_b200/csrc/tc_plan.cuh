@@ -39,7 +39,18 @@ struct SjDev {
     int64_t n_don_s, n_acc_s, n_don_u, n_acc_u, n_ann;
     const int32_t *rng_don_s, *rng_acc_s, *rng_don_u, *rng_acc_u;   // first row of each key prefix (n_prefix + 1 entries)
     int32_t n_prefix;
+    const struct AnnSlot* ann_hash; uint32_t ann_mask;              // open-addressing table over (k1, k2); 0 slots = use the sorted arrays
 };
+struct alignas(16) AnnSlot { u64 k1, k2; };                         // empty slot: k1 == ~0
+#ifdef TC_HOSTSIM
+inline
+#else
+__host__ __device__ inline
+#endif
+uint32_t ann_hash_of(u64 k1, u64 k2) {
+    u64 h = (k1 ^ (k2 * 0x9E3779B97F4A7C15ull)) * 0xD6E8FEB86659FD93ull;
+    return (uint32_t)(h >> 32);
+}
 
 struct VarDev {
     const u64* snp_key; const uint8_t* snp_alt; int64_t n_snp;
@@ -74,6 +85,7 @@ struct WorkDev {
     const uint8_t* md_init_pool; int64_t* md_init_off; int32_t* md_init_len; int32_t* nm_init;
     // measure
     int32_t* n_mdtok; int32_t* n_jn; uint8_t* mflags;
+    uint32_t* md_tok;        // input MD tags split into tokens (op << 30 | count), same CSR offsets as B.md
     int32_t *cig_cap, *seg_cap, *te_cap;
     int64_t* ws_off;         // n+1 (exclusive scan of the need)
     u64* ws;
@@ -88,7 +100,7 @@ struct WorkDev {
     int32_t* seq_len_out;    // exact length of the new SEQ (o_seq offsets are padded to 16 bytes)
 };
 
-enum { MF_HAS_I = 1, MF_HAS_D = 2, MF_HAS_N = 4, MF_MD_ACGTN = 8 };
+enum { MF_HAS_I = 1, MF_HAS_D = 2, MF_HAS_N = 4, MF_MD_ACGTN = 8, MF_MD_BYTES = 16 };   // MF_MD_BYTES: a count does not fit a token
 enum { TAG_NM = 1, TAG_MD = 2, TAG_JM = 4, TAG_JI = 8 };
 
 struct Params {
@@ -185,6 +197,17 @@ TC_HD bool sj_nearest(const u64* tab, const int32_t* rng, int32_t n_prefix, u64 
 
 TC_HD bool sj_annotated(const SjDev& S, int chrom, int32_t start, int32_t end, int strand) {
     const u64 k1 = ((u64)chrom << 32) | (uint32_t)start, k2 = ((u64)(uint32_t)end << 1) | (u64)strand;
+    if (S.ann_hash) {                                    // one or two probes instead of ~15 dependent search steps
+        for (uint32_t h = ann_hash_of(k1, k2) & S.ann_mask;; h = (h + 1) & S.ann_mask) {
+#ifdef TC_HOSTSIM
+            const AnnSlot e = S.ann_hash[h];
+#else
+            const ulonglong2 raw = *reinterpret_cast<const ulonglong2*>(S.ann_hash + h); AnnSlot e; e.k1 = raw.x; e.k2 = raw.y;
+#endif
+            if (e.k1 == k1 && e.k2 == k2) return true;
+            if (e.k1 == ~0ull) return false;
+        }
+    }
     int64_t lo = 0, hi = S.n_ann;                        // one lexicographic search over (k1, k2)
     while (lo < hi) {
         const int64_t m = (lo + hi) >> 1; const u64 a = S.ann_k1[m];
@@ -227,30 +250,84 @@ TC_HD bool del_match(const VarDev& V, int chrom, int64_t pos, int32_t ct) {   //
 
 // ---------------------------------------------------------------------------------- MD tokens
 
-struct MdCur { const uint8_t* p; int len; int i; };
+struct MdCur { const uint8_t* p; int len; int i; const uint32_t* tok; };   // tok != 0: pre-split tokens, len of them
 TC_HD bool is_dig(uint8_t c) { return c >= '0' && c <= '9'; }
+#define MD_TOK_MAX 0x3fffffff
 // splitMD (tr.py:128-157): runs of digits -> ('M', value); other runs -> '^...' = ('D', len-1),
-// else ('X', len).
-TC_HD bool md_next(MdCur& t, int& op, int32_t& cnt) {
-    if (t.i >= t.len) return false;
-    uint8_t c = t.p[t.i];
+// else ('X', len).  One token starting at byte s of the tag; returns the byte after it.
+TC_HD int md_token_at(const uint8_t* p, int len, int s, int& op, int64_t& cnt) {
+    int k = s; const uint8_t c = p[s];
     if (is_dig(c)) {
         int64_t v = 0;
-        while (t.i < t.len && is_dig(t.p[t.i])) { v = v * 10 + (t.p[t.i] - '0'); t.i++; }
-        op = 'M'; cnt = (int32_t)v;
+        while (k < len && is_dig(p[k])) { v = v * 10 + (p[k] - '0'); k++; }
+        op = 'M'; cnt = v;
     } else {
-        int s = t.i;
-        while (t.i < t.len && !is_dig(t.p[t.i])) t.i++;
-        int L = t.i - s;
+        while (k < len && !is_dig(p[k])) k++;
+        const int L = k - s;
         if (c == '^') { op = 'D'; cnt = L - 1; } else { op = 'X'; cnt = L; }
     }
+    return k;
+}
+TC_HD uint32_t md_tok_pack(int op, int64_t cnt) { return ((op == 'M' ? 0u : op == 'X' ? 1u : 2u) << 30) | (uint32_t)cnt; }
+TC_HD bool md_next(MdCur& t, int& op, int32_t& cnt) {
+    if (t.i >= t.len) return false;
+    if (t.tok) {
+        const uint32_t w = t.tok[t.i++]; const uint32_t k = w >> 30;
+        op = k == 0 ? 'M' : k == 1 ? 'X' : 'D'; cnt = (int32_t)(w & MD_TOK_MAX);
+        return true;
+    }
+    int64_t v; t.i = md_token_at(t.p, t.len, t.i, op, v); cnt = (int32_t)v;
     return true;
+}
+
+// splitMD over a whole tag, reading it in aligned 8-byte words (the buffers that hold MD tags are
+// 8-byte aligned and padded, so the words around [p, p+len) are readable).  Stores the tokens when
+// `tok` is given; returns their number; sets MF_MD_ACGTN (TC.py:1090 looks for a base letter in the
+// tag) and MF_MD_BYTES (a count that does not fit a token).
+TC_HD int md_tokenize(const uint8_t* p, int len, uint32_t* tok, uint8_t& mf) {
+    int ntok = 0, state = -1, L = 0; int64_t v = 0; bool caret = false, acgtn = false, big = false;
+    const int a = (int)((uintptr_t)p & 7);
+    const u64* wp = reinterpret_cast<const u64*>(p - a);
+    const int end = a + len;                                          // bytes [a, end) of the word stream
+    for (int w0 = 0; w0 < end; w0 += 8) {
+        const u64 word = wp[w0 >> 3];
+        const int k0 = w0 < a ? a - w0 : 0, k1 = end - w0 < 8 ? end - w0 : 8;
+        for (int k = k0; k < k1; k++) {
+            const uint32_t c = (uint32_t)(word >> (8 * k)) & 255u, d = c - '0';
+            if (d < 10u) {
+                if (state != 0) {
+                    if (state == 1) { if (tok) tok[ntok] = md_tok_pack(caret ? 'D' : 'X', caret ? L - 1 : L); ntok++; }
+                    state = 0; v = 0;
+                }
+                if (v <= MD_TOK_MAX) v = v * 10 + d;
+            } else {
+                if (state != 1) {
+                    if (state == 0) { if (v > MD_TOK_MAX) big = true; else if (tok) tok[ntok] = md_tok_pack('M', v); ntok++; }
+                    state = 1; L = 0; caret = c == '^';
+                }
+                L++;
+                const uint32_t u = c & 0xDFu;
+                acgtn |= u == 'A' || u == 'C' || u == 'G' || u == 'T' || u == 'N';
+            }
+        }
+    }
+    if (state == 0) { if (v > MD_TOK_MAX) big = true; else if (tok) tok[ntok] = md_tok_pack('M', v); ntok++; }
+    else if (state == 1) { if (tok) tok[ntok] = md_tok_pack(caret ? 'D' : 'X', caret ? L - 1 : L); ntok++; }
+    if (acgtn) mf |= MF_MD_ACGTN;
+    if (big) mf |= MF_MD_BYTES;
+    return ntok;
 }
 
 // `B` may be a copy of P.B whose cig_op / cig_len / md pointers address a staged (shared-memory) copy
 TC_HD void md_effective(const Params& P, const BatchDev& B, int64_t i, const uint8_t*& p, int& len) {
     if (P.W.status[i] & TC_ST_NMMD_DEVICE) { p = P.W.md_init_pool + P.W.md_init_off[i]; len = P.W.md_init_len[i]; }
     else { p = B.md + B.md_off[i]; len = (int)(B.md_off[i + 1] - B.md_off[i]); }
+}
+// cursor over the read's MD tokens: the pre-split tokens of an input tag when the measure pass stored them
+TC_HD void md_cursor(const Params& P, const BatchDev& B, int64_t i, MdCur& t) {
+    t.i = 0; t.tok = 0;
+    md_effective(P, B, i, t.p, t.len);
+    if (P.W.md_tok && !(P.W.status[i] & TC_ST_NMMD_DEVICE) && !(P.W.mflags[i] & MF_MD_BYTES)) { t.tok = P.W.md_tok + B.md_off[i]; t.len = P.W.n_mdtok[i]; }
 }
 
 TC_HD int read_class(int32_t flag, int32_t chrom) {           // TC.py:1570-1575 (Q1)
@@ -266,7 +343,7 @@ TC_HD int read_class(int32_t flag, int32_t chrom) {           // TC.py:1570-1575
 TC_HD void measure_read(const Params& P, int64_t i) {
     const BatchDev& B = P.B; const WorkDev& W = P.W;
     uint32_t st = W.status[i];
-    for (int k = 0; k < 10; k++) W.counters[10 * i + k] = -1;
+    // (the ten counters of every read start at -1 = "NA": one memset of the whole array by the caller)
     W.cig_buf[i] = -1; W.seg_buf[i] = -1; W.n_cig_cur[i] = 0; W.n_seg_cur[i] = 0;
     W.n_te[i] = 0; W.te_cnt[3 * i] = W.te_cnt[3 * i + 1] = W.te_cnt[3 * i + 2] = 0;
     W.nm_extra[i] = 0; W.refresh[i] = 0;
@@ -275,19 +352,23 @@ TC_HD void measure_read(const Params& P, int64_t i) {
     if ((st & TC_ST_CLASS_MASK) != 0) { W.ws_off[i] = 0; return; }
     int64_t c0 = B.cig_off[i], c1 = B.cig_off[i + 1];
     int nc = (int)(c1 - c0), nN = 0; uint8_t mf = 0;
-    for (int64_t c = c0; c < c1; c++) {
-        uint8_t op = B.cig_op[c];
-        if (op == 'I') mf |= MF_HAS_I; else if (op == 'D') mf |= MF_HAS_D; else if (op == 'N') { mf |= MF_HAS_N; nN++; }
+    {   // op bytes in aligned 8-byte words (the op array is 8-byte aligned and padded like the MD buffer)
+        const uint8_t* p = B.cig_op + c0; const int a = (int)((uintptr_t)p & 7), end = a + nc;
+        const u64* wp = reinterpret_cast<const u64*>(p - a);
+        for (int w0 = 0; w0 < end; w0 += 8) {
+            const u64 word = wp[w0 >> 3];
+            const int k0 = w0 < a ? a - w0 : 0, k1 = end - w0 < 8 ? end - w0 : 8;
+            for (int k = k0; k < k1; k++) {
+                const uint32_t op = (uint32_t)(word >> (8 * k)) & 255u;
+                if (op == 'I') mf |= MF_HAS_I; else if (op == 'D') mf |= MF_HAS_D; else if (op == 'N') { mf |= MF_HAS_N; nN++; }
+            }
+        }
     }
     int ntok = 0;
     if (!(st & TC_ST_NMMD_NONE)) {
-        MdCur t; md_effective(P, B, i, t.p, t.len); t.i = 0;
-        for (int k = 0; k < t.len; k++) {
-            uint8_t u = up8(t.p[k]);
-            if (u == 'A' || u == 'C' || u == 'T' || u == 'G' || u == 'N') { mf |= MF_MD_ACGTN; break; }
-        }
-        int op; int32_t cnt;
-        while (md_next(t, op, cnt)) ntok++;
+        const uint8_t* p; int len; md_effective(P, B, i, p, len);
+        uint32_t* tok = (W.md_tok && !(st & TC_ST_NMMD_DEVICE)) ? W.md_tok + B.md_off[i] : 0;
+        ntok = md_tokenize(p, len, tok, mf);
     }
     int nj = 0;
     if (mf & MF_HAS_N) nj = (B.tags[i] & TAG_JI) ? (int)((B.ji_off[i + 1] - B.ji_off[i]) / 2) : nN;   // tr.py:56-62
@@ -300,19 +381,17 @@ TC_HD void measure_read(const Params& P, int64_t i) {
 // ---------------------------------------------------------------------------------- K1 plan
 
 struct Emit {                 // newCIGAR / newSeq / MVal bookkeeping (endMatch, TC.py:1171-1183)
-    u64* cig; int nc; u64* seg; int ns; int32_t run; int64_t seqlen;
+    u64* cig; int nc; u64* seg; int ns; int32_t run; int64_t seqlen; u64 last;   // last = seg[ns - 1]
     TC_HD void match(int32_t n) { run += n; }
     TC_HD void flush() { if (run > 0) { cig[nc++] = cg_make('M', run); run = 0; } }
     TC_HD void op(int o, int32_t n) { flush(); cig[nc++] = cg_make(o, n); }
     TC_HD void push(int kind, int64_t src, int64_t len) {
         if (len <= 0) return;
         seqlen += len;
-        if (ns > 0) {
-            u64 last = seg[ns - 1];
-            if (seg_kind(last) == kind && seg_src(last) + seg_len(last) == src &&
-                seg_len(last) + len <= (int64_t)SEG_LEN_MASK) { seg[ns - 1] = seg_make(kind, seg_src(last), seg_len(last) + len); return; }
+        if (ns > 0 && seg_kind(last) == kind && seg_src(last) + seg_len(last) == src && seg_len(last) + len <= (int64_t)SEG_LEN_MASK) {
+            last = seg_make(kind, seg_src(last), seg_len(last) + len); seg[ns - 1] = last; return;
         }
-        seg[ns++] = seg_make(kind, src, len);
+        last = seg_make(kind, src, len); seg[ns++] = last;
     }
 };
 
@@ -346,7 +425,7 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
         return;
     }
     WsView v = ws_view(W, i);
-    Emit E; E.cig = v.cig[0]; E.nc = 0; E.seg = v.seg[0]; E.ns = 0; E.run = 0; E.seqlen = 0;
+    Emit E; E.cig = v.cig[0]; E.nc = 0; E.seg = v.seg[0]; E.ns = 0; E.run = 0; E.seqlen = 0; E.last = 0;
     const int chrom = B.chrom[i];
     const int64_t goff = P.G.chrom_off[chrom] - 1;       // plane index of 1-based position p is goff + p
     const uint8_t* seq = B.seq + B.seq_off[i];
@@ -356,9 +435,9 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
     // merge state (tr.py:171-211)
     int64_t ci = B.cig_off[i]; const int64_t cend = B.cig_off[i + 1];
     int32_t crem = ci < cend ? B.cig_len[ci] : 0;
-    MdCur md; md.i = 0; md.len = 0; md.p = 0;
+    MdCur md; md.i = 0; md.len = 0; md.p = 0; md.tok = 0;
     int mop = 0; int32_t mrem = 0; bool have_md = false;
-    if (stage1) { md_effective(P, B, i, md.p, md.len); have_md = md_next(md, mop, mrem); }
+    if (stage1) { md_cursor(P, B, i, md); have_md = md_next(md, mop, mrem); }
     bool fail = false;
     while (true) {
         int op; int32_t ct;
@@ -838,7 +917,7 @@ TC_HD void dry_read(const Params& P, int64_t i) {
     int64_t g = B.pos[i]; int nte = 0, uM = 0, uI = 0, uD = 0;
     int64_t ci = B.cig_off[i]; const int64_t cend = B.cig_off[i + 1];
     int32_t crem = ci < cend ? B.cig_len[ci] : 0;
-    MdCur md; md.i = 0; md_effective(P, B, i, md.p, md.len);
+    MdCur md; md_cursor(P, B, i, md);
     int mop = 0; int32_t mrem = 0; bool have_md = md_next(md, mop, mrem);
     while (true) {
         int op; int32_t ct;
