@@ -285,21 +285,23 @@ TC_HD bool md_next(MdCur& t, int& op, int32_t& cnt) {
 // `tok` is given; returns their number; sets MF_MD_ACGTN (TC.py:1090 looks for a base letter in the
 // tag) and MF_MD_BYTES (a count that does not fit a token).
 TC_HD int md_tokenize(const uint8_t* p, int len, uint32_t* tok, uint8_t& mf) {
-    int ntok = 0, state = -1, L = 0; int64_t v = 0; bool caret = false, acgtn = false, big = false;
+    int ntok = 0, state = -1, L = 0; uint32_t v = 0; bool caret = false, acgtn = false, big = false;   // v > MD_TOK_MAX: too big (sticky)
     const int a = (int)((uintptr_t)p & 7);
     const u64* wp = reinterpret_cast<const u64*>(p - a);
     const int end = a + len;                                          // bytes [a, end) of the word stream
     for (int w0 = 0; w0 < end; w0 += 8) {
         const u64 word = wp[w0 >> 3];
-        const int k0 = w0 < a ? a - w0 : 0, k1 = end - w0 < 8 ? end - w0 : 8;
-        for (int k = k0; k < k1; k++) {
-            const uint32_t c = (uint32_t)(word >> (8 * k)) & 255u, d = c - '0';
+        const uint32_t half[2] = {(uint32_t)word, (uint32_t)(word >> 32)};
+#pragma unroll
+        for (int k = 0; k < 8; k++) {                                 // constant shifts; bytes outside [a, end) are skipped
+            if (w0 + k < a || w0 + k >= end) continue;
+            const uint32_t c = (half[k >> 2] >> (8 * (k & 3))) & 255u, d = c - '0';
             if (d < 10u) {
                 if (state != 0) {
                     if (state == 1) { if (tok) tok[ntok] = md_tok_pack(caret ? 'D' : 'X', caret ? L - 1 : L); ntok++; }
                     state = 0; v = 0;
                 }
-                if (v <= MD_TOK_MAX) v = v * 10 + d;
+                v = v > MD_TOK_MAX / 10 ? 0xffffffffu : v * 10u + d;
             } else {
                 if (state != 1) {
                     if (state == 0) { if (v > MD_TOK_MAX) big = true; else if (tok) tok[ntok] = md_tok_pack('M', v); ntok++; }
