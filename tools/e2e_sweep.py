@@ -1,0 +1,28 @@
+"""e2e (host buffers through tc_correct_batch) over pipeline chunk sizes; wall-clock per call."""
+import os, sys, time, json
+import numpy as np, torch, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from tools.workload import Workload
+from transcriptclean_b200 import engine as E
+from transcriptclean_b200.tables import build_sj_tables
+n = int(os.environ.get("N", "1000000"))
+w = Workload(seed=20261019, chrom_len=248956422, n_genes=3000)
+sj = bench.write_sj(w)
+cols, nm = w.reads("pacbio", n, seed_offset=0)
+gi = w.genome_image()
+eng = E.Engine(0); eng.load_genome(gi); eng.load_junctions(build_sj_tables(sj, {w.chrom}, gi.index))
+pinned = {}
+b = E._BatchIn(); b.n_reads = n
+for k, a in cols.items():
+    t = torch.empty(max(a.nbytes, 8), dtype=torch.uint8, pin_memory=True)
+    if a.nbytes: t[:a.nbytes].copy_(torch.from_numpy(a.view(np.uint8).reshape(-1)))
+    pinned[k] = t; setattr(b, k, t.data_ptr())
+res = {}
+for ch in [int(x) for x in os.environ.get("CHUNKS", "32768,65536,131072,262144,524288").split(",")]:
+    eng.set_pipeline(ch)
+    for _ in range(2): eng.raw_correct(b)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(3): eng.raw_correct(b)
+    torch.cuda.synchronize(); res[ch] = (time.perf_counter() - t0) / 3 * 1e3
+print(json.dumps(res))

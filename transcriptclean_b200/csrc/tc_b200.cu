@@ -685,7 +685,7 @@ struct HostBuf {
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
         size_t want = n + n / 8 + 256;
-        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable | cudaHostAllocMapped);
         if (e == cudaSuccess) cap = want;
         return e;
     }
@@ -820,8 +820,13 @@ static int be_scan(tc_ctx* ctx, cudaStream_t st, DevBuf& tmpbuf, int64_t* a, int
     ctx->tm.launches += 2;
     return 0;
 }
+// One 8-byte total back to the host.  `host` lies in pinned memory, which the device can address
+// (unified addressing), so a one-thread kernel stores it: a cudaMemcpyAsync would queue on the
+// device-to-host copy engine behind the bulk download of the previous chunk and stall the pipeline.
+__global__ void k_publish_i64(const int64_t* dev, int64_t* host) { *host = *dev; __threadfence_system(); }
 static int be_read_i64(tc_ctx* ctx, cudaStream_t st, const int64_t* dev, int64_t* host) {
-    CK(cudaMemcpyAsync(host, dev, 8, cudaMemcpyDeviceToHost, st));
+    k_publish_i64<<<1, 1, 0, st>>>(dev, host);
+    CK(cudaGetLastError());
     return 0;
 }
 typedef cudaStream_t stream_t;
