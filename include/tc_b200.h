@@ -89,6 +89,11 @@ typedef struct {
     const uint8_t* md;        /* value of the MD tag (third ':' piece), when present */
     const int64_t* ji_off;    /* n+1 */
     const int32_t* ji;        /* integers of the input jI tag, when present */
+    /* 4-bit SEQ (optional): when seq_poff != NULL, `seq` holds two bases per byte (low nibble first),
+     * codes index the alphabet of tc_ctx_set_alphabet, row i starts at byte seq_poff[i] (a multiple
+     * of 4) and has seq_off[i+1]-seq_off[i] bases; seq_off keeps the dense base offsets.  The
+     * results then carry SEQ packed the same way (tc_batch_out.seq_bits == 4). */
+    const int64_t* seq_poff;  /* n+1, or NULL: SEQ is ASCII */
 } tc_batch_in;
 
 typedef struct {
@@ -110,6 +115,8 @@ typedef struct {
     const int32_t* ji;        /* 2 per junction */
     const int64_t* te_off;    /* n+1 */
     const tc_te* te;          /* in reference order (stage order, positional inside a stage) */
+    int32_t seq_bits;         /* 8: seq is ASCII; 4: two bases per byte, row i starts at byte seq_off[i] / 2 */
+    int32_t reserved;
 } tc_batch_out;
 
 /* device timing of the last batch call, milliseconds (CUDA events on the context's stream) */
@@ -157,6 +164,16 @@ int tc_ctx_load_variants(tc_ctx* ctx, int64_t n_snp, const uint64_t* snp_key, co
                          const int64_t* ins_aoff, const uint8_t* ins_bytes,
                          int64_t n_del, const uint64_t* del_key, const int32_t* del_size);
 
+/* Alphabet of the 4-bit SEQ form: code k stands for byte alphabet[k] (n <= 16).  It must hold every
+ * byte of the loaded genome (ACGTacgt and the literal-run bytes), because corrected reads copy
+ * genome bytes verbatim (Q6); batches with other SEQ bytes are sent as ASCII. */
+int tc_ctx_set_alphabet(tc_ctx* ctx, const uint8_t* alphabet, int32_t n);
+/* host helpers (tc_host.cpp): ASCII rows -> packed rows (returns the packed size, -1 when a byte is
+ * outside the alphabet; poff gets n+1 offsets; out needs sum(ceil(len/8)*4) bytes) and back. */
+int64_t tc_seq_pack(const uint8_t* seq, const int64_t* seq_off, int64_t n, const uint8_t* alphabet, int32_t n_alpha,
+                    uint8_t* out, int64_t* poff, int32_t n_threads);
+int64_t tc_seq_packed_size(const int64_t* seq_off, int64_t n);
+
 /* batch_correct() minus text rendering: host columns in, host columns out (H2D, kernels, D2H). */
 int tc_correct_batch(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out);
 /* dryRun() (TC.py:1615-1678): only status, counters, te_off, te are filled. */
@@ -188,6 +205,8 @@ void tc_free(void* p);
 int64_t tc_sam_n_reads(const tc_sam* s);
 int64_t tc_sam_header(const tc_sam* s, const char** text);      /* '@' lines, newline-terminated */
 void tc_sam_batch(const tc_sam* s, tc_batch_in* out);            /* view of the parsed columns */
+/* packs the SEQ column to the 4-bit form; 1 = packed, 0 = a SEQ byte is outside the alphabet (stays ASCII) */
+int tc_sam_pack_seq(tc_sam* s, const uint8_t* alphabet, int32_t n_alpha, int32_t n_threads);
 /* printableSAM / printableFa (transcript.py:244-268), create_log_string (TC.py:1591-1604), the TE
  * rows and the emission rules of batch_correct (TC.py:373-385).  The four texts are owned by `s`. */
 int tc_sam_render(tc_sam* s, const tc_batch_out* res, int32_t primary_only, int32_t canon_only, int32_t dry,

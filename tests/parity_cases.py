@@ -65,3 +65,50 @@ def check_generated(engine, seed, n_reads=150, unpinned=False, **kw):
     want = pipeline.oracle_texts(clean.genome, clean.lines, None, None, {}, dry=True)
     d = pipeline.first_diff(got, want)
     assert d is None, (seed, "dry", d)
+
+
+def check_seq_forms(engine, seed, n_reads=160):
+    """SEQ as 4-bit codes (tc_batch_in.seq_poff) and as ASCII give the same four texts, through the
+    column path and through the C++ SAM-text path; a SEQ byte outside the alphabet keeps the batch ASCII."""
+    import numpy as np
+    from transcriptclean_b200 import api, sam
+    from transcriptclean_b200.tables import build_sj_tables, build_variant_tables
+    case = synth.make_case(seed, n_reads=n_reads)
+    sjf, vcf = pipeline.write_tables(case.sj_rows, case.vcf_rows)
+    gi = GenomeImage.from_dict(case.genome)
+    want = pipeline.oracle_texts(case.genome, case.lines, sjf, vcf, {})
+    chroms = set(l.split("\t")[2] for l in case.lines)
+    text = "".join(l + "\n" for l in case.lines).encode()
+    try:
+        for seq4 in (True, False):
+            engine.seq4 = seq4
+            got = pipeline.product_texts(engine, gi, case.lines, sjf, vcf, {})
+            d = pipeline.first_diff(got, want)
+            assert d is None, (seq4, d)
+            refs = api.make_refs(gi, build_sj_tables(sjf, chroms, gi.index), build_variant_tables(vcf, 5, gi.index), engine=engine)
+            _, got = api.correct_sam_text(text, api.Struct(), refs)
+            d = pipeline.first_diff({k: v.decode() for k, v in got.items()}, want)
+            assert d is None, (seq4, "text path", d)
+        engine.seq4 = True
+        cols = sam.parse_lines(case.lines, gi).cols
+        packed = engine.pack_cols(cols)
+        if engine.alphabet is None:                     # a genome with more than 16 distinct bytes: ASCII only
+            assert packed is None and len(set("".join(case.genome.values())) | set("ACGTacgt")) > 16
+            return False
+        assert packed is not None and packed["seq"].size < cols["seq"].size * 0.52 + 4 * len(case.lines) + 64
+        res = engine.correct(packed)                    # explicit packed columns in, ASCII view out
+        engine.seq4 = False
+        ref = engine.correct(cols)
+        assert np.array_equal(res.seq_off, ref.seq_off) and np.array_equal(res.seq_len, ref.seq_len)
+        for i in range(len(case.lines)):
+            a, n = int(ref.seq_off[i]), int(ref.seq_len[i])
+            assert res.seq[a:a + n].tobytes() == ref.seq[a:a + n].tobytes(), i
+        engine.seq4 = True
+        odd = dict(cols)
+        odd["seq"] = cols["seq"].copy()
+        if odd["seq"].size:
+            odd["seq"][0] = ord("!")
+        assert engine.pack_cols(odd) is None
+        return True
+    finally:
+        engine.seq4 = True

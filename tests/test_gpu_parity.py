@@ -48,6 +48,19 @@ def test_tagless_input_at_scale(engine):
     pc.check_generated(engine, 1203, n_reads=400, tagless_frac=1.0)
 
 
+def test_seq_forms_agree(engine):
+    """4-bit and ASCII SEQ transport give the same texts; at least one of the cases really travels packed."""
+    assert sum(bool(pc.check_seq_forms(engine, seed, n_reads=300)) for seed in (1231, 1232, 1233)) >= 1
+
+
+def test_seq_forms_agree_when_pipelined(engine):
+    engine.set_pipeline(41)
+    try:
+        pc.check_seq_forms(engine, 1234, n_reads=300)
+    finally:
+        engine.set_pipeline(131072)
+
+
 def test_pipelined_chunks(engine):
     """tc_correct_batch cut into small chunks (3-stream pipeline, rebased offsets) gives the same texts."""
     for chunk in (16, 37, 100):

@@ -30,3 +30,7 @@ def test_reference_synthetic(engine, seed):
 @pytest.mark.parametrize("seed", range(200, 212))
 def test_generated_vs_oracle(engine, seed):
     pc.check_generated(engine, seed, unpinned=(seed % 3 == 0))
+
+
+def test_seq_forms_agree(engine):
+    assert sum(bool(pc.check_seq_forms(engine, seed)) for seed in (231, 232, 1232)) >= 1

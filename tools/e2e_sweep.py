@@ -12,6 +12,8 @@ sj = bench.write_sj(w)
 cols, nm = w.reads("pacbio", n, seed_offset=0)
 gi = w.genome_image()
 eng = E.Engine(0); eng.load_genome(gi); eng.load_junctions(build_sj_tables(sj, {w.chrom}, gi.index))
+if not os.environ.get("SEQ8"):
+    cols = eng.pack_cols(cols)
 pinned = {}
 b = E._BatchIn(); b.n_reads = n
 for k, a in cols.items():

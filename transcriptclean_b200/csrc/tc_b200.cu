@@ -734,6 +734,7 @@ static void host_nmmd(const GenomeDev& G, const uint8_t* seq, const CigSrc& cs, 
 
 // Everything that belongs to one batch (or one chunk of a pipelined batch) on the device.
 struct Slot {
+    DevBuf b_seqp, b_seq_poff, o_seqp;   // 4-bit SEQ: packed input rows + their offsets, packed output
     DevBuf b_flag, b_chrom, b_pos, b_tags, b_seq_off, b_seq, b_cig_off, b_cig_op, b_cig_len, b_md_off, b_md, b_ji_off, b_ji;
     BatchDev B; int64_t n = 0, n_seq = 0, n_cig = 0, n_md = 0, n_ji = 0, md_base = 0;
     int64_t seq_lo_word = 0, seq_hi_word = 0;       // words of B.seq (as uint32) that may be dereferenced
@@ -756,6 +757,7 @@ struct Slot {
                        &w_o_seq, &w_o_cig, &w_o_te, &w_o_jn, &w_seq_len, &w_plan, &w_fix_list, &init_pool, &cursors, &scan_tmp,
                        &o_nm, &o_md_off, &o_md_len, &o_md_pool, &o_seq, &o_cig_op, &o_cig_len, &o_te, &o_jm, &o_ji};
         for (DevBuf* b : d) b->release();
+        b_seqp.release(); b_seq_poff.release(); o_seqp.release();
         h_tot.release();
     }
 };
@@ -777,6 +779,9 @@ struct tc_ctx {
     Slot slot[2];
     int64_t n = 0; bool ran = false, ran_dry = false; bool piped = false;
     int64_t chunk_reads = 131072;   // reads per chunk of the pipelined tc_correct_batch (0 = never pipeline)
+    uint8_t alphabet[16] = {'A', 'C', 'G', 'T', 'N', 'a', 'c', 'g', 't', 'n', 0, 0, 0, 0, 0, 0}; int n_alpha = 10;   // 4-bit SEQ codes
+    bool genome_byte[256] = {};     // bytes the loaded genome can put into a read
+    bool packed = false;            // the current batch came with 4-bit SEQ (results go back packed)
     // pinned host outputs (whole batch)
     HostBuf h_status, h_counters, h_nm, h_seq_off, h_seq, h_cig_off, h_cig_op, h_cig_len, h_md_off, h_md_len, h_md,
         h_jn_off, h_jm, h_ji, h_te_off, h_te, h_seq_len;
@@ -787,6 +792,48 @@ static std::string g_create_err;
 
 #ifndef TC_HOSTSIM
 __global__ void k_set_u64(unsigned long long* p, unsigned long long v) { *p = v; }
+
+struct Alphabet { uint8_t c[16]; };
+// 4-bit SEQ rows -> ASCII rows, one warp per read: a lane turns one 32-bit word (8 bases) into 8 bytes
+// through a 256-entry table (packed byte -> two characters).
+__global__ void __launch_bounds__(256) k_seq_unpack(int64_t n, const int64_t* seq_off, const int64_t* poff, const uint8_t* packed,
+                                                    uint8_t* seq, Alphabet A) {
+    __shared__ uint16_t lut[256];
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) lut[t] = (uint16_t)(A.c[t & 15] | (A.c[t >> 4] << 8));
+    __syncthreads();
+    const int lane = threadIdx.x & 31; const int64_t nw = (int64_t)gridDim.x * 8;
+    for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += nw) {
+        const int64_t o = seq_off[i]; const int L = (int)(seq_off[i + 1] - o);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(packed + poff[i]);
+        uint8_t* dst = seq + o;
+        const bool al = (reinterpret_cast<uintptr_t>(dst) & 3) == 0;
+        for (int w = lane; w * 8 < L; w += 32) {
+            const uint32_t x = src[w];
+            const uint32_t lo = lut[x & 255u] | ((uint32_t)lut[(x >> 8) & 255u] << 16), hi = lut[(x >> 16) & 255u] | ((uint32_t)lut[x >> 24] << 16);
+            const int left = L - w * 8;
+            if (al && left >= 8) { reinterpret_cast<uint32_t*>(dst)[2 * w] = lo; reinterpret_cast<uint32_t*>(dst)[2 * w + 1] = hi; }
+            else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) if (k < left) dst[w * 8 + k] = (uint8_t)((k < 4 ? lo : hi) >> (8 * (k & 3)));
+            }
+        }
+    }
+}
+// ASCII rows -> 4-bit rows over the whole dense output buffer (rows are 16-byte aligned, so packed byte j
+// holds bases 2j and 2j+1 whatever the row): 16 bytes in, 8 bytes out per thread
+__global__ void __launch_bounds__(256) k_seq_pack(int64_t n16, const uint4* seq, uint2* out, Alphabet A) {
+    __shared__ uint8_t inv[256];
+    inv[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x < 16 && (threadIdx.x == 0 || A.c[threadIdx.x] != 0)) inv[A.c[threadIdx.x]] = (uint8_t)threadIdx.x;
+    __syncthreads();
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n16; t += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 v = seq[t];
+        auto pk = [&](uint32_t w) { return (uint32_t)inv[w & 255u] | ((uint32_t)inv[(w >> 8) & 255u] << 4) | ((uint32_t)inv[(w >> 16) & 255u] << 8) | ((uint32_t)inv[w >> 24] << 12); };
+        uint2 o; o.x = pk(v.x) | (pk(v.y) << 16); o.y = pk(v.z) | (pk(v.w) << 16);
+        out[t] = o;
+    }
+}
 
 static int be_h2d(tc_ctx* ctx, cudaStream_t st, DevBuf& d, size_t dst_off, const void* src, size_t bytes, size_t slack = 0) {
     CK(d.ensure(dst_off + bytes + slack + 8));
@@ -949,6 +996,9 @@ int tc_ctx_load_genome(tc_ctx* ctx, int32_t n_chrom, const int64_t* chrom_len, c
     G.chrom_off = (const int64_t*)ctx->chrom_off.p; G.chrom_len = (const int64_t*)ctx->chrom_len.p;
     G.exc_start = (const int64_t*)ctx->exc_start.p; G.exc_end = (const int64_t*)ctx->exc_end.p;
     G.exc_byte = (const uint8_t*)ctx->exc_byte.p; G.n_exc = n_exc; G.n_chrom = n_chrom;
+    memset(ctx->genome_byte, 0, sizeof(ctx->genome_byte));
+    for (const char* c = "ACGTacgt"; *c; c++) ctx->genome_byte[(uint8_t)*c] = true;
+    for (int64_t k = 0; k < n_exc; k++) ctx->genome_byte[exc_byte[k]] = true;
     ctx->have_genome = true;
     return TC_OK;
 }
@@ -1017,6 +1067,28 @@ int tc_ctx_load_variants(tc_ctx* ctx, int64_t n_snp, const uint64_t* snp_key, co
 
 }  // extern "C"
 
+// 4-bit SEQ rows of reads [r0, r1): upload, then expand to the ASCII rows the kernels read (B.seq at d0)
+static int seq_upload_packed(tc_ctx* ctx, Slot& S, const tc_batch_in* in, int64_t r0, int64_t r1, size_t d0, stream_t st) {
+    const int64_t n = r1 - r0;
+    CK(S.b_seq.ensure(d0 + (size_t)S.n_seq + 256 + 8));
+    if (n == 0) return 0;
+    const int64_t p0 = in->seq_poff[r0], pbytes = in->seq_poff[r1] - p0;
+    if (be_h2d(ctx, st, S.b_seqp, 0, in->seq + p0, (size_t)pbytes, 64) || be_h2d(ctx, st, S.b_seq_poff, 0, in->seq_poff + r0, (size_t)(n + 1) * 8)) return TC_E_CUDA;
+    const int64_t s0 = in->seq_off[r0];
+    uint8_t* dst = (uint8_t*)S.b_seq.p + d0 - s0; const uint8_t* src = (const uint8_t*)S.b_seqp.p - p0;
+#ifndef TC_HOSTSIM
+    Alphabet A; memcpy(A.c, ctx->alphabet, 16);
+    int64_t wb = (n + 7) / 8; int g = (int)(wb < 148 * 8 ? wb : 148 * 8);
+    k_seq_unpack<<<g, 256, 0, st>>>(n, (const int64_t*)S.b_seq_off.p, (const int64_t*)S.b_seq_poff.p, src, dst, A); ctx->tm.launches++;
+    CK(cudaGetLastError());
+#else
+    const int64_t* so = (const int64_t*)S.b_seq_off.p; const int64_t* po = (const int64_t*)S.b_seq_poff.p;
+    for (int64_t i = 0; i < n; i++)
+        for (int64_t k = 0; k < so[i + 1] - so[i]; k++) { const uint8_t b = src[po[i] + (k >> 1)]; dst[so[i] + k] = ctx->alphabet[(k & 1) ? b >> 4 : b & 15]; }
+#endif
+    return 0;
+}
+
 // uploads reads [r0, r1) of `in` into slot S.  CSR offsets stay the batch's absolute offsets; the
 // data pointers are shifted so that they can be applied unchanged.
 static int slot_upload(tc_ctx* ctx, Slot& S, const tc_batch_in* in, int64_t r0, int64_t r1, stream_t st) {
@@ -1030,7 +1102,7 @@ static int slot_upload(tc_ctx* ctx, Slot& S, const tc_batch_in* in, int64_t r0, 
     if (be_h2d(ctx, st, S.b_flag, 0, in->flag + r0, (size_t)n * 4) || be_h2d(ctx, st, S.b_chrom, 0, in->chrom + r0, (size_t)n * 4) ||
         be_h2d(ctx, st, S.b_pos, 0, in->pos + r0, (size_t)n * 4) || be_h2d(ctx, st, S.b_tags, 0, in->tags + r0, (size_t)n) ||
         be_h2d(ctx, st, S.b_seq_off, 0, n ? in->seq_off + r0 : zero_off, (size_t)(n + 1) * 8) ||
-        be_h2d(ctx, st, S.b_seq, d0, n ? in->seq + s0 : nullptr, (size_t)S.n_seq, 256) ||
+        (in->seq_poff ? seq_upload_packed(ctx, S, in, r0, r1, d0, st) : be_h2d(ctx, st, S.b_seq, d0, n ? in->seq + s0 : nullptr, (size_t)S.n_seq, 256)) ||
         be_h2d(ctx, st, S.b_cig_off, 0, n ? in->cig_off + r0 : zero_off, (size_t)(n + 1) * 8) ||
         be_h2d(ctx, st, S.b_cig_op, 0, n ? in->cig_op + c0 : nullptr, (size_t)S.n_cig) ||
         be_h2d(ctx, st, S.b_cig_len, 0, n ? in->cig_len + c0 : nullptr, (size_t)S.n_cig * 4) ||
@@ -1267,6 +1339,24 @@ static int host_reserve_all(tc_ctx* ctx, Slot& S, int64_t r0, int64_t n_total, b
     return 0;
 }
 
+// new SEQ rows of a slot -> host; packed to 4 bits first when the batch came in that form
+static int seq_download(tc_ctx* ctx, Slot& S, stream_t st) {
+    if (!ctx->packed) return be_d2h(ctx, st, ctx->h_seq, (size_t)S.base_seq, S.o_seq.p, (size_t)S.tot_seq);
+    if (S.tot_seq == 0) return 0;
+    CK(S.o_seqp.ensure((size_t)S.tot_seq / 2 + 64));
+#ifndef TC_HOSTSIM
+    Alphabet A; memcpy(A.c, ctx->alphabet, 16);
+    const int64_t n16 = S.tot_seq / 16; int64_t nb = (n16 + 255) / 256; int g = (int)(nb < 148 * 16 ? nb : 148 * 16);
+    k_seq_pack<<<g, 256, 0, st>>>(n16, (const uint4*)S.o_seq.p, (uint2*)S.o_seqp.p, A); ctx->tm.launches++;
+    CK(cudaGetLastError());
+#else
+    uint8_t inv[256] = {0}; for (int k = 0; k < ctx->n_alpha; k++) inv[ctx->alphabet[k]] = (uint8_t)k;
+    const uint8_t* a = (const uint8_t*)S.o_seq.p; uint8_t* o = (uint8_t*)S.o_seqp.p;
+    for (int64_t j = 0; j < S.tot_seq / 2; j++) o[j] = (uint8_t)(inv[a[2 * j]] | (inv[a[2 * j + 1]] << 4));
+#endif
+    return be_d2h(ctx, st, ctx->h_seq, (size_t)S.base_seq / 2, S.o_seqp.p, (size_t)S.tot_seq / 2);
+}
+
 // enqueues the device-to-host copies of a slot's results into the batch-wide pinned arrays
 static int slot_download(tc_ctx* ctx, Slot& S, int64_t r0, stream_t st) {
     const int64_t n = S.n; const size_t n1 = (size_t)n + 1;
@@ -1275,7 +1365,7 @@ static int slot_download(tc_ctx* ctx, Slot& S, int64_t r0, stream_t st) {
         be_d2h(ctx, st, ctx->h_te_off, (size_t)r0 * 8, S.W.o_te, n1 * 8) || be_d2h(ctx, st, ctx->h_te, (size_t)S.base_te * 16, S.o_te.p, (size_t)S.tot_te * 16)) return TC_E_CUDA;
     if (S.ran_dry) return 0;
     if (be_d2h(ctx, st, ctx->h_nm, (size_t)r0 * 4, S.o_nm.p, (size_t)n * 4) || be_d2h(ctx, st, ctx->h_seq_off, (size_t)r0 * 8, S.W.o_seq, n1 * 8) ||
-        be_d2h(ctx, st, ctx->h_seq_len, (size_t)r0 * 4, S.W.seq_len_out, (size_t)n * 4) || be_d2h(ctx, st, ctx->h_seq, (size_t)S.base_seq, S.o_seq.p, (size_t)S.tot_seq) ||
+        be_d2h(ctx, st, ctx->h_seq_len, (size_t)r0 * 4, S.W.seq_len_out, (size_t)n * 4) || seq_download(ctx, S, st) ||
         be_d2h(ctx, st, ctx->h_cig_off, (size_t)r0 * 8, S.W.o_cig, n1 * 8) || be_d2h(ctx, st, ctx->h_cig_op, (size_t)S.base_cig, S.o_cig_op.p, (size_t)S.tot_cig) ||
         be_d2h(ctx, st, ctx->h_cig_len, (size_t)S.base_cig * 4, S.o_cig_len.p, (size_t)S.tot_cig * 4) ||
         be_d2h(ctx, st, ctx->h_md_off, (size_t)r0 * 8, S.o_md_off.p, (size_t)n * 8) || be_d2h(ctx, st, ctx->h_md_len, (size_t)r0 * 4, S.o_md_len.p, (size_t)n * 4) ||
@@ -1293,6 +1383,19 @@ static void fill_out(tc_ctx* ctx, tc_batch_out* out, int64_t n) {
     out->md_off = (const int64_t*)ctx->h_md_off.p; out->md_len = (const int32_t*)ctx->h_md_len.p; out->md = (const uint8_t*)ctx->h_md.p;
     out->jn_off = (const int64_t*)ctx->h_jn_off.p; out->jm = (const int8_t*)ctx->h_jm.p; out->ji = (const int32_t*)ctx->h_ji.p;
     out->te_off = (const int64_t*)ctx->h_te_off.p; out->te = (const tc_te*)ctx->h_te.p;
+    out->seq_bits = ctx->packed ? 4 : 8;
+}
+
+// notes the SEQ form of the batch; a 4-bit batch needs an alphabet that holds every genome byte
+static int check_packed(tc_ctx* ctx, const tc_batch_in* in) {
+    ctx->packed = in->seq_poff != nullptr;
+    if (!ctx->packed) return 0;
+    bool have[256] = {false};
+    for (int k = 0; k < ctx->n_alpha; k++) have[ctx->alphabet[k]] = true;
+    for (int b = 0; b < 256; b++) if (ctx->genome_byte[b] && !have[b]) {
+        ctx->err = "4-bit SEQ: the alphabet lacks genome byte " + std::to_string(b) + " (tc_ctx_set_alphabet)"; return 1;
+    }
+    return 0;
 }
 
 static void reset_bases(Slot& S) { S.base_seq = S.base_cig = S.base_te = S.base_jn = S.base_md = 0; }
@@ -1309,6 +1412,7 @@ int tc_batch_upload(tc_ctx* ctx, const tc_batch_in* in) {
 #endif
     ctx->tm.h2d_bytes = 0;
     ctx->n = in->n_reads; ctx->ran = false;
+    if (check_packed(ctx, in)) return TC_E_ARG;
     int rc = slot_upload(ctx, ctx->slot[0], in, 0, in->n_reads, main_stream(ctx));
 #ifndef TC_HOSTSIM
     if (!rc) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -1369,6 +1473,7 @@ static int run_all(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out, int dr
         ctx->tm.h2d_bytes = ctx->tm.d2h_bytes = 0; ctx->tm.launches = 0; ctx->tm.md_pool_retries = 0; ctx->tm.exact_nmmd_reads = 0;
         ctx->tm.kernels_ms = ctx->tm.k_nmmd_init_ms = ctx->tm.k_measure_ms = ctx->tm.k_plan_ms = ctx->tm.k_junction_ms = ctx->tm.k_emit_ms = 0.f;
         ctx->n = n; ctx->ran = false;
+        if (check_packed(ctx, in)) return TC_E_ARG;
         const int64_t nchunk = (n + CH - 1) / CH;
         int64_t bs = 0, bc = 0, bt = 0, bj = 0, bm = 0;
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -1412,6 +1517,13 @@ static int run_all(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out, int dr
 }
 int tc_correct_batch(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out) { return run_all(ctx, in, out, 0); }
 int tc_dryrun_batch(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out) { return run_all(ctx, in, out, 1); }
+
+int tc_ctx_set_alphabet(tc_ctx* ctx, const uint8_t* alphabet, int32_t n) {
+    if (!ctx || !alphabet || n < 1 || n > 16) return TC_E_ARG;
+    for (int a = 0; a < n; a++) for (int b = a + 1; b < n; b++) if (alphabet[a] == alphabet[b]) { ctx->err = "tc_ctx_set_alphabet: duplicate byte"; return TC_E_ARG; }
+    memset(ctx->alphabet, 0, 16); memcpy(ctx->alphabet, alphabet, (size_t)n); ctx->n_alpha = n;
+    return TC_OK;
+}
 
 int tc_ctx_set_pipeline(tc_ctx* ctx, int64_t chunk_reads) {
     if (!ctx || chunk_reads < 0) return TC_E_ARG;

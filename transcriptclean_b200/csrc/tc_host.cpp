@@ -67,6 +67,8 @@ struct tc_sam {
     std::vector<int64_t> other_off; std::vector<Span> other;
     std::string header;
     std::string out_sam, out_fa, out_log, out_te;
+    // 4-bit SEQ form (tc_sam_pack_seq): packed rows, their offsets, the alphabet they index
+    std::vector<uint8_t> seqp; std::vector<int64_t> seq_poff; uint8_t alphabet[16] = {0}; int n_alpha = 0; bool packed = false;
 };
 
 namespace {
@@ -217,7 +219,9 @@ const Comp COMP;
 void render_range(const tc_sam* S, const tc_batch_out* R, int64_t a, int64_t b, bool primary_only, bool canon_only, bool dry,
                   std::string& sam, std::string& fa, std::string& lg, std::string& te) {
     const char* T = S->text;
-    std::string row, seq;
+    std::string row, seq, useq;
+    uint16_t lut16[256];
+    for (int t = 0; t < 256; t++) lut16[t] = (uint16_t)(S->alphabet[t & 15] | (S->alphabet[t >> 4] << 8));
     if (b > a && !dry) {
         const size_t sb = (size_t)((R->seq_off[b] - R->seq_off[a]) + (b - a) * 400 + (R->cig_off[b] - R->cig_off[a]) * 6);
         sam.reserve(sb); fa.reserve((size_t)(R->seq_off[b] - R->seq_off[a]) + (size_t)(b - a) * 64);
@@ -257,6 +261,13 @@ void render_range(const tc_sam* S, const tc_batch_out* R, int64_t a, int64_t b, 
         } else add_span(S->cigar[i]);
         add_span(S->f[6][i]); add_span(S->f[7][i]); add_span(S->f[8][i]);
         const uint8_t* sq = R->seq + R->seq_off[i]; const int32_t sl = R->seq_len[i];
+        if (R->seq_bits == 4) {                                       // two bases per byte, row at seq_off / 2
+            const uint8_t* pk = R->seq + R->seq_off[i] / 2;
+            useq.resize((size_t)sl + 2);
+            uint16_t* w = reinterpret_cast<uint16_t*>(&useq[0]);
+            for (int32_t k = 0; k < (sl + 1) / 2; k++) w[k] = lut16[pk[k]];
+            sq = reinterpret_cast<const uint8_t*>(useq.data());
+        }
         add((const char*)sq, sl);
         add("*", 1);
         for (int64_t k = S->other_off[i]; k < S->other_off[i + 1]; k++) {
@@ -385,11 +396,59 @@ void tc_sam_free(tc_sam* S) { delete S; }
 int64_t tc_sam_n_reads(const tc_sam* S) { return S ? S->n : 0; }
 int64_t tc_sam_header(const tc_sam* S, const char** text) { if (!S) return 0; if (text) *text = S->header.data(); return (int64_t)S->header.size(); }
 
+int64_t tc_seq_packed_size(const int64_t* seq_off, int64_t n) {
+    int64_t t = 0;
+    for (int64_t i = 0; i < n; i++) t += (seq_off[i + 1] - seq_off[i] + 7) / 8 * 4;
+    return t;
+}
+
+int64_t tc_seq_pack(const uint8_t* seq, const int64_t* seq_off, int64_t n, const uint8_t* alphabet, int32_t n_alpha,
+                    uint8_t* out, int64_t* poff, int32_t n_threads) {
+    if (n_alpha < 1 || n_alpha > 16) return -1;
+    uint8_t inv[256]; memset(inv, 0xff, sizeof(inv));
+    for (int k = 0; k < n_alpha; k++) inv[alphabet[k]] = (uint8_t)k;
+    poff[0] = 0;
+    for (int64_t i = 0; i < n; i++) poff[i + 1] = poff[i] + (seq_off[i + 1] - seq_off[i] + 7) / 8 * 4;
+    int T = n_threads < 1 ? 1 : n_threads; if (n < 4096) T = 1;
+    std::vector<int> bad((size_t)T, 0);
+    auto work = [&](int k) {
+        for (int64_t i = n * k / T; i < n * (k + 1) / T; i++) {
+            const uint8_t* r = seq + seq_off[i]; const int64_t L = seq_off[i + 1] - seq_off[i]; uint8_t* o = out + poff[i];
+            unsigned any = 0;
+            for (int64_t j = 0; j + 1 < L; j += 2) { const unsigned a = inv[r[j]], b = inv[r[j + 1]]; any |= a | b; o[j >> 1] = (uint8_t)(a | (b << 4)); }
+            if (L & 1) { const unsigned a = inv[r[L - 1]]; any |= a; o[L >> 1] = (uint8_t)(a & 15); }
+            for (int64_t j = (L + 1) / 2; j < poff[i + 1] - poff[i]; j++) o[j] = 0;
+            if (any & 0xf0) bad[(size_t)k] = 1;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int k = 0; k < T; k++) th.emplace_back(work, k);
+    for (auto& t : th) t.join();
+    for (int b : bad) if (b) return -1;
+    return poff[n];
+}
+
+// packs the parsed SEQ column to 4 bits per base; 1 = done (tc_sam_batch now yields the packed form),
+// 0 = a SEQ byte lies outside the alphabet (the batch stays ASCII)
+int tc_sam_pack_seq(tc_sam* S, const uint8_t* alphabet, int32_t n_alpha, int32_t n_threads) {
+    if (!S || !alphabet || n_alpha < 1 || n_alpha > 16) return 0;
+    memset(S->alphabet, 0, 16); memcpy(S->alphabet, alphabet, (size_t)n_alpha); S->n_alpha = n_alpha;
+    if (S->packed) return 1;
+    S->seq_poff.assign((size_t)S->n + 1, 0);
+    S->seqp.resize((size_t)tc_seq_packed_size(S->seq_off.data(), S->n) + 64);
+    if (tc_seq_pack(S->seq.data(), S->seq_off.data(), S->n, alphabet, n_alpha, S->seqp.data(), S->seq_poff.data(), n_threads) < 0) {
+        std::vector<uint8_t>().swap(S->seqp); return 0;
+    }
+    S->packed = true;
+    return 1;
+}
+
 void tc_sam_batch(const tc_sam* S, tc_batch_in* b) {
     memset(b, 0, sizeof(*b));
     b->n_reads = S->n; b->flag = S->flag.data(); b->chrom = S->chrom.data(); b->pos = S->pos.data(); b->tags = S->tags.data();
     b->seq_off = S->seq_off.data(); b->seq = S->seq.data(); b->cig_off = S->cig_off.data(); b->cig_op = S->cig_op.data();
     b->cig_len = S->cig_len.data(); b->md_off = S->md_off.data(); b->md = S->md.data(); b->ji_off = S->ji_off.data(); b->ji = S->ji.data();
+    if (S->packed) { b->seq = S->seqp.data(); b->seq_poff = S->seq_poff.data(); }
 }
 
 int tc_sam_render(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_t canon_only, int32_t dry, int32_t n_threads,

@@ -12,7 +12,7 @@ EXPORTS = ["tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_set_optio
            "tc_ctx_load_genome", "tc_ctx_load_junctions", "tc_ctx_load_variants", "tc_correct_batch",
            "tc_dryrun_batch", "tc_batch_upload", "tc_batch_run", "tc_batch_download", "tc_get_timing",
            "tc_ctx_set_pipeline", "tc_sam_parse", "tc_sam_free", "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_render",
-           "tc_sam_rnames", "tc_free"]
+           "tc_sam_rnames", "tc_free", "tc_ctx_set_alphabet", "tc_seq_pack", "tc_seq_packed_size", "tc_sam_pack_seq"]
 
 # status bits (include/tc_b200.h)
 ST_CLASS_MASK, ST_FALLBACK, ST_CIGAR_REWRITTEN = 3, 1 << 2, 1 << 3
@@ -31,13 +31,14 @@ class _Options(C.Structure):
 
 class _BatchIn(C.Structure):
     _fields_ = [("n_reads", C.c_int64)] + [(n, C.c_void_p) for n in (
-        "flag", "chrom", "pos", "tags", "seq_off", "seq", "cig_off", "cig_op", "cig_len", "md_off", "md", "ji_off", "ji")]
+        "flag", "chrom", "pos", "tags", "seq_off", "seq", "cig_off", "cig_op", "cig_len", "md_off", "md", "ji_off", "ji",
+        "seq_poff")]
 
 
 class _BatchOut(C.Structure):
     _fields_ = [("n_reads", C.c_int64)] + [(n, C.c_void_p) for n in (
         "status", "counters", "nm", "seq_off", "seq_len", "seq", "cig_off", "cig_op", "cig_len", "md_off", "md_len", "md",
-        "jn_off", "jm", "ji", "te_off", "te")]
+        "jn_off", "jm", "ji", "te_off", "te")] + [("seq_bits", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Timing(C.Structure):
@@ -99,10 +100,16 @@ def _declare(lib):
     lib.tc_sam_header.restype = C.c_int64
     lib.tc_sam_batch.argtypes = [C.c_void_p, C.POINTER(_BatchIn)]
     lib.tc_sam_batch.restype = None
+    lib.tc_ctx_set_alphabet.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
+    lib.tc_seq_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
+    lib.tc_seq_pack.restype = C.c_int64
+    lib.tc_seq_packed_size.argtypes = [C.c_void_p, C.c_int64]
+    lib.tc_seq_packed_size.restype = C.c_int64
+    lib.tc_sam_pack_seq.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32]
     lib.tc_sam_render.argtypes = [C.c_void_p, C.POINTER(_BatchOut)] + [C.c_int32] * 4 + [C.POINTER(C.c_void_p), C.POINTER(C.c_int64)] * 4 + [C.c_char_p, C.c_int64]
     for f in EXPORTS:
         if f not in ("tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_stream", "tc_sam_parse", "tc_sam_free",
-                     "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_rnames", "tc_free"):
+                     "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_rnames", "tc_free", "tc_seq_pack", "tc_seq_packed_size"):
             getattr(lib, f).restype = C.c_int
 
 
@@ -111,9 +118,9 @@ def _ptr(a):
 
 
 class BatchResult:
-    """numpy copies of a tc_batch_out."""
+    """numpy copies of a tc_batch_out (a 4-bit SEQ column is expanded to ASCII with `alphabet`)."""
 
-    def __init__(self, out, dry):
+    def __init__(self, out, dry, alphabet=None):
         n = out.n_reads
         self.n = n
         self.dry = dry
@@ -133,7 +140,13 @@ class BatchResult:
         self.nm = arr(out.nm, np.int32, n)
         self.seq_off = arr(out.seq_off, np.int64, n + 1) if n else np.zeros(1, np.int64)
         self.seq_len = arr(out.seq_len, np.int32, n)
-        self.seq = arr(out.seq, np.uint8, int(self.seq_off[-1]))
+        if out.seq_bits == 4:            # two bases per byte; rows are 16-byte aligned, so packed byte j = bases 2j, 2j+1
+            pk = arr(out.seq, np.uint8, int(self.seq_off[-1]) // 2)
+            al = np.frombuffer(bytes(alphabet).ljust(16, b"\0"), dtype=np.uint8).astype(np.uint16)
+            t = np.arange(256)
+            self.seq = (al[t & 15] | (al[t >> 4] << 8)).astype("<u2")[pk].view(np.uint8)
+        else:
+            self.seq = arr(out.seq, np.uint8, int(self.seq_off[-1]))
         self.cig_off = arr(out.cig_off, np.int64, n + 1) if n else np.zeros(1, np.int64)
         self.cig_op = arr(out.cig_op, np.uint8, int(self.cig_off[-1]))
         self.cig_len = arr(out.cig_len, np.int32, int(self.cig_off[-1]))
@@ -160,7 +173,7 @@ class SamText:
     """SAM text parsed by the library (tc_sam_parse): header, columnar batch, and the renderer of the
     four output texts.  Host-side only; the same logic as sam.py / render.py, in multi-threaded C++."""
 
-    def __init__(self, lib, text, genome, n_threads=None):
+    def __init__(self, lib, text, genome, n_threads=None, alphabet=None):
         self._lib = lib
         self._text = text if isinstance(text, bytes) else bytes(text)      # kept alive: fields are referenced
         names = (C.c_char_p * len(genome.names))(*[n.encode() for n in genome.names])
@@ -175,12 +188,16 @@ class SamText:
         p = C.c_char_p()
         n = lib.tc_sam_header(self._h, C.byref(p))
         self.header = C.string_at(p, n).decode() if n else ""
-        self.batch = _BatchIn()
-        lib.tc_sam_batch(self._h, C.byref(self.batch))
+        self._ascii = _BatchIn()
+        lib.tc_sam_batch(self._h, C.byref(self._ascii))
+        self.batch = self._ascii
+        if alphabet and lib.tc_sam_pack_seq(self._h, bytes(alphabet), len(alphabet), nt) == 1:    # SEQ column in 4-bit form
+            self.batch = _BatchIn()
+            lib.tc_sam_batch(self._h, C.byref(self.batch))
 
     def cols(self):
         """numpy views of the parsed columns (valid while this object lives)."""
-        b, n = self.batch, self.n
+        b, n = self._ascii, self.n
 
         def view(ptr, dtype, count):
             if not ptr or count == 0:
@@ -235,6 +252,8 @@ class Engine:
                               % (device, lib.tc_last_error(None).decode()))
         self.device = device
         self._keep = []
+        self.alphabet = None       # bytes of the 4-bit SEQ codes once a genome is loaded (None: SEQ travels as ASCII)
+        self.seq4 = True           # send / receive SEQ in 4-bit form whenever the batch allows it
 
     def close(self):
         if getattr(self, "_ctx", None):
@@ -268,6 +287,14 @@ class Engine:
         self._check(self._lib.tc_ctx_load_genome(
             self._ctx, len(g.names), _ptr(g.chrom_len), _ptr(g.chrom_off), int(g.n_pad), _ptr(g.bases2), _ptr(g.lower1),
             len(st), _ptr(st), _ptr(en), _ptr(by)), "tc_ctx_load_genome")
+        # alphabet of the 4-bit SEQ form: the usual bases plus whatever else the genome holds
+        al = bytearray(b"ACGTacgt")
+        for c in sorted(set(np.asarray(by, dtype=np.uint8).tolist())) + [ord("N"), ord("n")]:
+            if c not in al and (len(al) < 16 or c not in b"Nn"):
+                al.append(c)
+        self.alphabet = bytes(al) if len(al) <= 16 else None       # None: too many distinct genome bytes, SEQ stays ASCII
+        if self.alphabet:
+            self._check(self._lib.tc_ctx_set_alphabet(self._ctx, self.alphabet, len(self.alphabet)), "tc_ctx_set_alphabet")
 
     def load_junctions(self, t):
         self._check(self._lib.tc_ctx_load_junctions(
@@ -279,27 +306,49 @@ class Engine:
             self._ctx, len(v.snp_key), _ptr(v.snp_key), _ptr(v.snp_alt), len(v.ins_key), _ptr(v.ins_key), _ptr(v.ins_size),
             _ptr(v.ins_aoff), _ptr(v.ins_bytes), len(v.del_key), _ptr(v.del_key), _ptr(v.del_size)), "tc_ctx_load_variants")
 
-    @staticmethod
-    def _batch_in(cols):
+    def pack_cols(self, cols, n_threads=None):
+        """cols with the SEQ column in 4-bit form (`seq` packed, `seq_poff` added), or None when a SEQ
+        byte is outside the alphabet."""
+        if not self.alphabet:
+            return None
+        n = len(cols["flag"])
+        so = np.ascontiguousarray(cols["seq_off"], dtype=np.int64)
+        out = np.zeros(int(self._lib.tc_seq_packed_size(so.ctypes.data, n)) + 64, dtype=np.uint8)
+        poff = np.zeros(n + 1, dtype=np.int64)
+        seq = cols["seq"]
+        r = self._lib.tc_seq_pack(seq.ctypes.data if seq.size else None, so.ctypes.data, n, self.alphabet, len(self.alphabet),
+                                  out.ctypes.data, poff.ctypes.data, int(n_threads or min(32, os.cpu_count() or 1)))
+        if r < 0:
+            return None
+        packed = dict(cols)
+        packed["seq"], packed["seq_poff"], packed["seq_off"] = out, poff, so
+        return packed
+
+    def _batch_in(self, cols):
+        if self.seq4 and "seq_poff" not in cols:
+            cols = self.pack_cols(cols) or cols
         b = _BatchIn()
         b.n_reads = len(cols["flag"])
         for k in ("flag", "chrom", "pos", "tags", "seq_off", "seq", "cig_off", "cig_op", "cig_len", "md_off", "md",
-                  "ji_off", "ji"):
-            a = cols[k]
+                  "ji_off", "ji", "seq_poff"):
+            a = cols.get(k)
+            if a is None:
+                continue
             assert a.flags["C_CONTIGUOUS"]
             setattr(b, k, a.ctypes.data if a.size else None)
+        self._keep = [cols]          # the arrays behind the pointers
         return b
 
     def correct(self, cols):
         """tc_correct_batch: host columns in -> BatchResult (host copies)."""
         b, out = self._batch_in(cols), _BatchOut()
         self._check(self._lib.tc_correct_batch(self._ctx, C.byref(b), C.byref(out)), "tc_correct_batch")
-        return BatchResult(out, False)
+        return BatchResult(out, False, self.alphabet)
 
     def dryrun(self, cols):
         b, out = self._batch_in(cols), _BatchOut()
         self._check(self._lib.tc_dryrun_batch(self._ctx, C.byref(b), C.byref(out)), "tc_dryrun_batch")
-        return BatchResult(out, True)
+        return BatchResult(out, True, self.alphabet)
 
     # split calls for device-resident measurement
     def upload(self, cols):
@@ -312,7 +361,7 @@ class Engine:
     def download(self, dry=False, copy=True):
         out = _BatchOut()
         self._check(self._lib.tc_batch_download(self._ctx, C.byref(out)), "tc_batch_download")
-        return BatchResult(out, dry) if copy else out
+        return BatchResult(out, dry, self.alphabet) if copy else out
 
     def raw_correct(self, b):
         """tc_correct_batch on a prepared _BatchIn; returns the raw _BatchOut (no numpy copies)."""
@@ -326,7 +375,7 @@ class Engine:
         return out
 
     def parse_sam(self, text, genome, n_threads=None):
-        return SamText(self._lib, text, genome, n_threads)
+        return SamText(self._lib, text, genome, n_threads, self.alphabet if self.seq4 else None)
 
     def timing(self):
         t = Timing()
