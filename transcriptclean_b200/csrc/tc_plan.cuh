@@ -435,28 +435,32 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
     int nte = 0; u64 cnt_cor = 0, cnt_var = 0, cnt_big = 0;   // 21-bit fields: mismatches, insertions, deletions
     int32_t ins_removed = 0; bool sawD = false;
     // merge state (tr.py:171-211)
+    // The next CIGAR op and the next MD token are fetched one step ahead, and a pre-split token
+    // stays an undecoded word until the step that looks at it, so the loads have a whole step to land.
     int64_t ci = B.cig_off[i]; const int64_t cend = B.cig_off[i + 1];
-    int32_t crem = ci < cend ? B.cig_len[ci] : 0;
+    int cop = ci < cend ? B.cig_op[ci] : 0; int32_t crem = ci < cend ? B.cig_len[ci] : 0;
     MdCur md; md.i = 0; md.len = 0; md.p = 0; md.tok = 0;
-    int mop = 0; int32_t mrem = 0; bool have_md = false;
-    if (stage1) { md_cursor(P, B, i, md); have_md = md_next(md, mop, mrem); }
+    int mop = 0; int32_t mrem = 0; bool have_md = false; uint32_t mw = 0; bool mraw = false;
+#define TC_NEXT_CIGAR() do { ci++; if (ci < cend) { cop = B.cig_op[ci]; crem = B.cig_len[ci]; } } while (0)
+#define TC_NEXT_MD() do { if (md.tok) { have_md = md.i < md.len; if (have_md) { mw = md.tok[md.i++]; mraw = true; } } else have_md = md_next(md, mop, mrem); } while (0)
+    if (stage1) { md_cursor(P, B, i, md); TC_NEXT_MD(); }
     bool fail = false;
     while (true) {
         int op; int32_t ct;
         if (stage1) {
             if (!have_md && ci >= cend) break;
             if (ci >= cend) { fail = true; break; }                   // cigarOperation[cigarIndex] IndexError (Q14)
-            int cop = B.cig_op[ci];
-            if (cop == 'H' || cop == 'S' || cop == 'I' || cop == 'N') { op = cop; ct = crem; ci++; if (ci < cend) crem = B.cig_len[ci]; }
+            if (cop == 'H' || cop == 'S' || cop == 'I' || cop == 'N') { op = cop; ct = crem; TC_NEXT_CIGAR(); }
             else {
                 if (!have_md) { fail = true; break; }                 // mdCount[mdIndex] IndexError
-                if (crem < mrem) { mrem -= crem; op = cop; ct = crem; ci++; if (ci < cend) crem = B.cig_len[ci]; }
-                else if (crem > mrem) { crem -= mrem; op = mop; ct = mrem; have_md = md_next(md, mop, mrem); }
-                else { op = mop; ct = mrem; have_md = md_next(md, mop, mrem); ci++; if (ci < cend) crem = B.cig_len[ci]; }
+                if (mraw) { const uint32_t k = mw >> 30; mop = k == 0 ? 'M' : k == 1 ? 'X' : 'D'; mrem = (int32_t)(mw & MD_TOK_MAX); mraw = false; }
+                if (crem < mrem) { mrem -= crem; op = cop; ct = crem; TC_NEXT_CIGAR(); }
+                else if (crem > mrem) { crem -= mrem; op = mop; ct = mrem; TC_NEXT_MD(); }
+                else { op = mop; ct = mrem; TC_NEXT_MD(); TC_NEXT_CIGAR(); }
             }
         } else {
             if (ci >= cend) break;
-            op = B.cig_op[ci]; ct = B.cig_len[ci]; ci++;
+            op = cop; ct = crem; TC_NEXT_CIGAR();
         }
         // One straight-line body for every op kind (lanes of a warp sit on different kinds, so a
         // switch with six private copies of push / te_put / op would be executed six times over):
@@ -490,6 +494,8 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
         if (isM || isX || isS || isI) q += ct;
         if (isM || isX || isD || isNH) g += ct;
     }
+#undef TC_NEXT_CIGAR
+#undef TC_NEXT_MD
     if (fail) {                                                       // whole-read fallback (Q13): stage 1 raised
         W.status[i] = st | TC_ST_FALLBACK;                            // before stages 2-3 zeroed their counters
         return;
