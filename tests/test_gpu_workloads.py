@@ -113,3 +113,39 @@ def test_sam_text_fast_path_on_gpu(setup):
     assert header == "@HD\tVN:1.0\n"
     diff = pipeline.first_diff({k: v.decode() for k, v in got.items()}, want)
     assert diff is None, diff
+
+
+def test_plane_offsets_beyond_2_31(setup):
+    """hg38-scale layout: the contig the reads map to starts 2.3 Gb into the genome planes, so every
+    plane index exceeds 2^31 (chromosome id 1 in the table keys).  Results must equal the ones of
+    the same reads on the small single-contig image."""
+    from tools.workload import variants_from_reads
+    from transcriptclean_b200.genome import GenomeImage
+    from transcriptclean_b200.tables import build_sj_tables, build_variant_tables
+    w, gi, sjf, eng, d = setup
+    n = 20000
+    cols, nm = w.reads("ont", n, seed_offset=11)
+    vcf = goldens.write_rows(variants_from_reads(w, cols, 0, 3000, frac=0.3), d + "/v_big.vcf")
+
+    def run(image, cols):
+        eng.set_options()
+        eng.load_genome(image)
+        eng.load_junctions(build_sj_tables(sjf, {w.chrom}, image.index))
+        eng.load_variants(build_variant_tables(vcf, 5, image.index))
+        return eng.correct(cols)
+
+    small = run(gi, cols)
+    big = GenomeImage(["filler", w.chrom], [2_300_000_000, w.chrom_len])
+    big._put(int(big.chrom_off[1]), w.genome)
+    assert int(big.chrom_off[1]) > 2 ** 31
+    cols2 = dict(cols)
+    cols2["chrom"] = np.where(cols["chrom"] == 0, 1, cols["chrom"]).astype(np.int32)
+    large = run(big, cols2)
+    for name in ("status", "counters", "nm", "seq_len", "seq_off", "cig_off", "cig_op", "cig_len", "jn_off", "jm", "ji", "te_off", "md_len"):
+        assert np.array_equal(getattr(small, name), getattr(large, name)), name
+    assert np.array_equal(small.te, large.te)
+    for i in range(0, n, 7):
+        a, L = int(small.seq_off[i]), int(small.seq_len[i])
+        assert small.seq[a:a + L].tobytes() == large.seq[a:a + L].tobytes(), i
+        assert small.md[small.md_off[i]:small.md_off[i] + small.md_len[i]].tobytes() == large.md[large.md_off[i]:large.md_off[i] + large.md_len[i]].tobytes(), i
+    assert int((np.asarray(small.counters)[:, 2] > 0).sum()) + int((np.asarray(small.counters)[:, 5] > 0).sum()) > 100   # variant hits happened
