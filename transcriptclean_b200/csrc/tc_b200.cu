@@ -762,13 +762,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
             }
             __syncwarp();
             // (B) bulk copy, 16 output bytes per lane, with the shift in force at the chunk start
+            // (32-bit offsets from the read's first word; the clamps keep the gather inside the SEQ buffer)
+            const uint32_t* const rp = S32 + (in_base >> 2); const int rsub = (int)(in_base & 3);
+            const int64_t wlo64 = seq_lo - (in_base >> 2), whi64 = seq_hi - 5 - (in_base >> 2);
+            const int wlo = wlo64 < -0x40000000ll ? -0x40000000 : (int)wlo64, whi = whi64 > 0x40000000ll ? 0x40000000 : (int)whi64;
             for (int c = lane; c < nchunk; c += 32) {
                 const int p = c << 4; const int k = SM.chunk_bp[c];
-                const int64_t a = in_base + p + (nbp ? (int)SM.bp_shift[k] : 0);
-                int64_t wi = a >> 2; const int sh = (int)(a & 3) * 8;
-                if (wi < seq_lo) wi = seq_lo;
-                if (wi + 4 >= seq_hi) wi = seq_hi - 5;
-                const uint32_t x0 = S32[wi], x1 = S32[wi + 1], x2 = S32[wi + 2], x3 = S32[wi + 3], x4 = S32[wi + 4];
+                const int a = rsub + p + (nbp ? (int)SM.bp_shift[k] : 0);
+                int wi = a >> 2; const int sh = (a & 3) * 8;
+                wi = wi < wlo ? wlo : wi; wi = wi > whi ? whi : wi;
+                const uint32_t* xp = rp + wi;
+                const uint32_t x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3], x4 = xp[4];
                 uint4 o; o.x = __funnelshift_r(x0, x1, sh); o.y = __funnelshift_r(x1, x2, sh); o.z = __funnelshift_r(x2, x3, sh); o.w = __funnelshift_r(x3, x4, sh);
                 *reinterpret_cast<uint4*>(SM.seq + p) = o;
             }
@@ -779,11 +783,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
                 if (b & 15) {
                     int end = (b | 15) + 1; if (end > out_len) end = out_len;
                     if (k + 1 < nbp && (int)SM.bp_pos[k + 1] < end) end = SM.bp_pos[k + 1];
-                    const int64_t a = in_base + b + (int)SM.bp_shift[k];
-                    int64_t wi = a >> 2; const int sh = (int)(a & 3) * 8;
-                    if (wi < seq_lo) wi = seq_lo;
-                    if (wi + 4 >= seq_hi) wi = seq_hi - 5;
-                    const uint32_t x0 = S32[wi], x1 = S32[wi + 1], x2 = S32[wi + 2], x3 = S32[wi + 3], x4 = S32[wi + 4];
+                    const int a = rsub + b + (int)SM.bp_shift[k];
+                    int wi = a >> 2; const int sh = (a & 3) * 8;
+                    wi = wi < wlo ? wlo : wi; wi = wi > whi ? whi : wi;
+                    const uint32_t* xp = rp + wi;
+                    const uint32_t x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3], x4 = xp[4];
                     uint32_t w[4]; w[0] = __funnelshift_r(x0, x1, sh); w[1] = __funnelshift_r(x1, x2, sh); w[2] = __funnelshift_r(x2, x3, sh); w[3] = __funnelshift_r(x3, x4, sh);
                     const int n = end - b;
 #pragma unroll
@@ -848,7 +852,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
                     ibases += op == 'I' ? ct : 0; dbases += isD ? ct : 0;
                     if (isM) {
                         const int idx = nrun + __popc(mM & lt);
-                        if (idx < EMIT_MAXRUN && gcur + gs < 0x7fffffffll) { run_q[idx] = (uint16_t)(qcur + qs); run_g[idx] = (int32_t)(gcur + gs); run_ct[idx] = (uint16_t)ct; }
+                        if (idx < EMIT_MAXRUN && gcur + gs < 0x7fff0000ll) { run_q[idx] = (uint16_t)(qcur + qs); run_g[idx] = (int32_t)(gcur + gs); run_ct[idx] = (uint16_t)ct; }
                         else ovf = true;
                         // literal runs (N, IUPAC) under this M run?  (blocks of 256 bases; a run spans at most 17)
                         const int64_t ga = gbase + gcur + gs;
@@ -879,6 +883,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
                         if (lane < __popc(has)) { my_w = SM.rb_w[lane]; my_coff = SM.rb_coff[lane]; my_goff = SM.rb_goff[lane]; }
                     }
                     int rbase = 0;
+                    const uint32_t* const gw0p = P.G.g2 + (gbase >> 4); const int gsub = (int)(gbase & 15);
                     for (int t0 = 0; t0 < nit; t0 += 32) {
                         const int t = t0 + lane;
                         const unsigned word = __reduce_or_sync(FULL, (my_w >= t0 && my_w < t0 + 32) ? 1u << (my_w - t0) : 0u);
@@ -887,9 +892,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
                         const int coff = __shfl_sync(FULL, my_coff, r & 31), goff = __shfl_sync(FULL, my_goff, r & 31);
                         if (t < nit) {
                             const int p = (t + coff) << 4;                       // chunk start (query offset)
-                            const int64_t gb = gbase + p + goff;                 // plane index under chunk byte 0
-                            const uint32_t* gp = P.G.g2 + (gb >> 4);
-                            const uint32_t gw = __funnelshift_r(gp[0], gp[1], (int)(gb & 15) * 2);
+                            const int gb = gsub + p + goff;                      // bases from the read's first genome word to chunk byte 0
+                            const uint32_t* gp = gw0p + (gb >> 4);
+                            const uint32_t gw = __funnelshift_r(gp[0], gp[1], (gb & 15) * 2);
                             const uint4 x = *reinterpret_cast<const uint4*>(SM.seq + p);
                             const uint32_t d0 = (x.x & 0xDFDFDFDFu) ^ lut[gw & 255u], d1 = (x.y & 0xDFDFDFDFu) ^ lut[(gw >> 8) & 255u];
                             const uint32_t d2 = (x.z & 0xDFDFDFDFu) ^ lut[(gw >> 16) & 255u], d3 = (x.w & 0xDFDFDFDFu) ^ lut[gw >> 24];

@@ -735,12 +735,19 @@ TC_HD bool junction_init_read(const Params& P, int64_t i) {
         }
     }
     bool canon = true, annot = true;
-    for (int k = 0; k < nj; k++) {
-        int32_t* r = J + k * JN_STRIDE; r[2] = r[0]; r[3] = r[1];
-        int code = 0; junction_code(P, chrom, strand, r[0], r[1], r[2], r[3], code);
-        r[4] = code; r[5] = r[0]; r[6] = r[1]; r[7] = code;
-        if (code == 0 || code == 20) canon = false;
-        if (code < 20) annot = false;
+    for (int k0 = 0; k0 < nj; k0 += 4) {                // four junctions at a time: their genome / table loads overlap
+        int32_t b0[4], b1[4]; int code[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (k0 + u < nj) { b0[u] = J[(k0 + u) * JN_STRIDE]; b1[u] = J[(k0 + u) * JN_STRIDE + 1]; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (k0 + u < nj) { code[u] = 0; junction_code(P, chrom, strand, b0[u], b1[u], b0[u], b1[u], code[u]); }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (k0 + u < nj) {
+            int32_t* r = J + (k0 + u) * JN_STRIDE;
+            r[2] = b0[u]; r[3] = b1[u]; r[4] = code[u]; r[5] = b0[u]; r[6] = b1[u]; r[7] = code[u];
+            if (code[u] == 0 || code[u] == 20) canon = false;
+            if (code[u] < 20) annot = false;
+        }
     }
     if (!(tags & TAG_JM)) st |= TC_ST_JM_DEVICE | TC_ST_JI_DEVICE;     // tr.py:69-70
     else if (!(tags & TAG_JI)) st |= TC_ST_JI_DEVICE;                  // tr.py:56-57
