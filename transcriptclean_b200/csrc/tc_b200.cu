@@ -32,6 +32,7 @@ struct OutDev {
     uint8_t* md_pool; unsigned long long* md_cursor; int64_t md_cap;
     int64_t md_inline;       // MD values of <= 8 bytes live at md_inline + 8*i (no allocation); longer ones in the pool behind
     uint8_t* seq; uint8_t* cig_op; int32_t* cig_len; tc_te* te; int8_t* jm; int32_t* ji;
+    int32_t* exact_list; unsigned* exact_count;   // reads whose NM/MD need the token-emitting walk (k_nmmd_exact)
 };
 struct InitDev { uint8_t* pool; unsigned long long* cursor; int64_t cap; };
 
@@ -818,7 +819,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
         // ---- NM / MD
         if ((pflags & 1) && !(dbg & 4)) {
             __syncwarp();                                              // SM tables are dead from here on: their space holds the run list
-            int nm = 0, len = 0; int64_t off = 0; bool none = false; bool done = false;
+            int nm = 0, len = 0; int64_t off = 0; bool done = false;
             if (fast && ncig <= 32 * 4) {
                 // tier 1: run list (query offset, reference offset, length) of the M ops, lane-parallel
                 uint16_t* run_q = SM.run_q; uint16_t* run_ct = SM.run_ct; int32_t* run_g = SM.run_g;
@@ -959,14 +960,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
                     }
                 }
             }
-            if (!done) {
-                if (lane == 0) atomicAdd(O.md_cursor + 1, 1ull);             // statistics: reads that needed the exact NM/MD path
-                if (fast) nmmd_to_pool<true>(P.G, SM.seq, lut, cs, chrom, pos, lane, O.md_cursor, O.md_cap, O.md_pool, O.md_inline + 8 * i, nm, len, off, none);
-                else nmmd_to_pool<false>(P.G, out_seq, lut, cs, chrom, pos, lane, O.md_cursor, O.md_cap, O.md_pool, O.md_inline + 8 * i, nm, len, off, none);
+            if (!done) {                                               // a difference to the genome, a literal run, the contig end,
+                if (lane == 0) O.exact_list[atomicAdd(O.exact_count, 1u)] = (int32_t)i;   // a long read: k_nmmd_exact walks it
+            } else {
+                st = (st & ~(uint32_t)TC_ST_NMMD_NONE) | TC_ST_NMMD_DEVICE;
+                if (lane == 0) { O.nm[i] = nm + nm_extra; O.md_off[i] = off < 0 ? 0 : off; O.md_len[i] = off < 0 ? 0 : len; W.status[i] = st; }
             }
-            st = (st & ~(uint32_t)TC_ST_NMMD_NONE) | TC_ST_NMMD_DEVICE;
-            if (none) st |= TC_ST_NMMD_NONE;
-            if (lane == 0) { O.nm[i] = nm + nm_extra; O.md_off[i] = off < 0 ? 0 : off; O.md_len[i] = off < 0 ? 0 : len; W.status[i] = st; }
         } else if (st & TC_ST_NMMD_DEVICE) {                           // generated at init and never refreshed
             const int len = W.md_init_len[i];
             const int64_t off = pool_grab(O.md_cursor, O.md_cap, len, lane);
@@ -975,6 +974,31 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
         } else if (lane == 0) { O.nm[i] = 0; O.md_off[i] = 0; O.md_len[i] = 0; }
         __syncwarp();
         pw = pw_next;
+    }
+}
+
+// getNMandMDFlags (tr.py:280-342) for the reads k_emit could not settle with its clean-read check:
+// the token-emitting walk over the final SEQ and CIGAR (both already in the output arrays).
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_nmmd_exact(Params P, OutDev O) {
+    __shared__ uint32_t lut[256];
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) {
+        const uint32_t acgt = 0x54474341u;
+        lut[t] = ((acgt >> (8 * (t & 3))) & 255u) | (((acgt >> (8 * ((t >> 2) & 3))) & 255u) << 8) |
+                 (((acgt >> (8 * ((t >> 4) & 3))) & 255u) << 16) | (((acgt >> (8 * ((t >> 6) & 3))) & 255u) << 24);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = (int64_t)gridDim.x * WARPS_PER_BLOCK, nl = (int64_t)*O.exact_count;
+    for (int64_t t = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); t < nl; t += nw) {
+        const int64_t i = O.exact_list[t];
+        const int32_t* w = P.W.plan[i].w;
+        const int64_t o_seq = ((int64_t)w[EP_OSEQ_HI] << 32) | (uint32_t)w[EP_OSEQ_LO], o_cig = ((int64_t)w[EP_OCIG_HI] << 32) | (uint32_t)w[EP_OCIG_LO];
+        CigSrc cs; cs.packed = 0; cs.op = O.cig_op + o_cig; cs.len = O.cig_len + o_cig; cs.n = w[EP_NCIG];
+        int nm, len; int64_t off; bool none;
+        nmmd_to_pool<true>(P.G, O.seq + o_seq, lut, cs, w[EP_CHROM], (int64_t)w[EP_POS], lane, O.md_cursor, O.md_cap, O.md_pool, O.md_inline + 8 * i, nm, len, off, none);
+        uint32_t st = ((uint32_t)w[EP_STATUS] & ~(uint32_t)TC_ST_NMMD_NONE) | TC_ST_NMMD_DEVICE;
+        if (none) st |= TC_ST_NMMD_NONE;
+        if (lane == 0) { O.nm[i] = nm + w[EP_NMEXTRA]; O.md_off[i] = off < 0 ? 0 : off; O.md_len[i] = off < 0 ? 0 : len; P.W.status[i] = st; }
     }
 }
 
@@ -1469,6 +1493,7 @@ static OutDev make_out(Slot& S, unsigned long long* cur, int64_t md_cap) {
     O.md_pool = (uint8_t*)S.o_md_pool.p - S.base_md; O.md_cursor = cur; O.md_cap = S.base_md + md_cap; O.md_inline = S.base_md;
     O.seq = (uint8_t*)S.o_seq.p - S.base_seq; O.cig_op = (uint8_t*)S.o_cig_op.p - S.base_cig; O.cig_len = (int32_t*)S.o_cig_len.p - S.base_cig;
     O.te = (tc_te*)S.o_te.p - S.base_te; O.jm = (int8_t*)S.o_jm.p - S.base_jn; O.ji = (int32_t*)S.o_ji.p - 2 * S.base_jn;
+    O.exact_list = (int32_t*)S.w_fix_list.p; O.exact_count = cur ? (unsigned*)(cur + 1) : nullptr;   // (the junction stage is done with the list)
     return O;
 }
 
@@ -1589,6 +1614,7 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
         k_emit<<<ge, WARPS_PER_BLOCK * 32, EMIT_SMEM_BYTES, st>>>(P, O, dry, S.seq_lo_word, S.seq_hi_word); ctx->tm.launches += 2;
         CK(cudaGetLastError());
         if (timed && attempt == 0) CK(cudaEventRecord(ctx->ev[8], st));
+        if (!dry) { k_nmmd_exact<<<gw, WARPS_PER_BLOCK * 32, 0, st>>>(P, O); ctx->tm.launches++; CK(cudaGetLastError()); }
         if (be_read_i64(ctx, st, (const int64_t*)cur, tot) || be_read_i64(ctx, st, (const int64_t*)cur + 1, tot + 6) || be_sync(ctx, st)) return TC_E_CUDA;
         if (tot[0] - S.base_md <= md_cap) { S.md_used = tot[0] - S.base_md; ctx->tm.exact_nmmd_reads += tot[6]; break; }
         if (attempt >= 2) { ctx->err = "MD pool overflow"; return TC_E_CUDA; }
