@@ -90,14 +90,22 @@ def correct_batch_text(sam_transcripts, options, refs):
                                warn=print)
 
 
-def correct_sam_text(text, options, refs, dry=False):
+def correct_sam_text(text, options, refs, dry=False, consume=None):
     """Fast path for whole SAM texts (bytes): parsing and rendering in the library's C++ host code,
-    correction on the GPU.  Returns (header str, {"sam","fa","log","te"} as bytes)."""
+    correction on the GPU.  Returns (header str, {"sam","fa","log","te"} as bytes).  With
+    `consume(header, views)` the four texts are handed over as memoryviews of the library's own
+    buffers (no copies; only valid during the call) and (header, None) is returned."""
     _set_engine_options(options, refs)
     st = refs.engine.parse_sam(text, refs.genome)
     try:
         raw = refs.engine.raw_dryrun(st.batch) if dry else refs.engine.raw_correct(st.batch)
-        out = st.render(raw, bool(_opt(options, "primaryOnly", False)), bool(_opt(options, "canonOnly", False)), dry)
+        out = st.render(raw, bool(_opt(options, "primaryOnly", False)), bool(_opt(options, "canonOnly", False)), dry,
+                        copy=consume is None)
+        if consume is not None:
+            consume(st.header, out)
+            for v in out.values():
+                v.release()
+            out = None
         return st.header, out
     finally:
         st.close()

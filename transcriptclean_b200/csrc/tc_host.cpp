@@ -14,6 +14,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -33,6 +35,13 @@ struct Part {                       // what one parser thread produces
     std::vector<int64_t> other_off; std::vector<Span> other;
     std::vector<Span> header;
     std::string err;
+    void reset() {                   // empty, capacity kept: the parts of a host thread are reused from batch to batch
+        flag.clear(); chrom.clear(); pos.clear(); tags.clear(); cls.clear(); seq_len.clear(); cig_n.clear(); md_n.clear(); ji_n.clear();
+        seq.clear(); cig_op.clear(); md.clear(); cig_len.clear(); ji.clear(); line.clear(); cigar.clear(); other_off.clear(); other.clear();
+        for (auto& v : f) v.clear();
+        for (auto& v : tg) v.clear();
+        header.clear(); err.clear();
+    }
 };
 
 template <class V> inline void put_bytes(V& v, const char* p, int64_t n) {
@@ -307,6 +316,26 @@ void render_range(const tc_sam* S, const tc_batch_out* R, int64_t a, int64_t b, 
     }
 }
 
+std::mutex g_pool_mu; std::vector<tc_sam*> g_pool;
+tc_sam* sam_acquire() {
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    if (g_pool.empty()) return new tc_sam();
+    tc_sam* S = g_pool.back(); g_pool.pop_back();
+    return S;
+}
+void sam_release(tc_sam* S) {
+    if (!S) return;
+    S->text = nullptr; S->len = 0; S->n = 0; S->packed = false; S->n_alpha = 0;
+    S->flag.clear(); S->chrom.clear(); S->pos.clear(); S->tags.clear(); S->cls.clear(); S->seq_off.clear(); S->cig_off.clear(); S->md_off.clear();
+    S->ji_off.clear(); S->seq.clear(); S->cig_op.clear(); S->md.clear(); S->cig_len.clear(); S->ji.clear(); S->line.clear(); S->cigar.clear();
+    for (auto& v : S->f) v.clear();
+    for (auto& v : S->tg) v.clear();
+    S->other_off.clear(); S->other.clear(); S->header.clear(); S->seqp.clear(); S->seq_poff.clear();
+    S->out_sam.clear(); S->out_fa.clear(); S->out_log.clear(); S->out_te.clear();
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    if (g_pool.size() < 2) g_pool.push_back(S); else delete S;
+}
+
 }  // namespace
 
 extern "C" {
@@ -322,12 +351,17 @@ tc_sam* tc_sam_parse(const char* text, int64_t len, int32_t n_chrom, const char*
     cut[0] = 0;
     for (int k = 1; k < T; k++) { int64_t p = len / T * k; while (p < len && text[p] != '\n') p++; cut[k] = p < len ? p + 1 : len; }
     for (int k = 1; k <= T; k++) if (cut[k] < cut[k - 1]) cut[k] = cut[k - 1];
-    std::vector<Part> parts((size_t)T);
+    // Buffers are recycled (per calling thread / through a small pool of tc_sam objects): touching
+    // fresh pages costs more than the parsing itself.
+    static thread_local std::vector<Part> parts_tl;
+    std::vector<Part>& parts = parts_tl;
+    if (parts.size() < (size_t)T) parts.resize((size_t)T);
+    for (auto& p : parts) p.reset();
     std::vector<std::thread> th;
     for (int k = 0; k < T; k++) th.emplace_back(parse_range, text, cut[k], cut[k + 1], std::cref(cmap), chrom_len, std::ref(parts[(size_t)k]));
     for (auto& t : th) t.join();
-    for (auto& p : parts) if (!p.err.empty()) { set_err(err, err_cap, p.err); return nullptr; }
-    tc_sam* S = new tc_sam();
+    for (int k = 0; k < T; k++) if (!parts[(size_t)k].err.empty()) { set_err(err, err_cap, parts[(size_t)k].err); return nullptr; }
+    tc_sam* S = sam_acquire();
     S->text = text; S->len = len;
     // totals, then every part is copied to its place by its own thread
     std::vector<size_t> r0((size_t)T + 1, 0), s0((size_t)T + 1, 0), c0((size_t)T + 1, 0), m0((size_t)T + 1, 0), j0((size_t)T + 1, 0), o0((size_t)T + 1, 0);
@@ -355,7 +389,6 @@ tc_sam* tc_sam_parse(const char* text, int64_t len, int32_t n_chrom, const char*
             S->seq_off[r + i] = so; S->cig_off[r + i] = co; S->md_off[r + i] = mo; S->ji_off[r + i] = jo; S->other_off[r + i] = (int64_t)o0[k] + p.other_off[i];
             so += p.seq_len[i]; co += p.cig_n[i]; mo += p.md_n[i]; jo += p.ji_n[i];
         }
-        p = Part();
     };
     {
         std::vector<std::thread> tp;
@@ -392,7 +425,7 @@ char* tc_sam_rnames(const char* text, int64_t len, int64_t* out_len) {
 }
 void tc_free(void* p) { free(p); }
 
-void tc_sam_free(tc_sam* S) { delete S; }
+void tc_sam_free(tc_sam* S) { sam_release(S); }
 int64_t tc_sam_n_reads(const tc_sam* S) { return S ? S->n : 0; }
 int64_t tc_sam_header(const tc_sam* S, const char** text) { if (!S) return 0; if (text) *text = S->header.data(); return (int64_t)S->header.size(); }
 
@@ -467,7 +500,8 @@ int tc_sam_render(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_
     }
     int T = n_threads < 1 ? 1 : n_threads;
     if (S->n < 4096) T = 1;
-    std::vector<std::string> ps((size_t)T), pf((size_t)T), pl((size_t)T), pt((size_t)T);
+    static thread_local std::vector<std::string> ps, pf, pl, pt;      // per calling thread, capacity kept between batches
+    for (auto* v : {&ps, &pf, &pl, &pt}) { if (v->size() < (size_t)T) v->resize((size_t)T); for (auto& x : *v) x.clear(); }
     std::vector<std::thread> th;
     for (int k = 0; k < T; k++) {
         const int64_t a = S->n * k / T, b = S->n * (k + 1) / T;
@@ -475,12 +509,16 @@ int tc_sam_render(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_
                         std::ref(pl[(size_t)k]), std::ref(pt[(size_t)k]));
     }
     for (auto& t : th) t.join();
+    const bool tm = getenv("TC_HOST_TIMING") != nullptr;
+    auto now = [] { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+    const double t_r = now();
     auto join = [](std::string& dst, std::vector<std::string>& src) {
         size_t tot = 0; for (auto& s : src) tot += s.size();
         dst.clear(); dst.reserve(tot);
-        for (auto& s : src) { dst.append(s); std::string().swap(s); }
+        for (auto& s : src) dst.append(s);
     };
     join(S->out_sam, ps); join(S->out_fa, pf); join(S->out_log, pl); join(S->out_te, pt);
+    if (tm) fprintf(stderr, "tc_sam_render: threads done at +0, join %.3f s\n", now() - t_r);
     *sam = S->out_sam.data(); *sam_len = (int64_t)S->out_sam.size(); *fa = S->out_fa.data(); *fa_len = (int64_t)S->out_fa.size();
     *lg = S->out_log.data(); *lg_len = (int64_t)S->out_log.size(); *te = S->out_te.data(); *te_len = (int64_t)S->out_te.size();
     return TC_OK;

@@ -213,8 +213,9 @@ class SamText:
                 "cig_op": view(b.cig_op, np.uint8, int(co[-1])), "cig_len": view(b.cig_len, np.int32, int(co[-1])), "md_off": mo,
                 "md": view(b.md, np.uint8, int(mo[-1])), "ji_off": jo, "ji": view(b.ji, np.int32, int(jo[-1]))}
 
-    def render(self, raw_out, primary_only=False, canon_only=False, dry=False):
-        """raw_out: the _BatchOut of Engine.raw_correct / raw_dryrun for this batch -> four bytes objects."""
+    def render(self, raw_out, primary_only=False, canon_only=False, dry=False, copy=True):
+        """raw_out: the _BatchOut of Engine.raw_correct / raw_dryrun for this batch -> four bytes objects
+        (copy=False: memoryviews of the library's buffers, valid until this object is closed)."""
         ptr = [C.c_void_p() for _ in range(4)]
         ln = [C.c_int64() for _ in range(4)]
         err = C.create_string_buffer(1024)
@@ -224,7 +225,10 @@ class SamText:
         rc = self._lib.tc_sam_render(self._h, C.byref(raw_out), int(primary_only), int(canon_only), int(dry), self._nt, *args, err, 1024)
         if rc != 0:
             raise EngineError(err.value.decode())
-        return {k: C.string_at(p, l.value) if l.value else b"" for k, p, l in zip(("sam", "fa", "log", "te"), ptr, ln)}
+        if copy:
+            return {k: C.string_at(p, l.value) if l.value else b"" for k, p, l in zip(("sam", "fa", "log", "te"), ptr, ln)}
+        return {k: memoryview((C.c_char * l.value).from_address(p.value)).cast("B") if l.value else memoryview(b"")
+                for k, p, l in zip(("sam", "fa", "log", "te"), ptr, ln)}
 
     def close(self):
         if getattr(self, "_h", None):
