@@ -1145,15 +1145,21 @@ __global__ void __launch_bounds__(256) k_seq_unpack(int64_t n, const int64_t* se
         const int64_t o = seq_off[i]; const int L = (int)(seq_off[i + 1] - o);
         const uint32_t* src = reinterpret_cast<const uint32_t*>(packed + poff[i]);
         uint8_t* dst = seq + o;
-        const bool al = (reinterpret_cast<uintptr_t>(dst) & 3) == 0;
+        const int mis = (int)(reinterpret_cast<uintptr_t>(dst) & 3);   // the same for every 8-byte group of the row
         for (int w = lane; w * 8 < L; w += 32) {
             const uint32_t x = src[w];
             const uint32_t lo = lut[x & 255u] | ((uint32_t)lut[(x >> 8) & 255u] << 16), hi = lut[(x >> 16) & 255u] | ((uint32_t)lut[x >> 24] << 16);
-            const int left = L - w * 8;
-            if (al && left >= 8) { reinterpret_cast<uint32_t*>(dst)[2 * w] = lo; reinterpret_cast<uint32_t*>(dst)[2 * w + 1] = hi; }
-            else {
+            const int left = L - w * 8; uint8_t* d = dst + w * 8;
+            if (left < 8) {
 #pragma unroll
-                for (int k = 0; k < 8; k++) if (k < left) dst[w * 8 + k] = (uint8_t)((k < 4 ? lo : hi) >> (8 * (k & 3)));
+                for (int k = 0; k < 7; k++) if (k < left) d[k] = (uint8_t)((k < 4 ? lo : hi) >> (8 * (k & 3)));
+            } else if (mis == 0) { reinterpret_cast<uint32_t*>(d)[0] = lo; reinterpret_cast<uint32_t*>(d)[1] = hi; }
+            else if (mis == 2) {                       // widest naturally aligned stores: 2 + 4 + 2
+                *reinterpret_cast<uint16_t*>(d) = (uint16_t)lo; *reinterpret_cast<uint32_t*>(d + 2) = (lo >> 16) | (hi << 16); *reinterpret_cast<uint16_t*>(d + 6) = (uint16_t)(hi >> 16);
+            } else if (mis == 1) {                     // 1 + 2 + 4 + 1
+                d[0] = (uint8_t)lo; *reinterpret_cast<uint16_t*>(d + 1) = (uint16_t)(lo >> 8); *reinterpret_cast<uint32_t*>(d + 3) = (lo >> 24) | (hi << 8); d[7] = (uint8_t)(hi >> 24);
+            } else {                                   // 1 + 4 + 2 + 1
+                d[0] = (uint8_t)lo; *reinterpret_cast<uint32_t*>(d + 1) = (lo >> 8) | (hi << 24); *reinterpret_cast<uint16_t*>(d + 5) = (uint16_t)(hi >> 8); d[7] = (uint8_t)(hi >> 24);
             }
         }
     }
