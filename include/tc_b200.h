@@ -202,6 +202,8 @@ void tc_sam_free(tc_sam* s);
 /* distinct RNAMEs of the alignment lines, newline-joined (split_SAM's chromosome set, TC.py:535); free with tc_free */
 char* tc_sam_rnames(const char* text, int64_t len, int64_t* out_len);
 void tc_free(void* p);
+/* the '@' lines of a SAM text (trimmed, newline-terminated), for callers that stream a file in blocks; free with tc_free */
+char* tc_sam_header_lines(const char* text, int64_t len, int64_t* out_len);
 int64_t tc_sam_n_reads(const tc_sam* s);
 int64_t tc_sam_header(const tc_sam* s, const char** text);      /* '@' lines, newline-terminated */
 void tc_sam_batch(const tc_sam* s, tc_batch_in* out);            /* view of the parsed columns */

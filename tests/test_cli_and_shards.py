@@ -57,6 +57,24 @@ def test_cli_end_to_end_files(n_engines):
     assert not os.path.exists(d + "/TC_tmp")
 
 
+@pytest.mark.parametrize("n_engines", [1, 2])
+def test_cli_streams_the_sam_file_in_blocks(n_engines, monkeypatch):
+    """Blocks of a few kB (dozens per file, header lines only in the first): the same four files."""
+    case, d = _case_files(34, n_reads=150)
+    monkeypatch.setenv("TC_CLI_BLOCK_BYTES", "6000")
+    assert len(list(cli.sam_blocks(d + "/in.sam", 6000))) > 10
+    assert b"".join(cli.sam_blocks(d + "/in.sam", 6000)) == open(d + "/in.sam", "rb").read()
+    o = cli.get_options(["-s", d + "/in.sam", "-g", d + "/g.fa", "-j", d + "/sj.tab", "-v", d + "/v.vcf", "-o", d + "/TC"])
+    cli.run(o, engines=[HostSimEngine() for _ in range(n_engines)])
+    want = pipeline.oracle_texts(case.genome, case.lines, d + "/sj.tab", d + "/v.vcf", {})
+    sam = open(d + "/TC_clean.sam").read()
+    assert sam.startswith("@HD")
+    assert "".join(l + "\n" for l in sam.splitlines() if not l.startswith("@")) == want["sam"]
+    assert open(d + "/TC_clean.fa").read() == want["fa"]
+    assert open(d + "/TC_clean.log").read() == cli.LOG_HEADER + want["log"]
+    assert open(d + "/TC_clean.TE.log").read() == cli.TE_HEADER + want["te"]
+
+
 def test_cli_dry_run_writes_only_logs():
     case = synth.make_case(32, n_reads=80, quirks=False)
     d = tempfile.mkdtemp(prefix="tc_cli_")

@@ -107,19 +107,22 @@ def validate_chroms(genome, vcf_file, sam_chroms):
                                "SAM file.\nSAM chromosomes:\n" + fmt(sam_chroms) + "\nVCF chromosomes:\n" + fmt(vcf_chroms) + "\n")
 
 
-def write_outputs(options, header, texts):
-    """combine_outputs (TC.py:604-663): headers + bodies; no SAM / FASTA in --dryRun.
-    header: the '@' lines, newline-terminated; texts: bytes."""
-    pre = options.outprefix
-    with open(pre + "_clean.log", "wb") as f:
-        f.write(LOG_HEADER.encode() + texts["log"])
-    with open(pre + "_clean.TE.log", "wb") as f:
-        f.write(TE_HEADER.encode() + texts["te"])
-    if not options.dryRun:
-        with open(pre + "_clean.sam", "wb") as f:
-            f.write(header.encode() + texts["sam"])
-        with open(pre + "_clean.fa", "wb") as f:
-            f.write(texts["fa"])
+def sam_blocks(path, block_bytes):
+    """The SAM file as bytes blocks of about block_bytes that end at line boundaries."""
+    with open(path, "rb") as f:
+        rest = b""
+        while True:
+            buf = f.read(block_bytes)
+            if not buf:
+                if rest:
+                    yield rest
+                return
+            cut = buf.rfind(b"\n")
+            if cut < 0:
+                rest += buf
+                continue
+            yield rest + buf[:cut + 1]
+            rest = buf[cut + 1:]
 
 
 def n_gpus_available():
@@ -145,18 +148,25 @@ def split_text(text, n):
 
 def run(options, engines=None):
     """engines: optional list of pre-built Engine objects (tests inject CPU stand-ins here).
-    SAM parsing and text rendering run in the library's multi-threaded C++ host code
-    (csrc/tc_host.cpp); correction runs on the GPU(s); one host thread per GPU."""
+    The SAM file is streamed twice in blocks (TC_CLI_BLOCK_MB, default 256): a scan for the header
+    lines and the chromosome names (what split_SAM collects, TC.py:519-541), then the correction,
+    block by block - each block cut into one contiguous piece per GPU (one host thread per GPU),
+    the pieces' texts appended to the four output files in input order (combine_outputs,
+    TC.py:604-663: headers first; no SAM / FASTA in --dryRun).  SAM parsing and text rendering run
+    in the library's multi-threaded C++ host code (csrc/tc_host.cpp)."""
     import threading
     from . import engine as E
-    with open(options.sam, "rb") as f:
-        text = f.read()
+    block = int(os.environ.get("TC_CLI_BLOCK_BYTES", "0")) or max(1, int(os.environ.get("TC_CLI_BLOCK_MB", "256"))) << 20
+    lib = E.load_library() if engines is None else engines[0]._lib
+    chroms, header = set(), ""
+    for blk in sam_blocks(options.sam, block):
+        chroms |= E.sam_rnames(lib, blk)
+        header += E.sam_header_lines(lib, blk)
     print("Reading genome ..............................")
     genome = GenomeImage.from_fasta(options.refGenome)
     if engines is None:
         n = max(1, min(int(options.n_threads), max(1, n_gpus_available())))
         engines = [E.Engine(d) for d in range(n)]
-    chroms = E.sam_rnames(engines[0]._lib, text)
     validate_chroms(genome, options.variantFile, chroms)
     os.makedirs(options.tmp_dir, exist_ok=True)          # kept for interface compatibility (--tmpDir / --deleteTmp)
 
@@ -165,29 +175,51 @@ def run(options, engines=None):
             return iter("x\tx\t" + c for c in chroms)
 
     refs_list = [api.prep_refs(options, _ChromLines(), None, engine=e, genome=genome) for e in engines]
-    parts = split_text(text, len(engines))
-    results, errs = [None] * len(parts), []
+    dry = bool(options.dryRun)
+    pre = options.outprefix
+    files = {"log": open(pre + "_clean.log", "wb"), "te": open(pre + "_clean.TE.log", "wb")}
+    if not dry:
+        files["sam"] = open(pre + "_clean.sam", "wb")
+        files["fa"] = open(pre + "_clean.fa", "wb")
+    try:
+        files["log"].write(LOG_HEADER.encode())
+        files["te"].write(TE_HEADER.encode())
+        if not dry:
+            files["sam"].write(header.encode())
 
-    def work(k):
-        try:
-            results[k] = api.correct_sam_text(parts[k], options, refs_list[k], dry=bool(options.dryRun))
-        except Exception as e:
-            errs.append(e)
+        def sink(_header, views):                         # the library's own buffers, written without a copy
+            for k, f in files.items():
+                f.write(views[k])
 
-    ts = [threading.Thread(target=work, args=(k,)) for k in range(len(parts))]
-    for t in ts:
-        t.start()
-    for t in ts:
-        t.join()
-    if errs:
-        raise errs[0]
-    header = "".join(r[0] for r in results)
-    texts = {k: b"".join(r[1][k] for r in results) for k in ("sam", "fa", "log", "te")}
-    write_outputs(options, header, texts)
+        for blk in sam_blocks(options.sam, block):
+            if len(engines) == 1:
+                api.correct_sam_text(blk, options, refs_list[0], dry=dry, consume=sink)
+                continue
+            parts = split_text(blk, len(engines))
+            results, errs = [None] * len(parts), []
+
+            def work(k):
+                try:
+                    results[k] = api.correct_sam_text(parts[k], options, refs_list[k], dry=dry)[1]
+                except Exception as e:
+                    errs.append(e)
+
+            ts = [threading.Thread(target=work, args=(k,)) for k in range(len(parts))]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+            if errs:
+                raise errs[0]
+            for r in results:
+                for k, f in files.items():
+                    f.write(r[k])
+    finally:
+        for f in files.values():
+            f.close()
     if options.delete_tmp:
         import shutil
         shutil.rmtree(options.tmp_dir, ignore_errors=True)
-    return texts
 
 
 def main(argv=None):

@@ -1824,33 +1824,53 @@ static int run_all(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out, int dr
         const int64_t nchunk = (n + CH - 1) / CH;
         int64_t bs = 0, bc = 0, bt = 0, bj = 0, bm = 0;
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+        const bool trace = getenv("TC_PIPE_TRACE") != nullptr;        // per-chunk stream timestamps on stderr (debugging aid)
+        std::vector<cudaEvent_t> tev;
+        auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+        mark(ctx->s_in);
         if (slot_upload(ctx, ctx->slot[0], in, 0, CH < n ? CH : n, ctx->s_in)) return TC_E_CUDA;
         CK(cudaEventRecord(ctx->slot[0].ev_in, ctx->s_in));
+        mark(ctx->s_in);
         for (int64_t c = 0; c < nchunk; c++) {
             Slot& S = ctx->slot[c & 1];
             const int64_t r0 = c * CH;
             if (c + 1 < nchunk) {                                   // next upload: its slot's kernels (chunk c-1) are done
                 Slot& N = ctx->slot[(c + 1) & 1];
                 const int64_t a = (c + 1) * CH, b = a + CH < n ? a + CH : n;
+                mark(ctx->s_in);
                 if (slot_upload(ctx, N, in, a, b, ctx->s_in)) return TC_E_CUDA;
                 CK(cudaEventRecord(N.ev_in, ctx->s_in));
+                mark(ctx->s_in);
             }
             CK(cudaStreamWaitEvent(ctx->stream, S.ev_in, 0));
             if (c >= 2) CK(cudaStreamWaitEvent(ctx->stream, S.ev_out, 0));   // the slot's previous results have left the device
             S.base_seq = bs; S.base_cig = bc; S.base_te = bt; S.base_jn = bj; S.base_md = bm;
+            mark(ctx->stream);
             int rc = slot_run(ctx, S, dry, ctx->stream, false);
             if (rc) return rc;
             CK(cudaEventRecord(S.ev_cmp, ctx->stream));
+            mark(ctx->stream);
             if (host_reserve_all(ctx, S, r0, n, dry != 0, ctx->s_out)) return TC_E_CUDA;
             CK(cudaStreamWaitEvent(ctx->s_out, S.ev_cmp, 0));
+            mark(ctx->s_out);
             if (slot_download(ctx, S, r0, ctx->s_out)) return TC_E_CUDA;
             CK(cudaEventRecord(S.ev_out, ctx->s_out));
+            mark(ctx->s_out);
             bs += S.tot_seq; bc += S.tot_cig; bt += S.tot_te; bj += S.tot_jn; bm += S.md_used;
         }
         CK(cudaStreamSynchronize(ctx->s_out));
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         cudaEventElapsedTime(&ctx->tm.kernels_ms, ctx->ev[0], ctx->ev[1]);
+        if (trace) {      // order of marks: up0 b/e, then per chunk: [up(c+1) b/e], run b/e, down b/e
+            size_t k = 0; auto t = [&](size_t j) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], tev[j]); return ms; };
+            fprintf(stderr, "pipe: upload 0: %.2f-%.2f\n", t(0), t(1)); k = 2;
+            for (int64_t c = 0; c < nchunk; c++) {
+                if (c + 1 < nchunk) { fprintf(stderr, "pipe: upload %lld: %.2f-%.2f\n", (long long)(c + 1), t(k), t(k + 1)); k += 2; }
+                fprintf(stderr, "pipe: run %lld: %.2f-%.2f   download %lld: %.2f-%.2f\n", (long long)c, t(k), t(k + 1), (long long)c, t(k + 2), t(k + 3)); k += 4;
+            }
+            for (auto e : tev) cudaEventDestroy(e);
+        }
         ctx->ran = true; ctx->ran_dry = dry != 0; ctx->piped = true;
         fill_out(ctx, out, n);
         return TC_OK;

@@ -423,6 +423,24 @@ char* tc_sam_rnames(const char* text, int64_t len, int64_t* out_len) {
     if (out_len) *out_len = (int64_t)out.size();
     return r;
 }
+// the '@' lines of a SAM text, trimmed and newline-terminated (what tc_sam_parse sets aside as the header);
+// lets a caller that streams a file in blocks collect the header before any record is written
+char* tc_sam_header_lines(const char* text, int64_t len, int64_t* out_len) {
+    std::string out;
+    int64_t p = 0;
+    while (p < len) {
+        const char* nl = (const char*)memchr(text + p, '\n', (size_t)(len - p));
+        int64_t e = nl ? nl - text : len, s = p;
+        p = e + 1;
+        while (s < e && is_ws(text[s])) s++;
+        while (e > s && is_ws(text[e - 1])) e--;
+        if (s < e && text[s] == '@') { out.append(text + s, (size_t)(e - s)); out.push_back('\n'); }
+    }
+    char* r = (char*)malloc(out.size() + 1);
+    memcpy(r, out.data(), out.size()); r[out.size()] = 0;
+    if (out_len) *out_len = (int64_t)out.size();
+    return r;
+}
 void tc_free(void* p) { free(p); }
 
 void tc_sam_free(tc_sam* S) { sam_release(S); }

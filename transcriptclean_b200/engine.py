@@ -12,7 +12,7 @@ EXPORTS = ["tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_set_optio
            "tc_ctx_load_genome", "tc_ctx_load_junctions", "tc_ctx_load_variants", "tc_correct_batch",
            "tc_dryrun_batch", "tc_batch_upload", "tc_batch_run", "tc_batch_download", "tc_get_timing",
            "tc_ctx_set_pipeline", "tc_sam_parse", "tc_sam_free", "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_render",
-           "tc_sam_rnames", "tc_free", "tc_ctx_set_alphabet", "tc_seq_pack", "tc_seq_packed_size", "tc_sam_pack_seq"]
+           "tc_sam_rnames", "tc_free", "tc_ctx_set_alphabet", "tc_seq_pack", "tc_seq_packed_size", "tc_sam_pack_seq", "tc_sam_header_lines"]
 
 # status bits (include/tc_b200.h)
 ST_CLASS_MASK, ST_FALLBACK, ST_CIGAR_REWRITTEN = 3, 1 << 2, 1 << 3
@@ -92,6 +92,8 @@ def _declare(lib):
     lib.tc_sam_free.restype = None
     lib.tc_sam_rnames.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]
     lib.tc_sam_rnames.restype = C.c_void_p
+    lib.tc_sam_header_lines.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]
+    lib.tc_sam_header_lines.restype = C.c_void_p
     lib.tc_free.argtypes = [C.c_void_p]
     lib.tc_free.restype = None
     lib.tc_sam_n_reads.argtypes = [C.c_void_p]
@@ -109,7 +111,7 @@ def _declare(lib):
     lib.tc_sam_render.argtypes = [C.c_void_p, C.POINTER(_BatchOut)] + [C.c_int32] * 4 + [C.POINTER(C.c_void_p), C.POINTER(C.c_int64)] * 4 + [C.c_char_p, C.c_int64]
     for f in EXPORTS:
         if f not in ("tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_stream", "tc_sam_parse", "tc_sam_free",
-                     "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_rnames", "tc_free", "tc_seq_pack", "tc_seq_packed_size"):
+                     "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_rnames", "tc_free", "tc_seq_pack", "tc_seq_packed_size", "tc_sam_header_lines"):
             getattr(lib, f).restype = C.c_int
 
 
@@ -165,6 +167,16 @@ def sam_rnames(lib, text):
     p = lib.tc_sam_rnames(text, len(text), C.byref(n))
     try:
         return set(C.string_at(p, n.value).decode().split("\n")) - {""}
+    finally:
+        lib.tc_free(p)
+
+
+def sam_header_lines(lib, text):
+    """The '@' lines of a SAM text (bytes), newline-terminated, as str."""
+    n = C.c_int64()
+    p = lib.tc_sam_header_lines(text, len(text), C.byref(n))
+    try:
+        return C.string_at(p, n.value).decode()
     finally:
         lib.tc_free(p)
 
