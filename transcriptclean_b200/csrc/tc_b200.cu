@@ -578,7 +578,7 @@ __device__ void junction_fix_warp(const Params& P, int64_t i, int lane) {
             C[TC_C_COR_SJ] = cJ; C[TC_C_UNC_SJ] = uJ;
             W.n_te[i] = nte;
             if (any_ok) {
-                W.cig_buf[i] = (int8_t)cb; W.seg_buf[i] = (int8_t)sb; W.n_cig_cur[i] = nc; W.n_seg_cur[i] = ns;
+                W.cig_buf[i] = (int8_t)cb; W.seg_buf[i] = (int8_t)sb; W.n_cig_cur[i] = nc; W.n_seg_cur[i] = ns; W.seq_len_out[i] = (int32_t)seqlen;
                 W.refresh[i] = 1; W.nm_extra[i] = 0;
             }
         }

@@ -285,7 +285,10 @@ TC_HD bool md_next(MdCur& t, int& op, int32_t& cnt) {
 // `tok` is given; returns their number; sets MF_MD_ACGTN (TC.py:1090 looks for a base letter in the
 // tag) and MF_MD_BYTES (a count that does not fit a token).
 TC_HD int md_tokenize(const uint8_t* p, int len, uint32_t* tok, uint8_t& mf) {
-    int ntok = 0, state = -1, L = 0; uint32_t v = 0; bool caret = false, acgtn = false, big = false;   // v > MD_TOK_MAX: too big (sticky)
+    // One straight-line step per byte (the lanes of a warp are in different states, so branches on the
+    // state would all be walked): a token ends where the digit / non-digit class changes; the ended
+    // token's word is `cur` for a number and kind << 30 | count for a letter run.
+    int ntok = 0; uint32_t v = 0, L = 0, kind = 0; bool prev_dig = false, any = false, acgtn = false, big = false;   // v > MD_TOK_MAX: too big (sticky)
     const int a = (int)((uintptr_t)p & 7);
     const u64* wp = reinterpret_cast<const u64*>(p - a);
     const int end = a + len;                                          // bytes [a, end) of the word stream
@@ -296,25 +299,25 @@ TC_HD int md_tokenize(const uint8_t* p, int len, uint32_t* tok, uint8_t& mf) {
         for (int k = 0; k < 8; k++) {                                 // constant shifts; bytes outside [a, end) are skipped
             if (w0 + k < a || w0 + k >= end) continue;
             const uint32_t c = (half[k >> 2] >> (8 * (k & 3))) & 255u, d = c - '0';
-            if (d < 10u) {
-                if (state != 0) {
-                    if (state == 1) { if (tok) tok[ntok] = md_tok_pack(caret ? 'D' : 'X', caret ? L - 1 : L); ntok++; }
-                    state = 0; v = 0;
-                }
-                v = v > MD_TOK_MAX / 10 ? 0xffffffffu : v * 10u + d;
-            } else {
-                if (state != 1) {
-                    if (state == 0) { if (v > MD_TOK_MAX) big = true; else if (tok) tok[ntok] = md_tok_pack('M', v); ntok++; }
-                    state = 1; L = 0; caret = c == '^';
-                }
-                L++;
-                const uint32_t u = c & 0xDFu;
-                acgtn |= u == 'A' || u == 'C' || u == 'G' || u == 'T' || u == 'N';
+            const bool dig = d < 10u;
+            if (any && dig != prev_dig) {                             // the previous token ends here
+                const uint32_t w = prev_dig ? v : (kind << 30) | (L - (kind == 2u ? 1u : 0u));
+                if (prev_dig && v > MD_TOK_MAX) big = true; else if (tok) tok[ntok] = w;
+                ntok++;
             }
+            if (!any || dig != prev_dig) { v = 0; L = 0; kind = c == '^' ? 2u : 1u; }
+            v = !dig ? v : (v > MD_TOK_MAX / 10 ? 0xffffffffu : v * 10u + d);
+            L += dig ? 0u : 1u;
+            const uint32_t u = c & 0xDFu;
+            acgtn |= !dig && (u == 'A' || u == 'C' || u == 'G' || u == 'T' || u == 'N');
+            prev_dig = dig; any = true;
         }
     }
-    if (state == 0) { if (v > MD_TOK_MAX) big = true; else if (tok) tok[ntok] = md_tok_pack('M', v); ntok++; }
-    else if (state == 1) { if (tok) tok[ntok] = md_tok_pack(caret ? 'D' : 'X', caret ? L - 1 : L); ntok++; }
+    if (any) {
+        const uint32_t w = prev_dig ? v : (kind << 30) | (L - (kind == 2u ? 1u : 0u));
+        if (prev_dig && v > MD_TOK_MAX) big = true; else if (tok) tok[ntok] = w;
+        ntok++;
+    }
     if (acgtn) mf |= MF_MD_ACGTN;
     if (big) mf |= MF_MD_BYTES;
     return ntok;
@@ -508,7 +511,7 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
     C[TC_C_COR_MM] = O.correct_mismatches ? cM : -1; C[TC_C_UNC_MM] = O.correct_mismatches ? uM : -1;
     if (indel) { C[TC_C_COR_INS] = cI; C[TC_C_UNC_INS] = uI; C[TC_C_VAR_INS] = vI;
                  C[TC_C_COR_DEL] = cD; C[TC_C_UNC_DEL] = uD; C[TC_C_VAR_DEL] = vD; }
-    W.cig_buf[i] = 0; W.n_cig_cur[i] = E.nc; W.seg_buf[i] = 0; W.n_seg_cur[i] = E.ns;
+    W.cig_buf[i] = 0; W.n_cig_cur[i] = E.nc; W.seg_buf[i] = 0; W.n_seg_cur[i] = E.ns; W.seq_len_out[i] = (int32_t)E.seqlen;
     W.n_te[i] = nte; W.te_cnt[3 * i] = nteM; W.te_cnt[3 * i + 1] = nteI; W.te_cnt[3 * i + 2] = nteD;
     // NM/MD refresh points (Q7): end of correctDeletions when the CIGAR holds a D, else end of
     // correctMismatches; insertion removal never refreshes, so NM keeps counting removed bases.
@@ -846,7 +849,7 @@ TC_HD void junction_fix_read(const Params& P, int64_t i) {
                 C[TC_C_COR_SJ] = cJ; C[TC_C_UNC_SJ] = uJ;
                 W.n_te[i] = nte;
                 if (any_ok) {
-                    W.cig_buf[i] = (int8_t)cb; W.seg_buf[i] = (int8_t)sb; W.n_cig_cur[i] = nc; W.n_seg_cur[i] = ns;
+                    W.cig_buf[i] = (int8_t)cb; W.seg_buf[i] = (int8_t)sb; W.n_cig_cur[i] = nc; W.n_seg_cur[i] = ns; W.seq_len_out[i] = (int32_t)seqlen;
                     W.refresh[i] = 1; W.nm_extra[i] = 0;
                     st |= TC_ST_CIGAR_REWRITTEN | TC_ST_JM_DEVICE | TC_ST_JI_DEVICE;
                     if (degenerate) st |= TC_ST_ERR_INTRON;
@@ -868,7 +871,7 @@ TC_HD void sizes_read(const Params& P, int64_t i) {
     if ((st & TC_ST_CLASS_MASK) != 0) { W.o_seq[i] = W.o_cig[i] = W.o_te[i] = W.o_jn[i] = 0; W.seq_len_out[i] = 0; W.plan[i].w[EP_STATUS] = (int32_t)st; return; }
     int64_t sl;
     if (W.seg_buf[i] < 0) sl = B.seq_off[i + 1] - B.seq_off[i];
-    else { WsView v = ws_view(W, i); sl = 0; const u64* s = v.seg[W.seg_buf[i]]; for (int k = 0; k < W.n_seg_cur[i]; k++) sl += seg_len(s[k]); }
+    else sl = W.seq_len_out[i];                    // kept current by plan_read / the junction rescue (the sum of the segment lengths)
     W.o_seq[i] = (sl + 15) & ~15ll;                 // 16-byte aligned rows: tc_emit stores whole uint4
     W.seq_len_out[i] = (int32_t)sl;
     const int ncig = W.cig_buf[i] < 0 ? (int)(B.cig_off[i + 1] - B.cig_off[i]) : W.n_cig_cur[i];
