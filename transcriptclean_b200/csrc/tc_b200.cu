@@ -1565,9 +1565,9 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
     int64_t wb = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; int gw = (int)(wb < (int64_t)nsm * 8 ? wb : (int64_t)nsm * 8);
     if (timed) CK(cudaEventRecord(ctx->ev[2], st));
     // ---- init NM/MD (exact retry on overflow)
-    int64_t init_cap = S.init_pool.cap > (1 << 20) ? (int64_t)S.init_pool.cap : (1 << 20);
+    int64_t init_cap = S.init_pool.cap > (1 << 20) + 64 ? (int64_t)S.init_pool.cap - 64 : (1 << 20);
     for (int attempt = 0;; attempt++) {
-        CK(S.init_pool.ensure((size_t)init_cap)); init_cap = (int64_t)S.init_pool.cap;
+        CK(S.init_pool.ensure((size_t)init_cap + 64)); init_cap = (int64_t)S.init_pool.cap - 64;   // 64 spare bytes: md_tokenize reads whole 8-byte words
         if (be_zero(ctx, st, cur, 64)) return TC_E_CUDA;
         InitDev I; I.pool = (uint8_t*)S.init_pool.p; I.cursor = cur; I.cap = init_cap;
         P.W.md_init_pool = I.pool; S.W.md_init_pool = I.pool;
