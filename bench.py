@@ -283,10 +283,10 @@ def main():
     m_per_read = np.add.reduceat(np.concatenate((cig_m, [0])), np.minimum(res.cig_off[:-1], len(cig_m)))
     m_per_read = np.where(np.diff(res.cig_off) > 0, m_per_read, 0)
     # k_emit: SEQ in + SEQ out (16-byte padded rows) + 2-bit genome words under the verified M bases
-    # + CIGAR (8 B packed in, 5 B out) + TE rows (16 B in, 16 B out) + jM/jI (9 B) + MD + the 128-byte plan row
+    # + the planned CIGAR (8 B per op) + MD + the 128-byte plan row.  (TE rows, the CIGAR copy and jM / jI
+    # are moved by k_small; the segment lists k_emit reads are not counted.)
     bytes_emit = (int(cols["seq"].nbytes) + int(res.seq.nbytes) + 0.25 * float(m_per_read[refreshed].sum())
-                  + 13.0 * len(res.cig_op) + 32.0 * len(res.te) + 9.0 * len(res.jm) + float(res.md_len.sum())
-                  + 128.0 * int(primary.sum()))
+                  + 8.0 * len(res.cig_op) + float(res.md_len.sum()) + 128.0 * int(primary.sum()))
     bytes_plan = (5.0 * len(cols["cig_op"]) + float(cols["md"].nbytes) + 8.0 * len(res.cig_op) + 16.0 * len(res.te)
                   + 96.0 * int(primary.sum()))
     per = {k: v / steps for k, v in kern.items()}

@@ -62,10 +62,43 @@ TC_HD void cig_get(const CigSrc& c, int k, int& op, int32_t& len) {
     else { op = c.op[k]; len = c.len[k]; }
 }
 
+// TE rows back into the reference's order (stage order: mismatches, insertions, deletions, junctions;
+// positional inside a stage - the planner wrote them positionally), the final CIGAR and the jM / jI
+// snapshot of one read -> their places in the dense outputs.  Thread per read (k_pack): these are a few
+// hundred bytes per read, cheaper here than as warp-wide phases of the output kernel.
+TC_HD void small_copies_read(const Params& P, const OutDev& O, int64_t i, int dry) {
+    const BatchDev& B = P.B; const WorkDev& W = P.W;
+    if ((W.status[i] & TC_ST_CLASS_MASK) != 0) return;
+    const WsView v = ws_view(W, i);
+    const int nte = W.n_te[i];
+    const u64* src = reinterpret_cast<const u64*>(v.te); u64* dst = reinterpret_cast<u64*>(O.te + W.o_te[i]);
+    if (dry) { for (int k = 0; k < 2 * nte; k++) dst[k] = src[k]; return; }
+    int slot[4]; slot[0] = 0; slot[1] = W.te_cnt[3 * i]; slot[2] = slot[1] + W.te_cnt[3 * i + 1]; slot[3] = slot[2] + W.te_cnt[3 * i + 2];
+    for (int k = 0; k < nte; k++) {
+        const u64 a = src[2 * k], b = src[2 * k + 1];
+        const int t = (int)((b >> 32) & 3u);                          // tc_te.type
+        const int s = t == 0 ? slot[0]++ : t == 1 ? slot[1]++ : t == 2 ? slot[2]++ : slot[3]++;
+        dst[2 * s] = a; dst[2 * s + 1] = b;
+    }
+    const int cb = W.cig_buf[i]; const int64_t oc = W.o_cig[i];
+    if (cb < 0) {
+        const int64_t c0 = B.cig_off[i]; const int n = (int)(B.cig_off[i + 1] - c0);
+        for (int k = 0; k < n; k++) { O.cig_op[oc + k] = B.cig_op[c0 + k]; O.cig_len[oc + k] = B.cig_len[c0 + k]; }
+    } else {
+        const u64* c = v.cig[cb]; const int n = W.n_cig_cur[i];
+        for (int k = 0; k < n; k++) { O.cig_op[oc + k] = (uint8_t)cg_op(c[k]); O.cig_len[oc + k] = cg_len(c[k]); }
+    }
+    const int nj = W.n_jn[i]; const int64_t oj = W.o_jn[i];
+    for (int k = 0; k < nj; k++) { const int32_t* r = v.jn + k * JN_STRIDE; O.jm[oj + k] = (int8_t)r[7]; O.ji[2 * (oj + k)] = r[5]; O.ji[2 * (oj + k) + 1] = r[6]; }
+}
+
 #ifndef TC_HOSTSIM
 // ================================================================================== CUDA
 
 #define FULL 0xffffffffu
+// fields of a read's plan row (one word per lane, `pw`)
+#define PF(k) __shfl_sync(FULL, pw, (k))
+#define PF64(k) ((int64_t)(((u64)(uint32_t)PF((k) + 1) << 32) | (u64)(uint32_t)PF(k)))
 #define WARPS_PER_BLOCK 8
 #define EMIT_CAP 4096            // reads whose new SEQ fits are staged in shared memory
 #define EMIT_MAXBP 192
@@ -601,6 +634,51 @@ __global__ void k_dry(Params P) {
 
 __global__ void k_pack(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) pack_read(P, i); }
 
+// small_copies_read as one warp per read: TE rows into stage order by a ballot partition, CIGAR and
+// jM / jI copies, all from the read's 128-byte plan row.  A light kernel of its own (no shared memory,
+// few registers, 48 warps of an SM resident): these phases are latency, not bytes, and inside
+// k_emit they held its 30 resident warps up for a fifth of its time.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 6) k_small(Params P, OutDev O, int dry) {
+    const int lane = threadIdx.x & 31; const unsigned lt = (1u << lane) - 1u;
+    const BatchDev& B = P.B; const WorkDev& W = P.W;
+    const int64_t nw = (int64_t)gridDim.x * WARPS_PER_BLOCK;
+    for (int64_t i = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); i < B.n; i += nw) {
+        const int pw = W.plan[i].w[lane];
+        if (((uint32_t)PF(EP_STATUS) & TC_ST_CLASS_MASK) != 0) continue;
+        const int pflags = PF(EP_FLAGS), cig_cap = PF(EP_CIGCAP), seg_cap = PF(EP_SEGCAP), te_cap = PF(EP_TECAP);
+        const int ncig = PF(EP_NCIG), nte = PF(EP_NTE), nj = PF(EP_NJN);
+        const int te_mm = PF(EP_TEMM), te_ins = PF(EP_TEINS), te_del = PF(EP_TEDEL);
+        const int64_t ws_off = PF64(EP_WS_LO), o_cig = PF64(EP_OCIG_LO), o_te = PF64(EP_OTE_LO), o_jn = PF64(EP_OJN_LO), cig0 = PF64(EP_CIG0_LO);
+        const u64* const ws = W.ws + ws_off;
+        const tc_te* const ws_te = reinterpret_cast<const tc_te*>(ws + 3ll * seg_cap + 3ll * cig_cap);
+        tc_te* dst = O.te + o_te;
+        if (dry) { for (int k = lane; k < nte; k += 32) dst[k] = ws_te[k]; continue; }
+        int base0 = 0, base1 = te_mm, base2 = te_mm + te_ins, base3 = te_mm + te_ins + te_del;
+        for (int c = 0; c < nte; c += 32) {
+            const int k = c + lane; const bool valid = k < nte;
+            tc_te r; int t = -1;
+            if (valid) { r = ws_te[k]; t = r.type; }
+            const unsigned m0 = __ballot_sync(FULL, t == 0), m1 = __ballot_sync(FULL, t == 1), m2 = __ballot_sync(FULL, t == 2), m3 = __ballot_sync(FULL, t == 3);
+            if (valid) {
+                const int slot = t == 0 ? base0 + __popc(m0 & lt) : t == 1 ? base1 + __popc(m1 & lt) : t == 2 ? base2 + __popc(m2 & lt) : base3 + __popc(m3 & lt);
+                dst[slot] = r;
+            }
+            base0 += __popc(m0); base1 += __popc(m1); base2 += __popc(m2); base3 += __popc(m3);
+        }
+        const int cb = ((pflags >> 2) & 3) - 1;
+        CigSrc cs; cs.n = ncig;
+        if (cb < 0) { cs.packed = 0; cs.op = B.cig_op + cig0; cs.len = B.cig_len + cig0; }
+        else { cs.packed = ws + 3ll * seg_cap + (int64_t)cb * cig_cap; cs.op = 0; cs.len = 0; }
+        uint8_t* dop = O.cig_op + o_cig; int32_t* dl = O.cig_len + o_cig;
+        for (int k = lane; k < ncig; k += 32) { int op; int32_t l; cig_get(cs, k, op, l); dop[k] = (uint8_t)op; dl[k] = l; }
+        if (nj > 0) {
+            int8_t* djm = O.jm + o_jn; int32_t* dji = O.ji + 2 * o_jn;
+            const int32_t* jn = reinterpret_cast<const int32_t*>(ws + 3ll * seg_cap + 3ll * cig_cap + 2ll * te_cap);
+            for (int k = lane; k < nj; k += 32) { const int32_t* r = jn + k * JN_STRIDE; djm[k] = (int8_t)r[7]; dji[2 * k] = r[5]; dji[2 * k + 1] = r[6]; }
+        }
+    }
+}
+
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
@@ -638,14 +716,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
     int64_t i = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     int pw = i < B.n ? W.plan[i].w[lane] : 0;
     for (; i < B.n; i += nw) {
-#define PF(k) __shfl_sync(FULL, pw, (k))
-#define PF64(k) ((int64_t)(((u64)(uint32_t)PF((k) + 1) << 32) | (u64)(uint32_t)PF(k)))
         uint32_t st = (uint32_t)PF(EP_STATUS);
         const int pflags = PF(EP_FLAGS), cig_cap = PF(EP_CIGCAP), seg_cap = PF(EP_SEGCAP), nm_extra = PF(EP_NMEXTRA);
-        const int ncig = PF(EP_NCIG), nte = PF(EP_NTE), nj = PF(EP_NJN), out_len = PF(EP_OUTLEN), ns = PF(EP_NSEG), te_cap = PF(EP_TECAP);
-        const int te_mm = PF(EP_TEMM), te_ins = PF(EP_TEINS), te_del = PF(EP_TEDEL);
+        const int ncig = PF(EP_NCIG), out_len = PF(EP_OUTLEN), ns = PF(EP_NSEG);
         const int chrom = PF(EP_CHROM); const int64_t pos = PF(EP_POS);
-        const int64_t ws_off = PF64(EP_WS_LO), o_seq = PF64(EP_OSEQ_LO), o_cig = PF64(EP_OCIG_LO), o_te = PF64(EP_OTE_LO), o_jn = PF64(EP_OJN_LO);
+        const int64_t ws_off = PF64(EP_WS_LO), o_seq = PF64(EP_OSEQ_LO);
         const int64_t in_base = PF64(EP_INB_LO), cig0 = PF64(EP_CIG0_LO); const int Lq = PF(EP_LQ);
         // next read: fetch its row now (consumed at the end of this iteration), and pull its segment
         // list and SEQ lines towards L2
@@ -653,45 +728,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
         const int pw_next = inext < B.n ? W.plan[inext].w[lane] : 0;
         if ((st & TC_ST_CLASS_MASK) != 0) { if (lane == 0) { O.md_off[i] = 0; O.md_len[i] = 0; O.nm[i] = 0; } pw = pw_next; continue; }
         u64* const ws = W.ws + ws_off;
-        const tc_te* const ws_te = reinterpret_cast<const tc_te*>(ws + 3ll * seg_cap + 3ll * cig_cap);
         const int cb = ((pflags >> 2) & 3) - 1, sb = ((pflags >> 4) & 3) - 1;
-        // ---- TE rows: stage order (mismatch, insertion, deletion, junction), positional inside
-        if (nte > 0 && !(dbg & 1)) {
-            tc_te* dst = O.te + o_te;
-            if (dry) { for (int k = lane; k < nte; k += 32) dst[k] = ws_te[k]; }
-            else {
-                int base0 = 0, base1 = te_mm, base2 = te_mm + te_ins, base3 = te_mm + te_ins + te_del;
-                for (int c = 0; c < nte; c += 32) {
-                    const int k = c + lane; const bool valid = k < nte;
-                    tc_te r; int t = -1;
-                    if (valid) { r = ws_te[k]; t = r.type; }
-                    const unsigned m0 = __ballot_sync(FULL, t == 0), m1 = __ballot_sync(FULL, t == 1), m2 = __ballot_sync(FULL, t == 2), m3 = __ballot_sync(FULL, t == 3);
-                    if (valid) {
-                        const int slot = t == 0 ? base0 + __popc(m0 & lt) : t == 1 ? base1 + __popc(m1 & lt) : t == 2 ? base2 + __popc(m2 & lt) : base3 + __popc(m3 & lt);
-                        dst[slot] = r;
-                    }
-                    base0 += __popc(m0); base1 += __popc(m1); base2 += __popc(m2); base3 += __popc(m3);
-                }
-            }
-        }
         if (dry) { if (lane == 0) { O.md_off[i] = 0; O.md_len[i] = 0; O.nm[i] = 0; } pw = pw_next; continue; }
-        // ---- CIGAR
+        // (TE rows, the CIGAR and the jM / jI snapshot were copied by k_pack)
         CigSrc cs; cs.n = ncig;
         if (cb < 0) { cs.packed = 0; cs.op = B.cig_op + cig0; cs.len = B.cig_len + cig0; }
         else { cs.packed = ws + 3ll * seg_cap + (int64_t)cb * cig_cap; cs.op = 0; cs.len = 0; }
-        if (!(dbg & 1)) {
-            uint8_t* dop = O.cig_op + o_cig; int32_t* dl = O.cig_len + o_cig;
-            for (int k = lane; k < ncig; k += 32) { int op; int32_t l; cig_get(cs, k, op, l); dop[k] = (uint8_t)op; dl[k] = l; }
-        }
-        // ---- jM / jI snapshot
-        if (nj > 0 && !(dbg & 1)) {
-            int8_t* djm = O.jm + o_jn; int32_t* dji = O.ji + 2 * o_jn;
-            const int32_t* jn = reinterpret_cast<const int32_t*>(ws + 3ll * seg_cap + 3ll * cig_cap + 2ll * te_cap);
-            for (int k = lane; k < nj; k += 32) {
-                const int32_t* r = jn + k * JN_STRIDE;
-                djm[k] = (int8_t)r[7]; dji[2 * k] = r[5]; dji[2 * k + 1] = r[6];
-            }
-        }
         if (dbg & 2) { pw = pw_next; continue; }
         // ---- SEQ
         const uint8_t* in_seq = B.seq + in_base;
@@ -1522,14 +1564,11 @@ static void host_emit_read(Params& P, OutDev& O, int64_t i, int dry, std::vector
     uint32_t st = W.status[i]; O.md_off[i] = 0; O.md_len[i] = 0; O.nm[i] = 0;
     if ((st & TC_ST_CLASS_MASK) != 0) return;
     WsView v = ws_view(W, i);
-    int nte = W.n_te[i]; tc_te* dst = O.te + W.o_te[i];
-    if (dry) { for (int k = 0; k < nte; k++) dst[k] = v.te[k]; return; }
-    int m = 0; for (int ty = 0; ty < 4; ty++) for (int k = 0; k < nte; k++) if (v.te[k].type == ty) dst[m++] = v.te[k];
+    small_copies_read(P, O, i, dry);
+    if (dry) return;
     CigSrc cs;
     if (W.cig_buf[i] < 0) { cs.packed = 0; cs.op = B.cig_op + B.cig_off[i]; cs.len = B.cig_len + B.cig_off[i]; cs.n = (int)(B.cig_off[i + 1] - B.cig_off[i]); }
     else { cs.packed = v.cig[W.cig_buf[i]]; cs.op = 0; cs.len = 0; cs.n = W.n_cig_cur[i]; }
-    for (int k = 0; k < cs.n; k++) { int op; int32_t l; cig_get(cs, k, op, l); O.cig_op[W.o_cig[i] + k] = (uint8_t)op; O.cig_len[W.o_cig[i] + k] = l; }
-    for (int k = 0; k < W.n_jn[i]; k++) { const int32_t* r = v.jn + k * JN_STRIDE; O.jm[W.o_jn[i] + k] = (int8_t)r[7]; O.ji[2 * (W.o_jn[i] + k)] = r[5]; O.ji[2 * (W.o_jn[i] + k) + 1] = r[6]; }
     const uint8_t* in_seq = B.seq + B.seq_off[i]; uint8_t* out_seq = O.seq + W.o_seq[i];
     if (W.seg_buf[i] < 0) memcpy(out_seq, in_seq, (size_t)(B.seq_off[i + 1] - B.seq_off[i]));
     else { int64_t o = 0; const u64* segs = v.seg[W.seg_buf[i]];
@@ -1595,7 +1634,9 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
         CK(S.w_fix_list.ensure((size_t)(n + 1) * 4));
         if (be_zero(ctx, st, cur + 2, 8)) return TC_E_CUDA;
         k_jn_init<<<gb, TPB, 0, st>>>(P, (int32_t*)S.w_fix_list.p, (unsigned*)(cur + 2)); ctx->tm.launches++; CK(cudaGetLastError());
-        k_jn_fix<<<gw, WARPS_PER_BLOCK * 32, 0, st>>>(P, (const int32_t*)S.w_fix_list.p, (const unsigned*)(cur + 2)); ctx->tm.launches++; CK(cudaGetLastError());
+        int occ_j = 1; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_j, k_jn_fix, WARPS_PER_BLOCK * 32, 0));
+        const int gj = (int)(wb < (int64_t)nsm * occ_j ? wb : (int64_t)nsm * occ_j);            // persistent grid = the resident blocks
+        k_jn_fix<<<gj, WARPS_PER_BLOCK * 32, 0, st>>>(P, (const int32_t*)S.w_fix_list.p, (const unsigned*)(cur + 2)); ctx->tm.launches++; CK(cudaGetLastError());
         if (timed) CK(cudaEventRecord(ctx->ev[6], st));
         k_sizes<<<gb, TPB, 0, st>>>(P); ctx->tm.launches++; CK(cudaGetLastError());
     }
@@ -1611,13 +1652,19 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
     int occ = 1; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_emit, WARPS_PER_BLOCK * 32, EMIT_SMEM_BYTES));
     int ge = (int)(wb < (int64_t)nsm * occ ? wb : (int64_t)nsm * occ);
     int64_t md_cap = S.o_md_pool.cap > (size_t)(8 * n + (1 << 20)) ? (int64_t)S.o_md_pool.cap : (72 * n + 8 * S.n_cig + (1 << 20));
+    {   // persistent grid: exactly the resident blocks, so that no block waits for a second wave
+        int occ_s = 1; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_small, WARPS_PER_BLOCK * 32, 0));
+        const int gs = (int)(wb < (int64_t)nsm * occ_s ? wb : (int64_t)nsm * occ_s);
+        k_small<<<gs, WARPS_PER_BLOCK * 32, 0, st>>>(P, make_out(S, cur, md_cap), dry); ctx->tm.launches++; CK(cudaGetLastError());   // TE rows, CIGAR, jM / jI
+    }
     if (timed) CK(cudaEventRecord(ctx->ev[7], st));
     for (int attempt = 0;; attempt++) {
         CK(S.o_md_pool.ensure((size_t)md_cap)); md_cap = (int64_t)S.o_md_pool.cap;
         k_set_u64<<<1, 1, 0, st>>>(cur + 1, 0ull);
         k_set_u64<<<1, 1, 0, st>>>(cur, (unsigned long long)(S.base_md + 8 * n));      // the pool starts behind the inline slots
         OutDev O = make_out(S, cur, md_cap);
-        k_emit<<<ge, WARPS_PER_BLOCK * 32, EMIT_SMEM_BYTES, st>>>(P, O, dry, S.seq_lo_word, S.seq_hi_word); ctx->tm.launches += 2;
+        if (!dry) { k_emit<<<ge, WARPS_PER_BLOCK * 32, EMIT_SMEM_BYTES, st>>>(P, O, dry, S.seq_lo_word, S.seq_hi_word); ctx->tm.launches++; }   // (a dry run ends with k_pack)
+        ctx->tm.launches += 2;
         CK(cudaGetLastError());
         if (timed && attempt == 0) CK(cudaEventRecord(ctx->ev[8], st));
         if (!dry) { k_nmmd_exact<<<gw, WARPS_PER_BLOCK * 32, 0, st>>>(P, O); ctx->tm.launches++; CK(cudaGetLastError()); }
