@@ -6,8 +6,8 @@ def find(pat, start=0):
         if pat in src[i]: return i + 1
     raise KeyError(pat)
 pf = find("// the next read's segment list and SEQ lines")
-marks = [("loop/plan row", find("k_emit(Params P, OutDev O")), ("TE", find("// ---- TE rows")), ("CIGAR copy", find("// ---- CIGAR")),
-         ("jM/jI", find("// ---- jM / jI")), ("SEQ setup", find("// ---- SEQ")), ("(A) seg list", find("// (A) segment list")),
+marks = [("loop/plan row", find("k_emit(Params P, OutDev O")), ("setup2", find("(TE rows, the CIGAR and the jM")),
+         ("SEQ setup", find("// ---- SEQ")), ("(A) seg list", find("// (A) segment list")),
          ("prefetch", pf), ("exc+chunk_bp", find("if (fast) {", pf)), ("(B)", find("// (B) bulk copy")), ("(C)", find("// (C) the part")),
          ("(D)", find("// (D) genome slices")), ("(E)", find("// (E) one coalesced")), ("T1 scan", find("// ---- NM / MD")),
          ("T1 verify", find("// The staged SEQ is verified")), ("T1 md", find("// every aligned base equals the genome")),

@@ -809,15 +809,24 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
             const uint32_t* const rp = S32 + (in_base >> 2); const int rsub = (int)(in_base & 3);
             const int64_t wlo64 = seq_lo - (in_base >> 2), whi64 = seq_hi - 5 - (in_base >> 2);
             const int wlo = wlo64 < -0x40000000ll ? -0x40000000 : (int)wlo64, whi = whi64 > 0x40000000ll ? 0x40000000 : (int)whi64;
-            for (int c = lane; c < nchunk; c += 32) {
-                const int p = c << 4; const int k = SM.chunk_bp[c];
-                const int a = rsub + p + (nbp ? (int)SM.bp_shift[k] : 0);
-                int wi = a >> 2; const int sh = (a & 3) * 8;
+            auto src_of = [&](int c, int& sh) {                       // first source word of output chunk c, and its byte shift
+                const int k = SM.chunk_bp[c];
+                const int a = rsub + (c << 4) + (nbp ? (int)SM.bp_shift[k] : 0);
+                int wi = a >> 2; sh = (a & 3) * 8;
                 wi = wi < wlo ? wlo : wi; wi = wi > whi ? whi : wi;
-                const uint32_t* xp = rp + wi;
+                return rp + wi;
+            };
+            for (int c = lane; c < nchunk; c += 64) {                  // two chunks per trip: ten loads in flight per lane
+                int sh0, sh1 = 0; const int c1 = c + 32; const bool two = c1 < nchunk;
+                const uint32_t* xp = src_of(c, sh0); const uint32_t* yp = two ? src_of(c1, sh1) : xp;
                 const uint32_t x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3], x4 = xp[4];
-                uint4 o; o.x = __funnelshift_r(x0, x1, sh); o.y = __funnelshift_r(x1, x2, sh); o.z = __funnelshift_r(x2, x3, sh); o.w = __funnelshift_r(x3, x4, sh);
-                *reinterpret_cast<uint4*>(SM.seq + p) = o;
+                const uint32_t y0 = yp[0], y1 = yp[1], y2 = yp[2], y3 = yp[3], y4 = yp[4];
+                uint4 o; o.x = __funnelshift_r(x0, x1, sh0); o.y = __funnelshift_r(x1, x2, sh0); o.z = __funnelshift_r(x2, x3, sh0); o.w = __funnelshift_r(x3, x4, sh0);
+                *reinterpret_cast<uint4*>(SM.seq + (c << 4)) = o;
+                if (two) {
+                    o.x = __funnelshift_r(y0, y1, sh1); o.y = __funnelshift_r(y1, y2, sh1); o.z = __funnelshift_r(y2, y3, sh1); o.w = __funnelshift_r(y3, y4, sh1);
+                    *reinterpret_cast<uint4*>(SM.seq + (c1 << 4)) = o;
+                }
             }
             __syncwarp();
             // (C) the part of a chunk that follows a slice start inside it: same 5-word gather, byte stores
