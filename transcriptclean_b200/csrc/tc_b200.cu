@@ -936,22 +936,33 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutD
                     }
                     int rbase = 0;
                     const uint32_t* const gw0p = P.G.g2 + (gbase >> 4); const int gsub = (int)(gbase & 15);
-                    for (int t0 = 0; t0 < nit; t0 += 32) {
-                        const int t = t0 + lane;
+                    auto locate = [&](int t0, int& p, const uint32_t*& gp, int& gsh) {   // item t0 + lane: chunk start, genome words, shift
                         const unsigned word = __reduce_or_sync(FULL, (my_w >= t0 && my_w < t0 + 32) ? 1u << (my_w - t0) : 0u);
-                        int r = rbase + __popc(word & (0xffffffffu >> (31 - lane))) - 1;
+                        const int r = rbase + __popc(word & (0xffffffffu >> (31 - lane))) - 1;
                         rbase += __popc(word);
                         const int coff = __shfl_sync(FULL, my_coff, r & 31), goff = __shfl_sync(FULL, my_goff, r & 31);
-                        if (t < nit) {
-                            const int p = (t + coff) << 4;                       // chunk start (query offset)
-                            const int gb = gsub + p + goff;                      // bases from the read's first genome word to chunk byte 0
-                            const uint32_t* gp = gw0p + (gb >> 4);
-                            const uint32_t gw = __funnelshift_r(gp[0], gp[1], (gb & 15) * 2);
-                            const uint4 x = *reinterpret_cast<const uint4*>(SM.seq + p);
-                            const uint32_t d0 = (x.x & 0xDFDFDFDFu) ^ lut[gw & 255u], d1 = (x.y & 0xDFDFDFDFu) ^ lut[(gw >> 8) & 255u];
-                            const uint32_t d2 = (x.z & 0xDFDFDFDFu) ^ lut[(gw >> 16) & 255u], d3 = (x.w & 0xDFDFDFDFu) ^ lut[gw >> 24];
-                            bad |= (d0 | d1 | d2 | d3) != 0u;
-                        }
+                        p = (t0 + lane + coff) << 4;                             // chunk start (query offset)
+                        const int gb = gsub + p + goff;                          // bases from the read's first genome word to chunk byte 0
+                        gp = gw0p + (gb >> 4); gsh = (gb & 15) * 2;
+                    };
+                    auto differs = [&](int p, uint32_t g0, uint32_t g1, int gsh) {
+                        const uint32_t gw = __funnelshift_r(g0, g1, gsh);
+                        const uint4 x = *reinterpret_cast<const uint4*>(SM.seq + p);
+                        const uint32_t d0 = (x.x & 0xDFDFDFDFu) ^ lut[gw & 255u], d1 = (x.y & 0xDFDFDFDFu) ^ lut[(gw >> 8) & 255u];
+                        const uint32_t d2 = (x.z & 0xDFDFDFDFu) ^ lut[(gw >> 16) & 255u], d3 = (x.w & 0xDFDFDFDFu) ^ lut[gw >> 24];
+                        return (d0 | d1 | d2 | d3) != 0u;
+                    };
+                    for (int t0 = 0; t0 < nit; t0 += 64) {                 // two items per trip: four genome loads in flight per lane
+                        int pA, pB = 0, shA, shB = 0; const uint32_t* gA; const uint32_t* gB = gw0p;
+                        locate(t0, pA, gA, shA);
+                        const bool two = t0 + 32 < nit;                         // (uniform)
+                        if (two) locate(t0 + 32, pB, gB, shB);
+                        const bool vA = t0 + lane < nit, vB = two && t0 + 32 + lane < nit;
+                        uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+                        if (vA) { a0 = gA[0]; a1 = gA[1]; }
+                        if (vB) { b0 = gB[0]; b1 = gB[1]; }
+                        if (vA) bad |= differs(pA, a0, a1, shA);
+                        if (vB) bad |= differs(pB, b0, b1, shB);
                     }
                     for (int j = lane; j < 2 * nrun; j += 32) {
                         const int r = j >> 1, a = run_q[r], b = a + (int)run_ct[r];
