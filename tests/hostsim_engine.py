@@ -11,9 +11,9 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def build():
-    srcs = [os.path.join(_DIR, "hostsim.cpp"), os.path.join(_ROOT, "transcriptclean_b200", "csrc", "tc_b200.cu"),
-            os.path.join(_ROOT, "transcriptclean_b200", "csrc", "tc_plan.cuh"), os.path.join(_ROOT, "include", "tc_b200.h"),
-            os.path.join(_ROOT, "transcriptclean_b200", "csrc", "tc_host.cpp")]
+    csrc = os.path.join(_ROOT, "transcriptclean_b200", "csrc")
+    srcs = [os.path.join(_DIR, "hostsim.cpp"), os.path.join(_ROOT, "include", "tc_b200.h")] + \
+           sorted(os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".cpp")))
     if os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
         return _SO
     subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-x", "c++", "-shared", "-fPIC", "-pthread", "-o", _SO, srcs[0]])

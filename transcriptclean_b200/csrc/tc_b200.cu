@@ -1,13 +1,15 @@
-// tc_b200.cu - kernels and C ABI of the B200 correction engine (see include/tc_b200.h).
+// tc_b200.cu - C ABI and batch orchestration of the B200 correction engine (see include/tc_b200.h).
 //
-// Pipeline of one batch (all on the context's stream):
-//   k_init      warp/read   status word; NM/MD regeneration for reads lacking a tag (tr.py:47-48)
-//   k_measure   thread/read workspace sizing                      -> exclusive scan
-//   k_plan      thread/read mismatch + indel stages (tc_plan.cuh)
-//   k_junction  thread/read junction objects + noncanonical junction rescue
-//   k_sizes     thread/read exact output sizes                    -> 4 exclusive scans
-//   k_emit      warp/read   CIGAR / TE / jM,jI compaction, SEQ materialisation (genome gather),
-//                           NM/MD regeneration (genome gather + compare)
+// Pipeline of one batch (all on the context's stream; kernels in the .cuh files of this directory):
+//   k_init / k_init_nmmd   status word; NM/MD bootstrap of reads lacking a tag (tr.py:47-48)      tc_nmmd.cuh
+//   k_measure              workspace sizing, MD tags split into tokens        -> exclusive scan    tc_plan.cuh
+//   k_plan                 mismatch + indel stages                                                 tc_plan.cuh
+//   k_jn_init / k_jn_fix   junction objects; noncanonical junction rescue (warp per listed read)   tc_junction.cuh
+//   k_sizes, k_pack        exact output sizes -> 4 exclusive scans; one plan row per read          tc_plan.cuh
+//   k_small                TE rows / CIGAR / jM,jI into the dense outputs                          tc_emit.cuh
+//   k_emit                 new SEQ (genome gather) + the clean-read NM/MD check                    tc_emit.cuh
+//   k_nmmd_exact           token-emitting NM/MD walk for the reads k_emit lists                    tc_nmmd.cuh
+//   k_seq_unpack / k_seq_pack   4-bit SEQ <-> ASCII rows on the copy streams (this file)
 // With -DTC_HOSTSIM the same ABI is built for the CPU with serial loops instead of kernels;
 // that build lives under tests/hostsim and is TEST INFRASTRUCTURE for the host-side code
 // (parser, renderer, CLI) on machines without a GPU.  The product never loads it.
@@ -95,537 +97,13 @@ TC_HD void small_copies_read(const Params& P, const OutDev& O, int64_t i, int dr
 #ifndef TC_HOSTSIM
 // ================================================================================== CUDA
 
-#define FULL 0xffffffffu
-// fields of a read's plan row (one word per lane, `pw`)
-#define PF(k) __shfl_sync(FULL, pw, (k))
-#define PF64(k) ((int64_t)(((u64)(uint32_t)PF((k) + 1) << 32) | (u64)(uint32_t)PF(k)))
-#define WARPS_PER_BLOCK 8
-#define EMIT_CAP 4096            // reads whose new SEQ fits are staged in shared memory
-#define EMIT_MAXBP 192
-#define EMIT_MAXGI 192
-#define EMIT_MAXD 44
-
-#define EMIT_MAXRUN 32          // M runs of a read that tier 1 handles (one lane per run)
-struct __align__(16) EmitSmem {  // per warp
-    uint8_t seq[EMIT_CAP + 32];
-    uint8_t chunk_bp[(EMIT_CAP >> 4) + 16];                             // slice in force at the start of each 16-byte chunk
-    union {
-        struct {                                                        // while SEQ is built
-            uint16_t bp_pos[EMIT_MAXBP]; int16_t bp_shift[EMIT_MAXBP]; // starts of input-SEQ slices: output offset, src-dst shift
-            uint16_t gi_out[EMIT_MAXGI]; uint16_t gi_len[EMIT_MAXGI]; int32_t gi_src[EMIT_MAXGI];   // genome slices
-        };
-        struct {                                                        // while NM/MD is verified (tier 1)
-            uint16_t run_q[EMIT_MAXRUN], run_ct[EMIT_MAXRUN]; int32_t run_g[EMIT_MAXRUN];   // M runs: query offset, length, reference offset
-            int32_t rb_w[EMIT_MAXRUN], rb_coff[EMIT_MAXRUN], rb_goff[EMIT_MAXRUN];         // runs that own whole chunks: first item, chunk and genome offsets
-            int32_t d_g[EMIT_MAXD], d_ct[EMIT_MAXD], d_run[EMIT_MAXD];    // D ops: reference offset, length, match run before
-        };
-    };
-};
-#define EMIT_SMEM_BYTES (1024 + WARPS_PER_BLOCK * sizeof(EmitSmem))
-
-__device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
-    int x = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(FULL, x, d); if (lane >= d) x += y; }
-    total = __shfl_sync(FULL, x, 31);
-    return x - v;
-}
-
-__device__ __forceinline__ bool warp_range_has_exc(const GenomeDev& G, int64_t g0, int64_t g1, int lane) {
-    const int64_t b0 = g0 >> 8; const int nblk = (int)(((g1 - 1) >> 8) - b0) + 1;
-    bool hit = false;
-    for (int t = lane; t < nblk; t += 32) { const int64_t b = b0 + t; hit |= (G.excblk[b >> 5] >> (b & 31)) & 1u; }
-    return __any_sync(FULL, hit);
-}
-
-struct NmMd { int nm, len, ntok, carry; bool none; };
-
-// getNMandMDFlags (tr.py:280-342, Q8/Q9).  One warp walks the CIGAR (ops are fetched 32 at a
-// time, one per lane, and broadcast with shuffles; cursors are 32-bit offsets from POS).
-//  FAST (SEQ staged in shared memory, 16-byte aligned): every lane takes 16 bases of an M run -
-//    five LDS.32 + funnel shifts for the read bytes, two coalesced words of the 2-bit plane,
-//    a 256-entry code->ASCII table, one XOR per 4 bases; a 512-base chunk without difference
-//    costs ~50 instructions.  A chunk with any difference (or an M run that touches a literal
-//    run of the genome) is redone by the exact path below.
-//  exact path: lanes take consecutive bases, gather the genome byte (2-bit + case plane,
-//    literal runs), compare case-insensitively, and compact the mismatch tokens with
-//    ballot / popc / prefix sums.
-// WRITE=false measures NM and the MD length; WRITE=true writes the MD bytes.
-template <bool WRITE, bool FAST>
-__device__ NmMd warp_nmmd(const GenomeDev& G, const uint8_t* seq, const uint32_t* lut, const CigSrc& cs, int chrom,
-                          int64_t pos, int lane, uint8_t* dst) {
-    const int64_t goff = G.chrom_off[chrom] - 1, clen = G.chrom_len[chrom];
-    const int64_t gbase = goff + pos;                   // plane index of reference offset 0
-    NmMd R;
-    int nm = 0, len = 0, carry = 0, ntok = 0, q = 0, gr = 0; bool none = false;
-    // reference span: one literal-run check and one contig-end check for the whole read
-    bool span_exc, careful;
-    {
-        int64_t span = 0;
-        for (int k = lane; k < cs.n; k += 32) { int op; int32_t ct; cig_get(cs, k, op, ct); if (op == 'M' || op == 'D' || op == 'N' || op == 'H') span += ct; }
-#pragma unroll
-        for (int d = 16; d; d >>= 1) span += __shfl_xor_sync(FULL, span, d);
-        careful = pos < 1 || pos + span - 1 > clen || span > 0x7fffffffll;
-        span_exc = careful || (span > 0 && warp_range_has_exc(G, gbase, gbase + span, lane));
-    }
-    for (int k0 = 0; k0 < cs.n && !none; k0 += 32) {
-        int op_l = 0; int32_t ct_l = 0;
-        if (k0 + lane < cs.n) cig_get(cs, k0 + lane, op_l, ct_l);
-        const int nround = min(32, cs.n - k0);
-        for (int j = 0; j < nround; j++) {
-            const int op = __shfl_sync(FULL, op_l, j); const int32_t ct = __shfl_sync(FULL, ct_l, j);
-            if (op == 'M') {
-                if (ct <= 0) continue;
-                if (careful) { const int64_t g = pos + gr; if (g < 1 || g + ct - 1 > clen) { none = true; break; } }   // tr.py:303-304
-                const int64_t g0 = gbase + gr;
-                const bool exc = span_exc && warp_range_has_exc(G, g0, g0 + ct, lane);
-                for (int32_t c0 = 0; c0 < ct; c0 += (FAST ? 512 : 32)) {
-                    const int span = min(FAST ? 512 : 32, ct - c0);
-                    if (FAST) {
-                        bool bad = exc;
-                        if (!exc) {
-                            const int32_t lo = c0 + 16 * lane; int nb = ct - lo; nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-                            if (nb > 0) {
-                                const int a = q + lo;
-                                const uint32_t* sp = reinterpret_cast<const uint32_t*>(seq) + (a >> 2); const int sh = (a & 3) * 8;
-                                const uint32_t x0 = sp[0], x1 = sp[1], x2 = sp[2], x3 = sp[3], x4 = sp[4];
-                                const int64_t gb = g0 + lo; const uint32_t* gp = G.g2 + (gb >> 4);
-                                const uint32_t gw = __funnelshift_r(gp[0], gp[1], (int)(gb & 15) * 2);
-                                uint32_t d0 = (__funnelshift_r(x0, x1, sh) & 0xDFDFDFDFu) ^ lut[gw & 255u];
-                                uint32_t d1 = (__funnelshift_r(x1, x2, sh) & 0xDFDFDFDFu) ^ lut[(gw >> 8) & 255u];
-                                uint32_t d2 = (__funnelshift_r(x2, x3, sh) & 0xDFDFDFDFu) ^ lut[(gw >> 16) & 255u];
-                                uint32_t d3 = (__funnelshift_r(x3, x4, sh) & 0xDFDFDFDFu) ^ lut[gw >> 24];
-                                if (nb < 16) {                          // the lane that holds the end of the run
-                                    const uint32_t m0 = nb >= 4 ? ~0u : ((1u << (8 * nb)) - 1u);
-                                    const uint32_t m1 = nb >= 8 ? ~0u : (nb <= 4 ? 0u : ((1u << (8 * (nb - 4))) - 1u));
-                                    const uint32_t m2 = nb >= 12 ? ~0u : (nb <= 8 ? 0u : ((1u << (8 * (nb - 8))) - 1u));
-                                    const uint32_t m3 = nb <= 12 ? 0u : ((1u << (8 * (nb - 12))) - 1u);
-                                    d0 &= m0; d1 &= m1; d2 &= m2; d3 &= m3;
-                                }
-                                bad = (d0 | d1 | d2 | d3) != 0u;
-                            }
-                        }
-                        if (!__any_sync(FULL, bad)) { carry += span; continue; }
-                    }
-                    for (int32_t c = c0; c < c0 + span; c += 32) {       // exact path
-                        const int32_t idx = c + lane; const bool valid = idx < c0 + span;
-                        uint8_t rb = 0, gb = 0;
-                        if (valid) { rb = seq[q + idx]; gb = exc ? genome_byte(G, g0 + idx) : genome_byte_fast(G, g0 + idx); }
-                        const bool mism = valid && up8(rb) != up8(gb);
-                        const unsigned mask = __ballot_sync(FULL, mism);
-                        const int nvalid = min(32, c0 + span - c);
-                        if (mask == 0) { carry += nvalid; continue; }
-                        nm += __popc(mask); ntok += __popc(mask);
-                        const unsigned below = mask & ((1u << lane) - 1u);
-                        const int run_before = below ? (lane - (31 - __clz(below)) - 1) : carry + lane;
-                        const int nd = ndigits((uint32_t)run_before);
-                        int total; const int off = warp_excl_scan(mism ? nd + 1 : 0, lane, total);
-                        if (WRITE && mism) { write_dec(dst + len + off, (uint32_t)run_before, nd); dst[len + off + nd] = gb; }
-                        len += total;
-                        carry = nvalid - 1 - (31 - __clz(mask));
-                    }
-                }
-                q += ct; gr += ct;
-            } else if (op == 'D') {
-                int gl = ct;
-                if (careful) {
-                    const int64_t g = pos + gr;
-                    if (g < 1) { none = true; break; }
-                    gl = fetch_len(G, chrom, g, g + ct - 1);
-                    if (gl == 0) { none = true; break; }                // tr.py:327-328
-                }
-                const int nd = ndigits((uint32_t)carry);
-                if (WRITE) {
-                    if (lane == 0) { write_dec(dst + len, (uint32_t)carry, nd); dst[len + nd] = '^'; }
-                    for (int t = lane; t < gl; t += 32) dst[len + nd + 1 + t] = genome_byte(G, gbase + gr + t);
-                }
-                len += nd + 1 + gl; carry = 0; nm += ct; gr += ct; ntok++;
-            } else if (op == 'I') { q += ct; nm += ct; }
-            else if (op == 'S') q += ct;
-            else if (op == 'N' || op == 'H') gr += ct;
-        }
-    }
-    R.carry = carry;
-    if (!none && carry > 0) {
-        const int nd = ndigits((uint32_t)carry);
-        if (WRITE && lane == 0) write_dec(dst + len, (uint32_t)carry, nd);
-        len += nd;
-    }
-    R.nm = nm; R.len = len; R.none = none; R.ntok = ntok;
-    return R;
-}
-
-// grabs `len` bytes of an MD pool for the warp; returns the offset or -1 when the pool is full
-// (the cursor still advances, so the host learns the exact size needed for the retry)
-__device__ __forceinline__ int64_t pool_grab(unsigned long long* cursor, int64_t cap, int len, int lane) {
-    unsigned long long off = 0;
-    if (lane == 0) off = atomicAdd(cursor, (unsigned long long)len);
-    off = __shfl_sync(FULL, off, 0);
-    return ((int64_t)off + len <= cap) ? (int64_t)off : -1;
-}
-
-// measure, allocate, write: MD of one read into a pool.  Reads without any token (the usual
-// case after correction) only need the final run length.
-template <bool FAST>
-__device__ __forceinline__ void nmmd_to_pool(const GenomeDev& G, const uint8_t* seq, const uint32_t* lut, const CigSrc& cs,
-                                             int chrom, int64_t pos, int lane, unsigned long long* cursor, int64_t cap,
-                                             uint8_t* pool, int64_t inline_off, int& nm, int& len, int64_t& off, bool& none) {
-    NmMd r = warp_nmmd<false, FAST>(G, seq, lut, cs, chrom, pos, lane, 0);
-    none = r.none; nm = r.nm; len = r.none ? 0 : r.len;
-    off = (inline_off >= 0 && len <= 8) ? inline_off : pool_grab(cursor, cap, len, lane);
-    if (off >= 0 && len > 0) {
-        if (r.ntok == 0) { if (lane == 0) write_dec(pool + off, (uint32_t)r.carry, len); }
-        else warp_nmmd<true, FAST>(G, seq, lut, cs, chrom, pos, lane, pool + off);
-    }
-}
-
-// status word of every read (thread per read); reads that lack NM or MD (tr.py:47-48) are listed for k_init_nmmd
-__global__ void k_init(Params P, int32_t* list, unsigned* count) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.B.n) return;
-    const int cls = read_class(P.B.flag[i], P.B.chrom[i]);
-    const uint8_t tags = P.B.tags[i];
-    P.W.status[i] = (uint32_t)cls;
-    if (cls == 0 && (!(tags & TAG_NM) || !(tags & TAG_MD))) list[atomicAdd(count, 1u)] = (int32_t)i;
-}
-// NM/MD bootstrap of the listed reads, one warp per read
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_init_nmmd(Params P, InitDev I, int32_t* nm_init, const int32_t* list, const unsigned* count) {
-    const int lane = threadIdx.x & 31;
-    const int64_t nw = (int64_t)gridDim.x * WARPS_PER_BLOCK, nl = (int64_t)*count;
-    for (int64_t t = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); t < nl; t += nw) {
-        const int64_t i = list[t];
-        CigSrc cs; cs.packed = 0; cs.op = P.B.cig_op + P.B.cig_off[i]; cs.len = P.B.cig_len + P.B.cig_off[i];
-        cs.n = (int)(P.B.cig_off[i + 1] - P.B.cig_off[i]);
-        int nm, len; int64_t off; bool none;
-        nmmd_to_pool<false>(P.G, P.B.seq + P.B.seq_off[i], 0, cs, P.B.chrom[i], P.B.pos[i], lane, I.cursor, I.cap, I.pool, -1, nm, len, off, none);
-        uint32_t st = P.W.status[i] | TC_ST_NMMD_DEVICE;
-        if (none) { st |= TC_ST_NMMD_NONE; nm = 0; }
-        if (lane == 0) { P.W.md_init_off[i] = off < 0 ? 0 : off; P.W.md_init_len[i] = off < 0 ? 0 : len; nm_init[i] = nm; P.W.status[i] = st; }
-    }
-}
+#include "tc_warp.cuh"
+#include "tc_nmmd.cuh"
 
 __global__ void k_measure(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) measure_read(P, i); }
 __global__ void __launch_bounds__(128, 8) k_plan(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) plan_read(P, i); }
-// junction objects for every read; reads that need cleanNoncanonical are appended to `list`
-__global__ void __launch_bounds__(128, 8) k_jn_init(Params P, int32_t* list, unsigned* count) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P.B.n && junction_init_read(P, i)) list[atomicAdd(count, 1u)] = (int32_t)i;
-}
-// ---------------------------------------------------------------------------------- junction rescue, one warp per listed read
-// cleanNoncanonical (TC.py:1186-1231) with the control flow of junction_fix_read (tc_plan.cuh) kept
-// warp-uniform; what is a loop over a list there - the copies of seg_insert / seg_delete / cig_edit,
-// locate_exon, the length sums, the nearest-site searches - runs across the lanes here.
+#include "tc_junction.cuh"
 
-__device__ __forceinline__ int64_t w_seg_total(const u64* s, int n, int lane) {
-    int t = 0;
-    for (int j = lane; j < n; j += 32) t += (int)seg_len(s[j]);
-    return (int64_t)__reduce_add_sync(FULL, t);
-}
-__device__ __forceinline__ int64_t w_cig_qlen(const u64* c, int n, int lane) {                    // tr.py:591-605
-    int t = 0;
-    for (int k = lane; k < n; k += 32) { const int op = cg_op(c[k]); if (op == 'M' || op == 'S' || op == 'I') t += cg_len(c[k]); }
-    return (int64_t)__reduce_add_sync(FULL, t);
-}
-// group_CIGAR_by_exon_and_intron (TC.py:1379-1412): exon t = the ops between the (t-1)-th and the t-th N
-__device__ bool w_locate_exon(const u64* cig, int n, int t, ExonLoc& e, int& nN, int lane) {
-    const unsigned lt = (1u << lane) - 1u;
-    int ncount = 0, qcur = 0; int lo = 0, hi = -1; int q0 = 0, q1 = 0;
-    for (int k0 = 0; k0 < n; k0 += 32) {
-        const int k = k0 + lane; int op = 0, len = 0;
-        if (k < n) { const u64 c = cig[k]; op = cg_op(c); len = cg_len(c); }
-        const bool isN = op == 'N';
-        int qt; const int qs = qcur + warp_excl_scan((op == 'M' || op == 'S' || op == 'I') ? len : 0, lane, qt);
-        const unsigned mN = __ballot_sync(FULL, isN);
-        const int nb = ncount + __popc(mN & lt);
-        const unsigned mHi = __ballot_sync(FULL, isN && nb == t), mLo = __ballot_sync(FULL, isN && nb == t - 1);
-        if (mHi) { const int sl = __ffs(mHi) - 1; hi = k0 + sl; q1 = __shfl_sync(FULL, qs, sl); }
-        if (mLo) { const int sl = __ffs(mLo) - 1; lo = k0 + sl + 1; q0 = __shfl_sync(FULL, qs, sl); }
-        ncount += __popc(mN); qcur += qt;
-    }
-    nN = ncount;
-    if (t > ncount || t < 0) return false;
-    e.lo = lo; e.q0 = q0;
-    if (hi >= 0) { e.hi = hi; e.q1 = q1; e.nidx = hi; } else { e.hi = n; e.q1 = qcur; e.nidx = -1; }
-    return true;
-}
-__device__ int w_seg_insert(const u64* s, int n, u64* d, int64_t qpos, u64 ns, int lane) {
-    if (seg_len(ns) == 0) { for (int j = lane; j < n; j += 32) d[j] = s[j]; return n; }
-    bool found = false; int jstar = 0, shift = 0; int64_t qcur = 0;
-    for (int j0 = 0; j0 < n; j0 += 32) {
-        const int j = j0 + lane; const bool valid = j < n;
-        const u64 sg = valid ? s[j] : 0ull; const int len = valid ? (int)seg_len(sg) : 0;
-        int tot; const int64_t qs = qcur + warp_excl_scan(len, lane, tot);
-        int64_t q_at = 0;
-        if (!found) {
-            const unsigned mC = __ballot_sync(FULL, valid && qpos < qs + len);
-            if (mC) {
-                const int sl = __ffs(mC) - 1; jstar = j0 + sl;
-                q_at = ((int64_t)__shfl_sync(FULL, (int)(qs >> 32), sl) << 32) | (uint32_t)__shfl_sync(FULL, (int)(uint32_t)qs, sl);
-                found = true; shift = qpos > q_at ? 2 : 1;
-            }
-        }
-        if (valid) {
-            if (!found || j < jstar) d[j] = sg;
-            else if (j > jstar) d[j + shift] = sg;
-            else if (shift == 2) {
-                const int64_t l1 = qpos - qs;
-                d[j] = seg_make(seg_kind(sg), seg_src(sg), l1); d[j + 1] = ns; d[j + 2] = seg_make(seg_kind(sg), seg_src(sg) + l1, len - l1);
-            } else { d[j] = ns; d[j + 1] = sg; }
-        }
-        qcur += tot;
-    }
-    if (!found) { if (lane == 0) d[n] = ns; return n + 1; }
-    return n + shift;
-}
-__device__ int w_seg_delete(const u64* s, int n, u64* d, int64_t qa, int64_t qb, int lane) {
-    if (qa >= qb) { for (int j = lane; j < n; j += 32) d[j] = s[j]; return n; }
-    int m = 0; int64_t qcur = 0;
-    for (int j0 = 0; j0 < n; j0 += 32) {
-        const int j = j0 + lane; const bool valid = j < n;
-        const u64 sg = valid ? s[j] : 0ull; const int len = valid ? (int)seg_len(sg) : 0;
-        int tot; const int64_t a = qcur + warp_excl_scan(len, lane, tot), b = a + len;
-        const bool keep = b <= qa || a >= qb;
-        const int cnt = !valid ? 0 : keep ? 1 : (a < qa ? 1 : 0) + (b > qb ? 1 : 0);
-        int ctot; int p = m + warp_excl_scan(cnt, lane, ctot);
-        if (valid) {
-            if (keep) d[p] = sg;
-            else {
-                if (a < qa) d[p++] = seg_make(seg_kind(sg), seg_src(sg), qa - a);
-                if (b > qb) d[p] = seg_make(seg_kind(sg), seg_src(sg) + (qb - a), b - qb);
-            }
-        }
-        m += ctot; qcur += tot;
-    }
-    return m;
-}
-// editExonCIGAR (TC.py:1515-1555) on ops [lo,hi) plus the intron length change: the few ops the edit
-// touches are found by a (uniform) scalar walk, the list is copied across the lanes
-__device__ int w_cig_edit(const u64* src, int n, u64* dst, int lo, int hi, bool at_end, int nb, int intron_idx, int intron_delta,
-                          bool& degenerate, int lane) {
-    int sa = lo, sb = hi, km = -1, newlen = 0, ins_front = 0, ins_back = 0;
-    if (nb >= 0) {
-        if (hi - lo == 0) return -1;
-        if (at_end) { const u64 last = src[hi - 1]; if (cg_op(last) == 'M') { km = hi - 1; newlen = cg_len(last) + nb; } else ins_back = 1; }
-        else { const u64 first = src[lo]; if (cg_op(first) == 'M') { km = lo; newlen = cg_len(first) + nb; } else ins_front = 1; }
-    } else {
-        int64_t need = -(int64_t)nb;
-        if (at_end) {
-            int k = hi - 1; int32_t keep_len = -1;
-            for (; k >= lo; k--) {
-                const int64_t rem = (int64_t)cg_len(src[k]) - need;
-                if (rem > 0) { keep_len = (int32_t)rem; break; }
-                if (rem == 0) { k--; break; }
-                need = -rem;
-            }
-            sb = k + 1; if (keep_len >= 0) { km = k; newlen = keep_len; }
-        } else {
-            int k = lo; int32_t keep_len = -1;
-            for (; k < hi; k++) {
-                const int64_t rem = (int64_t)cg_len(src[k]) - need;
-                if (rem > 0) { keep_len = (int32_t)rem; break; }
-                if (rem == 0) { k++; break; }
-                need = -rem;
-            }
-            sa = k; if (keep_len >= 0) { km = k; newlen = keep_len; }
-        }
-        if (sb < sa) sb = sa;
-    }
-    const int nsurv = sb - sa; bool deg = false;
-    for (int k = lane; k < n; k += 32) {
-        u64 c = src[k];
-        if (k < lo || k >= hi) {
-            if (k == intron_idx) { const int32_t L = cg_len(c) + intron_delta; if (L <= 0) deg = true; c = cg_make('N', L); }
-            dst[k < lo ? k : lo + ins_front + nsurv + ins_back + (k - hi)] = c;
-        } else if (k >= sa && k < sb) {
-            if (k == km) c = cg_make(cg_op(c), newlen);
-            dst[lo + ins_front + (k - sa)] = c;
-        }
-    }
-    if (lane == 0) { if (ins_front) dst[lo] = cg_make('M', nb); if (ins_back) dst[lo + nsurv] = cg_make('M', nb); }
-    if (__any_sync(FULL, deg)) degenerate = true;
-    return lo + ins_front + nsurv + ins_back + (n - hi);
-}
-// sj_nearest (tc_plan.cuh) with a 32-way search: three probes instead of fifteen for ~17,000 sites
-__device__ bool w_sj_nearest(const u64* tab, const int32_t* rng, int32_t n_prefix, u64 prefix, int64_t q, bool tie_right, int& dist, int lane) {
-    if (prefix >= (u64)n_prefix) return false;
-    int lo = rng[prefix], hi = rng[prefix + 1];
-    if (lo == hi) return false;
-    const int lo0 = lo, hi0 = hi;
-    const u64 key = (prefix << 32) | (u64)(uint32_t)q;
-    while (hi - lo > 32) {
-        const int step = (hi - lo + 31) >> 5; const int idx = lo + lane * step;
-        const bool less = idx < hi && tab[idx] < key;
-        const int c = __popc(__ballot_sync(FULL, less));             // the probes below the key are the first c lanes
-        if (c == 0) { hi = lo; break; }
-        const int nlo = lo + (c - 1) * step + 1, nhi = lo + c * step;
-        lo = nlo; hi = nhi < hi ? nhi : hi;
-    }
-    { const int idx = lo + lane; const bool less = idx < hi && tab[idx] < key; lo += __popc(__ballot_sync(FULL, less)); }
-    const int i = lo; int64_t best;                                    // lower bound of the key inside [lo0, hi0)
-    if (i < hi0) {
-        best = (int64_t)(tab[i] & 0xffffffffull);
-        if (i > lo0) {
-            const int64_t left = (int64_t)(tab[i - 1] & 0xffffffffull);
-            const int64_t dl = q - left, dr = best - q;
-            if (dl < dr || (dl == dr && !tie_right)) best = left;
-        }
-    } else best = (int64_t)(tab[i - 1] & 0xffffffffull);
-    dist = (int)(best - q);
-    return true;
-}
-// fix_one_side_of_junction (TC.py:1415-1479); see fix_side in tc_plan.cuh
-__device__ bool w_fix_side(const Params& P, int chrom, int k, int side, int d, int32_t* bound_slot, int32_t& bound, JnState& S,
-                           u64* cig_dst, u64* seg_dst, bool& degenerate, int lane) {
-    if (d == 0) return true;
-    ExonLoc e; int nN; const int t = side == 0 ? k : k + 1;
-    if (!w_locate_exon(S.cig, S.nc, t, e, nN, lane)) return false;            // exonSeqs[targetExon] IndexError
-    const GenomeDev& G = P.G; const int64_t goff = G.chrom_off[chrom] - 1;
-    int ns2; int64_t newlen = S.seqlen;
-    if (side == 0) {
-        if (d > 0) {                                                  // case 1: extend exon end from the genome
-            const int32_t b = bound;
-            if (b < 1) return false;
-            const int gl = fetch_len(G, chrom, b, (int64_t)b + d - 1);
-            ns2 = w_seg_insert(S.seg, S.ns, seg_dst, e.q1, seg_make(1, goff + b, gl), lane); newlen += gl;
-        } else {                                                      // case 3: exon[0:d]
-            int64_t m = e.q1 - e.q0; if (m > -d) m = -d;
-            ns2 = w_seg_delete(S.seg, S.ns, seg_dst, e.q1 - m, e.q1, lane); newlen -= m;
-        }
-        bound += d; if (lane == 0) *bound_slot = bound;
-        if (k >= nN) return false;                                    // intronCIGARs[jn_number] IndexError
-        const int ncn = w_cig_edit(S.cig, S.nc, cig_dst, e.lo, e.hi, true, d, e.nidx, -d, degenerate, lane);
-        if (ncn < 0) return false;
-        S.nc = ncn;
-    } else {
-        if (d < 0) {                                                  // case 2: prepend to the next exon
-            const int64_t start = (int64_t)bound + 1 + d;
-            if (start < 1) return false;
-            const int gl = fetch_len(G, chrom, start, (int64_t)bound);
-            ns2 = w_seg_insert(S.seg, S.ns, seg_dst, e.q0, seg_make(1, goff + start, gl), lane); newlen += gl;
-        } else {                                                      // case 4: exon[d:]
-            int64_t m = e.q1 - e.q0; if (m > d) m = d;
-            ns2 = w_seg_delete(S.seg, S.ns, seg_dst, e.q0, e.q0 + m, lane); newlen -= m;
-        }
-        bound += d; if (lane == 0) *bound_slot = bound;
-        ExonLoc ek; ek.nidx = -1; int nn2; w_locate_exon(S.cig, S.nc, k, ek, nn2, lane);   // the intron before exon k+1 is the k-th N op
-        const int ncn = w_cig_edit(S.cig, S.nc, cig_dst, e.lo, e.hi, false, -d, ek.nidx, d, degenerate, lane);
-        if (ncn < 0) return false;
-        S.nc = ncn;
-    }
-    __syncwarp();                                                     // the new lists are read by other lanes from here on
-    S.cig = cig_dst; S.seg = seg_dst; S.ns = ns2; S.seqlen = newlen;
-    return newlen == w_cig_qlen(S.cig, S.nc, lane);                   // TC.py:1476-1477
-}
-
-__device__ void junction_fix_warp(const Params& P, int64_t i, int lane) {
-    const BatchDev& B = P.B; const WorkDev& W = P.W; const tc_options& O = P.O;
-    uint32_t st = W.status[i];
-    const int chrom = B.chrom[i]; const int strand = (B.flag[i] == 16) ? 1 : 0;
-    const int nj = W.n_jn[i];
-    WsView v = ws_view(W, i); int32_t* J = v.jn;
-    int32_t* C = W.counters + 10 * i;
-    bool canon = false, annot = (st & TC_ST_ALL_ANNOT) != 0;
-    st &= ~(uint32_t)(TC_ST_CANONICAL | TC_ST_ALL_ANNOT);
-    int nte = W.n_te[i]; int cJ = 0, uJ = 0;
-    const int64_t Lq = B.seq_off[i + 1] - B.seq_off[i];
-    int cb = W.cig_buf[i], sb = W.seg_buf[i]; int nc = W.n_cig_cur[i], ns = W.n_seg_cur[i];
-    if (cb < 0) {                                                     // still the input: bring it into the workspace
-        const int64_t c0 = B.cig_off[i]; nc = (int)(B.cig_off[i + 1] - c0);
-        for (int k = lane; k < nc; k += 32) v.cig[0][k] = cg_make(B.cig_op[c0 + k], B.cig_len[c0 + k]);
-        ns = 0; if (Lq > 0) { if (lane == 0) v.seg[0][0] = seg_make(0, 0, Lq); ns = 1; }
-        cb = 0; sb = 0;
-        __syncwarp();
-    }
-    int64_t seqlen = w_seg_total(v.seg[sb], ns, lane);
-    bool whole_fail = false, degenerate = false, any_ok = false;
-    const bool tie_right = O.sj_tie_right != 0;
-    for (int k = 0; k < nj && !whole_fail; k++) {
-        int32_t* r = J + k * JN_STRIDE;
-        const int code0 = r[4];
-        if (!(code0 == 0 || code0 == 20)) continue;
-        const int32_t id_a = r[2], id_b = r[3];
-        const int ds = strand == 0 ? 0 : 1, as = 1 - ds;             // sj.py:29-41
-        int32_t bnd[2] = {r[0], r[1]};
-        int dd[2] = {0, 0}; bool ok_t = true;                         // dd[0]: distance to the nearest donor, dd[1]: acceptor
-        const u64 pre = O.sj_ignore_strand ? (u64)chrom : (((u64)chrom << 1) | (u64)strand);
-#pragma unroll 1
-        for (int w = 0; w < 2 && ok_t; w++) {
-            const u64* tab = O.sj_ignore_strand ? (w == 0 ? P.S.don_u : P.S.acc_u) : (w == 0 ? P.S.don_s : P.S.acc_s);
-            const int32_t* rng = O.sj_ignore_strand ? (w == 0 ? P.S.rng_don_u : P.S.rng_acc_u) : (w == 0 ? P.S.rng_don_s : P.S.rng_acc_s);
-            ok_t = w_sj_nearest(tab, rng, P.S.n_prefix, pre, (int64_t)bnd[w == 0 ? ds : as] - 1, tie_right, dd[w], lane);
-        }
-        const int d_don = dd[0], d_acc = dd[1];
-        if (!ok_t) { whole_fail = true; break; }                      // Q23: raises outside the inner try
-        const int ad = d_don < 0 ? -d_don : d_don, aa = d_acc < 0 ? -d_acc : d_acc;
-        const int dist = ((d_don < 0) != (d_acc < 0)) ? ad + aa : (ad > aa ? ad - aa : aa - ad);   // TC.py:1371-1375
-        if (dist > O.max_sj_offset || ad > 2 * O.max_sj_offset || aa > 2 * O.max_sj_offset) {
-            uJ++; if (lane == 0) { int n2 = nte; te_put(v.te, n2, 3, id_a, id_b, dist, 1, 3); } nte++; continue;
-        }
-        const int t1 = (cb + 1) % 3, t2 = (cb + 2) % 3, u1 = (sb + 1) % 3, u2 = (sb + 2) % 3;   // the scratch buffers that are not the committed one
-        JnState S; S.cig = v.cig[cb]; S.nc = nc; S.seg = v.seg[sb]; S.ns = ns; S.seqlen = seqlen;
-        int used_c = cb, used_s = sb;
-        bool ok = true;
-#pragma unroll 1
-        for (int w = 0; w < 2 && ok; w++) {                           // donor side, then acceptor side
-            const int side = w == 0 ? ds : as, d = w == 0 ? d_don : d_acc;
-            if (d == 0) continue;
-            const int tc = used_c == cb ? t1 : t2, ts = used_s == sb ? u1 : u2;
-            ok = w_fix_side(P, chrom, k, side, d, &r[side], bnd[side], S, v.cig[tc], v.seg[ts], degenerate, lane); used_c = tc; used_s = ts;
-        }
-        int code = code0;
-        if (ok) {                                                     // update_post_ncsj_correction (TC.py:1279-1294)
-            if (!junction_code(P, chrom, strand, bnd[0], bnd[1], bnd[0], bnd[1], code)) ok = false;
-            if (lane == 0) { r[2] = bnd[0]; r[3] = bnd[1]; if (ok) r[4] = code; }
-        }
-        __syncwarp();
-        if (ok) {
-            cb = used_c; sb = used_s; nc = S.nc; ns = S.ns; seqlen = S.seqlen; any_ok = true;
-            bool cn = true, an = true;
-            for (int m = lane; m < nj; m += 32) {                     // tags + flags from the shared junction objects
-                int32_t* rr = J + m * JN_STRIDE;
-                const int c4 = rr[4];
-                rr[5] = rr[0]; rr[6] = rr[1]; rr[7] = c4;
-                if (c4 == 0 || c4 == 20) cn = false;
-                if (c4 < 20) an = false;
-            }
-            canon = __all_sync(FULL, cn); annot = __all_sync(FULL, an);
-            cJ++; if (lane == 0) { int n2 = nte; te_put(v.te, n2, 3, id_a, id_b, dist, 0, 0); } nte++;
-        } else {
-            uJ++; if (lane == 0) { int n2 = nte; te_put(v.te, n2, 3, id_a, id_b, dist, 1, 4); } nte++;
-        }
-        __syncwarp();
-    }
-    if (whole_fail) {                                                 // Q13/Q23: original read, TE dropped
-        st |= TC_ST_FALLBACK; st &= ~(uint32_t)TC_ST_CIGAR_REWRITTEN;
-        bool cn = true, an = true;
-        for (int m = lane; m < nj; m += 32) { const int c = J[m * JN_STRIDE + 4]; if (c == 0 || c == 20) cn = false; if (c < 20) an = false; }
-        canon = __all_sync(FULL, cn); annot = __all_sync(FULL, an);   // junction flags go back to the init values
-        if (lane == 0) {
-            W.cig_buf[i] = -1; W.seg_buf[i] = -1; W.n_te[i] = 0;
-            W.te_cnt[3 * i] = W.te_cnt[3 * i + 1] = W.te_cnt[3 * i + 2] = 0;
-            W.refresh[i] = 0; W.nm_extra[i] = 0;
-        }
-    } else {
-        if (any_ok) { st |= TC_ST_CIGAR_REWRITTEN | TC_ST_JM_DEVICE | TC_ST_JI_DEVICE; if (degenerate) st |= TC_ST_ERR_INTRON; }
-        if (lane == 0) {
-            C[TC_C_COR_SJ] = cJ; C[TC_C_UNC_SJ] = uJ;
-            W.n_te[i] = nte;
-            if (any_ok) {
-                W.cig_buf[i] = (int8_t)cb; W.seg_buf[i] = (int8_t)sb; W.n_cig_cur[i] = nc; W.n_seg_cur[i] = ns; W.seq_len_out[i] = (int32_t)seqlen;
-                W.refresh[i] = 1; W.nm_extra[i] = 0;
-            }
-        }
-    }
-    if (canon) st |= TC_ST_CANONICAL;
-    if (annot) st |= TC_ST_ALL_ANNOT;
-    if (lane == 0) W.status[i] = st;
-}
-
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_jn_fix(Params P, const int32_t* list, const unsigned* count) {
-    const int lane = threadIdx.x & 31;
-    const int64_t nw = (int64_t)gridDim.x * WARPS_PER_BLOCK, nl = (int64_t)*count;
-    for (int64_t t = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); t < nl; t += nw) junction_fix_warp(P, list[t], lane);
-}
 __global__ void k_sizes(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) sizes_read(P, i); }
 __global__ void k_dry(Params P) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -634,435 +112,7 @@ __global__ void k_dry(Params P) {
 
 __global__ void k_pack(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) pack_read(P, i); }
 
-// small_copies_read as one warp per read: TE rows into stage order by a ballot partition, CIGAR and
-// jM / jI copies, all from the read's 128-byte plan row.  A light kernel of its own (no shared memory,
-// few registers, 48 warps of an SM resident): these phases are latency, not bytes, and inside
-// k_emit they held its 30 resident warps up for a fifth of its time.
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 6) k_small(Params P, OutDev O, int dry) {
-    const int lane = threadIdx.x & 31; const unsigned lt = (1u << lane) - 1u;
-    const BatchDev& B = P.B; const WorkDev& W = P.W;
-    const int64_t nw = (int64_t)gridDim.x * WARPS_PER_BLOCK;
-    for (int64_t i = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); i < B.n; i += nw) {
-        const int pw = W.plan[i].w[lane];
-        if (((uint32_t)PF(EP_STATUS) & TC_ST_CLASS_MASK) != 0) continue;
-        const int pflags = PF(EP_FLAGS), cig_cap = PF(EP_CIGCAP), seg_cap = PF(EP_SEGCAP), te_cap = PF(EP_TECAP);
-        const int ncig = PF(EP_NCIG), nte = PF(EP_NTE), nj = PF(EP_NJN);
-        const int te_mm = PF(EP_TEMM), te_ins = PF(EP_TEINS), te_del = PF(EP_TEDEL);
-        const int64_t ws_off = PF64(EP_WS_LO), o_cig = PF64(EP_OCIG_LO), o_te = PF64(EP_OTE_LO), o_jn = PF64(EP_OJN_LO), cig0 = PF64(EP_CIG0_LO);
-        const u64* const ws = W.ws + ws_off;
-        const tc_te* const ws_te = reinterpret_cast<const tc_te*>(ws + 3ll * seg_cap + 3ll * cig_cap);
-        tc_te* dst = O.te + o_te;
-        if (dry) { for (int k = lane; k < nte; k += 32) dst[k] = ws_te[k]; continue; }
-        int base0 = 0, base1 = te_mm, base2 = te_mm + te_ins, base3 = te_mm + te_ins + te_del;
-        for (int c = 0; c < nte; c += 32) {
-            const int k = c + lane; const bool valid = k < nte;
-            tc_te r; int t = -1;
-            if (valid) { r = ws_te[k]; t = r.type; }
-            const unsigned m0 = __ballot_sync(FULL, t == 0), m1 = __ballot_sync(FULL, t == 1), m2 = __ballot_sync(FULL, t == 2), m3 = __ballot_sync(FULL, t == 3);
-            if (valid) {
-                const int slot = t == 0 ? base0 + __popc(m0 & lt) : t == 1 ? base1 + __popc(m1 & lt) : t == 2 ? base2 + __popc(m2 & lt) : base3 + __popc(m3 & lt);
-                dst[slot] = r;
-            }
-            base0 += __popc(m0); base1 += __popc(m1); base2 += __popc(m2); base3 += __popc(m3);
-        }
-        const int cb = ((pflags >> 2) & 3) - 1;
-        CigSrc cs; cs.n = ncig;
-        if (cb < 0) { cs.packed = 0; cs.op = B.cig_op + cig0; cs.len = B.cig_len + cig0; }
-        else { cs.packed = ws + 3ll * seg_cap + (int64_t)cb * cig_cap; cs.op = 0; cs.len = 0; }
-        uint8_t* dop = O.cig_op + o_cig; int32_t* dl = O.cig_len + o_cig;
-        for (int k = lane; k < ncig; k += 32) { int op; int32_t l; cig_get(cs, k, op, l); dop[k] = (uint8_t)op; dl[k] = l; }
-        if (nj > 0) {
-            int8_t* djm = O.jm + o_jn; int32_t* dji = O.ji + 2 * o_jn;
-            const int32_t* jn = reinterpret_cast<const int32_t*>(ws + 3ll * seg_cap + 3ll * cig_cap + 2ll * te_cap);
-            for (int k = lane; k < nj; k += 32) { const int32_t* r = jn + k * JN_STRIDE; djm[k] = (int8_t)r[7]; dji[2 * k] = r[5]; dji[2 * k + 1] = r[6]; }
-        }
-    }
-}
-
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// Output stage: one warp per read.  [seq_lo, seq_hi) = 32-bit words of B.seq that may be read
-// (the batch's SEQ buffer on the device, padded).
-//   1. plan row (128 B, one word per lane) -> everything about the read; the next read's row,
-//      segment list and SEQ lines are prefetched into L2 meanwhile
-//   2. TE rows back into stage order (ballot partition), CIGAR and jM/jI copies
-//   3. SEQ: built in shared memory - (A) segment list -> slice table, (B) 16-byte chunks gathered
-//      from the input SEQ with the shift in force, (C) fix-ups after slice starts, (D) genome
-//      slices byte-exact, (E) one coalesced 16-byte-vector store
-//   4. NM/MD (getNMandMDFlags): tier 1 stages the 2-bit genome words of every M run in shared
-//      memory with cp.async (all loads in flight at once) and verifies 16 bases per lane against
-//      the staged SEQ; a read that verifies clean needs no token (MD = total match length).
-//      Anything else (a difference, a D op, a literal run, the contig end) takes warp_nmmd.
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutDev O, int dry, int64_t seq_lo, int64_t seq_hi) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw);             // 4 bases (8 bits of the 2-bit plane) -> 4 ASCII bytes
-    EmitSmem& SM = reinterpret_cast<EmitSmem*>(smem_raw + 1024)[threadIdx.x >> 5];
-    for (int t = threadIdx.x; t < 256; t += blockDim.x) {
-        const uint32_t acgt = 0x54474341u;
-        lut[t] = ((acgt >> (8 * (t & 3))) & 255u) | (((acgt >> (8 * ((t >> 2) & 3))) & 255u) << 8) |
-                 (((acgt >> (8 * ((t >> 4) & 3))) & 255u) << 16) | (((acgt >> (8 * ((t >> 6) & 3))) & 255u) << 24);
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    const int64_t nw = (int64_t)gridDim.x * WARPS_PER_BLOCK;
-    const BatchDev& B = P.B; const WorkDev& W = P.W;
-    const uint32_t* S32 = reinterpret_cast<const uint32_t*>(B.seq);
-    const int dbg = P.O.reserved;     // profiling aid: bit0 skip small copies, bit1 skip SEQ, bit2 skip NM/MD (results invalid)
-    int64_t i = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    int pw = i < B.n ? W.plan[i].w[lane] : 0;
-    for (; i < B.n; i += nw) {
-        uint32_t st = (uint32_t)PF(EP_STATUS);
-        const int pflags = PF(EP_FLAGS), cig_cap = PF(EP_CIGCAP), seg_cap = PF(EP_SEGCAP), nm_extra = PF(EP_NMEXTRA);
-        const int ncig = PF(EP_NCIG), out_len = PF(EP_OUTLEN), ns = PF(EP_NSEG);
-        const int chrom = PF(EP_CHROM); const int64_t pos = PF(EP_POS);
-        const int64_t ws_off = PF64(EP_WS_LO), o_seq = PF64(EP_OSEQ_LO);
-        const int64_t in_base = PF64(EP_INB_LO), cig0 = PF64(EP_CIG0_LO); const int Lq = PF(EP_LQ);
-        // next read: fetch its row now (consumed at the end of this iteration), and pull its segment
-        // list and SEQ lines towards L2
-        const int64_t inext = i + nw;
-        const int pw_next = inext < B.n ? W.plan[inext].w[lane] : 0;
-        if ((st & TC_ST_CLASS_MASK) != 0) { if (lane == 0) { O.md_off[i] = 0; O.md_len[i] = 0; O.nm[i] = 0; } pw = pw_next; continue; }
-        u64* const ws = W.ws + ws_off;
-        const int cb = ((pflags >> 2) & 3) - 1, sb = ((pflags >> 4) & 3) - 1;
-        if (dry) { if (lane == 0) { O.md_off[i] = 0; O.md_len[i] = 0; O.nm[i] = 0; } pw = pw_next; continue; }
-        // (TE rows, the CIGAR and the jM / jI snapshot were copied by k_pack)
-        CigSrc cs; cs.n = ncig;
-        if (cb < 0) { cs.packed = 0; cs.op = B.cig_op + cig0; cs.len = B.cig_len + cig0; }
-        else { cs.packed = ws + 3ll * seg_cap + (int64_t)cb * cig_cap; cs.op = 0; cs.len = 0; }
-        if (dbg & 2) { pw = pw_next; continue; }
-        // ---- SEQ
-        const uint8_t* in_seq = B.seq + in_base;
-        uint8_t* out_seq = O.seq + o_seq;
-        const int64_t goff = P.G.chrom_off[chrom] - 1, clen = P.G.chrom_len[chrom];
-        const int64_t gbase = goff + pos;                                // plane index of the read's first reference base
-        const u64* const ws_seg = ws + (int64_t)(sb < 0 ? 0 : sb) * seg_cap;
-        bool fast = out_len <= EMIT_CAP;
-        int nbp = 0, ngi = 0;
-        if (fast) {
-            // (A) segment list -> starts of input slices (output offset, shift) + genome slices
-            if (sb < 0) { if (lane == 0) { SM.bp_pos[0] = 0; SM.bp_shift[0] = 0; } nbp = 1; }
-            else {
-                const u64* segs = ws_seg; int obase = 0; bool bad = false;
-                int last_shift = 0x7fffffff;                           // shift of the latest input slice (none yet)
-                for (int s0 = 0; s0 < ns; s0 += 32) {
-                    const int s = s0 + lane; const bool valid = s < ns;
-                    const u64 sg = valid ? segs[s] : 0ull;
-                    const int len = valid ? (int)seg_len(sg) : 0; const int64_t src = seg_src(sg); const int kind = seg_kind(sg);
-                    int total; const int ostart = obase + warp_excl_scan(len, lane, total);
-                    const bool isR = valid && kind == 0, isG = valid && kind == 1;
-                    const unsigned mR0 = __ballot_sync(FULL, isR), mG = __ballot_sync(FULL, isG);
-                    // an input slice that continues the previous one's shift (only genome slices lie between them:
-                    // corrected mismatches) is not a new slice - the genome bytes are patched in afterwards
-                    const int64_t shift = src - ostart;
-                    const bool shift_ok = shift >= -32768 && shift <= 32767;
-                    const int sh32 = shift_ok ? (int)shift : 0x7ffffffe;
-                    const unsigned prevR = mR0 & lt;
-                    const int prev_shift = __shfl_sync(FULL, sh32, prevR ? 31 - __clz(prevR) : lane);
-                    const bool isBP = isR && (!shift_ok || sh32 != (prevR ? prev_shift : last_shift));
-                    const unsigned mR = __ballot_sync(FULL, isBP);
-                    if (mR0) last_shift = __shfl_sync(FULL, sh32, 31 - __clz(mR0));
-                    if (isBP) {
-                        const int idx = nbp + __popc(mR & lt);
-                        if (idx < EMIT_MAXBP && shift_ok) { SM.bp_pos[idx] = (uint16_t)ostart; SM.bp_shift[idx] = (int16_t)shift; }
-                        else bad = true;
-                    }
-                    if (isG) {
-                        const int idx = ngi + __popc(mG & lt); const int64_t rel = src - gbase;
-                        if (idx < EMIT_MAXGI && len <= 65535 && rel >= -2147483647ll && rel <= 2147483647ll) {
-                            SM.gi_out[idx] = (uint16_t)ostart; SM.gi_len[idx] = (uint16_t)len; SM.gi_src[idx] = (int32_t)rel;
-                        } else bad = true;
-                    }
-                    nbp += __popc(mR); ngi += __popc(mG); obase += total;
-                }
-                if (__any_sync(FULL, bad)) fast = false;
-            }
-        }
-        // the next read's segment list and SEQ lines -> L2 while this read is being built
-        if (inext < B.n) {
-            const int64_t nws = ((int64_t)__shfl_sync(FULL, pw_next, EP_WS_HI) << 32) | (uint32_t)__shfl_sync(FULL, pw_next, EP_WS_LO);
-            const int64_t nin = ((int64_t)__shfl_sync(FULL, pw_next, EP_INB_HI) << 32) | (uint32_t)__shfl_sync(FULL, pw_next, EP_INB_LO);
-            const int nlq = __shfl_sync(FULL, pw_next, EP_LQ);
-            if (lane < 2) prefetch_l2(W.ws + nws + lane * 16);
-            else if ((lane - 2) * 128 < nlq) prefetch_l2(B.seq + nin + (lane - 2) * 128);
-        }
-        if (fast) {
-            __syncwarp();
-            bool read_exc = false;
-            for (int k = lane; k < ngi; k += 32) { const int64_t src = gbase + SM.gi_src[k]; read_exc |= genome_blk_has_exc(P.G, src) | genome_blk_has_exc(P.G, src + SM.gi_len[k] - 1) | (SM.gi_len[k] > 256); }
-            read_exc = __any_sync(FULL, read_exc);
-            const int nchunk = (out_len + 15) >> 4;
-            // each slice writes its index into the chunks that start inside it (slice k is in force from the
-            // first chunk boundary at or after its start up to the next slice's first chunk)
-            for (int k = lane; k < nbp; k += 32) {
-                const int c0 = k == 0 ? 0 : ((int)SM.bp_pos[k] + 15) >> 4;
-                const int c1 = k + 1 < nbp ? ((int)SM.bp_pos[k + 1] + 15) >> 4 : nchunk;
-                for (int c = c0; c < c1; c++) SM.chunk_bp[c] = (uint8_t)k;
-            }
-            __syncwarp();
-            // (B) bulk copy, 16 output bytes per lane, with the shift in force at the chunk start
-            // (32-bit offsets from the read's first word; the clamps keep the gather inside the SEQ buffer)
-            const uint32_t* const rp = S32 + (in_base >> 2); const int rsub = (int)(in_base & 3);
-            const int64_t wlo64 = seq_lo - (in_base >> 2), whi64 = seq_hi - 5 - (in_base >> 2);
-            const int wlo = wlo64 < -0x40000000ll ? -0x40000000 : (int)wlo64, whi = whi64 > 0x40000000ll ? 0x40000000 : (int)whi64;
-            auto src_of = [&](int c, int& sh) {                       // first source word of output chunk c, and its byte shift
-                const int k = SM.chunk_bp[c];
-                const int a = rsub + (c << 4) + (nbp ? (int)SM.bp_shift[k] : 0);
-                int wi = a >> 2; sh = (a & 3) * 8;
-                wi = wi < wlo ? wlo : wi; wi = wi > whi ? whi : wi;
-                return rp + wi;
-            };
-            for (int c = lane; c < nchunk; c += 64) {                  // two chunks per trip: ten loads in flight per lane
-                int sh0, sh1 = 0; const int c1 = c + 32; const bool two = c1 < nchunk;
-                const uint32_t* xp = src_of(c, sh0); const uint32_t* yp = two ? src_of(c1, sh1) : xp;
-                const uint32_t x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3], x4 = xp[4];
-                const uint32_t y0 = yp[0], y1 = yp[1], y2 = yp[2], y3 = yp[3], y4 = yp[4];
-                uint4 o; o.x = __funnelshift_r(x0, x1, sh0); o.y = __funnelshift_r(x1, x2, sh0); o.z = __funnelshift_r(x2, x3, sh0); o.w = __funnelshift_r(x3, x4, sh0);
-                *reinterpret_cast<uint4*>(SM.seq + (c << 4)) = o;
-                if (two) {
-                    o.x = __funnelshift_r(y0, y1, sh1); o.y = __funnelshift_r(y1, y2, sh1); o.z = __funnelshift_r(y2, y3, sh1); o.w = __funnelshift_r(y3, y4, sh1);
-                    *reinterpret_cast<uint4*>(SM.seq + (c1 << 4)) = o;
-                }
-            }
-            __syncwarp();
-            // (C) the part of a chunk that follows a slice start inside it: same 5-word gather, byte stores
-            for (int k = lane; k < nbp; k += 32) {
-                const int b = SM.bp_pos[k];
-                if (b & 15) {
-                    int end = (b | 15) + 1; if (end > out_len) end = out_len;
-                    if (k + 1 < nbp && (int)SM.bp_pos[k + 1] < end) end = SM.bp_pos[k + 1];
-                    const int a = rsub + b + (int)SM.bp_shift[k];
-                    int wi = a >> 2; const int sh = (a & 3) * 8;
-                    wi = wi < wlo ? wlo : wi; wi = wi > whi ? whi : wi;
-                    const uint32_t* xp = rp + wi;
-                    const uint32_t x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3], x4 = xp[4];
-                    uint32_t w[4]; w[0] = __funnelshift_r(x0, x1, sh); w[1] = __funnelshift_r(x1, x2, sh); w[2] = __funnelshift_r(x2, x3, sh); w[3] = __funnelshift_r(x3, x4, sh);
-                    const int n = end - b;
-#pragma unroll
-                    for (int j = 0; j < 15; j++) if (j < n) SM.seq[b + j] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
-                }
-            }
-            __syncwarp();
-            // (D) genome slices (corrected mismatches, deletion fills, junction extensions): byte exact (Q6)
-            for (int k = lane; k < ngi; k += 32) {
-                const int o = SM.gi_out[k], len = SM.gi_len[k]; const int64_t src = gbase + SM.gi_src[k];
-                if (read_exc) { for (int j = 0; j < len; j++) SM.seq[o + j] = genome_byte(P.G, src + j); }
-                else { for (int j = 0; j < len; j++) SM.seq[o + j] = genome_byte_fast(P.G, src + j); }
-            }
-            __syncwarp();
-            // (E) one coalesced store of the row (rows are padded to 16 bytes)
-            for (int c = lane; c < nchunk; c += 32) reinterpret_cast<uint4*>(out_seq)[c] = *reinterpret_cast<const uint4*>(SM.seq + (c << 4));
-        } else if (sb < 0) {
-            for (int64_t j = lane; j < Lq; j += 32) out_seq[j] = in_seq[j];
-        } else {
-            const u64* segs = ws_seg; int64_t o = 0;
-            for (int s = 0; s < ns; s++) {
-                const u64 sg = segs[s]; const int64_t src = seg_src(sg), len = seg_len(sg);
-                if (seg_kind(sg) == 0) { for (int64_t j = lane; j < len; j += 32) out_seq[o + j] = in_seq[src + j]; }
-                else { for (int64_t j = lane; j < len; j += 32) out_seq[o + j] = genome_byte(P.G, src + j); }
-                o += len;
-            }
-        }
-        // ---- NM / MD
-        if ((pflags & 1) && !(dbg & 4)) {
-            __syncwarp();                                              // SM tables are dead from here on: their space holds the run list
-            int nm = 0, len = 0; int64_t off = 0; bool done = false;
-            if (fast && ncig <= 32 * 4) {
-                // tier 1: run list (query offset, reference offset, length) of the M ops, lane-parallel
-                uint16_t* run_q = SM.run_q; uint16_t* run_ct = SM.run_ct; int32_t* run_g = SM.run_g;
-                int nrun = 0, qcur = 0, nD = 0, ibases = 0, dbases = 0, mcur = 0, m_at_last_d = 0, qsum = 0; int64_t gcur = 0; bool ovf = false;
-                for (int k0 = 0; k0 < ncig; k0 += 32) {
-                    int op = 0; int32_t ct = 0;
-                    if (k0 + lane < ncig) cig_get(cs, k0 + lane, op, ct);
-                    const int qadv = (op == 'M' || op == 'I' || op == 'S') ? ct : 0;
-                    const int gadv = (op == 'M' || op == 'D' || op == 'N' || op == 'H') ? ct : 0;
-                    // query offsets and matched-base counts share one scan (16 bits each: both are bounded by
-                    // the query length, which the REDUX total below checks against out_len <= EMIT_CAP)
-                    qsum += __reduce_add_sync(FULL, qadv);
-                    int qmtot, gtot; const int qm = warp_excl_scan((qadv << 16) | (op == 'M' ? (ct & 0xffff) : 0), lane, qmtot);
-                    const int gs = warp_excl_scan(gadv, lane, gtot);
-                    const int qs = (int)((unsigned)qm >> 16), ms = qm & 0xffff;              // ms: matched bases before this op
-                    const int qtot = (int)((unsigned)qmtot >> 16), mtot = qmtot & 0xffff;
-                    const bool isM = op == 'M' && ct > 0, isD = op == 'D';
-                    const unsigned mM = __ballot_sync(FULL, isM), mD = __ballot_sync(FULL, isD);
-                    {   // MD token of a D op: <matches since the previous token>^<bases>
-                        const unsigned prev = mD & lt;                  // nearest earlier D in this round, else the carried one
-                        const int cand = __shfl_sync(FULL, mcur + ms, prev ? 31 - __clz(prev) : lane);
-                        if (isD) {
-                            const int idx = nD + __popc(prev);
-                            if (idx < EMIT_MAXD) { SM.d_g[idx] = (int32_t)(gcur + gs); SM.d_ct[idx] = ct; SM.d_run[idx] = mcur + ms - (prev ? cand : m_at_last_d); }
-                            else ovf = true;
-                        }
-                        const int lastd = __shfl_sync(FULL, mcur + ms, mD ? 31 - __clz(mD) : 0);
-                        if (mD) m_at_last_d = lastd;
-                    }
-                    nD += __popc(mD);
-                    ibases += op == 'I' ? ct : 0; dbases += isD ? ct : 0;
-                    if (isM) {
-                        const int idx = nrun + __popc(mM & lt);
-                        if (idx < EMIT_MAXRUN && gcur + gs < 0x7fff0000ll) { run_q[idx] = (uint16_t)(qcur + qs); run_g[idx] = (int32_t)(gcur + gs); run_ct[idx] = (uint16_t)ct; }
-                        else ovf = true;
-                        // literal runs (N, IUPAC) under this M run?  (blocks of 256 bases; a run spans at most 17)
-                        const int64_t ga = gbase + gcur + gs;
-                        const uint32_t b1 = (uint32_t)((ga + ct - 1) >> 8);
-                        for (uint32_t b = (uint32_t)(ga >> 8); b <= b1; b++) ovf |= (P.G.excblk[b >> 5] >> (b & 31)) & 1u;
-                    }
-                    nrun += __popc(mM); qcur += qtot; gcur += gtot; mcur += mtot;
-                }
-                ibases = __reduce_add_sync(FULL, ibases); dbases = __reduce_add_sync(FULL, dbases);
-                const bool careful = pos < 1 || pos + gcur - 1 > clen || gbase < 16;   // (chunks may start up to 15 bases before a run)
-                bool tier1 = !careful && qsum == out_len && nD <= EMIT_MAXD && nrun <= EMIT_MAXRUN && !__any_sync(FULL, ovf);
-                if (tier1) {
-                    // The staged SEQ is verified in aligned 16-byte chunks (one LDS.128 per item; the 2-bit genome
-                    // words carry the shift).  Pass 1: chunks that lie wholly inside an M run, as one flat item
-                    // space over the runs that have any (lane r keeps run r's item offset / chunk offset / genome
-                    // offset; an item finds its run with REDUX.OR + POPC and fetches the two offsets by shuffle).
-                    // Pass 2: the partial chunk at the head and at the tail of every run, one lane each, masked.
-                    __syncwarp();
-                    bool bad = false; const int total_m = mcur;
-                    int my_w = 0x7fffffff, my_coff = 0, my_goff = 0, nit = 0;
-                    {
-                        int cnt = 0, c0 = 0, q0 = 0, g0 = 0;
-                        if (lane < nrun) { q0 = run_q[lane]; g0 = run_g[lane]; c0 = (q0 + 15) >> 4; cnt = ((q0 + (int)run_ct[lane]) >> 4) - c0; cnt = cnt < 0 ? 0 : cnt; }
-                        const int w = warp_excl_scan(cnt, lane, nit);
-                        const unsigned has = __ballot_sync(FULL, cnt > 0);
-                        if (cnt > 0) { const int k = __popc(has & lt); SM.rb_w[k] = w; SM.rb_coff[k] = c0 - w; SM.rb_goff[k] = g0 - q0; }
-                        __syncwarp();
-                        if (lane < __popc(has)) { my_w = SM.rb_w[lane]; my_coff = SM.rb_coff[lane]; my_goff = SM.rb_goff[lane]; }
-                    }
-                    int rbase = 0;
-                    const uint32_t* const gw0p = P.G.g2 + (gbase >> 4); const int gsub = (int)(gbase & 15);
-                    auto locate = [&](int t0, int& p, const uint32_t*& gp, int& gsh) {   // item t0 + lane: chunk start, genome words, shift
-                        const unsigned word = __reduce_or_sync(FULL, (my_w >= t0 && my_w < t0 + 32) ? 1u << (my_w - t0) : 0u);
-                        const int r = rbase + __popc(word & (0xffffffffu >> (31 - lane))) - 1;
-                        rbase += __popc(word);
-                        const int coff = __shfl_sync(FULL, my_coff, r & 31), goff = __shfl_sync(FULL, my_goff, r & 31);
-                        p = (t0 + lane + coff) << 4;                             // chunk start (query offset)
-                        const int gb = gsub + p + goff;                          // bases from the read's first genome word to chunk byte 0
-                        gp = gw0p + (gb >> 4); gsh = (gb & 15) * 2;
-                    };
-                    auto differs = [&](int p, uint32_t g0, uint32_t g1, int gsh) {
-                        const uint32_t gw = __funnelshift_r(g0, g1, gsh);
-                        const uint4 x = *reinterpret_cast<const uint4*>(SM.seq + p);
-                        const uint32_t d0 = (x.x & 0xDFDFDFDFu) ^ lut[gw & 255u], d1 = (x.y & 0xDFDFDFDFu) ^ lut[(gw >> 8) & 255u];
-                        const uint32_t d2 = (x.z & 0xDFDFDFDFu) ^ lut[(gw >> 16) & 255u], d3 = (x.w & 0xDFDFDFDFu) ^ lut[gw >> 24];
-                        return (d0 | d1 | d2 | d3) != 0u;
-                    };
-                    for (int t0 = 0; t0 < nit; t0 += 64) {                 // two items per trip: four genome loads in flight per lane
-                        int pA, pB = 0, shA, shB = 0; const uint32_t* gA; const uint32_t* gB = gw0p;
-                        locate(t0, pA, gA, shA);
-                        const bool two = t0 + 32 < nit;                         // (uniform)
-                        if (two) locate(t0 + 32, pB, gB, shB);
-                        const bool vA = t0 + lane < nit, vB = two && t0 + 32 + lane < nit;
-                        uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
-                        if (vA) { a0 = gA[0]; a1 = gA[1]; }
-                        if (vB) { b0 = gB[0]; b1 = gB[1]; }
-                        if (vA) bad |= differs(pA, a0, a1, shA);
-                        if (vB) bad |= differs(pB, b0, b1, shB);
-                    }
-                    for (int j = lane; j < 2 * nrun; j += 32) {
-                        const int r = j >> 1, a = run_q[r], b = a + (int)run_ct[r];
-                        const bool head = (a & 15) != 0;
-                        int s, e;
-                        if (!(j & 1)) { s = a; e = (a | 15) + 1; e = e < b ? e : b; if (!head) e = s; }
-                        else { s = b & ~15; e = b; if (!(b & 15) || (head && (b >> 4) == (a >> 4))) e = s; }
-                        if (e > s) {
-                            const int p = s & ~15, l8 = 8 * (s - p), h8 = 8 * (e - p);   // chunk bytes [lo, hi) count
-                            const int64_t gb = gbase + run_g[r] + (p - a);
-                            const uint32_t* gp = P.G.g2 + (gb >> 4);
-                            const uint32_t gw = __funnelshift_r(gp[0], gp[1], (int)(gb & 15) * 2);
-                            const uint4 x = *reinterpret_cast<const uint4*>(SM.seq + p);
-                            uint32_t d0 = (x.x & 0xDFDFDFDFu) ^ lut[gw & 255u], d1 = (x.y & 0xDFDFDFDFu) ^ lut[(gw >> 8) & 255u];
-                            uint32_t d2 = (x.z & 0xDFDFDFDFu) ^ lut[(gw >> 16) & 255u], d3 = (x.w & 0xDFDFDFDFu) ^ lut[gw >> 24];
-#define TC_BITS_BELOW(b, w) ((b) >= 32 * (w) + 32 ? ~0u : ((b) <= 32 * (w) ? 0u : ((1u << ((b) - 32 * (w))) - 1u)))
-                            d0 &= TC_BITS_BELOW(h8, 0) & ~TC_BITS_BELOW(l8, 0);
-                            d1 &= TC_BITS_BELOW(h8, 1) & ~TC_BITS_BELOW(l8, 1);
-                            d2 &= TC_BITS_BELOW(h8, 2) & ~TC_BITS_BELOW(l8, 2);
-                            d3 &= TC_BITS_BELOW(h8, 3) & ~TC_BITS_BELOW(l8, 3);
-#undef TC_BITS_BELOW
-                            bad |= (d0 | d1 | d2 | d3) != 0u;
-                        }
-                    }
-                    if (!__any_sync(FULL, bad)) {                      // every aligned base equals the genome
-                        nm = ibases + dbases;
-                        if (nD == 0) {                                 // MD is one number, at most 5 digits: the read's inline slot
-                            len = total_m > 0 ? ndigits((uint32_t)total_m) : 0;
-                            off = O.md_inline + 8 * i;
-                            if (lane == 0) *reinterpret_cast<unsigned long long*>(O.md_pool + off) = dec_word4((uint32_t)total_m, len);   // slot is 8-byte aligned; total_m <= EMIT_CAP
-                        } else {                                       // one token per D op, then the trailing run
-                            __syncwarp();
-                            int32_t* d_off = SM.run_g;                 // the run list is no longer needed
-                            int tlen = 0;
-                            for (int k0 = 0; k0 < nD; k0 += 32) {
-                                const int k = k0 + lane;
-                                const int t = k < nD ? ndigits((uint32_t)SM.d_run[k]) + 1 + SM.d_ct[k] : 0;
-                                int tot; const int to = tlen + warp_excl_scan(t, lane, tot);
-                                if (k < nD) d_off[k] = to;
-                                tlen += tot;
-                            }
-                            const int final_run = total_m - m_at_last_d, ndf = final_run > 0 ? ndigits((uint32_t)final_run) : 0;
-                            len = tlen + ndf;
-                            off = len <= 8 ? O.md_inline + 8 * i : pool_grab(O.md_cursor, O.md_cap, len, lane);
-                            __syncwarp();
-                            if (off >= 0) {
-                                uint8_t* out = O.md_pool + off;
-                                for (int k = lane; k < nD; k += 32) { const int nd = ndigits((uint32_t)SM.d_run[k]); write_dec(out + d_off[k], (uint32_t)SM.d_run[k], nd); out[d_off[k] + nd] = '^'; }
-                                for (int k = 0; k < nD; k++) {
-                                    uint8_t* bp = out + d_off[k] + ndigits((uint32_t)SM.d_run[k]) + 1; const int64_t g = gbase + SM.d_g[k]; const int ct = SM.d_ct[k];
-                                    for (int j = lane; j < ct; j += 32) bp[j] = genome_byte(P.G, g + j);
-                                }
-                                if (ndf > 0 && lane == 0) write_dec(out + tlen, (uint32_t)final_run, ndf);
-                            }
-                        }
-                        done = true;
-                    }
-                }
-            }
-            if (!done) {                                               // a difference to the genome, a literal run, the contig end,
-                if (lane == 0) O.exact_list[atomicAdd(O.exact_count, 1u)] = (int32_t)i;   // a long read: k_nmmd_exact walks it
-            } else {
-                st = (st & ~(uint32_t)TC_ST_NMMD_NONE) | TC_ST_NMMD_DEVICE;
-                if (lane == 0) { O.nm[i] = nm + nm_extra; O.md_off[i] = off < 0 ? 0 : off; O.md_len[i] = off < 0 ? 0 : len; W.status[i] = st; }
-            }
-        } else if (st & TC_ST_NMMD_DEVICE) {                           // generated at init and never refreshed
-            const int len = W.md_init_len[i];
-            const int64_t off = pool_grab(O.md_cursor, O.md_cap, len, lane);
-            if (off >= 0) { const uint8_t* s = W.md_init_pool + W.md_init_off[i]; for (int j = lane; j < len; j += 32) O.md_pool[off + j] = s[j]; }
-            if (lane == 0) { O.nm[i] = W.nm_init[i]; O.md_off[i] = off < 0 ? 0 : off; O.md_len[i] = off < 0 ? 0 : len; }
-        } else if (lane == 0) { O.nm[i] = 0; O.md_off[i] = 0; O.md_len[i] = 0; }
-        __syncwarp();
-        pw = pw_next;
-    }
-}
-
-// getNMandMDFlags (tr.py:280-342) for the reads k_emit could not settle with its clean-read check:
-// the token-emitting walk over the final SEQ and CIGAR (both already in the output arrays).
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_nmmd_exact(Params P, OutDev O) {
-    __shared__ uint32_t lut[256];
-    for (int t = threadIdx.x; t < 256; t += blockDim.x) {
-        const uint32_t acgt = 0x54474341u;
-        lut[t] = ((acgt >> (8 * (t & 3))) & 255u) | (((acgt >> (8 * ((t >> 2) & 3))) & 255u) << 8) |
-                 (((acgt >> (8 * ((t >> 4) & 3))) & 255u) << 16) | (((acgt >> (8 * ((t >> 6) & 3))) & 255u) << 24);
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int64_t nw = (int64_t)gridDim.x * WARPS_PER_BLOCK, nl = (int64_t)*O.exact_count;
-    for (int64_t t = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); t < nl; t += nw) {
-        const int64_t i = O.exact_list[t];
-        const int32_t* w = P.W.plan[i].w;
-        const int64_t o_seq = ((int64_t)w[EP_OSEQ_HI] << 32) | (uint32_t)w[EP_OSEQ_LO], o_cig = ((int64_t)w[EP_OCIG_HI] << 32) | (uint32_t)w[EP_OCIG_LO];
-        CigSrc cs; cs.packed = 0; cs.op = O.cig_op + o_cig; cs.len = O.cig_len + o_cig; cs.n = w[EP_NCIG];
-        int nm, len; int64_t off; bool none;
-        nmmd_to_pool<true>(P.G, O.seq + o_seq, lut, cs, w[EP_CHROM], (int64_t)w[EP_POS], lane, O.md_cursor, O.md_cap, O.md_pool, O.md_inline + 8 * i, nm, len, off, none);
-        uint32_t st = ((uint32_t)w[EP_STATUS] & ~(uint32_t)TC_ST_NMMD_NONE) | TC_ST_NMMD_DEVICE;
-        if (none) st |= TC_ST_NMMD_NONE;
-        if (lane == 0) { O.nm[i] = nm + w[EP_NMEXTRA]; O.md_off[i] = off < 0 ? 0 : off; O.md_len[i] = off < 0 ? 0 : len; P.W.status[i] = st; }
-    }
-}
+#include "tc_emit.cuh"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_); return TC_E_CUDA; } } while (0)
 
