@@ -43,6 +43,14 @@ def test_reads_longer_than_the_shared_memory_stage(engine):
     pc.check_generated(engine, 1202, n_reads=150, err=0.12, shift_frac=0.5)
 
 
+def test_tiny_reads_and_heavy_errors(engine):
+    """Reads of a few dozen bases (every row alignment of the packed / unpacked SEQ buffers, chunks that hold
+    several M runs) and reads with 15 % errors (many slices, deletion tokens in the clean-read MD)."""
+    pc.check_generated(engine, 5001, n_reads=300, exon_len=(12, 40), err=0.05)
+    pc.check_generated(engine, 5002, n_reads=300, exon_len=(12, 25), err=0.10, shift_frac=0.5)
+    pc.check_generated(engine, 5003, n_reads=60, exon_len=(200, 900), err=0.15)
+
+
 def test_tagless_input_at_scale(engine):
     """No NM/MD/jM/jI tags at all: NM/MD are bootstrapped on the device for every read (tr.py:47-48)."""
     pc.check_generated(engine, 1203, n_reads=400, tagless_frac=1.0)
