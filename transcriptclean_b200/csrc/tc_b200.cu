@@ -101,7 +101,10 @@ TC_HD void small_copies_read(const Params& P, const OutDev& O, int64_t i, int dr
 #include "tc_nmmd.cuh"
 
 __global__ void k_measure(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) measure_read(P, i); }
-__global__ void __launch_bounds__(128, 8) k_plan(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) plan_read(P, i); }
+#ifndef TC_PLAN_BLOCKS
+#define TC_PLAN_BLOCKS 4      // registers over occupancy: 8 blocks (62 registers, spills) was 7 % slower
+#endif
+__global__ void __launch_bounds__(128, TC_PLAN_BLOCKS) k_plan(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) plan_read(P, i); }
 #include "tc_junction.cuh"
 
 __global__ void k_sizes(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) sizes_read(P, i); }

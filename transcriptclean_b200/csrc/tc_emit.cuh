@@ -65,7 +65,10 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 //      memory with cp.async (all loads in flight at once) and verifies 16 bases per lane against
 //      the staged SEQ; a read that verifies clean needs no token (MD = total match length).
 //      Anything else (a difference, a D op, a literal run, the contig end) takes warp_nmmd.
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_emit(Params P, OutDev O, int dry, int64_t seq_lo, int64_t seq_hi) {
+#ifndef TC_EMIT_BLOCKS
+#define TC_EMIT_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_EMIT_BLOCKS) k_emit(Params P, OutDev O, int dry, int64_t seq_lo, int64_t seq_hi) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw);             // 4 bases (8 bits of the 2-bit plane) -> 4 ASCII bytes
     EmitSmem& SM = reinterpret_cast<EmitSmem*>(smem_raw + 1024)[threadIdx.x >> 5];

@@ -3,7 +3,10 @@
 #pragma once
 
 // junction objects for every read; reads that need cleanNoncanonical are appended to `list`
-__global__ void __launch_bounds__(128, 8) k_jn_init(Params P, int32_t* list, unsigned* count) {
+#ifndef TC_JNINIT_BLOCKS
+#define TC_JNINIT_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(128, TC_JNINIT_BLOCKS) k_jn_init(Params P, int32_t* list, unsigned* count) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P.B.n && junction_init_read(P, i)) list[atomicAdd(count, 1u)] = (int32_t)i;
 }
@@ -317,7 +320,10 @@ __device__ void junction_fix_warp(const Params& P, int64_t i, int lane) {
     if (lane == 0) W.status[i] = st;
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_jn_fix(Params P, const int32_t* list, const unsigned* count) {
+#ifndef TC_JNFIX_BLOCKS
+#define TC_JNFIX_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_JNFIX_BLOCKS) k_jn_fix(Params P, const int32_t* list, const unsigned* count) {
     const int lane = threadIdx.x & 31;
     const int64_t nw = (int64_t)gridDim.x * WARPS_PER_BLOCK, nl = (int64_t)*count;
     for (int64_t t = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); t < nl; t += nw) junction_fix_warp(P, list[t], lane);

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libtc_b200.so")
+LIB_PATH = os.environ.get("TC_B200_LIB") or os.path.join(_HERE, "csrc", "libtc_b200.so")   # (TC_B200_LIB: tuning builds)
 
 EXPORTS = ["tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_set_options", "tc_ctx_stream",
            "tc_ctx_load_genome", "tc_ctx_load_junctions", "tc_ctx_load_variants", "tc_correct_batch",
