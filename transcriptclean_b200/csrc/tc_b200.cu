@@ -672,7 +672,10 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
     S.tot_seq = S.tot_cig = S.tot_te = S.tot_jn = 0; S.md_used = 0;
     if (n == 0) { S.ran = true; S.ran_dry = dry != 0; return TC_OK; }
 #ifndef TC_HOSTSIM
-    const int TPB = 128; const int gb = (int)((n + TPB - 1) / TPB);
+#ifndef TC_TPB
+#define TC_TPB 128
+#endif
+    const int TPB = TC_TPB; const int gb = (int)((n + TPB - 1) / TPB);
     int nsm = 148; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
     int64_t wb = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; int gw = (int)(wb < (int64_t)nsm * 8 ? wb : (int64_t)nsm * 8);
     if (timed) CK(cudaEventRecord(ctx->ev[2], st));

@@ -6,7 +6,10 @@
 // jM / jI copies, all from the read's 128-byte plan row.  A light kernel of its own (no shared memory,
 // few registers, 48 warps of an SM resident): these phases are latency, not bytes, and inside
 // k_emit they held its 30 resident warps up for a fifth of its time.
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 6) k_small(Params P, OutDev O, int dry) {
+#ifndef TC_SMALL_BLOCKS
+#define TC_SMALL_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_SMALL_BLOCKS) k_small(Params P, OutDev O, int dry) {
     const int lane = threadIdx.x & 31; const unsigned lt = (1u << lane) - 1u;
     const BatchDev& B = P.B; const WorkDev& W = P.W;
     const int64_t nw = (int64_t)gridDim.x * WARPS_PER_BLOCK;
@@ -57,16 +60,16 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // (the batch's SEQ buffer on the device, padded).
 //   1. plan row (128 B, one word per lane) -> everything about the read; the next read's row,
 //      segment list and SEQ lines are prefetched into L2 meanwhile
-//   2. TE rows back into stage order (ballot partition), CIGAR and jM/jI copies
+//   2. (TE rows, CIGAR and jM / jI are copied by k_small above)
 //   3. SEQ: built in shared memory - (A) segment list -> slice table, (B) 16-byte chunks gathered
 //      from the input SEQ with the shift in force, (C) fix-ups after slice starts, (D) genome
 //      slices byte-exact, (E) one coalesced 16-byte-vector store
-//   4. NM/MD (getNMandMDFlags): tier 1 stages the 2-bit genome words of every M run in shared
-//      memory with cp.async (all loads in flight at once) and verifies 16 bases per lane against
-//      the staged SEQ; a read that verifies clean needs no token (MD = total match length).
-//      Anything else (a difference, a D op, a literal run, the contig end) takes warp_nmmd.
+//   4. NM/MD (getNMandMDFlags), clean-read check: a packed scan over the CIGAR gives the M runs; the
+//      staged SEQ is compared with the 2-bit genome words in aligned 16-byte chunks.  A read that
+//      verifies clean needs no token walk (MD = match lengths + the deletion tokens of the CIGAR);
+//      anything else (a difference, a literal run, the contig end, a long read) is listed for k_nmmd_exact.
 #ifndef TC_EMIT_BLOCKS
-#define TC_EMIT_BLOCKS 4
+#define TC_EMIT_BLOCKS (32 / WARPS_PER_BLOCK)
 #endif
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_EMIT_BLOCKS) k_emit(Params P, OutDev O, int dry, int64_t seq_lo, int64_t seq_hi) {
     extern __shared__ __align__(16) uint8_t smem_raw[];

@@ -321,7 +321,7 @@ __device__ void junction_fix_warp(const Params& P, int64_t i, int lane) {
 }
 
 #ifndef TC_JNFIX_BLOCKS
-#define TC_JNFIX_BLOCKS 4
+#define TC_JNFIX_BLOCKS (32 / WARPS_PER_BLOCK)
 #endif
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_JNFIX_BLOCKS) k_jn_fix(Params P, const int32_t* list, const unsigned* count) {
     const int lane = threadIdx.x & 31;

@@ -6,7 +6,9 @@
 // fields of a read's plan row (one word per lane, `pw`)
 #define PF(k) __shfl_sync(FULL, pw, (k))
 #define PF64(k) ((int64_t)(((u64)(uint32_t)PF((k) + 1) << 32) | (u64)(uint32_t)PF(k)))
+#ifndef WARPS_PER_BLOCK
 #define WARPS_PER_BLOCK 8
+#endif
 #define EMIT_CAP 4096            // reads whose new SEQ fits are staged in shared memory
 #define EMIT_MAXBP 192
 #define EMIT_MAXGI 192
