@@ -944,22 +944,26 @@ static int run_all(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out, int dr
         ctx->tm.kernels_ms = ctx->tm.k_nmmd_init_ms = ctx->tm.k_measure_ms = ctx->tm.k_plan_ms = ctx->tm.k_junction_ms = ctx->tm.k_emit_ms = 0.f;
         ctx->n = n; ctx->ran = false;
         if (check_packed(ctx, in)) return TC_E_ARG;
-        const int64_t nchunk = (n + CH - 1) / CH;
+        // chunk bounds: the first two chunks are a quarter and a half of the rest, so that the download
+        // stream (the bottleneck) starts early; the tail chunk is whatever remains
+        std::vector<int64_t> cut(1, 0);
+        for (int64_t a = 0, k = 0; a < n; k++) { const int64_t sz = k == 0 ? (CH + 3) / 4 : k == 1 ? (CH + 1) / 2 : CH; a = a + sz < n ? a + sz : n; cut.push_back(a); }
+        const int64_t nchunk = (int64_t)cut.size() - 1;
         int64_t bs = 0, bc = 0, bt = 0, bj = 0, bm = 0;
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));
         const bool trace = getenv("TC_PIPE_TRACE") != nullptr;        // per-chunk stream timestamps on stderr (debugging aid)
         std::vector<cudaEvent_t> tev;
         auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
         mark(ctx->s_in);
-        if (slot_upload(ctx, ctx->slot[0], in, 0, CH < n ? CH : n, ctx->s_in)) return TC_E_CUDA;
+        if (slot_upload(ctx, ctx->slot[0], in, 0, cut[1], ctx->s_in)) return TC_E_CUDA;
         CK(cudaEventRecord(ctx->slot[0].ev_in, ctx->s_in));
         mark(ctx->s_in);
         for (int64_t c = 0; c < nchunk; c++) {
             Slot& S = ctx->slot[c & 1];
-            const int64_t r0 = c * CH;
+            const int64_t r0 = cut[(size_t)c];
             if (c + 1 < nchunk) {                                   // next upload: its slot's kernels (chunk c-1) are done
                 Slot& N = ctx->slot[(c + 1) & 1];
-                const int64_t a = (c + 1) * CH, b = a + CH < n ? a + CH : n;
+                const int64_t a = cut[(size_t)c + 1], b = cut[(size_t)c + 2];
                 mark(ctx->s_in);
                 if (slot_upload(ctx, N, in, a, b, ctx->s_in)) return TC_E_CUDA;
                 CK(cudaEventRecord(N.ev_in, ctx->s_in));
