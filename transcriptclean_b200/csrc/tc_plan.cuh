@@ -401,9 +401,15 @@ struct Emit {                 // newCIGAR / newSeq / MVal bookkeeping (endMatch,
 };
 
 TC_HD void te_put(tc_te* te, int& n, int type, int32_t a, int32_t b, int32_t size, int status, int reason) {
-    u64* p = reinterpret_cast<u64*>(te + n);             // the TE area of the workspace is 8-byte aligned
-    p[0] = (u64)(uint32_t)a | ((u64)(uint32_t)b << 32);
-    p[1] = (u64)(uint32_t)size | ((u64)(uint32_t)(type & 255) << 32) | ((u64)(uint32_t)(status & 255) << 40) | ((u64)(uint32_t)(reason & 255) << 48);
+    // The TE area of a read starts 3*(cig_cap + seg_cap) units into its workspace; cig_cap + seg_cap and every
+    // read's workspace size are even numbers of 8-byte units (measure_read), so a row is 16-byte aligned.
+    const u64 w0 = (u64)(uint32_t)a | ((u64)(uint32_t)b << 32);
+    const u64 w1 = (u64)(uint32_t)size | ((u64)(uint32_t)(type & 255) << 32) | ((u64)(uint32_t)(status & 255) << 40) | ((u64)(uint32_t)(reason & 255) << 48);
+#ifdef TC_HOSTSIM
+    u64* p = reinterpret_cast<u64*>(te + n); p[0] = w0; p[1] = w1;
+#else
+    *reinterpret_cast<ulonglong2*>(te + n) = make_ulonglong2(w0, w1);
+#endif
     n++;
 }
 
