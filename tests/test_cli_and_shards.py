@@ -131,3 +131,20 @@ def test_world_size_2_gloo_shards_concatenate_in_order():
     outs = [p.communicate(timeout=300)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "RANK0_OK" in outs[0]
+
+
+def test_genome_image_cache_round_trip():
+    """The packed genome image saved next to the FASTA loads back identical (planes, literal runs, contig table)
+    and is rebuilt when the FASTA is newer."""
+    import numpy as np
+    from transcriptclean_b200.genome import GenomeImage
+    case, d = _case_files(35, 10)
+    a = GenomeImage.from_fasta_cached(d + "/g.fa")
+    assert os.path.exists(d + "/g.fa.tcb200.npz")
+    b = GenomeImage.from_fasta_cached(d + "/g.fa")          # from the image
+    assert a.names == b.names and np.array_equal(a.chrom_len, b.chrom_len) and np.array_equal(a.chrom_off, b.chrom_off)
+    assert np.array_equal(a.bases2, b.bases2) and np.array_equal(a.lower1, b.lower1)
+    assert all(np.array_equal(x, y) for x, y in zip(a.exceptions(), b.exceptions()))
+    os.utime(d + "/g.fa.tcb200.npz", (1, 1))                # stale image: rebuilt
+    c = GenomeImage.from_fasta_cached(d + "/g.fa")
+    assert np.array_equal(a.bases2, c.bases2) and os.path.getmtime(d + "/g.fa.tcb200.npz") > 1

@@ -163,7 +163,7 @@ def run(options, engines=None):
         chroms |= E.sam_rnames(lib, blk)
         header += E.sam_header_lines(lib, blk)
     print("Reading genome ..............................")
-    genome = GenomeImage.from_fasta(options.refGenome)
+    genome = GenomeImage.from_fasta_cached(options.refGenome)
     if engines is None:
         n = max(1, min(int(options.n_threads), max(1, n_gpus_available())))
         engines = [E.Engine(d) for d in range(n)]
