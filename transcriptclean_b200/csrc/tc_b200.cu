@@ -42,13 +42,7 @@ TC_HD int ndigits(uint32_t v) {
     return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 : v < 10000000u ? 7 :
            v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
 }
-// decimal digits of v (nd of them, nd <= 8) packed little-endian into one 64-bit word
-TC_HD unsigned long long dec_word(uint32_t v, int nd) {
-    unsigned long long w = 0;
-    for (int k = nd - 1; k >= 0; k--) { w |= (unsigned long long)('0' + v % 10) << (8 * k); v /= 10; }
-    return w;
-}
-// same for v < 10000 (nd <= 4), without a loop
+// decimal digits of v < 10000 (nd of them, nd <= 4) packed little-endian into one word, without a loop
 TC_HD unsigned long long dec_word4(uint32_t v, int nd) {
     const uint32_t d3 = v / 1000u, r3 = v - d3 * 1000u, d2 = r3 / 100u, r2 = r3 - d2 * 100u, d1 = r2 / 10u, d0 = r2 - d1 * 10u;
     const uint32_t w = (d3 | (d2 << 8) | (d1 << 16) | (d0 << 24)) + 0x30303030u;
