@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_EMIT_BLOCKS) k_emit(P
                     const int qtot = (int)((unsigned)qmtot >> 16), mtot = qmtot & 0xffff;
                     const bool isM = op == 'M' && ct > 0, isD = op == 'D';
                     const unsigned mM = __ballot_sync(FULL, isM), mD = __ballot_sync(FULL, isD);
-                    {   // MD token of a D op: <matches since the previous token>^<bases>
+                    if (mD) {   // MD token of a D op: <matches since the previous token>^<bases>   (uniform branch: most reads keep no D)
                         const unsigned prev = mD & lt;                  // nearest earlier D in this round, else the carried one
                         const int cand = __shfl_sync(FULL, mcur + ms, prev ? 31 - __clz(prev) : lane);
                         if (isD) {
@@ -267,8 +267,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_EMIT_BLOCKS) k_emit(P
                             if (idx < EMIT_MAXD) { SM.d_g[idx] = (int32_t)(gcur + gs); SM.d_ct[idx] = ct; SM.d_run[idx] = mcur + ms - (prev ? cand : m_at_last_d); }
                             else ovf = true;
                         }
-                        const int lastd = __shfl_sync(FULL, mcur + ms, mD ? 31 - __clz(mD) : 0);
-                        if (mD) m_at_last_d = lastd;
+                        m_at_last_d = __shfl_sync(FULL, mcur + ms, 31 - __clz(mD));
                     }
                     nD += __popc(mD);
                     ibases += op == 'I' ? ct : 0; dbases += isD ? ct : 0;
