@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--text-sample", type=int, default=100000, help="reads for the SAM-text path measurement (0 = skip)")
     ap.add_argument("--resident-only", action="store_true", help="profiling aid: only the device-resident steps (no pipelined e2e calls), so that a "
                     "launch list holds exactly the kernels of the timed region")
+    ap.add_argument("--no-dry", action="store_true", help="skip the --dryRun measurement")
     ap.add_argument("--seq8", action="store_true", help="send / receive SEQ as ASCII instead of the 4-bit form")
     ap.add_argument("--debug-mask", type=int, default=0, help="profiling aid: skip phases of k_emit (results invalid)")
     args = ap.parse_args()
@@ -268,10 +269,29 @@ def main():
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop()
 
-    tm = torch.tensor([ms_run, ms_e2e], dtype=torch.float64, device="cuda")
+    # ---- --dryRun (dryRun(), TC.py:1615-1678: the positional inventory of mismatches / indels) on the same batch
+    ms_dry = ms_dry_e2e = 0.0
+    if not args.no_dry and not args.resident_only:
+        dsteps = max(1, min(steps, 5))
+        eng._check(eng._lib.tc_batch_upload(eng._ctx, C.byref(b)), "upload")
+        for _ in range(2):
+            eng.run(dry=True)
+        barrier()
+        g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        g0.record(stream)
+        for _ in range(dsteps):
+            eng.run(dry=True)
+        g1.record(stream)
+        for _ in range(dsteps):
+            eng.raw_dryrun(b)
+        g2.record(stream)
+        barrier()
+        ms_dry, ms_dry_e2e = g0.elapsed_time(g1) / dsteps, g1.elapsed_time(g2) / dsteps
+
+    tm = torch.tensor([ms_run, ms_e2e, ms_dry, ms_dry_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms_run, ms_e2e = float(tm[0]), float(tm[1])
+    ms_run, ms_e2e, ms_dry, ms_dry_e2e = (float(x) for x in tm)
 
     # ---- algorithmic bytes of the dominant kernel (DESIGN.md "Kernels and rooflines")
     res = E.BatchResult(out, False, eng.alphabet)
@@ -318,6 +338,10 @@ def main():
                      "algorithmic_bytes_per_launch": dom_bytes},
         "clocks": clocks,
     }
+    if ms_dry > 0:
+        line["dry_run"] = {"value": args.reads * world / (ms_dry * 1e-3), "e2e": args.reads * world / (ms_dry_e2e * 1e-3), "unit": "reads/s",
+                           "ms_per_step": ms_dry, "e2e_ms_per_step": ms_dry_e2e,
+                           "note": "--dryRun inventory (tc_dryrun_batch) of the same batch: device-resident and through the ABI with host buffers"}
     if world == 1 and rank == 0 and args.text_sample > 0:
         # SAM text in -> four output texts (C++ host parse / render + GPU), in memory
         from transcriptclean_b200 import api

@@ -51,6 +51,11 @@ def test_tiny_reads_and_heavy_errors(engine):
     pc.check_generated(engine, 5003, n_reads=60, exon_len=(200, 900), err=0.15)
 
 
+def test_fully_tagged_input(engine):
+    """Every read carries NM and MD: the dry run then does not upload the SEQ column at all."""
+    pc.check_generated(engine, 1204, n_reads=300, tagless_frac=0.0)
+
+
 def test_tagless_input_at_scale(engine):
     """No NM/MD/jM/jI tags at all: NM/MD are bootstrapped on the device for every read (tr.py:47-48)."""
     pc.check_generated(engine, 1203, n_reads=400, tagless_frac=1.0)

@@ -34,3 +34,8 @@ def test_generated_vs_oracle(engine, seed):
 
 def test_seq_forms_agree(engine):
     assert sum(bool(pc.check_seq_forms(engine, seed)) for seed in (231, 232, 1232)) >= 1
+
+
+def test_fully_tagged_input(engine):
+    """Every read carries NM and MD: the dry run then does not upload the SEQ column at all."""
+    pc.check_generated(engine, 1204, n_reads=200, tagless_frac=0.0)

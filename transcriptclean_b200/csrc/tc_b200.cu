@@ -230,6 +230,7 @@ struct tc_ctx {
     uint8_t alphabet[16] = {'A', 'C', 'G', 'T', 'N', 'a', 'c', 'g', 't', 'n', 0, 0, 0, 0, 0, 0}; int n_alpha = 10;   // 4-bit SEQ codes
     bool genome_byte[256] = {};     // bytes the loaded genome can put into a read
     bool packed = false;            // the current batch came with 4-bit SEQ (results go back packed)
+    bool skip_seq = false;          // dry run over reads that all carry NM and MD: the SEQ column is never read, so it is not uploaded
     // pinned host outputs (whole batch)
     HostBuf h_status, h_counters, h_nm, h_seq_off, h_seq, h_cig_off, h_cig_op, h_cig_len, h_md_off, h_md_len, h_md,
         h_jn_off, h_jm, h_ji, h_te_off, h_te, h_seq_len;
@@ -556,7 +557,8 @@ static int slot_upload(tc_ctx* ctx, Slot& S, const tc_batch_in* in, int64_t r0, 
     if (be_h2d(ctx, st, S.b_flag, 0, in->flag + r0, (size_t)n * 4) || be_h2d(ctx, st, S.b_chrom, 0, in->chrom + r0, (size_t)n * 4) ||
         be_h2d(ctx, st, S.b_pos, 0, in->pos + r0, (size_t)n * 4) || be_h2d(ctx, st, S.b_tags, 0, in->tags + r0, (size_t)n) ||
         be_h2d(ctx, st, S.b_seq_off, 0, n ? in->seq_off + r0 : zero_off, (size_t)(n + 1) * 8) ||
-        (in->seq_poff ? seq_upload_packed(ctx, S, in, r0, r1, d0, st) : be_h2d(ctx, st, S.b_seq, d0, n ? in->seq + s0 : nullptr, (size_t)S.n_seq, 256)) ||
+        (ctx->skip_seq ? be_h2d(ctx, st, S.b_seq, d0, nullptr, 0, (size_t)S.n_seq + 256)
+                       : in->seq_poff ? seq_upload_packed(ctx, S, in, r0, r1, d0, st) : be_h2d(ctx, st, S.b_seq, d0, n ? in->seq + s0 : nullptr, (size_t)S.n_seq, 256)) ||
         be_h2d(ctx, st, S.b_cig_off, 0, n ? in->cig_off + r0 : zero_off, (size_t)(n + 1) * 8) ||
         be_h2d(ctx, st, S.b_cig_op, 0, n ? in->cig_op + c0 : nullptr, (size_t)S.n_cig) ||
         be_h2d(ctx, st, S.b_cig_len, 0, n ? in->cig_len + c0 : nullptr, (size_t)S.n_cig * 4) ||
@@ -930,6 +932,13 @@ static int run_all(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out, int dr
     if (!ctx || !in || !out || in->n_reads < 0) return TC_E_ARG;
     if (!ctx->have_genome) { ctx->err = "load a genome first"; return TC_E_STATE; }
     const int64_t n = in->n_reads;
+    // dryRun() only reads SEQ to bootstrap NM/MD (tr.py:47-48); when every primary read carries both tags the
+    // column - four fifths of the upload - stays on the host
+    bool all_tagged = dry != 0;
+    for (int64_t i = 0; all_tagged && i < n; i++)
+        if (!(in->chrom[i] < 0 || in->flag[i] == 4 || in->flag[i] > 16) && (in->tags[i] & (TAG_NM | TAG_MD)) != (TAG_NM | TAG_MD)) all_tagged = false;   // (read_class == 0)
+    struct SkipGuard { tc_ctx* c; ~SkipGuard() { c->skip_seq = false; } } guard{ctx};
+    ctx->skip_seq = all_tagged;
 #ifndef TC_HOSTSIM
     const int64_t CH = ctx->chunk_reads;
     if (CH > 0 && n > CH + CH / 2) {
