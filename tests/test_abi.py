@@ -42,3 +42,21 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no CPU fallback", ""), f
                 assert "hostsim" not in src.lower() or f in ("tc_b200.cu", "tc_plan.cuh"), f
+
+
+def test_header_is_plain_c():
+    """include/tc_b200.h compiles as C99 (what a cgo / JNI / ctypes-free C consumer would include) and the
+    record layouts are the ones engine.py mirrors."""
+    import subprocess
+    import tempfile
+    from transcriptclean_b200 import engine
+    src = ('#include "tc_b200.h"\n#include <stdio.h>\n'
+           'int main(void){ printf("%zu %zu %zu %zu %zu\\n", sizeof(tc_te), sizeof(tc_batch_in), sizeof(tc_batch_out), '
+           'sizeof(tc_options), sizeof(tc_timing)); return 0; }\n')
+    d = tempfile.mkdtemp()
+    open(d + "/t.c", "w").write(src)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           "-o", d + "/t", d + "/t.c"])
+    sizes = [int(x) for x in subprocess.check_output([d + "/t"]).split()]
+    assert sizes == [engine.TE_DTYPE.itemsize, ctypes.sizeof(engine._BatchIn), ctypes.sizeof(engine._BatchOut),
+                     ctypes.sizeof(engine._Options), ctypes.sizeof(engine.Timing)]
