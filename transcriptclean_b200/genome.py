@@ -198,5 +198,33 @@ class GenomeImage:
     def keys(self):
         return list(self.names)
 
+    def get_seq(self, chrom, start, end):
+        """pyfaidx `get_seq(chrom, start, end).seq` from the packed image: 1-based inclusive, case and literal
+        (non-ACGT) bases preserved, silently truncated past the contig end; start < 1 or an unknown contig raise."""
+        import bisect
+        if chrom not in self.index:
+            raise KeyError("Requested rname %s does not exist!" % chrom)
+        if start < 1:
+            raise IndexError("Requested start coordinate must be greater than 0.")
+        c = self.index[chrom]
+        end = min(int(end), int(self.chrom_len[c]))
+        if end < start:
+            return ""
+        if getattr(self, "_exc_sorted_n", -1) != len(self._exc):
+            self._exc_sorted = sorted(self._exc)
+            self._exc_starts = [e[0] for e in self._exc_sorted]
+            self._exc_sorted_n = len(self._exc)
+        off = int(self.chrom_off[c]) - 1
+        out = bytearray()
+        for p in range(off + start, off + end + 1):
+            k = bisect.bisect_right(self._exc_starts, p) - 1
+            if k >= 0 and p < self._exc_sorted[k][1]:
+                out.append(self._exc_sorted[k][2])
+                continue
+            code = (int(self.bases2[p >> 4]) >> ((p & 15) * 2)) & 3
+            low = (int(self.lower1[p >> 5]) >> (p & 31)) & 1
+            out.append(b"ACGT"[code] | (low << 5))
+        return out.decode("ascii")
+
     def nbytes(self):
         return self.bases2.nbytes + self.lower1.nbytes
