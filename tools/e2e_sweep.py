@@ -9,7 +9,8 @@ from transcriptclean_b200.tables import build_sj_tables
 n = int(os.environ.get("N", "1000000"))
 w = Workload(seed=20261019, chrom_len=248956422, n_genes=3000)
 sj = bench.write_sj(w)
-cols, nm = w.reads("pacbio", n, seed_offset=0)
+shape = os.environ.get("SHAPE", "pacbio")
+cols, nm = w.reads(shape, n, seed_offset=0)
 gi = w.genome_image()
 eng = E.Engine(0); eng.load_genome(gi); eng.load_junctions(build_sj_tables(sj, {w.chrom}, gi.index))
 if not os.environ.get("SEQ8"):
@@ -27,4 +28,6 @@ for ch in [int(x) for x in os.environ.get("CHUNKS", "32768,65536,131072,262144,5
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(3): eng.raw_correct(b)
     torch.cuda.synchronize(); res[ch] = (time.perf_counter() - t0) / 3 * 1e3
-print(json.dumps(res))
+t = eng.timing()
+print(json.dumps({"shape": shape, "reads": n, "ms_per_call": res, "reads_per_s": {k: n / (v * 1e-3) for k, v in res.items()},
+                  "exact_nmmd_reads": t["exact_nmmd_reads"], "h2d_bytes": t["h2d_bytes"], "d2h_bytes": t["d2h_bytes"]}))

@@ -697,7 +697,16 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
         init_cap = tot[0] + 1024; ctx->tm.md_pool_retries++;
     }
     if (timed) CK(cudaEventRecord(ctx->ev[4], st));
+#ifndef TC_HOSTSIM
+    if (S.w_ws.ensure((size_t)(tot[1] + 8) * 8) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->err = "out of device memory for the per-read workspace (" + std::to_string((tot[1] + 8) * 8 >> 20) + " MB for " + std::to_string(n) +
+                   " reads): run smaller batches, or tc_correct_batch / tc_dryrun_batch, which pipeline a batch in chunks (tc_ctx_set_pipeline)";
+        return TC_E_CUDA;
+    }
+#else
     CK(S.w_ws.ensure((size_t)(tot[1] + 8) * 8));
+#endif
     S.W.ws = (u64*)S.w_ws.p; P.W.ws = S.W.ws;
     if (dry) { k_dry<<<gb, TPB, 0, st>>>(P); ctx->tm.launches++; CK(cudaGetLastError()); if (timed) { CK(cudaEventRecord(ctx->ev[5], st)); CK(cudaEventRecord(ctx->ev[6], st)); } }
     else {
