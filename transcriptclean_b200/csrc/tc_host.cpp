@@ -75,7 +75,11 @@ struct tc_sam {
     std::vector<Span> line, f[9], cigar, tg[4];
     std::vector<int64_t> other_off; std::vector<Span> other;
     std::string header;
-    std::string out_sam, out_fa, out_log, out_te;
+    struct RawBuf {                  // output text: grown without initialising (a std::string resize would touch it twice)
+        char* p = nullptr; size_t cap = 0, n = 0;
+        void ensure(size_t want) { if (want > cap) { free(p); cap = want + want / 8 + 4096; p = (char*)malloc(cap); } }
+        ~RawBuf() { free(p); }
+    } out[4];                        // sam, fa, log, te
     // 4-bit SEQ form (tc_sam_pack_seq): packed rows, their offsets, the alphabet they index
     std::vector<uint8_t> seqp; std::vector<int64_t> seq_poff; uint8_t alphabet[16] = {0}; int n_alpha = 0; bool packed = false;
 };
@@ -331,7 +335,7 @@ void sam_release(tc_sam* S) {
     for (auto& v : S->f) v.clear();
     for (auto& v : S->tg) v.clear();
     S->other_off.clear(); S->other.clear(); S->header.clear(); S->seqp.clear(); S->seq_poff.clear();
-    S->out_sam.clear(); S->out_fa.clear(); S->out_log.clear(); S->out_te.clear();
+    for (auto& b : S->out) b.n = 0;
     std::lock_guard<std::mutex> g(g_pool_mu);
     if (g_pool.size() < 2) g_pool.push_back(S); else delete S;
 }
@@ -505,6 +509,7 @@ void tc_sam_batch(const tc_sam* S, tc_batch_in* b) {
 int tc_sam_render(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_t canon_only, int32_t dry, int32_t n_threads,
                   const char** sam, int64_t* sam_len, const char** fa, int64_t* fa_len, const char** lg, int64_t* lg_len,
                   const char** te, int64_t* te_len, char* err, int64_t err_cap) {
+    struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0); const double t_enter = ts0.tv_sec + 1e-9 * ts0.tv_nsec;
     if (!S || !R || R->n_reads != S->n) { set_err(err, err_cap, "tc_sam_render: result does not belong to this batch"); return TC_E_ARG; }
     for (int64_t i = 0; i < S->n; i++) {
         const uint32_t st = R->status[i];
@@ -530,15 +535,23 @@ int tc_sam_render(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_
     const bool tm = getenv("TC_HOST_TIMING") != nullptr;
     auto now = [] { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
     const double t_r = now();
-    auto join = [](std::string& dst, std::vector<std::string>& src) {
-        size_t tot = 0; for (auto& s : src) tot += s.size();
-        dst.clear(); dst.reserve(tot);
-        for (auto& s : src) dst.append(s);
-    };
-    join(S->out_sam, ps); join(S->out_fa, pf); join(S->out_log, pl); join(S->out_te, pt);
-    if (tm) fprintf(stderr, "tc_sam_render: threads done at +0, join %.3f s\n", now() - t_r);
-    *sam = S->out_sam.data(); *sam_len = (int64_t)S->out_sam.size(); *fa = S->out_fa.data(); *fa_len = (int64_t)S->out_fa.size();
-    *lg = S->out_log.data(); *lg_len = (int64_t)S->out_log.size(); *te = S->out_te.data(); *te_len = (int64_t)S->out_te.size();
+    // the parts of the T formatter threads -> one text each, copied by T threads again
+    std::vector<std::string>* parts[4] = {&ps, &pf, &pl, &pt};
+    std::vector<size_t> off((size_t)(4 * (T + 1)), 0);
+    for (int q = 0; q < 4; q++) {
+        for (int k = 0; k < T; k++) off[(size_t)(q * (T + 1) + k + 1)] = off[(size_t)(q * (T + 1) + k)] + (*parts[q])[(size_t)k].size();
+        S->out[q].ensure(off[(size_t)(q * (T + 1) + T)] + 1); S->out[q].n = off[(size_t)(q * (T + 1) + T)];
+    }
+    {
+        std::vector<std::thread> tj;
+        for (int k = 0; k < T; k++) tj.emplace_back([&, k] {
+            for (int q = 0; q < 4; q++) { const std::string& src = (*parts[q])[(size_t)k]; if (!src.empty()) memcpy(S->out[q].p + off[(size_t)(q * (T + 1) + k)], src.data(), src.size()); }
+        });
+        for (auto& t : tj) t.join();
+    }
+    if (tm) fprintf(stderr, "tc_sam_render: formatting %.3f s (%d threads), join %.3f s\n", t_r - t_enter, T, now() - t_r);
+    *sam = S->out[0].p; *sam_len = (int64_t)S->out[0].n; *fa = S->out[1].p; *fa_len = (int64_t)S->out[1].n;
+    *lg = S->out[2].p; *lg_len = (int64_t)S->out[2].n; *te = S->out[3].p; *te_len = (int64_t)S->out[3].n;
     return TC_OK;
 }
 
