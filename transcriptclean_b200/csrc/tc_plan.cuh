@@ -100,7 +100,8 @@ struct WorkDev {
     int32_t* seq_len_out;    // exact length of the new SEQ (o_seq offsets are padded to 16 bytes)
 };
 
-enum { MF_HAS_I = 1, MF_HAS_D = 2, MF_HAS_N = 4, MF_MD_ACGTN = 8, MF_MD_BYTES = 16 };   // MF_MD_BYTES: a count does not fit a token
+enum { MF_HAS_I = 1, MF_HAS_D = 2, MF_HAS_N = 4, MF_MD_ACGTN = 8, MF_MD_BYTES = 16, MF_JI_DONE = 32 };
+// MF_MD_BYTES: a count does not fit a token; MF_JI_DONE: plan_read already left the intron coordinates (compute_jI) in the junction records
 enum { TAG_NM = 1, TAG_MD = 2, TAG_JM = 4, TAG_JI = 8 };
 
 struct Params {
@@ -443,6 +444,7 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
     int64_t q = 0, g = B.pos[i];
     int nte = 0; u64 cnt_cor = 0, cnt_var = 0, cnt_big = 0;   // 21-bit fields: mismatches, insertions, deletions
     int32_t ins_removed = 0; bool sawD = false;
+    const bool want_ji = (mf & MF_HAS_N) && !(B.tags[i] & TAG_JI); int kN = 0;     // intron coordinates for reads without a jI tag
     // merge state (tr.py:171-211)
     // The next CIGAR op and the next MD token are fetched one step ahead, and a pre-split token
     // stays an undecoded word until the step that looks at it, so the loads have a whole step to land.
@@ -501,6 +503,7 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
         if (isM || isX || (isD && corrected)) E.match(ct);
         else if (isS || isNH || ((isI || isD) && !corrected)) E.op(op, ct);
         if (isM || isX || isS || isI) q += ct;
+        if (want_ji && op == 'N') { v.jn[kN * JN_STRIDE] = (int32_t)g; v.jn[kN * JN_STRIDE + 1] = (int32_t)(g + ct - 1); kN++; }   // compute_jI (tr.py:368-393) on the way
         if (isM || isX || isD || isNH) g += ct;
     }
 #undef TC_NEXT_CIGAR
@@ -523,6 +526,7 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
     // correctMismatches; insertion removal never refreshes, so NM keeps counting removed bases.
     if (indel && sawD) { W.refresh[i] = 1; W.nm_extra[i] = 0; }
     else if (stage1) { W.refresh[i] = 1; W.nm_extra[i] = ins_removed; }
+    if (want_ji) W.mflags[i] = mf | MF_JI_DONE;
     W.status[i] = st | TC_ST_CIGAR_REWRITTEN;
 }
 
@@ -734,7 +738,7 @@ TC_HD bool junction_init_read(const Params& P, int64_t i) {
         if (tags & TAG_JI) {
             const int32_t* ji = B.ji + B.ji_off[i];
             for (int k = 0; k < nj; k++) { J[k * JN_STRIDE] = ji[2 * k]; J[k * JN_STRIDE + 1] = ji[2 * k + 1]; }
-        } else {                                                      // compute_jI (tr.py:368-393)
+        } else if (!(W.mflags[i] & MF_JI_DONE)) {                     // compute_jI (tr.py:368-393), unless plan_read did it on its walk
             int64_t g = B.pos[i]; int k = 0;
             for (int64_t c = B.cig_off[i]; c < B.cig_off[i + 1]; c++) {
                 int op = B.cig_op[c]; int32_t ct = B.cig_len[c];
