@@ -39,3 +39,8 @@ def test_seq_forms_agree(engine):
 def test_fully_tagged_input(engine):
     """Every read carries NM and MD: the dry run then does not upload the SEQ column at all."""
     pc.check_generated(engine, 1204, n_reads=200, tagless_frac=0.0)
+
+
+def test_long_cigars(engine):
+    """15 % errors: CIGARs of well over 64 ops, where plan_read also leaves the intron coordinates."""
+    pc.check_generated(engine, 5003, n_reads=60, exon_len=(200, 900), err=0.15)

@@ -444,7 +444,9 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
     int64_t q = 0, g = B.pos[i];
     int nte = 0; u64 cnt_cor = 0, cnt_var = 0, cnt_big = 0;   // 21-bit fields: mismatches, insertions, deletions
     int32_t ins_removed = 0; bool sawD = false;
-    const bool want_ji = (mf & MF_HAS_N) && !(B.tags[i] & TAG_JI); int kN = 0;     // intron coordinates for reads without a jI tag
+    // intron coordinates for reads without a jI tag: computed on this walk when the CIGAR is long (k_jn_init would
+    // otherwise walk its ~150 ops again; for short CIGARs its own walk is cheaper than a fourth store stream here)
+    const bool want_ji = (mf & MF_HAS_N) && !(B.tags[i] & TAG_JI) && B.cig_off[i + 1] - B.cig_off[i] > 64; int kN = 0;
     // merge state (tr.py:171-211)
     // The next CIGAR op and the next MD token are fetched one step ahead, and a pre-split token
     // stays an undecoded word until the step that looks at it, so the loads have a whole step to land.
@@ -503,7 +505,14 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
         if (isM || isX || (isD && corrected)) E.match(ct);
         else if (isS || isNH || ((isI || isD) && !corrected)) E.op(op, ct);
         if (isM || isX || isS || isI) q += ct;
-        if (want_ji && op == 'N') { v.jn[kN * JN_STRIDE] = (int32_t)g; v.jn[kN * JN_STRIDE + 1] = (int32_t)(g + ct - 1); kN++; }   // compute_jI (tr.py:368-393) on the way
+        if (want_ji && op == 'N') {                                   // compute_jI (tr.py:368-393) on the way; one 8-byte store
+#ifdef TC_HOSTSIM
+            v.jn[kN * JN_STRIDE] = (int32_t)g; v.jn[kN * JN_STRIDE + 1] = (int32_t)(g + ct - 1);
+#else
+            *reinterpret_cast<int2*>(v.jn + kN * JN_STRIDE) = make_int2((int32_t)g, (int32_t)(g + ct - 1));
+#endif
+            kN++;
+        }
         if (isM || isX || isD || isNH) g += ct;
     }
 #undef TC_NEXT_CIGAR
