@@ -10,9 +10,16 @@ SJ table (tools/synth_gen.c; the real hg38 / GM12878 inputs are not shipped).  W
 rank corrects its own shard of the same shape (weak scaling, no data-path collective).
 
   value  device-resident throughput: inputs already in HBM, tc_batch_run() only
-  e2e    through the C ABI with host buffers: tc_correct_batch() = H2D + kernels + D2H
+  e2e    through the C ABI with pinned host buffers: tc_correct_batch() = H2D + kernels + D2H, pipelined in chunks;
+         the SEQ column travels as 4-bit codes (--seq8: ASCII)
   roofline  the dominant kernel's algorithmic bytes / its CUDA-event time vs measured HBM peak
-  cpu_baseline  the oracle port of the reference (oracle/tc_oracle.py) on a bounded sample
+            (traffic: DRAM bytes of that kernel from the committed ncu --set full capture)
+  dry_run   the --dryRun inventory (tc_dryrun_batch) of the same batch, device-resident and end to end
+  sam_text_path  SAM text in -> the four output texts (C++ host parse / render around the GPU), N=1 only
+  cpu_baseline  the oracle port of the reference (oracle/tc_oracle.py) on a bounded sample, one core
+  --impl reference  the same port on all host cores (the reference arm; the reference is pure Python
+                    and cannot travel to the GPU box)
+  --shape ont       BASELINE.json configs[3] shape;  --resident-only  profiling aid (see profiles/README.md)
 """
 import argparse
 import ctypes as C
