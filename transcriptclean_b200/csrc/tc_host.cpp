@@ -219,61 +219,73 @@ const char* const TE_TYPE[4] = {"Mismatch", "Insertion", "Deletion", "NC_SJ_boun
 const char* const TE_STATUS[2] = {"Corrected", "Uncorrected"};
 const char* const TE_REASON[6] = {"NA", "VariantMatch", "TooLarge", "TooFarFromAnnotJn", "Other", "DryRun"};
 
-inline void put_int(std::string& o, int64_t v) {
-    char b[24]; int n = 24; const bool neg = v < 0; uint64_t u = neg ? (uint64_t)(-v) : (uint64_t)v;
-    do { b[--n] = (char)('0' + u % 10); u /= 10; } while (u);
-    if (neg) b[--n] = '-';
-    o.append(b + n, (size_t)(24 - n));
-}
+// Text under construction.  The string is only storage (its size is the capacity in use); `n` is the length
+// written so far.  need(k) makes room for k more bytes once per record; the writers below do not check.
+struct Out {
+    std::string buf; size_t n = 0;
+    void clear() { n = 0; }
+    void need(size_t k) { if (n + k > buf.size()) buf.resize(std::max(buf.size() * 2, n + k + ((size_t)1 << 20))); }
+    void put(const char* p, size_t k) { memcpy(&buf[n], p, k); n += k; }
+    void ch(char c) { buf[n++] = c; }
+    void str(const char* z) { put(z, strlen(z)); }
+    void num(int64_t v) {
+        char b[24]; int k = 24; const bool neg = v < 0; uint64_t u = neg ? (uint64_t)(-v) : (uint64_t)v;
+        do { b[--k] = (char)('0' + u % 10); u /= 10; } while (u);
+        if (neg) b[--k] = '-';
+        put(b + k, (size_t)(24 - k));
+    }
+};
 
 struct Comp { uint8_t t[256]; Comp() { for (int k = 0; k < 256; k++) t[k] = (uint8_t)k; const char* a = "ACGTNacgtn*"; const char* b = "TGCANtgcan*"; for (int k = 0; a[k]; k++) t[(uint8_t)a[k]] = (uint8_t)b[k]; } };
 const Comp COMP;
 
 void render_range(const tc_sam* S, const tc_batch_out* R, int64_t a, int64_t b, bool primary_only, bool canon_only, bool dry,
-                  std::string& sam, std::string& fa, std::string& lg, std::string& te) {
+                  Out& sam, Out& fa, Out& lg, Out& te) {
     const char* T = S->text;
-    std::string row, seq, useq;
+    std::string useq;
     uint16_t lut16[256];
     for (int t = 0; t < 256; t++) lut16[t] = (uint16_t)(S->alphabet[t & 15] | (S->alphabet[t >> 4] << 8));
-    if (b > a && !dry) {
-        const size_t sb = (size_t)((R->seq_off[b] - R->seq_off[a]) + (b - a) * 400 + (R->cig_off[b] - R->cig_off[a]) * 6);
-        sam.reserve(sb); fa.reserve((size_t)(R->seq_off[b] - R->seq_off[a]) + (size_t)(b - a) * 64);
-    }
-    if (b > a) { lg.reserve((size_t)(b - a) * 80); te.reserve((size_t)(R->te_off[b] - R->te_off[a]) * 64 + 64); }
     for (int64_t i = a; i < b; i++) {
         const uint32_t st = R->status[i]; const int cls = (int)(st & TC_ST_CLASS_MASK);
+        const Span q = S->f[0][i], ch = S->f[2][i];
         // log row: TranscriptID, Mapping, ten counters ("NA" = -1)
-        lg.append(T + S->f[0][i].s, (size_t)S->f[0][i].n); lg.push_back('\t'); lg.append(CLASS_NAME[cls]);
-        for (int k = 0; k < 10; k++) { lg.push_back('\t'); const int32_t c = R->counters[10 * i + k]; if (c < 0) lg.append("NA"); else put_int(lg, c); }
-        lg.push_back('\n');
+        lg.need((size_t)q.n + 160);
+        lg.put(T + q.s, (size_t)q.n); lg.ch('\t'); lg.str(CLASS_NAME[cls]);
+        for (int k = 0; k < 10; k++) { lg.ch('\t'); const int32_t c = R->counters[10 * i + k]; if (c < 0) lg.put("NA", 2); else lg.num(c); }
+        lg.ch('\n');
         if (cls != 0) {
-            if (!dry && !primary_only && !canon_only) { sam.append(T + S->line[i].s, (size_t)S->line[i].n); sam.push_back('\n'); }
+            if (!dry && !primary_only && !canon_only) { sam.need((size_t)S->line[i].n + 1); sam.put(T + S->line[i].s, (size_t)S->line[i].n); sam.ch('\n'); }
             continue;
         }
-        for (int64_t k = R->te_off[i]; k < R->te_off[i + 1]; k++) {
+        const int64_t t0 = R->te_off[i], t1 = R->te_off[i + 1];
+        te.need((size_t)(t1 - t0) * ((size_t)q.n + (size_t)ch.n + 96));
+        for (int64_t k = t0; k < t1; k++) {
             const tc_te& r = R->te[k];
-            te.append(T + S->f[0][i].s, (size_t)S->f[0][i].n); te.push_back('\t');
-            te.append(T + S->f[2][i].s, (size_t)S->f[2][i].n); te.push_back('_'); put_int(te, r.a);
-            if (r.type != 0) { te.push_back('_'); put_int(te, r.b); }
-            te.push_back('\t'); te.append(TE_TYPE[r.type]); te.push_back('\t'); put_int(te, r.size); te.push_back('\t');
-            te.append(TE_STATUS[r.status]); te.push_back('\t'); te.append(TE_REASON[r.reason]); te.push_back('\n');
+            te.put(T + q.s, (size_t)q.n); te.ch('\t');
+            te.put(T + ch.s, (size_t)ch.n); te.ch('_'); te.num(r.a);
+            if (r.type != 0) { te.ch('_'); te.num(r.b); }
+            te.ch('\t'); te.str(TE_TYPE[r.type]); te.ch('\t'); te.num(r.size); te.ch('\t');
+            te.str(TE_STATUS[r.status]); te.ch('\t'); te.str(TE_REASON[r.reason]); te.ch('\n');
         }
         if (dry) continue;
         if (canon_only && !(st & (TC_ST_CANONICAL | TC_ST_ALL_ANNOT))) continue;
-        // ---- SAM line (printableSAM): empty fields are dropped, the line is stripped
-        row.clear();
-        auto add = [&](const char* p, int64_t n) { if (n > 0) { if (!row.empty()) row.push_back('\t'); row.append(p, (size_t)n); } };
+        // ---- SAM line (printableSAM): empty fields are dropped, the line is stripped.  Written in place.
+        const int32_t sl = R->seq_len[i];
+        const int64_t c0 = R->cig_off[i], c1 = R->cig_off[i + 1], j0 = R->jn_off[i], j1 = R->jn_off[i + 1];
+        sam.need((size_t)S->line[i].n + (size_t)sl + (size_t)(c1 - c0) * 12 + (size_t)R->md_len[i] + (size_t)(j1 - j0) * 40 + 128);
+        const size_t row0 = sam.n;
+        auto add = [&](const char* p, int64_t n) { if (n > 0) { if (sam.n > row0) sam.ch('\t'); sam.put(p, (size_t)n); } };
         auto add_span = [&](const Span& s) { add(T + s.s, s.n); };
-        auto add_num = [&](int64_t v) { if (!row.empty()) row.push_back('\t'); put_int(row, v); };
-        add_span(S->f[0][i]); add_num(S->flag[i]); add_span(S->f[2][i]); add_num(S->pos[i]); add_span(S->f[4][i]);
+        auto add_num = [&](int64_t v) { if (sam.n > row0) sam.ch('\t'); sam.num(v); };
+        add_span(q); add_num(S->flag[i]); add_span(ch); add_num(S->pos[i]); add_span(S->f[4][i]);
         if (st & TC_ST_CIGAR_REWRITTEN) {
-            if (R->cig_off[i + 1] > R->cig_off[i]) {
-                if (!row.empty()) row.push_back('\t');
-                for (int64_t k = R->cig_off[i]; k < R->cig_off[i + 1]; k++) { put_int(row, R->cig_len[k]); row.push_back((char)R->cig_op[k]); }
+            if (c1 > c0) {
+                if (sam.n > row0) sam.ch('\t');
+                for (int64_t k = c0; k < c1; k++) { sam.num(R->cig_len[k]); sam.ch((char)R->cig_op[k]); }
             }
         } else add_span(S->cigar[i]);
         add_span(S->f[6][i]); add_span(S->f[7][i]); add_span(S->f[8][i]);
-        const uint8_t* sq = R->seq + R->seq_off[i]; const int32_t sl = R->seq_len[i];
+        const uint8_t* sq = R->seq + R->seq_off[i];
         if (R->seq_bits == 4) {                                       // two bases per byte, row at seq_off / 2
             const uint8_t* pk = R->seq + R->seq_off[i] / 2;
             useq.resize((size_t)sl + 2);
@@ -285,38 +297,49 @@ void render_range(const tc_sam* S, const tc_batch_out* R, int64_t a, int64_t b, 
         add("*", 1);
         for (int64_t k = S->other_off[i]; k < S->other_off[i + 1]; k++) {
             // otherFields is one tab-joined field: dropped only when the whole join is empty
-            if (k == S->other_off[i]) { bool any = false; for (int64_t m = k; m < S->other_off[i + 1]; m++) any |= S->other[m].n > 0 || m > k; if (!any) break; if (!row.empty()) row.push_back('\t'); }
-            else row.push_back('\t');
-            row.append(T + S->other[k].s, (size_t)S->other[k].n);
+            if (k == S->other_off[i]) { bool any = false; for (int64_t m = k; m < S->other_off[i + 1]; m++) any |= S->other[m].n > 0 || m > k; if (!any) break; if (sam.n > row0) sam.ch('\t'); }
+            else sam.ch('\t');
+            sam.put(T + S->other[k].s, (size_t)S->other[k].n);
         }
         if (st & TC_ST_NMMD_DEVICE) {
             if (!(st & TC_ST_NMMD_NONE)) {
-                if (!row.empty()) row.push_back('\t');
-                row.append("NM:i:"); put_int(row, R->nm[i]); row.append("\tMD:Z:");
-                row.append((const char*)R->md + R->md_off[i], (size_t)R->md_len[i]);
+                if (sam.n > row0) sam.ch('\t');
+                sam.put("NM:i:", 5); sam.num(R->nm[i]); sam.put("\tMD:Z:", 6);
+                sam.put((const char*)R->md + R->md_off[i], (size_t)R->md_len[i]);
             }
         } else { add_span(S->tg[0][i]); add_span(S->tg[1][i]); }
-        const int64_t j0 = R->jn_off[i], j1 = R->jn_off[i + 1];
         if (st & TC_ST_JM_DEVICE) {
-            if (!row.empty()) row.push_back('\t');
-            row.append("jM:B:c");
-            if (j1 > j0) for (int64_t k = j0; k < j1; k++) { row.push_back(','); put_int(row, R->jm[k]); } else row.append(",-1");
+            if (sam.n > row0) sam.ch('\t');
+            sam.put("jM:B:c", 6);
+            if (j1 > j0) for (int64_t k = j0; k < j1; k++) { sam.ch(','); sam.num(R->jm[k]); } else sam.put(",-1", 3);
         } else add_span(S->tg[2][i]);
         if (st & TC_ST_JI_DEVICE) {
-            if (!row.empty()) row.push_back('\t');
-            row.append("jI:B:i");
-            if (j1 > j0) for (int64_t k = 2 * j0; k < 2 * j1; k++) { row.push_back(','); put_int(row, R->ji[k]); } else row.append(",-1");
+            if (sam.n > row0) sam.ch('\t');
+            sam.put("jI:B:i", 6);
+            if (j1 > j0) for (int64_t k = 2 * j0; k < 2 * j1; k++) { sam.ch(','); sam.num(R->ji[k]); } else sam.put(",-1", 3);
         } else add_span(S->tg[3][i]);
-        size_t x = 0, y = row.size();
-        while (x < y && is_ws(row[x])) x++;
-        while (y > x && is_ws(row[y - 1])) y--;
-        sam.append(row, x, y - x); sam.push_back('\n');
+        {   // strip
+            size_t x = row0, y = sam.n;
+            while (x < y && is_ws(sam.buf[x])) x++;
+            while (y > x && is_ws(sam.buf[y - 1])) y--;
+            if (x > row0) memmove(&sam.buf[row0], &sam.buf[x], y - x);
+            sam.n = row0 + (y - x);
+        }
+        sam.ch('\n');
         // ---- FASTA record (printableFa): reverse complement on the minus strand, 80 columns
-        fa.push_back('>'); fa.append(T + S->f[0][i].s, (size_t)S->f[0][i].n); fa.push_back('\n');
-        if (S->flag[i] == 16) { seq.resize((size_t)sl); for (int32_t k = 0; k < sl; k++) seq[(size_t)k] = (char)COMP.t[sq[sl - 1 - k]]; }
-        const char* sp = S->flag[i] == 16 ? seq.data() : (const char*)sq;
-        for (int32_t k = 0; k < sl; k += 80) { if (k) fa.push_back('\n'); fa.append(sp + k, (size_t)std::min(80, sl - k)); }
-        fa.push_back('\n');
+        fa.need((size_t)q.n + (size_t)sl + (size_t)sl / 80 + 8);
+        fa.ch('>'); fa.put(T + q.s, (size_t)q.n); fa.ch('\n');
+        if (S->flag[i] == 16) {
+            for (int32_t k = 0; k < sl; k += 80) {
+                if (k) fa.ch('\n');
+                const int32_t m = std::min(80, sl - k); char* d = &fa.buf[fa.n];
+                for (int32_t t = 0; t < m; t++) d[t] = (char)COMP.t[sq[sl - 1 - (k + t)]];
+                fa.n += (size_t)m;
+            }
+        } else {
+            for (int32_t k = 0; k < sl; k += 80) { if (k) fa.ch('\n'); fa.put((const char*)sq + k, (size_t)std::min(80, sl - k)); }
+        }
+        fa.ch('\n');
     }
 }
 
@@ -523,7 +546,7 @@ int tc_sam_render(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_
     }
     int T = n_threads < 1 ? 1 : n_threads;
     if (S->n < 4096) T = 1;
-    static thread_local std::vector<std::string> ps, pf, pl, pt;      // per calling thread, capacity kept between batches
+    static thread_local std::vector<Out> ps, pf, pl, pt;              // per calling thread, storage kept between batches
     for (auto* v : {&ps, &pf, &pl, &pt}) { if (v->size() < (size_t)T) v->resize((size_t)T); for (auto& x : *v) x.clear(); }
     std::vector<std::thread> th;
     for (int k = 0; k < T; k++) {
@@ -536,16 +559,16 @@ int tc_sam_render(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_
     auto now = [] { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
     const double t_r = now();
     // the parts of the T formatter threads -> one text each, copied by T threads again
-    std::vector<std::string>* parts[4] = {&ps, &pf, &pl, &pt};
+    std::vector<Out>* parts[4] = {&ps, &pf, &pl, &pt};
     std::vector<size_t> off((size_t)(4 * (T + 1)), 0);
     for (int q = 0; q < 4; q++) {
-        for (int k = 0; k < T; k++) off[(size_t)(q * (T + 1) + k + 1)] = off[(size_t)(q * (T + 1) + k)] + (*parts[q])[(size_t)k].size();
+        for (int k = 0; k < T; k++) off[(size_t)(q * (T + 1) + k + 1)] = off[(size_t)(q * (T + 1) + k)] + (*parts[q])[(size_t)k].n;
         S->out[q].ensure(off[(size_t)(q * (T + 1) + T)] + 1); S->out[q].n = off[(size_t)(q * (T + 1) + T)];
     }
     {
         std::vector<std::thread> tj;
         for (int k = 0; k < T; k++) tj.emplace_back([&, k] {
-            for (int q = 0; q < 4; q++) { const std::string& src = (*parts[q])[(size_t)k]; if (!src.empty()) memcpy(S->out[q].p + off[(size_t)(q * (T + 1) + k)], src.data(), src.size()); }
+            for (int q = 0; q < 4; q++) { const Out& src = (*parts[q])[(size_t)k]; if (src.n) memcpy(S->out[q].p + off[(size_t)(q * (T + 1) + k)], src.buf.data(), src.n); }
         });
         for (auto& t : tj) t.join();
     }
