@@ -101,7 +101,28 @@ _ORACLE = {}
 def _oracle_chunk(lines):
     oc, genome, sj = _ORACLE["ctx"]
     out = oc.correct_lines(lines, oc.Options(), genome, sj, None)
+    if _ORACLE.get("keep"):
+        _ORACLE["texts"] = out           # the parity check of the timed batch compares these with the GPU's texts
     return len(out["log"])
+
+
+def parity_check(w, gi, cols, nm, res, n_check, sj_path, texts=None):
+    """The GPU results of the first n_check reads of the TIMED batch, rendered to the four output texts,
+    against the oracle's texts for the same reads.  Returns None, or a description of the first difference."""
+    from transcriptclean_b200 import render, sam
+    lines = w.sam_lines(cols, nm, 0, n_check)
+    if texts is None:
+        oc, genome, sj = _ORACLE.get("ctx") or oracle_setup(w, sj_path)
+        texts = oc.correct_lines(lines, oc.Options(), genome, sj, None)
+    got = render.render_batch(sam.parse_lines(lines, gi), res, False, False)
+    for k in ("sam", "fa", "log", "te"):
+        if got[k] != texts[k]:
+            a, b = got[k].split("\n"), texts[k].split("\n")
+            for i, (x, y) in enumerate(zip(a, b)):
+                if x != y:
+                    return "%s line %d: got %r want %r" % (k, i, x[:300], y[:300])
+            return "%s: %d vs %d lines" % (k, len(a), len(b))
+    return None
 
 
 def oracle_rate(w, sj_path, lines, threads, steps=1, warmup=0):
@@ -184,6 +205,8 @@ def main():
     ap.add_argument("--no-dry", action="store_true", help="skip the --dryRun measurement")
     ap.add_argument("--seq8", action="store_true", help="send / receive SEQ as ASCII instead of the 4-bit form")
     ap.add_argument("--debug-mask", type=int, default=0, help="profiling aid: skip phases of k_emit (results invalid)")
+    ap.add_argument("--parity-reads", type=int, default=-1, help="reads of the timed batch whose texts are compared with the oracle's "
+                    "(default: --cpu-sample at N=1, 500 per rank at N>1; 0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -370,18 +393,37 @@ def main():
         line["sam_text_path"] = {"value": ns / (t1 - t0), "unit": "reads/s", "in_bytes": len(text),
                                  "out_bytes": sum(sizes.values()),
                                  "sample": "%d reads as SAM text -> clean SAM + FASTA + log + TE.log texts, host threads=%d" % (ns, min(32, os.cpu_count() or 1))}
+    texts, n_texts = None, 0
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         ns = min(args.cpu_sample, args.reads)
         lines = w.sam_lines(cols, nm, 0, ns)
+        _ORACLE["keep"] = True
         rate, sec = oracle_rate(w, sj_path, lines, 1)
+        texts, n_texts = _ORACLE.get("texts"), ns
         line["cpu_baseline"] = {"value": rate, "unit": "reads/s", "cores": 1, "kind": "port",
                                 "sample": "first %d reads of the same batch, 1 thread, oracle/tc_oracle.py with the "
                                           "reference's per-base genome walk (%.1f s)" % (ns, sec)}
+    # ---- parity of the TIMED batch: the texts of its first reads (every rank checks its own shard) against the oracle
+    n_par = args.parity_reads if args.parity_reads >= 0 else (min(args.cpu_sample, args.reads) if world == 1 else min(500, args.reads))
+    bad = None
+    if n_par > 0 and not args.debug_mask:
+        if texts is not None and n_texts != n_par:
+            texts = None
+        bad = parity_check(w, gi, cols, nm, res, n_par, sj_path, texts)
+        if bad:
+            sys.stderr.write("PARITY FAILURE on rank %d: %s\n" % (rank, bad))
+    flag = torch.tensor([1 if bad else 0, n_par if not args.debug_mask else 0], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.SUM)
+    line["parity_checked_reads"] = int(flag[1])
+    line["parity"] = "FAILED" if int(flag[0]) else ("ok: texts of the first %d reads of the timed batch per rank equal the oracle's" % n_par if n_par > 0 and not args.debug_mask else "not checked")
     if rank == 0:
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+    if int(flag[0]):
+        raise SystemExit(3)
 
 
 if __name__ == "__main__":

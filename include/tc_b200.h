@@ -54,7 +54,8 @@ enum {
     TC_ST_JI_DEVICE = 1u << 7,    /* jI must be rendered from ji[]; else input tag */
     TC_ST_CANONICAL = 1u << 8,    /* transcript.isCanonical */
     TC_ST_ALL_ANNOT = 1u << 9,    /* transcript.allJnsAnnotated */
-    TC_ST_ERR_INTRON = 1u << 10,  /* junction rescue drove an intron length <= 0 (unsupported) */
+    TC_ST_ERR_INTRON = 1u << 10,  /* informational: a junction rescue met the one text-CIGAR corner that is not modelled (a negative
+                                     intron behind an op other than M/S/I/D); that junction was left uncorrected ("Other") */
     TC_ST_ERR_MERGE = 1u << 11    /* dry run only: MD/CIGAR merge ran off a list (reference crashes) */
 };
 

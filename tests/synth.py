@@ -327,3 +327,64 @@ def _add_unpinned(rng, case):
         extra.append([chrom, i0 - 4, i1 - 4, col4] + r[4:])
         extra.append([chrom, i0 + 2, i1 - 2, other] + r[4:])
     case.sj_rows += extra
+
+
+def make_micro_intron_case(seed, n_reads=40):
+    """Reads whose junctions sit on introns of 1-10 bases next to annotated sites up to 9 bases away, so that the
+    rescue drives intron lengths to zero and below (tc_plan.cuh `intron_text_rules`).  The op in
+    front of the intron is an M, a D or an I, the op behind it an M, a D or an I.  Returns a Case (one contig,
+    no VCF); use with maxSJOffset 5 and 10, with and without the indel stage."""
+    rng = random.Random(seed)
+    length = 60000
+    gs = "".join(rng.choice(BASES) for _ in range(length))
+    case = Case()
+    case.genome = {"chr1": gs}
+    p = 8000
+    for r in range(n_reads):
+        strand = rng.choice("+-")
+        l1, l2 = rng.randrange(20, 60), rng.randrange(20, 60)
+        m = rng.randrange(1, 11)
+        pre, post = rng.choice("MMDI"), rng.choice("MMDI")
+        ops, seq, md = [], [], []
+        state = {"gp": p, "run": 0}
+
+        def match(n_):
+            ops.append(("M", n_)); seq.append(gs[state["gp"] - 1:state["gp"] - 1 + n_]); state["run"] += n_; state["gp"] += n_
+
+        def dele(n_):
+            ops.append(("D", n_)); md.append(str(state["run"]) + "^" + gs[state["gp"] - 1:state["gp"] - 1 + n_])
+            state["run"] = 0; state["gp"] += n_
+
+        def ins(n_):
+            ops.append(("I", n_)); seq.append("".join(rng.choice(BASES) for _ in range(n_)))
+
+        match(l1)
+        if pre == "D":
+            dele(rng.randrange(1, 9))                # longer than maxLenIndel now and then: the op survives the indel stage
+        elif pre == "I":
+            ins(rng.randrange(1, 9))
+        i0 = state["gp"]
+        ops.append(("N", m)); state["gp"] += m
+        i1 = state["gp"] - 1
+        if post == "D":
+            dele(rng.randrange(1, 9))
+        elif post == "I":
+            ins(rng.randrange(1, 9))
+        match(l2)
+        if rng.random() < 0.4:                       # an ordinary second intron behind, shifted off its annotated site now and then
+            a0 = state["gp"]; il = rng.randrange(80, 400)
+            ops.append(("N", il)); state["gp"] += il
+            sh = rng.choice([0, 0, 2, -3])
+            case.sj_rows.append(["chr1", a0 + sh, a0 + il - 1, 1 if strand == "+" else 2, 1, 1, 5, 0, 30])
+            match(rng.randrange(20, 50))
+        md.append(str(state["run"]))
+        cig = "".join("%d%s" % (c, o) for o, c in ops)
+        nm = sum(c for o, c in ops if o in "DI")
+        col4 = 1 if strand == "+" else 2
+        dd, da = rng.randrange(-9, 10), rng.randrange(-9, 10)
+        case.sj_rows.append(["chr1", i0 + dd, i0 + dd + 3000 + r, col4, 1, 1, 5, 0, 30])
+        case.sj_rows.append(["chr1", i1 + da - 3000 - r, i1 + da, col4, 1, 1, 5, 0, 30])
+        case.lines.append("\t".join(["mi%d_%d" % (seed, r), "0" if strand == "+" else "16", "chr1", str(p), "60", cig, "*", "0", "0",
+                                     "".join(seq), "*", "NM:i:%d" % nm, "MD:Z:" + "".join(md)]))
+        p = state["gp"] + 200
+    return case

@@ -34,3 +34,14 @@ def test_oracle_dry_run_equals_reference():
     want = ref_harness.run_reference(case.lines, case.genome, dryRun=True)
     got = pipeline.oracle_texts(case.genome, case.lines, None, None, {}, dry=True)
     assert {k: got[k] for k in ("log", "te")} == {k: want[k] for k in ("log", "te")}
+
+
+@pytest.mark.parametrize("seed", (7201, 7202, 7203))
+def test_oracle_equals_reference_on_micro_introns(seed):
+    """Rescues that shrink an intron to zero or below (tests/test_micro_introns.py)."""
+    case = synth.make_micro_intron_case(seed)
+    sjf, _ = pipeline.write_tables(case.sj_rows, None)
+    for opts in (dict(), dict(maxSJOffset=10, correctIndels=False)):
+        want = ref_harness.run_reference(case.lines, case.genome, sj_file=sjf, **opts)
+        d = pipeline.first_diff(pipeline.oracle_texts(case.genome, case.lines, sjf, None, opts), want)
+        assert d is None, (seed, opts, d)

@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_EMIT_BLOCKS) k_emit(P
                     const int qs = (int)((unsigned)qm >> 16), ms = qm & 0xffff;              // ms: matched bases before this op
                     const int qtot = (int)((unsigned)qmtot >> 16), mtot = qmtot & 0xffff;
                     const bool isM = op == 'M' && ct > 0, isD = op == 'D';
+                    ovf |= ct < 0;                                      // an intron of negative length (tc_plan.cuh, intron_text_rules): the exact walk
                     const unsigned mM = __ballot_sync(FULL, isM), mD = __ballot_sync(FULL, isD);
                     if (mD) {   // MD token of a D op: <matches since the previous token>^<bases>   (uniform branch: most reads keep no D)
                         const unsigned prev = mD & lt;                  // nearest earlier D in this round, else the carried one

@@ -281,7 +281,7 @@ void render_range(const tc_sam* S, const tc_batch_out* R, int64_t a, int64_t b, 
         if (st & TC_ST_CIGAR_REWRITTEN) {
             if (c1 > c0) {
                 if (sam.n > row0) sam.ch('\t');
-                for (int64_t k = c0; k < c1; k++) { sam.num(R->cig_len[k]); sam.ch((char)R->cig_op[k]); }
+                for (int64_t k = c0; k < c1; k++) { sam.num(R->cig_len[k]); sam.ch(R->cig_op[k] == 'd' ? 'D' : (char)R->cig_op[k]); }   // 'd': tc_plan.cuh, intron_text_rules
             }
         } else add_span(S->cigar[i]);
         add_span(S->f[6][i]); add_span(S->f[7][i]); add_span(S->f[8][i]);
@@ -536,11 +536,9 @@ int tc_sam_render(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_
     if (!S || !R || R->n_reads != S->n) { set_err(err, err_cap, "tc_sam_render: result does not belong to this batch"); return TC_E_ARG; }
     for (int64_t i = 0; i < S->n; i++) {
         const uint32_t st = R->status[i];
-        if (st & (TC_ST_ERR_INTRON | TC_ST_ERR_MERGE)) {
+        if (st & TC_ST_ERR_MERGE) {                                    // dry run only: the reference's dryRun() dies on this read
             std::string q(S->text + S->f[0][i].s, (size_t)S->f[0][i].n);
-            set_err(err, err_cap, (st & TC_ST_ERR_INTRON)
-                        ? "read " + q + ": junction rescue would leave an intron of length <= 0 (unsupported input)"
-                        : "read " + q + ": MD tag and CIGAR disagree (the reference's --dryRun crashes on this read)");
+            set_err(err, err_cap, "read " + q + ": MD tag and CIGAR disagree (the reference's --dryRun crashes on this read)");
             return TC_E_INPUT;
         }
     }

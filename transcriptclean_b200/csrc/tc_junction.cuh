@@ -100,7 +100,7 @@ __device__ int w_seg_delete(const u64* s, int n, u64* d, int64_t qa, int64_t qb,
 // editExonCIGAR (TC.py:1515-1555) on ops [lo,hi) plus the intron length change: the few ops the edit
 // touches are found by a (uniform) scalar walk, the list is copied across the lanes
 __device__ int w_cig_edit(const u64* src, int n, u64* dst, int lo, int hi, bool at_end, int nb, int intron_idx, int intron_delta,
-                          bool& degenerate, int lane) {
+                          bool& raised, bool& unsupported, int lane) {
     int sa = lo, sb = hi, km = -1, newlen = 0, ins_front = 0, ins_back = 0;
     if (nb >= 0) {
         if (hi - lo == 0) return -1;
@@ -129,20 +129,32 @@ __device__ int w_cig_edit(const u64* src, int n, u64* dst, int lo, int hi, bool 
         }
         if (sb < sa) sb = sa;
     }
-    const int nsurv = sb - sa; bool deg = false;
+    const int nsurv = sb - sa;
     for (int k = lane; k < n; k += 32) {
         u64 c = src[k];
-        if (k < lo || k >= hi) {
-            if (k == intron_idx) { const int32_t L = cg_len(c) + intron_delta; if (L <= 0) deg = true; c = cg_make('N', L); }
-            dst[k < lo ? k : lo + ins_front + nsurv + ins_back + (k - hi)] = c;
-        } else if (k >= sa && k < sb) {
+        if (k < lo || k >= hi) dst[k < lo ? k : lo + ins_front + nsurv + ins_back + (k - hi)] = c;
+        else if (k >= sa && k < sb) {
             if (k == km) c = cg_make(cg_op(c), newlen);
             dst[lo + ins_front + (k - sa)] = c;
         }
     }
     if (lane == 0) { if (ins_front) dst[lo] = cg_make('M', nb); if (ins_back) dst[lo + nsurv] = cg_make('M', nb); }
-    if (__any_sync(FULL, deg)) degenerate = true;
-    return lo + ins_front + nsurv + ins_back + (n - hi);
+    const int m = lo + ins_front + nsurv + ins_back + (n - hi);
+    __syncwarp();
+    if (intron_idx >= 0) {                                             // the intron whose length changes, under the text rules (tc_plan.cuh)
+        const int idx = intron_idx < lo ? intron_idx : lo + ins_front + nsurv + ins_back + (intron_idx - hi);
+        const int32_t L = cg_len(src[intron_idx]) + intron_delta;
+        bool ok = true, uns = false;
+        if (lane == 0) ok = intron_text_rules(dst, idx, L, uns);
+        ok = __shfl_sync(FULL, ok ? 1 : 0, 0) != 0; uns = __shfl_sync(FULL, uns ? 1 : 0, 0) != 0;
+        __syncwarp();
+        bool bad = false;                                              // other_dminus_ok across the lanes
+        for (int k = lane; k + 1 < m; k += 32)
+            bad |= cg_op(dst[k]) == CG_OP_DMINUS && k + 1 != idx && cg_op(dst[k + 1]) == 'N' && cg_len(dst[k + 1]) < 0;
+        if (!ok || __any_sync(FULL, bad)) raised = true;
+        if (uns) unsupported = true;
+    }
+    return m;
 }
 // sj_nearest (tc_plan.cuh) with a 32-way search: three probes instead of fifteen for ~17,000 sites
 __device__ bool w_sj_nearest(const u64* tab, const int32_t* rng, int32_t n_prefix, u64 prefix, int64_t q, bool tie_right, int& dist, int lane) {
@@ -174,8 +186,9 @@ __device__ bool w_sj_nearest(const u64* tab, const int32_t* rng, int32_t n_prefi
 }
 // fix_one_side_of_junction (TC.py:1415-1479); see fix_side in tc_plan.cuh
 __device__ bool w_fix_side(const Params& P, int chrom, int k, int side, int d, int32_t* bound_slot, int32_t& bound, JnState& S,
-                           u64* cig_dst, u64* seg_dst, bool& degenerate, int lane) {
+                           u64* cig_dst, u64* seg_dst, bool& unsupported, int lane) {
     if (d == 0) return true;
+    bool raised = false;
     ExonLoc e; int nN; const int t = side == 0 ? k : k + 1;
     if (!w_locate_exon(S.cig, S.nc, t, e, nN, lane)) return false;            // exonSeqs[targetExon] IndexError
     const GenomeDev& G = P.G; const int64_t goff = G.chrom_off[chrom] - 1;
@@ -192,8 +205,8 @@ __device__ bool w_fix_side(const Params& P, int chrom, int k, int side, int d, i
         }
         bound += d; if (lane == 0) *bound_slot = bound;
         if (k >= nN) return false;                                    // intronCIGARs[jn_number] IndexError
-        const int ncn = w_cig_edit(S.cig, S.nc, cig_dst, e.lo, e.hi, true, d, e.nidx, -d, degenerate, lane);
-        if (ncn < 0) return false;
+        const int ncn = w_cig_edit(S.cig, S.nc, cig_dst, e.lo, e.hi, true, d, e.nidx, -d, raised, unsupported, lane);
+        if (ncn < 0 || raised) return false;
         S.nc = ncn;
     } else {
         if (d < 0) {                                                  // case 2: prepend to the next exon
@@ -207,8 +220,8 @@ __device__ bool w_fix_side(const Params& P, int chrom, int k, int side, int d, i
         }
         bound += d; if (lane == 0) *bound_slot = bound;
         ExonLoc ek; ek.nidx = -1; int nn2; w_locate_exon(S.cig, S.nc, k, ek, nn2, lane);   // the intron before exon k+1 is the k-th N op
-        const int ncn = w_cig_edit(S.cig, S.nc, cig_dst, e.lo, e.hi, false, -d, ek.nidx, d, degenerate, lane);
-        if (ncn < 0) return false;
+        const int ncn = w_cig_edit(S.cig, S.nc, cig_dst, e.lo, e.hi, false, -d, ek.nidx, d, raised, unsupported, lane);
+        if (ncn < 0 || raised) return false;
         S.nc = ncn;
     }
     __syncwarp();                                                     // the new lists are read by other lanes from here on
@@ -236,7 +249,7 @@ __device__ void junction_fix_warp(const Params& P, int64_t i, int lane) {
         __syncwarp();
     }
     int64_t seqlen = w_seg_total(v.seg[sb], ns, lane);
-    bool whole_fail = false, degenerate = false, any_ok = false;
+    bool whole_fail = false, unsupported = false, any_ok = false;
     const bool tie_right = O.sj_tie_right != 0;
     for (int k = 0; k < nj && !whole_fail; k++) {
         int32_t* r = J + k * JN_STRIDE;
@@ -269,7 +282,7 @@ __device__ void junction_fix_warp(const Params& P, int64_t i, int lane) {
             const int side = w == 0 ? ds : as, d = w == 0 ? d_don : d_acc;
             if (d == 0) continue;
             const int tc = used_c == cb ? t1 : t2, ts = used_s == sb ? u1 : u2;
-            ok = w_fix_side(P, chrom, k, side, d, &r[side], bnd[side], S, v.cig[tc], v.seg[ts], degenerate, lane); used_c = tc; used_s = ts;
+            ok = w_fix_side(P, chrom, k, side, d, &r[side], bnd[side], S, v.cig[tc], v.seg[ts], unsupported, lane); used_c = tc; used_s = ts;
         }
         int code = code0;
         if (ok) {                                                     // update_post_ncsj_correction (TC.py:1279-1294)
@@ -305,7 +318,8 @@ __device__ void junction_fix_warp(const Params& P, int64_t i, int lane) {
             W.refresh[i] = 0; W.nm_extra[i] = 0;
         }
     } else {
-        if (any_ok) { st |= TC_ST_CIGAR_REWRITTEN | TC_ST_JM_DEVICE | TC_ST_JI_DEVICE; if (degenerate) st |= TC_ST_ERR_INTRON; }
+        if (any_ok) st |= TC_ST_CIGAR_REWRITTEN | TC_ST_JM_DEVICE | TC_ST_JI_DEVICE;
+        if (unsupported) st |= TC_ST_ERR_INTRON;
         if (lane == 0) {
             C[TC_C_COR_SJ] = cJ; C[TC_C_UNC_SJ] = uJ;
             W.n_te[i] = nte;

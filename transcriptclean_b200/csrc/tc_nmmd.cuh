@@ -25,11 +25,11 @@ __device__ NmMd warp_nmmd(const GenomeDev& G, const uint8_t* seq, const uint32_t
     // reference span: one literal-run check and one contig-end check for the whole read
     bool span_exc, careful;
     {
-        int64_t span = 0;
-        for (int k = lane; k < cs.n; k += 32) { int op; int32_t ct; cig_get(cs, k, op, ct); if (op == 'M' || op == 'D' || op == 'N' || op == 'H') span += ct; }
+        int64_t span = 0; bool neg = false;                 // (negative lengths - a rescued micro-intron - only widen the span that is checked)
+        for (int k = lane; k < cs.n; k += 32) { int op; int32_t ct; cig_get(cs, k, op, ct); if (op == 'M' || op == 'D' || op == 'N' || op == 'H') span += ct > 0 ? ct : 0; neg |= ct < 0; }
 #pragma unroll
         for (int d = 16; d; d >>= 1) span += __shfl_xor_sync(FULL, span, d);
-        careful = pos < 1 || pos + span - 1 > clen || span > 0x7fffffffll;
+        careful = pos < 1 || pos + span - 1 > clen || span > 0x7fffffffll || __any_sync(FULL, neg);
         span_exc = careful || (span > 0 && warp_range_has_exc(G, gbase, gbase + span, lane));
     }
     for (int k0 = 0; k0 < cs.n && !none; k0 += 32) {

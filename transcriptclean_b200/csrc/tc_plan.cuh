@@ -599,14 +599,49 @@ TC_HD int64_t cig_query_len(const u64* cig, int n) {             // tr.py:591-60
     return q;
 }
 
+// ---- introns of length <= 0 after a rescue.
+// fix_one_side_of_junction pastes the new CIGAR together as TEXT (TC.py:1466-1470) and every later consumer splits that
+// text again with two regular expressions (tr.py:579-588, TC.py:1504-1512).  An intron whose length went negative prints
+// as "-3N"; on the next split the '-' sticks to the op letter in front of it ("20M-" is no known op any more) while the
+// count parses as -3.  What follows from that, in terms of the op list (probe-verified against the
+// unmodified reference, tests/test_micro_introns.py):
+//   length 0                   "0N": an ordinary op, everything downstream is integer arithmetic
+//   < 0 behind M / S / I       the length check at TC.py:1476 no longer counts that op -> RuntimeError -> "Other"
+//   < 0 behind D               the check passes ("D-" was never counted).  The op is kept as 'd' here: no consumer knows it
+//                              (getNMandMDFlags skips it, tr.py:296-334), it prints as 'D', and the '-' it carries now
+//                              belongs to the text: a later re-serialisation prints "D-" + str(v) + "N", which parses as
+//                              -v for v >= 0 and raises ValueError ("--3") for v < 0
+//   < 0 behind anything else   (an intron, a clip, the start of the CIGAR) the split lists go out of step; not modelled:
+//                              the junction is left uncorrected ("Other") and TC_ST_ERR_INTRON is set on the read
+#define CG_OP_DMINUS 'd'
+// dst[idx] is the intron whose arithmetic length is L.  Returns false when the reference raises.
+TC_HD bool intron_text_rules(u64* dst, int idx, int32_t L, bool& unsupported) {
+    const int prev = idx > 0 ? cg_op(dst[idx - 1]) : 0;
+    if (prev == CG_OP_DMINUS) {
+        if (L < 0) return false;                                      // "5D--3N": int("--3")
+        dst[idx] = cg_make('N', -L); return true;                     // "5D-2N" parses as -2
+    }
+    if (L >= 0) { dst[idx] = cg_make('N', L); return true; }
+    if (prev == 'M' || prev == 'S' || prev == 'I') return false;      // the op's bases drop out of the length check
+    if (prev == 'D') { dst[idx - 1] = cg_make(CG_OP_DMINUS, cg_len(dst[idx - 1])); dst[idx] = cg_make('N', L); return true; }
+    unsupported = true; return false;
+}
+// every other "D-" of the list is printed again with its intron behind it: a negative one raises ("--")
+TC_HD bool other_dminus_ok(const u64* c, int n, int edited_idx) {
+    for (int k = 0; k + 1 < n; k++)
+        if (cg_op(c[k]) == CG_OP_DMINUS && k + 1 != edited_idx && cg_op(c[k + 1]) == 'N' && cg_len(c[k + 1]) < 0) return false;
+    return true;
+}
+
 // editExonCIGAR (TC.py:1515-1555) applied to ops [lo,hi) of src, plus the intron length change.
-// Returns the new op count, or -1 for the IndexError on an empty exon (TC.py:1526).
+// Returns the new op count, or -1 for the IndexError on an empty exon (TC.py:1526); `raised` is set when the
+// text rules above make the reference raise.
 TC_HD int cig_edit(const u64* src, int n, u64* dst, int lo, int hi, bool at_end, int nb,
-                   int intron_idx, int intron_delta, bool& degenerate) {
-    int m = 0;
+                   int intron_idx, int intron_delta, bool& raised, bool& unsupported) {
+    int m = 0, intron_dst = -1; int32_t intron_len = 0;
     for (int k = 0; k < lo; k++) {
         u64 c = src[k];
-        if (k == intron_idx) { int32_t L = cg_len(c) + intron_delta; if (L <= 0) degenerate = true; c = cg_make('N', L); }
+        if (k == intron_idx) { intron_dst = m; intron_len = cg_len(c) + intron_delta; }
         dst[m++] = c;
     }
     int ne = hi - lo;
@@ -648,9 +683,10 @@ TC_HD int cig_edit(const u64* src, int n, u64* dst, int lo, int hi, bool at_end,
     }
     for (int k = hi; k < n; k++) {
         u64 c = src[k];
-        if (k == intron_idx) { int32_t L = cg_len(c) + intron_delta; if (L <= 0) degenerate = true; c = cg_make('N', L); }
+        if (k == intron_idx) { intron_dst = m; intron_len = cg_len(c) + intron_delta; }
         dst[m++] = c;
     }
+    if (intron_dst >= 0 && (!intron_text_rules(dst, intron_dst, intron_len, unsupported) || !other_dminus_ok(dst, m, intron_dst))) raised = true;
     return m;
 }
 
@@ -691,8 +727,9 @@ struct JnState {              // the transcript copy being edited by attempt_jn_
 // still fail, exactly like intronBound.pos (Q18).  Returns false for every path on which the
 // reference raises inside the try at TC.py:1323-1342.
 TC_HD bool fix_side(const Params& P, int chrom, int k, int side, int d, int32_t* bound, JnState& S,
-                    u64* cig_dst, u64* seg_dst, bool& degenerate) {
+                    u64* cig_dst, u64* seg_dst, bool& unsupported) {
     if (d == 0) return true;
+    bool raised = false;
     ExonLoc e; int nN; int t = side == 0 ? k : k + 1;
     if (!locate_exon(S.cig, S.nc, t, e, nN)) return false;            // exonSeqs[targetExon] IndexError
     const GenomeDev& G = P.G; int64_t goff = G.chrom_off[chrom] - 1;
@@ -709,8 +746,8 @@ TC_HD bool fix_side(const Params& P, int chrom, int k, int side, int d, int32_t*
         }
         *bound += d;
         if (k >= nN) return false;                                    // intronCIGARs[jn_number] IndexError
-        int ncn = cig_edit(S.cig, S.nc, cig_dst, e.lo, e.hi, true, d, e.nidx, -d, degenerate);
-        if (ncn < 0) return false;
+        int ncn = cig_edit(S.cig, S.nc, cig_dst, e.lo, e.hi, true, d, e.nidx, -d, raised, unsupported);
+        if (ncn < 0 || raised) return false;
         S.nc = ncn;
     } else {
         if (d < 0) {                                                  // case 2: prepend to the next exon
@@ -725,8 +762,8 @@ TC_HD bool fix_side(const Params& P, int chrom, int k, int side, int d, int32_t*
         *bound += d;
         // the intron before exon k+1 is the k-th N op
         ExonLoc ek; ek.nidx = -1; int nn2; locate_exon(S.cig, S.nc, k, ek, nn2);
-        int ncn = cig_edit(S.cig, S.nc, cig_dst, e.lo, e.hi, false, -d, ek.nidx, d, degenerate);
-        if (ncn < 0) return false;
+        int ncn = cig_edit(S.cig, S.nc, cig_dst, e.lo, e.hi, false, -d, ek.nidx, d, raised, unsupported);
+        if (ncn < 0 || raised) return false;
         S.nc = ncn;
     }
     S.cig = cig_dst; S.seg = seg_dst; S.ns = ns2; S.seqlen = newlen;
@@ -804,7 +841,7 @@ TC_HD void junction_fix_read(const Params& P, int64_t i) {
                 cb = 0; sb = 0;
             }
             int64_t seqlen = 0; for (int s = 0; s < ns; s++) seqlen += seg_len(v.seg[sb][s]);
-            bool whole_fail = false, degenerate = false, any_ok = false;
+            bool whole_fail = false, unsupported = false, any_ok = false;
             const bool tie_right = O.sj_tie_right != 0;
             for (int k = 0; k < nj && !whole_fail; k++) {
                 int32_t* r = J + k * JN_STRIDE;
@@ -831,10 +868,10 @@ TC_HD void junction_fix_read(const Params& P, int64_t i) {
                 JnState S; S.cig = v.cig[cb]; S.nc = nc; S.seg = v.seg[sb]; S.ns = ns; S.seqlen = seqlen;
                 int used_c = cb, used_s = sb;
                 bool ok = true;
-                if (d_don != 0) { ok = fix_side(P, chrom, k, ds, d_don, &r[ds], S, v.cig[t1], v.seg[u1], degenerate); used_c = t1; used_s = u1; }
+                if (d_don != 0) { ok = fix_side(P, chrom, k, ds, d_don, &r[ds], S, v.cig[t1], v.seg[u1], unsupported); used_c = t1; used_s = u1; }
                 if (ok && d_acc != 0) {
                     int tc = used_c == cb ? t1 : t2, ts = used_s == sb ? u1 : u2;
-                    ok = fix_side(P, chrom, k, as, d_acc, &r[as], S, v.cig[tc], v.seg[ts], degenerate); used_c = tc; used_s = ts;
+                    ok = fix_side(P, chrom, k, as, d_acc, &r[as], S, v.cig[tc], v.seg[ts], unsupported); used_c = tc; used_s = ts;
                 }
                 if (ok) {                                             // update_post_ncsj_correction (TC.py:1279-1294)
                     r[2] = r[0]; r[3] = r[1];
@@ -871,8 +908,8 @@ TC_HD void junction_fix_read(const Params& P, int64_t i) {
                     W.cig_buf[i] = (int8_t)cb; W.seg_buf[i] = (int8_t)sb; W.n_cig_cur[i] = nc; W.n_seg_cur[i] = ns; W.seq_len_out[i] = (int32_t)seqlen;
                     W.refresh[i] = 1; W.nm_extra[i] = 0;
                     st |= TC_ST_CIGAR_REWRITTEN | TC_ST_JM_DEVICE | TC_ST_JI_DEVICE;
-                    if (degenerate) st |= TC_ST_ERR_INTRON;
                 }
+                if (unsupported) st |= TC_ST_ERR_INTRON;
             }
         }
     }

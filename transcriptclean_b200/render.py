@@ -50,7 +50,7 @@ class ReadView:
         self.SEQ = res.seq[res.seq_off[i]:res.seq_off[i] + res.seq_len[i]].tobytes().decode("ascii")
         if st & E.ST_CIGAR_REWRITTEN:
             a, b = res.cig_off[i], res.cig_off[i + 1]
-            self.CIGAR = "".join("%d%s" % (l, chr(o)) for o, l in zip(res.cig_op[a:b], res.cig_len[a:b]))
+            self.CIGAR = "".join("%d%s" % (l, chr(o).upper()) for o, l in zip(res.cig_op[a:b], res.cig_len[a:b]))   # 'd' = "D-" (tc_plan.cuh)
         else:
             self.CIGAR = pb.cigar_str[i]
         if st & E.ST_NMMD_DEVICE:
@@ -88,12 +88,10 @@ class ReadView:
 
 
 def check_errors(pb, res):
-    bad = (res.status & (E.ST_ERR_INTRON | E.ST_ERR_MERGE)) != 0
+    bad = (res.status & E.ST_ERR_MERGE) != 0       # (ST_ERR_INTRON is informational: that junction stayed uncorrected)
     if bad.any():
         i = int(bad.argmax())
         name = pb.lines[i].split("\t")[0]
-        if res.status[i] & E.ST_ERR_INTRON:
-            raise E.EngineError("read %s: junction rescue would leave an intron of length <= 0 (unsupported input)" % name)
         raise E.EngineError("read %s: MD tag and CIGAR disagree (the reference's --dryRun crashes on this read)" % name)
 
 
