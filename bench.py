@@ -155,28 +155,66 @@ def write_sj(w):
     return path
 
 
+_REF = {}
+
+
+def _ref_init(w_genome, chrom, sj_path, chrom_line):
+    """Pool initializer: one reference worker per process, as run_chunk does (prep_refs per worker, TC.py:560-586)."""
+    from oracle import ref_harness
+    _REF["w"] = ref_harness.Worker({chrom: w_genome}, sj_file=sj_path, chrom_lines=[chrom_line])
+
+
+def _ref_chunk(lines):
+    return len(_REF["w"].correct(lines)["log"])
+
+
+def reference_rate(w, sj_path, lines, threads, steps=1, warmup=0):
+    """Reads/s of the UNMODIFIED reference (oracle/_ref or /root/reference, under oracle/stubs): `threads` forked workers,
+    each with its own prep_refs; the timed region is the batch_correct calls (TC.py:350-403), like the GPU arm's
+    timed region excludes table set-up."""
+    import multiprocessing as mp
+    genome = w.genome.tobytes().decode("ascii")          # shared with the forked workers (copy-on-write pages)
+    chunks = [lines[i::threads] for i in range(threads)]
+    times = []
+    ctx = mp.get_context("fork")
+    with ctx.Pool(threads, initializer=_ref_init, initargs=(genome, w.chrom, sj_path, lines[0])) as pool:
+        pool.map(_ref_chunk, [c[:2] for c in chunks])    # every worker is up (prep_refs done) before the clock starts
+        for s in range(warmup + steps):
+            t0 = time.perf_counter(); pool.map(_ref_chunk, chunks, chunksize=1); t1 = time.perf_counter()
+            if s >= warmup:
+                times.append(t1 - t0)
+    return len(lines) / (sum(times) / len(times)), sum(times) / len(times)
+
+
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation (oracle port; the reference is pure
-    Python and is not shipped to the GPU box) with all host threads, on a bounded sample."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores, on a bounded sample of
+    the same workload.  The UNMODIFIED reference (pip-installed into oracle/_ref by __graft_entry__.build(), run under
+    oracle/stubs) when it is there, else the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from tools.workload import Workload
+    from oracle import ref_harness
     cores = os.cpu_count() or 1
     threads = min(cores, 64)
     w = Workload(seed=args.seed, chrom_len=args.chrom_len, n_genes=args.genes)
     sj_path = write_sj(w)
-    n_sample = args.ref_reads if args.ref_reads else threads * 600
+    real = ref_harness.available() and not args.ref_port
+    n_sample = args.ref_reads if args.ref_reads else threads * (300 if real else 600)
     cols, nm = w.reads(args.shape, n_sample)
     lines = w.sam_lines(cols, nm, 0, n_sample)
-    rate, sec = oracle_rate(w, sj_path, lines, threads, steps=args.steps, warmup=min(args.warmup, 1))
+    if real:
+        rate, sec = reference_rate(w, sj_path, lines, threads, steps=args.steps, warmup=min(args.warmup, 1))
+        kind, what = "reference", "the unmodified reference (TranscriptClean v2.1 installed in oracle/_ref, prep_refs + batch_correct under oracle/stubs)"
+    else:
+        rate, sec = oracle_rate(w, sj_path, lines, threads, steps=args.steps, warmup=min(args.warmup, 1))
+        kind, what = "port", "oracle/tc_oracle.py with the reference's per-base genome walk"
     line = {"impl": "reference", "metric": "reads corrected/sec", "value": rate, "unit": "reads/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "shape": args.shape, "reads_per_step": n_sample},
-            "cpu_baseline": {"value": rate, "unit": "reads/s", "cores": threads, "kind": "port",
-                             "sample": "first %d reads of the workload per step, %d forked workers, oracle/tc_oracle.py "
-                                       "with the reference's per-base genome walk" % (n_sample, threads)},
+            "cpu_baseline": {"value": rate, "unit": "reads/s", "cores": threads, "kind": kind,
+                             "sample": "first %d reads of the workload per step, %d forked workers, %s" % (n_sample, threads, what)},
             "e2e": {"value": rate, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -198,6 +236,7 @@ def main():
     ap.add_argument("--seed", type=int, default=20261019)
     ap.add_argument("--cpu-sample", type=int, default=3000)
     ap.add_argument("--ref-reads", type=int, default=0)
+    ap.add_argument("--ref-port", action="store_true", help="--impl reference: time the oracle port even when oracle/_ref holds the reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--text-sample", type=int, default=100000, help="reads for the SAM-text path measurement (0 = skip)")
     ap.add_argument("--resident-only", action="store_true", help="profiling aid: only the device-resident steps (no pipelined e2e calls), so that a "

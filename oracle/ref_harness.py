@@ -1,9 +1,9 @@
-"""Runs the UNMODIFIED reference (/root/reference) in-process under oracle/stubs.
+"""Runs the UNMODIFIED reference in-process under oracle/stubs.
 
-TEST INFRASTRUCTURE ONLY, and build-container only: /root/reference does not exist on the
-GPU box, so nothing that runs there may import this module.  Used by oracle/make_golden.py
-to produce tests/golden/*.json and by tests/test_oracle_vs_reference.py (auto-skipped when
-the reference tree is absent).
+TEST / BENCH INFRASTRUCTURE ONLY.  The reference is looked for at /root/reference (the build container) and then at
+oracle/_ref (the pip-installed copy `__graft_entry__.build()` makes there; git-ignored, but it travels to the GPU box,
+where `bench.py --impl reference` times it).  Used by oracle/make_golden*.py to produce tests/golden/*.json.gz, by
+tests/test_oracle_vs_reference.py (auto-skipped when no reference is found) and by bench.py's reference arm.
 """
 import io
 import os
@@ -11,12 +11,14 @@ import sys
 import tempfile
 import contextlib
 
-REF_ROOT = "/root/reference"
 _HERE = os.path.dirname(os.path.abspath(__file__))
+REF_ROOT = os.environ.get("TC_REF_ROOT") or "/root/reference"
+if not os.path.isdir(os.path.join(REF_ROOT, "TranscriptClean")):
+    REF_ROOT = os.path.join(_HERE, "_ref")
 
 
 def available():
-    return os.path.isdir(os.path.join(REF_ROOT, "TranscriptClean"))
+    return os.path.isfile(os.path.join(REF_ROOT, "TranscriptClean", "TranscriptClean.py"))
 
 
 def load():
@@ -86,3 +88,48 @@ def run_reference(lines, genome_seqs, sj_file=None, vcf_file=None, maxLenIndel=5
     os.system("rm -rf " + tmp)
     return {"sam": out.sam.getvalue(), "fa": out.fasta.getvalue(), "log": out.log.getvalue(),
             "te": out.TElog.getvalue()}
+
+
+class Worker:
+    """One worker process of the reference as run_chunk sets it up (TC.py:560-586): prep_refs once, then batch_correct on
+    whatever lines it is given.  `correct(lines)` returns the four texts."""
+
+    def __init__(self, genome_seqs, sj_file=None, vcf_file=None, chrom_lines=(), **opts):
+        TC, Struct, pyfaidx, pyranges = load()
+        self.TC, self.Struct = TC, Struct
+        pyranges.STRAND_MODE, pyranges.TIE = opts.pop("strand_mode", "same"), opts.pop("tie", "left")
+        self.tmp = tempfile.mkdtemp(prefix="tc_ref_") + "/"
+        gname = self.tmp + "genome.mem"
+        pyfaidx.REGISTRY[gname] = genome_seqs if hasattr(genome_seqs, "fetch") and hasattr(genome_seqs, "names") else _Mem(genome_seqs)
+        o = Struct()
+        o.refGenome, o.variantFile, o.sjAnnotFile, o.tmp_dir = gname, vcf_file, sj_file, self.tmp
+        o.maxLenIndel, o.maxSJOffset = opts.get("maxLenIndel", 5), opts.get("maxSJOffset", 5)
+        tf = lambda b: "true" if b else "false"
+        o.correctMismatches, o.correctIndels, o.correctSJs = (tf(opts.get(k, True)) for k in ("correctMismatches", "correctIndels", "correctSJs"))
+        o.primaryOnly, o.canonOnly, o.dryRun, o.buffer_size = opts.get("primaryOnly", False), opts.get("canonOnly", False), False, 100
+        self.o = o
+        with self._quiet():
+            self.refs = TC.prep_refs(o, list(chrom_lines), [])
+
+    @contextlib.contextmanager
+    def _quiet(self):
+        import warnings
+        sink = io.StringIO()
+        with contextlib.redirect_stdout(sink), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            devnull = os.open(os.devnull, os.O_WRONLY)
+            saved = os.dup(2)
+            os.dup2(devnull, 2)
+            try:
+                yield
+            finally:
+                os.dup2(saved, 2)
+                os.close(devnull)
+                os.close(saved)
+
+    def correct(self, lines):
+        out = self.Struct()
+        out.sam, out.fasta, out.log, out.TElog = io.StringIO(), io.StringIO(), io.StringIO(), io.StringIO()
+        with self._quiet():
+            self.TC.batch_correct(list(lines), self.o, self.refs, out, buffer_size=100)
+        return {"sam": out.sam.getvalue(), "fa": out.fasta.getvalue(), "log": out.log.getvalue(), "te": out.TElog.getvalue()}
