@@ -216,6 +216,27 @@ int tc_sam_render(tc_sam* s, const tc_batch_out* res, int32_t primary_only, int3
                   int32_t n_threads, const char** sam, int64_t* sam_len, const char** fa, int64_t* fa_len,
                   const char** log, int64_t* log_len, const char** te, int64_t* te_len, char* err, int64_t err_cap);
 
+/* ---- host side: lookup tables from their files (csrc/tc_tables.cpp, multi-threaded C++; no GPU involved) ----
+ * tc_vcf_parse replaces processVCF (TranscriptClean.py:769-856): VCF text (already decompressed) -> the arrays of
+ * tc_ctx_load_variants.  tc_sj_parse replaces processSpliceAnnotation (TranscriptClean.py:666-766): STAR SJ.out.tab
+ * text -> the arrays of tc_ctx_load_junctions.  `use[c]` = 0 drops rows of contig c (contigs no read maps to, TC.py:685;
+ * NULL keeps all).  NULL + `err` for rows the reference's int() / indexing would raise on. */
+typedef struct tc_vcf tc_vcf;
+tc_vcf* tc_vcf_parse(const char* text, int64_t len, int32_t n_chrom, const char* const* chrom_names, const uint8_t* use,
+                     int32_t max_len_indel, int32_t n_threads, char* err, int64_t err_cap);
+void tc_vcf_tables(const tc_vcf* v, int64_t* n_snp, const uint64_t** snp_key, const uint8_t** snp_alt, int64_t* n_ins,
+                   const uint64_t** ins_key, const int32_t** ins_size, const int64_t** ins_aoff, const uint8_t** ins_bytes,
+                   int64_t* n_del, const uint64_t** del_key, const int32_t** del_size);
+int64_t tc_vcf_n_records(const tc_vcf* v);
+void tc_vcf_free(tc_vcf* v);
+typedef struct tc_sj tc_sj;
+tc_sj* tc_sj_parse(const char* text, int64_t len, int32_t n_chrom, const char* const* chrom_names, const uint8_t* use,
+                   char* err, int64_t err_cap);
+void tc_sj_tables(const tc_sj* s, int64_t* n_don_s, const uint64_t** don_s, int64_t* n_acc_s, const uint64_t** acc_s,
+                  int64_t* n_don_u, const uint64_t** don_u, int64_t* n_acc_u, const uint64_t** acc_u,
+                  int64_t* n_annot, const uint64_t** ann_k1, const uint64_t** ann_k2);
+void tc_sj_free(tc_sj* s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,3 +6,4 @@
 #define TC_HOSTSIM 1
 #include "../../transcriptclean_b200/csrc/tc_b200.cu"
 #include "../../transcriptclean_b200/csrc/tc_host.cpp"
+#include "../../transcriptclean_b200/csrc/tc_tables.cpp"

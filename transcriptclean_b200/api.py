@@ -47,13 +47,9 @@ def make_refs(genome, sj_tables=None, var_tables=None, device=0, engine=None):
     return refs
 
 
-def prep_refs(options, transcripts, sam_header=None, device=0, engine=None, genome=None):
-    """TC.py:203-255: genome, splice annotation restricted to the chromosomes of `transcripts`,
-    variant catalogues.  No temp files are written."""
-    if genome is None:
-        print("Reading genome ..............................")
-        genome = GenomeImage.from_fasta(_opt(options, "refGenome"))
-    chroms = set(t.split("\t")[2] for t in transcripts)
+def build_tables(options, chroms, genome):
+    """The splice-junction and variant tables of prep_refs (TC.py:224-253) as host arrays: built ONCE, whatever the
+    number of GPUs (`make_refs` uploads the same arrays to every engine)."""
     sj = var = None
     sj_file, vcf = _opt(options, "sjAnnotFile"), _opt(options, "variantFile")
     if not _truthy(_opt(options, "correctSJs", "true")):
@@ -65,9 +61,20 @@ def prep_refs(options, transcripts, sam_header=None, device=0, engine=None, geno
         print("No splice annotation provided. Will skip splice junction correction.")
     if vcf is not None:
         print("Processing variant file .................")
-        var = build_variant_tables(vcf, int(_opt(options, "maxLenIndel", 5)), genome.index)
+        var = build_variant_tables(vcf, int(_opt(options, "maxLenIndel", 5)), genome.index, read_chroms=chroms)
     else:
         print("No variant file provided. Transcript correction will not be variant-aware.")
+    return sj, var
+
+
+def prep_refs(options, transcripts, sam_header=None, device=0, engine=None, genome=None):
+    """TC.py:203-255: genome, splice annotation restricted to the chromosomes of `transcripts`,
+    variant catalogues.  No temp files are written."""
+    if genome is None:
+        print("Reading genome ..............................")
+        genome = GenomeImage.from_fasta(_opt(options, "refGenome"))
+    chroms = set(t.split("\t")[2] for t in transcripts)
+    sj, var = build_tables(options, chroms, genome)
     return make_refs(genome, sj, var, device=device, engine=engine)
 
 

@@ -170,12 +170,10 @@ def run(options, engines=None):
     validate_chroms(genome, options.variantFile, chroms)
     os.makedirs(options.tmp_dir, exist_ok=True)          # kept for interface compatibility (--tmpDir / --deleteTmp)
 
-    class _ChromLines:                                    # prep_refs only needs the chromosome of each line
-        def __iter__(self):
-            return iter("x\tx\t" + c for c in chroms)
-
-    refs_list = [api.prep_refs(options, _ChromLines(), None, engine=e, genome=genome) for e in engines]
     dry = bool(options.dryRun)
+    # tables: parsed once and uploaded to every GPU; a dry run never opens the SJ / VCF files (TC.py:589-601)
+    sj, var = (None, None) if dry else api.build_tables(options, chroms, genome)
+    refs_list = [api.make_refs(genome, sj, var, engine=e) for e in engines]
     pre = options.outprefix
     files = {"log": open(pre + "_clean.log", "wb"), "te": open(pre + "_clean.TE.log", "wb")}
     if not dry:

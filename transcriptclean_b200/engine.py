@@ -12,7 +12,8 @@ EXPORTS = ["tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_set_optio
            "tc_ctx_load_genome", "tc_ctx_load_junctions", "tc_ctx_load_variants", "tc_correct_batch",
            "tc_dryrun_batch", "tc_batch_upload", "tc_batch_run", "tc_batch_download", "tc_get_timing",
            "tc_ctx_set_pipeline", "tc_sam_parse", "tc_sam_free", "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_render",
-           "tc_sam_rnames", "tc_free", "tc_ctx_set_alphabet", "tc_seq_pack", "tc_seq_packed_size", "tc_sam_pack_seq", "tc_sam_header_lines"]
+           "tc_sam_rnames", "tc_free", "tc_ctx_set_alphabet", "tc_seq_pack", "tc_seq_packed_size", "tc_sam_pack_seq", "tc_sam_header_lines",
+           "tc_vcf_parse", "tc_vcf_tables", "tc_vcf_n_records", "tc_vcf_free", "tc_sj_parse", "tc_sj_tables", "tc_sj_free"]
 
 # status bits (include/tc_b200.h)
 ST_CLASS_MASK, ST_FALLBACK, ST_CIGAR_REWRITTEN = 3, 1 << 2, 1 << 3
@@ -109,8 +110,22 @@ def _declare(lib):
     lib.tc_seq_packed_size.restype = C.c_int64
     lib.tc_sam_pack_seq.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32]
     lib.tc_sam_render.argtypes = [C.c_void_p, C.POINTER(_BatchOut)] + [C.c_int32] * 4 + [C.POINTER(C.c_void_p), C.POINTER(C.c_int64)] * 4 + [C.c_char_p, C.c_int64]
+    lib.tc_vcf_parse.restype = C.c_void_p
+    lib.tc_vcf_parse.argtypes = [C.c_char_p, C.c_int64, C.c_int32, C.POINTER(C.c_char_p), C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int64]
+    lib.tc_vcf_tables.restype = None
+    lib.tc_vcf_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 11
+    lib.tc_vcf_n_records.restype = C.c_int64
+    lib.tc_vcf_n_records.argtypes = [C.c_void_p]
+    lib.tc_vcf_free.restype = None
+    lib.tc_vcf_free.argtypes = [C.c_void_p]
+    lib.tc_sj_parse.restype = C.c_void_p
+    lib.tc_sj_parse.argtypes = [C.c_char_p, C.c_int64, C.c_int32, C.POINTER(C.c_char_p), C.c_void_p, C.c_char_p, C.c_int64]
+    lib.tc_sj_tables.restype = None
+    lib.tc_sj_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 11
+    lib.tc_sj_free.restype = None
+    lib.tc_sj_free.argtypes = [C.c_void_p]
     for f in EXPORTS:
-        if f not in ("tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_stream", "tc_sam_parse", "tc_sam_free",
+        if f not in ("tc_vcf_parse", "tc_vcf_tables", "tc_vcf_n_records", "tc_vcf_free", "tc_sj_parse", "tc_sj_tables", "tc_sj_free", "tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_stream", "tc_sam_parse", "tc_sam_free",
                      "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_rnames", "tc_free", "tc_seq_pack", "tc_seq_packed_size", "tc_sam_header_lines"):
             getattr(lib, f).restype = C.c_int
 
