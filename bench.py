@@ -338,7 +338,7 @@ def main():
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop()
 
-    res = E.BatchResult(out, False, eng.alphabet)        # host copies of the last corrected batch (the dry run below reuses the buffers)
+    res = E.BatchResult(out, False, eng.alphabet, hcols)  # host copies of the last corrected batch (the dry run below reuses the buffers)
     # ---- --dryRun (dryRun(), TC.py:1615-1678: the positional inventory of mismatches / indels) on the same batch
     ms_dry = ms_dry_e2e = 0.0
     if not args.no_dry and not args.resident_only:
@@ -367,14 +367,14 @@ def main():
     st = res.status
     primary = (st & E.ST_CLASS_MASK) == 0
     refreshed = primary & ((st & E.ST_NMMD_DEVICE) != 0)
-    seq_len_out = np.diff(res.seq_off)
     cig_m = np.where(res.cig_op == ord("M"), res.cig_len, 0).astype(np.int64)
     m_per_read = np.add.reduceat(np.concatenate((cig_m, [0])), np.minimum(res.cig_off[:-1], len(cig_m)))
     m_per_read = np.where(np.diff(res.cig_off) > 0, m_per_read, 0)
     # k_emit: SEQ in + SEQ out (16-byte padded rows) + 2-bit genome words under the verified M bases
     # + the planned CIGAR (8 B per op) + MD + the 128-byte plan row.  (TE rows, the CIGAR copy and jM / jI
     # are moved by k_small; the segment lists k_emit reads are not counted.)
-    bytes_emit = (int(cols["seq"].nbytes) + int(res.seq.nbytes) + 0.25 * float(m_per_read[refreshed].sum())
+    seq_out_bytes = int(((res.seq_len.astype(np.int64) + 15) & ~15).sum())
+    bytes_emit = (int(cols["seq"].nbytes) + seq_out_bytes + 0.25 * float(m_per_read[refreshed].sum())
                   + 8.0 * len(res.cig_op) + float(res.md_len.sum()) + 128.0 * int(primary.sum()))
     bytes_plan = (5.0 * len(cols["cig_op"]) + float(cols["md"].nbytes) + 8.0 * len(res.cig_op) + 16.0 * len(res.te)
                   + 96.0 * int(primary.sum()))

@@ -63,7 +63,7 @@ enum {
 enum { TC_C_COR_DEL, TC_C_UNC_DEL, TC_C_VAR_DEL, TC_C_COR_INS, TC_C_UNC_INS, TC_C_VAR_INS,
        TC_C_COR_MM, TC_C_UNC_MM, TC_C_COR_SJ, TC_C_UNC_SJ };
 
-/* one row of the .TE.log (TC.py:911-936, 1017-1046, 1119-1134, 1227-1228, 1650-1668) */
+/* one row of the .TE.log (TC.py:911-936, 1017-1046, 1119-1134, 1227-1228, 1650-1668), decoded */
 typedef struct {
     int32_t a;        /* Mismatch: position; Insertion/Deletion: g-1; NC_SJ: intron start */
     int32_t b;        /* Insertion/Deletion: g+size-1; NC_SJ: intron end; Mismatch: unused */
@@ -73,6 +73,40 @@ typedef struct {
     uint8_t reason;   /* 0 NA 1 VariantMatch 2 TooLarge 3 TooFarFromAnnotJn 4 Other 5 DryRun */
     uint8_t pad;
 } tc_te;
+
+/* The rows cross the ABI as 8-byte words (tc_batch_out.te): bits 0-31 a, 32-55 size, 56-57 type, 58 status, 59-61 reason.
+ * An NC_SJ row is followed by one more word whose low 32 bits hold b; for an Insertion / Deletion b = a + size.
+ * Decodes the row at w[0] and returns the number of words it occupies (1 or 2). */
+static inline int tc_te_decode(const uint64_t* w, tc_te* row) {
+    row->a = (int32_t)(uint32_t)w[0]; row->size = (int32_t)((w[0] >> 32) & 0xffffffu);
+    row->type = (uint8_t)((w[0] >> 56) & 3u); row->status = (uint8_t)((w[0] >> 58) & 1u); row->reason = (uint8_t)((w[0] >> 59) & 7u); row->pad = 0;
+    if (row->type == 3) { row->b = (int32_t)(uint32_t)w[1]; return 2; }
+    row->b = row->type == 0 ? 0 : row->a + row->size;
+    return 1;
+}
+
+/* SEQ delta: the corrected SEQ of a read as an edit script against its INPUT SEQ (the caller holds it), tc_batch_out.delta.
+ * A stream of ops, each a header byte kind << 6 | n6 (n6 < 62: n = n6; 62: n = the next 2 bytes; 63: n = the next 4 bytes,
+ * little endian): kind 0 COPY n input bases, 1 SKIP n input bases, 2 LIT: the n bytes that follow (genome bases, case and
+ * N / IUPAC kept).  delta_len < 0: the SEQ is the input SEQ.  Writes the new SEQ to `out` (capacity out_cap) and returns
+ * its length, or -1 when the script runs past the input, the output or its own end. */
+static inline int64_t tc_seq_apply_delta(const uint8_t* in_seq, int64_t in_len, const uint8_t* delta, int64_t delta_len,
+                                         uint8_t* out, int64_t out_cap) {
+    int64_t q = 0, o = 0, k = 0, j;
+    if (delta_len < 0) { if (in_len > out_cap) return -1; for (j = 0; j < in_len; j++) out[j] = in_seq[j]; return in_len; }
+    while (k < delta_len) {
+        const int kind = delta[k] >> 6; int64_t n = delta[k] & 63; k++;
+        if (n == 62) { if (k + 2 > delta_len) return -1; n = (int64_t)delta[k] | ((int64_t)delta[k + 1] << 8); k += 2; }
+        else if (n == 63) { if (k + 4 > delta_len) return -1; n = (int64_t)delta[k] | ((int64_t)delta[k + 1] << 8) | ((int64_t)delta[k + 2] << 16) | ((int64_t)delta[k + 3] << 24); k += 4; }
+        if (kind == 1) { q += n; continue; }
+        if (o + n > out_cap) return -1;
+        if (kind == 0) { if (q + n > in_len) return -1; for (j = 0; j < n; j++) out[o + j] = in_seq[q + j]; q += n; }
+        else if (kind == 2) { if (k + n > delta_len) return -1; for (j = 0; j < n; j++) out[o + j] = delta[k + j]; k += n; }
+        else return -1;
+        o += n;
+    }
+    return o;
+}
 
 /* Columnar batch of SAM records (what Transcript.__init__ parses, transcript.py:10-72). */
 typedef struct {
@@ -92,8 +126,8 @@ typedef struct {
     const int32_t* ji;        /* integers of the input jI tag, when present */
     /* 4-bit SEQ (optional): when seq_poff != NULL, `seq` holds two bases per byte (low nibble first),
      * codes index the alphabet of tc_ctx_set_alphabet, row i starts at byte seq_poff[i] (a multiple
-     * of 4) and has seq_off[i+1]-seq_off[i] bases; seq_off keeps the dense base offsets.  The
-     * results then carry SEQ packed the same way (tc_batch_out.seq_bits == 4). */
+     * of 4) and has seq_off[i+1]-seq_off[i] bases; seq_off keeps the dense base offsets.  (The results
+     * never carry SEQ rows: the new SEQ comes back as a delta against the input SEQ, tc_batch_out.delta.) */
     const int64_t* seq_poff;  /* n+1, or NULL: SEQ is ASCII */
 } tc_batch_in;
 
@@ -102,11 +136,12 @@ typedef struct {
     const uint32_t* status;   /* n */
     const int32_t* counters;  /* 10 n */
     const int32_t* nm;        /* n; valid with TC_ST_NMMD_DEVICE */
-    const int64_t* seq_off;   /* n+1; rows start at multiples of 16 bytes */
+    const int64_t* delta_off; /* n; start of the read's SEQ delta in delta[] (arbitrary order) */
+    const int32_t* delta_len; /* n; < 0: the SEQ is the input SEQ */
     const int32_t* seq_len;   /* n; length of the read's new SEQ */
-    const uint8_t* seq;
-    const int64_t* cig_off;   /* n+1 */
-    const uint8_t* cig_op;
+    const uint8_t* delta;     /* SEQ deltas (tc_seq_apply_delta) */
+    const int64_t* cig_off;   /* n+1; a read whose CIGAR was not rewritten (no TC_ST_CIGAR_REWRITTEN) has no ops here */
+    const uint8_t* cig_op;    /* op letters; 'd' prints as 'D' (a "D-" of the reference's text CIGAR) */
     const int32_t* cig_len;
     const int64_t* md_off;    /* n; start of the read's MD value in md[] (arbitrary order) */
     const int32_t* md_len;    /* n */
@@ -114,10 +149,8 @@ typedef struct {
     const int64_t* jn_off;    /* n+1; junction objects of the read */
     const int8_t* jm;         /* motif codes */
     const int32_t* ji;        /* 2 per junction */
-    const int64_t* te_off;    /* n+1 */
-    const tc_te* te;          /* in reference order (stage order, positional inside a stage) */
-    int32_t seq_bits;         /* 8: seq is ASCII; 4: two bases per byte, row i starts at byte seq_off[i] / 2 */
-    int32_t reserved;
+    const int64_t* te_off;    /* n+1; in 8-byte words */
+    const uint64_t* te;       /* .TE.log rows as words (tc_te_decode), in reference order (stage order, positional inside a stage) */
 } tc_batch_out;
 
 /* device timing of the last batch call, milliseconds (CUDA events on the context's stream) */

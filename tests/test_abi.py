@@ -9,6 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared():
     text = open(os.path.join(ROOT, "include", "tc_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"static inline[^{]*\{.*?\n\}\n", "", text, flags=re.S)      # header-only helpers (tc_te_decode, tc_seq_apply_delta)
     return sorted(set(re.findall(r"\b(tc_[a-z_0-9]+)\s*\(", text)))
 
 
@@ -51,7 +52,12 @@ def test_header_is_plain_c():
     import tempfile
     from transcriptclean_b200 import engine
     src = ('#include "tc_b200.h"\n#include <stdio.h>\n'
-           'int main(void){ printf("%zu %zu %zu %zu %zu\\n", sizeof(tc_te), sizeof(tc_batch_in), sizeof(tc_batch_out), '
+           'int main(void){ tc_te r; uint64_t w[2] = {((uint64_t)3 << 56) | ((uint64_t)1 << 58) | ((uint64_t)4 << 59) | ((uint64_t)7 << 32) | 1000u, 2000u};\n'
+           ' const uint8_t in[6] = {65, 67, 71, 84, 65, 65}, dl[6] = {(0 << 6) | 2, (1 << 6) | 1, (2 << 6) | 2, 110, 110, (0 << 6) | 3}; uint8_t out[8];\n'
+           ' if (tc_te_decode(w, &r) != 2 || r.a != 1000 || r.b != 2000 || r.size != 7 || r.type != 3 || r.status != 1 || r.reason != 4) return 1;\n'
+           ' if (tc_seq_apply_delta(in, 6, dl, 6, out, 8) != 7 || out[0] != 65 || out[1] != 67 || out[2] != 110 || out[4] != 84 || out[6] != 65) return 2;\n'
+           ' if (tc_seq_apply_delta(in, 6, dl, -1, out, 8) != 6 || tc_seq_apply_delta(in, 6, dl, 6, out, 5) != -1) return 3;\n'
+           ' printf("%zu %zu %zu %zu %zu\\n", sizeof(tc_te), sizeof(tc_batch_in), sizeof(tc_batch_out), '
            'sizeof(tc_options), sizeof(tc_timing)); return 0; }\n')
     d = tempfile.mkdtemp()
     open(d + "/t.c", "w").write(src)

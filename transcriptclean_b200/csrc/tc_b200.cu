@@ -33,7 +33,10 @@ struct OutDev {
     int32_t* nm; int64_t* md_off; int32_t* md_len;
     uint8_t* md_pool; unsigned long long* md_cursor; int64_t md_cap;
     int64_t md_inline;       // MD values of <= 8 bytes live at md_inline + 8*i (no allocation); longer ones in the pool behind
-    uint8_t* seq; uint8_t* cig_op; int32_t* cig_len; tc_te* te; int8_t* jm; int32_t* ji;
+    int64_t* delta_off; int32_t* delta_len;                              // SEQ delta of every read (-1: SEQ is the input SEQ)
+    uint8_t* delta_pool;                                                 // dense: a read's delta lies at its delta_off
+    uint8_t* seq;            // device scratch: SEQ rows of the reads whose NM/MD need the exact walk (never downloaded)
+    uint8_t* cig_op; int32_t* cig_len; u64* te; int8_t* jm; int32_t* ji;
     int32_t* exact_list; unsigned* exact_count;   // reads whose NM/MD need the token-emitting walk (k_nmmd_exact)
 };
 struct InitDev { uint8_t* pool; unsigned long long* cursor; int64_t cap; };
@@ -58,29 +61,46 @@ TC_HD void cig_get(const CigSrc& c, int k, int& op, int32_t& len) {
     else { op = c.op[k]; len = c.len[k]; }
 }
 
+// SEQ delta of one read from its segment list (serial; the warp version is in k_small).  dst == 0: size only.
+TC_HD int64_t delta_encode(const GenomeDev& G, const u64* segs, int ns, uint8_t* dst) {
+    int64_t n = 0, cur = 0;
+    for (int s = 0; s < ns; s++) {
+        const int64_t src = seg_src(segs[s]), len = seg_len(segs[s]);
+        if (len <= 0) continue;
+        if (seg_kind(segs[s]) == 0) {
+            const int64_t gap = src - cur;
+            if (gap > 0) { if (dst) dl_put_hdr(dst + n, DL_SKIP, gap); n += dl_hdr_len(gap); }
+            if (dst) dl_put_hdr(dst + n, DL_COPY, len);
+            n += dl_hdr_len(len); cur = src + len;
+        } else {
+            if (dst) { dl_put_hdr(dst + n, DL_LIT, len); for (int64_t j = 0; j < len; j++) dst[n + dl_hdr_len(len) + j] = genome_byte(G, src + j); }
+            n += dl_hdr_len(len) + len;
+        }
+    }
+    return n;
+}
+
 // TE rows back into the reference's order (stage order: mismatches, insertions, deletions, junctions;
-// positional inside a stage - the planner wrote them positionally), the final CIGAR and the jM / jI
-// snapshot of one read -> their places in the dense outputs.  Thread per read (k_pack): these are a few
-// hundred bytes per read, cheaper here than as warp-wide phases of the output kernel.
+// positional inside a stage - the planner wrote them positionally) as compact words, the final CIGAR and the jM / jI
+// snapshot of one read -> their places in the dense outputs.  Serial twin of k_small (CPU test build).
 TC_HD void small_copies_read(const Params& P, const OutDev& O, int64_t i, int dry) {
-    const BatchDev& B = P.B; const WorkDev& W = P.W;
+    const WorkDev& W = P.W;
     if ((W.status[i] & TC_ST_CLASS_MASK) != 0) return;
     const WsView v = ws_view(W, i);
     const int nte = W.n_te[i];
-    const u64* src = reinterpret_cast<const u64*>(v.te); u64* dst = reinterpret_cast<u64*>(O.te + W.o_te[i]);
-    if (dry) { for (int k = 0; k < 2 * nte; k++) dst[k] = src[k]; return; }
+    u64* dst = O.te + W.o_te[i];
     int slot[4]; slot[0] = 0; slot[1] = W.te_cnt[3 * i]; slot[2] = slot[1] + W.te_cnt[3 * i + 1]; slot[3] = slot[2] + W.te_cnt[3 * i + 2];
+    const int base3 = slot[3]; int k3 = 0;
     for (int k = 0; k < nte; k++) {
-        const u64 a = src[2 * k], b = src[2 * k + 1];
-        const int t = (int)((b >> 32) & 3u);                          // tc_te.type
-        const int s = t == 0 ? slot[0]++ : t == 1 ? slot[1]++ : t == 2 ? slot[2]++ : slot[3]++;
-        dst[2 * s] = a; dst[2 * s + 1] = b;
+        const tc_te r = v.te[k];
+        const u64 w = te_word(r.a, r.size, r.type, r.status, r.reason);
+        if (dry) { dst[k] = w; continue; }                            // (a dry run lists the rows positionally; no junction rows)
+        if (r.type == 3) { dst[base3 + 2 * k3] = w; dst[base3 + 2 * k3 + 1] = (u64)(uint32_t)r.b; k3++; }
+        else dst[slot[r.type]++] = w;
     }
+    if (dry) return;
     const int cb = W.cig_buf[i]; const int64_t oc = W.o_cig[i];
-    if (cb < 0) {
-        const int64_t c0 = B.cig_off[i]; const int n = (int)(B.cig_off[i + 1] - c0);
-        for (int k = 0; k < n; k++) { O.cig_op[oc + k] = B.cig_op[c0 + k]; O.cig_len[oc + k] = B.cig_len[c0 + k]; }
-    } else {
+    if (cb >= 0) {
         const u64* c = v.cig[cb]; const int n = W.n_cig_cur[i];
         for (int k = 0; k < n; k++) { O.cig_op[oc + k] = (uint8_t)cg_op(c[k]); O.cig_len[oc + k] = cg_len(c[k]); }
     }
@@ -182,17 +202,17 @@ static void host_nmmd(const GenomeDev& G, const uint8_t* seq, const CigSrc& cs, 
 
 // Everything that belongs to one batch (or one chunk of a pipelined batch) on the device.
 struct Slot {
-    DevBuf b_seqp, b_seq_poff, o_seqp;   // 4-bit SEQ: packed input rows + their offsets, packed output
+    DevBuf b_seqp, b_seq_poff;           // 4-bit SEQ: packed input rows + their offsets
     DevBuf b_flag, b_chrom, b_pos, b_tags, b_seq_off, b_seq, b_cig_off, b_cig_op, b_cig_len, b_md_off, b_md, b_ji_off, b_ji;
     BatchDev B; int64_t n = 0, n_seq = 0, n_cig = 0, n_md = 0, n_ji = 0, md_base = 0;
     int64_t seq_lo_word = 0, seq_hi_word = 0;       // words of B.seq (as uint32) that may be dereferenced
     DevBuf w_status, w_counters, w_md_init_off, w_md_init_len, w_nm_init, w_n_mdtok, w_md_tok, w_n_jn, w_mflags,
         w_cig_cap, w_seg_cap, w_te_cap, w_ws_off, w_ws, w_cig_buf, w_n_cig_cur, w_seg_buf, w_n_seg_cur, w_n_te,
-        w_te_cnt, w_nm_extra, w_refresh, w_o_seq, w_o_cig, w_o_te, w_o_jn, w_seq_len, w_plan, w_fix_list, init_pool, cursors, scan_tmp;
+        w_te_cnt, w_nm_extra, w_refresh, w_o_seq, w_o_cig, w_o_te, w_o_jn, w_o_delta, w_delta_size, w_seq_len, w_plan, w_fix_list, init_pool, cursors, scan_tmp;
     WorkDev W;
-    DevBuf o_nm, o_md_off, o_md_len, o_md_pool, o_seq, o_cig_op, o_cig_len, o_te, o_jm, o_ji;
-    int64_t tot_seq = 0, tot_cig = 0, tot_te = 0, tot_jn = 0, md_used = 0;
-    int64_t base_seq = 0, base_cig = 0, base_te = 0, base_jn = 0, base_md = 0;   // position of this chunk in the batch output
+    DevBuf o_nm, o_md_off, o_md_len, o_md_pool, o_delta_off, o_delta_len, o_delta_pool, o_seq, o_cig_op, o_cig_len, o_te, o_jm, o_ji;
+    int64_t tot_seq = 0, tot_cig = 0, tot_te = 0, tot_jn = 0, md_used = 0, delta_used = 0;
+    int64_t base_cig = 0, base_te = 0, base_jn = 0, base_md = 0, base_delta = 0;   // position of this chunk in the batch output
     HostBuf h_tot;
     bool ran = false, ran_dry = false;
 #ifndef TC_HOSTSIM
@@ -202,10 +222,10 @@ struct Slot {
         DevBuf* d[] = {&b_flag, &b_chrom, &b_pos, &b_tags, &b_seq_off, &b_seq, &b_cig_off, &b_cig_op, &b_cig_len, &b_md_off, &b_md, &b_ji_off, &b_ji,
                        &w_status, &w_counters, &w_md_init_off, &w_md_init_len, &w_nm_init, &w_n_mdtok, &w_md_tok, &w_n_jn, &w_mflags, &w_cig_cap, &w_seg_cap,
                        &w_te_cap, &w_ws_off, &w_ws, &w_cig_buf, &w_n_cig_cur, &w_seg_buf, &w_n_seg_cur, &w_n_te, &w_te_cnt, &w_nm_extra, &w_refresh,
-                       &w_o_seq, &w_o_cig, &w_o_te, &w_o_jn, &w_seq_len, &w_plan, &w_fix_list, &init_pool, &cursors, &scan_tmp,
-                       &o_nm, &o_md_off, &o_md_len, &o_md_pool, &o_seq, &o_cig_op, &o_cig_len, &o_te, &o_jm, &o_ji};
+                       &w_o_seq, &w_o_cig, &w_o_te, &w_o_jn, &w_o_delta, &w_delta_size, &w_seq_len, &w_plan, &w_fix_list, &init_pool, &cursors, &scan_tmp,
+                       &o_nm, &o_md_off, &o_md_len, &o_md_pool, &o_delta_off, &o_delta_len, &o_delta_pool, &o_seq, &o_cig_op, &o_cig_len, &o_te, &o_jm, &o_ji};
         for (DevBuf* b : d) b->release();
-        b_seqp.release(); b_seq_poff.release(); o_seqp.release();
+        b_seqp.release(); b_seq_poff.release();
         h_tot.release();
     }
 };
@@ -229,10 +249,10 @@ struct tc_ctx {
     int64_t chunk_reads = 131072;   // reads per chunk of the pipelined tc_correct_batch (0 = never pipeline)
     uint8_t alphabet[16] = {'A', 'C', 'G', 'T', 'N', 'a', 'c', 'g', 't', 'n', 0, 0, 0, 0, 0, 0}; int n_alpha = 10;   // 4-bit SEQ codes
     bool genome_byte[256] = {};     // bytes the loaded genome can put into a read
-    bool packed = false;            // the current batch came with 4-bit SEQ (results go back packed)
+    bool packed = false;            // the current batch came with 4-bit SEQ
     bool skip_seq = false;          // dry run over reads that all carry NM and MD: the SEQ column is never read, so it is not uploaded
     // pinned host outputs (whole batch)
-    HostBuf h_status, h_counters, h_nm, h_seq_off, h_seq, h_cig_off, h_cig_op, h_cig_len, h_md_off, h_md_len, h_md,
+    HostBuf h_status, h_counters, h_nm, h_delta_off, h_delta_len, h_delta, h_cig_off, h_cig_op, h_cig_len, h_md_off, h_md_len, h_md,
         h_jn_off, h_jm, h_ji, h_te_off, h_te, h_seq_len;
     tc_timing tm;
 };
@@ -274,22 +294,6 @@ __global__ void __launch_bounds__(256) k_seq_unpack(int64_t n, const int64_t* se
         }
     }
 }
-// ASCII rows -> 4-bit rows over the whole dense output buffer (rows are 16-byte aligned, so packed byte j
-// holds bases 2j and 2j+1 whatever the row): 16 bytes in, 8 bytes out per thread
-__global__ void __launch_bounds__(256) k_seq_pack(int64_t n16, const uint4* seq, uint2* out, Alphabet A) {
-    __shared__ uint8_t inv[256];
-    inv[threadIdx.x] = 0;
-    __syncthreads();
-    if (threadIdx.x < 16 && (threadIdx.x == 0 || A.c[threadIdx.x] != 0)) inv[A.c[threadIdx.x]] = (uint8_t)threadIdx.x;
-    __syncthreads();
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n16; t += (int64_t)gridDim.x * blockDim.x) {
-        const uint4 v = seq[t];
-        auto pk = [&](uint32_t w) { return (uint32_t)inv[w & 255u] | ((uint32_t)inv[(w >> 8) & 255u] << 4) | ((uint32_t)inv[(w >> 16) & 255u] << 8) | ((uint32_t)inv[w >> 24] << 12); };
-        uint2 o; o.x = pk(v.x) | (pk(v.y) << 16); o.y = pk(v.z) | (pk(v.w) << 16);
-        out[t] = o;
-    }
-}
-
 static int be_h2d(tc_ctx* ctx, cudaStream_t st, DevBuf& d, size_t dst_off, const void* src, size_t bytes, size_t slack = 0) {
     CK(d.ensure(dst_off + bytes + slack + 8));
     if (bytes) CK(cudaMemcpyAsync((char*)d.p + dst_off, src, bytes, cudaMemcpyHostToDevice, st));
@@ -391,7 +395,7 @@ void tc_ctx_destroy(tc_ctx* ctx) {
                    &ctx->ins_key, &ctx->ins_size, &ctx->ins_aoff, &ctx->ins_bytes, &ctx->del_key, &ctx->del_size};
     for (DevBuf* b : d) b->release();
     for (int k = 0; k < 2; k++) ctx->slot[k].release();
-    HostBuf* h[] = {&ctx->h_status, &ctx->h_counters, &ctx->h_nm, &ctx->h_seq_off, &ctx->h_seq, &ctx->h_cig_off, &ctx->h_cig_op, &ctx->h_cig_len,
+    HostBuf* h[] = {&ctx->h_status, &ctx->h_counters, &ctx->h_nm, &ctx->h_delta_off, &ctx->h_delta_len, &ctx->h_delta, &ctx->h_cig_off, &ctx->h_cig_op, &ctx->h_cig_len,
                     &ctx->h_md_off, &ctx->h_md_len, &ctx->h_md, &ctx->h_jn_off, &ctx->h_jm, &ctx->h_ji, &ctx->h_te_off, &ctx->h_te, &ctx->h_seq_len};
     for (HostBuf* b : h) b->release();
 #ifndef TC_HOSTSIM
@@ -583,8 +587,8 @@ static int alloc_work(tc_ctx* ctx, Slot& S) {
     CK(S.w_te_cap.ensure(n1 * 4)); CK(S.w_ws_off.ensure(n1 * 8)); CK(S.w_cig_buf.ensure(n1)); CK(S.w_n_cig_cur.ensure(n1 * 4));
     CK(S.w_seg_buf.ensure(n1)); CK(S.w_n_seg_cur.ensure(n1 * 4)); CK(S.w_n_te.ensure(n1 * 4)); CK(S.w_te_cnt.ensure(n1 * 12));
     CK(S.w_nm_extra.ensure(n1 * 4)); CK(S.w_refresh.ensure(n1)); CK(S.w_o_seq.ensure(n1 * 8)); CK(S.w_o_cig.ensure(n1 * 8));
-    CK(S.w_o_te.ensure(n1 * 8)); CK(S.w_o_jn.ensure(n1 * 8)); CK(S.w_seq_len.ensure(n1 * 4)); CK(S.w_plan.ensure(n1 * sizeof(EmitPlan))); CK(S.cursors.ensure(64));
-    CK(S.o_nm.ensure(n1 * 4)); CK(S.o_md_off.ensure(n1 * 8)); CK(S.o_md_len.ensure(n1 * 4));
+    CK(S.w_o_te.ensure(n1 * 8)); CK(S.w_o_jn.ensure(n1 * 8)); CK(S.w_o_delta.ensure(n1 * 8)); CK(S.w_delta_size.ensure(n1 * 4)); CK(S.w_seq_len.ensure(n1 * 4)); CK(S.w_plan.ensure(n1 * sizeof(EmitPlan))); CK(S.cursors.ensure(64));
+    CK(S.o_nm.ensure(n1 * 4)); CK(S.o_md_off.ensure(n1 * 8)); CK(S.o_md_len.ensure(n1 * 4)); CK(S.o_delta_off.ensure(n1 * 8)); CK(S.o_delta_len.ensure(n1 * 4));
     WorkDev& W = S.W;
     W.status = (uint32_t*)S.w_status.p; W.counters = (int32_t*)S.w_counters.p;
     W.md_init_off = (int64_t*)S.w_md_init_off.p; W.md_init_len = (int32_t*)S.w_md_init_len.p; W.nm_init = (int32_t*)S.w_nm_init.p;
@@ -595,6 +599,7 @@ static int alloc_work(tc_ctx* ctx, Slot& S) {
     W.seg_buf = (int8_t*)S.w_seg_buf.p; W.n_seg_cur = (int32_t*)S.w_n_seg_cur.p; W.n_te = (int32_t*)S.w_n_te.p;
     W.te_cnt = (int32_t*)S.w_te_cnt.p; W.nm_extra = (int32_t*)S.w_nm_extra.p; W.refresh = (uint8_t*)S.w_refresh.p;
     W.o_seq = (int64_t*)S.w_o_seq.p; W.o_cig = (int64_t*)S.w_o_cig.p; W.o_te = (int64_t*)S.w_o_te.p; W.o_jn = (int64_t*)S.w_o_jn.p;
+    W.o_delta = (int64_t*)S.w_o_delta.p; W.delta_size = (int32_t*)S.w_delta_size.p;
     W.seq_len_out = (int32_t*)S.w_seq_len.p; W.plan = (EmitPlan*)S.w_plan.p;
     return 0;
 }
@@ -608,8 +613,9 @@ static Params make_params(tc_ctx* ctx, Slot& S) {
 static OutDev make_out(Slot& S, unsigned long long* cur, int64_t md_cap) {
     OutDev O; O.nm = (int32_t*)S.o_nm.p; O.md_off = (int64_t*)S.o_md_off.p; O.md_len = (int32_t*)S.o_md_len.p;
     O.md_pool = (uint8_t*)S.o_md_pool.p - S.base_md; O.md_cursor = cur; O.md_cap = S.base_md + md_cap; O.md_inline = S.base_md;
-    O.seq = (uint8_t*)S.o_seq.p - S.base_seq; O.cig_op = (uint8_t*)S.o_cig_op.p - S.base_cig; O.cig_len = (int32_t*)S.o_cig_len.p - S.base_cig;
-    O.te = (tc_te*)S.o_te.p - S.base_te; O.jm = (int8_t*)S.o_jm.p - S.base_jn; O.ji = (int32_t*)S.o_ji.p - 2 * S.base_jn;
+    O.delta_off = (int64_t*)S.o_delta_off.p; O.delta_len = (int32_t*)S.o_delta_len.p; O.delta_pool = (uint8_t*)S.o_delta_pool.p - S.base_delta;
+    O.seq = (uint8_t*)S.o_seq.p; O.cig_op = (uint8_t*)S.o_cig_op.p - S.base_cig; O.cig_len = (int32_t*)S.o_cig_len.p - S.base_cig;
+    O.te = (u64*)S.o_te.p - S.base_te; O.jm = (int8_t*)S.o_jm.p - S.base_jn; O.ji = (int32_t*)S.o_ji.p - 2 * S.base_jn;
     O.exact_list = (int32_t*)S.w_fix_list.p; O.exact_count = cur ? (unsigned*)(cur + 1) : nullptr;   // (the junction stage is done with the list)
     return O;
 }
@@ -627,10 +633,10 @@ static void host_init_read(Params& P, int64_t i, std::vector<uint8_t>& pool) {
     }
     P.W.status[i] = st;
 }
-// scalar twin of k_emit (test infrastructure)
+// scalar twin of k_small + k_emit (test infrastructure)
 static void host_emit_read(Params& P, OutDev& O, int64_t i, int dry, std::vector<uint8_t>& pool) {
     const BatchDev& B = P.B; const WorkDev& W = P.W;
-    uint32_t st = W.status[i]; O.md_off[i] = 0; O.md_len[i] = 0; O.nm[i] = 0;
+    uint32_t st = W.status[i]; O.md_off[i] = 0; O.md_len[i] = 0; O.nm[i] = 0; O.delta_off[i] = 0; O.delta_len[i] = -1;
     if ((st & TC_ST_CLASS_MASK) != 0) return;
     WsView v = ws_view(W, i);
     small_copies_read(P, O, i, dry);
@@ -638,12 +644,17 @@ static void host_emit_read(Params& P, OutDev& O, int64_t i, int dry, std::vector
     CigSrc cs;
     if (W.cig_buf[i] < 0) { cs.packed = 0; cs.op = B.cig_op + B.cig_off[i]; cs.len = B.cig_len + B.cig_off[i]; cs.n = (int)(B.cig_off[i + 1] - B.cig_off[i]); }
     else { cs.packed = v.cig[W.cig_buf[i]]; cs.op = 0; cs.len = 0; cs.n = W.n_cig_cur[i]; }
-    const uint8_t* in_seq = B.seq + B.seq_off[i]; uint8_t* out_seq = O.seq + W.o_seq[i];
+    const uint8_t* in_seq = B.seq + B.seq_off[i];
+    std::vector<uint8_t> row((size_t)W.seq_len_out[i] + 16);
+    uint8_t* out_seq = row.data();
     if (W.seg_buf[i] < 0) memcpy(out_seq, in_seq, (size_t)(B.seq_off[i + 1] - B.seq_off[i]));
     else { int64_t o = 0; const u64* segs = v.seg[W.seg_buf[i]];
         for (int s = 0; s < W.n_seg_cur[i]; s++) { int64_t src = seg_src(segs[s]), len = seg_len(segs[s]);
             for (int64_t j = 0; j < len; j++) out_seq[o + j] = seg_kind(segs[s]) ? genome_byte(P.G, src + j) : in_seq[src + j];
-            o += len; } }
+            o += len; }
+        const int64_t dn = delta_encode(P.G, segs, W.n_seg_cur[i], nullptr);
+        O.delta_off[i] = W.o_delta[i]; O.delta_len[i] = dn == W.delta_size[i] ? (int32_t)dn : -2;   // (-2: the planner's size is wrong; the renderers refuse it)
+        if (dn == W.delta_size[i]) delta_encode(P.G, segs, W.n_seg_cur[i], O.delta_pool + W.o_delta[i]); }
     if (W.refresh[i]) {
         int nm; bool none; std::string md; host_nmmd(P.G, out_seq, cs, B.chrom[i], B.pos[i], nm, none, md);
         st = (st & ~(uint32_t)TC_ST_NMMD_NONE) | TC_ST_NMMD_DEVICE; if (none) st |= TC_ST_NMMD_NONE;
@@ -665,7 +676,7 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
     CK(S.h_tot.ensure(128)); int64_t* tot = (int64_t*)S.h_tot.p;
     unsigned long long* cur = (unsigned long long*)S.cursors.p;
     Params P = make_params(ctx, S);
-    S.tot_seq = S.tot_cig = S.tot_te = S.tot_jn = 0; S.md_used = 0;
+    S.tot_seq = S.tot_cig = S.tot_te = S.tot_jn = 0; S.md_used = 0; S.delta_used = 0;
     if (n == 0) { S.ran = true; S.ran_dry = dry != 0; return TC_OK; }
 #ifndef TC_HOSTSIM
 #ifndef TC_TPB
@@ -721,14 +732,15 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
         if (timed) CK(cudaEventRecord(ctx->ev[6], st));
         k_sizes<<<gb, TPB, 0, st>>>(P); ctx->tm.launches++; CK(cudaGetLastError());
     }
-    int64_t* sc[4] = {S.W.o_seq, S.W.o_cig, S.W.o_te, S.W.o_jn};
-    const int64_t bases[4] = {S.base_seq, S.base_cig, S.base_te, S.base_jn};
-    for (int k = 0; k < 4; k++) { if (be_zero(ctx, st, sc[k] + n, 8) || be_scan(ctx, st, S.scan_tmp, sc[k], n + 1, bases[k]) || be_read_i64(ctx, st, sc[k] + n, tot + 1 + k)) return TC_E_CUDA; }
+    int64_t* sc[5] = {S.W.o_seq, S.W.o_cig, S.W.o_te, S.W.o_jn, S.W.o_delta};
+    const int64_t bases[5] = {0, S.base_cig, S.base_te, S.base_jn, S.base_delta};   // (SEQ rows are device scratch: slot-local offsets)
+    for (int k = 0; k < 5; k++) { if (be_zero(ctx, st, sc[k] + n, 8) || be_scan(ctx, st, S.scan_tmp, sc[k], n + 1, bases[k]) || be_read_i64(ctx, st, sc[k] + n, tot + 1 + k)) return TC_E_CUDA; }
     k_pack<<<gb, TPB, 0, st>>>(P); ctx->tm.launches++; CK(cudaGetLastError());
     if (be_sync(ctx, st)) return TC_E_CUDA;
-    S.tot_seq = tot[1] - bases[0]; S.tot_cig = tot[2] - bases[1]; S.tot_te = tot[3] - bases[2]; S.tot_jn = tot[4] - bases[3];
+    S.tot_seq = tot[1] - bases[0]; S.tot_cig = tot[2] - bases[1]; S.tot_te = tot[3] - bases[2]; S.tot_jn = tot[4] - bases[3]; S.delta_used = tot[5] - bases[4];
     CK(S.o_seq.ensure((size_t)S.tot_seq + 64)); CK(S.o_cig_op.ensure((size_t)S.tot_cig + 64)); CK(S.o_cig_len.ensure((size_t)S.tot_cig * 4 + 64));
-    CK(S.o_te.ensure((size_t)S.tot_te * 16 + 64)); CK(S.o_jm.ensure((size_t)S.tot_jn + 64)); CK(S.o_ji.ensure((size_t)S.tot_jn * 8 + 64));
+    CK(S.o_te.ensure((size_t)S.tot_te * 8 + 64)); CK(S.o_jm.ensure((size_t)S.tot_jn + 64)); CK(S.o_ji.ensure((size_t)S.tot_jn * 8 + 64));
+    CK(S.o_delta_pool.ensure((size_t)S.delta_used + 64));
     CK(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMIT_SMEM_BYTES));
     int occ = 1; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_emit, WARPS_PER_BLOCK * 32, EMIT_SMEM_BYTES));
     int ge = (int)(wb < (int64_t)nsm * occ ? wb : (int64_t)nsm * occ);
@@ -736,7 +748,7 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
     {   // persistent grid: exactly the resident blocks, so that no block waits for a second wave
         int occ_s = 1; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_small, WARPS_PER_BLOCK * 32, 0));
         const int gs = (int)(wb < (int64_t)nsm * occ_s ? wb : (int64_t)nsm * occ_s);
-        k_small<<<gs, WARPS_PER_BLOCK * 32, 0, st>>>(P, make_out(S, cur, md_cap), dry); ctx->tm.launches++; CK(cudaGetLastError());   // TE rows, CIGAR, jM / jI
+        k_small<<<gs, WARPS_PER_BLOCK * 32, 0, st>>>(P, make_out(S, cur, md_cap), dry); ctx->tm.launches++; CK(cudaGetLastError());   // TE rows, CIGAR, jM / jI, SEQ delta
     }
     if (timed) CK(cudaEventRecord(ctx->ev[7], st));
     for (int attempt = 0;; attempt++) {
@@ -744,7 +756,7 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
         k_set_u64<<<1, 1, 0, st>>>(cur + 1, 0ull);
         k_set_u64<<<1, 1, 0, st>>>(cur, (unsigned long long)(S.base_md + 8 * n));      // the pool starts behind the inline slots
         OutDev O = make_out(S, cur, md_cap);
-        if (!dry) { k_emit<<<ge, WARPS_PER_BLOCK * 32, EMIT_SMEM_BYTES, st>>>(P, O, dry, S.seq_lo_word, S.seq_hi_word); ctx->tm.launches++; }   // (a dry run ends with k_pack)
+        if (!dry) { k_emit<<<ge, WARPS_PER_BLOCK * 32, EMIT_SMEM_BYTES, st>>>(P, O, dry, S.seq_lo_word, S.seq_hi_word); ctx->tm.launches++; }   // (a dry run ends with k_small)
         ctx->tm.launches += 2;
         CK(cudaGetLastError());
         if (timed && attempt == 0) CK(cudaEventRecord(ctx->ev[8], st));
@@ -779,12 +791,14 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
         if (dry) { dry_read(P, i); dry_sizes(P, i); }
         else { plan_read(P, i); junction_read(P, i); sizes_read(P, i); }
     }
-    int64_t* sc[4] = {S.W.o_seq, S.W.o_cig, S.W.o_te, S.W.o_jn};
-    const int64_t bases[4] = {S.base_seq, S.base_cig, S.base_te, S.base_jn};
-    for (int k = 0; k < 4; k++) { sc[k][n] = 0; be_scan(ctx, st, S.scan_tmp, sc[k], n + 1, bases[k]); tot[1 + k] = sc[k][n] - bases[k]; }
-    S.tot_seq = tot[1]; S.tot_cig = tot[2]; S.tot_te = tot[3]; S.tot_jn = tot[4];
+    int64_t* sc[5] = {S.W.o_seq, S.W.o_cig, S.W.o_te, S.W.o_jn, S.W.o_delta};
+    const int64_t bases[5] = {0, S.base_cig, S.base_te, S.base_jn, S.base_delta};
+    for (int k = 0; k < 5; k++) { sc[k][n] = 0; be_scan(ctx, st, S.scan_tmp, sc[k], n + 1, bases[k]); tot[1 + k] = sc[k][n] - bases[k]; }
+    S.tot_seq = tot[1]; S.tot_cig = tot[2]; S.tot_te = tot[3]; S.tot_jn = tot[4]; S.delta_used = tot[5];
     CK(S.o_seq.ensure((size_t)S.tot_seq + 64)); CK(S.o_cig_op.ensure((size_t)S.tot_cig + 64)); CK(S.o_cig_len.ensure((size_t)S.tot_cig * 4 + 64));
-    CK(S.o_te.ensure((size_t)S.tot_te * 16 + 64)); CK(S.o_jm.ensure((size_t)S.tot_jn + 64)); CK(S.o_ji.ensure((size_t)S.tot_jn * 8 + 64));
+    CK(S.o_te.ensure((size_t)S.tot_te * 8 + 64)); CK(S.o_jm.ensure((size_t)S.tot_jn + 64)); CK(S.o_ji.ensure((size_t)S.tot_jn * 8 + 64));
+    CK(S.o_delta_pool.ensure((size_t)S.delta_used + 64));
+    for (int64_t i = 0; i < n; i++) pack_read(P, i);
     OutDev O = make_out(S, nullptr, 0);
     for (int64_t i = 0; i < n; i++) host_emit_read(P, O, i, dry, opool);
     for (int64_t i = 0; i < n; i++) O.md_off[i] += S.base_md;
@@ -800,12 +814,13 @@ static int host_reserve_all(tc_ctx* ctx, Slot& S, int64_t r0, int64_t n_total, b
     const size_t n1 = (size_t)n_total + 1; (void)r0;
     if (host_reserve(ctx, ctx->h_status, n1 * 4, 0, busy) || host_reserve(ctx, ctx->h_counters, n1 * 40, 0, busy) ||
         host_reserve(ctx, ctx->h_te_off, n1 * 8, 0, busy) ||
-        host_reserve(ctx, ctx->h_te, (size_t)(S.base_te + S.tot_te) * 16 + 64, (size_t)S.base_te * 16, busy)) return TC_E_CUDA;
+        host_reserve(ctx, ctx->h_te, (size_t)(S.base_te + S.tot_te) * 8 + 64, (size_t)S.base_te * 8, busy)) return TC_E_CUDA;
     if (dry) return 0;
-    if (host_reserve(ctx, ctx->h_nm, n1 * 4, 0, busy) || host_reserve(ctx, ctx->h_seq_off, n1 * 8, 0, busy) || host_reserve(ctx, ctx->h_seq_len, n1 * 4, 0, busy) ||
+    if (host_reserve(ctx, ctx->h_nm, n1 * 4, 0, busy) || host_reserve(ctx, ctx->h_delta_off, n1 * 8, 0, busy) || host_reserve(ctx, ctx->h_delta_len, n1 * 4, 0, busy) ||
+        host_reserve(ctx, ctx->h_seq_len, n1 * 4, 0, busy) ||
         host_reserve(ctx, ctx->h_cig_off, n1 * 8, 0, busy) || host_reserve(ctx, ctx->h_md_off, n1 * 8, 0, busy) || host_reserve(ctx, ctx->h_md_len, n1 * 4, 0, busy) ||
         host_reserve(ctx, ctx->h_jn_off, n1 * 8, 0, busy) ||
-        host_reserve(ctx, ctx->h_seq, (size_t)(S.base_seq + S.tot_seq) + 64, (size_t)S.base_seq, busy) ||
+        host_reserve(ctx, ctx->h_delta, (size_t)(S.base_delta + S.delta_used) + 64, (size_t)S.base_delta, busy) ||
         host_reserve(ctx, ctx->h_cig_op, (size_t)(S.base_cig + S.tot_cig) + 64, (size_t)S.base_cig, busy) ||
         host_reserve(ctx, ctx->h_cig_len, (size_t)(S.base_cig + S.tot_cig) * 4 + 64, (size_t)S.base_cig * 4, busy) ||
         host_reserve(ctx, ctx->h_md, (size_t)(S.base_md + S.md_used) + 64, (size_t)S.base_md, busy) ||
@@ -814,33 +829,17 @@ static int host_reserve_all(tc_ctx* ctx, Slot& S, int64_t r0, int64_t n_total, b
     return 0;
 }
 
-// new SEQ rows of a slot -> host; packed to 4 bits first when the batch came in that form
-static int seq_download(tc_ctx* ctx, Slot& S, stream_t st) {
-    if (!ctx->packed) return be_d2h(ctx, st, ctx->h_seq, (size_t)S.base_seq, S.o_seq.p, (size_t)S.tot_seq);
-    if (S.tot_seq == 0) return 0;
-    CK(S.o_seqp.ensure((size_t)S.tot_seq / 2 + 64));
-#ifndef TC_HOSTSIM
-    Alphabet A; memcpy(A.c, ctx->alphabet, 16);
-    const int64_t n16 = S.tot_seq / 16; int64_t nb = (n16 + 255) / 256; int g = (int)(nb < 148 * 16 ? nb : 148 * 16);
-    k_seq_pack<<<g, 256, 0, st>>>(n16, (const uint4*)S.o_seq.p, (uint2*)S.o_seqp.p, A); ctx->tm.launches++;
-    CK(cudaGetLastError());
-#else
-    uint8_t inv[256] = {0}; for (int k = 0; k < ctx->n_alpha; k++) inv[ctx->alphabet[k]] = (uint8_t)k;
-    const uint8_t* a = (const uint8_t*)S.o_seq.p; uint8_t* o = (uint8_t*)S.o_seqp.p;
-    for (int64_t j = 0; j < S.tot_seq / 2; j++) o[j] = (uint8_t)(inv[a[2 * j]] | (inv[a[2 * j + 1]] << 4));
-#endif
-    return be_d2h(ctx, st, ctx->h_seq, (size_t)S.base_seq / 2, S.o_seqp.p, (size_t)S.tot_seq / 2);
-}
-
 // enqueues the device-to-host copies of a slot's results into the batch-wide pinned arrays
 static int slot_download(tc_ctx* ctx, Slot& S, int64_t r0, stream_t st) {
     const int64_t n = S.n; const size_t n1 = (size_t)n + 1;
     if (n == 0) return 0;
     if (be_d2h(ctx, st, ctx->h_status, (size_t)r0 * 4, S.W.status, (size_t)n * 4) || be_d2h(ctx, st, ctx->h_counters, (size_t)r0 * 40, S.W.counters, (size_t)n * 40) ||
-        be_d2h(ctx, st, ctx->h_te_off, (size_t)r0 * 8, S.W.o_te, n1 * 8) || be_d2h(ctx, st, ctx->h_te, (size_t)S.base_te * 16, S.o_te.p, (size_t)S.tot_te * 16)) return TC_E_CUDA;
+        be_d2h(ctx, st, ctx->h_te_off, (size_t)r0 * 8, S.W.o_te, n1 * 8) || be_d2h(ctx, st, ctx->h_te, (size_t)S.base_te * 8, S.o_te.p, (size_t)S.tot_te * 8)) return TC_E_CUDA;
     if (S.ran_dry) return 0;
-    if (be_d2h(ctx, st, ctx->h_nm, (size_t)r0 * 4, S.o_nm.p, (size_t)n * 4) || be_d2h(ctx, st, ctx->h_seq_off, (size_t)r0 * 8, S.W.o_seq, n1 * 8) ||
-        be_d2h(ctx, st, ctx->h_seq_len, (size_t)r0 * 4, S.W.seq_len_out, (size_t)n * 4) || seq_download(ctx, S, st) ||
+    if (be_d2h(ctx, st, ctx->h_nm, (size_t)r0 * 4, S.o_nm.p, (size_t)n * 4) || be_d2h(ctx, st, ctx->h_delta_off, (size_t)r0 * 8, S.o_delta_off.p, (size_t)n * 8) ||
+        be_d2h(ctx, st, ctx->h_delta_len, (size_t)r0 * 4, S.o_delta_len.p, (size_t)n * 4) ||
+        be_d2h(ctx, st, ctx->h_delta, (size_t)S.base_delta, S.o_delta_pool.p, (size_t)S.delta_used) ||
+        be_d2h(ctx, st, ctx->h_seq_len, (size_t)r0 * 4, S.W.seq_len_out, (size_t)n * 4) ||
         be_d2h(ctx, st, ctx->h_cig_off, (size_t)r0 * 8, S.W.o_cig, n1 * 8) || be_d2h(ctx, st, ctx->h_cig_op, (size_t)S.base_cig, S.o_cig_op.p, (size_t)S.tot_cig) ||
         be_d2h(ctx, st, ctx->h_cig_len, (size_t)S.base_cig * 4, S.o_cig_len.p, (size_t)S.tot_cig * 4) ||
         be_d2h(ctx, st, ctx->h_md_off, (size_t)r0 * 8, S.o_md_off.p, (size_t)n * 8) || be_d2h(ctx, st, ctx->h_md_len, (size_t)r0 * 4, S.o_md_len.p, (size_t)n * 4) ||
@@ -853,12 +852,12 @@ static void fill_out(tc_ctx* ctx, tc_batch_out* out, int64_t n) {
     memset(out, 0, sizeof(*out));
     out->n_reads = n;
     out->status = (const uint32_t*)ctx->h_status.p; out->counters = (const int32_t*)ctx->h_counters.p; out->nm = (const int32_t*)ctx->h_nm.p;
-    out->seq_off = (const int64_t*)ctx->h_seq_off.p; out->seq_len = (const int32_t*)ctx->h_seq_len.p; out->seq = (const uint8_t*)ctx->h_seq.p;
+    out->delta_off = (const int64_t*)ctx->h_delta_off.p; out->delta_len = (const int32_t*)ctx->h_delta_len.p; out->delta = (const uint8_t*)ctx->h_delta.p;
+    out->seq_len = (const int32_t*)ctx->h_seq_len.p;
     out->cig_off = (const int64_t*)ctx->h_cig_off.p; out->cig_op = (const uint8_t*)ctx->h_cig_op.p; out->cig_len = (const int32_t*)ctx->h_cig_len.p;
     out->md_off = (const int64_t*)ctx->h_md_off.p; out->md_len = (const int32_t*)ctx->h_md_len.p; out->md = (const uint8_t*)ctx->h_md.p;
     out->jn_off = (const int64_t*)ctx->h_jn_off.p; out->jm = (const int8_t*)ctx->h_jm.p; out->ji = (const int32_t*)ctx->h_ji.p;
-    out->te_off = (const int64_t*)ctx->h_te_off.p; out->te = (const tc_te*)ctx->h_te.p;
-    out->seq_bits = ctx->packed ? 4 : 8;
+    out->te_off = (const int64_t*)ctx->h_te_off.p; out->te = (const uint64_t*)ctx->h_te.p;
 }
 
 // notes the SEQ form of the batch; a 4-bit batch needs an alphabet that holds every genome byte
@@ -873,7 +872,7 @@ static int check_packed(tc_ctx* ctx, const tc_batch_in* in) {
     return 0;
 }
 
-static void reset_bases(Slot& S) { S.base_seq = S.base_cig = S.base_te = S.base_jn = S.base_md = 0; }
+static void reset_bases(Slot& S) { S.base_cig = S.base_te = S.base_jn = S.base_md = S.base_delta = 0; }
 
 extern "C" {
 
@@ -961,7 +960,7 @@ static int run_all(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out, int dr
         std::vector<int64_t> cut(1, 0);
         for (int64_t a = 0, k = 0; a < n; k++) { const int64_t sz = k == 0 ? (CH + 3) / 4 : k == 1 ? (CH + 1) / 2 : CH; a = a + sz < n ? a + sz : n; cut.push_back(a); }
         const int64_t nchunk = (int64_t)cut.size() - 1;
-        int64_t bs = 0, bc = 0, bt = 0, bj = 0, bm = 0;
+        int64_t bc = 0, bt = 0, bj = 0, bm = 0, bd = 0;
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));
         const bool trace = getenv("TC_PIPE_TRACE") != nullptr;        // per-chunk stream timestamps on stderr (debugging aid)
         std::vector<cudaEvent_t> tev;
@@ -983,7 +982,7 @@ static int run_all(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out, int dr
             }
             CK(cudaStreamWaitEvent(ctx->stream, S.ev_in, 0));
             if (c >= 2) CK(cudaStreamWaitEvent(ctx->stream, S.ev_out, 0));   // the slot's previous results have left the device
-            S.base_seq = bs; S.base_cig = bc; S.base_te = bt; S.base_jn = bj; S.base_md = bm;
+            S.base_cig = bc; S.base_te = bt; S.base_jn = bj; S.base_md = bm; S.base_delta = bd;
             mark(ctx->stream);
             int rc = slot_run(ctx, S, dry, ctx->stream, false);
             if (rc) return rc;
@@ -995,7 +994,7 @@ static int run_all(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out, int dr
             if (slot_download(ctx, S, r0, ctx->s_out)) return TC_E_CUDA;
             CK(cudaEventRecord(S.ev_out, ctx->s_out));
             mark(ctx->s_out);
-            bs += S.tot_seq; bc += S.tot_cig; bt += S.tot_te; bj += S.tot_jn; bm += S.md_used;
+            bc += S.tot_cig; bt += S.tot_te; bj += S.tot_jn; bm += S.md_used; bd += S.delta_used;
         }
         CK(cudaStreamSynchronize(ctx->s_out));
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));

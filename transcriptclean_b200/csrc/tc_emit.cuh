@@ -2,28 +2,30 @@
 // Part of the CUDA build of tc_b200.cu (included there; not a translation unit of its own).
 #pragma once
 
-// small_copies_read as one warp per read: TE rows into stage order by a ballot partition, CIGAR and
-// jM / jI copies, all from the read's 128-byte plan row.  A light kernel of its own (no shared memory,
-// few registers, 48 warps of an SM resident): these phases are latency, not bytes, and inside
-// k_emit they held its 30 resident warps up for a fifth of its time.
+// small_copies_read as one warp per read: TE rows into stage order by a ballot partition (as compact words), CIGAR and
+// jM / jI copies, and the SEQ delta (the new SEQ as an edit script against the input SEQ, from the read's segment list),
+// all from the read's 128-byte plan row.  A light kernel of its own (no shared memory, few registers, many resident
+// warps): these phases are latency, not bytes, and inside k_emit they held its 30 resident warps up for a fifth of its time.
 #ifndef TC_SMALL_BLOCKS
-#define TC_SMALL_BLOCKS 6
+#define TC_SMALL_BLOCKS 5
 #endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_SMALL_BLOCKS) k_small(Params P, OutDev O, int dry) {
     const int lane = threadIdx.x & 31; const unsigned lt = (1u << lane) - 1u;
     const BatchDev& B = P.B; const WorkDev& W = P.W;
     const int64_t nw = (int64_t)gridDim.x * WARPS_PER_BLOCK;
     for (int64_t i = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); i < B.n; i += nw) {
         const int pw = W.plan[i].w[lane];
-        if (((uint32_t)PF(EP_STATUS) & TC_ST_CLASS_MASK) != 0) continue;
-        const int pflags = PF(EP_FLAGS), cig_cap = PF(EP_CIGCAP), seg_cap = PF(EP_SEGCAP), te_cap = PF(EP_TECAP);
-        const int ncig = PF(EP_NCIG), nte = PF(EP_NTE), nj = PF(EP_NJN);
+        if (((uint32_t)PF(EP_STATUS) & TC_ST_CLASS_MASK) != 0) { if (lane == 0 && !dry) { O.delta_off[i] = 0; O.delta_len[i] = -1; } continue; }
+        const int pflags = PF(EP_FLAGS), cig_cap = PF(EP_CIGCAP);
+        const int ncig = PF(EP_NCIG), nte = PF(EP_NTE), nj = PF(EP_NJN), ns = PF(EP_NSEG);
+        const int seg_cap = EP_SEGCAP_OF(cig_cap, nj), te_cap = EP_TECAP_OF(cig_cap, nj);
         const int te_mm = PF(EP_TEMM), te_ins = PF(EP_TEINS), te_del = PF(EP_TEDEL);
-        const int64_t ws_off = PF64(EP_WS_LO), o_cig = PF64(EP_OCIG_LO), o_te = PF64(EP_OTE_LO), o_jn = PF64(EP_OJN_LO), cig0 = PF64(EP_CIG0_LO);
+        const int64_t ws_off = PF64(EP_WS_LO), o_cig = PF64(EP_OCIG_LO), o_te = PF64(EP_OTE_LO), o_jn = PF64(EP_OJN_LO);
         const u64* const ws = W.ws + ws_off;
         const tc_te* const ws_te = reinterpret_cast<const tc_te*>(ws + 3ll * seg_cap + 3ll * cig_cap);
-        tc_te* dst = O.te + o_te;
-        if (dry) { for (int k = lane; k < nte; k += 32) dst[k] = ws_te[k]; continue; }
+        u64* dst = O.te + o_te;
+        if (dry) { for (int k = lane; k < nte; k += 32) { const tc_te r = ws_te[k]; dst[k] = te_word(r.a, r.size, r.type, r.status, r.reason); } continue; }
         int base0 = 0, base1 = te_mm, base2 = te_mm + te_ins, base3 = te_mm + te_ins + te_del;
         for (int c = 0; c < nte; c += 32) {
             const int k = c + lane; const bool valid = k < nte;
@@ -31,26 +33,62 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_SMALL_BLOCKS) k_small
             if (valid) { r = ws_te[k]; t = r.type; }
             const unsigned m0 = __ballot_sync(FULL, t == 0), m1 = __ballot_sync(FULL, t == 1), m2 = __ballot_sync(FULL, t == 2), m3 = __ballot_sync(FULL, t == 3);
             if (valid) {
-                const int slot = t == 0 ? base0 + __popc(m0 & lt) : t == 1 ? base1 + __popc(m1 & lt) : t == 2 ? base2 + __popc(m2 & lt) : base3 + __popc(m3 & lt);
-                dst[slot] = r;
+                const u64 w = te_word(r.a, r.size, r.type, r.status, r.reason);
+                if (t == 3) { const int slot = base3 + 2 * __popc(m3 & lt); dst[slot] = w; dst[slot + 1] = (u64)(uint32_t)r.b; }   // a junction row: two words
+                else dst[t == 0 ? base0 + __popc(m0 & lt) : t == 1 ? base1 + __popc(m1 & lt) : base2 + __popc(m2 & lt)] = w;
             }
-            base0 += __popc(m0); base1 += __popc(m1); base2 += __popc(m2); base3 += __popc(m3);
+            base0 += __popc(m0); base1 += __popc(m1); base2 += __popc(m2); base3 += 2 * __popc(m3);
         }
-        const int cb = ((pflags >> 2) & 3) - 1;
-        CigSrc cs; cs.n = ncig;
-        if (cb < 0) { cs.packed = 0; cs.op = B.cig_op + cig0; cs.len = B.cig_len + cig0; }
-        else { cs.packed = ws + 3ll * seg_cap + (int64_t)cb * cig_cap; cs.op = 0; cs.len = 0; }
-        uint8_t* dop = O.cig_op + o_cig; int32_t* dl = O.cig_len + o_cig;
-        for (int k = lane; k < ncig; k += 32) { int op; int32_t l; cig_get(cs, k, op, l); dop[k] = (uint8_t)op; dl[k] = l; }
+        const int cb = ((pflags >> 2) & 3) - 1, sb = ((pflags >> 4) & 3) - 1;
+        if (cb >= 0) {                                                 // (an untouched CIGAR is not sent back)
+            const u64* c = ws + 3ll * seg_cap + (int64_t)cb * cig_cap;
+            uint8_t* dop = O.cig_op + o_cig; int32_t* dl = O.cig_len + o_cig;
+            for (int k = lane; k < ncig; k += 32) { const u64 x = c[k]; dop[k] = (uint8_t)cg_op(x); dl[k] = cg_len(x); }
+        }
         if (nj > 0) {
             int8_t* djm = O.jm + o_jn; int32_t* dji = O.ji + 2 * o_jn;
             const int32_t* jn = reinterpret_cast<const int32_t*>(ws + 3ll * seg_cap + 3ll * cig_cap + 2ll * te_cap);
             for (int k = lane; k < nj; k += 32) { const int32_t* r = jn + k * JN_STRIDE; djm[k] = (int8_t)r[7]; dji[2 * k] = r[5]; dji[2 * k + 1] = r[6]; }
         }
+        // ---- SEQ delta (delta_encode in tc_b200.cu is the serial twin): one pass over the segment list.  Its size is known
+        //      (EP_DLEN, kept by the planner) and its place came out of the scans, so every segment's bytes go straight out.
+        const int dlen = PF(EP_DLEN); const int64_t o_dl = PF64_2(EP_ODL_LO, EP_ODL_HI);
+        if (lane == 0) { O.delta_off[i] = o_dl; O.delta_len[i] = dlen; }
+        if (sb < 0 || dlen <= 0) continue;
+        const u64* segs = ws + (int64_t)sb * seg_cap;
+        uint8_t* const dout = O.delta_pool + o_dl;
+        int cur = 0, off0 = 0;                                         // input cursor (end of the latest input slice), bytes so far
+        for (int s0 = 0; s0 < ns; s0 += 32) {
+            const int s = s0 + lane; const bool valid = s < ns;
+            const u64 sg = valid ? segs[s] : 0ull;
+            const int len = valid ? (int)seg_len(sg) : 0; const int64_t src = seg_src(sg);
+            const bool isR = len > 0 && seg_kind(sg) == 0, isG = len > 0 && seg_kind(sg) == 1;
+            const unsigned mR = __ballot_sync(FULL, isR);
+            const int my_end = (int)src + len;                         // (input offsets fit 32 bits: reads are shorter than 2^24 bases)
+            const unsigned prevR = mR & lt;
+            const int prev_end = __shfl_sync(FULL, my_end, prevR ? 31 - __clz(prevR) : lane);
+            const int gap = isR ? (int)src - (prevR ? prev_end : cur) : 0;
+            const int hl = len < 62 ? 1 : len < 65536 ? 3 : 5, hg = gap <= 0 ? 0 : gap < 62 ? 1 : gap < 65536 ? 3 : 5;
+            const int sz = isR ? hg + hl : isG ? hl + len : 0;
+            int tot; const int off = off0 + warp_excl_scan(sz, lane, tot);
+            if (sz > 0 && off + sz <= dlen) {
+                uint8_t* p = dout + off;
+                if (isR) { if (gap > 0) p += dl_put_hdr(p, DL_SKIP, gap); dl_put_hdr(p, DL_COPY, len); }
+                else {                                                 // genome bases, byte exact (Q6): a few per slice, decoded from one pair of plane words
+                    p += dl_put_hdr(p, DL_LIT, len);
+                    if (len <= 16 && !(genome_blk_has_exc(P.G, src) | genome_blk_has_exc(P.G, src + len - 1))) {
+                        const uint32_t* g2 = P.G.g2 + (src >> 4); const uint32_t* lo = P.G.lo1 + (src >> 5);
+                        const uint32_t code = __funnelshift_r(g2[0], g2[1], (int)(src & 15) * 2), low = __funnelshift_r(lo[0], lo[1], (int)(src & 31));
+                        for (int j = 0; j < len; j++) p[j] = (uint8_t)(((0x54474341u >> (((code >> (2 * j)) & 3u) * 8)) & 0xffu) | (((low >> j) & 1u) << 5));
+                    } else for (int j = 0; j < len; j++) p[j] = genome_byte(P.G, src + j);
+                }
+            }
+            if (mR) cur = __shfl_sync(FULL, my_end, 31 - __clz(mR));
+            off0 += tot;
+        }
+        if (off0 != dlen && lane == 0) O.delta_len[i] = -2;            // the planner's size and the list disagree: the host refuses the batch
     }
 }
-
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Output stage: one warp per read.  [seq_lo, seq_hi) = 32-bit words of B.seq that may be read
 // (the batch's SEQ buffer on the device, padded).
@@ -87,7 +125,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_EMIT_BLOCKS) k_emit(P
     int pw = i < B.n ? W.plan[i].w[lane] : 0;
     for (; i < B.n; i += nw) {
         uint32_t st = (uint32_t)PF(EP_STATUS);
-        const int pflags = PF(EP_FLAGS), cig_cap = PF(EP_CIGCAP), seg_cap = PF(EP_SEGCAP), nm_extra = PF(EP_NMEXTRA);
+        const int pflags = PF(EP_FLAGS), cig_cap = PF(EP_CIGCAP), seg_cap = EP_SEGCAP_OF(PF(EP_CIGCAP), PF(EP_NJN)), nm_extra = PF(EP_NMEXTRA);
         const int ncig = PF(EP_NCIG), out_len = PF(EP_OUTLEN), ns = PF(EP_NSEG);
         const int chrom = PF(EP_CHROM); const int64_t pos = PF(EP_POS);
         const int64_t ws_off = PF64(EP_WS_LO), o_seq = PF64(EP_OSEQ_LO);
@@ -224,8 +262,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_EMIT_BLOCKS) k_emit(P
                 else { for (int j = 0; j < len; j++) SM.seq[o + j] = genome_byte_fast(P.G, src + j); }
             }
             __syncwarp();
-            // (E) one coalesced store of the row (rows are padded to 16 bytes)
-            for (int c = lane; c < nchunk; c += 32) reinterpret_cast<uint4*>(out_seq)[c] = *reinterpret_cast<const uint4*>(SM.seq + (c << 4));
+            // (E) the row itself only leaves the SM for the reads whose NM/MD need the exact walk (below): the caller gets
+            //     the new SEQ as a delta against the input SEQ (k_small)
         } else if (sb < 0) {
             for (int64_t j = lane; j < Lq; j += 32) out_seq[j] = in_seq[j];
         } else {
@@ -393,7 +431,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_EMIT_BLOCKS) k_emit(P
                 }
             }
             if (!done) {                                               // a difference to the genome, a literal run, the contig end,
-                if (lane == 0) O.exact_list[atomicAdd(O.exact_count, 1u)] = (int32_t)i;   // a long read: k_nmmd_exact walks it
+                if (fast) {                                            // a long read: k_nmmd_exact walks it, on the row stored here
+                    const int nchunk = (out_len + 15) >> 4;            // (rows are padded to 16 bytes; the tier-1 tables never overlap SM.seq)
+                    for (int c = lane; c < nchunk; c += 32) reinterpret_cast<uint4*>(out_seq)[c] = *reinterpret_cast<const uint4*>(SM.seq + (c << 4));
+                }
+                if (lane == 0) O.exact_list[atomicAdd(O.exact_count, 1u)] = (int32_t)i;
             } else {
                 st = (st & ~(uint32_t)TC_ST_NMMD_NONE) | TC_ST_NMMD_DEVICE;
                 if (lane == 0) { O.nm[i] = nm + nm_extra; O.md_off[i] = off < 0 ? 0 : off; O.md_len[i] = off < 0 ? 0 : len; W.status[i] = st; }

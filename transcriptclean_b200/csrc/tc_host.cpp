@@ -239,12 +239,27 @@ struct Out {
 struct Comp { uint8_t t[256]; Comp() { for (int k = 0; k < 256; k++) t[k] = (uint8_t)k; const char* a = "ACGTNacgtn*"; const char* b = "TGCANtgcan*"; for (int k = 0; a[k]; k++) t[(uint8_t)a[k]] = (uint8_t)b[k]; } };
 const Comp COMP;
 
+// tc_seq_apply_delta (include/tc_b200.h) with block copies
+int64_t apply_delta(const uint8_t* in, int64_t in_len, const uint8_t* dl, int64_t dn, uint8_t* out, int64_t cap) {
+    if (dn < 0) { if (in_len > cap) return -1; memcpy(out, in, (size_t)in_len); return in_len; }
+    int64_t q = 0, o = 0, k = 0;
+    while (k < dn) {
+        const int kind = dl[k] >> 6; int64_t n = dl[k] & 63; k++;
+        if (n == 62) { if (k + 2 > dn) return -1; n = (int64_t)dl[k] | ((int64_t)dl[k + 1] << 8); k += 2; }
+        else if (n == 63) { if (k + 4 > dn) return -1; n = (int64_t)dl[k] | ((int64_t)dl[k + 1] << 8) | ((int64_t)dl[k + 2] << 16) | ((int64_t)dl[k + 3] << 24); k += 4; }
+        if (kind == 1) { q += n; continue; }
+        if (o + n > cap) return -1;
+        if (kind == 0) { if (q + n > in_len) return -1; memcpy(out + o, in + q, (size_t)n); q += n; }
+        else if (kind == 2) { if (k + n > dn) return -1; memcpy(out + o, dl + k, (size_t)n); k += n; }
+        else return -1;
+        o += n;
+    }
+    return o;
+}
+
 void render_range(const tc_sam* S, const tc_batch_out* R, int64_t a, int64_t b, bool primary_only, bool canon_only, bool dry,
-                  Out& sam, Out& fa, Out& lg, Out& te) {
+                  Out& sam, Out& fa, Out& lg, Out& te, int64_t& bad_delta) {
     const char* T = S->text;
-    std::string useq;
-    uint16_t lut16[256];
-    for (int t = 0; t < 256; t++) lut16[t] = (uint16_t)(S->alphabet[t & 15] | (S->alphabet[t >> 4] << 8));
     for (int64_t i = a; i < b; i++) {
         const uint32_t st = R->status[i]; const int cls = (int)(st & TC_ST_CLASS_MASK);
         const Span q = S->f[0][i], ch = S->f[2][i];
@@ -259,8 +274,8 @@ void render_range(const tc_sam* S, const tc_batch_out* R, int64_t a, int64_t b, 
         }
         const int64_t t0 = R->te_off[i], t1 = R->te_off[i + 1];
         te.need((size_t)(t1 - t0) * ((size_t)q.n + (size_t)ch.n + 96));
-        for (int64_t k = t0; k < t1; k++) {
-            const tc_te& r = R->te[k];
+        for (int64_t k = t0; k < t1;) {
+            tc_te r; k += tc_te_decode(R->te + k, &r);
             te.put(T + q.s, (size_t)q.n); te.ch('\t');
             te.put(T + ch.s, (size_t)ch.n); te.ch('_'); te.num(r.a);
             if (r.type != 0) { te.ch('_'); te.num(r.b); }
@@ -285,15 +300,15 @@ void render_range(const tc_sam* S, const tc_batch_out* R, int64_t a, int64_t b, 
             }
         } else add_span(S->cigar[i]);
         add_span(S->f[6][i]); add_span(S->f[7][i]); add_span(S->f[8][i]);
-        const uint8_t* sq = R->seq + R->seq_off[i];
-        if (R->seq_bits == 4) {                                       // two bases per byte, row at seq_off / 2
-            const uint8_t* pk = R->seq + R->seq_off[i] / 2;
-            useq.resize((size_t)sl + 2);
-            uint16_t* w = reinterpret_cast<uint16_t*>(&useq[0]);
-            for (int32_t k = 0; k < (sl + 1) / 2; k++) w[k] = lut16[pk[k]];
-            sq = reinterpret_cast<const uint8_t*>(useq.data());
+        // SEQ: the input SEQ with the read's delta applied (include/tc_b200.h), written in place
+        const uint8_t* sq = reinterpret_cast<const uint8_t*>(&sam.buf[sam.n]) + (sam.n > row0 && sl > 0 ? 1 : 0);
+        if (sl > 0) {
+            if (sam.n > row0) sam.ch('\t');
+            const uint8_t* in = S->seq.data() + S->seq_off[i]; const int64_t in_len = S->seq_off[i + 1] - S->seq_off[i];
+            uint8_t* d = reinterpret_cast<uint8_t*>(&sam.buf[sam.n]);
+            if (R->delta_len[i] < -1 || apply_delta(in, in_len, R->delta + R->delta_off[i], R->delta_len[i], d, sl) != sl) { bad_delta = i; return; }
+            sam.n += (size_t)sl;
         }
-        add((const char*)sq, sl);
         add("*", 1);
         for (int64_t k = S->other_off[i]; k < S->other_off[i + 1]; k++) {
             // otherFields is one tab-joined field: dropped only when the whole join is empty
@@ -546,13 +561,17 @@ int tc_sam_render(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_
     if (S->n < 4096) T = 1;
     static thread_local std::vector<Out> ps, pf, pl, pt;              // per calling thread, storage kept between batches
     for (auto* v : {&ps, &pf, &pl, &pt}) { if (v->size() < (size_t)T) v->resize((size_t)T); for (auto& x : *v) x.clear(); }
-    std::vector<std::thread> th;
+    std::vector<std::thread> th; std::vector<int64_t> bad((size_t)T, -1);
     for (int k = 0; k < T; k++) {
         const int64_t a = S->n * k / T, b = S->n * (k + 1) / T;
         th.emplace_back(render_range, S, R, a, b, primary_only != 0, canon_only != 0, dry != 0, std::ref(ps[(size_t)k]), std::ref(pf[(size_t)k]),
-                        std::ref(pl[(size_t)k]), std::ref(pt[(size_t)k]));
+                        std::ref(pl[(size_t)k]), std::ref(pt[(size_t)k]), std::ref(bad[(size_t)k]));
     }
     for (auto& t : th) t.join();
+    for (int k = 0; k < T; k++) if (bad[(size_t)k] >= 0) {
+        set_err(err, err_cap, "read " + std::string(S->text + S->f[0][bad[(size_t)k]].s, (size_t)S->f[0][bad[(size_t)k]].n) + ": the SEQ delta does not fit the input SEQ (result of another batch?)");
+        return TC_E_ARG;
+    }
     const bool tm = getenv("TC_HOST_TIMING") != nullptr;
     auto now = [] { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
     const double t_r = now();

@@ -20,6 +20,23 @@ __device__ __forceinline__ int64_t w_seg_total(const u64* s, int n, int lane) {
     for (int j = lane; j < n; j += 32) t += (int)seg_len(s[j]);
     return (int64_t)__reduce_add_sync(FULL, t);
 }
+// dl_list_size (tc_plan.cuh) across the lanes: bytes of the SEQ delta of a segment list
+__device__ int w_delta_size(const u64* s, int n, int lane) {
+    const unsigned lt = (1u << lane) - 1u;
+    int total = 0, cur = 0;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane; const u64 sg = j < n ? s[j] : 0ull;
+        const int len = j < n ? (int)seg_len(sg) : 0; const int src = (int)seg_src(sg);
+        const bool isR = len > 0 && seg_kind(sg) == 0, isG = len > 0 && seg_kind(sg) == 1;
+        const unsigned mR = __ballot_sync(FULL, isR), prevR = mR & lt;
+        const int my_end = src + len;
+        const int prev_end = __shfl_sync(FULL, my_end, prevR ? 31 - __clz(prevR) : lane);
+        const int gap = isR ? src - (prevR ? prev_end : cur) : 0;
+        total += isR ? (gap > 0 ? dl_hdr_len(gap) : 0) + dl_hdr_len(len) : isG ? dl_hdr_len(len) + len : 0;
+        if (mR) cur = __shfl_sync(FULL, my_end, 31 - __clz(mR));
+    }
+    return __reduce_add_sync(FULL, total);
+}
 __device__ __forceinline__ int64_t w_cig_qlen(const u64* c, int n, int lane) {                    // tr.py:591-605
     int t = 0;
     for (int k = lane; k < n; k += 32) { const int op = cg_op(c[k]); if (op == 'M' || op == 'S' || op == 'I') t += cg_len(c[k]); }
@@ -320,11 +337,13 @@ __device__ void junction_fix_warp(const Params& P, int64_t i, int lane) {
     } else {
         if (any_ok) st |= TC_ST_CIGAR_REWRITTEN | TC_ST_JM_DEVICE | TC_ST_JI_DEVICE;
         if (unsupported) st |= TC_ST_ERR_INTRON;
+        const int dsize = any_ok ? w_delta_size(v.seg[sb], ns, lane) : 0;
         if (lane == 0) {
             C[TC_C_COR_SJ] = cJ; C[TC_C_UNC_SJ] = uJ;
             W.n_te[i] = nte;
             if (any_ok) {
                 W.cig_buf[i] = (int8_t)cb; W.seg_buf[i] = (int8_t)sb; W.n_cig_cur[i] = nc; W.n_seg_cur[i] = ns; W.seq_len_out[i] = (int32_t)seqlen;
+                W.delta_size[i] = dsize;
                 W.refresh[i] = 1; W.nm_extra[i] = 0;
             }
         }

@@ -185,6 +185,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_nmmd_exact(Params P, O
         const int32_t* w = P.W.plan[i].w;
         const int64_t o_seq = ((int64_t)w[EP_OSEQ_HI] << 32) | (uint32_t)w[EP_OSEQ_LO], o_cig = ((int64_t)w[EP_OCIG_HI] << 32) | (uint32_t)w[EP_OCIG_LO];
         CigSrc cs; cs.packed = 0; cs.op = O.cig_op + o_cig; cs.len = O.cig_len + o_cig; cs.n = w[EP_NCIG];
+        if (((w[EP_FLAGS] >> 2) & 3) == 0) {                           // the input CIGAR (never copied to the outputs)
+            const int64_t c0 = ((int64_t)w[EP_CIG0_HI] << 32) | (uint32_t)w[EP_CIG0_LO];
+            cs.op = P.B.cig_op + c0; cs.len = P.B.cig_len + c0;
+        }
         int nm, len; int64_t off; bool none;
         nmmd_to_pool<true>(P.G, O.seq + o_seq, lut, cs, w[EP_CHROM], (int64_t)w[EP_POS], lane, O.md_cursor, O.md_cap, O.md_pool, O.md_inline + 8 * i, nm, len, off, none);
         uint32_t st = ((uint32_t)w[EP_STATUS] & ~(uint32_t)TC_ST_NMMD_NONE) | TC_ST_NMMD_DEVICE;

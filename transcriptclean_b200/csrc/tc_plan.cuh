@@ -71,11 +71,14 @@ struct BatchDev {
 // everything tc_emit needs to know about a read: one 128-byte row, one word per lane.
 // Words 0-15 are written by sizes_read, 16-31 by pack_read once the output offsets are scanned.
 struct alignas(16) EmitPlan { int32_t w[32]; };
-enum { EP_FLAGS, EP_NCIG, EP_NSEG, EP_NTE, EP_TEMM, EP_TEINS, EP_TEDEL, EP_NJN, EP_OUTLEN, EP_NMEXTRA, EP_CIGCAP, EP_SEGCAP, EP_TECAP,
+enum { EP_FLAGS, EP_NCIG, EP_NSEG, EP_NTE, EP_TEMM, EP_TEINS, EP_TEDEL, EP_NJN, EP_OUTLEN, EP_NMEXTRA, EP_CIGCAP, EP_DLEN, EP_ODL_LO,
        EP_STATUS, EP_CHROM, EP_POS,
        EP_WS_LO = 16, EP_WS_HI, EP_OSEQ_LO, EP_OSEQ_HI, EP_OCIG_LO, EP_OCIG_HI, EP_OTE_LO, EP_OTE_HI, EP_OJN_LO, EP_OJN_HI,
-       EP_INB_LO, EP_INB_HI, EP_LQ, EP_CIG0_LO, EP_CIG0_HI };
-// EP_FLAGS: bit0 refresh, bits 2-3 cig_buf+1, bits 4-5 seg_buf+1
+       EP_INB_LO, EP_INB_HI, EP_LQ, EP_CIG0_LO, EP_CIG0_HI, EP_ODL_HI };
+// EP_FLAGS: bit0 refresh, bits 2-3 cig_buf+1, bits 4-5 seg_buf+1.  EP_DLEN: bytes of the SEQ delta; EP_ODL: its place in the delta output.
+// The other two list capacities follow from EP_CIGCAP and EP_NJN (measure_read): segments cc + 2 nj + 2, TE rows cc - nj - 1.
+#define EP_SEGCAP_OF(cc, nj) ((cc) + 2 * (nj) + 2)
+#define EP_TECAP_OF(cc, nj) ((cc) - (nj) - 1)
 
 // per-read state (structure of arrays) + workspace
 struct WorkDev {
@@ -95,7 +98,8 @@ struct WorkDev {
     int32_t* n_te; int32_t* te_cnt;         // te_cnt: 3 per read (mismatch, insertion, deletion rows)
     int32_t* nm_extra; uint8_t* refresh;
     // exact output sizes, turned into offsets (n+1) by exclusive scans
-    int64_t *o_seq, *o_cig, *o_te, *o_jn;
+    int64_t *o_seq, *o_cig, *o_te, *o_jn, *o_delta;
+    int32_t* delta_size;     // bytes of the read's SEQ delta (kept current by plan_read / the junction rescue, like seq_len_out)
     EmitPlan* plan;
     int32_t* seq_len_out;    // exact length of the new SEQ (o_seq offsets are padded to 16 bytes)
 };
@@ -120,6 +124,37 @@ TC_HD int64_t seg_len(u64 s) { return (int64_t)(s & SEG_LEN_MASK); }
 TC_HD u64 cg_make(int op, int32_t len) { return ((u64)(uint32_t)op << 32) | (uint32_t)len; }
 TC_HD int cg_op(u64 c) { return (int)(c >> 32); }
 TC_HD int32_t cg_len(u64 c) { return (int32_t)(uint32_t)c; }
+
+// .TE.log row as it crosses the ABI (include/tc_b200.h, tc_te_decode): a | size << 32 | type << 56 | status << 58 | reason << 59;
+// a junction row (type 3) is followed by one more word that holds b.  (Insertion / Deletion: b = a + size.)
+TC_HD u64 te_word(int32_t a, int32_t size, int type, int status, int reason) {
+    return (u64)(uint32_t)a | ((u64)((uint32_t)size & 0xffffffu) << 32) | ((u64)(type & 3) << 56) | ((u64)(status & 1) << 58) | ((u64)(reason & 7) << 59);
+}
+// New SEQ as an edit script against the input SEQ (include/tc_b200.h, "SEQ delta"): ops COPY n / SKIP n / LIT n + n bytes;
+// header byte = kind << 6 | n6, n6 < 62: n = n6; 62: n in the next 2 bytes; 63: n in the next 4 bytes (little endian).
+enum { DL_COPY = 0, DL_SKIP = 1, DL_LIT = 2 };
+TC_HD int dl_hdr_len(int64_t n) { return n < 62 ? 1 : n < 65536 ? 3 : 5; }
+TC_HD int dl_put_hdr(uint8_t* p, int kind, int64_t n) {
+    if (n < 62) { p[0] = (uint8_t)((kind << 6) | (int)n); return 1; }
+    if (n < 65536) { p[0] = (uint8_t)((kind << 6) | 62); p[1] = (uint8_t)(n & 255); p[2] = (uint8_t)(n >> 8); return 3; }
+    p[0] = (uint8_t)((kind << 6) | 63); p[1] = (uint8_t)(n & 255); p[2] = (uint8_t)((n >> 8) & 255); p[3] = (uint8_t)((n >> 16) & 255); p[4] = (uint8_t)((n >> 24) & 255);
+    return 5;
+}
+
+// bytes one segment adds to the delta; `in_end` = end of the latest input slice before it (updated)
+TC_HD int dl_seg_size(u64 sg, int64_t& in_end) {
+    const int64_t len = seg_len(sg);
+    if (len <= 0) return 0;
+    if (seg_kind(sg)) return dl_hdr_len(len) + (int)len;
+    const int64_t src = seg_src(sg), gap = src - in_end;
+    in_end = src + len;
+    return (gap > 0 ? dl_hdr_len(gap) : 0) + dl_hdr_len(len);
+}
+TC_HD int64_t dl_list_size(const u64* segs, int ns) {
+    int64_t n = 0, in_end = 0;
+    for (int s = 0; s < ns; s++) n += dl_seg_size(segs[s], in_end);
+    return n;
+}
 
 struct WsView { u64* cig[3]; u64* seg[3]; tc_te* te; int32_t* jn; };
 // junction record, 8 int32: b0 b1 start end code snap_ji0 snap_ji1 snap_jm
@@ -352,7 +387,7 @@ TC_HD void measure_read(const Params& P, int64_t i) {
     // (the ten counters of every read start at -1 = "NA": one memset of the whole array by the caller)
     W.cig_buf[i] = -1; W.seg_buf[i] = -1; W.n_cig_cur[i] = 0; W.n_seg_cur[i] = 0;
     W.n_te[i] = 0; W.te_cnt[3 * i] = W.te_cnt[3 * i + 1] = W.te_cnt[3 * i + 2] = 0;
-    W.nm_extra[i] = 0; W.refresh[i] = 0;
+    W.nm_extra[i] = 0; W.refresh[i] = 0; W.delta_size[i] = 0;
     W.n_mdtok[i] = 0; W.n_jn[i] = 0; W.mflags[i] = 0;
     W.cig_cap[i] = W.seg_cap[i] = W.te_cap[i] = 0;
     if ((st & TC_ST_CLASS_MASK) != 0) { W.ws_off[i] = 0; return; }
@@ -388,6 +423,7 @@ TC_HD void measure_read(const Params& P, int64_t i) {
 
 struct Emit {                 // newCIGAR / newSeq / MVal bookkeeping (endMatch, TC.py:1171-1183)
     u64* cig; int nc; u64* seg; int ns; int32_t run; int64_t seqlen; u64 last;   // last = seg[ns - 1]
+    int64_t dsz, in_end;      // bytes of the SEQ delta of the finished segments; end of the latest input slice among them
     TC_HD void match(int32_t n) { run += n; }
     TC_HD void flush() { if (run > 0) { cig[nc++] = cg_make('M', run); run = 0; } }
     TC_HD void op(int o, int32_t n) { flush(); cig[nc++] = cg_make(o, n); }
@@ -397,8 +433,10 @@ struct Emit {                 // newCIGAR / newSeq / MVal bookkeeping (endMatch,
         if (ns > 0 && seg_kind(last) == kind && seg_src(last) + seg_len(last) == src && seg_len(last) + len <= (int64_t)SEG_LEN_MASK) {
             last = seg_make(kind, seg_src(last), seg_len(last) + len); seg[ns - 1] = last; return;
         }
+        if (ns > 0) dsz += dl_seg_size(last, in_end);           // the previous segment is final now
         last = seg_make(kind, src, len); seg[ns++] = last;
     }
+    TC_HD int64_t delta_bytes() { int64_t e = in_end; return ns > 0 ? dsz + dl_seg_size(last, e) : dsz; }
 };
 
 TC_HD void te_put(tc_te* te, int& n, int type, int32_t a, int32_t b, int32_t size, int status, int reason) {
@@ -437,7 +475,7 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
         return;
     }
     WsView v = ws_view(W, i);
-    Emit E; E.cig = v.cig[0]; E.nc = 0; E.seg = v.seg[0]; E.ns = 0; E.run = 0; E.seqlen = 0; E.last = 0;
+    Emit E; E.cig = v.cig[0]; E.nc = 0; E.seg = v.seg[0]; E.ns = 0; E.run = 0; E.seqlen = 0; E.last = 0; E.dsz = 0; E.in_end = 0;
     const int chrom = B.chrom[i];
     const int64_t goff = P.G.chrom_off[chrom] - 1;       // plane index of 1-based position p is goff + p
     const uint8_t* seq = B.seq + B.seq_off[i];
@@ -530,6 +568,7 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
     if (indel) { C[TC_C_COR_INS] = cI; C[TC_C_UNC_INS] = uI; C[TC_C_VAR_INS] = vI;
                  C[TC_C_COR_DEL] = cD; C[TC_C_UNC_DEL] = uD; C[TC_C_VAR_DEL] = vD; }
     W.cig_buf[i] = 0; W.n_cig_cur[i] = E.nc; W.seg_buf[i] = 0; W.n_seg_cur[i] = E.ns; W.seq_len_out[i] = (int32_t)E.seqlen;
+    W.delta_size[i] = (int32_t)E.delta_bytes();
     W.n_te[i] = nte; W.te_cnt[3 * i] = nteM; W.te_cnt[3 * i + 1] = nteI; W.te_cnt[3 * i + 2] = nteD;
     // NM/MD refresh points (Q7): end of correctDeletions when the CIGAR holds a D, else end of
     // correctMismatches; insertion removal never refreshes, so NM keeps counting removed bases.
@@ -906,6 +945,7 @@ TC_HD void junction_fix_read(const Params& P, int64_t i) {
                 W.n_te[i] = nte;
                 if (any_ok) {
                     W.cig_buf[i] = (int8_t)cb; W.seg_buf[i] = (int8_t)sb; W.n_cig_cur[i] = nc; W.n_seg_cur[i] = ns; W.seq_len_out[i] = (int32_t)seqlen;
+                    W.delta_size[i] = (int32_t)dl_list_size(v.seg[sb], ns);
                     W.refresh[i] = 1; W.nm_extra[i] = 0;
                     st |= TC_ST_CIGAR_REWRITTEN | TC_ST_JM_DEVICE | TC_ST_JI_DEVICE;
                 }
@@ -924,23 +964,25 @@ TC_HD void junction_read(const Params& P, int64_t i) { if (junction_init_read(P,
 TC_HD void sizes_read(const Params& P, int64_t i) {
     const BatchDev& B = P.B; const WorkDev& W = P.W;
     uint32_t st = W.status[i];
-    if ((st & TC_ST_CLASS_MASK) != 0) { W.o_seq[i] = W.o_cig[i] = W.o_te[i] = W.o_jn[i] = 0; W.seq_len_out[i] = 0; W.plan[i].w[EP_STATUS] = (int32_t)st; return; }
+    if ((st & TC_ST_CLASS_MASK) != 0) { W.o_seq[i] = W.o_cig[i] = W.o_te[i] = W.o_jn[i] = W.o_delta[i] = 0; W.seq_len_out[i] = 0; W.plan[i].w[EP_STATUS] = (int32_t)st; return; }
     int64_t sl;
     if (W.seg_buf[i] < 0) sl = B.seq_off[i + 1] - B.seq_off[i];
     else sl = W.seq_len_out[i];                    // kept current by plan_read / the junction rescue (the sum of the segment lengths)
     W.o_seq[i] = (sl + 15) & ~15ll;                 // 16-byte aligned rows: tc_emit stores whole uint4
     W.seq_len_out[i] = (int32_t)sl;
     const int ncig = W.cig_buf[i] < 0 ? (int)(B.cig_off[i + 1] - B.cig_off[i]) : W.n_cig_cur[i];
-    W.o_cig[i] = ncig;
-    W.o_te[i] = W.n_te[i];
+    W.o_cig[i] = W.cig_buf[i] < 0 ? 0 : ncig;      // an untouched CIGAR is not sent back: the caller still holds its text
+    W.o_te[i] = 2 * W.n_te[i] - (W.te_cnt[3 * i] + W.te_cnt[3 * i + 1] + W.te_cnt[3 * i + 2]);   // 8-byte words: a junction row takes two (tc_te_word)
     W.o_jn[i] = W.n_jn[i];
+    const int32_t dlen = W.seg_buf[i] < 0 ? -1 : W.delta_size[i];     // -1: the SEQ is the input SEQ
+    W.o_delta[i] = dlen < 0 ? 0 : dlen;
     EmitPlan ep;
     for (int k = 0; k < 16; k++) ep.w[k] = 0;
     ep.w[EP_FLAGS] = (W.refresh[i] ? 1 : 0) | ((W.cig_buf[i] + 1) << 2) | ((W.seg_buf[i] + 1) << 4);
     ep.w[EP_NCIG] = ncig; ep.w[EP_NSEG] = W.n_seg_cur[i]; ep.w[EP_NTE] = W.n_te[i];
     ep.w[EP_TEMM] = W.te_cnt[3 * i]; ep.w[EP_TEINS] = W.te_cnt[3 * i + 1]; ep.w[EP_TEDEL] = W.te_cnt[3 * i + 2];
     ep.w[EP_NJN] = W.n_jn[i]; ep.w[EP_OUTLEN] = (int32_t)sl; ep.w[EP_NMEXTRA] = W.nm_extra[i];
-    ep.w[EP_CIGCAP] = W.cig_cap[i]; ep.w[EP_SEGCAP] = W.seg_cap[i]; ep.w[EP_TECAP] = W.te_cap[i];
+    ep.w[EP_CIGCAP] = W.cig_cap[i]; ep.w[EP_DLEN] = dlen;
     ep.w[EP_STATUS] = (int32_t)st; ep.w[EP_CHROM] = B.chrom[i]; ep.w[EP_POS] = B.pos[i];
 #ifndef TC_HOSTSIM
     int4* dst = reinterpret_cast<int4*>(W.plan[i].w);
@@ -955,10 +997,10 @@ TC_HD void sizes_read(const Params& P, int64_t i) {
 
 TC_HD void dry_sizes(const Params& P, int64_t i) {
     const WorkDev& W = P.W;
-    W.o_seq[i] = W.o_cig[i] = W.o_jn[i] = 0; W.o_te[i] = W.n_te[i]; W.seq_len_out[i] = 0;
+    W.o_seq[i] = W.o_cig[i] = W.o_jn[i] = W.o_delta[i] = 0; W.o_te[i] = W.n_te[i]; W.seq_len_out[i] = 0;
     EmitPlan ep;
     for (int k = 0; k < 16; k++) ep.w[k] = 0;
-    ep.w[EP_NTE] = W.n_te[i]; ep.w[EP_CIGCAP] = W.cig_cap[i]; ep.w[EP_SEGCAP] = W.seg_cap[i]; ep.w[EP_TECAP] = W.te_cap[i];
+    ep.w[EP_NTE] = W.n_te[i]; ep.w[EP_CIGCAP] = W.cig_cap[i]; ep.w[EP_NJN] = W.n_jn[i]; ep.w[EP_DLEN] = -1;
     ep.w[EP_STATUS] = (int32_t)W.status[i];
     for (int k = 0; k < 16; k++) W.plan[i].w[k] = ep.w[k];
 }
@@ -976,7 +1018,8 @@ TC_HD void pack_read(const Params& P, int64_t i) {
     w[EP_INB_LO] = (int32_t)(uint32_t)ib; w[EP_INB_HI] = (int32_t)(ib >> 32);
     w[EP_LQ] = (int32_t)(B.seq_off[i + 1] - ib);
     w[EP_CIG0_LO] = (int32_t)(uint32_t)c0; w[EP_CIG0_HI] = (int32_t)(c0 >> 32);
-    w[31] = 0;
+    const int64_t od = W.o_delta[i];
+    w[EP_ODL_LO] = (int32_t)(uint32_t)od; w[EP_ODL_HI] = (int32_t)(od >> 32);
 }
 
 // dryRun (TC.py:1615-1678): positional inventory of X / D / I from the MD x CIGAR merge.

@@ -6,6 +6,7 @@
 // fields of a read's plan row (one word per lane, `pw`)
 #define PF(k) __shfl_sync(FULL, pw, (k))
 #define PF64(k) ((int64_t)(((u64)(uint32_t)PF((k) + 1) << 32) | (u64)(uint32_t)PF(k)))
+#define PF64_2(lo, hi) ((int64_t)(((u64)(uint32_t)PF(hi) << 32) | (u64)(uint32_t)PF(lo)))
 #ifndef WARPS_PER_BLOCK
 #define WARPS_PER_BLOCK 8
 #endif

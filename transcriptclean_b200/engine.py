@@ -38,8 +38,8 @@ class _BatchIn(C.Structure):
 
 class _BatchOut(C.Structure):
     _fields_ = [("n_reads", C.c_int64)] + [(n, C.c_void_p) for n in (
-        "status", "counters", "nm", "seq_off", "seq_len", "seq", "cig_off", "cig_op", "cig_len", "md_off", "md_len", "md",
-        "jn_off", "jm", "ji", "te_off", "te")] + [("seq_bits", C.c_int32), ("reserved", C.c_int32)]
+        "status", "counters", "nm", "delta_off", "delta_len", "seq_len", "delta", "cig_off", "cig_op", "cig_len", "md_off", "md_len", "md",
+        "jn_off", "jm", "ji", "te_off", "te")]
 
 
 class Timing(C.Structure):
@@ -134,13 +134,66 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
 
 
-class BatchResult:
-    """numpy copies of a tc_batch_out (a 4-bit SEQ column is expanded to ASCII with `alphabet`)."""
+def decode_te_words(words, te_off):
+    """tc_batch_out.te (8-byte words, tc_te_decode in include/tc_b200.h) -> (rows as TE_DTYPE, row offsets per read)."""
+    n = len(te_off) - 1
+    if len(words) == 0:
+        return np.zeros(0, dtype=TE_DTYPE), np.zeros(n + 1, dtype=np.int64)
+    nw = np.diff(te_off)
+    read = np.repeat(np.arange(n), nw)
+    idx = np.arange(len(words)) - np.repeat(te_off[:-1], nw)
+    typ = ((words >> np.uint64(56)) & np.uint64(3)).astype(np.int64)
+    # junction rows (type 3) close a read's list and take two words each: the first one marks where the pairs begin
+    first3 = np.full(n, np.iinfo(np.int64).max)
+    np.minimum.at(first3, read[typ == 3], idx[typ == 3])
+    f3 = first3[read]
+    is_row = (idx < f3) | (((idx - f3) & 1) == 0)
+    w = words[is_row]
+    rows = np.zeros(len(w), dtype=TE_DTYPE)
+    rows["a"] = (w & np.uint64(0xffffffff)).astype(np.uint32).view(np.int32)
+    rows["size"] = ((w >> np.uint64(32)) & np.uint64(0xffffff)).astype(np.int32)
+    rows["type"] = ((w >> np.uint64(56)) & np.uint64(3)).astype(np.uint8)
+    rows["status"] = ((w >> np.uint64(58)) & np.uint64(1)).astype(np.uint8)
+    rows["reason"] = ((w >> np.uint64(59)) & np.uint64(7)).astype(np.uint8)
+    nxt = np.concatenate((words[1:], np.zeros(1, dtype=np.uint64)))[is_row]
+    b3 = (nxt & np.uint64(0xffffffff)).astype(np.uint32).view(np.int32)
+    rows["b"] = np.where(rows["type"] == 3, b3, np.where(rows["type"] == 0, 0, rows["a"] + rows["size"]))
+    per_read = np.bincount(read[is_row], minlength=n)
+    return rows, np.concatenate(([0], np.cumsum(per_read))).astype(np.int64)
 
-    def __init__(self, out, dry, alphabet=None):
+
+def apply_delta(in_seq, delta):
+    """tc_seq_apply_delta (include/tc_b200.h): input SEQ bytes + delta bytes -> new SEQ bytes."""
+    out, q, k, n_d = bytearray(), 0, 0, len(delta)
+    while k < n_d:
+        kind, n = delta[k] >> 6, delta[k] & 63
+        k += 1
+        if n == 62:
+            n = delta[k] | (delta[k + 1] << 8); k += 2
+        elif n == 63:
+            n = delta[k] | (delta[k + 1] << 8) | (delta[k + 2] << 16) | (delta[k + 3] << 24); k += 4
+        if kind == 1:
+            q += n
+        elif kind == 0:
+            if q + n > len(in_seq):
+                raise EngineError("SEQ delta runs past the input SEQ")
+            out += in_seq[q:q + n]; q += n
+        elif kind == 2:
+            out += delta[k:k + n]; k += n
+        else:
+            raise EngineError("malformed SEQ delta")
+    return bytes(out)
+
+
+class BatchResult:
+    """numpy copies of a tc_batch_out.  The new SEQ of a read comes back as a delta against its input SEQ
+    (`read_seq(i)` applies it to the `cols` the batch was made from); TE rows are decoded to TE_DTYPE."""
+
+    def __init__(self, out, dry, alphabet=None, cols=None):
         n = out.n_reads
         self.n = n
         self.dry = dry
+        self._cols, self._alphabet = cols, alphabet
 
         def arr(p, dtype, count):
             if not p or count == 0:
@@ -150,20 +203,17 @@ class BatchResult:
 
         self.status = arr(out.status, np.uint32, n)
         self.counters = arr(out.counters, np.int32, 10 * n).reshape(n, 10)
-        self.te_off = arr(out.te_off, np.int64, n + 1) if n else np.zeros(1, np.int64)
-        self.te = arr(out.te, TE_DTYPE, int(self.te_off[-1]))
+        self.te_word_off = arr(out.te_off, np.int64, n + 1) if n else np.zeros(1, np.int64)
+        self.te_words = arr(out.te, np.uint64, int(self.te_word_off[-1]))
+        self.te, self.te_off = decode_te_words(self.te_words, self.te_word_off)
         if dry:
             return
         self.nm = arr(out.nm, np.int32, n)
-        self.seq_off = arr(out.seq_off, np.int64, n + 1) if n else np.zeros(1, np.int64)
         self.seq_len = arr(out.seq_len, np.int32, n)
-        if out.seq_bits == 4:            # two bases per byte; rows are 16-byte aligned, so packed byte j = bases 2j, 2j+1
-            pk = arr(out.seq, np.uint8, int(self.seq_off[-1]) // 2)
-            al = np.frombuffer(bytes(alphabet).ljust(16, b"\0"), dtype=np.uint8).astype(np.uint16)
-            t = np.arange(256)
-            self.seq = (al[t & 15] | (al[t >> 4] << 8)).astype("<u2")[pk].view(np.uint8)
-        else:
-            self.seq = arr(out.seq, np.uint8, int(self.seq_off[-1]))
+        self.delta_off = arr(out.delta_off, np.int64, n)
+        self.delta_len = arr(out.delta_len, np.int32, n)
+        d_total = int((self.delta_off + np.maximum(self.delta_len, 0)).max()) if n else 0
+        self.delta = arr(out.delta, np.uint8, d_total)
         self.cig_off = arr(out.cig_off, np.int64, n + 1) if n else np.zeros(1, np.int64)
         self.cig_op = arr(out.cig_op, np.uint8, int(self.cig_off[-1]))
         self.cig_len = arr(out.cig_len, np.int32, int(self.cig_off[-1]))
@@ -174,6 +224,34 @@ class BatchResult:
         self.jn_off = arr(out.jn_off, np.int64, n + 1) if n else np.zeros(1, np.int64)
         self.jm = arr(out.jm, np.int8, int(self.jn_off[-1]))
         self.ji = arr(out.ji, np.int32, 2 * int(self.jn_off[-1]))
+
+    def input_seq(self, i):
+        """The input SEQ of read i as bytes (ASCII), from the columns the batch was made from."""
+        c = self._cols
+        if c is None:
+            raise EngineError("this BatchResult was made without the input columns: read_seq() needs them")
+        a, b = int(c["seq_off"][i]), int(c["seq_off"][i + 1])
+        if c.get("seq_poff") is None:
+            return c["seq"][a:b].tobytes()
+        p = int(c["seq_poff"][i])
+        pk = c["seq"][p:p + (b - a + 1) // 2]
+        al = np.frombuffer(bytes(self._alphabet).ljust(16, b"\0"), dtype=np.uint8)
+        out = np.empty(2 * len(pk), dtype=np.uint8)
+        out[0::2], out[1::2] = al[pk & 15], al[pk >> 4]
+        return out[:b - a].tobytes()
+
+    def read_seq(self, i):
+        """The corrected SEQ of read i as bytes."""
+        s = self.input_seq(i)
+        if self.delta_len[i] < -1:
+            raise EngineError("read %d: the engine flagged its SEQ delta as inconsistent" % i)
+        if self.delta_len[i] < 0:
+            return s
+        a = int(self.delta_off[i])
+        out = apply_delta(s, self.delta[a:a + int(self.delta_len[i])].tobytes())
+        if len(out) != int(self.seq_len[i]):
+            raise EngineError("read %d: SEQ delta gives %d bases, seq_len says %d" % (i, len(out), int(self.seq_len[i])))
+        return out
 
 
 def sam_rnames(lib, text):
@@ -374,12 +452,12 @@ class Engine:
         """tc_correct_batch: host columns in -> BatchResult (host copies)."""
         b, out = self._batch_in(cols), _BatchOut()
         self._check(self._lib.tc_correct_batch(self._ctx, C.byref(b), C.byref(out)), "tc_correct_batch")
-        return BatchResult(out, False, self.alphabet)
+        return BatchResult(out, False, self.alphabet, self._keep[0])
 
     def dryrun(self, cols):
         b, out = self._batch_in(cols), _BatchOut()
         self._check(self._lib.tc_dryrun_batch(self._ctx, C.byref(b), C.byref(out)), "tc_dryrun_batch")
-        return BatchResult(out, True, self.alphabet)
+        return BatchResult(out, True, self.alphabet, self._keep[0])
 
     # split calls for device-resident measurement
     def upload(self, cols):
@@ -392,7 +470,7 @@ class Engine:
     def download(self, dry=False, copy=True):
         out = _BatchOut()
         self._check(self._lib.tc_batch_download(self._ctx, C.byref(out)), "tc_batch_download")
-        return BatchResult(out, dry, self.alphabet) if copy else out
+        return BatchResult(out, dry, self.alphabet, self._keep[0] if self._keep else None) if copy else out
 
     def raw_correct(self, b):
         """tc_correct_batch on a prepared _BatchIn; returns the raw _BatchOut (no numpy copies)."""

@@ -47,7 +47,7 @@ class ReadView:
         self.QNAME, self.FLAG, self.CHROM, self.POS, self.MAPQ = f[0], int(f[1]), f[2], int(f[3]), f[4]
         self.RNEXT, self.PNEXT, self.TLEN, self.QUAL = f[6], f[7], f[8], "*"
         self.strand = "-" if self.FLAG == 16 else "+"
-        self.SEQ = res.seq[res.seq_off[i]:res.seq_off[i] + res.seq_len[i]].tobytes().decode("ascii")
+        self.SEQ = res.read_seq(i).decode("ascii")
         if st & E.ST_CIGAR_REWRITTEN:
             a, b = res.cig_off[i], res.cig_off[i + 1]
             self.CIGAR = "".join("%d%s" % (l, chr(o).upper()) for o, l in zip(res.cig_op[a:b], res.cig_len[a:b]))   # 'd' = "D-" (tc_plan.cuh)
