@@ -423,7 +423,6 @@ TC_HD void measure_read(const Params& P, int64_t i) {
 
 struct Emit {                 // newCIGAR / newSeq / MVal bookkeeping (endMatch, TC.py:1171-1183)
     u64* cig; int nc; u64* seg; int ns; int32_t run; int64_t seqlen; u64 last;   // last = seg[ns - 1]
-    int64_t dsz, in_end;      // bytes of the SEQ delta of the finished segments; end of the latest input slice among them
     TC_HD void match(int32_t n) { run += n; }
     TC_HD void flush() { if (run > 0) { cig[nc++] = cg_make('M', run); run = 0; } }
     TC_HD void op(int o, int32_t n) { flush(); cig[nc++] = cg_make(o, n); }
@@ -433,10 +432,8 @@ struct Emit {                 // newCIGAR / newSeq / MVal bookkeeping (endMatch,
         if (ns > 0 && seg_kind(last) == kind && seg_src(last) + seg_len(last) == src && seg_len(last) + len <= (int64_t)SEG_LEN_MASK) {
             last = seg_make(kind, seg_src(last), seg_len(last) + len); seg[ns - 1] = last; return;
         }
-        if (ns > 0) dsz += dl_seg_size(last, in_end);           // the previous segment is final now
         last = seg_make(kind, src, len); seg[ns++] = last;
     }
-    TC_HD int64_t delta_bytes() { int64_t e = in_end; return ns > 0 ? dsz + dl_seg_size(last, e) : dsz; }
 };
 
 TC_HD void te_put(tc_te* te, int& n, int type, int32_t a, int32_t b, int32_t size, int status, int reason) {
@@ -475,7 +472,7 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
         return;
     }
     WsView v = ws_view(W, i);
-    Emit E; E.cig = v.cig[0]; E.nc = 0; E.seg = v.seg[0]; E.ns = 0; E.run = 0; E.seqlen = 0; E.last = 0; E.dsz = 0; E.in_end = 0;
+    Emit E; E.cig = v.cig[0]; E.nc = 0; E.seg = v.seg[0]; E.ns = 0; E.run = 0; E.seqlen = 0; E.last = 0;
     const int chrom = B.chrom[i];
     const int64_t goff = P.G.chrom_off[chrom] - 1;       // plane index of 1-based position p is goff + p
     const uint8_t* seq = B.seq + B.seq_off[i];
@@ -492,29 +489,33 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
     int cop = ci < cend ? B.cig_op[ci] : 0; int32_t crem = ci < cend ? B.cig_len[ci] : 0;
     MdCur md; md.i = 0; md.len = 0; md.p = 0; md.tok = 0;
     int mop = 0; int32_t mrem = 0; bool have_md = false; uint32_t mw = 0; bool mraw = false;
-#define TC_NEXT_CIGAR() do { ci++; if (ci < cend) { cop = B.cig_op[ci]; crem = B.cig_len[ci]; } } while (0)
-#define TC_NEXT_MD() do { if (md.tok) { have_md = md.i < md.len; if (have_md) { mw = md.tok[md.i++]; mraw = true; } } else have_md = md_next(md, mop, mrem); } while (0)
-    if (stage1) { md_cursor(P, B, i, md); TC_NEXT_MD(); }
+    if (stage1) {
+        md_cursor(P, B, i, md);
+        if (md.tok) { have_md = md.i < md.len; if (have_md) { mw = md.tok[md.i++]; mraw = true; } } else have_md = md_next(md, mop, mrem);
+    }
+    const bool have_cat = P.V.n_snp > 0 || P.V.n_ins > 0 || P.V.n_del > 0;
+    const int32_t max_indel = O.max_len_indel;
     bool fail = false;
+    // The 32 reads of a warp sit on different kinds of op at any moment, so every `if` in this loop would be walked by
+    // the whole warp once per branch taken (the first version spent four fifths of its issue slots that way: 13 of 32
+    // lanes active on average).  The step is therefore written as one straight block - selects and predicated stores -
+    // with branches left only for the loop exits and the variant catalogue searches.
     while (true) {
-        int op; int32_t ct;
-        if (stage1) {
-            if (!have_md && ci >= cend) break;
-            if (ci >= cend) { fail = true; break; }                   // cigarOperation[cigarIndex] IndexError (Q14)
-            if (cop == 'H' || cop == 'S' || cop == 'I' || cop == 'N') { op = cop; ct = crem; TC_NEXT_CIGAR(); }
-            else {
-                if (!have_md) { fail = true; break; }                 // mdCount[mdIndex] IndexError
-                if (mraw) { const uint32_t k = mw >> 30; mop = k == 0 ? 'M' : k == 1 ? 'X' : 'D'; mrem = (int32_t)(mw & MD_TOK_MAX); mraw = false; }
-                if (crem < mrem) { mrem -= crem; op = cop; ct = crem; TC_NEXT_CIGAR(); }
-                else if (crem > mrem) { crem -= mrem; op = mop; ct = mrem; TC_NEXT_MD(); }
-                else { op = mop; ct = mrem; TC_NEXT_MD(); TC_NEXT_CIGAR(); }
-            }
-        } else {
-            if (ci >= cend) break;
-            op = cop; ct = crem; TC_NEXT_CIGAR();
+        if (ci >= cend) { fail = stage1 && have_md; break; }          // MD left over: cigarOperation[cigarIndex] IndexError (Q14)
+        const bool pass = !stage1 || cop == 'H' || cop == 'S' || cop == 'I' || cop == 'N';
+        if (!pass && !have_md) { fail = true; break; }                // mdCount[mdIndex] IndexError
+        if (mraw) { const uint32_t k = mw >> 30; mop = k == 0 ? 'M' : k == 1 ? 'X' : 'D'; mrem = (int32_t)(mw & MD_TOK_MAX); mraw = false; }
+        // ---- one step of the merge (tr.py:171-211): the shorter of the two current entries is the piece; ties take the MD entry
+        const bool take_c = pass || crem < mrem, tie = !pass && crem == mrem;
+        const bool adv_c = take_c || tie, adv_m = !take_c;
+        const int op = take_c ? cop : mop; const int32_t ct = take_c ? crem : mrem;
+        { const int32_t m0 = mrem; mrem = (!pass && take_c) ? mrem - crem : mrem; crem = (adv_m && !tie) ? crem - m0 : crem; }
+        if (adv_c) { ci++; if (ci < cend) { cop = B.cig_op[ci]; crem = B.cig_len[ci]; } }              // fetched one step ahead of their use
+        if (adv_m) {
+            if (md.tok) { have_md = md.i < md.len; if (have_md) { mw = md.tok[md.i++]; mraw = true; } }   // (stays an undecoded word until the next step)
+            else have_md = md_next(md, mop, mrem);
         }
-        // One straight-line body for every op kind (lanes of a warp sit on different kinds, so a
-        // switch with six private copies of push / te_put / op would be executed six times over):
+        // ---- the piece:
         //   M            SEQ slice, joins the match run
         //   X            TE row; SNP catalogue hit -> kept as is (TC.py:1115-1130, Q11), else genome bases verbatim (Q6)
         //   S            CIGAR op + SEQ slice
@@ -523,26 +524,43 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
         //   N, H         CIGAR op;   anything else vanishes (Q10)
         const bool isM = op == 'M', isX = op == 'X', isS = op == 'S', isI = op == 'I', isD = op == 'D', isNH = op == 'N' || op == 'H';
         const bool edit = isX || ((isI || isD) && indel);                  // gets a TE row
-        bool variant = false, toolarge = false;
-        if (edit) {
-            if (isX) { if (P.V.n_snp > 0) variant = snp_match(P.V, chrom, g, seq[q]); }   // SEQ is only touched when a catalogue exists
-            else {
-                toolarge = ct > O.max_len_indel;
-                if (!toolarge) variant = isI ? (P.V.n_ins > 0 && ins_match(P.V, chrom, g - 1, ct, seq + q)) : (P.V.n_del > 0 && del_match(P.V, chrom, g - 1, ct));
-            }
-            const bool kept = variant || toolarge;
-            te_put(v.te, nte, isX ? 0 : isI ? 1 : 2, (int32_t)(isX ? g : g - 1), isX ? 0 : (int32_t)(g + ct - 1), ct, kept ? 1 : 0, toolarge ? 2 : variant ? 1 : 0);
-            const u64 inc = 1ull << (isX ? 0 : isI ? 21 : 42);
-            if (toolarge) cnt_big += inc; else if (variant) cnt_var += inc; else cnt_cor += inc;
+        const bool toolarge = edit && !isX && ct > max_indel;
+        bool variant = false;
+        if (have_cat && edit && !toolarge) {                               // SEQ is only touched when a catalogue exists
+            if (isX) variant = P.V.n_snp > 0 && snp_match(P.V, chrom, g, seq[q]);
+            else variant = isI ? (P.V.n_ins > 0 && ins_match(P.V, chrom, g - 1, ct, seq + q)) : (P.V.n_del > 0 && del_match(P.V, chrom, g - 1, ct));
         }
-        const bool corrected = edit && !variant && !toolarge;
+        const bool kept = variant || toolarge, corrected = edit && !kept;
+        if (edit) te_put(v.te, nte, isX ? 0 : isI ? 1 : 2, (int32_t)(isX ? g : g - 1), isX ? 0 : (int32_t)(g + ct - 1), ct, kept ? 1 : 0, toolarge ? 2 : variant ? 1 : 0);
+        {
+            const u64 inc = edit ? 1ull << (isX ? 0 : isI ? 21 : 42) : 0ull;
+            cnt_big += toolarge ? inc : 0ull; cnt_var += (variant && !toolarge) ? inc : 0ull; cnt_cor += corrected ? inc : 0ull;
+        }
         sawD |= isD;
-        if (isI && corrected) ins_removed += ct;
+        ins_removed += (isI && corrected) ? ct : 0;
         const bool from_genome = (isX || isD) && corrected;
-        if (isM || isS || (isX && !corrected) || (isI && !corrected) || from_genome) E.push(from_genome ? 1 : 0, from_genome ? goff + g : q, ct);
-        if (isM || isX || (isD && corrected)) E.match(ct);
-        else if (isS || isNH || ((isI || isD) && !corrected)) E.op(op, ct);
-        if (isM || isX || isS || isI) q += ct;
+        {   // Emit.push: the slice joins the segment before it when it continues it
+            const bool do_push = ct > 0 && (isM || isS || (isX && !corrected) || (isI && !corrected) || from_genome);
+            const int kind = from_genome ? 1 : 0; const int64_t src = from_genome ? goff + g : q;
+            const int64_t l_src = seg_src(E.last), l_len = seg_len(E.last); const int l_kind = seg_kind(E.last);
+            const bool merge = do_push && E.ns > 0 && l_kind == kind && l_src + l_len == src && l_len + ct <= (int64_t)SEG_LEN_MASK;
+            const bool fresh = do_push && !merge;
+            E.seqlen += do_push ? ct : 0;
+            const u64 nl = merge ? seg_make(kind, l_src, l_len + ct) : seg_make(kind, src, ct);
+            if (do_push) { E.seg[merge ? E.ns - 1 : E.ns] = nl; E.last = nl; }
+            E.ns += fresh ? 1 : 0;
+        }
+        {   // Emit.match / Emit.op (endMatch, TC.py:1171-1183)
+            const bool join = isM || isX || (isD && corrected);
+            const bool isop = !join && (isS || isNH || ((isI || isD) && !corrected));
+            const bool fl = isop && E.run > 0;
+            if (fl) E.cig[E.nc] = cg_make('M', E.run);
+            E.nc += fl ? 1 : 0;
+            if (isop) E.cig[E.nc] = cg_make(op, ct);
+            E.nc += isop ? 1 : 0;
+            E.run = isop ? 0 : E.run + (join ? ct : 0);
+        }
+        q += (isM || isX || isS || isI) ? ct : 0;
         if (want_ji && op == 'N') {                                   // compute_jI (tr.py:368-393) on the way; one 8-byte store
 #ifdef TC_HOSTSIM
             v.jn[kN * JN_STRIDE] = (int32_t)g; v.jn[kN * JN_STRIDE + 1] = (int32_t)(g + ct - 1);
@@ -551,10 +569,8 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
 #endif
             kN++;
         }
-        if (isM || isX || isD || isNH) g += ct;
+        g += (isM || isX || isD || isNH) ? ct : 0;
     }
-#undef TC_NEXT_CIGAR
-#undef TC_NEXT_MD
     if (fail) {                                                       // whole-read fallback (Q13): stage 1 raised
         W.status[i] = st | TC_ST_FALLBACK;                            // before stages 2-3 zeroed their counters
         return;
@@ -568,7 +584,7 @@ TC_HD void plan_read(const Params& P, int64_t i, const BatchDev& B) {
     if (indel) { C[TC_C_COR_INS] = cI; C[TC_C_UNC_INS] = uI; C[TC_C_VAR_INS] = vI;
                  C[TC_C_COR_DEL] = cD; C[TC_C_UNC_DEL] = uD; C[TC_C_VAR_DEL] = vD; }
     W.cig_buf[i] = 0; W.n_cig_cur[i] = E.nc; W.seg_buf[i] = 0; W.n_seg_cur[i] = E.ns; W.seq_len_out[i] = (int32_t)E.seqlen;
-    W.delta_size[i] = (int32_t)E.delta_bytes();
+    W.delta_size[i] = (int32_t)dl_list_size(E.seg, E.ns);              // bytes of the SEQ delta: one more walk over the finished list (cheaper than booking every step)
     W.n_te[i] = nte; W.te_cnt[3 * i] = nteM; W.te_cnt[3 * i + 1] = nteI; W.te_cnt[3 * i + 2] = nteD;
     // NM/MD refresh points (Q7): end of correctDeletions when the CIGAR holds a D, else end of
     // correctMismatches; insertion removal never refreshes, so NM keeps counting removed bases.
