@@ -238,7 +238,9 @@ def main():
     ap.add_argument("--ref-reads", type=int, default=0)
     ap.add_argument("--ref-port", action="store_true", help="--impl reference: time the oracle port even when oracle/_ref holds the reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--text-sample", type=int, default=100000, help="reads for the SAM-text path measurement (0 = skip)")
+    ap.add_argument("--text-sample", type=int, default=200000, help="reads for the SAM-text path measurement (0 = skip)")
+    ap.add_argument("--text-block-mb", type=int, default=16, help="block size of the SAM-text path measurement (the CLI's TC_CLI_BLOCK_MB)")
+    ap.add_argument("--text-workers", type=int, default=3, help="pipelined workers (engine contexts) of the SAM-text path measurement")
     ap.add_argument("--resident-only", action="store_true", help="profiling aid: only the device-resident steps (no pipelined e2e calls), so that a "
                     "launch list holds exactly the kernels of the timed region")
     ap.add_argument("--no-dry", action="store_true", help="skip the --dryRun measurement")
@@ -412,26 +414,37 @@ def main():
                            "ms_per_step": ms_dry, "e2e_ms_per_step": ms_dry_e2e,
                            "note": "--dryRun inventory (tc_dryrun_batch) of the same batch: device-resident and through the ABI with host buffers"}
     if world == 1 and rank == 0 and args.text_sample > 0:
-        # SAM text in -> four output texts (C++ host parse / render + GPU), in memory
+        # SAM text in -> four output texts, as the CLI runs it: blocks of the text go through workers with
+        # their own engine context (parse k+1 | GPU k | render k-1 overlap), texts delivered in input order
         from transcriptclean_b200 import api
+        from transcriptclean_b200.cli import split_text
         ns = min(args.text_sample, args.reads)
         text = ("\n".join(w.sam_lines(cols, nm, 0, ns)) + "\n").encode()
-        refs = api.Struct(); refs.genome = gi; refs.engine = eng
-        sizes = {}
+        n_workers = max(1, args.text_workers)
+        sj_tab = build_sj_tables(sj_path, {w.chrom}, gi.index)
+        refs_list = [api.make_refs(gi, sj_tab, None, engine=eng)] + [api.make_refs(gi, sj_tab, None, device=local) for _ in range(n_workers - 1)]
+        blocks = split_text(text, max(n_workers, len(text) // (args.text_block_mb << 20)))
+        sizes = {"sam": 0, "fa": 0, "log": 0, "te": 0}
         devnull = open(os.devnull, "wb")
 
         def sink(header, views):            # what the CLI does with the four texts: write them out
-            for k, v in views.items():
-                devnull.write(v)
-                sizes[k] = len(v)
-        api.correct_sam_text(text, api.Struct(), refs, consume=sink)
+            for k, vs in views.items():
+                for v in vs:
+                    devnull.write(v)
+                    sizes[k] += len(v)
+        api.correct_sam_stream(blocks, api.Struct(), refs_list, sink)
+        for k in sizes:
+            sizes[k] = 0
         t0 = time.perf_counter()
-        api.correct_sam_text(text, api.Struct(), refs, consume=sink)
+        api.correct_sam_stream(blocks, api.Struct(), refs_list, sink)
         t1 = time.perf_counter()
         devnull.close()
+        for r in refs_list[1:]:
+            r.engine.close()
         line["sam_text_path"] = {"value": ns / (t1 - t0), "unit": "reads/s", "in_bytes": len(text),
                                  "out_bytes": sum(sizes.values()),
-                                 "sample": "%d reads as SAM text -> clean SAM + FASTA + log + TE.log texts, host threads=%d" % (ns, min(32, os.cpu_count() or 1))}
+                                 "sample": "%d reads as SAM text -> clean SAM + FASTA + log + TE.log texts; %d blocks through %d pipelined workers "
+                                           "(own engine context each, one GPU), host threads=%d" % (ns, len(blocks), n_workers, min(32, os.cpu_count() or 1))}
     texts, n_texts = None, 0
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         ns = min(args.cpu_sample, args.reads)

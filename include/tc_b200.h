@@ -248,6 +248,12 @@ int tc_sam_pack_seq(tc_sam* s, const uint8_t* alphabet, int32_t n_alpha, int32_t
 int tc_sam_render(tc_sam* s, const tc_batch_out* res, int32_t primary_only, int32_t canon_only, int32_t dry,
                   int32_t n_threads, const char** sam, int64_t* sam_len, const char** fa, int64_t* fa_len,
                   const char** log, int64_t* log_len, const char** te, int64_t* te_len, char* err, int64_t err_cap);
+/* the same texts without the final copy: n_parts pieces per text, in order (the formatter threads' own buffers);
+ * ptr[4 * k + q] / len[4 * k + q] = piece k of text q (0 sam, 1 fa, 2 log, 3 te); ptr / len hold 4 * max_parts entries.
+ * Valid until the calling thread renders again. */
+int tc_sam_render_parts(tc_sam* s, const tc_batch_out* res, int32_t primary_only, int32_t canon_only, int32_t dry,
+                        int32_t n_threads, int32_t* n_parts, const char** ptr, int64_t* len, int32_t max_parts,
+                        char* err, int64_t err_cap);
 
 /* ---- host side: lookup tables from their files (csrc/tc_tables.cpp, multi-threaded C++; no GPU involved) ----
  * tc_vcf_parse replaces processVCF (TranscriptClean.py:769-856): VCF text (already decompressed) -> the arrays of

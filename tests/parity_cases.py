@@ -81,7 +81,7 @@ def check_seq_forms(engine, seed, n_reads=160):
     text = "".join(l + "\n" for l in case.lines).encode()
     try:
         for seq4 in (True, False):
-            engine.seq4 = seq4
+            engine.seq4 = engine.seq4_text = seq4
             got = pipeline.product_texts(engine, gi, case.lines, sjf, vcf, {})
             d = pipeline.first_diff(got, want)
             assert d is None, (seq4, d)
@@ -110,4 +110,4 @@ def check_seq_forms(engine, seed, n_reads=160):
         assert engine.pack_cols(odd) is None
         return True
     finally:
-        engine.seq4 = True
+        engine.seq4, engine.seq4_text = True, False

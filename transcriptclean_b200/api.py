@@ -118,6 +118,84 @@ def correct_sam_text(text, options, refs, dry=False, consume=None):
         st.close()
 
 
+def correct_sam_stream(blocks, options, refs_list, sink, dry=False, n_threads=None):
+    """Pipelined text path: `blocks` yields SAM text (bytes, whole lines) in input order; every entry of `refs_list` is a
+    worker with its own Engine (several per GPU are fine - they are what overlaps parsing, the GPU call and rendering of
+    successive blocks, the way the reference overlaps its worker processes, TC.py:48-62).  `sink(header, views)` gets the
+    four texts of every block in input order, each as a list of pieces (memoryviews of the formatter threads' own buffers:
+    nothing is copied together; valid during the call).
+    Host threads for the C++ parser / renderer are split between the workers."""
+    import os
+    import threading
+    n_workers = len(refs_list)
+    per = max(1, int(n_threads or min(32, os.cpu_count() or 1)) // n_workers)
+    it = enumerate(blocks)
+    lock = threading.Lock()
+    cond = threading.Condition()
+    ready, state = {}, {"next": 0, "err": None, "end": None}
+
+    def take():
+        with lock:
+            try:
+                return next(it)
+            except StopIteration:
+                return None
+
+    def work(refs):
+        try:
+            _set_engine_options(options, refs)
+            while state["err"] is None:
+                item = take()
+                if item is None:
+                    return
+                idx, text = item
+                st = refs.engine.parse_sam(text, refs.genome, per)
+                try:
+                    raw = refs.engine.raw_dryrun(st.batch) if dry else refs.engine.raw_correct(st.batch)
+                    out = st.render_parts(raw, bool(_opt(options, "primaryOnly", False)), bool(_opt(options, "canonOnly", False)), dry)
+                    done = threading.Event()
+                    with cond:
+                        ready[idx] = (st.header, out, done)
+                        cond.notify_all()
+                    done.wait()                                    # the writer is through with this block's buffers
+                    for vs in out.values():
+                        for v in vs:
+                            v.release()
+                finally:
+                    st.close()
+        except BaseException as e:                                 # surfaced by the writer loop
+            with cond:
+                state["err"] = state["err"] or e
+                cond.notify_all()
+
+    threads = [threading.Thread(target=work, args=(r,), daemon=True) for r in refs_list]
+    for t in threads:
+        t.start()
+    try:
+        while True:
+            with cond:
+                while state["next"] not in ready and state["err"] is None and any(t.is_alive() for t in threads):
+                    cond.wait(0.05)
+                if state["err"] is not None:
+                    raise state["err"]
+                if state["next"] not in ready:
+                    break                                          # every worker has finished and nothing is pending
+                header, out, done = ready.pop(state["next"])
+            try:
+                sink(header, out)
+            finally:
+                done.set()
+            state["next"] += 1
+    finally:
+        with cond:
+            state["err"] = state["err"] or RuntimeError("stream aborted")
+            for _, _, d in ready.values():
+                d.set()
+        for t in threads:
+            t.join(timeout=5)
+    return state["next"]
+
+
 def batch_correct(sam_transcripts, options, refs, outfiles, buffer_size=100):
     """TC.py:350-403.  `buffer_size` only staggers disk writes in the reference; the whole list
     is one device batch here."""

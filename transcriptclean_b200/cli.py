@@ -148,15 +148,15 @@ def split_text(text, n):
 
 def run(options, engines=None):
     """engines: optional list of pre-built Engine objects (tests inject CPU stand-ins here).
-    The SAM file is streamed twice in blocks (TC_CLI_BLOCK_MB, default 256): a scan for the header
-    lines and the chromosome names (what split_SAM collects, TC.py:519-541), then the correction,
-    block by block - each block cut into one contiguous piece per GPU (one host thread per GPU),
-    the pieces' texts appended to the four output files in input order (combine_outputs,
-    TC.py:604-663: headers first; no SAM / FASTA in --dryRun).  SAM parsing and text rendering run
-    in the library's multi-threaded C++ host code (csrc/tc_host.cpp)."""
-    import threading
+    The SAM file is streamed twice in blocks (TC_CLI_BLOCK_MB, default 16): a scan for the header lines and the
+    chromosome names (what split_SAM collects, TC.py:519-541), then the correction.  Blocks are handed to worker
+    threads in input order - TC_CLI_WORKERS_PER_GPU (default 3) workers per GPU, each with its own engine context, so
+    that parsing block k+1, correcting block k and rendering block k-1 overlap - and their four texts are appended to
+    the output files in input order (combine_outputs, TC.py:604-663: headers first; no SAM / FASTA in --dryRun).
+    SAM parsing and text rendering run in the library's multi-threaded C++ host code (csrc/tc_host.cpp); the SJ / VCF
+    tables are parsed once (csrc/tc_tables.cpp) and uploaded to every context."""
     from . import engine as E
-    block = int(os.environ.get("TC_CLI_BLOCK_BYTES", "0")) or max(1, int(os.environ.get("TC_CLI_BLOCK_MB", "256"))) << 20
+    block = int(os.environ.get("TC_CLI_BLOCK_BYTES", "0")) or max(1, int(os.environ.get("TC_CLI_BLOCK_MB", "16"))) << 20
     lib = E.load_library() if engines is None else engines[0]._lib
     chroms, header = set(), ""
     for blk in sam_blocks(options.sam, block):
@@ -166,55 +166,41 @@ def run(options, engines=None):
     genome = GenomeImage.from_fasta_cached(options.refGenome)
     if engines is None:
         n = max(1, min(int(options.n_threads), max(1, n_gpus_available())))
-        engines = [E.Engine(d) for d in range(n)]
+        per_gpu = max(1, int(os.environ.get("TC_CLI_WORKERS_PER_GPU", "3")))
+        engines = [E.Engine(d) for d in range(n) for _ in range(per_gpu)]
     validate_chroms(genome, options.variantFile, chroms)
     os.makedirs(options.tmp_dir, exist_ok=True)          # kept for interface compatibility (--tmpDir / --deleteTmp)
-
     dry = bool(options.dryRun)
-    # tables: parsed once and uploaded to every GPU; a dry run never opens the SJ / VCF files (TC.py:589-601)
+    # tables: parsed once and uploaded to every context; a dry run never opens the SJ / VCF files (TC.py:589-601)
     sj, var = (None, None) if dry else api.build_tables(options, chroms, genome)
     refs_list = [api.make_refs(genome, sj, var, engine=e) for e in engines]
     pre = options.outprefix
-    files = {"log": open(pre + "_clean.log", "wb"), "te": open(pre + "_clean.TE.log", "wb")}
+    names = {"log": pre + "_clean.log", "te": pre + "_clean.TE.log"}
     if not dry:
-        files["sam"] = open(pre + "_clean.sam", "wb")
-        files["fa"] = open(pre + "_clean.fa", "wb")
+        names.update({"sam": pre + "_clean.sam", "fa": pre + "_clean.fa"})
+    files = {k: open(v + ".partial", "wb") for k, v in names.items()}     # renamed on success: an abort leaves no truncated final file
+    ok = False
     try:
         files["log"].write(LOG_HEADER.encode())
         files["te"].write(TE_HEADER.encode())
         if not dry:
             files["sam"].write(header.encode())
 
-        def sink(_header, views):                         # the library's own buffers, written without a copy
+        def sink(_header, views):                         # the formatter threads' own buffers, written without a copy
             for k, f in files.items():
-                f.write(views[k])
+                for piece in views[k]:
+                    f.write(piece)
 
-        for blk in sam_blocks(options.sam, block):
-            if len(engines) == 1:
-                api.correct_sam_text(blk, options, refs_list[0], dry=dry, consume=sink)
-                continue
-            parts = split_text(blk, len(engines))
-            results, errs = [None] * len(parts), []
-
-            def work(k):
-                try:
-                    results[k] = api.correct_sam_text(parts[k], options, refs_list[k], dry=dry)[1]
-                except Exception as e:
-                    errs.append(e)
-
-            ts = [threading.Thread(target=work, args=(k,)) for k in range(len(parts))]
-            for t in ts:
-                t.start()
-            for t in ts:
-                t.join()
-            if errs:
-                raise errs[0]
-            for r in results:
-                for k, f in files.items():
-                    f.write(r[k])
+        api.correct_sam_stream(sam_blocks(options.sam, block), options, refs_list, sink, dry=dry)
+        ok = True
     finally:
         for f in files.values():
             f.close()
+        for v in names.values():
+            if ok:
+                os.replace(v + ".partial", v)
+            elif os.path.exists(v + ".partial"):
+                os.remove(v + ".partial")
     if options.delete_tmp:
         import shutil
         shutil.rmtree(options.tmp_dir, ignore_errors=True)

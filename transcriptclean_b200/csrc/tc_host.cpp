@@ -218,6 +218,18 @@ const char* const CLASS_NAME[3] = {"primary", "unmapped", "non-primary"};
 const char* const TE_TYPE[4] = {"Mismatch", "Insertion", "Deletion", "NC_SJ_boundary"};
 const char* const TE_STATUS[2] = {"Corrected", "Uncorrected"};
 const char* const TE_REASON[6] = {"NA", "VariantMatch", "TooLarge", "TooFarFromAnnotJn", "Other", "DryRun"};
+const size_t TE_TYPE_N[4] = {8, 9, 8, 14};
+struct TeTails {                    // "<Corrected|Uncorrected>\t<reason>\n" for every (status, reason)
+    std::string s[2][8];
+    TeTails() { for (int a = 0; a < 2; a++) for (int b = 0; b < 8; b++) s[a][b] = std::string(TE_STATUS[a]) + "\t" + (b < 6 ? TE_REASON[b] : "NA") + "\n"; }
+};
+const TeTails TE_TAILS;
+#define TE_TAIL TE_TAILS_P
+#define TE_TAIL_N TE_TAILS_N
+struct TeTailsP { const char* p[2][8]; size_t n[2][8]; TeTailsP() { for (int a = 0; a < 2; a++) for (int b = 0; b < 8; b++) { p[a][b] = TE_TAILS.s[a][b].data(); n[a][b] = TE_TAILS.s[a][b].size(); } } };
+const TeTailsP TE_TP;
+#define TE_TAILS_P TE_TP.p
+#define TE_TAILS_N TE_TP.n
 
 // Text under construction.  The string is only storage (its size is the capacity in use); `n` is the length
 // written so far.  need(k) makes room for k more bytes once per record; the writers below do not check.
@@ -228,11 +240,14 @@ struct Out {
     void put(const char* p, size_t k) { memcpy(&buf[n], p, k); n += k; }
     void ch(char c) { buf[n++] = c; }
     void str(const char* z) { put(z, strlen(z)); }
-    void num(int64_t v) {
-        char b[24]; int k = 24; const bool neg = v < 0; uint64_t u = neg ? (uint64_t)(-v) : (uint64_t)v;
-        do { b[--k] = (char)('0' + u % 10); u /= 10; } while (u);
-        if (neg) b[--k] = '-';
-        put(b + k, (size_t)(24 - k));
+    void num(int64_t v) {                                        // digits written in place, two at a time
+        static const char D2[201] = "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+        uint64_t u = v < 0 ? (uint64_t)(-v) : (uint64_t)v;
+        if (v < 0) buf[n++] = '-';
+        int nd = 1; for (uint64_t t = u; t >= 10; t /= 10) nd++;
+        char* e = &buf[n] + nd; n += (size_t)nd;
+        while (u >= 100) { const unsigned r = (unsigned)(u % 100); u /= 100; e -= 2; e[0] = D2[2 * r]; e[1] = D2[2 * r + 1]; }
+        if (u >= 10) { e -= 2; e[0] = D2[2 * u]; e[1] = D2[2 * u + 1]; } else { e[-1] = (char)('0' + u); }
     }
 };
 
@@ -274,13 +289,17 @@ void render_range(const tc_sam* S, const tc_batch_out* R, int64_t a, int64_t b, 
         }
         const int64_t t0 = R->te_off[i], t1 = R->te_off[i + 1];
         te.need((size_t)(t1 - t0) * ((size_t)q.n + (size_t)ch.n + 96));
-        for (int64_t k = t0; k < t1;) {
-            tc_te r; k += tc_te_decode(R->te + k, &r);
-            te.put(T + q.s, (size_t)q.n); te.ch('\t');
-            te.put(T + ch.s, (size_t)ch.n); te.ch('_'); te.num(r.a);
-            if (r.type != 0) { te.ch('_'); te.num(r.b); }
-            te.ch('\t'); te.str(TE_TYPE[r.type]); te.ch('\t'); te.num(r.size); te.ch('\t');
-            te.str(TE_STATUS[r.status]); te.ch('\t'); te.str(TE_REASON[r.reason]); te.ch('\n');
+        if (t1 > t0) {                                                // every row of the read starts with "<QNAME>\t<chrom>_"
+            const size_t pre0 = te.n, pre_n = (size_t)q.n + (size_t)ch.n + 2;
+            te.put(T + q.s, (size_t)q.n); te.ch('\t'); te.put(T + ch.s, (size_t)ch.n); te.ch('_');
+            for (int64_t k = t0; k < t1;) {
+                tc_te r; k += tc_te_decode(R->te + k, &r);
+                if (te.n != pre0 + pre_n) { memcpy(&te.buf[te.n], &te.buf[pre0], pre_n); te.n += pre_n; }
+                te.num(r.a);
+                if (r.type != 0) { te.ch('_'); te.num(r.b); }
+                te.ch('\t'); te.put(TE_TYPE[r.type], TE_TYPE_N[r.type]); te.ch('\t'); te.num(r.size); te.ch('\t');
+                te.put(TE_TAIL[r.status][r.reason], TE_TAIL_N[r.status][r.reason]);
+            }
         }
         if (dry) continue;
         if (canon_only && !(st & (TC_ST_CANONICAL | TC_ST_ALL_ANNOT))) continue;
@@ -544,10 +563,10 @@ void tc_sam_batch(const tc_sam* S, tc_batch_in* b) {
     if (S->packed) { b->seq = S->seqp.data(); b->seq_poff = S->seq_poff.data(); }
 }
 
-int tc_sam_render(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_t canon_only, int32_t dry, int32_t n_threads,
-                  const char** sam, int64_t* sam_len, const char** fa, int64_t* fa_len, const char** lg, int64_t* lg_len,
-                  const char** te, int64_t* te_len, char* err, int64_t err_cap) {
-    struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0); const double t_enter = ts0.tv_sec + 1e-9 * ts0.tv_nsec;
+// the four texts as the parts of the T formatter threads (ps / pf / pl / pt, per calling thread, storage kept between batches)
+static thread_local std::vector<Out> ps, pf, pl, pt;
+static int render_parts(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_t canon_only, int32_t dry, int32_t n_threads,
+                        int& T_out, char* err, int64_t err_cap) {
     if (!S || !R || R->n_reads != S->n) { set_err(err, err_cap, "tc_sam_render: result does not belong to this batch"); return TC_E_ARG; }
     for (int64_t i = 0; i < S->n; i++) {
         const uint32_t st = R->status[i];
@@ -559,7 +578,6 @@ int tc_sam_render(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_
     }
     int T = n_threads < 1 ? 1 : n_threads;
     if (S->n < 4096) T = 1;
-    static thread_local std::vector<Out> ps, pf, pl, pt;              // per calling thread, storage kept between batches
     for (auto* v : {&ps, &pf, &pl, &pt}) { if (v->size() < (size_t)T) v->resize((size_t)T); for (auto& x : *v) x.clear(); }
     std::vector<std::thread> th; std::vector<int64_t> bad((size_t)T, -1);
     for (int k = 0; k < T; k++) {
@@ -572,6 +590,17 @@ int tc_sam_render(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_
         set_err(err, err_cap, "read " + std::string(S->text + S->f[0][bad[(size_t)k]].s, (size_t)S->f[0][bad[(size_t)k]].n) + ": the SEQ delta does not fit the input SEQ (result of another batch?)");
         return TC_E_ARG;
     }
+    T_out = T;
+    return TC_OK;
+}
+
+int tc_sam_render(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_t canon_only, int32_t dry, int32_t n_threads,
+                  const char** sam, int64_t* sam_len, const char** fa, int64_t* fa_len, const char** lg, int64_t* lg_len,
+                  const char** te, int64_t* te_len, char* err, int64_t err_cap) {
+    struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0); const double t_enter = ts0.tv_sec + 1e-9 * ts0.tv_nsec;
+    int T = 1;
+    const int rc = render_parts(S, R, primary_only, canon_only, dry, n_threads, T, err, err_cap);
+    if (rc != TC_OK) return rc;
     const bool tm = getenv("TC_HOST_TIMING") != nullptr;
     auto now = [] { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
     const double t_r = now();
@@ -592,6 +621,21 @@ int tc_sam_render(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_
     if (tm) fprintf(stderr, "tc_sam_render: formatting %.3f s (%d threads), join %.3f s\n", t_r - t_enter, T, now() - t_r);
     *sam = S->out[0].p; *sam_len = (int64_t)S->out[0].n; *fa = S->out[1].p; *fa_len = (int64_t)S->out[1].n;
     *lg = S->out[2].p; *lg_len = (int64_t)S->out[2].n; *te = S->out[3].p; *te_len = (int64_t)S->out[3].n;
+    return TC_OK;
+}
+
+// tc_sam_render without the final copy: every text comes as n_parts pieces (the formatter threads' own buffers, in
+// order), ptr[4 * k + q] / len[4 * k + q] for part k of text q (0 sam, 1 fa, 2 log, 3 te).  The pieces stay valid until
+// the calling thread renders again.
+int tc_sam_render_parts(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_t canon_only, int32_t dry, int32_t n_threads,
+                        int32_t* n_parts, const char** ptr, int64_t* len, int32_t max_parts, char* err, int64_t err_cap) {
+    int T = 1;
+    if (n_threads > max_parts) n_threads = max_parts;
+    const int rc = render_parts(S, R, primary_only, canon_only, dry, n_threads, T, err, err_cap);
+    if (rc != TC_OK) return rc;
+    std::vector<Out>* parts[4] = {&ps, &pf, &pl, &pt};
+    for (int k = 0; k < T; k++) for (int q = 0; q < 4; q++) { ptr[4 * k + q] = (*parts[q])[(size_t)k].buf.data(); len[4 * k + q] = (int64_t)(*parts[q])[(size_t)k].n; }
+    *n_parts = T;
     return TC_OK;
 }
 

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("TC_B200_LIB") or os.path.join(_HERE, "csrc", "libtc_b
 EXPORTS = ["tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_set_options", "tc_ctx_stream",
            "tc_ctx_load_genome", "tc_ctx_load_junctions", "tc_ctx_load_variants", "tc_correct_batch",
            "tc_dryrun_batch", "tc_batch_upload", "tc_batch_run", "tc_batch_download", "tc_get_timing",
-           "tc_ctx_set_pipeline", "tc_sam_parse", "tc_sam_free", "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_render",
+           "tc_ctx_set_pipeline", "tc_sam_parse", "tc_sam_free", "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_render", "tc_sam_render_parts",
            "tc_sam_rnames", "tc_free", "tc_ctx_set_alphabet", "tc_seq_pack", "tc_seq_packed_size", "tc_sam_pack_seq", "tc_sam_header_lines",
            "tc_vcf_parse", "tc_vcf_tables", "tc_vcf_n_records", "tc_vcf_free", "tc_sj_parse", "tc_sj_tables", "tc_sj_free"]
 
@@ -110,6 +110,7 @@ def _declare(lib):
     lib.tc_seq_packed_size.restype = C.c_int64
     lib.tc_sam_pack_seq.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32]
     lib.tc_sam_render.argtypes = [C.c_void_p, C.POINTER(_BatchOut)] + [C.c_int32] * 4 + [C.POINTER(C.c_void_p), C.POINTER(C.c_int64)] * 4 + [C.c_char_p, C.c_int64]
+    lib.tc_sam_render_parts.argtypes = [C.c_void_p, C.POINTER(_BatchOut)] + [C.c_int32] * 4 + [C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_int32, C.c_char_p, C.c_int64]
     lib.tc_vcf_parse.restype = C.c_void_p
     lib.tc_vcf_parse.argtypes = [C.c_char_p, C.c_int64, C.c_int32, C.POINTER(C.c_char_p), C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int64]
     lib.tc_vcf_tables.restype = None
@@ -335,6 +336,21 @@ class SamText:
         return {k: memoryview((C.c_char * l.value).from_address(p.value)).cast("B") if l.value else memoryview(b"")
                 for k, p, l in zip(("sam", "fa", "log", "te"), ptr, ln)}
 
+    def render_parts(self, raw_out, primary_only=False, canon_only=False, dry=False):
+        """Like render(copy=False) but without the library's final join: {"sam","fa","log","te"} -> list of memoryviews
+        (the formatter threads' pieces, in order), valid until this thread renders again."""
+        cap = 64
+        ptr, ln, n = (C.c_void_p * (4 * cap))(), (C.c_int64 * (4 * cap))(), C.c_int32()
+        err = C.create_string_buffer(1024)
+        rc = self._lib.tc_sam_render_parts(self._h, C.byref(raw_out), int(primary_only), int(canon_only), int(dry), self._nt,
+                                           C.byref(n), ptr, ln, cap, err, 1024)
+        if rc != 0:
+            raise EngineError(err.value.decode())
+        out = {}
+        for q, name in enumerate(("sam", "fa", "log", "te")):
+            out[name] = [memoryview((C.c_char * ln[4 * k + q]).from_address(ptr[4 * k + q])).cast("B") for k in range(n.value) if ln[4 * k + q]]
+        return out
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.tc_sam_free(self._h)
@@ -362,7 +378,8 @@ class Engine:
         self.device = device
         self._keep = []
         self.alphabet = None       # bytes of the 4-bit SEQ codes once a genome is loaded (None: SEQ travels as ASCII)
-        self.seq4 = True           # send / receive SEQ in 4-bit form whenever the batch allows it
+        self.seq4 = True           # send SEQ in 4-bit form whenever the batch allows it (column path: PCIe is what limits it)
+        self.seq4_text = False     # SAM-text path: ASCII (the host's parse / render threads limit it; packing would only add to them)
 
     def close(self):
         if getattr(self, "_ctx", None):
@@ -484,7 +501,7 @@ class Engine:
         return out
 
     def parse_sam(self, text, genome, n_threads=None):
-        return SamText(self._lib, text, genome, n_threads, self.alphabet if self.seq4 else None)
+        return SamText(self._lib, text, genome, n_threads, self.alphabet if (self.seq4 and self.seq4_text) else None)
 
     def timing(self):
         t = Timing()
