@@ -244,7 +244,8 @@ def main():
     ap.add_argument("--resident-only", action="store_true", help="profiling aid: only the device-resident steps (no pipelined e2e calls), so that a "
                     "launch list holds exactly the kernels of the timed region")
     ap.add_argument("--no-dry", action="store_true", help="skip the --dryRun measurement")
-    ap.add_argument("--seq8", action="store_true", help="send / receive SEQ as ASCII instead of the 4-bit form")
+    ap.add_argument("--seq8", action="store_true", help="send SEQ as ASCII instead of a packed form")
+    ap.add_argument("--seq4", action="store_true", help="send SEQ as 4-bit codes instead of the 2-bit form")
     ap.add_argument("--debug-mask", type=int, default=0, help="profiling aid: skip phases of k_emit (results invalid)")
     ap.add_argument("--parity-reads", type=int, default=-1, help="reads of the timed batch whose texts are compared with the oracle's "
                     "(default: --cpu-sample at N=1, 500 per rank at N>1; 0 = skip)")
@@ -280,20 +281,25 @@ def main():
     # inputs in pinned host memory; SEQ travels in the ABI's 4-bit form (two bases per byte) unless --seq8
     hcols = cols
     if not args.seq8:
-        hcols = eng.pack_cols(cols)
+        hcols = (None if args.seq4 else eng.pack_cols2(cols)) or eng.pack_cols(cols)
         if hcols is None:
             raise SystemExit("the synthetic SEQ column holds bytes outside the engine's alphabet")
+    seq_form = "ASCII" if args.seq8 else ("2-bit codes + a list of the bases outside ACGT" if hcols.get("seq_bits") == 2 else "4-bit codes")
     pinned = {}
     for k, a in hcols.items():
+        if not isinstance(a, np.ndarray):
+            continue
         t = torch.empty(max(a.nbytes, 8), dtype=torch.uint8, pin_memory=True)
         if a.nbytes:
             t[:a.nbytes].copy_(torch.from_numpy(a.view(np.uint8).reshape(-1)))
         pinned[k] = t
     b = E._BatchIn()
     b.n_reads = args.reads
-    for k in hcols:
+    for k in pinned:
         setattr(b, k, pinned[k].data_ptr())
-    h2d_bytes = int(sum(a.nbytes for a in hcols.values()))
+    b.seq_bits = int(hcols.get("seq_bits", 4 if "seq_poff" in hcols else 8))
+    b.n_exc = len(hcols["exc_pos"]) if "exc_pos" in hcols else 0
+    h2d_bytes = int(sum(a.nbytes for a in hcols.values() if isinstance(a, np.ndarray)))
 
     stream = torch.cuda.ExternalStream(eng.stream())
 
@@ -397,7 +403,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "shape": args.shape, "reads_per_gpu_per_step": args.reads,
                    "mean_read_len": float(cols["seq"].nbytes) / args.reads,
-                   "seq_form": "ASCII" if args.seq8 else "4-bit codes on the host side of the ABI (expanded / packed on the device)",
+                   "seq_form": seq_form + " on the host side of the ABI (expanded on the device); the new SEQ comes back as a delta against the input SEQ",
                    "l2": "inputs (%.2f GB per step) are larger than L2; no flush needed" % (h2d_bytes / 1e9),
                    "parallelism": "reads sharded by input-order chunk, tables replicated, no collective"},
         "e2e": {"value": reads_total * steps / (ms_e2e * 1e-3), "unit": "reads/s", "ms_per_step": ms_e2e / steps,

@@ -129,6 +129,12 @@ typedef struct {
      * of 4) and has seq_off[i+1]-seq_off[i] bases; seq_off keeps the dense base offsets.  (The results
      * never carry SEQ rows: the new SEQ comes back as a delta against the input SEQ, tc_batch_out.delta.) */
     const int64_t* seq_poff;  /* n+1, or NULL: SEQ is ASCII */
+    /* 2-bit SEQ (optional, seq_bits == 2; seq_bits 0 / 4 / 8 = the forms above): `seq` holds four bases per byte (base j of a row in
+     * bits 2*(j%4) of its byte j/4; A=0 C=1 G=2 T=3), rows at seq_poff[i] (multiples of 4) as for the 4-bit form.  Every base that is
+     * not one of ACGT (upper case) is listed: exc_pos[k] = its index in the dense SEQ column (seq_off units, ascending), exc_byte[k] =
+     * the byte.  Sequencer reads are ACGT almost everywhere, so this is a quarter of the ASCII column on the host link. */
+    int32_t seq_bits; int32_t reserved0;
+    int64_t n_exc; const int64_t* exc_pos; const uint8_t* exc_byte;
 } tc_batch_in;
 
 typedef struct {
@@ -207,6 +213,11 @@ int tc_ctx_set_alphabet(tc_ctx* ctx, const uint8_t* alphabet, int32_t n);
 int64_t tc_seq_pack(const uint8_t* seq, const int64_t* seq_off, int64_t n, const uint8_t* alphabet, int32_t n_alpha,
                     uint8_t* out, int64_t* poff, int32_t n_threads);
 int64_t tc_seq_packed_size(const int64_t* seq_off, int64_t n);
+/* ASCII rows -> 2-bit rows + the list of bases outside ACGT (at most exc_cap of them, else -1 is returned and the caller
+ * uses another form); out needs sum(ceil(len/16)*4) bytes (tc_seq_packed2_size), poff n+1 entries. */
+int64_t tc_seq_pack2(const uint8_t* seq, const int64_t* seq_off, int64_t n, uint8_t* out, int64_t* poff,
+                     int64_t exc_cap, int64_t* exc_pos, uint8_t* exc_byte, int64_t* n_exc, int32_t n_threads);
+int64_t tc_seq_packed2_size(const int64_t* seq_off, int64_t n);
 
 /* batch_correct() minus text rendering: host columns in, host columns out (H2D, kernels, D2H). */
 int tc_correct_batch(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out);

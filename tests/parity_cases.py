@@ -80,17 +80,20 @@ def check_seq_forms(engine, seed, n_reads=160):
     chroms = set(l.split("\t")[2] for l in case.lines)
     text = "".join(l + "\n" for l in case.lines).encode()
     try:
-        for seq4 in (True, False):
-            engine.seq4 = engine.seq4_text = seq4
+        for seq2, seq4 in ((True, True), (False, True), (False, False)):          # 2-bit + listed bases, 4-bit codes, ASCII
+            engine.seq2, engine.seq4, engine.seq4_text = seq2, seq4, seq4
             got = pipeline.product_texts(engine, gi, case.lines, sjf, vcf, {})
             d = pipeline.first_diff(got, want)
-            assert d is None, (seq4, d)
+            assert d is None, (seq2, seq4, d)
             refs = api.make_refs(gi, build_sj_tables(sjf, chroms, gi.index), build_variant_tables(vcf, 5, gi.index), engine=engine)
             _, got = api.correct_sam_text(text, api.Struct(), refs)
             d = pipeline.first_diff({k: v.decode() for k, v in got.items()}, want)
             assert d is None, (seq4, "text path", d)
         engine.seq4 = True
         cols = sam.parse_lines(case.lines, gi).cols
+        p2 = engine.pack_cols2(cols, max_exc_frac=1.0)      # explicit 2-bit columns in: every base outside ACGT is listed
+        assert p2 is not None and p2["seq_bits"] == 2 and p2["seq"].size < cols["seq"].size * 0.27 + 4 * len(case.lines) + 64
+        r2 = engine.correct(p2)
         packed = engine.pack_cols(cols)
         if engine.alphabet is None:                     # a genome with more than 16 distinct bytes: ASCII only
             assert packed is None and len(set("".join(case.genome.values())) | set("ACGTacgt")) > 16
@@ -101,7 +104,8 @@ def check_seq_forms(engine, seed, n_reads=160):
         ref = engine.correct(cols)
         assert np.array_equal(res.seq_len, ref.seq_len) and np.array_equal(res.delta_len, ref.delta_len)
         for i in range(len(case.lines)):
-            assert res.read_seq(i) == ref.read_seq(i) and len(res.read_seq(i)) == int(ref.seq_len[i]), i
+            assert res.read_seq(i) == ref.read_seq(i) == r2.read_seq(i) and len(res.read_seq(i)) == int(ref.seq_len[i]), i
+        assert np.array_equal(r2.status, ref.status) and np.array_equal(r2.te_words, ref.te_words) and np.array_equal(r2.nm, ref.nm)
         engine.seq4 = True
         odd = dict(cols)
         odd["seq"] = cols["seq"].copy()
@@ -110,4 +114,4 @@ def check_seq_forms(engine, seed, n_reads=160):
         assert engine.pack_cols(odd) is None
         return True
     finally:
-        engine.seq4, engine.seq4_text = True, False
+        engine.seq2, engine.seq4, engine.seq4_text = True, True, False

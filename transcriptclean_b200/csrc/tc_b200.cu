@@ -17,6 +17,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -202,7 +203,7 @@ static void host_nmmd(const GenomeDev& G, const uint8_t* seq, const CigSrc& cs, 
 
 // Everything that belongs to one batch (or one chunk of a pipelined batch) on the device.
 struct Slot {
-    DevBuf b_seqp, b_seq_poff;           // 4-bit SEQ: packed input rows + their offsets
+    DevBuf b_seqp, b_seq_poff, b_exc_pos, b_exc_byte;   // 4-bit / 2-bit SEQ: packed input rows + their offsets; the 2-bit form's listed bases
     DevBuf b_flag, b_chrom, b_pos, b_tags, b_seq_off, b_seq, b_cig_off, b_cig_op, b_cig_len, b_md_off, b_md, b_ji_off, b_ji;
     BatchDev B; int64_t n = 0, n_seq = 0, n_cig = 0, n_md = 0, n_ji = 0, md_base = 0;
     int64_t seq_lo_word = 0, seq_hi_word = 0;       // words of B.seq (as uint32) that may be dereferenced
@@ -225,7 +226,7 @@ struct Slot {
                        &w_o_seq, &w_o_cig, &w_o_te, &w_o_jn, &w_o_delta, &w_delta_size, &w_seq_len, &w_plan, &w_fix_list, &init_pool, &cursors, &scan_tmp,
                        &o_nm, &o_md_off, &o_md_len, &o_md_pool, &o_delta_off, &o_delta_len, &o_delta_pool, &o_seq, &o_cig_op, &o_cig_len, &o_te, &o_jm, &o_ji};
         for (DevBuf* b : d) b->release();
-        b_seqp.release(); b_seq_poff.release();
+        b_seqp.release(); b_seq_poff.release(); b_exc_pos.release(); b_exc_byte.release();
         h_tot.release();
     }
 };
@@ -294,6 +295,32 @@ __global__ void __launch_bounds__(256) k_seq_unpack(int64_t n, const int64_t* se
         }
     }
 }
+// 2-bit SEQ rows -> ASCII rows, one warp per read: a lane turns one byte (4 bases) into 4 characters
+__global__ void __launch_bounds__(256) k_seq_unpack2(int64_t n, const int64_t* seq_off, const int64_t* poff, const uint8_t* packed, uint8_t* seq) {
+    __shared__ uint32_t lut[256];
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) {
+        const uint32_t acgt = 0x54474341u;
+        lut[t] = ((acgt >> (8 * (t & 3))) & 255u) | (((acgt >> (8 * ((t >> 2) & 3))) & 255u) << 8) |
+                 (((acgt >> (8 * ((t >> 4) & 3))) & 255u) << 16) | (((acgt >> (8 * ((t >> 6) & 3))) & 255u) << 24);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31; const int64_t nw = (int64_t)gridDim.x * 8;
+    for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += nw) {
+        const int64_t o = seq_off[i]; const int L = (int)(seq_off[i + 1] - o);
+        const uint8_t* src = packed + poff[i]; uint8_t* dst = seq + o;
+        const int mis = (int)(reinterpret_cast<uintptr_t>(dst) & 3);
+        for (int b = lane; b * 4 < L; b += 32) {
+            const uint32_t x = lut[src[b]]; const int left = L - b * 4; uint8_t* d = dst + b * 4;
+            if (left >= 4 && mis == 0) *reinterpret_cast<uint32_t*>(d) = x;
+            else if (left >= 4 && mis == 2) { *reinterpret_cast<uint16_t*>(d) = (uint16_t)x; *reinterpret_cast<uint16_t*>(d + 2) = (uint16_t)(x >> 16); }
+            else { for (int k = 0; k < 4; k++) if (k < left) d[k] = (uint8_t)(x >> (8 * k)); }
+        }
+    }
+}
+__global__ void k_seq_patch(int64_t n_exc, const int64_t* pos, const uint8_t* byte, uint8_t* seq) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_exc; k += (int64_t)gridDim.x * blockDim.x) seq[pos[k]] = byte[k];
+}
+
 static int be_h2d(tc_ctx* ctx, cudaStream_t st, DevBuf& d, size_t dst_off, const void* src, size_t bytes, size_t slack = 0) {
     CK(d.ensure(dst_off + bytes + slack + 8));
     if (bytes) CK(cudaMemcpyAsync((char*)d.p + dst_off, src, bytes, cudaMemcpyHostToDevice, st));
@@ -526,24 +553,39 @@ int tc_ctx_load_variants(tc_ctx* ctx, int64_t n_snp, const uint64_t* snp_key, co
 
 }  // extern "C"
 
-// 4-bit SEQ rows of reads [r0, r1): upload, then expand to the ASCII rows the kernels read (B.seq at d0)
+// packed (4-bit or 2-bit) SEQ rows of reads [r0, r1): upload, then expand to the ASCII rows the kernels read (B.seq at d0)
 static int seq_upload_packed(tc_ctx* ctx, Slot& S, const tc_batch_in* in, int64_t r0, int64_t r1, size_t d0, stream_t st) {
     const int64_t n = r1 - r0;
     CK(S.b_seq.ensure(d0 + (size_t)S.n_seq + 256 + 8));
     if (n == 0) return 0;
+    const bool two = in->seq_bits == 2;
     const int64_t p0 = in->seq_poff[r0], pbytes = in->seq_poff[r1] - p0;
     if (be_h2d(ctx, st, S.b_seqp, 0, in->seq + p0, (size_t)pbytes, 64) || be_h2d(ctx, st, S.b_seq_poff, 0, in->seq_poff + r0, (size_t)(n + 1) * 8)) return TC_E_CUDA;
-    const int64_t s0 = in->seq_off[r0];
+    const int64_t s0 = in->seq_off[r0], s1 = in->seq_off[r1];
     uint8_t* dst = (uint8_t*)S.b_seq.p + d0 - s0; const uint8_t* src = (const uint8_t*)S.b_seqp.p - p0;
+    int64_t e0 = 0, e1 = 0;                                            // listed bases of these reads (exc_pos is ascending)
+    if (two && in->n_exc > 0) {
+        e0 = std::lower_bound(in->exc_pos, in->exc_pos + in->n_exc, s0) - in->exc_pos; e1 = std::lower_bound(in->exc_pos, in->exc_pos + in->n_exc, s1) - in->exc_pos;
+        if (e1 > e0 && (be_h2d(ctx, st, S.b_exc_pos, 0, in->exc_pos + e0, (size_t)(e1 - e0) * 8) || be_h2d(ctx, st, S.b_exc_byte, 0, in->exc_byte + e0, (size_t)(e1 - e0)))) return TC_E_CUDA;
+    }
 #ifndef TC_HOSTSIM
-    Alphabet A; memcpy(A.c, ctx->alphabet, 16);
     int64_t wb = (n + 7) / 8; int g = (int)(wb < 148 * 8 ? wb : 148 * 8);
-    k_seq_unpack<<<g, 256, 0, st>>>(n, (const int64_t*)S.b_seq_off.p, (const int64_t*)S.b_seq_poff.p, src, dst, A); ctx->tm.launches++;
+    if (two) {
+        k_seq_unpack2<<<g, 256, 0, st>>>(n, (const int64_t*)S.b_seq_off.p, (const int64_t*)S.b_seq_poff.p, src, dst); ctx->tm.launches++;
+        if (e1 > e0) { k_seq_patch<<<(int)std::min<int64_t>((e1 - e0 + 255) / 256, 1184), 256, 0, st>>>(e1 - e0, (const int64_t*)S.b_exc_pos.p, (const uint8_t*)S.b_exc_byte.p, dst); ctx->tm.launches++; }
+    } else {
+        Alphabet A; memcpy(A.c, ctx->alphabet, 16);
+        k_seq_unpack<<<g, 256, 0, st>>>(n, (const int64_t*)S.b_seq_off.p, (const int64_t*)S.b_seq_poff.p, src, dst, A); ctx->tm.launches++;
+    }
     CK(cudaGetLastError());
 #else
     const int64_t* so = (const int64_t*)S.b_seq_off.p; const int64_t* po = (const int64_t*)S.b_seq_poff.p;
     for (int64_t i = 0; i < n; i++)
-        for (int64_t k = 0; k < so[i + 1] - so[i]; k++) { const uint8_t b = src[po[i] + (k >> 1)]; dst[so[i] + k] = ctx->alphabet[(k & 1) ? b >> 4 : b & 15]; }
+        for (int64_t k = 0; k < so[i + 1] - so[i]; k++) {
+            if (two) dst[so[i] + k] = (uint8_t)"ACGT"[(src[po[i] + (k >> 2)] >> (2 * (k & 3))) & 3];
+            else { const uint8_t b = src[po[i] + (k >> 1)]; dst[so[i] + k] = ctx->alphabet[(k & 1) ? b >> 4 : b & 15]; }
+        }
+    for (int64_t k = e0; k < e1; k++) dst[in->exc_pos[k]] = in->exc_byte[k];
 #endif
     return 0;
 }
@@ -863,6 +905,7 @@ static void fill_out(tc_ctx* ctx, tc_batch_out* out, int64_t n) {
 // notes the SEQ form of the batch; a 4-bit batch needs an alphabet that holds every genome byte
 static int check_packed(tc_ctx* ctx, const tc_batch_in* in) {
     ctx->packed = in->seq_poff != nullptr;
+    if (in->seq_poff && in->seq_bits == 2) return 0;                   // 2-bit rows carry their own list of other bytes: no alphabet involved
     if (!ctx->packed) return 0;
     bool have[256] = {false};
     for (int k = 0; k < ctx->n_alpha; k++) have[ctx->alphabet[k]] = true;

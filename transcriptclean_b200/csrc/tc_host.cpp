@@ -541,6 +541,44 @@ int64_t tc_seq_pack(const uint8_t* seq, const int64_t* seq_off, int64_t n, const
 }
 
 // packs the parsed SEQ column to 4 bits per base; 1 = done (tc_sam_batch now yields the packed form),
+int64_t tc_seq_packed2_size(const int64_t* seq_off, int64_t n) {
+    int64_t t = 0;
+    for (int64_t i = 0; i < n; i++) t += (seq_off[i + 1] - seq_off[i] + 15) / 16 * 4;
+    return t;
+}
+int64_t tc_seq_pack2(const uint8_t* seq, const int64_t* seq_off, int64_t n, uint8_t* out, int64_t* poff,
+                     int64_t exc_cap, int64_t* exc_pos, uint8_t* exc_byte, int64_t* n_exc, int32_t n_threads) {
+    uint8_t code[256]; memset(code, 0xff, sizeof(code));
+    code[(uint8_t)'A'] = 0; code[(uint8_t)'C'] = 1; code[(uint8_t)'G'] = 2; code[(uint8_t)'T'] = 3;
+    poff[0] = 0;
+    for (int64_t i = 0; i < n; i++) poff[i + 1] = poff[i] + (seq_off[i + 1] - seq_off[i] + 15) / 16 * 4;
+    int T = n_threads < 1 ? 1 : n_threads; if (n < 4096) T = 1;
+    std::vector<std::vector<std::pair<int64_t, uint8_t>>> exc((size_t)T);
+    auto work = [&](int k) {
+        auto& ex = exc[(size_t)k];
+        for (int64_t i = n * k / T; i < n * (k + 1) / T; i++) {
+            const uint8_t* r = seq + seq_off[i]; const int64_t L = seq_off[i + 1] - seq_off[i]; uint8_t* o = out + poff[i];
+            const int64_t nb = poff[i + 1] - poff[i];
+            for (int64_t b = 0; b < nb; b++) {
+                unsigned v = 0;
+                for (int t = 0; t < 4; t++) {
+                    const int64_t j = 4 * b + t;
+                    if (j < L) { unsigned c = code[r[j]]; if (c > 3) { ex.emplace_back(seq_off[i] + j, r[j]); c = 0; } v |= c << (2 * t); }
+                }
+                o[b] = (uint8_t)v;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int k = 0; k < T; k++) th.emplace_back(work, k);
+    for (auto& t : th) t.join();
+    int64_t m = 0; for (auto& e : exc) m += (int64_t)e.size();
+    *n_exc = m;
+    if (m > exc_cap) return -1;
+    m = 0;
+    for (auto& e : exc) for (auto& x : e) { exc_pos[m] = x.first; exc_byte[m] = x.second; m++; }   // (thread ranges are ascending read ranges)
+    return poff[n];
+}
 // 0 = a SEQ byte lies outside the alphabet (the batch stays ASCII)
 int tc_sam_pack_seq(tc_sam* S, const uint8_t* alphabet, int32_t n_alpha, int32_t n_threads) {
     if (!S || !alphabet || n_alpha < 1 || n_alpha > 16) return 0;

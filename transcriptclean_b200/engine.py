@@ -12,7 +12,7 @@ EXPORTS = ["tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_set_optio
            "tc_ctx_load_genome", "tc_ctx_load_junctions", "tc_ctx_load_variants", "tc_correct_batch",
            "tc_dryrun_batch", "tc_batch_upload", "tc_batch_run", "tc_batch_download", "tc_get_timing",
            "tc_ctx_set_pipeline", "tc_sam_parse", "tc_sam_free", "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_render", "tc_sam_render_parts",
-           "tc_sam_rnames", "tc_free", "tc_ctx_set_alphabet", "tc_seq_pack", "tc_seq_packed_size", "tc_sam_pack_seq", "tc_sam_header_lines",
+           "tc_sam_rnames", "tc_free", "tc_ctx_set_alphabet", "tc_seq_pack", "tc_seq_packed_size", "tc_seq_pack2", "tc_seq_packed2_size", "tc_sam_pack_seq", "tc_sam_header_lines",
            "tc_vcf_parse", "tc_vcf_tables", "tc_vcf_n_records", "tc_vcf_free", "tc_sj_parse", "tc_sj_tables", "tc_sj_free"]
 
 # status bits (include/tc_b200.h)
@@ -33,7 +33,7 @@ class _Options(C.Structure):
 class _BatchIn(C.Structure):
     _fields_ = [("n_reads", C.c_int64)] + [(n, C.c_void_p) for n in (
         "flag", "chrom", "pos", "tags", "seq_off", "seq", "cig_off", "cig_op", "cig_len", "md_off", "md", "ji_off", "ji",
-        "seq_poff")]
+        "seq_poff")] + [("seq_bits", C.c_int32), ("reserved0", C.c_int32), ("n_exc", C.c_int64), ("exc_pos", C.c_void_p), ("exc_byte", C.c_void_p)]
 
 
 class _BatchOut(C.Structure):
@@ -108,6 +108,10 @@ def _declare(lib):
     lib.tc_seq_pack.restype = C.c_int64
     lib.tc_seq_packed_size.argtypes = [C.c_void_p, C.c_int64]
     lib.tc_seq_packed_size.restype = C.c_int64
+    lib.tc_seq_packed2_size.argtypes = [C.c_void_p, C.c_int64]
+    lib.tc_seq_packed2_size.restype = C.c_int64
+    lib.tc_seq_pack2.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32]
+    lib.tc_seq_pack2.restype = C.c_int64
     lib.tc_sam_pack_seq.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32]
     lib.tc_sam_render.argtypes = [C.c_void_p, C.POINTER(_BatchOut)] + [C.c_int32] * 4 + [C.POINTER(C.c_void_p), C.POINTER(C.c_int64)] * 4 + [C.c_char_p, C.c_int64]
     lib.tc_sam_render_parts.argtypes = [C.c_void_p, C.POINTER(_BatchOut)] + [C.c_int32] * 4 + [C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_int32, C.c_char_p, C.c_int64]
@@ -127,7 +131,7 @@ def _declare(lib):
     lib.tc_sj_free.argtypes = [C.c_void_p]
     for f in EXPORTS:
         if f not in ("tc_vcf_parse", "tc_vcf_tables", "tc_vcf_n_records", "tc_vcf_free", "tc_sj_parse", "tc_sj_tables", "tc_sj_free", "tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_stream", "tc_sam_parse", "tc_sam_free",
-                     "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_rnames", "tc_free", "tc_seq_pack", "tc_seq_packed_size", "tc_sam_header_lines"):
+                     "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_rnames", "tc_free", "tc_seq_pack", "tc_seq_packed_size", "tc_seq_pack2", "tc_seq_packed2_size", "tc_sam_header_lines"):
             getattr(lib, f).restype = C.c_int
 
 
@@ -235,6 +239,12 @@ class BatchResult:
         if c.get("seq_poff") is None:
             return c["seq"][a:b].tobytes()
         p = int(c["seq_poff"][i])
+        if int(c.get("seq_bits", 4)) == 2:
+            pk = c["seq"][p:p + (b - a + 3) // 4]
+            out = np.frombuffer(b"ACGT", dtype=np.uint8)[(pk[:, None] >> (2 * np.arange(4, dtype=np.uint8))) & 3].reshape(-1)[:b - a].copy()
+            lo, hi = np.searchsorted(c["exc_pos"], a), np.searchsorted(c["exc_pos"], b)
+            out[c["exc_pos"][lo:hi] - a] = c["exc_byte"][lo:hi]
+            return out.tobytes()
         pk = c["seq"][p:p + (b - a + 1) // 2]
         al = np.frombuffer(bytes(self._alphabet).ljust(16, b"\0"), dtype=np.uint8)
         out = np.empty(2 * len(pk), dtype=np.uint8)
@@ -378,6 +388,7 @@ class Engine:
         self.device = device
         self._keep = []
         self.alphabet = None       # bytes of the 4-bit SEQ codes once a genome is loaded (None: SEQ travels as ASCII)
+        self.seq2 = True           # ... and in 2-bit form + a list of the bases outside ACGT when those are few (sequencer reads)
         self.seq4 = True           # send SEQ in 4-bit form whenever the batch allows it (column path: PCIe is what limits it)
         self.seq4_text = False     # SAM-text path: ASCII (the host's parse / render threads limit it; packing would only add to them)
 
@@ -432,6 +443,25 @@ class Engine:
             self._ctx, len(v.snp_key), _ptr(v.snp_key), _ptr(v.snp_alt), len(v.ins_key), _ptr(v.ins_key), _ptr(v.ins_size),
             _ptr(v.ins_aoff), _ptr(v.ins_bytes), len(v.del_key), _ptr(v.del_key), _ptr(v.del_size)), "tc_ctx_load_variants")
 
+    def pack_cols2(self, cols, n_threads=None, max_exc_frac=0.02):
+        """cols with the SEQ column in 2-bit form (`seq` packed, `seq_poff`, `seq_bits` = 2, `exc_pos` / `exc_byte` = the bases
+        outside ACGT), or None when more than max_exc_frac of the bases would have to be listed."""
+        n = len(cols["flag"])
+        so = np.ascontiguousarray(cols["seq_off"], dtype=np.int64)
+        out = np.zeros(int(self._lib.tc_seq_packed2_size(so.ctypes.data, n)) + 64, dtype=np.uint8)
+        poff = np.zeros(n + 1, dtype=np.int64)
+        cap = int(max_exc_frac * int(so[-1] if n else 0)) + 1024
+        epos, ebyte, ne = np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.uint8), C.c_int64()
+        seq = cols["seq"]
+        r = self._lib.tc_seq_pack2(seq.ctypes.data if seq.size else None, so.ctypes.data, n, out.ctypes.data, poff.ctypes.data, cap,
+                                   epos.ctypes.data, ebyte.ctypes.data, C.byref(ne), int(n_threads or min(32, os.cpu_count() or 1)))
+        if r < 0:
+            return None
+        packed = dict(cols)
+        packed["seq"], packed["seq_poff"], packed["seq_off"] = out, poff, so
+        packed["seq_bits"], packed["exc_pos"], packed["exc_byte"] = 2, epos[:ne.value].copy(), ebyte[:ne.value].copy()
+        return packed
+
     def pack_cols(self, cols, n_threads=None):
         """cols with the SEQ column in 4-bit form (`seq` packed, `seq_poff` added), or None when a SEQ
         byte is outside the alphabet."""
@@ -452,16 +482,18 @@ class Engine:
 
     def _batch_in(self, cols):
         if self.seq4 and "seq_poff" not in cols:
-            cols = self.pack_cols(cols) or cols
+            cols = (self.pack_cols2(cols) if self.seq2 else None) or self.pack_cols(cols) or cols
         b = _BatchIn()
         b.n_reads = len(cols["flag"])
         for k in ("flag", "chrom", "pos", "tags", "seq_off", "seq", "cig_off", "cig_op", "cig_len", "md_off", "md",
-                  "ji_off", "ji", "seq_poff"):
+                  "ji_off", "ji", "seq_poff", "exc_pos", "exc_byte"):
             a = cols.get(k)
             if a is None:
                 continue
             assert a.flags["C_CONTIGUOUS"]
             setattr(b, k, a.ctypes.data if a.size else None)
+        b.seq_bits = int(cols.get("seq_bits", 4 if cols.get("seq_poff") is not None else 8))
+        b.n_exc = len(cols["exc_pos"]) if cols.get("exc_pos") is not None else 0
         self._keep = [cols]          # the arrays behind the pointers
         return b
 
