@@ -135,7 +135,7 @@ def test_world_size_2_gloo_shards_concatenate_in_order():
 
 def test_genome_image_cache_round_trip():
     """The packed genome image saved next to the FASTA loads back identical (planes, literal runs, contig table)
-    and is rebuilt when the FASTA is newer."""
+    and is rebuilt when it was not made from this very FASTA file."""
     import numpy as np
     from transcriptclean_b200.genome import GenomeImage
     case, d = _case_files(35, 10)
@@ -145,6 +145,13 @@ def test_genome_image_cache_round_trip():
     assert a.names == b.names and np.array_equal(a.chrom_len, b.chrom_len) and np.array_equal(a.chrom_off, b.chrom_off)
     assert np.array_equal(a.bases2, b.bases2) and np.array_equal(a.lower1, b.lower1)
     assert all(np.array_equal(x, y) for x, y in zip(a.exceptions(), b.exceptions()))
-    os.utime(d + "/g.fa.tcb200.npz", (1, 1))                # stale image: rebuilt
+    assert b.source == GenomeImage.fasta_fingerprint(d + "/g.fa")
+    # another genome copied over the same path with an OLDER time stamp (cp -p, rsync -t): the image is not trusted
+    other = synth.make_case(36, n_reads=5)
+    st = os.stat(d + "/g.fa")
+    other.write_fasta(d + "/g.fa")
+    os.utime(d + "/g.fa", ns=(st.st_atime_ns - 10 ** 12, st.st_mtime_ns - 10 ** 12))
     c = GenomeImage.from_fasta_cached(d + "/g.fa")
-    assert np.array_equal(a.bases2, c.bases2) and os.path.getmtime(d + "/g.fa.tcb200.npz") > 1
+    fresh = GenomeImage.from_fasta(d + "/g.fa")
+    assert np.array_equal(c.bases2, fresh.bases2) and not np.array_equal(c.bases2, a.bases2)
+    assert GenomeImage.load(d + "/g.fa.tcb200.npz").source == GenomeImage.fasta_fingerprint(d + "/g.fa")

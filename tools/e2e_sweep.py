@@ -14,13 +14,15 @@ cols, nm = w.reads(shape, n, seed_offset=0)
 gi = w.genome_image()
 eng = E.Engine(0); eng.load_genome(gi); eng.load_junctions(build_sj_tables(sj, {w.chrom}, gi.index))
 if not os.environ.get("SEQ8"):
-    cols = eng.pack_cols(cols)
+    cols = (None if os.environ.get("SEQ4") else eng.pack_cols2(cols)) or eng.pack_cols(cols)
 pinned = {}
 b = E._BatchIn(); b.n_reads = n
 for k, a in cols.items():
+    if not isinstance(a, np.ndarray): continue
     t = torch.empty(max(a.nbytes, 8), dtype=torch.uint8, pin_memory=True)
     if a.nbytes: t[:a.nbytes].copy_(torch.from_numpy(a.view(np.uint8).reshape(-1)))
     pinned[k] = t; setattr(b, k, t.data_ptr())
+b.seq_bits = int(cols.get("seq_bits", 4 if "seq_poff" in cols else 8)); b.n_exc = len(cols["exc_pos"]) if "exc_pos" in cols else 0
 res = {}
 for ch in [int(x) for x in os.environ.get("CHUNKS", "32768,65536,131072,262144,524288").split(",")]:
     eng.set_pipeline(ch)

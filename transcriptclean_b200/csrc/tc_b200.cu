@@ -151,11 +151,11 @@ struct HostBuf {
     void* p = nullptr; size_t cap = 0;
     cudaError_t ensure(size_t n) {
         if (n <= cap) return cudaSuccess;
+        size_t want = n + n / 8 + 256; void* q = nullptr;
+        cudaError_t e = cudaHostAlloc(&q, want, cudaHostAllocPortable | cudaHostAllocMapped);   // new buffer first: a failed grow keeps the old one
+        if (e != cudaSuccess) return e;
         if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
-        size_t want = n + n / 8 + 256;
-        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable | cudaHostAllocMapped);
-        if (e == cudaSuccess) cap = want;
+        p = q; cap = want;
         return e;
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }

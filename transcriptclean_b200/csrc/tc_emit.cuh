@@ -11,6 +11,13 @@
 #endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_SMALL_BLOCKS) k_small(Params P, OutDev O, int dry) {
+    __shared__ uint32_t lut[256];                                      // 4 bases (8 bits of the 2-bit plane) -> 4 ASCII bytes
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) {
+        const uint32_t acgt = 0x54474341u;
+        lut[t] = ((acgt >> (8 * (t & 3))) & 255u) | (((acgt >> (8 * ((t >> 2) & 3))) & 255u) << 8) |
+                 (((acgt >> (8 * ((t >> 4) & 3))) & 255u) << 16) | (((acgt >> (8 * ((t >> 6) & 3))) & 255u) << 24);
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31; const unsigned lt = (1u << lane) - 1u;
     const BatchDev& B = P.B; const WorkDev& W = P.W;
     const int64_t nw = (int64_t)gridDim.x * WARPS_PER_BLOCK;
@@ -70,16 +77,28 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_SMALL_BLOCKS) k_small
             const int gap = isR ? (int)src - (prevR ? prev_end : cur) : 0;
             const int hl = len < 62 ? 1 : len < 65536 ? 3 : 5, hg = gap <= 0 ? 0 : gap < 62 ? 1 : gap < 65536 ? 3 : 5;
             const int sz = isR ? hg + hl : isG ? hl + len : 0;
+            // genome slices: the plane words are asked for now, so that they travel while the warp scans the sizes
+            uint32_t code = 0, low = 0; bool plain = false;
+            if (isG && len <= 16) {
+                const int64_t b0 = src >> 8, b1 = (src + len - 1) >> 8;
+                plain = !(((P.G.excblk[b0 >> 5] >> (b0 & 31)) | (P.G.excblk[b1 >> 5] >> (b1 & 31))) & 1u);
+                const uint32_t* g2 = P.G.g2 + (src >> 4); const uint32_t* lo = P.G.lo1 + (src >> 5);
+                code = __funnelshift_r(g2[0], g2[1], (int)(src & 15) * 2); low = __funnelshift_r(lo[0], lo[1], (int)(src & 31));
+            }
             int tot; const int off = off0 + warp_excl_scan(sz, lane, tot);
             if (sz > 0 && off + sz <= dlen) {
                 uint8_t* p = dout + off;
-                if (isR) { if (gap > 0) p += dl_put_hdr(p, DL_SKIP, gap); dl_put_hdr(p, DL_COPY, len); }
-                else {                                                 // genome bases, byte exact (Q6): a few per slice, decoded from one pair of plane words
-                    p += dl_put_hdr(p, DL_LIT, len);
-                    if (len <= 16 && !(genome_blk_has_exc(P.G, src) | genome_blk_has_exc(P.G, src + len - 1))) {
-                        const uint32_t* g2 = P.G.g2 + (src >> 4); const uint32_t* lo = P.G.lo1 + (src >> 5);
-                        const uint32_t code = __funnelshift_r(g2[0], g2[1], (int)(src & 15) * 2), low = __funnelshift_r(lo[0], lo[1], (int)(src & 31));
-                        for (int j = 0; j < len; j++) p[j] = (uint8_t)(((0x54474341u >> (((code >> (2 * j)) & 3u) * 8)) & 0xffu) | (((low >> j) & 1u) << 5));
+                if (isR) {
+                    if (gap > 0) { if (hg == 1) *p++ = (uint8_t)((DL_SKIP << 6) | gap); else p += dl_put_hdr(p, DL_SKIP, gap); }
+                    if (hl == 1) *p = (uint8_t)((DL_COPY << 6) | len); else dl_put_hdr(p, DL_COPY, len);
+                } else {                                               // genome bases, byte exact (Q6), four at a time
+                    if (hl == 1) *p++ = (uint8_t)((DL_LIT << 6) | len); else p += dl_put_hdr(p, DL_LIT, len);
+                    if (plain) {
+                        for (int j = 0; j < len; j += 4) {
+                            const uint32_t w4 = lut[(code >> (2 * j)) & 255u] | (((((low >> j) & 15u) * 0x00204081u) & 0x01010101u) << 5);
+                            const int m = len - j;
+                            p[j] = (uint8_t)w4; if (m > 1) p[j + 1] = (uint8_t)(w4 >> 8); if (m > 2) p[j + 2] = (uint8_t)(w4 >> 16); if (m > 3) p[j + 3] = (uint8_t)(w4 >> 24);
+                        }
                     } else for (int j = 0; j < len; j++) p[j] = genome_byte(P.G, src + j);
                 }
             }

@@ -77,7 +77,12 @@ struct tc_sam {
     std::string header;
     struct RawBuf {                  // output text: grown without initialising (a std::string resize would touch it twice)
         char* p = nullptr; size_t cap = 0, n = 0;
-        void ensure(size_t want) { if (want > cap) { free(p); cap = want + want / 8 + 4096; p = (char*)malloc(cap); } }
+        bool ensure(size_t want) {
+            if (want <= cap) return true;
+            const size_t c2 = want + want / 8 + 4096; char* q = (char*)malloc(c2);
+            if (!q) return false;                                     // (the old buffer stays as it was)
+            free(p); p = q; cap = c2; return true;
+        }
         ~RawBuf() { free(p); }
     } out[4];                        // sam, fa, log, te
     // 4-bit SEQ form (tc_sam_pack_seq): packed rows, their offsets, the alphabet they index
@@ -480,6 +485,7 @@ char* tc_sam_rnames(const char* text, int64_t len, int64_t* out_len) {
         if (seen.emplace(std::string(text + a, (size_t)(b - a)), 1).second) { out.append(text + a, (size_t)(b - a)); out.push_back('\n'); }
     }
     char* r = (char*)malloc(out.size() + 1);
+    if (!r) { if (out_len) *out_len = 0; return nullptr; }           // (callers treat NULL as "out of memory")
     memcpy(r, out.data(), out.size()); r[out.size()] = 0;
     if (out_len) *out_len = (int64_t)out.size();
     return r;
@@ -498,6 +504,7 @@ char* tc_sam_header_lines(const char* text, int64_t len, int64_t* out_len) {
         if (s < e && text[s] == '@') { out.append(text + s, (size_t)(e - s)); out.push_back('\n'); }
     }
     char* r = (char*)malloc(out.size() + 1);
+    if (!r) { if (out_len) *out_len = 0; return nullptr; }           // (callers treat NULL as "out of memory")
     memcpy(r, out.data(), out.size()); r[out.size()] = 0;
     if (out_len) *out_len = (int64_t)out.size();
     return r;
@@ -647,7 +654,8 @@ int tc_sam_render(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_
     std::vector<size_t> off((size_t)(4 * (T + 1)), 0);
     for (int q = 0; q < 4; q++) {
         for (int k = 0; k < T; k++) off[(size_t)(q * (T + 1) + k + 1)] = off[(size_t)(q * (T + 1) + k)] + (*parts[q])[(size_t)k].n;
-        S->out[q].ensure(off[(size_t)(q * (T + 1) + T)] + 1); S->out[q].n = off[(size_t)(q * (T + 1) + T)];
+        if (!S->out[q].ensure(off[(size_t)(q * (T + 1) + T)] + 1)) { set_err(err, err_cap, "tc_sam_render: out of host memory"); return TC_E_ARG; }
+        S->out[q].n = off[(size_t)(q * (T + 1) + T)];
     }
     {
         std::vector<std::thread> tj;

@@ -269,6 +269,8 @@ def sam_rnames(lib, text):
     """Set of RNAME strings of the alignment lines of a SAM text (bytes)."""
     n = C.c_int64()
     p = lib.tc_sam_rnames(text, len(text), C.byref(n))
+    if not p:
+        raise MemoryError("tc_sam_rnames")
     try:
         return set(C.string_at(p, n.value).decode().split("\n")) - {""}
     finally:
@@ -279,6 +281,8 @@ def sam_header_lines(lib, text):
     """The '@' lines of a SAM text (bytes), newline-terminated, as str."""
     n = C.c_int64()
     p = lib.tc_sam_header_lines(text, len(text), C.byref(n))
+    if not p:
+        raise MemoryError("tc_sam_header_lines")
     try:
         return C.string_at(p, n.value).decode()
     finally:

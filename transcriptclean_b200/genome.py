@@ -128,12 +128,13 @@ class GenomeImage:
         return g
 
     # ------------------------------------------------------------------ on-disk image
-    def save(self, path):
-        """The packed image as one .npz (what the device gets; 0.375 bytes per base)."""
+    def save(self, path, source=None):
+        """The packed image as one .npz (what the device gets; 0.375 bytes per base).  `source` = fingerprint of the FASTA
+        it was made from (fasta_fingerprint), kept so that a cache is never trusted for another file."""
         st, en, by = self.exceptions()
         with open(path, "wb") as f:
             np.savez(f, names=np.asarray(self.names), chrom_len=self.chrom_len, bases2=self.bases2, lower1=self.lower1,
-                     exc_start=st, exc_end=en, exc_byte=by)
+                     exc_start=st, exc_end=en, exc_byte=by, source=np.asarray(source if source is not None else [], dtype=np.int64))
 
     @classmethod
     def load(cls, path):
@@ -143,27 +144,47 @@ class GenomeImage:
             raise ValueError("genome image %s does not match its own contig table" % path)
         g.bases2, g.lower1 = z["bases2"], z["lower1"]
         g._exc = list(zip(z["exc_start"].tolist(), z["exc_end"].tolist(), z["exc_byte"].tolist()))
+        g.source = z["source"].tolist() if "source" in z.files else []
         return g
+
+    @staticmethod
+    def fasta_fingerprint(path):
+        """[size, mtime_ns, crc32 of the first MB, crc32 of the last MB]: cheap, and different for a different genome copied
+        over the same path whatever its time stamps say."""
+        import os
+        import zlib
+        st = os.stat(path)
+        with open(path, "rb") as f:
+            head = f.read(1 << 20)
+            f.seek(max(0, st.st_size - (1 << 20)))
+            tail = f.read(1 << 20)
+        return [int(st.st_size), int(st.st_mtime_ns), zlib.crc32(head), zlib.crc32(tail)]
 
     @classmethod
     def from_fasta_cached(cls, path, cache=None):
         """from_fasta, keeping the packed image next to the FASTA (<fasta>.tcb200.npz, like pyfaidx keeps its .fai
-        there): packing a 3-Gb genome takes minutes, loading the image seconds.  The image is rebuilt when the
-        FASTA is newer; a read-only directory just means no cache.  TC_GENOME_CACHE=0 turns it off."""
+        there): packing a 3-Gb genome takes minutes, loading the image seconds.  The image is rebuilt unless it was made from
+        this very file (size, mtime and checksums of its first and last MB); a read-only directory just means no cache.
+        TC_GENOME_CACHE=0 turns it off."""
         import os
         if os.environ.get("TC_GENOME_CACHE", "1") == "0":
             return cls.from_fasta(path)
         cache = cache or str(path) + ".tcb200.npz"
+        fp = cls.fasta_fingerprint(path)
         try:
-            if os.path.exists(cache) and os.path.getmtime(cache) >= os.path.getmtime(path):
-                return cls.load(cache)
+            if os.path.exists(cache):
+                g = cls.load(cache)
+                if g.source == fp:
+                    print("Using the packed genome image %s" % cache)
+                    return g
         except Exception:
             pass
         g = cls.from_fasta(path)
         try:
             tmp = cache + ".tmp%d" % os.getpid()
-            g.save(tmp)
+            g.save(tmp, source=fp)
             os.replace(tmp, cache)
+            print("Wrote the packed genome image %s (reused while the FASTA stays the same file)" % cache)
         except Exception:
             pass
         return g
