@@ -134,6 +134,29 @@ class Workload:
             lines.append("\t".join(f))
         return lines
 
+    def write_sam(self, path, cols, nm, lo, hi, header=True):
+        """SAM file with reads [lo, hi) (the lines of sam_lines(), written by the C generator)."""
+        if header:                                   # (without a header the reads are appended to the file)
+            with open(path, "w") as f:
+                f.write("@HD\tVN:1.0\tSO:unsorted\n@SQ\tSN:%s\tLN:%d\n" % (self.chrom, self.chrom_len))
+        self.lib.tcsynth_write_sam.restype = C.c_int64
+        self.lib.tcsynth_write_sam.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, C.c_int64] + [C.c_void_p] * 12
+        a = [np.ascontiguousarray(cols[k]) for k in ("flag", "chrom", "pos", "tags", "seq_off", "seq", "cig_off", "cig_op", "cig_len", "md_off", "md")]
+        nm = np.ascontiguousarray(nm, dtype=np.int32)
+        r = self.lib.tcsynth_write_sam(path.encode(), b"a", self.chrom.encode(), lo, hi, *[x.ctypes.data for x in a], nm.ctypes.data)
+        if r < 0:
+            raise IOError("cannot write " + path)
+        return r
+
+    def write_fasta(self, path, width=60):
+        n = len(self.genome)
+        pad = (-n) % width
+        body = np.concatenate((self.genome, np.full(pad, ord("\n"), dtype=np.uint8))).reshape(-1, width)
+        lines = np.concatenate((body, np.full((body.shape[0], 1), ord("\n"), dtype=np.uint8)), axis=1).tobytes()
+        with open(path, "wb") as f:
+            f.write((">%s\n" % self.chrom).encode())
+            f.write(lines[:len(lines) - pad] if pad == 0 else lines[:-(pad + 1)] + b"\n")
+
     def close(self):
         self.lib.tcsynth_free_genes(C.byref(self.genes))
 
