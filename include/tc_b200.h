@@ -235,6 +235,11 @@ int tc_batch_download(tc_ctx* ctx, tc_batch_out* out);
 
 int tc_get_timing(tc_ctx* ctx, tc_timing* t);
 
+/* Splice motif of n introns with the junction kernel's motif fetch (getSJMotifCode, spliceJunction.py:71-89; getIntronMotif of
+ * accessory_scripts/get_SJs_from_gtf.py:44-66): code[k] = 1 GTAG, 2 CTAC, 3 GCAG, 4 CTGC, 5 ATAC, 6 GTAT, 0 anything else
+ * (including an intron end past the contig), -1 where pyfaidx would raise (a coordinate below 1).  Host arrays in and out. */
+int tc_intron_motifs(tc_ctx* ctx, int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end, int8_t* code);
+
 /* ---- host side: SAM text <-> columns (csrc/tc_host.cpp, multi-threaded C++; no GPU involved) ----
  * tc_sam_parse replaces split_SAM (TranscriptClean.py:519-541) + the field / tag handling of
  * Transcript.__init__ (transcript.py:10-72): header lines are set aside, alignment lines become a

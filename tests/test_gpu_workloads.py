@@ -149,3 +149,32 @@ def test_plane_offsets_beyond_2_31(setup):
         assert small.read_seq(i) == large.read_seq(i), i
         assert small.md[small.md_off[i]:small.md_off[i] + small.md_len[i]].tobytes() == large.md[large.md_off[i]:large.md_off[i] + large.md_len[i]].tobytes(), i
     assert int((np.asarray(small.counters)[:, 2] > 0).sum()) + int((np.asarray(small.counters)[:, 5] > 0).sum()) > 100   # variant hits happened
+
+
+def test_command_line_on_the_gpu(monkeypatch):
+    """The `transcriptclean` command line itself on the GPU: files in, the four files out, blocks of a few kB
+    through three pipelined workers per GPU on every visible GPU; --dryRun writes the two logs only."""
+    import synth
+    from transcriptclean_b200 import cli
+    case = synth.make_case(4711, n_reads=400)
+    d = tempfile.mkdtemp(prefix="tc_cli_gpu_")
+    case.write_fasta(d + "/g.fa"); case.write_sam(d + "/in.sam"); case.write_sj(d + "/sj.tab"); case.write_vcf(d + "/v.vcf")
+    monkeypatch.setenv("TC_CLI_BLOCK_BYTES", "20000")
+    o = cli.get_options(["-s", d + "/in.sam", "-g", d + "/g.fa", "-j", d + "/sj.tab", "-v", d + "/v.vcf", "-t", "8", "-o", d + "/TC", "--canonOnly"])
+    cli.run(o)
+    want = pipeline.oracle_texts(case.genome, case.lines, d + "/sj.tab", d + "/v.vcf", {"canonOnly": True})
+    sam = open(d + "/TC_clean.sam").read()
+    assert sam.startswith("@HD")
+    assert "".join(l + "\n" for l in sam.splitlines() if not l.startswith("@")) == want["sam"]
+    assert open(d + "/TC_clean.fa").read() == want["fa"]
+    assert open(d + "/TC_clean.log").read() == cli.LOG_HEADER + want["log"]
+    assert open(d + "/TC_clean.TE.log").read() == cli.TE_HEADER + want["te"]
+    assert not [f for f in os.listdir(d) if f.endswith(".partial")]
+    o = cli.get_options(["-s", d + "/in.sam", "-g", d + "/g.fa", "--dryRun", "-o", d + "/DRY"])
+    clean = synth.make_case(4711, n_reads=400, quirks=False)
+    clean.write_sam(d + "/in.sam")
+    cli.run(o)
+    want = pipeline.oracle_texts(clean.genome, clean.lines, None, None, {}, dry=True)
+    assert open(d + "/DRY_clean.log").read() == cli.LOG_HEADER + want["log"]
+    assert open(d + "/DRY_clean.TE.log").read() == cli.TE_HEADER + want["te"]
+    assert not os.path.exists(d + "/DRY_clean.sam")

@@ -204,6 +204,7 @@ static void host_nmmd(const GenomeDev& G, const uint8_t* seq, const CigSrc& cs, 
 // Everything that belongs to one batch (or one chunk of a pipelined batch) on the device.
 struct Slot {
     DevBuf b_seqp, b_seq_poff, b_exc_pos, b_exc_byte;   // 4-bit / 2-bit SEQ: packed input rows + their offsets; the 2-bit form's listed bases
+    int unpack_bits = 0; int64_t unpack_p0 = 0, unpack_s0 = 0, unpack_nexc = 0; size_t unpack_d0 = 0;   // expansion still to be launched (slot_run does it on its own stream)
     DevBuf b_flag, b_chrom, b_pos, b_tags, b_seq_off, b_seq, b_cig_off, b_cig_op, b_cig_len, b_md_off, b_md, b_ji_off, b_ji;
     BatchDev B; int64_t n = 0, n_seq = 0, n_cig = 0, n_md = 0, n_ji = 0, md_base = 0;
     int64_t seq_lo_word = 0, seq_hi_word = 0;       // words of B.seq (as uint32) that may be dereferenced
@@ -295,7 +296,17 @@ __global__ void __launch_bounds__(256) k_seq_unpack(int64_t n, const int64_t* se
         }
     }
 }
-// 2-bit SEQ rows -> ASCII rows, one warp per read: a lane turns one byte (4 bases) into 4 characters
+// 8 characters (lo, hi) to d, whose address mod 4 is `mis` (the same for every 8-byte group of a row): the widest naturally aligned stores
+__device__ __forceinline__ void store8(uint8_t* d, uint32_t lo, uint32_t hi, int left, int mis) {
+    if (left < 8) {
+#pragma unroll
+        for (int k = 0; k < 7; k++) if (k < left) d[k] = (uint8_t)((k < 4 ? lo : hi) >> (8 * (k & 3)));
+    } else if (mis == 0) { reinterpret_cast<uint32_t*>(d)[0] = lo; reinterpret_cast<uint32_t*>(d)[1] = hi; }
+    else if (mis == 2) { *reinterpret_cast<uint16_t*>(d) = (uint16_t)lo; *reinterpret_cast<uint32_t*>(d + 2) = (lo >> 16) | (hi << 16); *reinterpret_cast<uint16_t*>(d + 6) = (uint16_t)(hi >> 16); }
+    else if (mis == 1) { d[0] = (uint8_t)lo; *reinterpret_cast<uint16_t*>(d + 1) = (uint16_t)(lo >> 8); *reinterpret_cast<uint32_t*>(d + 3) = (lo >> 24) | (hi << 8); d[7] = (uint8_t)(hi >> 24); }
+    else { d[0] = (uint8_t)lo; *reinterpret_cast<uint32_t*>(d + 1) = (lo >> 8) | (hi << 24); *reinterpret_cast<uint16_t*>(d + 5) = (uint16_t)(hi >> 8); d[7] = (uint8_t)(hi >> 24); }
+}
+// 2-bit SEQ rows -> ASCII rows, one warp per read: a lane turns two bytes (8 bases) into 8 characters
 __global__ void __launch_bounds__(256) k_seq_unpack2(int64_t n, const int64_t* seq_off, const int64_t* poff, const uint8_t* packed, uint8_t* seq) {
     __shared__ uint32_t lut[256];
     for (int t = threadIdx.x; t < 256; t += blockDim.x) {
@@ -307,14 +318,10 @@ __global__ void __launch_bounds__(256) k_seq_unpack2(int64_t n, const int64_t* s
     const int lane = threadIdx.x & 31; const int64_t nw = (int64_t)gridDim.x * 8;
     for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += nw) {
         const int64_t o = seq_off[i]; const int L = (int)(seq_off[i + 1] - o);
-        const uint8_t* src = packed + poff[i]; uint8_t* dst = seq + o;
+        const uint16_t* src = reinterpret_cast<const uint16_t*>(packed + poff[i]);     // rows start at multiples of 4 bytes
+        uint8_t* dst = seq + o;
         const int mis = (int)(reinterpret_cast<uintptr_t>(dst) & 3);
-        for (int b = lane; b * 4 < L; b += 32) {
-            const uint32_t x = lut[src[b]]; const int left = L - b * 4; uint8_t* d = dst + b * 4;
-            if (left >= 4 && mis == 0) *reinterpret_cast<uint32_t*>(d) = x;
-            else if (left >= 4 && mis == 2) { *reinterpret_cast<uint16_t*>(d) = (uint16_t)x; *reinterpret_cast<uint16_t*>(d + 2) = (uint16_t)(x >> 16); }
-            else { for (int k = 0; k < 4; k++) if (k < left) d[k] = (uint8_t)(x >> (8 * k)); }
-        }
+        for (int w = lane; w * 8 < L; w += 32) { const uint32_t x = src[w]; store8(dst + w * 8, lut[x & 255u], lut[x >> 8], L - w * 8, mis); }
     }
 }
 __global__ void k_seq_patch(int64_t n_exc, const int64_t* pos, const uint8_t* byte, uint8_t* seq) {
@@ -562,23 +569,17 @@ static int seq_upload_packed(tc_ctx* ctx, Slot& S, const tc_batch_in* in, int64_
     const int64_t p0 = in->seq_poff[r0], pbytes = in->seq_poff[r1] - p0;
     if (be_h2d(ctx, st, S.b_seqp, 0, in->seq + p0, (size_t)pbytes, 64) || be_h2d(ctx, st, S.b_seq_poff, 0, in->seq_poff + r0, (size_t)(n + 1) * 8)) return TC_E_CUDA;
     const int64_t s0 = in->seq_off[r0], s1 = in->seq_off[r1];
-    uint8_t* dst = (uint8_t*)S.b_seq.p + d0 - s0; const uint8_t* src = (const uint8_t*)S.b_seqp.p - p0;
     int64_t e0 = 0, e1 = 0;                                            // listed bases of these reads (exc_pos is ascending)
     if (two && in->n_exc > 0) {
         e0 = std::lower_bound(in->exc_pos, in->exc_pos + in->n_exc, s0) - in->exc_pos; e1 = std::lower_bound(in->exc_pos, in->exc_pos + in->n_exc, s1) - in->exc_pos;
         if (e1 > e0 && (be_h2d(ctx, st, S.b_exc_pos, 0, in->exc_pos + e0, (size_t)(e1 - e0) * 8) || be_h2d(ctx, st, S.b_exc_byte, 0, in->exc_byte + e0, (size_t)(e1 - e0)))) return TC_E_CUDA;
     }
 #ifndef TC_HOSTSIM
-    int64_t wb = (n + 7) / 8; int g = (int)(wb < 148 * 8 ? wb : 148 * 8);
-    if (two) {
-        k_seq_unpack2<<<g, 256, 0, st>>>(n, (const int64_t*)S.b_seq_off.p, (const int64_t*)S.b_seq_poff.p, src, dst); ctx->tm.launches++;
-        if (e1 > e0) { k_seq_patch<<<(int)std::min<int64_t>((e1 - e0 + 255) / 256, 1184), 256, 0, st>>>(e1 - e0, (const int64_t*)S.b_exc_pos.p, (const uint8_t*)S.b_exc_byte.p, dst); ctx->tm.launches++; }
-    } else {
-        Alphabet A; memcpy(A.c, ctx->alphabet, 16);
-        k_seq_unpack<<<g, 256, 0, st>>>(n, (const int64_t*)S.b_seq_off.p, (const int64_t*)S.b_seq_poff.p, src, dst, A); ctx->tm.launches++;
-    }
-    CK(cudaGetLastError());
+    // the expansion itself is launched by slot_run on the compute stream: the upload stream carries copies only, so the next
+    // chunk's bytes follow at once (the kernel stream has slack, the host link has none)
+    S.unpack_bits = two ? 2 : 4; S.unpack_p0 = p0; S.unpack_s0 = s0; S.unpack_nexc = e1 - e0; S.unpack_d0 = d0;
 #else
+    uint8_t* dst = (uint8_t*)S.b_seq.p + d0 - s0; const uint8_t* src = (const uint8_t*)S.b_seqp.p - p0;
     const int64_t* so = (const int64_t*)S.b_seq_off.p; const int64_t* po = (const int64_t*)S.b_seq_poff.p;
     for (int64_t i = 0; i < n; i++)
         for (int64_t k = 0; k < so[i + 1] - so[i]; k++) {
@@ -594,7 +595,7 @@ static int seq_upload_packed(tc_ctx* ctx, Slot& S, const tc_batch_in* in, int64_
 // data pointers are shifted so that they can be applied unchanged.
 static int slot_upload(tc_ctx* ctx, Slot& S, const tc_batch_in* in, int64_t r0, int64_t r1, stream_t st) {
     const int64_t n = r1 - r0;
-    S.n = n; S.ran = false;
+    S.n = n; S.ran = false; S.unpack_bits = 0;
     static const int64_t zero_off[1] = {0};
     const int64_t s0 = n ? in->seq_off[r0] : 0, c0 = n ? in->cig_off[r0] : 0, m0 = n ? in->md_off[r0] : 0, j0 = n ? in->ji_off[r0] : 0;
     S.n_seq = n ? in->seq_off[r1] - s0 : 0; S.n_cig = n ? in->cig_off[r1] - c0 : 0;
@@ -725,6 +726,19 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
 #define TC_TPB 128
 #endif
     const int TPB = TC_TPB; const int gb = (int)((n + TPB - 1) / TPB);
+    if (S.unpack_bits) {                                               // packed SEQ rows -> the ASCII rows the kernels read
+        uint8_t* dst = (uint8_t*)S.b_seq.p + S.unpack_d0 - S.unpack_s0; const uint8_t* src = (const uint8_t*)S.b_seqp.p - S.unpack_p0;
+        int64_t wb0 = (n + 7) / 8; int g = (int)(wb0 < 148 * 8 ? wb0 : 148 * 8);
+        if (S.unpack_bits == 2) {
+            k_seq_unpack2<<<g, 256, 0, st>>>(n, (const int64_t*)S.b_seq_off.p, (const int64_t*)S.b_seq_poff.p, src, dst); ctx->tm.launches++;
+            if (S.unpack_nexc > 0) { k_seq_patch<<<(int)std::min<int64_t>((S.unpack_nexc + 255) / 256, 1184), 256, 0, st>>>(S.unpack_nexc, (const int64_t*)S.b_exc_pos.p, (const uint8_t*)S.b_exc_byte.p, dst); ctx->tm.launches++; }
+        } else {
+            Alphabet A; memcpy(A.c, ctx->alphabet, 16);
+            k_seq_unpack<<<g, 256, 0, st>>>(n, (const int64_t*)S.b_seq_off.p, (const int64_t*)S.b_seq_poff.p, src, dst, A); ctx->tm.launches++;
+        }
+        CK(cudaGetLastError());
+        S.unpack_bits = 0;
+    }
     int nsm = 148; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
     int64_t wb = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; int gw = (int)(wb < (int64_t)nsm * 8 ? wb : (int64_t)nsm * 8);
     if (timed) CK(cudaEventRecord(ctx->ev[2], st));
@@ -1077,6 +1091,36 @@ int tc_ctx_set_pipeline(tc_ctx* ctx, int64_t chunk_reads) {
     if (!ctx || chunk_reads < 0) return TC_E_ARG;
     ctx->chunk_reads = chunk_reads;
     return TC_OK;
+}
+
+#ifndef TC_HOSTSIM
+__global__ void k_motifs(GenomeDev G, int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end, int8_t* code) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        code[k] = (chrom[k] < 0 || chrom[k] >= G.n_chrom) ? (int8_t)-1 : (int8_t)intron_motif(G, chrom[k], start[k], end[k]);
+}
+#endif
+int tc_intron_motifs(tc_ctx* ctx, int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end, int8_t* code) {
+    if (!ctx || n < 0 || (n && (!chrom || !start || !end || !code))) return TC_E_ARG;
+    if (!ctx->have_genome) { ctx->err = "tc_intron_motifs: load a genome first"; return TC_E_STATE; }
+    if (n == 0) return TC_OK;
+#ifndef TC_HOSTSIM
+    CK(cudaSetDevice(ctx->device));
+    DevBuf dc, ds, de, dk;
+    stream_t st = main_stream(ctx);
+    int rc = TC_OK;
+    if (be_h2d(ctx, st, dc, 0, chrom, (size_t)n * 4) || be_h2d(ctx, st, ds, 0, start, (size_t)n * 4) || be_h2d(ctx, st, de, 0, end, (size_t)n * 4) ||
+        dk.ensure((size_t)n + 8) != cudaSuccess) rc = TC_E_CUDA;
+    if (!rc) {
+        k_motifs<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(ctx->G, n, (const int32_t*)dc.p, (const int32_t*)ds.p, (const int32_t*)de.p, (int8_t*)dk.p);
+        if (cudaGetLastError() != cudaSuccess || cudaMemcpyAsync(code, dk.p, (size_t)n, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { ctx->err = "tc_intron_motifs: CUDA error"; rc = TC_E_CUDA; }
+    }
+    dc.release(); ds.release(); de.release(); dk.release();
+    return rc;
+#else
+    for (int64_t k = 0; k < n; k++) code[k] = (chrom[k] < 0 || chrom[k] >= ctx->G.n_chrom) ? (int8_t)-1 : (int8_t)intron_motif(ctx->G, chrom[k], start[k], end[k]);
+    return TC_OK;
+#endif
 }
 
 int tc_get_timing(tc_ctx* ctx, tc_timing* t) { if (!ctx || !t) return TC_E_ARG; *t = ctx->tm; return TC_OK; }

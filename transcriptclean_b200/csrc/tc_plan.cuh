@@ -632,6 +632,14 @@ TC_HD bool junction_code(const Params& P, int chrom, int strand, int32_t b0, int
     return true;
 }
 
+// the motif part of checkSpliceMotif alone (sj.py:48-68, 71-89): -1 = pyfaidx would raise (a coordinate below 1)
+TC_HD int intron_motif(const GenomeDev& G, int chrom, int32_t b0, int32_t b1) {
+    if (b0 < 1 || b1 - 1 < 1) return -1;
+    if (fetch_len(G, chrom, b0, (int64_t)b0 + 1) != 2 || fetch_len(G, chrom, (int64_t)b1 - 1, b1) != 2) return 0;
+    const int64_t goff = G.chrom_off[chrom] - 1, ga = goff + b0, gb = goff + b1 - 1;
+    return motif_code(genome_byte(G, ga), genome_byte(G, ga + 1), genome_byte(G, gb), genome_byte(G, gb + 1));
+}
+
 struct ExonLoc { int lo, hi; int64_t q0, q1; int nidx; };
 // group_CIGAR_by_exon_and_intron (TC.py:1379-1412): exon t = ops between the t-th and (t+1)-th N;
 // its sequence = the M/S/I bases in that range.

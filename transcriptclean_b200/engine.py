@@ -13,7 +13,7 @@ EXPORTS = ["tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_set_optio
            "tc_dryrun_batch", "tc_batch_upload", "tc_batch_run", "tc_batch_download", "tc_get_timing",
            "tc_ctx_set_pipeline", "tc_sam_parse", "tc_sam_free", "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_render", "tc_sam_render_parts",
            "tc_sam_rnames", "tc_free", "tc_ctx_set_alphabet", "tc_seq_pack", "tc_seq_packed_size", "tc_seq_pack2", "tc_seq_packed2_size", "tc_sam_pack_seq", "tc_sam_header_lines",
-           "tc_vcf_parse", "tc_vcf_tables", "tc_vcf_n_records", "tc_vcf_free", "tc_sj_parse", "tc_sj_tables", "tc_sj_free"]
+           "tc_vcf_parse", "tc_vcf_tables", "tc_vcf_n_records", "tc_vcf_free", "tc_sj_parse", "tc_sj_tables", "tc_sj_free", "tc_intron_motifs"]
 
 # status bits (include/tc_b200.h)
 ST_CLASS_MASK, ST_FALLBACK, ST_CIGAR_REWRITTEN = 3, 1 << 2, 1 << 3
@@ -115,6 +115,7 @@ def _declare(lib):
     lib.tc_sam_pack_seq.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32]
     lib.tc_sam_render.argtypes = [C.c_void_p, C.POINTER(_BatchOut)] + [C.c_int32] * 4 + [C.POINTER(C.c_void_p), C.POINTER(C.c_int64)] * 4 + [C.c_char_p, C.c_int64]
     lib.tc_sam_render_parts.argtypes = [C.c_void_p, C.POINTER(_BatchOut)] + [C.c_int32] * 4 + [C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_int32, C.c_char_p, C.c_int64]
+    lib.tc_intron_motifs.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.tc_vcf_parse.restype = C.c_void_p
     lib.tc_vcf_parse.argtypes = [C.c_char_p, C.c_int64, C.c_int32, C.POINTER(C.c_char_p), C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int64]
     lib.tc_vcf_tables.restype = None
@@ -538,6 +539,14 @@ class Engine:
 
     def parse_sam(self, text, genome, n_threads=None):
         return SamText(self._lib, text, genome, n_threads, self.alphabet if (self.seq4 and self.seq4_text) else None)
+
+    def intron_motifs(self, chrom, start, end):
+        """Motif codes (0-6, -1 where a coordinate is below 1) of introns [start, end] (1-based inclusive) on contig ids `chrom`,
+        with the junction kernel's motif fetch on the device."""
+        c, s, e = (np.ascontiguousarray(x, dtype=np.int32) for x in (chrom, start, end))
+        out = np.zeros(len(c), dtype=np.int8)
+        self._check(self._lib.tc_intron_motifs(self._ctx, len(c), _ptr(c), _ptr(s), _ptr(e), _ptr(out)), "tc_intron_motifs")
+        return out
 
     def timing(self):
         t = Timing()
