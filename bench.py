@@ -392,9 +392,10 @@ def main():
     peak, peak_src = peaks()
     achieved = dom_bytes / (per[dom] * 1e-3) / 1e9
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_k_emit_traffic.json")
-    if dom == "k_emit_ms" and os.path.exists(tpath):      # DRAM bytes per read from the committed ncu --set full capture
-        traffic = json.load(open(tpath))["dram_bytes_per_read"] * args.reads
+    tpath = os.path.join(ROOT, "profiles", "r02_kernel_traffic.json")
+    if os.path.exists(tpath):            # DRAM bytes per read of that kernel from the committed ncu --set full captures
+        per_read = json.load(open(tpath))["dram_bytes_per_read"].get(args.shape, {}).get(dom.replace("_ms", ""))
+        traffic = per_read * args.reads if per_read is not None else None
 
     reads_total = args.reads * world
     line = {

@@ -7,7 +7,7 @@
 // all from the read's 128-byte plan row.  A light kernel of its own (no shared memory, few registers, many resident
 // warps): these phases are latency, not bytes, and inside k_emit they held its 30 resident warps up for a fifth of its time.
 #ifndef TC_SMALL_BLOCKS
-#define TC_SMALL_BLOCKS 5
+#define TC_SMALL_BLOCKS 4
 #endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_SMALL_BLOCKS) k_small(Params P, OutDev O, int dry) {
@@ -33,41 +33,58 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_SMALL_BLOCKS) k_small
         const tc_te* const ws_te = reinterpret_cast<const tc_te*>(ws + 3ll * seg_cap + 3ll * cig_cap);
         u64* dst = O.te + o_te;
         if (dry) { for (int k = lane; k < nte; k += 32) { const tc_te r = ws_te[k]; dst[k] = te_word(r.a, r.size, r.type, r.status, r.reason); } continue; }
+        const int cb = ((pflags >> 2) & 3) - 1, sb = ((pflags >> 4) & 3) - 1;
+        // The lists of a read are independent of one another, but every loop below uses what it loads at once, so taken one
+        // after the other they are five memory round trips in a row per read (ncu: 9 stalled warps per issue, all on loads).
+        // The first round of every list is therefore asked for here, together, and each loop asks for its next round before
+        // it works on the current one.
+        const u64* const cigs = ws + 3ll * seg_cap + (int64_t)(cb < 0 ? 0 : cb) * cig_cap;
+        const u64* const segs = ws + (int64_t)(sb < 0 ? 0 : sb) * seg_cap;
+        const int32_t* const jn = reinterpret_cast<const int32_t*>(ws + 3ll * seg_cap + 3ll * cig_cap + 2ll * te_cap);
+        const ulonglong2* const te2 = reinterpret_cast<const ulonglong2*>(ws_te);
+        ulonglong2 te_nx = lane < nte ? te2[lane] : make_ulonglong2(0ull, 0ull);
+        u64 cg_nx = (cb >= 0 && lane < ncig) ? cigs[lane] : 0ull;
+        u64 sg_nx = (sb >= 0 && lane < ns) ? segs[lane] : 0ull;
+        int j5 = 0, j6 = 0, j7 = 0;
+        if (lane < nj) { const int32_t* r = jn + lane * JN_STRIDE; j5 = r[5]; j6 = r[6]; j7 = r[7]; }
         int base0 = 0, base1 = te_mm, base2 = te_mm + te_ins, base3 = te_mm + te_ins + te_del;
         for (int c = 0; c < nte; c += 32) {
             const int k = c + lane; const bool valid = k < nte;
-            tc_te r; int t = -1;
-            if (valid) { r = ws_te[k]; t = r.type; }
+            const ulonglong2 raw = te_nx;
+            if (k + 32 < nte) te_nx = te2[k + 32];
+            // (a workspace row: a | b << 32, size | type << 32 | status << 40 | reason << 48 - te_put in tc_plan.cuh)
+            const int32_t ra = (int32_t)(uint32_t)raw.x, rb = (int32_t)(uint32_t)(raw.x >> 32), rsize = (int32_t)(uint32_t)raw.y;
+            const int t = valid ? (int)((raw.y >> 32) & 255u) : -1, rstatus = (int)((raw.y >> 40) & 255u), rreason = (int)((raw.y >> 48) & 255u);
             const unsigned m0 = __ballot_sync(FULL, t == 0), m1 = __ballot_sync(FULL, t == 1), m2 = __ballot_sync(FULL, t == 2), m3 = __ballot_sync(FULL, t == 3);
             if (valid) {
-                const u64 w = te_word(r.a, r.size, r.type, r.status, r.reason);
-                if (t == 3) { const int slot = base3 + 2 * __popc(m3 & lt); dst[slot] = w; dst[slot + 1] = (u64)(uint32_t)r.b; }   // a junction row: two words
+                const u64 w = te_word(ra, rsize, t, rstatus, rreason);
+                if (t == 3) { const int slot = base3 + 2 * __popc(m3 & lt); dst[slot] = w; dst[slot + 1] = (u64)(uint32_t)rb; }   // a junction row: two words
                 else dst[t == 0 ? base0 + __popc(m0 & lt) : t == 1 ? base1 + __popc(m1 & lt) : base2 + __popc(m2 & lt)] = w;
             }
             base0 += __popc(m0); base1 += __popc(m1); base2 += __popc(m2); base3 += 2 * __popc(m3);
         }
-        const int cb = ((pflags >> 2) & 3) - 1, sb = ((pflags >> 4) & 3) - 1;
         if (cb >= 0) {                                                 // (an untouched CIGAR is not sent back)
-            const u64* c = ws + 3ll * seg_cap + (int64_t)cb * cig_cap;
             uint8_t* dop = O.cig_op + o_cig; int32_t* dl = O.cig_len + o_cig;
-            for (int k = lane; k < ncig; k += 32) { const u64 x = c[k]; dop[k] = (uint8_t)cg_op(x); dl[k] = cg_len(x); }
+            for (int k = lane; k < ncig; k += 32) { const u64 x = cg_nx; if (k + 32 < ncig) cg_nx = cigs[k + 32]; dop[k] = (uint8_t)cg_op(x); dl[k] = cg_len(x); }
         }
         if (nj > 0) {
             int8_t* djm = O.jm + o_jn; int32_t* dji = O.ji + 2 * o_jn;
-            const int32_t* jn = reinterpret_cast<const int32_t*>(ws + 3ll * seg_cap + 3ll * cig_cap + 2ll * te_cap);
-            for (int k = lane; k < nj; k += 32) { const int32_t* r = jn + k * JN_STRIDE; djm[k] = (int8_t)r[7]; dji[2 * k] = r[5]; dji[2 * k + 1] = r[6]; }
+            for (int k = lane; k < nj; k += 32) {
+                if (k >= 32) { const int32_t* r = jn + k * JN_STRIDE; j5 = r[5]; j6 = r[6]; j7 = r[7]; }
+                djm[k] = (int8_t)j7; dji[2 * k] = j5; dji[2 * k + 1] = j6;
+            }
         }
         // ---- SEQ delta (delta_encode in tc_b200.cu is the serial twin): one pass over the segment list.  Its size is known
         //      (EP_DLEN, kept by the planner) and its place came out of the scans, so every segment's bytes go straight out.
         const int dlen = PF(EP_DLEN); const int64_t o_dl = PF64_2(EP_ODL_LO, EP_ODL_HI);
         if (lane == 0) { O.delta_off[i] = o_dl; O.delta_len[i] = dlen; }
         if (sb < 0 || dlen <= 0) continue;
-        const u64* segs = ws + (int64_t)sb * seg_cap;
         uint8_t* const dout = O.delta_pool + o_dl;
         int cur = 0, off0 = 0;                                         // input cursor (end of the latest input slice), bytes so far
         for (int s0 = 0; s0 < ns; s0 += 32) {
             const int s = s0 + lane; const bool valid = s < ns;
-            const u64 sg = valid ? segs[s] : 0ull;
+            const u64 sg = valid ? sg_nx : 0ull;
+            if (s + 32 < ns) sg_nx = segs[s + 32];
             const int len = valid ? (int)seg_len(sg) : 0; const int64_t src = seg_src(sg);
             const bool isR = len > 0 && seg_kind(sg) == 0, isG = len > 0 && seg_kind(sg) == 1;
             const unsigned mR = __ballot_sync(FULL, isR);
