@@ -245,6 +245,7 @@ def main():
                     "launch list holds exactly the kernels of the timed region")
     ap.add_argument("--no-dry", action="store_true", help="skip the --dryRun measurement")
     ap.add_argument("--seq8", action="store_true", help="send SEQ as ASCII instead of a packed form")
+    ap.add_argument("--cig40", action="store_true", help="send the CIGAR as op + length arrays instead of 16-bit words")
     ap.add_argument("--seq4", action="store_true", help="send SEQ as 4-bit codes instead of the 2-bit form")
     ap.add_argument("--debug-mask", type=int, default=0, help="profiling aid: skip phases of k_emit (results invalid)")
     ap.add_argument("--parity-reads", type=int, default=-1, help="reads of the timed batch whose texts are compared with the oracle's "
@@ -284,6 +285,10 @@ def main():
         hcols = (None if args.seq4 else eng.pack_cols2(cols)) or eng.pack_cols(cols)
         if hcols is None:
             raise SystemExit("the synthetic SEQ column holds bytes outside the engine's alphabet")
+    if not args.cig40:
+        hcols = eng.pack_cigar(hcols)
+        if "cig16" in hcols:              # the op / length arrays stay on the host
+            hcols = {k: v for k, v in hcols.items() if k not in ("cig_op", "cig_len")}
     seq_form = "ASCII" if args.seq8 else ("2-bit codes + a list of the bases outside ACGT" if hcols.get("seq_bits") == 2 else "4-bit codes")
     pinned = {}
     for k, a in hcols.items():
@@ -299,6 +304,7 @@ def main():
         setattr(b, k, pinned[k].data_ptr())
     b.seq_bits = int(hcols.get("seq_bits", 4 if "seq_poff" in hcols else 8))
     b.n_exc = len(hcols["exc_pos"]) if "exc_pos" in hcols else 0
+    b.n_cig_exc = len(hcols["cig_exc_idx"]) if "cig_exc_idx" in hcols else 0
     h2d_bytes = int(sum(a.nbytes for a in hcols.values() if isinstance(a, np.ndarray)))
 
     stream = torch.cuda.ExternalStream(eng.stream())
@@ -404,6 +410,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "shape": args.shape, "reads_per_gpu_per_step": args.reads,
                    "mean_read_len": float(cols["seq"].nbytes) / args.reads,
+                   "cigar_form": "16-bit words + listed long ops" if "cig16" in hcols else "op + length arrays",
                    "seq_form": seq_form + " on the host side of the ABI (expanded on the device); the new SEQ comes back as a delta against the input SEQ",
                    "l2": "inputs (%.2f GB per step) are larger than L2; no flush needed" % (h2d_bytes / 1e9),
                    "parallelism": "reads sharded by input-order chunk, tables replicated, no collective"},

@@ -135,6 +135,11 @@ typedef struct {
      * the byte.  Sequencer reads are ACGT almost everywhere, so this is a quarter of the ASCII column on the host link. */
     int32_t seq_bits; int32_t reserved0;
     int64_t n_exc; const int64_t* exc_pos; const uint8_t* exc_byte;
+    /* 16-bit CIGAR (optional, cig16 != NULL; cig_op / cig_len are then not read): one word per op, op code in bits 0-3 (index into
+     * "MIDNSHP=XB"), length in bits 4-15; ops with a length outside 1..4095 or another letter have the word 0xFFFF and are listed:
+     * cig_exc_idx[k] = the op's index in the dense CIGAR column (cig_off units, ascending), cig_exc_op / cig_exc_len = the op.
+     * (tc_cig_pack16.)  Long-read CIGARs are mostly 1-5-base ops: two fifths of the bytes of the op + length arrays. */
+    const uint16_t* cig16; int64_t n_cig_exc; const int64_t* cig_exc_idx; const uint8_t* cig_exc_op; const int32_t* cig_exc_len;
 } tc_batch_in;
 
 typedef struct {
@@ -218,6 +223,9 @@ int64_t tc_seq_packed_size(const int64_t* seq_off, int64_t n);
 int64_t tc_seq_pack2(const uint8_t* seq, const int64_t* seq_off, int64_t n, uint8_t* out, int64_t* poff,
                      int64_t exc_cap, int64_t* exc_pos, uint8_t* exc_byte, int64_t* n_exc, int32_t n_threads);
 int64_t tc_seq_packed2_size(const int64_t* seq_off, int64_t n);
+/* CIGAR op + length arrays -> 16-bit words + the list of ops that do not fit (at most exc_cap, else -1 is returned). */
+int64_t tc_cig_pack16(const uint8_t* cig_op, const int32_t* cig_len, int64_t n_ops, uint16_t* out, int64_t exc_cap,
+                      int64_t* exc_idx, uint8_t* exc_op, int32_t* exc_len, int32_t n_threads);
 
 /* batch_correct() minus text rendering: host columns in, host columns out (H2D, kernels, D2H). */
 int tc_correct_batch(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out);

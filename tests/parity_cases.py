@@ -106,6 +106,14 @@ def check_seq_forms(engine, seed, n_reads=160):
         for i in range(len(case.lines)):
             assert res.read_seq(i) == ref.read_seq(i) == r2.read_seq(i) and len(res.read_seq(i)) == int(ref.seq_len[i]), i
         assert np.array_equal(r2.status, ref.status) and np.array_equal(r2.te_words, ref.te_words) and np.array_equal(r2.nm, ref.nm)
+        engine.cig16 = True                              # CIGAR as 16-bit words (introns and other long ops listed) against op + length arrays
+        pc16 = engine.pack_cigar(cols)
+        assert "cig16" in pc16 and len(pc16["cig_exc_idx"]) < len(cols["cig_op"])     # (introns of 4,096 bases and more are listed: tools/workload shapes)
+        r16 = engine.correct(pc16)
+        engine.cig16 = False
+        r40 = engine.correct(cols)
+        for name in ("status", "counters", "nm", "te_words", "cig_op", "cig_len", "jm", "ji", "delta_len", "md_len"):
+            assert np.array_equal(getattr(r16, name), getattr(r40, name)), name
         engine.seq4 = True
         odd = dict(cols)
         odd["seq"] = cols["seq"].copy()
@@ -114,4 +122,4 @@ def check_seq_forms(engine, seed, n_reads=160):
         assert engine.pack_cols(odd) is None
         return True
     finally:
-        engine.seq2, engine.seq4, engine.seq4_text = True, True, False
+        engine.seq2, engine.seq4, engine.seq4_text, engine.cig16 = True, True, False, True

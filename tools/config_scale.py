@@ -146,7 +146,9 @@ def main():
         shape = "pacbio" if (args.config == 3 or step % 2 == 0) else "ont"
         cols, nm = w.reads(shape, n, seed_offset=1000 * rank + step)
         cols["chrom"] = np.where(cols["chrom"] == 0, cidx, cols["chrom"]).astype(np.int32)
-        hcols = eng.pack_cols2(cols) or eng.pack_cols(cols)
+        hcols = eng.pack_cigar(eng.pack_cols2(cols) or eng.pack_cols(cols))
+        if "cig16" in hcols:
+            hcols = {k: v for k, v in hcols.items() if k not in ("cig_op", "cig_len")}
         pinned = {}
         b = E._BatchIn(); b.n_reads = n
         for k, a in hcols.items():
@@ -157,6 +159,7 @@ def main():
                 t[:a.nbytes].copy_(torch.from_numpy(a.view(np.uint8).reshape(-1)))
             pinned[k] = t; setattr(b, k, t.data_ptr())
         b.seq_bits = int(hcols.get("seq_bits", 4)); b.n_exc = len(hcols["exc_pos"]) if "exc_pos" in hcols else 0
+        b.n_cig_exc = len(hcols["cig_exc_idx"]) if "cig_exc_idx" in hcols else 0
         for mode in (("dry", "full") if args.config == 5 else ("full",)):
             if step == 0:
                 (eng.raw_dryrun if mode == "dry" else eng.raw_correct)(b)      # warm-up of this mode's buffers

@@ -15,6 +15,9 @@ gi = w.genome_image()
 eng = E.Engine(0); eng.load_genome(gi); eng.load_junctions(build_sj_tables(sj, {w.chrom}, gi.index))
 if not os.environ.get("SEQ8"):
     cols = (None if os.environ.get("SEQ4") else eng.pack_cols2(cols)) or eng.pack_cols(cols)
+if not os.environ.get("CIG40"):
+    cols = eng.pack_cigar(cols)
+    if "cig16" in cols: cols = {k: v for k, v in cols.items() if k not in ("cig_op", "cig_len")}
 pinned = {}
 b = E._BatchIn(); b.n_reads = n
 for k, a in cols.items():
@@ -22,7 +25,7 @@ for k, a in cols.items():
     t = torch.empty(max(a.nbytes, 8), dtype=torch.uint8, pin_memory=True)
     if a.nbytes: t[:a.nbytes].copy_(torch.from_numpy(a.view(np.uint8).reshape(-1)))
     pinned[k] = t; setattr(b, k, t.data_ptr())
-b.seq_bits = int(cols.get("seq_bits", 4 if "seq_poff" in cols else 8)); b.n_exc = len(cols["exc_pos"]) if "exc_pos" in cols else 0
+b.seq_bits = int(cols.get("seq_bits", 4 if "seq_poff" in cols else 8)); b.n_exc = len(cols["exc_pos"]) if "exc_pos" in cols else 0; b.n_cig_exc = len(cols["cig_exc_idx"]) if "cig_exc_idx" in cols else 0
 res = {}
 for ch in [int(x) for x in os.environ.get("CHUNKS", "32768,65536,131072,262144,524288").split(",")]:
     eng.set_pipeline(ch)

@@ -1,7 +1,8 @@
-"""Per-source-line instruction counts of an ncu capture: python tools/prof_lines.py REP N_READS [top]"""
+"""Per-source-line instruction counts of an ncu capture: python tools/prof_lines.py REP N_READS [top] [--by-line] [--kernel=REGEX]"""
 import csv, subprocess, sys, io
 rep, nreads = sys.argv[1], float(sys.argv[2]); top = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 60
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+kern = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--kernel=")]
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + (["-k", "regex:" + kern[0]] if kern else []), capture_output=True, text=True).stdout
 rows = []; cur = None
 for row in csv.reader(io.StringIO(out)):
     if len(row) < 10:

@@ -1,6 +1,7 @@
 """Phase sums of k_emit from a prof_lines --by-line dump: python tools/prof_phases.py LINES.txt"""
 import re, sys
-src = open('/root/repo/transcriptclean_b200/csrc/tc_emit.cuh').read().splitlines()
+import os
+src = open(os.environ.get('TC_EMIT_SRC', '/root/repo/transcriptclean_b200/csrc/tc_emit.cuh')).read().splitlines()
 def find(pat, start=0):
     for i in range(start, len(src)):
         if pat in src[i]: return i + 1
@@ -9,7 +10,7 @@ pf = find("// the next read's segment list and SEQ lines")
 marks = [("loop/plan row", find("k_emit(Params P, OutDev O")), ("setup2", find("(TE rows, the CIGAR and the jM")),
          ("SEQ setup", find("// ---- SEQ")), ("(A) seg list", find("// (A) segment list")),
          ("prefetch", pf), ("exc+chunk_bp", find("if (fast) {", pf)), ("(B)", find("// (B) bulk copy")), ("(C)", find("// (C) the part")),
-         ("(D)", find("// (D) genome slices")), ("(E)", find("// (E) one coalesced")), ("T1 scan", find("// ---- NM / MD")),
+         ("(D)", find("// (D) genome slices")), ("(E)", find("// (E) ")), ("T1 scan", find("// ---- NM / MD")),
          ("T1 verify", find("// The staged SEQ is verified")), ("T1 md", find("// every aligned base equals the genome")),
          ("exact+finish", find("if (!done) {")), ("end", len(src) + 1)]
 rows = []

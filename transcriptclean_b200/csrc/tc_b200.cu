@@ -204,6 +204,7 @@ static void host_nmmd(const GenomeDev& G, const uint8_t* seq, const CigSrc& cs, 
 // Everything that belongs to one batch (or one chunk of a pipelined batch) on the device.
 struct Slot {
     DevBuf b_seqp, b_seq_poff, b_exc_pos, b_exc_byte;   // 4-bit / 2-bit SEQ: packed input rows + their offsets; the 2-bit form's listed bases
+    DevBuf b_cig16, b_cexc_idx, b_cexc_op, b_cexc_len; bool cig_unpack = false; int64_t cig_nexc = 0, cig_c0 = 0;   // 16-bit CIGAR form
     int unpack_bits = 0; int64_t unpack_p0 = 0, unpack_s0 = 0, unpack_nexc = 0; size_t unpack_d0 = 0;   // expansion still to be launched (slot_run does it on its own stream)
     DevBuf b_flag, b_chrom, b_pos, b_tags, b_seq_off, b_seq, b_cig_off, b_cig_op, b_cig_len, b_md_off, b_md, b_ji_off, b_ji;
     BatchDev B; int64_t n = 0, n_seq = 0, n_cig = 0, n_md = 0, n_ji = 0, md_base = 0;
@@ -228,6 +229,7 @@ struct Slot {
                        &o_nm, &o_md_off, &o_md_len, &o_md_pool, &o_delta_off, &o_delta_len, &o_delta_pool, &o_seq, &o_cig_op, &o_cig_len, &o_te, &o_jm, &o_ji};
         for (DevBuf* b : d) b->release();
         b_seqp.release(); b_seq_poff.release(); b_exc_pos.release(); b_exc_byte.release();
+        b_cig16.release(); b_cexc_idx.release(); b_cexc_op.release(); b_cexc_len.release();
         h_tot.release();
     }
 };
@@ -323,6 +325,16 @@ __global__ void __launch_bounds__(256) k_seq_unpack2(int64_t n, const int64_t* s
         const int mis = (int)(reinterpret_cast<uintptr_t>(dst) & 3);
         for (int w = lane; w * 8 < L; w += 32) { const uint32_t x = src[w]; store8(dst + w * 8, lut[x & 255u], lut[x >> 8], L - w * 8, mis); }
     }
+}
+// 16-bit CIGAR words -> the op / length arrays the kernels read (flat over the ops), then the listed ops
+__global__ void k_cig_unpack(int64_t n_ops, const uint16_t* w, uint8_t* op, int32_t* len) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_ops; k += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned x = w[k];
+        op[k] = (uint8_t)"MIDNSHP=XB??????"[x & 15u]; len[k] = (int32_t)(x >> 4);
+    }
+}
+__global__ void k_cig_patch(int64_t n_exc, const int64_t* idx, const uint8_t* eop, const int32_t* elen, uint8_t* op, int32_t* len) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_exc; k += (int64_t)gridDim.x * blockDim.x) { op[idx[k]] = eop[k]; len[idx[k]] = elen[k]; }
 }
 __global__ void k_seq_patch(int64_t n_exc, const int64_t* pos, const uint8_t* byte, uint8_t* seq) {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_exc; k += (int64_t)gridDim.x * blockDim.x) seq[pos[k]] = byte[k];
@@ -591,6 +603,33 @@ static int seq_upload_packed(tc_ctx* ctx, Slot& S, const tc_batch_in* in, int64_
     return 0;
 }
 
+// CIGAR ops [c0, c0 + S.n_cig): as op / length arrays, or as 16-bit words + listed ops that slot_run expands (cig_unpack)
+static int cig_upload(tc_ctx* ctx, Slot& S, const tc_batch_in* in, int64_t c0, stream_t st) {
+    S.cig_unpack = false;
+    if (!in->cig16) {
+        return be_h2d(ctx, st, S.b_cig_op, 0, S.n_cig ? in->cig_op + c0 : nullptr, (size_t)S.n_cig) ||
+               be_h2d(ctx, st, S.b_cig_len, 0, S.n_cig ? in->cig_len + c0 : nullptr, (size_t)S.n_cig * 4);
+    }
+    CK(S.b_cig_op.ensure((size_t)S.n_cig + 72)); CK(S.b_cig_len.ensure((size_t)S.n_cig * 4 + 72));
+    if (S.n_cig == 0) return 0;
+    if (be_h2d(ctx, st, S.b_cig16, 0, in->cig16 + c0, (size_t)S.n_cig * 2)) return TC_E_CUDA;
+    int64_t e0 = 0, e1 = 0;
+    if (in->n_cig_exc > 0) {
+        e0 = std::lower_bound(in->cig_exc_idx, in->cig_exc_idx + in->n_cig_exc, c0) - in->cig_exc_idx;
+        e1 = std::lower_bound(in->cig_exc_idx, in->cig_exc_idx + in->n_cig_exc, c0 + S.n_cig) - in->cig_exc_idx;
+        if (e1 > e0 && (be_h2d(ctx, st, S.b_cexc_idx, 0, in->cig_exc_idx + e0, (size_t)(e1 - e0) * 8) || be_h2d(ctx, st, S.b_cexc_op, 0, in->cig_exc_op + e0, (size_t)(e1 - e0)) ||
+                        be_h2d(ctx, st, S.b_cexc_len, 0, in->cig_exc_len + e0, (size_t)(e1 - e0) * 4))) return TC_E_CUDA;
+    }
+#ifndef TC_HOSTSIM
+    S.cig_unpack = true; S.cig_nexc = e1 - e0; S.cig_c0 = c0;
+#else
+    uint8_t* op = (uint8_t*)S.b_cig_op.p; int32_t* len = (int32_t*)S.b_cig_len.p; const uint16_t* w = (const uint16_t*)S.b_cig16.p;
+    for (int64_t k = 0; k < S.n_cig; k++) { op[k] = (uint8_t)"MIDNSHP=XB??????"[w[k] & 15u]; len[k] = (int32_t)(w[k] >> 4); }
+    for (int64_t k = e0; k < e1; k++) { op[in->cig_exc_idx[k] - c0] = in->cig_exc_op[k]; len[in->cig_exc_idx[k] - c0] = in->cig_exc_len[k]; }
+#endif
+    return 0;
+}
+
 // uploads reads [r0, r1) of `in` into slot S.  CSR offsets stay the batch's absolute offsets; the
 // data pointers are shifted so that they can be applied unchanged.
 static int slot_upload(tc_ctx* ctx, Slot& S, const tc_batch_in* in, int64_t r0, int64_t r1, stream_t st) {
@@ -607,8 +646,7 @@ static int slot_upload(tc_ctx* ctx, Slot& S, const tc_batch_in* in, int64_t r0, 
         (ctx->skip_seq ? be_h2d(ctx, st, S.b_seq, d0, nullptr, 0, (size_t)S.n_seq + 256)
                        : in->seq_poff ? seq_upload_packed(ctx, S, in, r0, r1, d0, st) : be_h2d(ctx, st, S.b_seq, d0, n ? in->seq + s0 : nullptr, (size_t)S.n_seq, 256)) ||
         be_h2d(ctx, st, S.b_cig_off, 0, n ? in->cig_off + r0 : zero_off, (size_t)(n + 1) * 8) ||
-        be_h2d(ctx, st, S.b_cig_op, 0, n ? in->cig_op + c0 : nullptr, (size_t)S.n_cig) ||
-        be_h2d(ctx, st, S.b_cig_len, 0, n ? in->cig_len + c0 : nullptr, (size_t)S.n_cig * 4) ||
+        cig_upload(ctx, S, in, c0, st) ||
         be_h2d(ctx, st, S.b_md_off, 0, n ? in->md_off + r0 : zero_off, (size_t)(n + 1) * 8) ||
         be_h2d(ctx, st, S.b_md, 0, n ? in->md + m0 : nullptr, (size_t)S.n_md) ||
         be_h2d(ctx, st, S.b_ji_off, 0, n ? in->ji_off + r0 : zero_off, (size_t)(n + 1) * 8) ||
@@ -726,6 +764,15 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
 #define TC_TPB 128
 #endif
     const int TPB = TC_TPB; const int gb = (int)((n + TPB - 1) / TPB);
+    if (S.cig_unpack) {                                                // 16-bit CIGAR words -> op / length arrays
+        k_cig_unpack<<<(int)std::min<int64_t>((S.n_cig + 255) / 256, 148 * 16), 256, 0, st>>>(S.n_cig, (const uint16_t*)S.b_cig16.p, (uint8_t*)S.b_cig_op.p, (int32_t*)S.b_cig_len.p); ctx->tm.launches++;
+        if (S.cig_nexc > 0) {
+            k_cig_patch<<<(int)std::min<int64_t>((S.cig_nexc + 255) / 256, 1184), 256, 0, st>>>(S.cig_nexc, (const int64_t*)S.b_cexc_idx.p, (const uint8_t*)S.b_cexc_op.p, (const int32_t*)S.b_cexc_len.p,
+                                                                                              (uint8_t*)S.b_cig_op.p - S.cig_c0, (int32_t*)S.b_cig_len.p - S.cig_c0); ctx->tm.launches++;
+        }
+        CK(cudaGetLastError());
+        S.cig_unpack = false;
+    }
     if (S.unpack_bits) {                                               // packed SEQ rows -> the ASCII rows the kernels read
         uint8_t* dst = (uint8_t*)S.b_seq.p + S.unpack_d0 - S.unpack_s0; const uint8_t* src = (const uint8_t*)S.b_seqp.p - S.unpack_p0;
         int64_t wb0 = (n + 7) / 8; int g = (int)(wb0 < 148 * 8 ? wb0 : 148 * 8);

@@ -586,6 +586,28 @@ int64_t tc_seq_pack2(const uint8_t* seq, const int64_t* seq_off, int64_t n, uint
     for (auto& e : exc) for (auto& x : e) { exc_pos[m] = x.first; exc_byte[m] = x.second; m++; }   // (thread ranges are ascending read ranges)
     return poff[n];
 }
+int64_t tc_cig_pack16(const uint8_t* cig_op, const int32_t* cig_len, int64_t n_ops, uint16_t* out, int64_t exc_cap,
+                      int64_t* exc_idx, uint8_t* exc_op, int32_t* exc_len, int32_t n_threads) {
+    uint8_t code[256]; memset(code, 0xff, sizeof(code));
+    const char* letters = "MIDNSHP=XB";
+    for (int k = 0; letters[k]; k++) code[(uint8_t)letters[k]] = (uint8_t)k;
+    int T = n_threads < 1 ? 1 : n_threads; if (n_ops < (1 << 16)) T = 1;
+    std::vector<std::vector<int64_t>> exc((size_t)T);
+    auto work = [&](int t) {
+        for (int64_t k = n_ops * t / T; k < n_ops * (t + 1) / T; k++) {
+            const unsigned c = code[cig_op[k]]; const int32_t l = cig_len[k];
+            if (c > 9 || l < 1 || l > 4095) { out[k] = 0xFFFFu; exc[(size_t)t].push_back(k); } else out[k] = (uint16_t)(c | ((unsigned)l << 4));
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+    int64_t m = 0; for (auto& e : exc) m += (int64_t)e.size();
+    if (m > exc_cap) return -1;
+    m = 0;
+    for (auto& e : exc) for (int64_t k : e) { exc_idx[m] = k; exc_op[m] = cig_op[k]; exc_len[m] = cig_len[k]; m++; }
+    return m;
+}
 // 0 = a SEQ byte lies outside the alphabet (the batch stays ASCII)
 int tc_sam_pack_seq(tc_sam* S, const uint8_t* alphabet, int32_t n_alpha, int32_t n_threads) {
     if (!S || !alphabet || n_alpha < 1 || n_alpha > 16) return 0;

@@ -12,7 +12,7 @@ EXPORTS = ["tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_set_optio
            "tc_ctx_load_genome", "tc_ctx_load_junctions", "tc_ctx_load_variants", "tc_correct_batch",
            "tc_dryrun_batch", "tc_batch_upload", "tc_batch_run", "tc_batch_download", "tc_get_timing",
            "tc_ctx_set_pipeline", "tc_sam_parse", "tc_sam_free", "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_render", "tc_sam_render_parts",
-           "tc_sam_rnames", "tc_free", "tc_ctx_set_alphabet", "tc_seq_pack", "tc_seq_packed_size", "tc_seq_pack2", "tc_seq_packed2_size", "tc_sam_pack_seq", "tc_sam_header_lines",
+           "tc_sam_rnames", "tc_free", "tc_ctx_set_alphabet", "tc_seq_pack", "tc_seq_packed_size", "tc_seq_pack2", "tc_seq_packed2_size", "tc_cig_pack16", "tc_sam_pack_seq", "tc_sam_header_lines",
            "tc_vcf_parse", "tc_vcf_tables", "tc_vcf_n_records", "tc_vcf_free", "tc_sj_parse", "tc_sj_tables", "tc_sj_free", "tc_intron_motifs"]
 
 # status bits (include/tc_b200.h)
@@ -33,7 +33,8 @@ class _Options(C.Structure):
 class _BatchIn(C.Structure):
     _fields_ = [("n_reads", C.c_int64)] + [(n, C.c_void_p) for n in (
         "flag", "chrom", "pos", "tags", "seq_off", "seq", "cig_off", "cig_op", "cig_len", "md_off", "md", "ji_off", "ji",
-        "seq_poff")] + [("seq_bits", C.c_int32), ("reserved0", C.c_int32), ("n_exc", C.c_int64), ("exc_pos", C.c_void_p), ("exc_byte", C.c_void_p)]
+        "seq_poff")] + [("seq_bits", C.c_int32), ("reserved0", C.c_int32), ("n_exc", C.c_int64), ("exc_pos", C.c_void_p), ("exc_byte", C.c_void_p),
+                     ("cig16", C.c_void_p), ("n_cig_exc", C.c_int64), ("cig_exc_idx", C.c_void_p), ("cig_exc_op", C.c_void_p), ("cig_exc_len", C.c_void_p)]
 
 
 class _BatchOut(C.Structure):
@@ -112,6 +113,8 @@ def _declare(lib):
     lib.tc_seq_packed2_size.restype = C.c_int64
     lib.tc_seq_pack2.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32]
     lib.tc_seq_pack2.restype = C.c_int64
+    lib.tc_cig_pack16.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+    lib.tc_cig_pack16.restype = C.c_int64
     lib.tc_sam_pack_seq.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32]
     lib.tc_sam_render.argtypes = [C.c_void_p, C.POINTER(_BatchOut)] + [C.c_int32] * 4 + [C.POINTER(C.c_void_p), C.POINTER(C.c_int64)] * 4 + [C.c_char_p, C.c_int64]
     lib.tc_sam_render_parts.argtypes = [C.c_void_p, C.POINTER(_BatchOut)] + [C.c_int32] * 4 + [C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_int32, C.c_char_p, C.c_int64]
@@ -132,7 +135,7 @@ def _declare(lib):
     lib.tc_sj_free.argtypes = [C.c_void_p]
     for f in EXPORTS:
         if f not in ("tc_vcf_parse", "tc_vcf_tables", "tc_vcf_n_records", "tc_vcf_free", "tc_sj_parse", "tc_sj_tables", "tc_sj_free", "tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_stream", "tc_sam_parse", "tc_sam_free",
-                     "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_rnames", "tc_free", "tc_seq_pack", "tc_seq_packed_size", "tc_seq_pack2", "tc_seq_packed2_size", "tc_sam_header_lines"):
+                     "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_rnames", "tc_free", "tc_seq_pack", "tc_seq_packed_size", "tc_seq_pack2", "tc_seq_packed2_size", "tc_cig_pack16", "tc_sam_header_lines"):
             getattr(lib, f).restype = C.c_int
 
 
@@ -393,6 +396,7 @@ class Engine:
         self.device = device
         self._keep = []
         self.alphabet = None       # bytes of the 4-bit SEQ codes once a genome is loaded (None: SEQ travels as ASCII)
+        self.cig16 = True          # CIGAR as 16-bit words + a list of the ops that do not fit (column path)
         self.seq2 = True           # ... and in 2-bit form + a list of the bases outside ACGT when those are few (sequencer reads)
         self.seq4 = True           # send SEQ in 4-bit form whenever the batch allows it (column path: PCIe is what limits it)
         self.seq4_text = False     # SAM-text path: ASCII (the host's parse / render threads limit it; packing would only add to them)
@@ -467,6 +471,24 @@ class Engine:
         packed["seq_bits"], packed["exc_pos"], packed["exc_byte"] = 2, epos[:ne.value].copy(), ebyte[:ne.value].copy()
         return packed
 
+    def pack_cigar(self, cols, n_threads=None, max_exc_frac=0.25):
+        """cols with the CIGAR as 16-bit words (`cig16`) + the listed ops that do not fit (`cig_exc_*`); cols unchanged when
+        more than max_exc_frac of the ops would have to be listed."""
+        n_ops = len(cols["cig_op"])
+        if n_ops == 0 or "cig16" in cols:
+            return cols
+        cap = int(max_exc_frac * n_ops) + 64
+        w = np.zeros(n_ops + 8, dtype=np.uint16)
+        eidx, eop, elen = np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.uint8), np.zeros(cap, dtype=np.int32)
+        op, ln = np.ascontiguousarray(cols["cig_op"]), np.ascontiguousarray(cols["cig_len"], dtype=np.int32)
+        m = self._lib.tc_cig_pack16(op.ctypes.data, ln.ctypes.data, n_ops, w.ctypes.data, cap, eidx.ctypes.data, eop.ctypes.data, elen.ctypes.data,
+                                    int(n_threads or min(32, os.cpu_count() or 1)))
+        if m < 0:
+            return cols
+        out = dict(cols)
+        out["cig16"], out["cig_exc_idx"], out["cig_exc_op"], out["cig_exc_len"] = w, eidx[:m].copy(), eop[:m].copy(), elen[:m].copy()
+        return out
+
     def pack_cols(self, cols, n_threads=None):
         """cols with the SEQ column in 4-bit form (`seq` packed, `seq_poff` added), or None when a SEQ
         byte is outside the alphabet."""
@@ -488,10 +510,12 @@ class Engine:
     def _batch_in(self, cols):
         if self.seq4 and "seq_poff" not in cols:
             cols = (self.pack_cols2(cols) if self.seq2 else None) or self.pack_cols(cols) or cols
+        if self.cig16:
+            cols = self.pack_cigar(cols)
         b = _BatchIn()
         b.n_reads = len(cols["flag"])
         for k in ("flag", "chrom", "pos", "tags", "seq_off", "seq", "cig_off", "cig_op", "cig_len", "md_off", "md",
-                  "ji_off", "ji", "seq_poff", "exc_pos", "exc_byte"):
+                  "ji_off", "ji", "seq_poff", "exc_pos", "exc_byte", "cig16", "cig_exc_idx", "cig_exc_op", "cig_exc_len"):
             a = cols.get(k)
             if a is None:
                 continue
@@ -499,6 +523,7 @@ class Engine:
             setattr(b, k, a.ctypes.data if a.size else None)
         b.seq_bits = int(cols.get("seq_bits", 4 if cols.get("seq_poff") is not None else 8))
         b.n_exc = len(cols["exc_pos"]) if cols.get("exc_pos") is not None else 0
+        b.n_cig_exc = len(cols["cig_exc_idx"]) if cols.get("cig_exc_idx") is not None else 0
         self._keep = [cols]          # the arrays behind the pointers
         return b
 
