@@ -337,7 +337,7 @@ def main():
         for k in kern:
             kern[k] += t[k]
         launches += t["launches"]
-        exact_reads = t["exact_nmmd_reads"]
+        exact_reads = t["exact_nmmd_reads"]; ascii_reads = t["ascii_path_reads"]
     e1.record(stream)
     barrier()
     ms_run = e0.elapsed_time(e1)
@@ -417,7 +417,7 @@ def main():
         "e2e": {"value": reads_total * steps / (ms_e2e * 1e-3), "unit": "reads/s", "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": int(launches),
-        "kernel_ms_per_step": per, "exact_nmmd_reads_per_step": int(exact_reads),
+        "kernel_ms_per_step": per, "exact_nmmd_reads_per_step": int(exact_reads), "ascii_path_reads_per_step": int(ascii_reads),
         "roofline": {"bound": "hbm", "kernel": dom.replace("_ms", ""), "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom_bytes},

@@ -172,6 +172,7 @@ typedef struct {
     int32_t md_pool_retries;
     int64_t h2d_bytes, d2h_bytes;
     int64_t exact_nmmd_reads; /* reads whose NM/MD needed the exact path (a difference to the genome, a D op, ...) */
+    int64_t ascii_path_reads; /* reads the 2-bit check (k_verify) could not settle: their new SEQ was built in ASCII by k_emit */
 } tc_timing;
 
 tc_ctx* tc_ctx_create(int device);

@@ -119,6 +119,9 @@ __global__ void k_measure(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim
 #ifndef TC_PLAN_BLOCKS
 #define TC_PLAN_BLOCKS 4      // registers over occupancy: 8 blocks (62 registers, spills) was 7 % slower
 #endif
+// (Handing the reads of a 256-read tile out in order of their work - a counting sort in shared memory, so that the 32 reads of a warp
+//  are neighbours in list length - was measured in round 2 and lost: k_plan 1.22 -> 1.37 ms, ONT 5.71 -> 5.97 ms per 1 M reads.  The
+//  lanes that idle are not what bounds these kernels; the scattered per-read rows the permutation adds cost more.)
 __global__ void __launch_bounds__(128, TC_PLAN_BLOCKS) k_plan(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) plan_read(P, i); }
 #include "tc_junction.cuh"
 
@@ -131,6 +134,7 @@ __global__ void k_dry(Params P) {
 __global__ void k_pack(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) pack_read(P, i); }
 
 #include "tc_emit.cuh"
+#include "tc_fast.cuh"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_); return TC_E_CUDA; } } while (0)
 
@@ -205,6 +209,7 @@ static void host_nmmd(const GenomeDev& G, const uint8_t* seq, const CigSrc& cs, 
 struct Slot {
     DevBuf b_seqp, b_seq_poff, b_exc_pos, b_exc_byte;   // 4-bit / 2-bit SEQ: packed input rows + their offsets; the 2-bit form's listed bases
     DevBuf b_cig16, b_cexc_idx, b_cexc_op, b_cexc_len; bool cig_unpack = false; int64_t cig_nexc = 0, cig_c0 = 0;   // 16-bit CIGAR form
+    DevBuf b_plane, b_plane_ok, w_rest_list; int plane_mode = 0; bool plane_ready = false; int64_t plane_s0 = 0, plane_p0 = 0, plane_nexc = 0;   // 2-bit plane of the input SEQ (tc_fast.cuh); plane_mode 2: the caller's 2-bit rows, 1: made from the ASCII rows, 0: none
     int unpack_bits = 0; int64_t unpack_p0 = 0, unpack_s0 = 0, unpack_nexc = 0; size_t unpack_d0 = 0;   // expansion still to be launched (slot_run does it on its own stream)
     DevBuf b_flag, b_chrom, b_pos, b_tags, b_seq_off, b_seq, b_cig_off, b_cig_op, b_cig_len, b_md_off, b_md, b_ji_off, b_ji;
     BatchDev B; int64_t n = 0, n_seq = 0, n_cig = 0, n_md = 0, n_ji = 0, md_base = 0;
@@ -230,6 +235,7 @@ struct Slot {
         for (DevBuf* b : d) b->release();
         b_seqp.release(); b_seq_poff.release(); b_exc_pos.release(); b_exc_byte.release();
         b_cig16.release(); b_cexc_idx.release(); b_cexc_op.release(); b_cexc_len.release();
+        b_plane.release(); b_plane_ok.release(); w_rest_list.release();
         h_tot.release();
     }
 };
@@ -254,6 +260,7 @@ struct tc_ctx {
     uint8_t alphabet[16] = {'A', 'C', 'G', 'T', 'N', 'a', 'c', 'g', 't', 'n', 0, 0, 0, 0, 0, 0}; int n_alpha = 10;   // 4-bit SEQ codes
     bool genome_byte[256] = {};     // bytes the loaded genome can put into a read
     bool packed = false;            // the current batch came with 4-bit SEQ
+    bool no_plane = false;          // TC_NO_PLANE=1: k_emit decides every read (the ASCII path alone; for measurements and tests)
     bool skip_seq = false;          // dry run over reads that all carry NM and MD: the SEQ column is never read, so it is not uploaded
     // pinned host outputs (whole batch)
     HostBuf h_status, h_counters, h_nm, h_delta_off, h_delta_len, h_delta, h_cig_off, h_cig_op, h_cig_len, h_md_off, h_md_len, h_md,
@@ -414,6 +421,7 @@ tc_ctx* tc_ctx_create(int device) {
     ctx->opt.correct_mismatches = ctx->opt.correct_indels = ctx->opt.correct_sjs = 1;
     memset(&ctx->G, 0, sizeof(ctx->G)); memset(&ctx->S, 0, sizeof(ctx->S)); memset(&ctx->V, 0, sizeof(ctx->V));
     memset(&ctx->tm, 0, sizeof(ctx->tm));
+    { const char* np = getenv("TC_NO_PLANE"); ctx->no_plane = np && np[0] == '1'; }
 #ifndef TC_HOSTSIM
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -657,6 +665,10 @@ static int slot_upload(tc_ctx* ctx, Slot& S, const tc_batch_in* in, int64_t r0, 
     B.cig_off = (const int64_t*)S.b_cig_off.p; B.cig_op = (const uint8_t*)S.b_cig_op.p - c0; B.cig_len = (const int32_t*)S.b_cig_len.p - c0;
     B.md_off = (const int64_t*)S.b_md_off.p; B.md = (const uint8_t*)S.b_md.p - m0; B.ji_off = (const int64_t*)S.b_ji_off.p; B.ji = (const int32_t*)S.b_ji.p - j0;
     S.seq_lo_word = (s0 - (int64_t)d0) / 4; S.seq_hi_word = S.seq_lo_word + (int64_t)(S.b_seq.cap / 4);
+    // 2-bit plane of the SEQ column for k_verify: the caller's own 2-bit rows when they came that way, else made from the ASCII rows (slot_run)
+    S.plane_ready = false; S.plane_s0 = s0;
+    S.plane_mode = (ctx->skip_seq || n == 0) ? 0 : (in->seq_poff && in->seq_bits == 2) ? 2 : 1;
+    if (S.plane_mode == 2) { S.plane_p0 = in->seq_poff[r0]; S.plane_nexc = S.unpack_nexc; }
     return TC_OK;
 }
 
@@ -786,6 +798,19 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
         CK(cudaGetLastError());
         S.unpack_bits = 0;
     }
+    if (!dry && S.plane_mode && !S.plane_ready && !ctx->no_plane) {
+        CK(S.b_plane_ok.ensure((size_t)n + 8)); CK(S.w_rest_list.ensure((size_t)(n + 1) * 4));
+        if (S.plane_mode == 2) {
+            CK(cudaMemsetAsync(S.b_plane_ok.p, 1, (size_t)n, st));
+            if (S.plane_nexc > 0) { k_seq_plane_flags<<<(int)std::min<int64_t>((S.plane_nexc + 255) / 256, 1184), 256, 0, st>>>(S.plane_nexc, (const int64_t*)S.b_exc_pos.p, (const int64_t*)S.b_seq_off.p, n, (uint8_t*)S.b_plane_ok.p); ctx->tm.launches++; }
+        } else {
+            CK(S.b_plane.ensure(((size_t)S.n_seq / 16 + (size_t)n + 8) * 4));
+            int64_t wb0 = (n + 7) / 8; int g = (int)(wb0 < 148 * 8 ? wb0 : 148 * 8);
+            k_seq_plane<<<g, 256, 0, st>>>(n, (const int64_t*)S.b_seq_off.p, S.B.seq, S.plane_s0, (uint32_t*)S.b_plane.p, (uint8_t*)S.b_plane_ok.p); ctx->tm.launches++;
+        }
+        CK(cudaGetLastError());
+        S.plane_ready = true;
+    }
     int nsm = 148; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
     int64_t wb = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; int gw = (int)(wb < (int64_t)nsm * 8 ? wb : (int64_t)nsm * 8);
     if (timed) CK(cudaEventRecord(ctx->ev[2], st));
@@ -858,14 +883,22 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
         CK(S.o_md_pool.ensure((size_t)md_cap)); md_cap = (int64_t)S.o_md_pool.cap;
         k_set_u64<<<1, 1, 0, st>>>(cur + 1, 0ull);
         k_set_u64<<<1, 1, 0, st>>>(cur, (unsigned long long)(S.base_md + 8 * n));      // the pool starts behind the inline slots
+        k_set_u64<<<1, 1, 0, st>>>(cur + 3, 0ull);
         OutDev O = make_out(S, cur, md_cap);
-        if (!dry) { k_emit<<<ge, WARPS_PER_BLOCK * 32, EMIT_SMEM_BYTES, st>>>(P, O, dry, S.seq_lo_word, S.seq_hi_word); ctx->tm.launches++; }   // (a dry run ends with k_small)
-        ctx->tm.launches += 2;
+        if (!dry && S.plane_ready && !ctx->no_plane) {                // NM / MD on the 2-bit plane; what that cannot settle goes to k_emit as a list
+            SeqPlane SP; SP.ok = (const uint8_t*)S.b_plane_ok.p; SP.s0 = S.plane_s0; SP.by_poff = S.plane_mode == 2; SP.poff = (const int64_t*)S.b_seq_poff.p;
+            SP.words = S.plane_mode == 2 ? (const uint32_t*)S.b_seqp.p - (S.plane_p0 >> 2) : (const uint32_t*)S.b_plane.p;
+            int occ_v = 1; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_v, k_verify, WARPS_PER_BLOCK * 32, 0));
+            const int gv = (int)(wb < (int64_t)nsm * occ_v ? wb : (int64_t)nsm * occ_v);
+            k_verify<<<gv, WARPS_PER_BLOCK * 32, 0, st>>>(P, O, SP, (int32_t*)S.w_rest_list.p, (unsigned*)(cur + 3)); ctx->tm.launches++;
+            k_emit<<<ge, WARPS_PER_BLOCK * 32, EMIT_SMEM_BYTES, st>>>(P, O, dry, S.seq_lo_word, S.seq_hi_word, (const int32_t*)S.w_rest_list.p, (const unsigned*)(cur + 3)); ctx->tm.launches++;
+        } else if (!dry) { k_emit<<<ge, WARPS_PER_BLOCK * 32, EMIT_SMEM_BYTES, st>>>(P, O, dry, S.seq_lo_word, S.seq_hi_word, nullptr, nullptr); ctx->tm.launches++; }   // (a dry run ends with k_small)
+        ctx->tm.launches += 3;
         CK(cudaGetLastError());
         if (timed && attempt == 0) CK(cudaEventRecord(ctx->ev[8], st));
         if (!dry) { k_nmmd_exact<<<gw, WARPS_PER_BLOCK * 32, 0, st>>>(P, O); ctx->tm.launches++; CK(cudaGetLastError()); }
-        if (be_read_i64(ctx, st, (const int64_t*)cur, tot) || be_read_i64(ctx, st, (const int64_t*)cur + 1, tot + 6) || be_sync(ctx, st)) return TC_E_CUDA;
-        if (tot[0] - S.base_md <= md_cap) { S.md_used = tot[0] - S.base_md; ctx->tm.exact_nmmd_reads += tot[6]; break; }
+        if (be_read_i64(ctx, st, (const int64_t*)cur, tot) || be_read_i64(ctx, st, (const int64_t*)cur + 1, tot + 6) || be_read_i64(ctx, st, (const int64_t*)cur + 3, tot + 7) || be_sync(ctx, st)) return TC_E_CUDA;
+        if (tot[0] - S.base_md <= md_cap) { S.md_used = tot[0] - S.base_md; ctx->tm.exact_nmmd_reads += tot[6]; ctx->tm.ascii_path_reads += (S.plane_ready && !ctx->no_plane) ? tot[7] : n; break; }
         if (attempt >= 2) { ctx->err = "MD pool overflow"; return TC_E_CUDA; }
         md_cap = tot[0] - S.base_md + 1024; ctx->tm.md_pool_retries++;
     }
@@ -1004,7 +1037,7 @@ int tc_batch_run(tc_ctx* ctx, int dry) {
 #ifndef TC_HOSTSIM
     CK(cudaSetDevice(ctx->device));
 #endif
-    ctx->tm.launches = 0; ctx->tm.md_pool_retries = 0; ctx->tm.exact_nmmd_reads = 0;
+    ctx->tm.launches = 0; ctx->tm.md_pool_retries = 0; ctx->tm.exact_nmmd_reads = 0; ctx->tm.ascii_path_reads = 0;
     ctx->tm.kernels_ms = ctx->tm.k_nmmd_init_ms = ctx->tm.k_measure_ms = ctx->tm.k_plan_ms = ctx->tm.k_junction_ms = ctx->tm.k_emit_ms = 0.f;
     reset_bases(ctx->slot[0]);
     int rc = slot_run(ctx, ctx->slot[0], dry, main_stream(ctx), true);
@@ -1055,7 +1088,7 @@ static int run_all(tc_ctx* ctx, const tc_batch_in* in, tc_batch_out* out, int dr
     const int64_t CH = ctx->chunk_reads;
     if (CH > 0 && n > CH + CH / 2) {
         CK(cudaSetDevice(ctx->device));
-        ctx->tm.h2d_bytes = ctx->tm.d2h_bytes = 0; ctx->tm.launches = 0; ctx->tm.md_pool_retries = 0; ctx->tm.exact_nmmd_reads = 0;
+        ctx->tm.h2d_bytes = ctx->tm.d2h_bytes = 0; ctx->tm.launches = 0; ctx->tm.md_pool_retries = 0; ctx->tm.exact_nmmd_reads = 0; ctx->tm.ascii_path_reads = 0;
         ctx->tm.kernels_ms = ctx->tm.k_nmmd_init_ms = ctx->tm.k_measure_ms = ctx->tm.k_plan_ms = ctx->tm.k_junction_ms = ctx->tm.k_emit_ms = 0.f;
         ctx->n = n; ctx->ran = false;
         if (check_packed(ctx, in)) return TC_E_ARG;

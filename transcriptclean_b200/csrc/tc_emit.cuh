@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_SMALL_BLOCKS) k_small
 #ifndef TC_EMIT_BLOCKS
 #define TC_EMIT_BLOCKS (32 / WARPS_PER_BLOCK)
 #endif
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_EMIT_BLOCKS) k_emit(Params P, OutDev O, int dry, int64_t seq_lo, int64_t seq_hi) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_EMIT_BLOCKS) k_emit(Params P, OutDev O, int dry, int64_t seq_lo, int64_t seq_hi, const int32_t* list, const unsigned* list_n) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw);             // 4 bases (8 bits of the 2-bit plane) -> 4 ASCII bytes
     EmitSmem& SM = reinterpret_cast<EmitSmem*>(smem_raw + 1024)[threadIdx.x >> 5];
@@ -157,9 +157,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_EMIT_BLOCKS) k_emit(P
     const BatchDev& B = P.B; const WorkDev& W = P.W;
     const uint32_t* S32 = reinterpret_cast<const uint32_t*>(B.seq);
     const int dbg = P.O.reserved;     // profiling aid: bit0 skip small copies, bit1 skip SEQ, bit2 skip NM/MD (results invalid)
-    int64_t i = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    int pw = i < B.n ? W.plan[i].w[lane] : 0;
-    for (; i < B.n; i += nw) {
+    // `list` != 0: only the reads k_verify (tc_fast.cuh) could not settle, in the list's order
+    const int64_t n_items = list ? (int64_t)*list_n : B.n;
+    int64_t it = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int64_t i = it < n_items ? (list ? (int64_t)list[it] : it) : 0;
+    int pw = it < n_items ? W.plan[i].w[lane] : 0;
+    for (; it < n_items; it += nw) {
         uint32_t st = (uint32_t)PF(EP_STATUS);
         const int pflags = PF(EP_FLAGS), cig_cap = PF(EP_CIGCAP), seg_cap = EP_SEGCAP_OF(PF(EP_CIGCAP), PF(EP_NJN)), nm_extra = PF(EP_NMEXTRA);
         const int ncig = PF(EP_NCIG), out_len = PF(EP_OUTLEN), ns = PF(EP_NSEG);
@@ -168,17 +171,19 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_EMIT_BLOCKS) k_emit(P
         const int64_t in_base = PF64(EP_INB_LO), cig0 = PF64(EP_CIG0_LO); const int Lq = PF(EP_LQ);
         // next read: fetch its row now (consumed at the end of this iteration), and pull its segment
         // list and SEQ lines towards L2
-        const int64_t inext = i + nw;
-        const int pw_next = inext < B.n ? W.plan[inext].w[lane] : 0;
-        if ((st & TC_ST_CLASS_MASK) != 0) { if (lane == 0) { O.md_off[i] = 0; O.md_len[i] = 0; O.nm[i] = 0; } pw = pw_next; continue; }
+        const bool more = it + nw < n_items;
+        const int64_t inext = more ? (list ? (int64_t)list[it + nw] : it + nw) : 0;
+        const int pw_next = more ? W.plan[inext].w[lane] : 0;
+#define TC_EMIT_NEXT() do { pw = pw_next; i = inext; } while (0)
+        if ((st & TC_ST_CLASS_MASK) != 0) { if (lane == 0) { O.md_off[i] = 0; O.md_len[i] = 0; O.nm[i] = 0; } TC_EMIT_NEXT(); continue; }
         u64* const ws = W.ws + ws_off;
         const int cb = ((pflags >> 2) & 3) - 1, sb = ((pflags >> 4) & 3) - 1;
-        if (dry) { if (lane == 0) { O.md_off[i] = 0; O.md_len[i] = 0; O.nm[i] = 0; } pw = pw_next; continue; }
+        if (dry) { if (lane == 0) { O.md_off[i] = 0; O.md_len[i] = 0; O.nm[i] = 0; } TC_EMIT_NEXT(); continue; }
         // (TE rows, the CIGAR and the jM / jI snapshot were copied by k_pack)
         CigSrc cs; cs.n = ncig;
         if (cb < 0) { cs.packed = 0; cs.op = B.cig_op + cig0; cs.len = B.cig_len + cig0; }
         else { cs.packed = ws + 3ll * seg_cap + (int64_t)cb * cig_cap; cs.op = 0; cs.len = 0; }
-        if (dbg & 2) { pw = pw_next; continue; }
+        if (dbg & 2) { TC_EMIT_NEXT(); continue; }
         // ---- SEQ
         const uint8_t* in_seq = B.seq + in_base;
         uint8_t* out_seq = O.seq + o_seq;
@@ -227,7 +232,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_EMIT_BLOCKS) k_emit(P
             }
         }
         // the next read's segment list and SEQ lines -> L2 while this read is being built
-        if (inext < B.n) {
+        if (more) {
             const int64_t nws = ((int64_t)__shfl_sync(FULL, pw_next, EP_WS_HI) << 32) | (uint32_t)__shfl_sync(FULL, pw_next, EP_WS_LO);
             const int64_t nin = ((int64_t)__shfl_sync(FULL, pw_next, EP_INB_HI) << 32) | (uint32_t)__shfl_sync(FULL, pw_next, EP_INB_LO);
             const int nlq = __shfl_sync(FULL, pw_next, EP_LQ);
@@ -483,7 +488,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_EMIT_BLOCKS) k_emit(P
             if (lane == 0) { O.nm[i] = W.nm_init[i]; O.md_off[i] = off < 0 ? 0 : off; O.md_len[i] = off < 0 ? 0 : len; }
         } else if (lane == 0) { O.nm[i] = 0; O.md_off[i] = 0; O.md_len[i] = 0; }
         __syncwarp();
-        pw = pw_next;
+        TC_EMIT_NEXT();
     }
+#undef TC_EMIT_NEXT
 }
 

@@ -47,7 +47,7 @@ class Timing(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "kernels_ms", "d2h_ms", "k_nmmd_init_ms", "k_measure_ms",
                                          "k_plan_ms", "k_junction_ms", "k_emit_ms")] + \
                [("launches", C.c_int32), ("md_pool_retries", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("exact_nmmd_reads", C.c_int64)]
+                ("exact_nmmd_reads", C.c_int64), ("ascii_path_reads", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
