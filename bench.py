@@ -239,8 +239,8 @@ def main():
     ap.add_argument("--ref-port", action="store_true", help="--impl reference: time the oracle port even when oracle/_ref holds the reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--text-sample", type=int, default=200000, help="reads for the SAM-text path measurement (0 = skip)")
-    ap.add_argument("--text-block-mb", type=int, default=16, help="block size of the SAM-text path measurement (the CLI's TC_CLI_BLOCK_MB)")
-    ap.add_argument("--text-workers", type=int, default=3, help="pipelined workers (engine contexts) of the SAM-text path measurement")
+    ap.add_argument("--text-block-mb", type=int, default=12, help="block size of the SAM-text path measurement (the CLI's TC_CLI_BLOCK_MB)")
+    ap.add_argument("--text-workers", type=int, default=4, help="pipelined workers (engine contexts) of the SAM-text path measurement")
     ap.add_argument("--resident-only", action="store_true", help="profiling aid: only the device-resident steps (no pipelined e2e calls), so that a "
                     "launch list holds exactly the kernels of the timed region")
     ap.add_argument("--no-dry", action="store_true", help="skip the --dryRun measurement")

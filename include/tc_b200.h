@@ -175,6 +175,7 @@ typedef struct {
     int64_t ascii_path_reads; /* reads the 2-bit check (k_verify) could not settle: their new SEQ was built in ASCII by k_emit */
 } tc_timing;
 
+int tc_device_count(void);                  /* GPUs this process can open (0: none); the CLI sizes its worker set with it (--threads, TC.py:560-586) */
 tc_ctx* tc_ctx_create(int device);
 void tc_ctx_destroy(tc_ctx* ctx);
 const char* tc_last_error(tc_ctx* ctx);     /* ctx may be NULL: error of the failed create */
@@ -275,7 +276,7 @@ int tc_sam_render(tc_sam* s, const tc_batch_out* res, int32_t primary_only, int3
                   const char** log, int64_t* log_len, const char** te, int64_t* te_len, char* err, int64_t err_cap);
 /* the same texts without the final copy: n_parts pieces per text, in order (the formatter threads' own buffers);
  * ptr[4 * k + q] / len[4 * k + q] = piece k of text q (0 sam, 1 fa, 2 log, 3 te); ptr / len hold 4 * max_parts entries.
- * Valid until the calling thread renders again. */
+ * Valid until the tc_sam is rendered again or freed (the pieces are its own storage). */
 int tc_sam_render_parts(tc_sam* s, const tc_batch_out* res, int32_t primary_only, int32_t canon_only, int32_t dry,
                         int32_t n_threads, int32_t* n_parts, const char** ptr, int64_t* len, int32_t max_parts,
                         char* err, int64_t err_cap);

@@ -132,7 +132,7 @@ def correct_sam_stream(blocks, options, refs_list, sink, dry=False, n_threads=No
     it = enumerate(blocks)
     lock = threading.Lock()
     cond = threading.Condition()
-    ready, state = {}, {"next": 0, "err": None, "end": None}
+    ready, state = {}, {"next": 0, "err": None, "end": None, "live": n_workers}
 
     def take():
         with lock:
@@ -141,7 +141,11 @@ def correct_sam_stream(blocks, options, refs_list, sink, dry=False, n_threads=No
             except StopIteration:
                 return None
 
+    timing = os.environ.get("TC_STREAM_TIMING") == "1"           # per-worker seconds by stage, to stderr
+    import time
+
     def work(refs):
+        tm = {"parse": 0.0, "abi": 0.0, "render": 0.0, "wait_writer": 0.0, "close": 0.0, "blocks": 0}
         try:
             _set_engine_options(options, refs)
             while state["err"] is None:
@@ -149,24 +153,40 @@ def correct_sam_stream(blocks, options, refs_list, sink, dry=False, n_threads=No
                 if item is None:
                     return
                 idx, text = item
+                t0 = time.perf_counter()
                 st = refs.engine.parse_sam(text, refs.genome, per)
+                t1 = time.perf_counter()
                 try:
                     raw = refs.engine.raw_dryrun(st.batch) if dry else refs.engine.raw_correct(st.batch)
+                    t2 = time.perf_counter()
                     out = st.render_parts(raw, bool(_opt(options, "primaryOnly", False)), bool(_opt(options, "canonOnly", False)), dry)
+                    t3 = time.perf_counter()
                     done = threading.Event()
                     with cond:
                         ready[idx] = (st.header, out, done)
                         cond.notify_all()
                     done.wait()                                    # the writer is through with this block's buffers
+                    t4 = time.perf_counter()
                     for vs in out.values():
                         for v in vs:
                             v.release()
                 finally:
                     st.close()
+                t5 = time.perf_counter()
+                for k, v in (("parse", t1 - t0), ("abi", t2 - t1), ("render", t3 - t2), ("wait_writer", t4 - t3), ("close", t5 - t4)):
+                    tm[k] += v
+                tm["blocks"] += 1
         except BaseException as e:                                 # surfaced by the writer loop
             with cond:
                 state["err"] = state["err"] or e
                 cond.notify_all()
+        finally:
+            with cond:
+                state["live"] -= 1
+                cond.notify_all()                                  # (the writer also waits for the last worker to leave)
+            if timing:
+                import sys
+                print("correct_sam_stream worker (%d threads): %s" % (per, {k: round(v, 4) for k, v in tm.items()}), file=sys.stderr)
 
     threads = [threading.Thread(target=work, args=(r,), daemon=True) for r in refs_list]
     for t in threads:
@@ -174,7 +194,7 @@ def correct_sam_stream(blocks, options, refs_list, sink, dry=False, n_threads=No
     try:
         while True:
             with cond:
-                while state["next"] not in ready and state["err"] is None and any(t.is_alive() for t in threads):
+                while state["next"] not in ready and state["err"] is None and state["live"] > 0:
                     cond.wait(0.05)
                 if state["err"] is not None:
                     raise state["err"]

@@ -108,7 +108,25 @@ def validate_chroms(genome, vcf_file, sam_chroms):
 
 
 def sam_blocks(path, block_bytes):
-    """The SAM file as bytes blocks of about block_bytes that end at line boundaries."""
+    """The SAM file as blocks of about block_bytes that end at line boundaries: slices of a private mapping of the file
+    (no copy: the parser threads read the page cache), or bytes objects read in a loop where the file cannot be mapped."""
+    import mmap
+    mm = None
+    try:
+        with open(path, "rb") as f:
+            if os.fstat(f.fileno()).st_size > 0:
+                mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_COPY)
+    except (OSError, ValueError):
+        mm = None
+    if mm is not None:
+        mv, n, a = memoryview(mm), len(mm), 0
+        while a < n:
+            b = n if a + block_bytes >= n else mm.rfind(b"\n", a, a + block_bytes) + 1
+            if b <= a:                                    # a line longer than a block
+                b = mm.find(b"\n", a + block_bytes) + 1 or n
+            yield mv[a:b]
+            a = b
+        return
     with open(path, "rb") as f:
         rest = b""
         while True:
@@ -125,12 +143,60 @@ def sam_blocks(path, block_bytes):
             rest = buf[cut + 1:]
 
 
-def n_gpus_available():
+def n_gpus_available(lib=None):
+    """GPUs the library can open (asked of the CUDA runtime through the C ABI: importing torch for this cost seconds)."""
     try:
-        import torch
-        return torch.cuda.device_count()
+        from . import engine as E
+        return int((lib or E.load_library()).tc_device_count())
     except Exception:
         return 1
+
+
+class _FileWriters:
+    """One writer thread per output file: the four texts of a block are written side by side (the page-cache copies of
+    the clean SAM, the FASTA and the TE log are what the writing end of the pipeline spends its time on)."""
+
+    def __init__(self, files):
+        import queue
+        import threading
+        self.files, self.q, self.err = files, {k: queue.Queue() for k in files}, []
+        self.threads = [threading.Thread(target=self._run, args=(k,), daemon=True) for k in files]
+        for t in self.threads:
+            t.start()
+
+    def _run(self, k):
+        f, q = self.files[k], self.q[k]
+        while True:
+            item = q.get()
+            if item is None:
+                return
+            pieces, done = item
+            try:
+                for piece in pieces:
+                    f.write(piece)
+            except BaseException as e:
+                self.err.append(e)
+            finally:
+                done.set()
+
+    def write(self, views):
+        """Writes views[k] (a list of buffers) to file k for every k; returns when all of it is written."""
+        import threading
+        evs = []
+        for k in self.files:
+            ev = threading.Event()
+            self.q[k].put((views[k], ev))
+            evs.append(ev)
+        for ev in evs:
+            ev.wait()
+        if self.err:
+            raise self.err[0]
+
+    def close(self):
+        for k in self.files:
+            self.q[k].put(None)
+        for t in self.threads:
+            t.join()
 
 
 def split_text(text, n):
@@ -148,32 +214,62 @@ def split_text(text, n):
 
 def run(options, engines=None):
     """engines: optional list of pre-built Engine objects (tests inject CPU stand-ins here).
-    The SAM file is streamed twice in blocks (TC_CLI_BLOCK_MB, default 16): a scan for the header lines and the
+    The SAM file is streamed twice in blocks (TC_CLI_BLOCK_MB, default 12): a scan for the header lines and the
     chromosome names (what split_SAM collects, TC.py:519-541), then the correction.  Blocks are handed to worker
-    threads in input order - TC_CLI_WORKERS_PER_GPU (default 3) workers per GPU, each with its own engine context, so
+    threads in input order - TC_CLI_WORKERS_PER_GPU (default 4) workers per GPU, each with its own engine context, so
     that parsing block k+1, correcting block k and rendering block k-1 overlap - and their four texts are appended to
     the output files in input order (combine_outputs, TC.py:604-663: headers first; no SAM / FASTA in --dryRun).
     SAM parsing and text rendering run in the library's multi-threaded C++ host code (csrc/tc_host.cpp); the SJ / VCF
     tables are parsed once (csrc/tc_tables.cpp) and uploaded to every context."""
     from . import engine as E
-    block = int(os.environ.get("TC_CLI_BLOCK_BYTES", "0")) or max(1, int(os.environ.get("TC_CLI_BLOCK_MB", "16"))) << 20
+    import time
+    t_start = time.perf_counter()
+    timing = os.environ.get("TC_CLI_TIMING") == "1"
+
+    def stamp(what):                                      # TC_CLI_TIMING=1: seconds since the start of run(), to stderr
+        if timing:
+            print("cli %-28s %8.3f s" % (what, time.perf_counter() - t_start), file=sys.stderr)
+    block = int(os.environ.get("TC_CLI_BLOCK_BYTES", "0")) or max(1, int(os.environ.get("TC_CLI_BLOCK_MB", "12"))) << 20
     lib = E.load_library() if engines is None else engines[0]._lib
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=max(2, min(16, os.cpu_count() or 2)))
+    made = None
+    if engines is None:                                   # the device contexts come up while the SAM file is scanned
+        n = max(1, min(int(options.n_threads), max(1, n_gpus_available(lib))))
+        per_gpu = max(1, int(os.environ.get("TC_CLI_WORKERS_PER_GPU", "4")))
+        made = [pool.submit(E.Engine, d) for d in range(n) for _ in range(per_gpu)]
     chroms, header = set(), ""
+    pending = []
+
+    def scan(blk):                                        # (C calls: the pool's threads run side by side)
+        return E.sam_rnames(lib, blk), E.sam_header_lines(lib, blk)
+
+    def drain(keep):
+        nonlocal header
+        while len(pending) > keep:
+            names, head = pending.pop(0).result()
+            chroms.update(names)
+            header += head
     for blk in sam_blocks(options.sam, block):
-        chroms |= E.sam_rnames(lib, blk)
-        header += E.sam_header_lines(lib, blk)
+        pending.append(pool.submit(scan, blk))
+        drain(24)                                         # bounded: at most 24 blocks of the file in memory
+    drain(0)
+    stamp("scan of the SAM file")
     print("Reading genome ..............................")
     genome = GenomeImage.from_fasta_cached(options.refGenome)
-    if engines is None:
-        n = max(1, min(int(options.n_threads), max(1, n_gpus_available())))
-        per_gpu = max(1, int(os.environ.get("TC_CLI_WORKERS_PER_GPU", "3")))
-        engines = [E.Engine(d) for d in range(n) for _ in range(per_gpu)]
+    stamp("genome image")
+    if made is not None:
+        engines = [f.result() for f in made]
+    pool.shutdown(wait=False)
+    stamp("engine contexts")
     validate_chroms(genome, options.variantFile, chroms)
     os.makedirs(options.tmp_dir, exist_ok=True)          # kept for interface compatibility (--tmpDir / --deleteTmp)
     dry = bool(options.dryRun)
     # tables: parsed once and uploaded to every context; a dry run never opens the SJ / VCF files (TC.py:589-601)
     sj, var = (None, None) if dry else api.build_tables(options, chroms, genome)
+    stamp("tables built")
     refs_list = [api.make_refs(genome, sj, var, engine=e) for e in engines]
+    stamp("tables and genome on the GPUs")
     pre = options.outprefix
     names = {"log": pre + "_clean.log", "te": pre + "_clean.TE.log"}
     if not dry:
@@ -186,12 +282,16 @@ def run(options, engines=None):
         if not dry:
             files["sam"].write(header.encode())
 
-        def sink(_header, views):                         # the formatter threads' own buffers, written without a copy
-            for k, f in files.items():
-                for piece in views[k]:
-                    f.write(piece)
+        writers = _FileWriters(files)
 
-        api.correct_sam_stream(sam_blocks(options.sam, block), options, refs_list, sink, dry=dry)
+        def sink(_header, views):                         # the formatter threads' own buffers, written without a copy
+            writers.write(views)
+
+        try:
+            api.correct_sam_stream(sam_blocks(options.sam, block), options, refs_list, sink, dry=dry)
+        finally:
+            writers.close()
+        stamp("correction pass")
         ok = True
     finally:
         for f in files.values():
@@ -201,6 +301,7 @@ def run(options, engines=None):
                 os.replace(v + ".partial", v)
             elif os.path.exists(v + ".partial"):
                 os.remove(v + ".partial")
+    stamp("files closed")
     if options.delete_tmp:
         import shutil
         shutil.rmtree(options.tmp_dir, ignore_errors=True)

@@ -138,6 +138,16 @@ __global__ void k_pack(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x 
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_); return TC_E_CUDA; } } while (0)
 
+// page-locked memory for the host parser's column buffers (tc_host.cpp)
+extern void* (*tc_pinned_alloc)(size_t);
+extern void (*tc_pinned_free)(void*);
+static struct PinnedHooks {
+    PinnedHooks() {
+        tc_pinned_alloc = [](size_t n) -> void* { void* p = nullptr; if (cudaHostAlloc(&p, n, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; };
+        tc_pinned_free = [](void* p) { cudaFreeHost(p); };
+    }
+} g_pinned_hooks;
+
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
     cudaError_t ensure(size_t n) {
@@ -467,6 +477,16 @@ int tc_ctx_set_options(tc_ctx* ctx, const tc_options* o) {
     if (o->max_len_indel < 0 || o->max_sj_offset < 0) { ctx->err = "negative maxLenIndel / maxSJOffset"; return TC_E_ARG; }
     ctx->opt = *o;
     return TC_OK;
+}
+
+int tc_device_count(void) {
+#ifndef TC_HOSTSIM
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+#else
+    return 1;
+#endif
 }
 
 void* tc_ctx_stream(tc_ctx* ctx) {

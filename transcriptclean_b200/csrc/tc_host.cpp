@@ -23,17 +23,56 @@
 
 #include "../../include/tc_b200.h"
 
+// page-locked host memory is the CUDA translation unit's business: tc_b200.cu installs these two (null: plain malloc)
+void* (*tc_pinned_alloc)(size_t) = nullptr;
+void (*tc_pinned_free)(void*) = nullptr;
+
 namespace {
 
 struct Span { int64_t s; int32_t n; };
 
+// std::vector whose resize() leaves new elements uninitialised: the column buffers are resized to their final size and then
+// filled by the parser threads, and value-initialising them first was a serial pass over every byte of the batch (most of
+// tc_sam_parse's time on 16 threads: profiles/r02f_host_text_probe.json)
+template <class T> struct DefaultInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = DefaultInitAlloc<U>; };
+    using std::allocator<T>::allocator;
+    template <class U, class... A> void construct(U* p, A&&... a) {
+        if constexpr (sizeof...(A) == 0) ::new ((void*)p) U; else ::new ((void*)p) U(std::forward<A>(a)...);
+    }
+};
+template <class T> using UV = std::vector<T, DefaultInitAlloc<T>>;
+
+// The same for the batch's large columns (SEQ, CIGAR, MD), in page-locked memory: tc_correct_batch then copies them to the device
+// straight from where the parser put them (a pageable source goes through the driver's staging buffer first: two more passes
+// over every byte on the host).  The objects are pooled, so the cost of page-locking is paid once per pipeline worker.
+// Falls back to malloc when no device is there (or the hooks are not installed); a 64-byte header in front of the block says which it was.
+template <class T> struct PinnedAlloc : DefaultInitAlloc<T> {
+    template <class U> struct rebind { using other = PinnedAlloc<U>; };
+    PinnedAlloc() = default;
+    template <class U> PinnedAlloc(const PinnedAlloc<U>&) {}
+    T* allocate(size_t n) {
+        const size_t bytes = n * sizeof(T) + 64; void* p = nullptr; uint64_t kind = 0;
+        if (bytes >= ((size_t)1 << 20) && tc_pinned_alloc && (p = tc_pinned_alloc(bytes)) != nullptr) kind = 1;
+        if (!p) { p = malloc(bytes); if (!p) throw std::bad_alloc(); }
+        *reinterpret_cast<uint64_t*>(p) = kind;
+        return reinterpret_cast<T*>(reinterpret_cast<char*>(p) + 64);
+    }
+    void deallocate(T* q, size_t) {
+        void* p = reinterpret_cast<char*>(q) - 64;
+        if (*reinterpret_cast<uint64_t*>(p) == 1) { tc_pinned_free(p); return; }
+        free(p);
+    }
+};
+template <class T> using PV = std::vector<T, PinnedAlloc<T>>;
+
 struct Part {                       // what one parser thread produces
-    std::vector<int32_t> flag, chrom, pos; std::vector<uint8_t> tags, cls;
-    std::vector<int64_t> seq_len, cig_n, md_n, ji_n;
-    std::vector<uint8_t> seq, cig_op, md; std::vector<int32_t> cig_len, ji;
-    std::vector<Span> line, f[9], cigar, tg[4];
-    std::vector<int64_t> other_off; std::vector<Span> other;
-    std::vector<Span> header;
+    UV<int32_t> flag, chrom, pos; UV<uint8_t> tags, cls;
+    UV<int64_t> seq_len, cig_n, md_n, ji_n;
+    UV<uint8_t> seq, cig_op, md; UV<int32_t> cig_len, ji;
+    UV<Span> line, f[9], cigar, tg[4];
+    UV<int64_t> other_off; UV<Span> other;
+    UV<Span> header;
     std::string err;
     void reset() {                   // empty, capacity kept: the parts of a host thread are reused from batch to batch
         flag.clear(); chrom.clear(); pos.clear(); tags.clear(); cls.clear(); seq_len.clear(); cig_n.clear(); md_n.clear(); ji_n.clear();
@@ -66,14 +105,17 @@ bool py_int(const char* p, int n, int64_t& out) {
 
 }  // namespace
 
+namespace { struct SamBufs; }
 struct tc_sam {
     const char* text = nullptr; int64_t len = 0;
+    SamBufs* bufs = nullptr;         // the parser threads' parts and the formatter threads' texts: storage that travels with the object through the pool
+    ~tc_sam();
     int64_t n = 0;
-    std::vector<int32_t> flag, chrom, pos; std::vector<uint8_t> tags, cls;
-    std::vector<int64_t> seq_off, cig_off, md_off, ji_off;
-    std::vector<uint8_t> seq, cig_op, md; std::vector<int32_t> cig_len, ji;
-    std::vector<Span> line, f[9], cigar, tg[4];
-    std::vector<int64_t> other_off; std::vector<Span> other;
+    UV<int32_t> flag, chrom, pos; UV<uint8_t> tags, cls;
+    UV<int64_t> seq_off, cig_off, md_off, ji_off;
+    PV<uint8_t> seq, cig_op, md; PV<int32_t> cig_len; UV<int32_t> ji;
+    UV<Span> line, f[9], cigar, tg[4];
+    UV<int64_t> other_off; UV<Span> other;
     std::string header;
     struct RawBuf {                  // output text: grown without initialising (a std::string resize would touch it twice)
         char* p = nullptr; size_t cap = 0, n = 0;
@@ -86,7 +128,7 @@ struct tc_sam {
         ~RawBuf() { free(p); }
     } out[4];                        // sam, fa, log, te
     // 4-bit SEQ form (tc_sam_pack_seq): packed rows, their offsets, the alphabet they index
-    std::vector<uint8_t> seqp; std::vector<int64_t> seq_poff; uint8_t alphabet[16] = {0}; int n_alpha = 0; bool packed = false;
+    UV<uint8_t> seqp; UV<int64_t> seq_poff; uint8_t alphabet[16] = {0}; int n_alpha = 0; bool packed = false;
 };
 
 namespace {
@@ -382,10 +424,11 @@ void render_range(const tc_sam* S, const tc_batch_out* R, int64_t a, int64_t b, 
     }
 }
 
+struct SamBufs { std::vector<Part> parts; std::vector<Out> ps, pf, pl, pt; };
 std::mutex g_pool_mu; std::vector<tc_sam*> g_pool;
 tc_sam* sam_acquire() {
     std::lock_guard<std::mutex> g(g_pool_mu);
-    if (g_pool.empty()) return new tc_sam();
+    if (g_pool.empty()) { tc_sam* S = new tc_sam(); S->bufs = new SamBufs(); return S; }
     tc_sam* S = g_pool.back(); g_pool.pop_back();
     return S;
 }
@@ -399,10 +442,12 @@ void sam_release(tc_sam* S) {
     S->other_off.clear(); S->other.clear(); S->header.clear(); S->seqp.clear(); S->seq_poff.clear();
     for (auto& b : S->out) b.n = 0;
     std::lock_guard<std::mutex> g(g_pool_mu);
-    if (g_pool.size() < 2) g_pool.push_back(S); else delete S;
+    if (g_pool.size() < 8) g_pool.push_back(S); else delete S;   // (one object per pipeline worker is in use at a time)
 }
 
 }  // namespace
+
+tc_sam::~tc_sam() { delete bufs; }
 
 extern "C" {
 
@@ -419,15 +464,14 @@ tc_sam* tc_sam_parse(const char* text, int64_t len, int32_t n_chrom, const char*
     for (int k = 1; k <= T; k++) if (cut[k] < cut[k - 1]) cut[k] = cut[k - 1];
     // Buffers are recycled (per calling thread / through a small pool of tc_sam objects): touching
     // fresh pages costs more than the parsing itself.
-    static thread_local std::vector<Part> parts_tl;
-    std::vector<Part>& parts = parts_tl;
+    tc_sam* S = sam_acquire();
+    std::vector<Part>& parts = S->bufs->parts;
     if (parts.size() < (size_t)T) parts.resize((size_t)T);
     for (auto& p : parts) p.reset();
     std::vector<std::thread> th;
     for (int k = 0; k < T; k++) th.emplace_back(parse_range, text, cut[k], cut[k + 1], std::cref(cmap), chrom_len, std::ref(parts[(size_t)k]));
     for (auto& t : th) t.join();
-    for (int k = 0; k < T; k++) if (!parts[(size_t)k].err.empty()) { set_err(err, err_cap, parts[(size_t)k].err); return nullptr; }
-    tc_sam* S = sam_acquire();
+    for (int k = 0; k < T; k++) if (!parts[(size_t)k].err.empty()) { set_err(err, err_cap, parts[(size_t)k].err); sam_release(S); return nullptr; }
     S->text = text; S->len = len;
     // totals, then every part is copied to its place by its own thread
     std::vector<size_t> r0((size_t)T + 1, 0), s0((size_t)T + 1, 0), c0((size_t)T + 1, 0), m0((size_t)T + 1, 0), j0((size_t)T + 1, 0), o0((size_t)T + 1, 0);
@@ -440,7 +484,9 @@ tc_sam* tc_sam_parse(const char* text, int64_t len, int32_t n_chrom, const char*
     const size_t n = r0[T];
     S->flag.resize(n); S->chrom.resize(n); S->pos.resize(n); S->tags.resize(n); S->cls.resize(n);
     S->seq_off.resize(n + 1); S->cig_off.resize(n + 1); S->md_off.resize(n + 1); S->ji_off.resize(n + 1); S->other_off.resize(n);
-    S->seq.resize(s0[T] + 64); S->cig_op.resize(c0[T] + 8); S->cig_len.resize(c0[T] + 8); S->md.resize(m0[T] + 8); S->ji.resize(j0[T] + 8);
+    // (page-locking a new block is expensive: grow with headroom, so that blocks of about the same size never reallocate)
+    auto fit = [](auto& v, size_t want) { if (v.capacity() < want) { v.clear(); v.reserve(want + want / 4 + ((size_t)1 << 16)); } v.resize(want); };
+    fit(S->seq, s0[T] + 64); fit(S->cig_op, c0[T] + 8); fit(S->cig_len, c0[T] + 8); fit(S->md, m0[T] + 8); S->ji.resize(j0[T] + 8);
     S->line.resize(n); for (int k = 0; k < 9; k++) S->f[k].resize(n); S->cigar.resize(n); for (int k = 0; k < 4; k++) S->tg[k].resize(n);
     S->other.resize(o0[T]);
     auto place = [&](int k) {
@@ -616,7 +662,7 @@ int tc_sam_pack_seq(tc_sam* S, const uint8_t* alphabet, int32_t n_alpha, int32_t
     S->seq_poff.assign((size_t)S->n + 1, 0);
     S->seqp.resize((size_t)tc_seq_packed_size(S->seq_off.data(), S->n) + 64);
     if (tc_seq_pack(S->seq.data(), S->seq_off.data(), S->n, alphabet, n_alpha, S->seqp.data(), S->seq_poff.data(), n_threads) < 0) {
-        std::vector<uint8_t>().swap(S->seqp); return 0;
+        UV<uint8_t>().swap(S->seqp); return 0;
     }
     S->packed = true;
     return 1;
@@ -631,7 +677,6 @@ void tc_sam_batch(const tc_sam* S, tc_batch_in* b) {
 }
 
 // the four texts as the parts of the T formatter threads (ps / pf / pl / pt, per calling thread, storage kept between batches)
-static thread_local std::vector<Out> ps, pf, pl, pt;
 static int render_parts(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_t canon_only, int32_t dry, int32_t n_threads,
                         int& T_out, char* err, int64_t err_cap) {
     if (!S || !R || R->n_reads != S->n) { set_err(err, err_cap, "tc_sam_render: result does not belong to this batch"); return TC_E_ARG; }
@@ -645,6 +690,7 @@ static int render_parts(tc_sam* S, const tc_batch_out* R, int32_t primary_only, 
     }
     int T = n_threads < 1 ? 1 : n_threads;
     if (S->n < 4096) T = 1;
+    std::vector<Out>&ps = S->bufs->ps, &pf = S->bufs->pf, &pl = S->bufs->pl, &pt = S->bufs->pt;
     for (auto* v : {&ps, &pf, &pl, &pt}) { if (v->size() < (size_t)T) v->resize((size_t)T); for (auto& x : *v) x.clear(); }
     std::vector<std::thread> th; std::vector<int64_t> bad((size_t)T, -1);
     for (int k = 0; k < T; k++) {
@@ -672,7 +718,7 @@ int tc_sam_render(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_
     auto now = [] { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
     const double t_r = now();
     // the parts of the T formatter threads -> one text each, copied by T threads again
-    std::vector<Out>* parts[4] = {&ps, &pf, &pl, &pt};
+    std::vector<Out>* parts[4] = {&S->bufs->ps, &S->bufs->pf, &S->bufs->pl, &S->bufs->pt};
     std::vector<size_t> off((size_t)(4 * (T + 1)), 0);
     for (int q = 0; q < 4; q++) {
         for (int k = 0; k < T; k++) off[(size_t)(q * (T + 1) + k + 1)] = off[(size_t)(q * (T + 1) + k)] + (*parts[q])[(size_t)k].n;
@@ -694,14 +740,14 @@ int tc_sam_render(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_
 
 // tc_sam_render without the final copy: every text comes as n_parts pieces (the formatter threads' own buffers, in
 // order), ptr[4 * k + q] / len[4 * k + q] for part k of text q (0 sam, 1 fa, 2 log, 3 te).  The pieces stay valid until
-// the calling thread renders again.
+// the tc_sam is rendered again or freed.
 int tc_sam_render_parts(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_t canon_only, int32_t dry, int32_t n_threads,
                         int32_t* n_parts, const char** ptr, int64_t* len, int32_t max_parts, char* err, int64_t err_cap) {
     int T = 1;
     if (n_threads > max_parts) n_threads = max_parts;
     const int rc = render_parts(S, R, primary_only, canon_only, dry, n_threads, T, err, err_cap);
     if (rc != TC_OK) return rc;
-    std::vector<Out>* parts[4] = {&ps, &pf, &pl, &pt};
+    std::vector<Out>* parts[4] = {&S->bufs->ps, &S->bufs->pf, &S->bufs->pl, &S->bufs->pt};
     for (int k = 0; k < T; k++) for (int q = 0; q < 4; q++) { ptr[4 * k + q] = (*parts[q])[(size_t)k].buf.data(); len[4 * k + q] = (int64_t)(*parts[q])[(size_t)k].n; }
     *n_parts = T;
     return TC_OK;

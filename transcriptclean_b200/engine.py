@@ -8,7 +8,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TC_B200_LIB") or os.path.join(_HERE, "csrc", "libtc_b200.so")   # (TC_B200_LIB: tuning builds)
 
-EXPORTS = ["tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_set_options", "tc_ctx_stream",
+EXPORTS = ["tc_device_count", "tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_set_options", "tc_ctx_stream",
            "tc_ctx_load_genome", "tc_ctx_load_junctions", "tc_ctx_load_variants", "tc_correct_batch",
            "tc_dryrun_batch", "tc_batch_upload", "tc_batch_run", "tc_batch_download", "tc_get_timing",
            "tc_ctx_set_pipeline", "tc_sam_parse", "tc_sam_free", "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_render", "tc_sam_render_parts",
@@ -67,6 +67,8 @@ def load_library(path=LIB_PATH):
 
 
 def _declare(lib):
+    lib.tc_device_count.restype = C.c_int
+    lib.tc_device_count.argtypes = []
     lib.tc_ctx_create.restype = C.c_void_p
     lib.tc_ctx_create.argtypes = [C.c_int]
     lib.tc_ctx_destroy.argtypes = [C.c_void_p]
@@ -134,7 +136,7 @@ def _declare(lib):
     lib.tc_sj_free.restype = None
     lib.tc_sj_free.argtypes = [C.c_void_p]
     for f in EXPORTS:
-        if f not in ("tc_vcf_parse", "tc_vcf_tables", "tc_vcf_n_records", "tc_vcf_free", "tc_sj_parse", "tc_sj_tables", "tc_sj_free", "tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_stream", "tc_sam_parse", "tc_sam_free",
+        if f not in ("tc_vcf_parse", "tc_vcf_tables", "tc_vcf_n_records", "tc_vcf_free", "tc_sj_parse", "tc_sj_tables", "tc_sj_free", "tc_device_count", "tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_stream", "tc_sam_parse", "tc_sam_free",
                      "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_rnames", "tc_free", "tc_seq_pack", "tc_seq_packed_size", "tc_seq_pack2", "tc_seq_packed2_size", "tc_cig_pack16", "tc_sam_header_lines"):
             getattr(lib, f).restype = C.c_int
 
@@ -269,10 +271,20 @@ class BatchResult:
         return out
 
 
+def _c_text(text):
+    """(argument for a `const char*` parameter, length) of a SAM text: bytes as they are, any other writable buffer (a slice
+    of the CLI's file mapping) without a copy."""
+    if isinstance(text, bytes):
+        return text, len(text)
+    mv = memoryview(text)
+    return ((C.c_char * mv.nbytes).from_buffer(mv) if mv.nbytes and not mv.readonly else bytes(mv)), mv.nbytes
+
+
 def sam_rnames(lib, text):
     """Set of RNAME strings of the alignment lines of a SAM text (bytes)."""
     n = C.c_int64()
-    p = lib.tc_sam_rnames(text, len(text), C.byref(n))
+    text, n_text = _c_text(text)
+    p = lib.tc_sam_rnames(text, n_text, C.byref(n))
     if not p:
         raise MemoryError("tc_sam_rnames")
     try:
@@ -284,7 +296,8 @@ def sam_rnames(lib, text):
 def sam_header_lines(lib, text):
     """The '@' lines of a SAM text (bytes), newline-terminated, as str."""
     n = C.c_int64()
-    p = lib.tc_sam_header_lines(text, len(text), C.byref(n))
+    text, n_text = _c_text(text)
+    p = lib.tc_sam_header_lines(text, n_text, C.byref(n))
     if not p:
         raise MemoryError("tc_sam_header_lines")
     try:
@@ -299,12 +312,12 @@ class SamText:
 
     def __init__(self, lib, text, genome, n_threads=None, alphabet=None):
         self._lib = lib
-        self._text = text if isinstance(text, bytes) else bytes(text)      # kept alive: fields are referenced
+        self._text, n_text = _c_text(text)                                 # kept alive: fields are referenced
         names = (C.c_char_p * len(genome.names))(*[n.encode() for n in genome.names])
         err = C.create_string_buffer(1024)
         nt = int(n_threads or min(32, os.cpu_count() or 1))
         self._nt = nt
-        self._h = lib.tc_sam_parse(self._text, len(self._text), len(genome.names), names, genome.chrom_len.ctypes.data, nt, err, 1024)
+        self._h = lib.tc_sam_parse(self._text, n_text, len(genome.names), names, genome.chrom_len.ctypes.data, nt, err, 1024)
         if not self._h:
             from .sam import SamFormatError
             raise SamFormatError(err.value.decode())
@@ -356,7 +369,7 @@ class SamText:
 
     def render_parts(self, raw_out, primary_only=False, canon_only=False, dry=False):
         """Like render(copy=False) but without the library's final join: {"sam","fa","log","te"} -> list of memoryviews
-        (the formatter threads' pieces, in order), valid until this thread renders again."""
+        (the formatter threads' pieces, in order), valid until this object renders again or is closed."""
         cap = 64
         ptr, ln, n = (C.c_void_p * (4 * cap))(), (C.c_int64 * (4 * cap))(), C.c_int32()
         err = C.create_string_buffer(1024)
