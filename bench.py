@@ -392,6 +392,13 @@ def main():
                   + 8.0 * len(res.cig_op) + float(res.md_len.sum()) + 128.0 * int(primary.sum()))
     bytes_plan = (5.0 * len(cols["cig_op"]) + float(cols["md"].nbytes) + 8.0 * len(res.cig_op) + 16.0 * len(res.te)
                   + 96.0 * int(primary.sum()))
+    # whole step against SURVEY.md 8(d)'s bytes per read (B_read): 4-bit SEQ in, CIGAR / MD in, the fixed record, 2-bit + case plane under
+    # the exonic reference bases, ASCII SEQ out, CIGAR' / MD' / junction / TE rows out  (MD in is counted by its bytes)
+    n_jn_total = int(len(res.jm)) if hasattr(res, "jm") else 0
+    m_total = float(m_per_read[primary].sum())
+    bytes_step = (0.5 * float(cols["seq"].nbytes) + 4.0 * len(cols["cig_op"]) + float(cols["md"].nbytes) + 32.0 * args.reads
+                  + 0.375 * m_total + float(res.seq_len.astype(np.int64).sum()) + 4.0 * len(res.cig_op) + float(res.md_len.sum())
+                  + 9.0 * n_jn_total + 16.0 * len(res.te) + 24.0 * args.reads)
     per = {k: v / steps for k, v in kern.items()}
     dom = max(("k_emit_ms", "k_plan_ms", "k_junction_ms", "k_nmmd_init_ms", "k_measure_ms"), key=lambda k: per[k])
     dom_bytes = bytes_emit if dom == "k_emit_ms" else bytes_plan
@@ -420,7 +427,13 @@ def main():
         "kernel_ms_per_step": per, "exact_nmmd_reads_per_step": int(exact_reads), "ascii_path_reads_per_step": int(ascii_reads),
         "roofline": {"bound": "hbm", "kernel": dom.replace("_ms", ""), "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": dom_bytes},
+                     "algorithmic_bytes_per_launch": dom_bytes,
+                     "note": "k_emit = the output stage (k_verify + k_emit over the reads it lists); the byte formula is SURVEY.md 8(d)'s "
+                             "(ASCII SEQ in and out counted) although the stage itself now reads the 2-bit plane and writes no SEQ row: "
+                             "`traffic` is what it moves"},
+        "roofline_step": {"bound": "hbm", "achieved": bytes_step / (ms_run / steps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": bytes_step / (ms_run / steps * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_step": bytes_step,
+                          "note": "every kernel of the step against SURVEY.md 8(d)'s B_read x reads"},
         "clocks": clocks,
     }
     if ms_dry > 0:

@@ -123,3 +123,46 @@ def check_seq_forms(engine, seed, n_reads=160):
         return True
     finally:
         engine.seq2, engine.seq4, engine.seq4_text, engine.cig16 = True, True, False, True
+
+
+def check_plane_and_ascii_paths(engine, seed, n_reads=300, **kw):
+    """The NM / MD check on the 2-bit plane (k_verify) and the ASCII path alone (a context made under TC_NO_PLANE=1: k_emit
+    decides every read) give the same results, for SEQ sent as 2-bit rows, as 4-bit codes and as ASCII; the plane path really
+    settles reads (fewer reads reach the ASCII path than the batch holds)."""
+    import os
+    import numpy as np
+    from transcriptclean_b200 import sam
+    from transcriptclean_b200.engine import Engine
+    from transcriptclean_b200.tables import build_sj_tables, build_variant_tables
+    case = synth.make_case(seed, n_reads=n_reads, **kw)
+    sjf, vcf = pipeline.write_tables(case.sj_rows, case.vcf_rows)
+    gi = GenomeImage.from_dict(case.genome)
+    chroms = set(l.split("\t")[2] for l in case.lines)
+    cols = sam.parse_lines(case.lines, gi).cols
+    os.environ["TC_NO_PLANE"] = "1"
+    try:
+        plain = Engine(engine.device)
+    finally:
+        del os.environ["TC_NO_PLANE"]
+    names = ("status", "counters", "nm", "te_words", "cig_op", "cig_len", "jm", "ji", "delta_len", "md_len", "seq_len")
+    try:
+        for e in (engine, plain):
+            e.load_genome(gi); e.load_junctions(build_sj_tables(sjf, chroms, gi.index)); e.load_variants(build_variant_tables(vcf, 5, gi.index))
+        settled = 0
+        for seq2, seq4 in ((True, True), (False, True), (False, False)):
+            for e in (engine, plain):
+                e.seq2, e.seq4 = seq2, seq4
+            a, b = engine.correct(cols), plain.correct(cols)
+            ta, tb = engine.timing(), plain.timing()
+            assert tb["ascii_path_reads"] == len(case.lines) and ta["ascii_path_reads"] <= len(case.lines)
+            settled += len(case.lines) - ta["ascii_path_reads"]
+            for name in names:
+                assert np.array_equal(getattr(a, name), getattr(b, name)), (seq2, seq4, name)
+            for i in range(len(case.lines)):                       # (MD values lie in arbitrary order in the pool)
+                ma = a.md[int(a.md_off[i]):int(a.md_off[i]) + int(a.md_len[i])].tobytes()
+                mb = b.md[int(b.md_off[i]):int(b.md_off[i]) + int(b.md_len[i])].tobytes()
+                assert ma == mb and a.read_seq(i) == b.read_seq(i), (seq2, seq4, i, ma, mb)
+        return settled
+    finally:
+        plain.close()
+        engine.seq2, engine.seq4 = True, True

@@ -91,3 +91,11 @@ def test_empty_batch(engine):
     refs = api.make_refs(GenomeImage.from_dict({"chr1": "ACGT" * 100}), engine=engine)
     out = api.correct_batch_text([], api.Struct(), refs)
     assert out == {"sam": "", "fa": "", "log": "", "te": ""}
+
+
+def test_plane_path_and_ascii_path_agree(engine):
+    """k_verify (NM / MD on the 2-bit plane of the input SEQ) against k_emit deciding every read (TC_NO_PLANE=1), every SEQ form;
+    with variants in play (reads that keep a mismatch go to the ASCII path) and with heavy errors."""
+    assert pc.check_plane_and_ascii_paths(engine, 4101, n_reads=300) > 0
+    assert pc.check_plane_and_ascii_paths(engine, 4102, n_reads=200, err=0.10, shift_frac=0.5) > 0
+    pc.check_plane_and_ascii_paths(engine, 4103, n_reads=200, exon_len=(12, 40), err=0.05)
