@@ -137,7 +137,7 @@ void set_err(char* err, int64_t cap, const std::string& m) {
     if (err && cap > 0) { snprintf(err, (size_t)cap, "%s", m.c_str()); }
 }
 
-void parse_range(const char* T, int64_t a, int64_t b, const std::unordered_map<std::string, int>& cmap, const int64_t* clen, Part& P) {
+void parse_range_body(const char* T, int64_t a, int64_t b, const std::unordered_map<std::string, int>& cmap, const int64_t* clen, Part& P) {
     int64_t p = a;
     std::vector<Span> fld;
     {   // sized from the byte range: a long-read SAM line is mostly SEQ (and QUAL when present)
@@ -259,6 +259,12 @@ void parse_range(const char* T, int64_t a, int64_t b, const std::unordered_map<s
 #undef qname
 }
 
+// (a thread body: an allocation failure must come back as the part's error, not end the process)
+void parse_range(const char* T, int64_t a, int64_t b, const std::unordered_map<std::string, int>& cmap, const int64_t* clen, Part& P) {
+    try { parse_range_body(T, a, b, cmap, clen, P); }
+    catch (const std::exception& e) { P.err = std::string("tc_sam_parse: ") + e.what(); }
+}
+
 template <class T> void append(std::vector<T>& d, const std::vector<T>& s) { d.insert(d.end(), s.begin(), s.end()); }
 
 const char* const CLASS_NAME[3] = {"primary", "unmapped", "non-primary"};
@@ -319,8 +325,8 @@ int64_t apply_delta(const uint8_t* in, int64_t in_len, const uint8_t* dl, int64_
     return o;
 }
 
-void render_range(const tc_sam* S, const tc_batch_out* R, int64_t a, int64_t b, bool primary_only, bool canon_only, bool dry,
-                  Out& sam, Out& fa, Out& lg, Out& te, int64_t& bad_delta) {
+void render_range_body(const tc_sam* S, const tc_batch_out* R, int64_t a, int64_t b, bool primary_only, bool canon_only, bool dry,
+                       Out& sam, Out& fa, Out& lg, Out& te, int64_t& bad_delta) {
     const char* T = S->text;
     for (int64_t i = a; i < b; i++) {
         const uint32_t st = R->status[i]; const int cls = (int)(st & TC_ST_CLASS_MASK);
@@ -464,7 +470,9 @@ tc_sam* tc_sam_parse(const char* text, int64_t len, int32_t n_chrom, const char*
     for (int k = 1; k <= T; k++) if (cut[k] < cut[k - 1]) cut[k] = cut[k - 1];
     // Buffers are recycled (per calling thread / through a small pool of tc_sam objects): touching
     // fresh pages costs more than the parsing itself.
-    tc_sam* S = sam_acquire();
+    tc_sam* S = nullptr;
+  try {
+    S = sam_acquire();
     std::vector<Part>& parts = S->bufs->parts;
     if (parts.size() < (size_t)T) parts.resize((size_t)T);
     for (auto& p : parts) p.reset();
@@ -511,6 +519,11 @@ tc_sam* tc_sam_parse(const char* text, int64_t len, int32_t n_chrom, const char*
     S->other_off.push_back((int64_t)S->other.size());
     S->n = (int64_t)S->flag.size();
     return S;
+  } catch (const std::exception& e) {                                  // allocation failure: an error return, not the end of the process
+    set_err(err, err_cap, std::string("tc_sam_parse: ") + e.what());
+    if (S) { try { sam_release(S); } catch (...) {} }
+    return nullptr;
+  }
 }
 
 // distinct RNAME values of the alignment lines, newline-joined (what split_SAM collects for
@@ -677,6 +690,13 @@ void tc_sam_batch(const tc_sam* S, tc_batch_in* b) {
 }
 
 // the four texts as the parts of the T formatter threads (ps / pf / pl / pt, per calling thread, storage kept between batches)
+// (a thread body: -2 in bad_delta = out of host memory)
+static void render_range(const tc_sam* S, const tc_batch_out* R, int64_t a, int64_t b, bool primary_only, bool canon_only, bool dry,
+                         Out& sam, Out& fa, Out& lg, Out& te, int64_t& bad_delta) {
+    try { render_range_body(S, R, a, b, primary_only, canon_only, dry, sam, fa, lg, te, bad_delta); }
+    catch (const std::exception&) { bad_delta = -2; }
+}
+
 static int render_parts(tc_sam* S, const tc_batch_out* R, int32_t primary_only, int32_t canon_only, int32_t dry, int32_t n_threads,
                         int& T_out, char* err, int64_t err_cap) {
     if (!S || !R || R->n_reads != S->n) { set_err(err, err_cap, "tc_sam_render: result does not belong to this batch"); return TC_E_ARG; }
@@ -699,6 +719,7 @@ static int render_parts(tc_sam* S, const tc_batch_out* R, int32_t primary_only, 
                         std::ref(pl[(size_t)k]), std::ref(pt[(size_t)k]), std::ref(bad[(size_t)k]));
     }
     for (auto& t : th) t.join();
+    for (int k = 0; k < T; k++) if (bad[(size_t)k] == -2) { set_err(err, err_cap, "tc_sam_render: out of host memory"); return TC_E_ARG; }
     for (int k = 0; k < T; k++) if (bad[(size_t)k] >= 0) {
         set_err(err, err_cap, "read " + std::string(S->text + S->f[0][bad[(size_t)k]].s, (size_t)S->f[0][bad[(size_t)k]].n) + ": the SEQ delta does not fit the input SEQ (result of another batch?)");
         return TC_E_ARG;
