@@ -152,6 +152,23 @@ def n_gpus_available(lib=None):
         return 1
 
 
+def _hide_unused_gpus(want):
+    """The CUDA runtime brings up every visible device when it starts (seconds on an eight-GPU box, during which the scan of the
+    SAM file stalls as well): before the first CUDA call, CUDA_VISIBLE_DEVICES is narrowed to the `want` devices this run will
+    open - the first ones of the current list, or of /dev/nvidia<N> when the variable is not set."""
+    import re
+    cur = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if cur is not None:
+        ids = [x.strip() for x in cur.split(",") if x.strip()]
+    else:
+        try:
+            ids = [str(k) for k in sorted(int(m.group(1)) for m in (re.fullmatch(r"nvidia(\d+)", f) for f in os.listdir("/dev")) if m)]
+        except OSError:
+            ids = []
+    if len(ids) > want:
+        os.environ["CUDA_VISIBLE_DEVICES"] = ",".join(ids[:want])
+
+
 class _FileWriters:
     """One writer thread per output file: the four texts of a block are written side by side (the page-cache copies of
     the clean SAM, the FASTA and the TE log are what the writing end of the pipeline spends its time on)."""
@@ -216,7 +233,7 @@ def run(options, engines=None):
     """engines: optional list of pre-built Engine objects (tests inject CPU stand-ins here).
     The SAM file is streamed twice in blocks (TC_CLI_BLOCK_MB, default 12): a scan for the header lines and the
     chromosome names (what split_SAM collects, TC.py:519-541), then the correction.  Blocks are handed to worker
-    threads in input order - TC_CLI_WORKERS_PER_GPU (default 4) workers per GPU, each with its own engine context, so
+    threads in input order - TC_CLI_WORKERS_PER_GPU (default: up to 4) workers per GPU, each with its own engine context, so
     that parsing block k+1, correcting block k and rendering block k-1 overlap - and their four texts are appended to
     the output files in input order (combine_outputs, TC.py:604-663: headers first; no SAM / FASTA in --dryRun).
     SAM parsing and text rendering run in the library's multi-threaded C++ host code (csrc/tc_host.cpp); the SJ / VCF
@@ -235,8 +252,16 @@ def run(options, engines=None):
     pool = ThreadPoolExecutor(max_workers=max(2, min(16, os.cpu_count() or 2)))
     made = None
     if engines is None:                                   # the device contexts come up while the SAM file is scanned
-        n = max(1, min(int(options.n_threads), max(1, n_gpus_available(lib))))
-        per_gpu = max(1, int(os.environ.get("TC_CLI_WORKERS_PER_GPU", "4")))
+        # GPUs: the text path is bound by the host's cores (parser / formatter threads, file writes), one GPU keeps about a
+        # dozen of them busy, and opening a device context costs most of a second: one GPU per 12 host cores, at most
+        # --threads of the visible ones (TC_CLI_GPUS overrides).  profiles/r02f_cli_wallclock_8gpu_box.json
+        cores = os.cpu_count() or 4
+        want = int(os.environ.get("TC_CLI_GPUS", "0")) or max(1, min(int(options.n_threads), max(1, cores // 12)))
+        _hide_unused_gpus(want)
+        n = max(1, min(want, max(1, n_gpus_available(lib))))
+        # workers per GPU: four where the host has the cores for them (each worker's parser / formatter threads are the host's
+        # cores divided by the workers), fewer on a box with many GPUs and few cores
+        per_gpu = int(os.environ.get("TC_CLI_WORKERS_PER_GPU", "0")) or max(1, min(4, ((os.cpu_count() or 4) // 4) // n))
         made = [pool.submit(E.Engine, d) for d in range(n) for _ in range(per_gpu)]
     chroms, header = set(), ""
     pending = []
