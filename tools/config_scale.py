@@ -146,7 +146,8 @@ def main():
         shape = "pacbio" if (args.config == 3 or step % 2 == 0) else "ont"
         cols, nm = w.reads(shape, n, seed_offset=1000 * rank + step)
         cols["chrom"] = np.where(cols["chrom"] == 0, cidx, cols["chrom"]).astype(np.int32)
-        hcols = eng.pack_cigar(eng.pack_cols2(cols) or eng.pack_cols(cols))
+        nt = max(1, (os.cpu_count() or 8) // world)                   # this rank's share of the host threads
+        hcols = eng.pack_cigar(eng.pack_cols2(cols, n_threads=nt) or eng.pack_cols(cols, n_threads=nt), n_threads=nt)
         if "cig16" in hcols:
             hcols = {k: v for k, v in hcols.items() if k not in ("cig_op", "cig_len")}
         pinned = {}
@@ -161,9 +162,11 @@ def main():
         b.seq_bits = int(hcols.get("seq_bits", 4)); b.n_exc = len(hcols["exc_pos"]) if "exc_pos" in hcols else 0
         b.n_cig_exc = len(hcols["cig_exc_idx"]) if "cig_exc_idx" in hcols else 0
         for mode in (("dry", "full") if args.config == 5 else ("full",)):
-            if step == 0:
-                (eng.raw_dryrun if mode == "dry" else eng.raw_correct)(b)      # warm-up of this mode's buffers
+            if step < 2:
+                (eng.raw_dryrun if mode == "dry" else eng.raw_correct)(b)      # warm-up of this mode's buffers (both read shapes)
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()            # every rank times its call at the same moment: no rank's generator threads run beside it
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             out = (eng.raw_dryrun if mode == "dry" else eng.raw_correct)(b)
