@@ -155,3 +155,54 @@ def test_genome_image_cache_round_trip():
     fresh = GenomeImage.from_fasta(d + "/g.fa")
     assert np.array_equal(c.bases2, fresh.bases2) and not np.array_equal(c.bases2, a.bases2)
     assert GenomeImage.load(d + "/g.fa.tcb200.npz").source == GenomeImage.fasta_fingerprint(d + "/g.fa")
+
+
+def test_unused_gpus_are_hidden_before_cuda_starts(monkeypatch):
+    """cli._hide_unused_gpus narrows CUDA_VISIBLE_DEVICES to the first `want` devices of the current list (or of /dev/nvidia<N>)
+    and never widens it."""
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "3,5,6,7")
+    cli._hide_unused_gpus(2)
+    assert os.environ["CUDA_VISIBLE_DEVICES"] == "3,5"
+    cli._hide_unused_gpus(8)
+    assert os.environ["CUDA_VISIBLE_DEVICES"] == "3,5"
+    monkeypatch.delenv("CUDA_VISIBLE_DEVICES")
+    monkeypatch.setattr(os, "listdir", lambda p: ["nvidia0", "nvidia1", "nvidia10", "nvidia2", "nvidiactl", "nvidia-uvm", "null"])
+    cli._hide_unused_gpus(3)
+    assert os.environ["CUDA_VISIBLE_DEVICES"] == "0,1,2"
+    monkeypatch.delenv("CUDA_VISIBLE_DEVICES")
+    monkeypatch.setattr(os, "listdir", lambda p: ["null", "zero"])
+    cli._hide_unused_gpus(1)
+    assert "CUDA_VISIBLE_DEVICES" not in os.environ
+
+
+def test_file_writers_write_every_piece_in_order_and_surface_errors():
+    d = tempfile.mkdtemp(prefix="tc_wr_")
+    files = {k: open(d + "/" + k, "wb") for k in ("sam", "fa", "log", "te")}
+    w = cli._FileWriters(files)
+    for blk in range(5):
+        w.write({k: [memoryview(("%s%d-%d|" % (k, blk, p)).encode()) for p in range(3)] for k in files})
+    w.close()
+    for f in files.values():
+        f.close()
+    assert open(d + "/fa").read() == "".join("fa%d-%d|" % (b, p) for b in range(5) for p in range(3))
+    closed = {k: open(d + "/" + k + "2", "wb") for k in ("log", "te")}
+    w = cli._FileWriters(closed)
+    closed["te"].close()
+    with pytest.raises(ValueError):
+        w.write({"log": [b"x"], "te": [b"y"]})
+    w.close()
+
+
+def test_sam_blocks_are_slices_of_a_mapping_and_cover_the_file():
+    d = tempfile.mkdtemp(prefix="tc_blk_")
+    lines = [("read%d\t0\tchr1\t%d\t60\t10M\t*\t0\t0\tACGTACGTAC\t*" % (k, k + 1)).encode() for k in range(500)]
+    for tail in (b"\n", b""):                             # with and without a newline at the end of the file
+        open(d + "/x.sam", "wb").write(b"\n".join(lines) + tail)
+        blocks = list(cli.sam_blocks(d + "/x.sam", 700))
+        assert len(blocks) > 20 and all(isinstance(b, memoryview) for b in blocks)
+        assert b"".join(blocks) == b"\n".join(lines) + tail
+        assert all(bytes(b).endswith(b"\n") for b in blocks[:-1])
+    open(d + "/long.sam", "wb").write(b"A" * 5000 + b"\n" + b"B" * 10 + b"\n")      # a line longer than a block
+    assert [len(b) for b in cli.sam_blocks(d + "/long.sam", 1000)] == [5001, 11]
+    open(d + "/empty.sam", "wb").close()
+    assert list(cli.sam_blocks(d + "/empty.sam", 1000)) == []
