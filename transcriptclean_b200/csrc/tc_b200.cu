@@ -117,12 +117,26 @@ TC_HD void small_copies_read(const Params& P, const OutDev& O, int64_t i, int dr
 
 __global__ void k_measure(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) measure_read(P, i); }
 #ifndef TC_PLAN_BLOCKS
-#define TC_PLAN_BLOCKS 4      // registers over occupancy: 8 blocks (62 registers, spills) was 7 % slower
+#define TC_PLAN_BLOCKS 5      // registers over occupancy: 8 blocks (62 registers, spills) was 7 % slower; 5 with the junction objects fused in: 1.54 -> 1.50 ms
 #endif
 // (Handing the reads of a 256-read tile out in order of their work - a counting sort in shared memory, so that the 32 reads of a warp
 //  are neighbours in list length - was measured in round 2 and lost: k_plan 1.22 -> 1.37 ms, ONT 5.71 -> 5.97 ms per 1 M reads.  The
 //  lanes that idle are not what bounds these kernels; the scattered per-read rows the permutation adds cost more.)
-__global__ void __launch_bounds__(128, TC_PLAN_BLOCKS) k_plan(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) plan_read(P, i); }
+// TC_FUSE_JNINIT: the read's junction objects (junction_init_read: motif fetches and annotation lookups, all latency) are made by the
+// thread that planned the read, so that their waits are filled by the other warps' planning instead of a kernel of their own
+#ifndef TC_FUSE_JNINIT
+#define TC_FUSE_JNINIT 1
+#endif
+__global__ void __launch_bounds__(128, TC_PLAN_BLOCKS) k_plan(Params P, int32_t* list, unsigned* count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.B.n) return;
+    plan_read(P, i);
+#if TC_FUSE_JNINIT
+    if (junction_init_read(P, i)) list[atomicAdd(count, 1u)] = (int32_t)i;
+#else
+    (void)list; (void)count;
+#endif
+}
 #include "tc_junction.cuh"
 
 __global__ void k_sizes(Params P) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < P.B.n) sizes_read(P, i); }
@@ -869,11 +883,13 @@ static int slot_run(tc_ctx* ctx, Slot& S, int dry, stream_t st, bool timed) {
     S.W.ws = (u64*)S.w_ws.p; P.W.ws = S.W.ws;
     if (dry) { k_dry<<<gb, TPB, 0, st>>>(P); ctx->tm.launches++; CK(cudaGetLastError()); if (timed) { CK(cudaEventRecord(ctx->ev[5], st)); CK(cudaEventRecord(ctx->ev[6], st)); } }
     else {
-        k_plan<<<gb, TPB, 0, st>>>(P); ctx->tm.launches++; CK(cudaGetLastError());
-        if (timed) CK(cudaEventRecord(ctx->ev[5], st));
         CK(S.w_fix_list.ensure((size_t)(n + 1) * 4));
         if (be_zero(ctx, st, cur + 2, 8)) return TC_E_CUDA;
+        k_plan<<<gb, TPB, 0, st>>>(P, (int32_t*)S.w_fix_list.p, (unsigned*)(cur + 2)); ctx->tm.launches++; CK(cudaGetLastError());
+        if (timed) CK(cudaEventRecord(ctx->ev[5], st));
+#if !TC_FUSE_JNINIT
         k_jn_init<<<gb, TPB, 0, st>>>(P, (int32_t*)S.w_fix_list.p, (unsigned*)(cur + 2)); ctx->tm.launches++; CK(cudaGetLastError());
+#endif
         int occ_j = 1; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_j, k_jn_fix, WARPS_PER_BLOCK * 32, 0));
         const int gj = (int)(wb < (int64_t)nsm * occ_j ? wb : (int64_t)nsm * occ_j);            // persistent grid = the resident blocks
         k_jn_fix<<<gj, WARPS_PER_BLOCK * 32, 0, st>>>(P, (const int32_t*)S.w_fix_list.p, (const unsigned*)(cur + 2)); ctx->tm.launches++; CK(cudaGetLastError());
