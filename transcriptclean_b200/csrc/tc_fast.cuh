@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, TC_FAST_BLOCKS) k_verify
                     if (lane < nrun) {
                         const int q = SM.run_q[lane];
                         int s = -1;                                    // last segment that starts at or before q
-                        for (int step = 1 << (31 - __clz(ns)); step >= 1; step >>= 1) { const int t = s + step; if (t < ns && (int)SM.seg_o[t] <= q) s = t; }
+                        for (int step = ns > 0 ? 1 << (31 - __clz(ns)) : 0; step >= 1; step >>= 1) { const int t = s + step; if (t < ns && (int)SM.seg_o[t] <= q) s = t; }
                         if (s >= 0) {
                             const u64 sg = sb < 0 ? seg_make(0, 0, Lq) : segs[s]; const int o = SM.seg_o[s], slen = (int)seg_len(sg);
                             if (seg_kind(sg) == 0 && q > o && q < o + slen) {

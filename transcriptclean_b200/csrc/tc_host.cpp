@@ -69,14 +69,15 @@ template <class T> using PV = std::vector<T, PinnedAlloc<T>>;
 struct Part {                       // what one parser thread produces
     UV<int32_t> flag, chrom, pos; UV<uint8_t> tags, cls;
     UV<int64_t> seq_len, cig_n, md_n, ji_n;
-    UV<uint8_t> seq, cig_op, md; UV<int32_t> cig_len, ji;
+    UV<uint8_t> cig_op, md; UV<int32_t> cig_len, ji;
+    UV<Span> seq_at; size_t seq_bytes = 0;   // where every read's SEQ lies in the text (copied once, straight into the batch's column)
     UV<Span> line, f[9], cigar, tg[4];
     UV<int64_t> other_off; UV<Span> other;
     UV<Span> header;
     std::string err;
     void reset() {                   // empty, capacity kept: the parts of a host thread are reused from batch to batch
         flag.clear(); chrom.clear(); pos.clear(); tags.clear(); cls.clear(); seq_len.clear(); cig_n.clear(); md_n.clear(); ji_n.clear();
-        seq.clear(); cig_op.clear(); md.clear(); cig_len.clear(); ji.clear(); line.clear(); cigar.clear(); other_off.clear(); other.clear();
+        seq_at.clear(); seq_bytes = 0; cig_op.clear(); md.clear(); cig_len.clear(); ji.clear(); line.clear(); cigar.clear(); other_off.clear(); other.clear();
         for (auto& v : f) v.clear();
         for (auto& v : tg) v.clear();
         header.clear(); err.clear();
@@ -142,7 +143,7 @@ void parse_range_body(const char* T, int64_t a, int64_t b, const std::unordered_
     std::vector<Span> fld;
     {   // sized from the byte range: a long-read SAM line is mostly SEQ (and QUAL when present)
         const size_t bytes = (size_t)(b - a), est = bytes / 1500 + 16;
-        P.seq.reserve(bytes - bytes / 8); P.cig_op.reserve(est * 40); P.cig_len.reserve(est * 40); P.md.reserve(est * 80);
+        P.seq_at.reserve(est); P.cig_op.reserve(est * 40); P.cig_len.reserve(est * 40); P.md.reserve(est * 80);
         P.flag.reserve(est); P.chrom.reserve(est); P.pos.reserve(est); P.tags.reserve(est); P.cls.reserve(est); P.line.reserve(est);
         for (int k = 0; k < 9; k++) P.f[k].reserve(est);
         for (int k = 0; k < 4; k++) P.tg[k].reserve(est);
@@ -252,7 +253,7 @@ void parse_range_body(const char* T, int64_t a, int64_t b, const std::unordered_
             }
         }
         P.chrom.push_back(c); P.pos.push_back((int32_t)posv); P.tags.push_back(tb);
-        put_bytes(P.seq, T + fld[9].s, fld[9].n);
+        P.seq_at.push_back(fld[9]); P.seq_bytes += (size_t)fld[9].n;
         P.seq_len.push_back(fld[9].n); P.cig_n.push_back(nops); P.md_n.push_back(mdn); P.ji_n.push_back(jin);
         P.cigar.push_back(fld[5]); for (int k = 0; k < 4; k++) P.tg[k].push_back(tg[k]);
     }
@@ -485,7 +486,7 @@ tc_sam* tc_sam_parse(const char* text, int64_t len, int32_t n_chrom, const char*
     std::vector<size_t> r0((size_t)T + 1, 0), s0((size_t)T + 1, 0), c0((size_t)T + 1, 0), m0((size_t)T + 1, 0), j0((size_t)T + 1, 0), o0((size_t)T + 1, 0);
     for (int k = 0; k < T; k++) {
         const Part& p = parts[(size_t)k];
-        r0[k + 1] = r0[k] + p.flag.size(); s0[k + 1] = s0[k] + p.seq.size(); c0[k + 1] = c0[k] + p.cig_op.size();
+        r0[k + 1] = r0[k] + p.flag.size(); s0[k + 1] = s0[k] + p.seq_bytes; c0[k + 1] = c0[k] + p.cig_op.size();
         m0[k + 1] = m0[k] + p.md.size(); j0[k + 1] = j0[k] + p.ji.size(); o0[k + 1] = o0[k] + p.other.size();
         for (auto& h : p.header) { S->header.append(text + h.s, (size_t)h.n); S->header.push_back('\n'); }
     }
@@ -501,12 +502,14 @@ tc_sam* tc_sam_parse(const char* text, int64_t len, int32_t n_chrom, const char*
         Part& p = parts[(size_t)k]; const size_t r = r0[k], m = p.flag.size();
         auto cp = [](auto& dst, size_t at, const auto& src) { if (!src.empty()) memcpy(dst.data() + at, src.data(), src.size() * sizeof(src[0])); };
         cp(S->flag, r, p.flag); cp(S->chrom, r, p.chrom); cp(S->pos, r, p.pos); cp(S->tags, r, p.tags); cp(S->cls, r, p.cls);
-        cp(S->seq, s0[k], p.seq); cp(S->cig_op, c0[k], p.cig_op); cp(S->cig_len, c0[k], p.cig_len); cp(S->md, m0[k], p.md); cp(S->ji, j0[k], p.ji);
+        cp(S->cig_op, c0[k], p.cig_op); cp(S->cig_len, c0[k], p.cig_len); cp(S->md, m0[k], p.md); cp(S->ji, j0[k], p.ji);
         cp(S->line, r, p.line); for (int q = 0; q < 9; q++) cp(S->f[q], r, p.f[q]); cp(S->cigar, r, p.cigar); for (int q = 0; q < 4; q++) cp(S->tg[q], r, p.tg[q]);
         cp(S->other, o0[k], p.other);
         int64_t so = (int64_t)s0[k], co = (int64_t)c0[k], mo = (int64_t)m0[k], jo = (int64_t)j0[k];
+        size_t si = 0;                                                   // (seq_at holds the primary reads only)
         for (size_t i = 0; i < m; i++) {
             S->seq_off[r + i] = so; S->cig_off[r + i] = co; S->md_off[r + i] = mo; S->ji_off[r + i] = jo; S->other_off[r + i] = (int64_t)o0[k] + p.other_off[i];
+            if (p.cls[i] == 0) { const Span sp = p.seq_at[si++]; if (sp.n > 0) memcpy(S->seq.data() + so, text + sp.s, (size_t)sp.n); }
             so += p.seq_len[i]; co += p.cig_n[i]; mo += p.md_n[i]; jo += p.ji_n[i];
         }
     };
