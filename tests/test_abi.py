@@ -66,3 +66,22 @@ def test_header_is_plain_c():
     sizes = [int(x) for x in subprocess.check_output([d + "/t"]).split()]
     assert sizes == [engine.TE_DTYPE.itemsize, ctypes.sizeof(engine._BatchIn), ctypes.sizeof(engine._BatchOut),
                      ctypes.sizeof(engine._Options), ctypes.sizeof(engine.Timing)]
+
+
+def test_host_only_entry_points_work_without_a_gpu():
+    """tc_cig_pack16 (16-bit CIGAR words + listed ops) and tc_device_count are host code: callable on a machine without a GPU."""
+    import numpy as np
+    from transcriptclean_b200 import engine
+    lib = engine.load_library()
+    assert lib.tc_device_count() >= 0
+    op = np.frombuffer(b"MIDNSHP=XBMQM", dtype=np.uint8).copy()
+    ln = np.array([5, 1, 4095, 4096, 7, 2, 3, 9, 8, 6, 0, 4, -1], dtype=np.int32)
+    w = np.zeros(len(op) + 8, dtype=np.uint16)
+    ei, eo, el = np.zeros(8, np.int64), np.zeros(8, np.uint8), np.zeros(8, np.int32)
+    m = lib.tc_cig_pack16(op.ctypes.data, ln.ctypes.data, len(op), w.ctypes.data, 8, ei.ctypes.data, eo.ctypes.data, el.ctypes.data, 1)
+    assert m == 4 and list(ei[:4]) == [3, 10, 11, 12]            # 4096N (too long), 0M, the letter Q, -1M
+    assert [chr(c) for c in eo[:4]] == ["N", "M", "Q", "M"] and list(el[:4]) == [4096, 0, 4, -1]
+    assert all(w[k] == 0xFFFF for k in (3, 10, 11, 12))
+    for k in (0, 1, 2, 4, 5, 6, 7, 8, 9):
+        assert "MIDNSHP=XB"[w[k] & 15] == chr(op[k]) and (w[k] >> 4) == ln[k]
+    assert lib.tc_cig_pack16(op.ctypes.data, ln.ctypes.data, len(op), w.ctypes.data, 3, ei.ctypes.data, eo.ctypes.data, el.ctypes.data, 1) == -1
