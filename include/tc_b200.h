@@ -302,6 +302,19 @@ void tc_sj_tables(const tc_sj* s, int64_t* n_don_s, const uint64_t** don_s, int6
                   int64_t* n_annot, const uint64_t** ann_k1, const uint64_t** ann_k2);
 void tc_sj_free(tc_sj* s);
 
+/* refs.genome from its FASTA (pyfaidx.Fasta(options.refGenome), TranscriptClean.py:221): the file is mapped and packed by all host
+ * threads into the planes of tc_ctx_load_genome.  tc_fasta_open finds the contigs (name = first word of the header line, pyfaidx's
+ * key, TC.py:469-470) and their lengths; tc_fasta_pack fills zeroed planes (chrom_off[k] = plane index of contig k's first base,
+ * n_pad = bases the planes hold) and returns the number of literal runs (every byte outside ACGTacgt), which tc_fasta_exceptions
+ * copies out.  GenomeImage.from_fasta (genome.py) is the same logic in numpy. */
+typedef struct tc_fasta tc_fasta;
+tc_fasta* tc_fasta_open(const char* path, int32_t n_threads, char* err, int64_t err_cap);
+int32_t tc_fasta_n_contigs(const tc_fasta* f);
+int tc_fasta_contig(const tc_fasta* f, int32_t k, const char** name, int32_t* name_len, int64_t* length);
+int64_t tc_fasta_pack(tc_fasta* f, const int64_t* chrom_off, int64_t n_pad, uint32_t* bases2, uint32_t* lower1, int32_t n_threads);
+int64_t tc_fasta_exceptions(const tc_fasta* f, int64_t* start, int64_t* end, uint8_t* byte);
+void tc_fasta_free(tc_fasta* f);
+
 #ifdef __cplusplus
 }
 #endif

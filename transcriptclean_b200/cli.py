@@ -281,7 +281,7 @@ def run(options, engines=None):
     drain(0)
     stamp("scan of the SAM file")
     print("Reading genome ..............................")
-    genome = GenomeImage.from_fasta_cached(options.refGenome)
+    genome = GenomeImage.from_fasta_cached(options.refGenome, lib=lib)
     stamp("genome image")
     if made is not None:
         engines = [f.result() for f in made]

@@ -227,4 +227,145 @@ void tc_sj_tables(const tc_sj* s, int64_t* n_don_s, const uint64_t** don_s, int6
     *n_annot = (int64_t)s->ann_k1.size(); *ann_k1 = s->ann_k1.data(); *ann_k2 = s->ann_k2.data();
 }
 
+// ---------------------------------------------------------------------------------- FASTA -> genome image
+// Replaces pyfaidx.Fasta's indexing of the reference FASTA (TranscriptClean.py:221) for the device: the file is mapped, cut into
+// records ('>' of the first header, then every "\n>") and packed by all host threads into the planes of tc_ctx_load_genome
+// (2-bit bases, lower-case bits, literal runs for every byte outside ACGTacgt).  GenomeImage.from_fasta (genome.py) is the same
+// logic in numpy; tests compare the two bit by bit.
+}  // extern "C"  (reopened below)
+
+#include <atomic>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+struct tc_fasta {
+    const char* data = nullptr; int64_t len = 0; bool mapped = false; std::string held;
+    struct Rec { int64_t name_s; int32_t name_n; int64_t body_s, body_e, length; };
+    std::vector<Rec> recs;
+    struct Task { int32_t rec; int64_t a, b, base0; };                  // bytes [a, b) of a record's body; base0 = bases of the record before a
+    std::vector<Task> tasks;
+    std::vector<int64_t> exc_start, exc_end; std::vector<uint8_t> exc_byte;
+    ~tc_fasta() { if (mapped && data) munmap((void*)data, (size_t)len); }
+};
+
+namespace tc_tables_detail {
+template <class F> void run_tasks(size_t n, int T, F f) {
+    std::atomic<size_t> next(0);
+    auto work = [&]() { for (size_t k = next.fetch_add(1); k < n; k = next.fetch_add(1)) f(k); };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(work);
+    work();
+    for (auto& x : th) x.join();
+}
+}  // namespace tc_tables_detail
+
+extern "C" {
+
+tc_fasta* tc_fasta_open(const char* path, int32_t n_threads, char* err, int64_t err_cap) {
+    using namespace tc_tables_detail;
+    const int T = n_threads < 1 ? 1 : n_threads;
+    tc_fasta* F = new tc_fasta();
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { set_err(err, err_cap, std::string("cannot open ") + path); delete F; return nullptr; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); set_err(err, err_cap, std::string("cannot stat ") + path); delete F; return nullptr; }
+    F->len = (int64_t)st.st_size;
+    if (F->len > 0) {
+        void* m = mmap(nullptr, (size_t)F->len, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) { close(fd); set_err(err, err_cap, std::string("cannot map ") + path); delete F; return nullptr; }
+        F->data = (const char*)m; F->mapped = true;
+    }
+    close(fd);
+    const char* D = F->data; const int64_t n = F->len;
+    // records: '>' of the first header, then every "\n>" behind a header line
+    int64_t pos = 0;
+    while (pos < n) {
+        const char* hp = (const char*)memchr(D + pos, '>', (size_t)(n - pos));
+        if (!hp) break;
+        const int64_t h = hp - D;
+        const char* nlp = (const char*)memchr(D + h, '\n', (size_t)(n - h));
+        const int64_t nl = nlp ? nlp - D : n;
+        int64_t end = n;
+        if (nl < n) { const char* nx = (const char*)memmem(D + nl, (size_t)(n - nl), "\n>", 2); if (nx) end = (nx - D) + 1; }
+        int64_t a = h + 1; while (a < nl && ws(D[a])) a++;
+        int64_t b = a; while (b < nl && !ws(D[b])) b++;
+        if (b == a) { set_err(err, err_cap, "FASTA header without a name"); delete F; return nullptr; }
+        tc_fasta::Rec r; r.name_s = a; r.name_n = (int32_t)(b - a); r.body_s = nl < n ? nl + 1 : n; r.body_e = end; r.length = 0;
+        if (r.body_e < r.body_s) r.body_e = r.body_s;
+        F->recs.push_back(r);
+        pos = end;
+    }
+    // bases per record: every body byte that is not a line end; counted by all threads over pieces of 4 MB
+    const int64_t piece = (int64_t)4 << 20;
+    for (size_t k = 0; k < F->recs.size(); k++)
+        for (int64_t a = F->recs[k].body_s; a < F->recs[k].body_e; a += piece)
+            F->tasks.push_back({(int32_t)k, a, std::min(a + piece, F->recs[k].body_e), 0});
+    std::vector<int64_t> cnt(F->tasks.size(), 0);
+    run_tasks(F->tasks.size(), T, [&](size_t k) {
+        const tc_fasta::Task& t = F->tasks[k]; int64_t le = 0;
+        for (int64_t j = t.a; j < t.b; j++) le += (D[j] == '\n') | (D[j] == '\r');
+        cnt[k] = (t.b - t.a) - le;
+    });
+    for (size_t k = 0; k < F->tasks.size(); k++) {
+        tc_fasta::Rec& r = F->recs[(size_t)F->tasks[k].rec];
+        F->tasks[k].base0 = r.length; r.length += cnt[k];
+    }
+    return F;
+}
+int32_t tc_fasta_n_contigs(const tc_fasta* f) { return f ? (int32_t)f->recs.size() : 0; }
+int tc_fasta_contig(const tc_fasta* f, int32_t k, const char** name, int32_t* name_len, int64_t* length) {
+    if (!f || k < 0 || (size_t)k >= f->recs.size()) return TC_E_ARG;
+    *name = f->data + f->recs[(size_t)k].name_s; *name_len = f->recs[(size_t)k].name_n; *length = f->recs[(size_t)k].length;
+    return TC_OK;
+}
+// planes must be zero; chrom_off[k] = plane index of contig k's first base.  Returns the number of literal runs (kept inside; tc_fasta_exceptions).
+int64_t tc_fasta_pack(tc_fasta* F, const int64_t* chrom_off, int64_t n_pad, uint32_t* bases2, uint32_t* lower1, int32_t n_threads) {
+    using namespace tc_tables_detail;
+    if (!F || !chrom_off || !bases2 || !lower1) return -1;
+    for (size_t k = 0; k < F->recs.size(); k++) if (chrom_off[k] < 0 || chrom_off[k] + F->recs[k].length > n_pad) return -1;
+    uint8_t code[256], kind[256];                                       // kind: 0 ACGT, 1 acgt, 2 line end, 3 literal
+    for (int c = 0; c < 256; c++) { code[c] = 0; kind[c] = 3; }
+    const char* up = "ACGT"; const char* lo = "acgt";
+    for (int k = 0; k < 4; k++) { code[(uint8_t)up[k]] = (uint8_t)k; kind[(uint8_t)up[k]] = 0; code[(uint8_t)lo[k]] = (uint8_t)k; kind[(uint8_t)lo[k]] = 1; }
+    kind[10] = kind[13] = 2;
+    struct Run { int64_t s, e; uint8_t b; };
+    std::vector<std::vector<Run>> runs(F->tasks.size());
+    const char* D = F->data;
+    run_tasks(F->tasks.size(), n_threads < 1 ? 1 : n_threads, [&](size_t ti) {
+        const tc_fasta::Task& t = F->tasks[ti];
+        int64_t p = chrom_off[t.rec] + t.base0;                            // plane index of the next base
+        const int64_t p_first = p;
+        uint32_t w2 = 0, wl = 0; std::vector<Run>& R = runs[ti];
+        // a word goes out when the plane index leaves it - OR-ed in, because the first and the last word of a piece are shared with
+        // the neighbouring pieces (the planes start as zeros)
+        auto put2 = [&](int64_t word, uint32_t v) { if (v) __atomic_fetch_or(&bases2[word], v, __ATOMIC_RELAXED); };
+        auto putl = [&](int64_t word, uint32_t v) { if (v) __atomic_fetch_or(&lower1[word], v, __ATOMIC_RELAXED); };
+        for (int64_t j = t.a; j < t.b; j++) {
+            const uint8_t c = (uint8_t)D[j]; const uint8_t k = kind[c];
+            if (k == 2) continue;
+            w2 |= (uint32_t)code[c] << ((p & 15) * 2);
+            if (k == 1) wl |= 1u << (p & 31);
+            else if (k == 3) { if (!R.empty() && R.back().e == p && R.back().b == c) R.back().e = p + 1; else R.push_back({p, p + 1, c}); }
+            p++;
+            if ((p & 15) == 0) { put2((p - 1) >> 4, w2); w2 = 0; if ((p & 31) == 0) { putl((p - 1) >> 5, wl); wl = 0; } }
+        }
+        if (p > p_first) { if (p & 15) put2(p >> 4, w2); if (p & 31) putl(p >> 5, wl); }
+    });
+    F->exc_start.clear(); F->exc_end.clear(); F->exc_byte.clear();
+    for (auto& R : runs) for (const Run& r : R) {                       // (pieces are in plane order: runs that meet at a piece boundary are joined)
+        if (!F->exc_start.empty() && F->exc_end.back() == r.s && F->exc_byte.back() == r.b) F->exc_end.back() = r.e;
+        else { F->exc_start.push_back(r.s); F->exc_end.push_back(r.e); F->exc_byte.push_back(r.b); }
+    }
+    return (int64_t)F->exc_start.size();
+}
+int64_t tc_fasta_exceptions(const tc_fasta* f, int64_t* start, int64_t* end, uint8_t* byte) {
+    if (!f) return 0;
+    const size_t n = f->exc_start.size();
+    if (start && end && byte && n) { memcpy(start, f->exc_start.data(), n * 8); memcpy(end, f->exc_end.data(), n * 8); memcpy(byte, f->exc_byte.data(), n); }
+    return (int64_t)n;
+}
+void tc_fasta_free(tc_fasta* f) { delete f; }
+
 }  // extern "C"

@@ -127,6 +127,36 @@ class GenomeImage:
             g._put(int(g.chrom_off[i]), body)
         return g
 
+    @classmethod
+    def from_fasta_lib(cls, path, lib, n_threads=None):
+        """from_fasta through the library's C++ packer (tc_fasta_open / tc_fasta_pack, csrc/tc_tables.cpp): the file is mapped
+        and packed by all host threads - seconds for a 3-Gb genome where the numpy passes above take minutes.  Same image."""
+        import ctypes as C
+        import os
+        nt = int(n_threads or min(32, os.cpu_count() or 1))
+        err = C.create_string_buffer(512)
+        h = lib.tc_fasta_open(os.fsencode(str(path)), nt, err, 512)
+        if not h:
+            raise ValueError("%s: %s" % (path, err.value.decode() or "cannot read the FASTA file"))
+        try:
+            names, lens = [], []
+            p, n, L = C.c_void_p(), C.c_int32(), C.c_int64()
+            for k in range(lib.tc_fasta_n_contigs(h)):
+                lib.tc_fasta_contig(h, k, C.byref(p), C.byref(n), C.byref(L))
+                names.append(C.string_at(p, n.value).decode())
+                lens.append(int(L.value))
+            g = cls(names, lens)
+            n_exc = lib.tc_fasta_pack(h, g.chrom_off.ctypes.data, g.n_pad, g.bases2.ctypes.data, g.lower1.ctypes.data, nt)
+            if n_exc < 0:
+                raise ValueError("%s: the contig table does not fit the planes" % path)
+            st, en, by = np.zeros(n_exc, dtype=np.int64), np.zeros(n_exc, dtype=np.int64), np.zeros(n_exc, dtype=np.uint8)
+            if n_exc:
+                lib.tc_fasta_exceptions(h, st.ctypes.data, en.ctypes.data, by.ctypes.data)
+            g._exc = list(zip(st.tolist(), en.tolist(), by.tolist()))
+            return g
+        finally:
+            lib.tc_fasta_free(h)
+
     # ------------------------------------------------------------------ on-disk image
     def save(self, path, source=None):
         """The packed image as one .npz (what the device gets; 0.375 bytes per base).  `source` = fingerprint of the FASTA
@@ -161,14 +191,15 @@ class GenomeImage:
         return [int(st.st_size), int(st.st_mtime_ns), zlib.crc32(head), zlib.crc32(tail)]
 
     @classmethod
-    def from_fasta_cached(cls, path, cache=None):
+    def from_fasta_cached(cls, path, cache=None, lib=None):
         """from_fasta, keeping the packed image next to the FASTA (<fasta>.tcb200.npz, like pyfaidx keeps its .fai
-        there): packing a 3-Gb genome takes minutes, loading the image seconds.  The image is rebuilt unless it was made from
+        there): loading the image is faster still than packing the FASTA (with `lib`, the library's C++ packer; else numpy).  The image is rebuilt unless it was made from
         this very file (size, mtime and checksums of its first and last MB); a read-only directory just means no cache.
         TC_GENOME_CACHE=0 turns it off."""
         import os
+        build = (lambda: cls.from_fasta_lib(path, lib)) if lib is not None else (lambda: cls.from_fasta(path))
         if os.environ.get("TC_GENOME_CACHE", "1") == "0":
-            return cls.from_fasta(path)
+            return build()
         cache = cache or str(path) + ".tcb200.npz"
         fp = cls.fasta_fingerprint(path)
         try:
@@ -179,7 +210,7 @@ class GenomeImage:
                     return g
         except Exception:
             pass
-        g = cls.from_fasta(path)
+        g = build()
         try:
             tmp = cache + ".tmp%d" % os.getpid()
             g.save(tmp, source=fp)
