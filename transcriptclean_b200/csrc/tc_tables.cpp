@@ -264,17 +264,16 @@ template <class F> void run_tasks(size_t n, int T, F f) {
 extern "C" {
 
 tc_fasta* tc_fasta_open(const char* path, int32_t n_threads, char* err, int64_t err_cap) {
-    using namespace tc_tables_detail;
     const int T = n_threads < 1 ? 1 : n_threads;
     tc_fasta* F = new tc_fasta();
     const int fd = open(path, O_RDONLY);
-    if (fd < 0) { set_err(err, err_cap, std::string("cannot open ") + path); delete F; return nullptr; }
+    if (fd < 0) { tc_tables_detail::set_err(err, err_cap, std::string("cannot open ") + path); delete F; return nullptr; }
     struct stat st;
-    if (fstat(fd, &st) != 0) { close(fd); set_err(err, err_cap, std::string("cannot stat ") + path); delete F; return nullptr; }
+    if (fstat(fd, &st) != 0) { close(fd); tc_tables_detail::set_err(err, err_cap, std::string("cannot stat ") + path); delete F; return nullptr; }
     F->len = (int64_t)st.st_size;
     if (F->len > 0) {
         void* m = mmap(nullptr, (size_t)F->len, PROT_READ, MAP_PRIVATE, fd, 0);
-        if (m == MAP_FAILED) { close(fd); set_err(err, err_cap, std::string("cannot map ") + path); delete F; return nullptr; }
+        if (m == MAP_FAILED) { close(fd); tc_tables_detail::set_err(err, err_cap, std::string("cannot map ") + path); delete F; return nullptr; }
         F->data = (const char*)m; F->mapped = true;
     }
     close(fd);
@@ -289,9 +288,9 @@ tc_fasta* tc_fasta_open(const char* path, int32_t n_threads, char* err, int64_t 
         const int64_t nl = nlp ? nlp - D : n;
         int64_t end = n;
         if (nl < n) { const char* nx = (const char*)memmem(D + nl, (size_t)(n - nl), "\n>", 2); if (nx) end = (nx - D) + 1; }
-        int64_t a = h + 1; while (a < nl && ws(D[a])) a++;
-        int64_t b = a; while (b < nl && !ws(D[b])) b++;
-        if (b == a) { set_err(err, err_cap, "FASTA header without a name"); delete F; return nullptr; }
+        int64_t a = h + 1; while (a < nl && tc_tables_detail::ws(D[a])) a++;
+        int64_t b = a; while (b < nl && !tc_tables_detail::ws(D[b])) b++;
+        if (b == a) { tc_tables_detail::set_err(err, err_cap, "FASTA header without a name"); delete F; return nullptr; }
         tc_fasta::Rec r; r.name_s = a; r.name_n = (int32_t)(b - a); r.body_s = nl < n ? nl + 1 : n; r.body_e = end; r.length = 0;
         if (r.body_e < r.body_s) r.body_e = r.body_s;
         F->recs.push_back(r);
@@ -303,7 +302,7 @@ tc_fasta* tc_fasta_open(const char* path, int32_t n_threads, char* err, int64_t 
         for (int64_t a = F->recs[k].body_s; a < F->recs[k].body_e; a += piece)
             F->tasks.push_back({(int32_t)k, a, std::min(a + piece, F->recs[k].body_e), 0});
     std::vector<int64_t> cnt(F->tasks.size(), 0);
-    run_tasks(F->tasks.size(), T, [&](size_t k) {
+    tc_tables_detail::run_tasks(F->tasks.size(), T, [&](size_t k) {
         const tc_fasta::Task& t = F->tasks[k]; int64_t le = 0;
         for (int64_t j = t.a; j < t.b; j++) le += (D[j] == '\n') | (D[j] == '\r');
         cnt[k] = (t.b - t.a) - le;
@@ -322,7 +321,6 @@ int tc_fasta_contig(const tc_fasta* f, int32_t k, const char** name, int32_t* na
 }
 // planes must be zero; chrom_off[k] = plane index of contig k's first base.  Returns the number of literal runs (kept inside; tc_fasta_exceptions).
 int64_t tc_fasta_pack(tc_fasta* F, const int64_t* chrom_off, int64_t n_pad, uint32_t* bases2, uint32_t* lower1, int32_t n_threads) {
-    using namespace tc_tables_detail;
     if (!F || !chrom_off || !bases2 || !lower1) return -1;
     for (size_t k = 0; k < F->recs.size(); k++) if (chrom_off[k] < 0 || chrom_off[k] + F->recs[k].length > n_pad) return -1;
     uint8_t code[256], kind[256];                                       // kind: 0 ACGT, 1 acgt, 2 line end, 3 literal
@@ -333,7 +331,7 @@ int64_t tc_fasta_pack(tc_fasta* F, const int64_t* chrom_off, int64_t n_pad, uint
     struct Run { int64_t s, e; uint8_t b; };
     std::vector<std::vector<Run>> runs(F->tasks.size());
     const char* D = F->data;
-    run_tasks(F->tasks.size(), n_threads < 1 ? 1 : n_threads, [&](size_t ti) {
+    tc_tables_detail::run_tasks(F->tasks.size(), n_threads < 1 ? 1 : n_threads, [&](size_t ti) {
         const tc_fasta::Task& t = F->tasks[ti];
         int64_t p = chrom_off[t.rec] + t.base0;                            // plane index of the next base
         const int64_t p_first = p;
