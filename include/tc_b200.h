@@ -293,6 +293,8 @@ void tc_vcf_tables(const tc_vcf* v, int64_t* n_snp, const uint64_t** snp_key, co
                    const uint64_t** ins_key, const int32_t** ins_size, const int64_t** ins_aoff, const uint8_t** ins_bytes,
                    int64_t* n_del, const uint64_t** del_key, const int32_t** del_size);
 int64_t tc_vcf_n_records(const tc_vcf* v);
+/* distinct CHROM values of a VCF text, each followed by a NUL (validate_chroms, TranscriptClean.py:497-505); tc_free */
+char* tc_vcf_chroms(const char* text, int64_t len, int64_t* out_len);
 void tc_vcf_free(tc_vcf* v);
 typedef struct tc_sj tc_sj;
 tc_sj* tc_sj_parse(const char* text, int64_t len, int32_t n_chrom, const char* const* chrom_names, const uint8_t* use,

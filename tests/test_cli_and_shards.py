@@ -206,3 +206,23 @@ def test_sam_blocks_are_slices_of_a_mapping_and_cover_the_file():
     assert [len(b) for b in cli.sam_blocks(d + "/long.sam", 1000)] == [5001, 11]
     open(d + "/empty.sam", "wb").close()
     assert list(cli.sam_blocks(d + "/empty.sam", 1000)) == []
+
+
+def test_vcf_chromosomes_from_the_library_equal_the_python_scan():
+    import gzip
+    case, d = _case_files(41)
+    lib = HostSimEngine()._lib
+    rows = open(d + "/v.vcf").read()
+    extra = "##meta\n#CHROM\tPOS\n\n   \nchrQ\t5\t.\tA\tT\nchrQ\t9\t.\tA\tT\nnotab\nchr1\t7\t.\tC\tG\nlast_without_newline"
+    open(d + "/w.vcf", "w").write(rows + extra)
+    with gzip.open(d + "/w.vcf.gz", "wt") as f:
+        f.write(rows + extra)
+    for path in (d + "/w.vcf", d + "/w.vcf.gz"):
+        got, want = cli.vcf_chrom_set(path, lib), cli.vcf_chrom_set(path)
+        assert got == want and {"chrQ", "chr1", "notab\n", "last_without_newline"} <= got
+    genome = type("G", (), {"keys": lambda self: ["chr1", "chr2", "chr3", "chrQ"]})()
+    cli.validate_chroms(genome, d + "/w.vcf", {"chr1"}, lib=lib)
+    with pytest.raises(RuntimeError, match="None of the chromosomes included in the VCF file"):
+        cli.validate_chroms(genome, d + "/w.vcf.gz", {"chr3"}, lib=lib)
+    with pytest.raises(RuntimeError, match="Problem reading the provided VCF file"):
+        cli.validate_chroms(genome, d + "/missing.vcf", {"chr1"}, lib=lib)

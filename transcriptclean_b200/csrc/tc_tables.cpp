@@ -263,6 +263,28 @@ template <class F> void run_tasks(size_t n, int T, F f) {
 
 extern "C" {
 
+// distinct first columns of the record lines of a VCF text (what validate_chroms collects, TranscriptClean.py:497-505: every line
+// that is not blank and does not start with '#', cut at its first tab), each followed by a NUL, in a malloc'ed buffer (tc_free)
+char* tc_vcf_chroms(const char* text, int64_t len, int64_t* out_len) {
+    std::vector<std::string> seen; std::string last; bool have_last = false;
+    tc_tables_detail::each_line(text, 0, len, [&](const char* p, int64_t n) {
+        if (n > 0 && p[0] == '#') return;
+        int64_t a = 0; while (a < n && tc_tables_detail::ws(p[a])) a++;
+        if (a == n) return;                                             // blank
+        const char* tp = (const char*)memchr(p, '\t', (size_t)n);
+        const int64_t k = tp ? tp - p : (p + n < text + len ? n + 1 : n);   // (no tab: Python's split keeps the line end in the name)
+        if (have_last && (int64_t)last.size() == k && memcmp(last.data(), p, (size_t)k) == 0) return;
+        last.assign(p, (size_t)k); have_last = true;
+        if (std::find(seen.begin(), seen.end(), last) == seen.end()) seen.push_back(last);
+    });
+    size_t total = 0; for (auto& x : seen) total += x.size() + 1;
+    char* out = (char*)malloc(total + 1);
+    if (!out) return nullptr;
+    size_t o = 0; for (auto& x : seen) { memcpy(out + o, x.data(), x.size()); o += x.size(); out[o++] = 0; }
+    out[o] = 0; *out_len = (int64_t)o;
+    return out;
+}
+
 tc_fasta* tc_fasta_open(const char* path, int32_t n_threads, char* err, int64_t err_cap) {
     const int T = n_threads < 1 ? 1 : n_threads;
     tc_fasta* F = new tc_fasta();

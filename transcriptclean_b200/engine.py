@@ -14,7 +14,7 @@ EXPORTS = ["tc_device_count", "tc_ctx_create", "tc_ctx_destroy", "tc_last_error"
            "tc_ctx_set_pipeline", "tc_sam_parse", "tc_sam_free", "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_render", "tc_sam_render_parts",
            "tc_sam_rnames", "tc_free", "tc_ctx_set_alphabet", "tc_seq_pack", "tc_seq_packed_size", "tc_seq_pack2", "tc_seq_packed2_size", "tc_cig_pack16", "tc_sam_pack_seq", "tc_sam_header_lines",
            "tc_vcf_parse", "tc_vcf_tables", "tc_vcf_n_records", "tc_vcf_free", "tc_sj_parse", "tc_sj_tables", "tc_sj_free", "tc_intron_motifs",
-           "tc_fasta_open", "tc_fasta_n_contigs", "tc_fasta_contig", "tc_fasta_pack", "tc_fasta_exceptions", "tc_fasta_free"]
+           "tc_vcf_chroms", "tc_fasta_open", "tc_fasta_n_contigs", "tc_fasta_contig", "tc_fasta_pack", "tc_fasta_exceptions", "tc_fasta_free"]
 
 # status bits (include/tc_b200.h)
 ST_CLASS_MASK, ST_FALLBACK, ST_CIGAR_REWRITTEN = 3, 1 << 2, 1 << 3
@@ -136,6 +136,8 @@ def _declare(lib):
     lib.tc_sj_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 11
     lib.tc_sj_free.restype = None
     lib.tc_sj_free.argtypes = [C.c_void_p]
+    lib.tc_vcf_chroms.restype = C.c_void_p
+    lib.tc_vcf_chroms.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]
     lib.tc_fasta_open.restype = C.c_void_p
     lib.tc_fasta_open.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int64]
     lib.tc_fasta_n_contigs.restype = C.c_int32
@@ -148,7 +150,7 @@ def _declare(lib):
     lib.tc_fasta_free.argtypes = [C.c_void_p]
     lib.tc_fasta_free.restype = None
     for f in EXPORTS:
-        if f not in ("tc_fasta_open", "tc_fasta_n_contigs", "tc_fasta_pack", "tc_fasta_exceptions", "tc_fasta_free", "tc_vcf_parse", "tc_vcf_tables", "tc_vcf_n_records", "tc_vcf_free", "tc_sj_parse", "tc_sj_tables", "tc_sj_free", "tc_device_count", "tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_stream", "tc_sam_parse", "tc_sam_free",
+        if f not in ("tc_vcf_chroms", "tc_fasta_open", "tc_fasta_n_contigs", "tc_fasta_pack", "tc_fasta_exceptions", "tc_fasta_free", "tc_vcf_parse", "tc_vcf_tables", "tc_vcf_n_records", "tc_vcf_free", "tc_sj_parse", "tc_sj_tables", "tc_sj_free", "tc_device_count", "tc_ctx_create", "tc_ctx_destroy", "tc_last_error", "tc_ctx_stream", "tc_sam_parse", "tc_sam_free",
                      "tc_sam_n_reads", "tc_sam_header", "tc_sam_batch", "tc_sam_rnames", "tc_free", "tc_seq_pack", "tc_seq_packed_size", "tc_seq_pack2", "tc_seq_packed2_size", "tc_cig_pack16", "tc_sam_header_lines"):
             getattr(lib, f).restype = C.c_int
 
