@@ -16,12 +16,14 @@ rank corrects its own shard of the same shape (weak scaling, no data-path collec
             (traffic: DRAM bytes of that kernel from the committed ncu --set full capture)
   dry_run   the --dryRun inventory (tc_dryrun_batch) of the same batch, device-resident and end to end
   sam_text_path  SAM text in -> the four output texts (C++ host parse / render around the GPU), N=1 only
+  seam_batch_correct  the reference's own seam as a maintainer calls it: api.batch_correct(list of line strings, ..., outfiles), N=1 only
   cpu_baseline  the oracle port of the reference (oracle/tc_oracle.py) on a bounded sample, one core
   --impl reference  the same port on all host cores (the reference arm; the reference is pure Python
                     and cannot travel to the GPU box)
   --shape ont       BASELINE.json configs[3] shape;  --resident-only  profiling aid (see profiles/README.md)
 """
 import argparse
+import contextlib
 import ctypes as C
 import json
 import os
@@ -446,7 +448,8 @@ def main():
         from transcriptclean_b200 import api
         from transcriptclean_b200.cli import split_text
         ns = min(args.text_sample, args.reads)
-        text = ("\n".join(w.sam_lines(cols, nm, 0, ns)) + "\n").encode()
+        sam_lines = w.sam_lines(cols, nm, 0, ns)
+        text = ("\n".join(sam_lines) + "\n").encode()
         n_workers = max(1, args.text_workers)
         sj_tab = build_sj_tables(sj_path, {w.chrom}, gi.index)
         refs_list = [api.make_refs(gi, sj_tab, None, engine=eng)] + [api.make_refs(gi, sj_tab, None, device=local) for _ in range(n_workers - 1)]
@@ -466,6 +469,25 @@ def main():
         api.correct_sam_stream(blocks, api.Struct(), refs_list, sink)
         t1 = time.perf_counter()
         devnull.close()
+        # the reference's own seam, as a maintainer would call it (option A): a list of SAM line strings in,
+        # four open text files written - api.batch_correct on one context (str join / encode / decode included)
+        import io
+        import tempfile
+        seam_n = min(100000, ns)
+        seam_lines = sam_lines[:seam_n]
+        seam_s = 1e30
+        with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
+            for _ in range(2):
+                outs = api.Struct(sam=open(td + "/c.sam", "w"), fasta=open(td + "/c.fa", "w"), log=open(td + "/c.log", "w"), TElog=open(td + "/c.TE.log", "w"))
+                ts0 = time.perf_counter()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    api.batch_correct(seam_lines, api.Struct(), refs_list[0], outs)
+                for fo in outs.values():
+                    fo.close()
+                seam_s = min(seam_s, time.perf_counter() - ts0)
+        line["seam_batch_correct"] = {"value": seam_n / seam_s, "unit": "reads/s",
+                                      "sample": "api.batch_correct(list of %d SAM line strings, options, refs, outfiles) on one engine context, "
+                                                "the four text files written and closed, best of 2" % seam_n}
         for r in refs_list[1:]:
             r.engine.close()
         line["sam_text_path"] = {"value": ns / (t1 - t0), "unit": "reads/s", "in_bytes": len(text),

@@ -216,15 +216,45 @@ def correct_sam_stream(blocks, options, refs_list, sink, dry=False, n_threads=No
     return state["next"]
 
 
+def _seam_texts(sam_transcripts, options, refs, dry=False):
+    """The four texts for a list of SAM lines - what the reference's seam functions are handed.  Lists of any size go through the
+    library's C++ parser / renderer (the lines are joined into one text: the fast path of the command line); a handful of lines,
+    or TC_PY_TEXT=1, through the Python twins sam.py / render.py.  Same texts either way (tests/test_host_fast_path.py)."""
+    import os
+    lines = sam_transcripts if isinstance(sam_transcripts, list) else list(sam_transcripts)
+    if len(lines) < 16 or os.environ.get("TC_PY_TEXT") == "1" or not hasattr(refs.engine, "parse_sam"):
+        return dry_run_text(lines, refs) if dry else correct_batch_text(lines, options, refs)
+    text = "\n".join(lines) + "\n"                       # (lines that end in a newline leave blank lines, which the parser skips)
+    _, out = correct_sam_text(text.encode(), options if options is not None else Struct(), refs, dry=dry)
+    return out                                           # bytes: _write_text hands them to the files without a str round trip
+
+
+def _write_text(f, data):
+    """Writes a text (str, or bytes in the file's own encoding) to an open text file.  Bytes go straight to the binary file
+    under a text-mode file object (after a flush of what the caller wrote before) - decoding several GB to str only for the
+    file object to encode them again is most of the seam's time."""
+    import os
+    if isinstance(data, str):
+        f.write(data)
+        return
+    raw = getattr(f, "buffer", None)
+    enc = str(getattr(f, "encoding", "") or "").lower().replace("-", "").replace("_", "")
+    if raw is not None and os.linesep == "\n" and enc in ("utf8", "ascii", "latin1", "iso88591", "ansix3.41968", "usascii", "646"):
+        f.flush()
+        raw.write(data)
+    else:
+        f.write(bytes(data).decode())
+
+
 def batch_correct(sam_transcripts, options, refs, outfiles, buffer_size=100):
     """TC.py:350-403.  `buffer_size` only staggers disk writes in the reference; the whole list
     is one device batch here."""
     print("Correcting transcripts...")
-    out = correct_batch_text(sam_transcripts, options, refs)
-    outfiles.sam.write(out["sam"])
-    outfiles.fasta.write(out["fa"])
-    outfiles.log.write(out["log"])
-    outfiles.TElog.write(out["te"])
+    out = _seam_texts(sam_transcripts, options, refs)
+    _write_text(outfiles.sam, out["sam"])
+    _write_text(outfiles.fasta, out["fa"])
+    _write_text(outfiles.log, out["log"])
+    _write_text(outfiles.TElog, out["te"])
 
 
 def correct_transcript(transcript_line, options, refs):
@@ -264,6 +294,6 @@ def dryRun(sam_lines, options, outfiles, refs=None, device=0):
     print("Dry run mode: Identifying indels and mismatches.........")
     if refs is None:
         refs = make_refs(GenomeImage.from_fasta(_opt(options, "refGenome")), device=device)
-    out = dry_run_text(sam_lines, refs)
-    outfiles.log.write(out["log"])
-    outfiles.TElog.write(out["te"])
+    out = _seam_texts(sam_lines, options, refs, dry=True)
+    _write_text(outfiles.log, out["log"])
+    _write_text(outfiles.TElog, out["te"])
