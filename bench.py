@@ -11,15 +11,17 @@ rank corrects its own shard of the same shape (weak scaling, no data-path collec
 
   value  device-resident throughput: inputs already in HBM, tc_batch_run() only
   e2e    through the C ABI with pinned host buffers: tc_correct_batch() = H2D + kernels + D2H, pipelined in chunks;
-         the SEQ column travels as 4-bit codes (--seq8: ASCII)
+         the SEQ column travels as 2-bit codes + the listed bases outside ACGT (--seq4: 4-bit codes, --seq8: ASCII),
+         the CIGAR as 16-bit words + the listed long ops (--cig40: op + length arrays)
   roofline  the dominant kernel's algorithmic bytes / its CUDA-event time vs measured HBM peak
-            (traffic: DRAM bytes of that kernel from the committed ncu --set full capture)
+            (traffic: DRAM bytes of that kernel from the committed ncu --set full capture); roofline_step: the whole step
+            against SURVEY.md 8(d)'s bytes per read
   dry_run   the --dryRun inventory (tc_dryrun_batch) of the same batch, device-resident and end to end
   sam_text_path  SAM text in -> the four output texts (C++ host parse / render around the GPU), N=1 only
   seam_batch_correct  the reference's own seam as a maintainer calls it: api.batch_correct(list of line strings, ..., outfiles), N=1 only
   cpu_baseline  the oracle port of the reference (oracle/tc_oracle.py) on a bounded sample, one core
-  --impl reference  the same port on all host cores (the reference arm; the reference is pure Python
-                    and cannot travel to the GPU box)
+  --impl reference  the unmodified reference (pip-installed into oracle/_ref by build(), run under oracle/stubs) on all host
+                    cores; the oracle port where that install is missing
   --shape ont       BASELINE.json configs[3] shape;  --resident-only  profiling aid (see profiles/README.md)
 """
 import argparse
