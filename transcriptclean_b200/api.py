@@ -72,8 +72,12 @@ def prep_refs(options, transcripts, sam_header=None, device=0, engine=None, geno
     variant catalogues.  No temp files are written."""
     if genome is None:
         print("Reading genome ..............................")
-        genome = GenomeImage.from_fasta(_opt(options, "refGenome"))
-    chroms = set(t.split("\t")[2] for t in transcripts)
+        try:
+            lib = engine._lib if engine is not None else E.load_library()
+        except Exception:
+            lib = None
+        genome = GenomeImage.from_fasta_cached(_opt(options, "refGenome"), lib=lib)      # packed by the library, cached next to the FASTA
+    chroms = set(t.split("\t", 3)[2] for t in transcripts)
     sj, var = build_tables(options, chroms, genome)
     return make_refs(genome, sj, var, device=device, engine=engine)
 
@@ -293,7 +297,7 @@ def dryRun(sam_lines, options, outfiles, refs=None, device=0):
     """TC.py:1615-1678."""
     print("Dry run mode: Identifying indels and mismatches.........")
     if refs is None:
-        refs = make_refs(GenomeImage.from_fasta(_opt(options, "refGenome")), device=device)
+        refs = make_refs(GenomeImage.from_fasta_cached(_opt(options, "refGenome"), lib=E.load_library()), device=device)
     out = _seam_texts(sam_lines, options, refs, dry=True)
     _write_text(outfiles.log, out["log"])
     _write_text(outfiles.TElog, out["te"])
