@@ -220,17 +220,25 @@ def correct_sam_stream(blocks, options, refs_list, sink, dry=False, n_threads=No
     return state["next"]
 
 
-def _seam_texts(sam_transcripts, options, refs, dry=False):
-    """The four texts for a list of SAM lines - what the reference's seam functions are handed.  Lists of any size go through the
-    library's C++ parser / renderer (the lines are joined into one text: the fast path of the command line); a handful of lines,
-    or TC_PY_TEXT=1, through the Python twins sam.py / render.py.  Same texts either way (tests/test_host_fast_path.py)."""
+def _seam_write(sam_transcripts, options, refs, files, dry=False):
+    """Corrects a list of SAM lines - what the reference's seam functions are handed - and writes the texts to `files`
+    ({"sam","fa","log","te"} -> open text file; missing keys are skipped).  Lists of any size go through the library's C++
+    parser / renderer (the lines are joined into one text: the fast path of the command line) and its buffers are written without
+    a copy; a handful of lines, or TC_PY_TEXT=1, go through the Python twins sam.py / render.py.  Same texts either way
+    (tests/test_host_fast_path.py)."""
     import os
     lines = sam_transcripts if isinstance(sam_transcripts, list) else list(sam_transcripts)
     if len(lines) < 16 or os.environ.get("TC_PY_TEXT") == "1" or not hasattr(refs.engine, "parse_sam"):
-        return dry_run_text(lines, refs) if dry else correct_batch_text(lines, options, refs)
+        out = dry_run_text(lines, refs) if dry else correct_batch_text(lines, options, refs)
+        for k, f in files.items():
+            f.write(out[k])
+        return
     text = "\n".join(lines) + "\n"                       # (lines that end in a newline leave blank lines, which the parser skips)
-    _, out = correct_sam_text(text.encode(), options if options is not None else Struct(), refs, dry=dry)
-    return out                                           # bytes: _write_text hands them to the files without a str round trip
+
+    def sink(_header, views):
+        for k, f in files.items():
+            _write_text(f, views[k])
+    correct_sam_text(text.encode(), options if options is not None else Struct(), refs, dry=dry, consume=sink)
 
 
 def _write_text(f, data):
@@ -254,11 +262,7 @@ def batch_correct(sam_transcripts, options, refs, outfiles, buffer_size=100):
     """TC.py:350-403.  `buffer_size` only staggers disk writes in the reference; the whole list
     is one device batch here."""
     print("Correcting transcripts...")
-    out = _seam_texts(sam_transcripts, options, refs)
-    _write_text(outfiles.sam, out["sam"])
-    _write_text(outfiles.fasta, out["fa"])
-    _write_text(outfiles.log, out["log"])
-    _write_text(outfiles.TElog, out["te"])
+    _seam_write(sam_transcripts, options, refs, {"sam": outfiles.sam, "fa": outfiles.fasta, "log": outfiles.log, "te": outfiles.TElog})
 
 
 def correct_transcript(transcript_line, options, refs):
@@ -298,6 +302,4 @@ def dryRun(sam_lines, options, outfiles, refs=None, device=0):
     print("Dry run mode: Identifying indels and mismatches.........")
     if refs is None:
         refs = make_refs(GenomeImage.from_fasta_cached(_opt(options, "refGenome"), lib=E.load_library()), device=device)
-    out = _seam_texts(sam_lines, options, refs, dry=True)
-    _write_text(outfiles.log, out["log"])
-    _write_text(outfiles.TElog, out["te"])
+    _seam_write(sam_lines, options, refs, {"log": outfiles.log, "te": outfiles.TElog}, dry=True)
